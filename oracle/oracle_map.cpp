@@ -1,0 +1,153 @@
+// oracle_map.cpp -- CPU restatement of the cube-grid local map and the LaserMapping frame loop
+// (TEST INFRASTRUCTURE, see cm_oracle.h).  Follows L_SLAM/src/util/FeatureMap.h:59-74,102-108,146-148,189-376,
+// 464-487, odometry/LaserMatcher.cpp:18-33,288-355, odometry/LaserMapping.cpp:39-59,
+// util/transform_utils.h:502-507,601-614, scan_to_scan_match/ScanMatch.cpp:349-360.
+#include "cm_oracle.h"
+#include <algorithm>
+#include <cmath>
+
+namespace cmo {
+
+FeatureMap::FeatureMap(const MapParams& p) : _p(p) {
+  int n = p.cubeW * p.cubeH * p.cubeD;
+  cornerCube.resize(n); surfCube.resize(n);
+  originW = (int)std::round((p.cubeW - 1) / 2.0);   // FeatureMap.h:63-65
+  originH = (int)std::round((p.cubeH - 1) / 2.0);
+  originD = (int)std::round((p.cubeD - 1) / 2.0);
+}
+bool FeatureMap::isIndexValid(int i, int j, int k) const {
+  return 0 <= i && i < _p.cubeW && 0 <= j && j < _p.cubeH && 0 <= k && k < _p.cubeD;
+}
+// FeatureMap.h:475-487
+bool FeatureMap::worldToCube(float x, float y, float z, int& i, int& j, int& k) const {
+  i = (int)(std::round(x / _p.cubeSize) + originW);
+  j = (int)(std::round(y / _p.cubeSize) + originH);
+  k = (int)(std::round(z / _p.cubeSize) + originD);
+  return isIndexValid(i, j, k);
+}
+// FeatureMap.h:354-376 (literal, including the in-place swap order)
+void FeatureMap::shift(int di, int dj, int dk) {
+  if (di != 0 || dj != 0 || dk != 0) {
+    for (int i = 0; i < _p.cubeW; i++)
+      for (int j = 0; j < _p.cubeH; j++)
+        for (int k = 0; k < _p.cubeD; k++) {
+          int oi = i - di, oj = j - dj, ok = k - dk;
+          if (isIndexValid(oi, oj, ok)) {
+            std::swap(cornerCube[toIndex(i, j, k)], cornerCube[toIndex(oi, oj, ok)]);
+            std::swap(surfCube[toIndex(i, j, k)], surfCube[toIndex(oi, oj, ok)]);
+          } else {
+            cornerCube[toIndex(i, j, k)].clear();
+            surfCube[toIndex(i, j, k)].clear();
+          }
+        }
+  }
+}
+// FeatureMap.h:308-352
+void FeatureMap::computeActiveArea(const float s[3]) {
+  _cubeValidInd.clear();
+  int window = (int)std::ceil(_p.validDistance / _p.cubeSize);
+  for (int i = _curW - window; i <= _curW + window; i++)
+    for (int j = _curH - window; j <= _curH + window; j++)
+      for (int k = _curD - window; k <= _curD + window; k++) {
+        if (!isIndexValid(i, j, k)) continue;
+        float centerX = _p.cubeSize * (i - originW);
+        float centerY = _p.cubeSize * (j - originH);
+        float centerZ = _p.cubeSize * (k - originD);
+        bool inFov = false;
+        for (int ii = -1; ii <= 1 && !inFov; ii += 2)
+          for (int jj = -1; jj <= 1 && !inFov; jj += 2)
+            for (int kk = -1; kk <= 1 && !inFov; kk += 2) {
+              float cx = (float)(centerX + _p.cubeSize / 2.0 * ii);
+              float cy = (float)(centerY + _p.cubeSize / 2.0 * jj);
+              float cz = (float)(centerZ + _p.cubeSize / 2.0 * kk);
+              float dx = s[0] - cx, dy = s[1] - cy, dz = s[2] - cz;
+              float sq = dx * dx + dy * dy + dz * dz;
+              if (std::sqrt((double)sq) < _p.validDistance) inFov = true;
+            }
+        if (inFov) _cubeValidInd.push_back(toIndex(i, j, k));
+      }
+}
+// FeatureMap.h:232-254
+void FeatureMap::update(const float s[3]) {
+  int gi, gj, gk;
+  worldToCube(s[0], s[1], s[2], gi, gj, gk);
+  const int PAD = 3;
+  int ni = std::min(std::max(gi, PAD), _p.cubeW - PAD - 1);
+  int nj = std::min(std::max(gj, PAD), _p.cubeH - PAD - 1);
+  int nk = std::min(std::max(gk, PAD), _p.cubeD - PAD - 1);
+  shift(ni - gi, nj - gj, nk - gk);
+  originW += ni - gi; originH += nj - gj; originD += nk - gk;
+  _curW = ni; _curH = nj; _curD = nk;
+  computeActiveArea(s);
+}
+void FeatureMap::getSurroundFeature(std::vector<PointI>& corner, std::vector<PointI>& surf) const {
+  corner.clear(); surf.clear();
+  for (size_t v : _cubeValidInd) {
+    corner.insert(corner.end(), cornerCube[v].begin(), cornerCube[v].end());
+    surf.insert(surf.end(), surfCube[v].begin(), surfCube[v].end());
+  }
+}
+// FeatureMap.h:289-306
+void FeatureMap::downsizeValidCloud() {
+  std::vector<PointI> tmp;
+  for (size_t v : _cubeValidInd) {
+    voxel_filter(cornerCube[v].data(), cornerCube[v].size(), _p.mapFilterCorner, tmp);
+    cornerCube[v].swap(tmp);
+    voxel_filter(surfCube[v].data(), surfCube[v].size(), _p.mapFilterSurf, tmp);
+    surfCube[v].swap(tmp);
+  }
+}
+// FeatureMap.h:189-230 + transformPointCloud transform_utils.h:601-614
+void FeatureMap::addFeatureCloud(const std::vector<PointI>& corner, const std::vector<PointI>& surf, const Iso& tf) {
+  auto push = [&](const std::vector<PointI>& in, std::vector<std::vector<PointI>>& cubes) {
+    for (const PointI& p : in) {
+      PointI q = p;
+      q.x = ((tf.R[0] * p.x + tf.R[1] * p.y) + tf.R[2] * p.z) + tf.t[0];
+      q.y = ((tf.R[3] * p.x + tf.R[4] * p.y) + tf.R[5] * p.z) + tf.t[1];
+      q.z = ((tf.R[6] * p.x + tf.R[7] * p.y) + tf.R[8] * p.z) + tf.t[2];
+      int i, j, k;
+      if (worldToCube(q.x, q.y, q.z, i, j, k)) cubes[toIndex(i, j, k)].push_back(q);
+    }
+  };
+  push(corner, cornerCube);
+  push(surf, surfCube);
+  downsizeValidCloud();
+}
+size_t FeatureMap::totalPoints() const {
+  size_t n = 0;
+  for (auto& c : cornerCube) n += c.size();
+  for (auto& c : surfCube) n += c.size();
+  return n;
+}
+
+LaserMapping::LaserMapping(const MapParams& mp, const MatchParams& sp, const KnnBackend& knn)
+    : map(mp), _mp(mp), _sp(sp), _knn(knn) {
+  mappedLast = mappedNew = odomLast = iso_identity();   // LaserMatcher.cpp:31-32
+}
+
+// LaserMapping.cpp:39-59 (hasNewData / publishResult are ROS plumbing and are not restated)
+Iso LaserMapping::process(const Iso& odomNew, const std::vector<PointI>& corner, const std::vector<PointI>& surf) {
+  // transformMerge, LaserMatcher.cpp:333-340 -> transformAssociate transform_utils.h:502-507
+  Iso L2W = iso_mul(mappedLast, iso_inverse(odomLast));
+  mappedNew = iso_mul(L2W, odomNew);
+  // prepareFeatureFrame, LaserMatcher.cpp:288-301
+  voxel_filter(corner.data(), corner.size(), _mp.filterCorner, cornerDS);
+  voxel_filter(surf.data(), surf.size(), _mp.filterSurf, surfDS);
+  // prepareFeatureSurround, LaserMatcher.cpp:303-325
+  map.update(mappedNew.t);
+  map.getSurroundFeature(surroundCorner, surroundSurf);
+  // optimizeTransform, LaserMatcher.cpp:327-331 -> ScanMatch.cpp:349-360
+  float pose[6];
+  iso_to_twist(mappedNew, pose);
+  scan_match(_sp, _knn, surroundCorner.data(), surroundCorner.size(), surroundSurf.data(), surroundSurf.size(),
+             cornerDS.data(), cornerDS.size(), surfDS.data(), surfDS.size(), pose, lastMatch, keepLog);
+  twist_to_iso(pose, mappedNew);
+  // transformUpdate, LaserMatcher.cpp:342-347
+  mappedLast = mappedNew;
+  odomLast = odomNew;
+  // featureMapUpdate, LaserMatcher.cpp:349-355
+  map.addFeatureCloud(cornerDS, surfDS, mappedNew);
+  return mappedNew;
+}
+
+}  // namespace cmo
