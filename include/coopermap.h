@@ -1,0 +1,122 @@
+/* coopermap.h -- C ABI of the B200-native LOAM hot path (scan registration + scan-to-map registration).
+ *
+ * Drop-in boundary for ZhekaiJin/the-Cooper-Mapper (L_SLAM).  Every entry point names the reference interface it
+ * replaces (file:line relative to the reference tree).  Plain pointers and sizes only; clouds are arrays of
+ * cm_point = the x, y, z, intensity payload of pcl::PointXYZI (16 bytes, not PCL's 32-byte padded struct; see
+ * INTEGRATION.md for the one-line repack a nodelet does).  All *_host entry points take HOST buffers and copy
+ * inside the call; the *_dev entry points take device pointers (inputs already resident in HBM).
+ *
+ * Status codes: 0 = ok; > 0 = soft outcome of the algorithm (the reference prints a warning and carries on);
+ * < 0 = hard error (cm_last_error() has the text).  No exceptions cross this boundary.  A context is NOT
+ * thread-safe: one context <-> one CUDA stream <-> one host thread (the reference drives each stage from one
+ * worker thread, LaserMapping.cpp:21,27-37).  There is no CPU fallback: without a CUDA device cm_ctx_create fails.
+ */
+#ifndef COOPERMAP_H
+#define COOPERMAP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_OK 0
+#define CM_TOO_FEW_REF 1        /* "reference cloud points too few."  ScanMatch.cpp:57-61 */
+#define CM_TOO_FEW_MATCHES 2    /* "matched cloud points too few."    ScanMatch.cpp:141-145 */
+#define CM_NOT_CONVERGED 3      /* iteration cap hit, pose still written back  ScanMatch.cpp:342-346 */
+#define CM_LOW_SCORE 4          /* ScanMatch.cpp:323-335 (useScore) */
+#define CM_ERR_ARG (-1)
+#define CM_ERR_CUDA (-2)
+#define CM_ERR_CAPACITY (-3)
+#define CM_ERR_UNSUPPORTED (-4)
+
+typedef struct cm_ctx cm_ctx;
+
+typedef struct cm_point { float x, y, z, intensity; } cm_point;      /* pcl::PointXYZI payload */
+typedef struct cm_pose { float rx, ry, rz, tx, ty, tz; } cm_pose;    /* lidar_slam::Twist, Twist.h:14-20 (R = Rz Ry Rx) */
+typedef struct cm_iso { float R[9]; float t[3]; } cm_iso;            /* Eigen::Isometry3f: row-major rotation + translation */
+
+/* Parameters.  Defaults (cm_config_default) are the reference's: RegistrationParams (ScanRegistration.cpp:32-49),
+ * ScanMatch as configured by LaserMatcher (LaserMatcher.cpp:80-118, ScanMatch.cpp:21-33), FeatureMap (FeatureMap.h:59-70). */
+typedef struct cm_config {
+  int device;                         /* CUDA ordinal */
+  /* scan registration */
+  float scan_period;                  /* 0.1 */
+  int n_feature_regions;              /* 6 */
+  int curvature_region;               /* 5 */
+  int max_corner_sharp;               /* 2 */
+  int max_surface_flat;               /* 4 */
+  float less_flat_filter_size;        /* 0.2 */
+  float surface_curvature_threshold;  /* 0.02 */
+  float blind_degree_threshold;       /* 0.5 */
+  float blind_radius;                 /* 2.5  OrganizedScanRegistration.cpp:29 */
+  /* scan-to-map solver */
+  int max_iterations;                 /* 10   ScanMatch.h:36 */
+  float delta_t_abort, delta_r_abort; /* 0.1, 0.1  LaserMatcher.cpp:94 */
+  int use_score;                      /* 0    LaserMatcher.cpp:95 */
+  double score_threshold;             /* 800  ScanMatch.cpp:24 */
+  float match_percentage_threshold;   /* 0.4 */
+  /* mapping stage */
+  float filter_corner, filter_surf;          /* 1.0, 1.0  LaserMatcher.cpp:80-85 */
+  float map_filter_corner, map_filter_surf;  /* 1.0, 1.0  LaserMatcher.cpp:87-92 */
+  int cube_w, cube_h, cube_d;                /* 121, 121, 11  LaserMatcher.cpp:107-113 */
+  float cube_size, valid_distance;           /* 50, 150  FeatureMap.h:65-66 */
+  /* search grid (implementation parameters; results do not depend on them) */
+  float cell_corner, cell_surf;       /* edge of the hash cells; <= 0: 6 x / 3 x the matching map leaf */
+} cm_config;
+
+typedef struct cm_match_stats {
+  int status;        /* CM_OK (converged), CM_TOO_FEW_REF, CM_TOO_FEW_MATCHES, CM_NOT_CONVERGED, CM_LOW_SCORE */
+  int ret;           /* the reference's bool return (always 0 when use_score = 0, quirk: ScanMatch.cpp:263,342-346) */
+  int converged, degenerate;
+  int iterations;    /* pose updates applied */
+  int rows, line_matches, plane_matches;   /* counters of the last evaluated iteration */
+  double score;
+} cm_match_stats;
+
+/* one Gauss-Newton iteration as the oracle logs it (tests / diagnostics) */
+typedef struct cm_iter_trace {
+  float pose_in[6];
+  float AtA[36], AtB[6], x[6];
+  int rows, line_matches, plane_matches, degenerate;
+} cm_iter_trace;
+
+void cm_config_default(cm_config* cfg);
+int cm_ctx_create(const cm_config* cfg, cm_ctx** out);
+void cm_ctx_destroy(cm_ctx* ctx);
+const char* cm_last_error(const cm_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long cm_launch_count(const cm_ctx* ctx);
+
+/* Exact 5 nearest neighbours of nq map-frame queries (xyz triples) in `map`, squared L2 in float, ordered by
+ * (d2, index).  Exact for neighbours within sqrt(gate) of the query (the reference rejects d2[4] >= 5.0 anyway);
+ * beyond that idx = -1 / d2 is a lower bound on the true 5th distance that is >= gate.
+ * Replaces nanoflann::KdTreeFLANN::setInputCloud + nearestKSearch, nanoflann_pcl.h:132-162 (call sites
+ * ScanMatch.cpp:75-76,100-101,119). */
+int cm_knn5_host(cm_ctx* ctx, const cm_point* map, size_t n_map, float cell, float gate, const float* queries_xyz,
+                 size_t nq, int* idx_out, float* d2_out);
+
+/* ScanMatch::scanMatchScan(refCorner, refSurf, corner, surf, Twist&), ScanMatch.h:51-55 / ScanMatch.cpp:51-347.
+ * pose is read as the initial guess and overwritten with the result (also when not converged, like the reference).
+ * trace (optional, cfg.max_iterations entries) and nn_corner / nn_surf (optional, max_iterations x n x 5 ints,
+ * -1 where the 5.0 gate rejected the query) expose every iteration for parity tests. */
+int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_corner, const cm_point* ref_surf,
+                            size_t n_ref_surf, const cm_point* corner, size_t n_corner, const cm_point* surf, size_t n_surf,
+                            cm_pose* pose, cm_match_stats* stats, cm_iter_trace* trace, int* nn_corner, int* nn_surf);
+
+/* ScanMatch::scanMatchScan(..., Eigen::Isometry3f&), ScanMatch.h:47-50 / ScanMatch.cpp:349-360: Isometry -> Twist
+ * (getEulerAngles, transform_utils.h:54-60) -> solve -> Twist -> Isometry. */
+int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_corner, const cm_point* ref_surf,
+                                size_t n_ref_surf, const cm_point* corner, size_t n_corner, const cm_point* surf,
+                                size_t n_surf, cm_iso* pose, cm_match_stats* stats);
+
+/* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
+ * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.
+ * op: 0 QR-solve 6x6 (42 -> 6 floats), 1 QR-solve 5x3 (20 -> 3), 2 eig 3x3 (6 -> 12), 3 eig 6x6 (36 -> 42),
+ * 4 eig 6x6 values (36 -> 6), 5 inverse 6x6 (36 -> 36), 6 pose -> R, sin, cos (6 -> 15). */
+int cm_debug_math_host(cm_ctx* ctx, int op, const float* in, size_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COOPERMAP_H */

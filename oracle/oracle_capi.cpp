@@ -56,6 +56,21 @@ int cmo_inverse6(const float* A, float* inv) { return cm::inverse_lu<6>(A, inv) 
 void cmo_pose_to_matrix(const float* pose, float* R) { cm::pose_to_matrix(pose, R); }
 void cmo_iso_to_twist(const float* R, const float* t, float* pose) { Iso i; std::memcpy(i.R, R, 36); std::memcpy(i.t, t, 12); iso_to_twist(i, pose); }
 
+// same op codes as cm_debug_math_host (include/coopermap.h): the shared header compiled for the HOST
+void cmo_debug_math(int op, const float* in, size_t n, float* out) {
+  static const int ni[7] = {42, 20, 6, 36, 36, 36, 6}, no[7] = {6, 3, 12, 42, 6, 36, 15};
+  for (size_t t = 0; t < n; t++) {
+    const float* a = in + t * ni[op]; float* o = out + t * no[op];
+    if (op == 0) { float A[36], b[6]; std::memcpy(A, a, 144); std::memcpy(b, a + 36, 24); cm::colpiv_qr_solve<6, 6>(A, b, o); }
+    else if (op == 1) { float A[15], b[5]; std::memcpy(A, a, 60); std::memcpy(b, a + 15, 20); cm::colpiv_qr_solve<5, 3>(A, b, o); }
+    else if (op == 2) cm::eig3_sym(a, o, o + 3);
+    else if (op == 3) cm::eig_sym<6>(a, o, o + 6);
+    else if (op == 4) cm::eig_sym<6>(a, o, (float*)nullptr);
+    else if (op == 5) { float inv[36]; bool ok = cm::inverse_lu<6>(a, inv); for (int i = 0; i < 36; i++) o[i] = ok ? inv[i] : 0.f; }
+    else if (op == 6) { cm::pose_to_matrix(a, o); for (int i = 0; i < 3; i++) cm::cm_sincosf(a[i], o + 9 + i, o + 12 + i); }
+  }
+}
+
 // ---- scan registration ------------------------------------------------------------------------------------------
 struct ScanRegHandle { ScanRegResult r; };
 static ScanRegParams make_prm(const float* f, const int* iv) {

@@ -2,7 +2,10 @@
 // cm_oracle.h).  Follows L_SLAM/src/scan_to_scan_match/ScanMatch.cpp:51-347, util/feature_utils.h:17-26,63-75,
 // 97-204, util/transform_utils.h:288-331,476-482, util/Angle.h:17-29, util/Twist.h.
 // Canonical choices where the reference's arithmetic is compiler/library defined (documented in DESIGN.md):
-//  * AtA / AtB (Eigen dynamic GEMM, ScanMatch.cpp:206-208) are accumulated row by row, in row order.
+//  * AtA / AtB (Eigen dynamic float GEMM, ScanMatch.cpp:206-208; its blocked/vectorised summation order is
+//    unknowable) are defined as the CORRECTLY ROUNDED float product: float products are exact in double, they
+//    are accumulated in double and rounded to float once.  Any summation order gives the same float (up to
+//    ~1e-13 relative before rounding), which is what lets the GPU's tree reduction match bit for bit.
 //  * the 5 neighbours of a query are ordered by (d2, index) (nanoflann orders ties by traversal).
 //  * unqualified fabs()/sqrt() in feature_utils.h resolve to the C double overloads.
 #include "cm_oracle.h"
@@ -194,8 +197,9 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
       break;
     }
     float AtA[36], AtB[6], matX[6];
-    for (int t = 0; t < 36; t++) AtA[t] = 0.f;
-    for (int t = 0; t < 6; t++) AtB[t] = 0.f;
+    double AtAd[36], AtBd[6];
+    for (int t = 0; t < 36; t++) AtAd[t] = 0.0;
+    for (int t = 0; t < 6; t++) AtBd[t] = 0.0;
     for (size_t i = 0; i < laserCloudSelNum; i++) {
       const PointI& pointOri = laserCloudOri[i];
       const PointI& coeff = coeffSel[i];
@@ -212,10 +216,12 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
       float row[6] = {arx, ary, arz, coeff.x, coeff.y, coeff.z};
       float b = -coeff.intensity;
       for (int r = 0; r < 6; r++) {
-        for (int c = 0; c < 6; c++) AtA[r * 6 + c] += row[r] * row[c];
-        AtB[r] += row[r] * b;
+        for (int c = 0; c < 6; c++) AtAd[r * 6 + c] += (double)row[r] * (double)row[c];
+        AtBd[r] += (double)row[r] * (double)b;
       }
     }
+    for (int t = 0; t < 36; t++) AtA[t] = (float)AtAd[t];
+    for (int t = 0; t < 6; t++) AtB[t] = (float)AtBd[t];
     {
       float Aw[36], bw[6];
       std::memcpy(Aw, AtA, sizeof(Aw)); std::memcpy(bw, AtB, sizeof(bw));

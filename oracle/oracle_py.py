@@ -103,6 +103,18 @@ def iso_to_twist(R, t):
     return pose
 
 
+MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15)}
+
+
+def debug_math(op, inputs):
+    """Batch form of the hooks above, same op codes as cm_debug_math_host."""
+    nin, nout = MATH_DIMS[op]
+    a = _f32(inputs).reshape(-1, nin)
+    out = np.empty((len(a), nout), np.float32)
+    lib().cmo_debug_math(C.c_int(op), _p(a), C.c_size_t(len(a)), _p(out))
+    return out
+
+
 # ---- scan registration ------------------------------------------------------------------------------------
 _SR_FIELDS = [("cloud", np.float32, 5), ("scanStart", np.int32, 1), ("scanEnd", np.int32, 1), ("sharp", np.float32, 4),
               ("lessSharp", np.float32, 4), ("flat", np.float32, 4), ("lessFlat", np.float32, 4),

@@ -1,0 +1,39 @@
+"""The shared small-matrix header (csrc/cm_math.h) must mean the same thing on the GPU and on the host, bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(op, n, rng):
+    if op in (0, 3, 4):
+        B = rng.normal(size=(n, 12, 6)).astype(np.float32) * np.array([1, 1, 1, 30, 30, 30], np.float32)
+        B[::7, :, 0] *= 1e-3                      # near-degenerate direction
+        A = np.einsum("nkr,nkc->nrc", B, B).astype(np.float32).reshape(n, 36)
+        if op == 0:
+            return np.concatenate([A, rng.normal(size=(n, 6)).astype(np.float32) * 10], 1)
+        return A
+    if op == 1:
+        nrm = rng.normal(size=(n, 3)); nrm[:, 2] += 2.0
+        xy = rng.uniform(-20, 20, (n, 5, 2))
+        z = (3.0 - nrm[:, None, 0] * xy[..., 0] - nrm[:, None, 1] * xy[..., 1]) / nrm[:, None, 2] + rng.normal(0, 0.05, (n, 5))
+        A = np.concatenate([xy, z[..., None]], -1).astype(np.float32).reshape(n, 15)
+        return np.concatenate([A, -np.ones((n, 5), np.float32)], 1)
+    if op == 2:
+        B = rng.normal(size=(n, 6, 3)).astype(np.float32) * rng.choice([1e-2, 1.0, 5.0], (n, 1, 1)).astype(np.float32)
+        B[::5, :, 1] = 2 * B[::5, :, 0] + 1e-4 * B[::5, :, 1]     # near rank-1 (a line)
+        C = np.einsum("nkr,nkc->nrc", B, B).astype(np.float32)
+        return np.stack([C[:, 0, 0], C[:, 1, 0], C[:, 2, 0], C[:, 1, 1], C[:, 2, 1], C[:, 2, 2]], 1)
+    if op == 5:
+        return (rng.normal(size=(n, 36)) + 2 * np.eye(6).ravel()).astype(np.float32)
+    if op == 6:
+        return (rng.uniform(-1, 1, (n, 6)) * np.array([3.2, 1.6, 3.2, 100, 100, 100])).astype(np.float32)
+    raise ValueError(op)
+
+
+@pytest.mark.parametrize("op", range(7))
+def test_math_device_equals_host(ctx, oracle, op):
+    x = _inputs(op, 4096, np.random.default_rng(100 + op))
+    dev = ctx.debug_math(op, x)
+    host = oracle.debug_math(op, x)
+    assert np.array_equal(dev.view(np.uint32), host.view(np.uint32))

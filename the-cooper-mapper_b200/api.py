@@ -1,0 +1,214 @@
+"""ctypes binding of include/coopermap.h and host-side mirrors of the reference's operator classes.
+
+Mirrors (same names, argument meaning and error behaviour as the reference):
+  ScanMatch.scanMatchScan   <- lidar_slam::ScanMatch::scanMatchScan   (ScanMatch.h:47-55)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+CM_OK, CM_TOO_FEW_REF, CM_TOO_FEW_MATCHES, CM_NOT_CONVERGED, CM_LOW_SCORE = 0, 1, 2, 3, 4
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class CoopermapError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libcoopermap.so")
+
+
+class Config(C.Structure):
+    """cm_config (include/coopermap.h)."""
+    _fields_ = [("device", C.c_int), ("scan_period", C.c_float), ("n_feature_regions", C.c_int),
+                ("curvature_region", C.c_int), ("max_corner_sharp", C.c_int), ("max_surface_flat", C.c_int),
+                ("less_flat_filter_size", C.c_float), ("surface_curvature_threshold", C.c_float),
+                ("blind_degree_threshold", C.c_float), ("blind_radius", C.c_float), ("max_iterations", C.c_int),
+                ("delta_t_abort", C.c_float), ("delta_r_abort", C.c_float), ("use_score", C.c_int),
+                ("score_threshold", C.c_double), ("match_percentage_threshold", C.c_float),
+                ("filter_corner", C.c_float), ("filter_surf", C.c_float), ("map_filter_corner", C.c_float),
+                ("map_filter_surf", C.c_float), ("cube_w", C.c_int), ("cube_h", C.c_int), ("cube_d", C.c_int),
+                ("cube_size", C.c_float), ("valid_distance", C.c_float), ("cell_corner", C.c_float),
+                ("cell_surf", C.c_float)]
+
+
+class MatchStats(C.Structure):
+    _fields_ = [("status", C.c_int), ("ret", C.c_int), ("converged", C.c_int), ("degenerate", C.c_int),
+                ("iterations", C.c_int), ("rows", C.c_int), ("line_matches", C.c_int), ("plane_matches", C.c_int),
+                ("score", C.c_double)]
+
+
+class IterTrace(C.Structure):
+    _fields_ = [("pose_in", C.c_float * 6), ("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("x", C.c_float * 6),
+                ("rows", C.c_int), ("line_matches", C.c_int), ("plane_matches", C.c_int), ("degenerate", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libcoopermap.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise CoopermapError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)" % p)
+    L = C.CDLL(p)
+    L.cm_last_error.restype = C.c_char_p
+    L.cm_launch_count.restype = C.c_ulonglong
+    _lib = L
+    return L
+
+
+def _f32(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """cm_ctx: one context <-> one CUDA stream <-> one host thread."""
+
+    def __init__(self, **kw):
+        L = load_library()
+        self.L = L
+        self.cfg = Config()
+        L.cm_config_default(C.byref(self.cfg))
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise CoopermapError("unknown config field %s" % k)
+            setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        rc = L.cm_ctx_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise CoopermapError("cm_ctx_create failed (%d): no usable CUDA device; there is no CPU fallback" % rc)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cm_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise CoopermapError("coopermap error %d: %s" % (rc, self.L.cm_last_error(self.h).decode()))
+        return rc
+
+    def launch_count(self):
+        return int(self.L.cm_launch_count(self.h))
+
+    # ---- device self-test of the shared math ------------------------------------------------------------------
+    MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15)}
+
+    def debug_math(self, op, inputs):
+        nin, nout = self.MATH_DIMS[op]
+        a = _f32(inputs, nin)
+        out = np.empty((len(a), nout), np.float32)
+        self._check(self.L.cm_debug_math_host(self.h, C.c_int(op), _ptr(a), C.c_size_t(len(a)), _ptr(out)))
+        return out
+
+    # ---- exact 5-NN ---------------------------------------------------------------------------------------
+    def knn5(self, map_pts, queries, cell=1.2, gate=5.0):
+        m = _f32(map_pts, 4); q = _f32(queries, 3)
+        idx = np.empty((len(q), 5), np.int32); d2 = np.empty((len(q), 5), np.float32)
+        self._check(self.L.cm_knn5_host(self.h, _ptr(m), C.c_size_t(len(m)), C.c_float(cell), C.c_float(gate), _ptr(q),
+                                        C.c_size_t(len(q)), _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    # ---- stateless scan-to-map --------------------------------------------------------------------------------
+    def match_stateless(self, ref_corner, ref_surf, corner, surf, pose, trace=False):
+        rc_ = _f32(ref_corner, 4); rs = _f32(ref_surf, 4); c = _f32(corner, 4); s = _f32(surf, 4)
+        p = _f32(pose).copy()
+        st = MatchStats()
+        iters = self.cfg.max_iterations
+        tr = (IterTrace * iters)() if trace else None
+        nnc = np.empty((iters, len(c), 5), np.int32) if trace else None
+        nns = np.empty((iters, len(s), 5), np.int32) if trace else None
+        rc = self._check(self.L.cm_match_stateless_host(
+            self.h, _ptr(rc_), C.c_size_t(len(rc_)), _ptr(rs), C.c_size_t(len(rs)), _ptr(c), C.c_size_t(len(c)), _ptr(s),
+            C.c_size_t(len(s)), _ptr(p), C.byref(st), tr, _ptr(nnc), _ptr(nns)))
+        stats = dict(status=rc, ret=bool(st.ret), converged=bool(st.converged), degenerate=bool(st.degenerate),
+                     iterations=st.iterations, rows=st.rows, line=st.line_matches, plane=st.plane_matches, score=st.score)
+        log = []
+        if trace:
+            n_eval = st.iterations + (1 if rc == CM_TOO_FEW_MATCHES else 0)
+            for it in range(n_eval):
+                t = tr[it]
+                log.append(dict(pose_in=np.array(t.pose_in[:], np.float32), AtA=np.array(t.AtA[:], np.float32).reshape(6, 6),
+                                AtB=np.array(t.AtB[:], np.float32), x=np.array(t.x[:], np.float32),
+                                counts=np.array([t.rows, t.line_matches, t.plane_matches, t.degenerate], np.int32),
+                                nnCorner=nnc[it], nnSurf=nns[it]))
+        return p, stats, log
+
+    def match_stateless_iso(self, ref_corner, ref_surf, corner, surf, R, t):
+        rc_ = _f32(ref_corner, 4); rs = _f32(ref_surf, 4); c = _f32(corner, 4); s = _f32(surf, 4)
+        iso = np.concatenate([_f32(R).ravel(), _f32(t).ravel()]).astype(np.float32)
+        st = MatchStats()
+        rc = self._check(self.L.cm_match_stateless_iso_host(
+            self.h, _ptr(rc_), C.c_size_t(len(rc_)), _ptr(rs), C.c_size_t(len(rs)), _ptr(c), C.c_size_t(len(c)), _ptr(s),
+            C.c_size_t(len(s)), _ptr(iso), C.byref(st)))
+        return iso[:9].reshape(3, 3).copy(), iso[9:].copy(), rc, st
+
+
+class ScanMatch:
+    """Mirror of lidar_slam::ScanMatch (ScanMatch.h:22-86): the scan-to-map Gauss-Newton operator.
+
+    scanMatchScan(referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform) -> (bool, transform)
+    `transform` is a Twist (rx, ry, rz, tx, ty, tz); it is written back even when the call returns False, exactly
+    like the reference (ScanMatch.cpp:342-346).
+    """
+
+    def __init__(self, maxIterations=10, ctx=None, **cfg):
+        cfg.setdefault("delta_t_abort", 0.05)   # class defaults, ScanMatch.cpp:22
+        cfg.setdefault("delta_r_abort", 0.05)
+        cfg.setdefault("use_score", 1)          # ScanMatch.cpp:23
+        cfg["max_iterations"] = int(maxIterations)
+        self.ctx = ctx or Context(**cfg)
+        self._match_count = 0
+        self._fail_match_count = 0
+        self._total_score = 0.0
+        self.last_stats = None
+
+    def setConvergeThreshold(self, deltaTAbort, deltaRAbort):   # ScanMatch.h:29-32
+        self._rebuild(delta_t_abort=deltaTAbort, delta_r_abort=deltaRAbort)
+
+    def setUseCore(self, useScore):   # ScanMatch.h:34 (sic)
+        self._rebuild(use_score=int(bool(useScore)))
+
+    def setScoreThreshold(self, score):   # ScanMatch.h:25
+        self._rebuild(score_threshold=float(score))
+
+    def _rebuild(self, **kw):
+        vals = {f[0]: getattr(self.ctx.cfg, f[0]) for f in Config._fields_}
+        vals.update(kw)
+        self.ctx.close()
+        self.ctx = Context(**vals)
+
+    def scanMatchScan(self, referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform):
+        pose, stats, _ = self.ctx.match_stateless(referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform)
+        self.last_stats = stats
+        if stats["ret"]:
+            self._match_count += 1
+            self._total_score += stats["score"]
+        elif stats["status"] != CM_TOO_FEW_REF:
+            self._fail_match_count += 1
+        return bool(stats["ret"]), pose
+
+    def getAverageScore(self):   # ScanMatch.h:59-61
+        return self._total_score / self._match_count if self._match_count > 0 else 0.0

@@ -1,0 +1,259 @@
+// cm_capi.cu -- the extern "C" boundary declared in include/coopermap.h.
+#include "../../include/coopermap.h"
+#include "cm_host.h"
+#include "cm_math.h"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace cm {
+unsigned long long g_launch_count = 0;
+}
+
+using namespace cm;
+
+struct cm_ctx {
+  cm_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // scratch for the host-buffer entry points
+  DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
+  DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
+  GridStorage grid_a, grid_b;
+};
+
+static MatchParamsDev dev_params(const cm_config& c) {
+  MatchParamsDev p;
+  p.max_iterations = c.max_iterations;
+  p.delta_t_abort = c.delta_t_abort; p.delta_r_abort = c.delta_r_abort;
+  p.knn_gate = 5.0f; p.plane_max_dist = 0.2f;
+  p.min_ref_corner = 50; p.min_ref_surf = 100; p.min_rows = 50; p.eig_threshold = 100.f;
+  return p;
+}
+
+static int fail(cm_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define CM_CUDA_CHECK(ctx, expr)                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(ctx, CM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" {
+
+void cm_config_default(cm_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->device = 0;
+  c->scan_period = 0.1f; c->n_feature_regions = 6; c->curvature_region = 5; c->max_corner_sharp = 2; c->max_surface_flat = 4;
+  c->less_flat_filter_size = 0.2f; c->surface_curvature_threshold = 0.02f; c->blind_degree_threshold = 0.5f; c->blind_radius = 2.5f;
+  c->max_iterations = 10; c->delta_t_abort = 0.1f; c->delta_r_abort = 0.1f; c->use_score = 0; c->score_threshold = 800.0;
+  c->match_percentage_threshold = 0.4f;
+  c->filter_corner = 1.0f; c->filter_surf = 1.0f; c->map_filter_corner = 1.0f; c->map_filter_surf = 1.0f;
+  c->cube_w = 121; c->cube_h = 121; c->cube_d = 11; c->cube_size = 50.f; c->valid_distance = 150.f;
+  c->cell_corner = 0.f; c->cell_surf = 0.f;
+}
+
+int cm_ctx_create(const cm_config* cfg, cm_ctx** out) {
+  if (!cfg || !out) return CM_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    fprintf(stderr, "coopermap: no usable CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(e));
+    return CM_ERR_CUDA;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return CM_ERR_CUDA;
+  cm_ctx* ctx = new cm_ctx();
+  ctx->cfg = *cfg;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CM_ERR_CUDA; }
+  *out = ctx;
+  return CM_OK;
+}
+
+void cm_ctx_destroy(cm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  delete ctx;
+}
+
+const char* cm_last_error(const cm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+unsigned long long cm_launch_count(const cm_ctx*) { return cm::g_launch_count; }
+
+static float cell_or_default(float cell, float leaf, float mult) { return cell > 0.f ? cell : mult * leaf; }
+
+int cm_knn5_host(cm_ctx* ctx, const cm_point* map, size_t n_map, float cell, float gate, const float* q, size_t nq,
+                 int* idx_out, float* d2_out) {
+  if (!ctx || (!map && n_map) || (!q && nq) || !idx_out || !d2_out || !(gate > 0.f)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (nq == 0) return CM_OK;
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    if (!(cell > 0.f)) cell = 1.2f;
+    ctx->d_ref_surf.reserve((n_map ? n_map : 1) * sizeof(cm_point));
+    ctx->d_q.reserve(nq * 3 * sizeof(float));
+    ctx->d_idx.reserve(nq * 5 * sizeof(int));
+    ctx->d_d2.reserve(nq * 5 * sizeof(float));
+    if (n_map) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, map, n_map * sizeof(cm_point), cudaMemcpyHostToDevice, ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_q.p, q, nq * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->grid_a.build((const float4*)ctx->d_ref_surf.p, (int)n_map, cell, gate, 0, ctx->stream);
+    launch_knn5(ctx->grid_a.view, (const float*)ctx->d_q.p, (int)nq, (int*)ctx->d_idx.p, (float*)ctx->d_d2.p, ctx->stream);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(idx_out, ctx->d_idx.p, nq * 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(d2_out, ctx->d_d2.p, nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+static void fill_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out) {
+  out->converged = (st.flags & CM_F_CONVERGED) ? 1 : 0;
+  out->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
+  out->iterations = st.iterations;
+  out->rows = st.rows; out->line_matches = st.line; out->plane_matches = st.plane;
+  out->score = st.score;
+  out->ret = 0;
+  if (st.flags & CM_F_TOO_FEW_REF) out->status = CM_TOO_FEW_REF;
+  else if (st.flags & CM_F_TOO_FEW_MATCHES) out->status = CM_TOO_FEW_MATCHES;
+  else if (!(st.flags & CM_F_CONVERGED)) out->status = CM_NOT_CONVERGED;
+  else {
+    out->status = CM_OK;
+    if (cfg.use_score) {   // ScanMatch.cpp:263-341
+      double match_count = (double)(st.line + st.plane);
+      float percent = (float)(match_count / (double)nq);
+      if (st.score < cfg.score_threshold || (double)percent < (double)cfg.match_percentage_threshold) out->status = CM_LOW_SCORE;
+      else out->ret = 1;
+    }
+  }
+}
+
+int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, const cm_point* ref_surf, size_t nrs,
+                            const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, cm_pose* pose,
+                            cm_match_stats* stats, cm_iter_trace* trace, int* nn_corner, int* nn_surf) {
+  if (!ctx || !pose || (!ref_corner && nrc) || (!ref_surf && nrs) || (!corner && nc) || (!surf && ns))
+    return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const cm_config& cfg = ctx->cfg;
+    MatchParamsDev prm = dev_params(cfg);
+    cudaStream_t st = ctx->stream;
+    const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
+    ctx->d_ref_corner.reserve((nrc ? nrc : 1) * sizeof(cm_point));
+    ctx->d_ref_surf.reserve((nrs ? nrs : 1) * sizeof(cm_point));
+    ctx->d_corner.reserve(capC * sizeof(cm_point));
+    ctx->d_surf.reserve(capS * sizeof(cm_point));
+    ctx->d_counts.reserve(2 * sizeof(int));
+    ctx->d_views.reserve(2 * sizeof(GridView));
+    ctx->d_pose.reserve(6 * sizeof(float));
+    ctx->d_state.reserve(sizeof(MatchState));
+    ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
+    ctx->d_sums.reserve(32 * sizeof(double));
+    const bool want_nn = nn_corner || nn_surf;
+    if (trace) ctx->d_trace.reserve(sizeof(IterTrace) * prm.max_iterations);
+    if (want_nn) ctx->d_nn.reserve((size_t)prm.max_iterations * capQ * 5 * sizeof(int));
+    if (nrc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_corner.p, ref_corner, nrc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (nrs) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, ref_surf, nrs * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    int counts[2] = {(int)nc, (int)ns};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, pose, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nrc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 6.f), prm.knn_gate, 0, st);
+    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)nrs, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 3.f), prm.knn_gate, 0, st);
+    GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
+    if (trace) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, sizeof(IterTrace) * prm.max_iterations, st));
+    if (want_nn) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_nn.p, 0xFF, (size_t)prm.max_iterations * capQ * 5 * sizeof(int), st));
+    MatchLaunch m;
+    m.nstreams = 1;
+    m.corner = (const float4*)ctx->d_corner.p; m.surf = (const float4*)ctx->d_surf.p;
+    m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
+    m.cap_corner = capC; m.cap_surf = capS;
+    m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
+    m.pose_in = (const float*)ctx->d_pose.p;
+    m.state = (MatchState*)ctx->d_state.p;
+    m.rows = (RowOut*)ctx->d_rows.p;
+    m.sums = (double*)ctx->d_sums.p;
+    m.trace = trace ? (IterTrace*)ctx->d_trace.p : nullptr;
+    m.nn = want_nn ? (int*)ctx->d_nn.p : nullptr;
+    m.orig_idx = 1;
+    m.prm = prm;
+    launch_match(m, st);
+    MatchState hs;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    std::vector<int> hnn;
+    if (want_nn) {
+      hnn.resize((size_t)prm.max_iterations * capQ * 5);
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hnn.data(), ctx->d_nn.p, hnn.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    if (trace) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(trace, ctx->d_trace.p, sizeof(IterTrace) * prm.max_iterations, cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    if (want_nn) {
+      for (int it = 0; it < prm.max_iterations; it++) {
+        const int* src = hnn.data() + (size_t)it * capQ * 5;
+        if (nn_corner && nc) memcpy(nn_corner + (size_t)it * nc * 5, src, nc * 5 * sizeof(int));
+        if (nn_surf && ns) memcpy(nn_surf + (size_t)it * ns * 5, src + nc * 5, ns * 5 * sizeof(int));
+      }
+    }
+    pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2];
+    pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
+    cm_match_stats local;
+    fill_stats(cfg, hs, nc + ns, &local);
+    if (stats) *stats = local;
+    return local.status;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+// host-side Isometry <-> Twist, transform_utils.h:54-60, 288-299, 308-331
+static void iso_to_twist_host(const cm_iso* it, cm_pose* p) {
+  p->tx = it->t[0]; p->ty = it->t[1]; p->tz = it->t[2];
+  p->rx = atan2f(it->R[7], it->R[8]);
+  p->ry = asinf(-it->R[6]);
+  p->rz = atan2f(it->R[3], it->R[0]);
+}
+static void twist_to_iso_host(const cm_pose* p, cm_iso* it) {
+  float pose[6] = {p->rx, p->ry, p->rz, p->tx, p->ty, p->tz};
+  pose_to_matrix(pose, it->R);
+  it->t[0] = p->tx; it->t[1] = p->ty; it->t[2] = p->tz;
+}
+
+int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, const cm_point* ref_surf, size_t nrs,
+                                const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, cm_iso* pose,
+                                cm_match_stats* stats) {
+  if (!pose) return fail(ctx, CM_ERR_ARG, "bad argument");
+  cm_pose tw;
+  iso_to_twist_host(pose, &tw);
+  int rc = cm_match_stateless_host(ctx, ref_corner, nrc, ref_surf, nrs, corner, nc, surf, ns, &tw, stats, nullptr, nullptr, nullptr);
+  if (rc < 0) return rc;
+  twist_to_iso_host(&tw, pose);
+  return rc;
+}
+
+int cm_debug_math_host(cm_ctx* ctx, int op, const float* in, size_t n, float* out) {
+  int nin, nout;
+  if (!ctx || !in || !out || debug_math_dims(op, &nin, &nout) != 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (n == 0) return CM_OK;
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    ctx->d_q.reserve(n * nin * sizeof(float));
+    ctx->d_d2.reserve(n * nout * sizeof(float));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_q.p, in, n * nin * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    launch_debug_math(op, (const float*)ctx->d_q.p, nin, (float*)ctx->d_d2.p, nout, (int)n, ctx->stream);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_d2.p, n * nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// cm_debug.cu -- device-side self-test hook: runs the shared small-matrix routines of cm_math.h ON THE GPU so a test
+// can compare them bit for bit with the same header compiled for the host inside the oracle (tests/test_math_gpu.py).  This guards
+// the assumption every parity claim rests on: cm_math.h means the same thing on both sides (it once did not --
+// see the note in colpiv_qr_solve).
+#include "cm_host.h"
+#include "cm_math.h"
+
+namespace cm {
+
+// op 0: colpiv_qr_solve<6,6> (36 + 6 -> 6)   1: colpiv_qr_solve<5,3> (15 + 5 -> 3)   2: eig3_sym (6 -> 3 + 9)
+// op 3: eig_sym<6> (36 -> 6 + 36)   4: eig_sym<6> values only (36 -> 6)   5: inverse_lu<6> (36 -> 36)
+// op 6: pose_to_matrix + cm_sincosf (6 -> 9 + 3 + 3)
+__device__ void debug_math_op(int op, const float* in, float* out) {
+  if (op == 0) { float A[36], b[6], x[6]; for (int i = 0; i < 36; i++) A[i] = in[i]; for (int i = 0; i < 6; i++) b[i] = in[36 + i]; colpiv_qr_solve<6, 6>(A, b, x); for (int i = 0; i < 6; i++) out[i] = x[i]; }
+  else if (op == 1) { float A[15], b[5], x[3]; for (int i = 0; i < 15; i++) A[i] = in[i]; for (int i = 0; i < 5; i++) b[i] = in[15 + i]; colpiv_qr_solve<5, 3>(A, b, x); for (int i = 0; i < 3; i++) out[i] = x[i]; }
+  else if (op == 2) { float w[3], V[9]; eig3_sym(in, w, V); for (int i = 0; i < 3; i++) out[i] = w[i]; for (int i = 0; i < 9; i++) out[3 + i] = V[i]; }
+  else if (op == 3) { float w[6], V[36]; eig_sym<6>(in, w, V); for (int i = 0; i < 6; i++) out[i] = w[i]; for (int i = 0; i < 36; i++) out[6 + i] = V[i]; }
+  else if (op == 4) { float w[6]; eig_sym<6>(in, w, (float*)nullptr); for (int i = 0; i < 6; i++) out[i] = w[i]; }
+  else if (op == 5) { float inv[36]; bool ok = inverse_lu<6>(in, inv); for (int i = 0; i < 36; i++) out[i] = ok ? inv[i] : 0.f; }
+  else if (op == 6) { float R[9]; pose_to_matrix(in, R); for (int i = 0; i < 9; i++) out[i] = R[i]; for (int i = 0; i < 3; i++) cm_sincosf(in[i], &out[9 + i], &out[12 + i]); }
+}
+__global__ void debug_math_kernel(int op, const float* in, int nin, float* out, int nout, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) debug_math_op(op, in + (size_t)i * nin, out + (size_t)i * nout);
+}
+int debug_math_dims(int op, int* nin, int* nout) {
+  static const int ni[7] = {42, 20, 6, 36, 36, 36, 6}, no[7] = {6, 3, 12, 42, 6, 36, 15};
+  if (op < 0 || op > 6) return -1;
+  *nin = ni[op]; *nout = no[op];
+  return 0;
+}
+void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream) {
+  CM_LAUNCH(debug_math_kernel, (n + 63) / 64, 64, 0, stream, op, d_in, nin, d_out, nout, n);
+}
+
+}  // namespace cm

@@ -1,0 +1,134 @@
+// cm_device.cuh -- device-side building blocks: the voxel-cell hash ("grid") that replaces the reference's
+// KD-tree, and the exact 5-nearest-neighbour search over it.
+//
+// Replaces nanoflann::KdTreeFLANN::setInputCloud / nearestKSearch (nanoflann_pcl.h:132-162, core
+// nanoflann.hpp:931-1030,1433-1497) as used by ScanMatch.cpp:68-76,100-101,119.  Exactness argument: the
+// reference discards a query whose 5th neighbour has d2 >= 5.0 (ScanMatch.cpp:102,120), so the search radius is
+// bounded; cells are visited in growing cubic shells around the query and the search stops as soon as the 5th
+// best distance is provably smaller than the distance to any unvisited cell.  Distances are accumulated exactly
+// like L2_Simple_Adaptor::evalMetric (nanoflann.hpp:364-372): ((0 + dx*dx) + dy*dy) + dz*dz in float, unfused.
+// Ties are broken by (d2, index) -- the canonical order of the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace cm {
+
+#define CM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+// One hash slot: packed cell coordinates -> [start, start + count) in the point pool.  16 bytes, one LDG.128.
+struct __align__(16) CellEntry {
+  unsigned long long key;
+  unsigned int start;
+  unsigned int count;
+};
+
+// Read-only view of one grid (one map cloud of one stream).
+struct GridView {
+  const CellEntry* entries;   // open addressing, linear probing, capacity = mask + 1 (power of two)
+  const float4* pts;          // x, y, z, w  (w = original index bits for stateless clouds, intensity for the map)
+  unsigned int mask;
+  float ox, oy, oz;           // lattice origin
+  float cell, inv_cell;       // cell edge and 1/edge (float, computed once on the host)
+  int npts;                   // number of points in the cloud (the reference gates on it, ScanMatch.cpp:57-58)
+  int max_level;              // last shell to visit so that (max_level + 0.48) * cell >= sqrt(gate)
+};
+
+__host__ __device__ __forceinline__ unsigned long long pack_cell(int x, int y, int z) {
+  const unsigned long long B = 1ull << 20;
+  return ((unsigned long long)(x + (long long)B) & 0x1FFFFF) | (((unsigned long long)(y + (long long)B) & 0x1FFFFF) << 21) |
+         (((unsigned long long)(z + (long long)B) & 0x1FFFFF) << 42);
+}
+__host__ __device__ __forceinline__ unsigned int hash_cell(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (unsigned int)k;
+}
+__device__ __forceinline__ int cell_coord(float p, float o, float inv) { return (int)floorf((p - o) * inv); }
+
+__device__ __forceinline__ bool grid_probe(const GridView& g, int x, int y, int z, unsigned int* start, unsigned int* count) {
+  unsigned long long key = pack_cell(x, y, z);
+  unsigned int h = hash_cell(key) & g.mask;
+  while (true) {
+    uint4 e = __ldg(reinterpret_cast<const uint4*>(g.entries + h));
+    unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    if (k == key) { *start = e.z; *count = e.w; return true; }
+    if (k == CM_EMPTY_KEY) return false;
+    h = (h + 1) & g.mask;
+  }
+}
+
+// Sorted 5-best list by (d2, idx).  slot = position in the point pool (to fetch the coordinates afterwards).
+struct Top5 {
+  float d[5];
+  int idx[5];
+  int slot[5];
+};
+__device__ __forceinline__ void top5_init(Top5& t) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) { t.d[k] = FLT_MAX; t.idx[k] = 0x7fffffff; t.slot[k] = -1; }
+}
+__device__ __forceinline__ bool lex_less(float d, int i, float d2, int i2) { return d < d2 || (d == d2 && i < i2); }
+__device__ __forceinline__ void top5_insert(Top5& t, float d, int idx, int slot) {
+  if (!lex_less(d, idx, t.d[4], t.idx[4])) return;
+  bool c0 = lex_less(d, idx, t.d[0], t.idx[0]);
+  bool c1 = lex_less(d, idx, t.d[1], t.idx[1]);
+  bool c2 = lex_less(d, idx, t.d[2], t.idx[2]);
+  bool c3 = lex_less(d, idx, t.d[3], t.idx[3]);
+  // new slot k = c_{k-1} ? old[k-1] : (c_k ? new : old[k])
+  t.d[4] = c3 ? t.d[3] : d;            t.idx[4] = c3 ? t.idx[3] : idx;            t.slot[4] = c3 ? t.slot[3] : slot;
+  t.d[3] = c2 ? t.d[2] : (c3 ? d : t.d[3]); t.idx[3] = c2 ? t.idx[2] : (c3 ? idx : t.idx[3]); t.slot[3] = c2 ? t.slot[2] : (c3 ? slot : t.slot[3]);
+  t.d[2] = c1 ? t.d[1] : (c2 ? d : t.d[2]); t.idx[2] = c1 ? t.idx[1] : (c2 ? idx : t.idx[2]); t.slot[2] = c1 ? t.slot[1] : (c2 ? slot : t.slot[2]);
+  t.d[1] = c0 ? t.d[0] : (c1 ? d : t.d[1]); t.idx[1] = c0 ? t.idx[0] : (c1 ? idx : t.idx[1]); t.slot[1] = c0 ? t.slot[0] : (c1 ? slot : t.slot[1]);
+  t.d[0] = c0 ? d : t.d[0];            t.idx[0] = c0 ? idx : t.idx[0];            t.slot[0] = c0 ? slot : t.slot[0];
+}
+
+// kOrigIdx: tie-break index = original cloud index stored in pts[].w (stateless clouds); otherwise the pool slot.
+template <bool kOrigIdx>
+__device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, Top5& best) {
+  unsigned int start, count;
+  if (!grid_probe(g, x, y, z, &start, &count)) return;
+  for (unsigned int j = start; j < start + count; j++) {
+    float4 p = __ldg(g.pts + j);
+    float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    top5_insert(best, d, kOrigIdx ? __float_as_int(p.w) : (int)j, (int)j);
+  }
+}
+
+// Exact 5-NN of (qx,qy,qz) among the grid's points, provided the 5th neighbour lies within
+// (max_level + 0.48) * cell; beyond that the returned 5th distance is only an upper bound (>= the bound).
+template <bool kOrigIdx>
+__device__ __forceinline__ void knn5_search(const GridView& g, float qx, float qy, float qz, Top5& best) {
+  top5_init(best);
+  float fx = (qx - g.ox) * g.inv_cell, fy = (qy - g.oy) * g.inv_cell, fz = (qz - g.oz) * g.inv_cell;
+  float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  // keep the cast defined for absurd coordinates
+  if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return;
+  int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+  // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
+  int lx = cx + ((fx - flx) < 0.5f ? -1 : 0), ly = cy + ((fy - fly) < 0.5f ? -1 : 0), lz = cz + ((fz - flz) < 0.5f ? -1 : 0);
+#pragma unroll
+  for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++) scan_cell<kOrigIdx>(g, lx + dx, ly + dy, lz + dz, qx, qy, qz, best);
+  for (int L = 1; L <= g.max_level; L++) {
+    float r = ((float)(L - 1) + 0.48f) * g.cell;   // radius guaranteed by the previous level
+    if (best.d[4] < r * r) return;
+    int n = 2 + 2 * L;
+    for (int dz = 0; dz < n; dz++)
+      for (int dy = 0; dy < n; dy++) {
+        bool shell_row = (dz == 0 || dz == n - 1 || dy == 0 || dy == n - 1);
+        if (shell_row) {
+          for (int dx = 0; dx < n; dx++) scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, best);
+        } else {
+          scan_cell<kOrigIdx>(g, lx - L, ly - L + dy, lz - L + dz, qx, qy, qz, best);
+          scan_cell<kOrigIdx>(g, lx - L + n - 1, ly - L + dy, lz - L + dz, qx, qy, qz, best);
+        }
+      }
+  }
+}
+
+}  // namespace cm

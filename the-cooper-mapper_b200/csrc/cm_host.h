@@ -1,0 +1,71 @@
+// cm_host.h -- host-side plumbing shared by the .cu translation units (device buffers, launch descriptors).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <string>
+#include "cm_match.cuh"
+
+namespace cm {
+
+struct CudaError { cudaError_t code; const char* what; };
+
+// Every kernel launch goes through CM_LAUNCH so that cm_launch_count() reports what actually ran.
+extern unsigned long long g_launch_count;
+#define CM_LAUNCH(kern, grid, block, smem, stream, ...)        \
+  do {                                                         \
+    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
+    ++cm::g_launch_count;                                      \
+  } while (0)
+
+// Grow-only device allocation.
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) throw CudaError{e, "cudaMalloc"};
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  ~DeviceBuffer() { release(); }
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+};
+
+// Storage behind one GridView built from a caller-supplied cloud (stateless matching / knn).
+struct GridStorage {
+  DeviceBuffer entries, pts, cell_of, cursor;
+  GridView view;
+  // keep_w = 0: pts[].w := original index (tie-break + reported neighbour index); 1: keep the input w
+  void build(const float4* d_pts, int n, float cell_size, float gate, int keep_w, cudaStream_t stream);
+};
+
+int grid_max_level(float cell, float gate);
+void launch_knn5(const GridView& g, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t stream);
+
+struct MatchLaunch {
+  int nstreams;
+  const float4* corner; const float4* surf;   // [nstreams][cap]
+  const int* n_corner; const int* n_surf;     // device, per stream
+  int cap_corner, cap_surf;
+  const GridView* grid_corner; const GridView* grid_surf;   // device arrays [nstreams]
+  const float* pose_in;                       // device [nstreams][6]
+  MatchState* state;                          // device [nstreams]
+  RowOut* rows;                               // device [nstreams][cap_corner + cap_surf]
+  double* sums;                               // device [nstreams][32] (A^T A / A^T b partial sums)
+  IterTrace* trace;                           // optional device [nstreams][max_iterations]
+  int* nn;                                    // optional device [max_iterations][nstreams][cap][5]
+  int orig_idx;                               // grids carry original indices in pts[].w
+  MatchParamsDev prm;
+};
+void launch_match(const MatchLaunch& m, cudaStream_t stream);
+
+int debug_math_dims(int op, int* nin, int* nout);
+void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream);
+
+}  // namespace cm

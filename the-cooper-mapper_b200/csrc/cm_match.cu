@@ -1,0 +1,480 @@
+// cm_match.cu -- scan-to-map registration kernels (K4 grid build, K5 fused correspondence, K6 reduce + solve).
+//
+// Replaces ScanMatch::scanMatchScan (L_SLAM/src/scan_to_scan_match/ScanMatch.cpp:51-347) and the helpers it
+// calls (util/feature_utils.h:17-26,63-75,97-204; util/transform_utils.h:288-311,476-482; util/Angle.h).
+// Compiled with -fmad=false: every float operation below is an IEEE operation in source order, which is what
+// makes rows, neighbour sets and poses bit-identical to the CPU oracle.
+#include "cm_match.cuh"
+#include "cm_math.h"
+#include "cm_host.h"
+
+namespace cm {
+
+// ============================================================================================================
+// K4: grid build for a stateless reference cloud (the reference rebuilds two KD-trees per call,
+// ScanMatch.cpp:75-76).  count -> offsets -> scatter; O(M), no sort.
+// ============================================================================================================
+__global__ void grid_clear_kernel(CellEntry* e, unsigned int cap) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { e[i].key = CM_EMPTY_KEY; e[i].start = 0; e[i].count = 0; }
+}
+
+__global__ void grid_count_kernel(const float4* __restrict__ pts, int n, CellEntry* entries, unsigned int mask, float ox,
+                                  float oy, float oz, float inv, int* __restrict__ cell_of) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { cell_of[i] = -1; return; }
+  float fx = floorf((p.x - ox) * inv), fy = floorf((p.y - oy) * inv), fz = floorf((p.z - oz) * inv);
+  if (!(fabsf(fx) < 1.0e6f && fabsf(fy) < 1.0e6f && fabsf(fz) < 1.0e6f)) { cell_of[i] = -1; return; }
+  unsigned long long key = pack_cell((int)fx, (int)fy, (int)fz);
+  unsigned int h = hash_cell(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&entries[h].key, CM_EMPTY_KEY, key);
+    if (prev == CM_EMPTY_KEY || prev == key) break;
+    h = (h + 1) & mask;
+  }
+  atomicAdd(&entries[h].count, 1u);
+  cell_of[i] = (int)h;
+}
+
+__global__ void grid_offsets_kernel(CellEntry* entries, unsigned int cap, unsigned int* cursor) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  unsigned int c = entries[i].count;
+  if (c) { entries[i].start = atomicAdd(cursor, c); entries[i].count = 0; }
+}
+
+__global__ void grid_scatter_kernel(const float4* __restrict__ pts, int n, CellEntry* entries, const int* __restrict__ cell_of,
+                                    float4* __restrict__ out, int keep_w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int h = cell_of[i];
+  if (h < 0) return;
+  float4 p = pts[i];
+  unsigned int j = atomicAdd(&entries[h].count, 1u);
+  if (!keep_w) p.w = __int_as_float(i);
+  out[entries[h].start + j] = p;
+}
+
+// ============================================================================================================
+// Pose bookkeeping (Twist + Angle caches + Isometry3f rotation)
+// ============================================================================================================
+__device__ void state_set_pose(MatchState& st, const float pose[6]) {
+  for (int k = 0; k < 6; k++) st.pose[k] = pose[k];
+  for (int k = 0; k < 3; k++) cm_sincosf(pose[k], &st.sn[k], &st.cs[k]);   // Angle(float), Angle.h:19-20
+  pose_to_matrix(pose, st.R);                                             // convertTransform, transform_utils.h:308-311
+}
+
+__global__ void match_init_kernel(MatchState* states, const float* __restrict__ poses, const GridView* gc, const GridView* gs,
+                                  MatchParamsDev prm, int nstreams) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams) return;
+  MatchState& st = states[s];
+  state_set_pose(st, poses + 6 * s);
+  for (int k = 0; k < 36; k++) st.P[k] = 0.f;
+  st.flags = 0; st.iterations = 0; st.rows = st.line = st.plane = 0; st.score = 0.0; st.done = 0;
+  if (gc[s].npts < prm.min_ref_corner || gs[s].npts < prm.min_ref_surf) { st.flags = CM_F_TOO_FEW_REF; st.done = 1; }   // ScanMatch.cpp:57-61
+}
+
+// ============================================================================================================
+// K5: fused correspondence.  One thread per query: transform -> exact 5-NN -> line / plane fit -> residual and
+// Jacobian row (ScanMatch.cpp:97-132 and :154-204 fused).
+// ============================================================================================================
+struct CorrArgs {
+  const float4* corner; const float4* surf;   // [nstreams][cap*]
+  const int* n_corner; const int* n_surf;     // per stream (device)
+  int cap_corner, cap_surf;
+  const GridView* grid_corner; const GridView* grid_surf;
+  const MatchState* state;
+  RowOut* rows;                               // [nstreams][cap_corner + cap_surf]
+  int* nn;                                    // optional [nstreams][cap_corner + cap_surf][5], -1 where gated out
+  MatchParamsDev prm;
+};
+
+struct PoseCoef {   // pose-only factors of the Jacobian text at ScanMatch.cpp:185-195, same association
+  float x1, x2, x3, x4, x5, x6;
+  float y1, y2, y3, y4, y5, y6, y7, y8, y9;
+  float z1, z3, z4, z5, z6, z7;
+};
+__device__ __forceinline__ void make_pose_coef(const MatchState& st, PoseCoef& k) {
+  float srx = st.sn[0], crx = st.cs[0], sry = st.sn[1], cry = st.cs[1], srz = st.sn[2], crz = st.cs[2];
+  k.x1 = crz * sry * crx + srz * srx;  k.x2 = srz * crx - crz * sry * srx;
+  k.x3 = srz * sry * crx - crz * srx;  k.x4 = srz * sry * srx + crz * crx;
+  k.x5 = cry * crx;                    k.x6 = cry * srx;
+  k.y1 = -crz * sry;  k.y2 = crz * cry * srx;  k.y3 = crz * cry * crx;
+  k.y4 = -srz * sry;  k.y5 = srz * cry * srx;  k.y6 = srz * cry * crx;
+  k.y7 = -cry;        k.y8 = sry * srx;        k.y9 = sry * crx;
+  k.z1 = -srz * cry;  k.z3 = crz * srx - srz * sry * crx;
+  k.z4 = crz * cry;   k.z5 = crz * sry * srx - srz * crx;  k.z6 = crz * sry * crx;  k.z7 = srz * srx;
+}
+
+__device__ __forceinline__ float norm3f(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }
+
+// findLine (feature_utils.h:108-154) + getCornerFeatureCoefficients (:17-26, 63-75).  Returns bit0 kept, bit1 counted.
+__device__ __forceinline__ int corner_row(const float4 nb[5], float sx, float sy, float sz, float co[4]) {
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { cx += nb[j].x; cy += nb[j].y; cz += nb[j].z; }
+  cx /= 5.0f; cy /= 5.0f; cz /= 5.0f;
+  float a00 = 0.f, a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f, a22 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    float ax = nb[j].x - cx, ay = nb[j].y - cy, az = nb[j].z - cz;
+    a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
+  }
+  float A[6] = {a00 / 5.0f, a10 / 5.0f, a20 / 5.0f, a11 / 5.0f, a21 / 5.0f, a22 / 5.0f};
+  float w[3], V[9];
+  eig3_sym(A, w, V);
+  if (!(w[2] > 5.f * w[1])) return 0;
+  float vx = V[2], vy = V[5], vz = V[8];
+  float Ax = cx - vx * 0.1f, Ay = cy - vy * 0.1f, Az = cz - vz * 0.1f;
+  float Bx = cx + vx * 0.1f, By = cy + vy * 0.1f, Bz = cz + vz * 0.1f;
+  float bx = sx - Bx, by = sy - By, bz = sz - Bz;
+  float ax = sx - Ax, ay = sy - Ay, az = sz - Az;
+  float kx = by * az - bz * ay, ky = bz * ax - bx * az, kz = bx * ay - by * ax;
+  float knorm = norm3f(kx, ky, kz);
+  float lengthAB = norm3f(Ax - Bx, Ay - By, Az - Bz);
+  float ex = Bx - Ax, ey = By - Ay, ez = Bz - Az;
+  float ux = ky * ez - kz * ey, uy = kz * ex - kx * ez, uz = kx * ey - ky * ex;
+  float den = knorm * lengthAB;
+  float dirx = -ux / den, diry = -uy / den, dirz = -uz / den;
+  float distance = knorm / lengthAB;
+  float weight = (float)(1 - 0.9f * fabs((double)distance));
+  co[0] = dirx * weight; co[1] = diry * weight; co[2] = dirz * weight; co[3] = distance * weight;
+  return ((double)weight > 0.1) ? 3 : 2;
+}
+
+// findPlane (feature_utils.h:157-204) + getSurfaceFeatureCoefficients (:97-106).
+__device__ __forceinline__ int surf_row(const float4 nb[5], float sx, float sy, float sz, float max_dist, float co[4]) {
+  float A[15], B[5], X[3];
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    cx += nb[j].x; cy += nb[j].y; cz += nb[j].z;
+    A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z;
+    B[j] = -1.f;
+  }
+  cx /= 5.0f; cy /= 5.0f; cz /= 5.0f;
+  colpiv_qr_solve<5, 3>(A, B, X);
+  float p0 = X[0], p1 = X[1], p2 = X[2], p3 = 0.f;
+  float norm = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
+  p0 /= norm; p1 /= norm; p2 /= norm; p3 /= norm;
+  p3 = -(p0 * cx + p1 * cy + p2 * cz);
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    float distance = (p0 * nb[j].x + p1 * nb[j].y + p2 * nb[j].z) + p3;
+    if (fabs((double)distance) > max_dist) return 0;
+  }
+  float distance = ((p0 * sx + p1 * sy) + p2 * sz) + p3;
+  float xn = norm3f(sx, sy, sz);
+  float weight = (float)(1 - 0.9 * fabs((double)distance) / sqrt((double)xn));
+  co[0] = p0 * weight; co[1] = p1 * weight; co[2] = p2 * weight; co[3] = distance * weight;
+  return ((double)weight > 0.1) ? 3 : 2;
+}
+
+template <bool kOrigIdx>
+__global__ void __launch_bounds__(256) corr_kernel(CorrArgs a) {
+  const int s = blockIdx.y;
+  const MatchState& st = a.state[s];
+  if (st.done) return;
+  __shared__ PoseCoef kc;
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x == 0) make_pose_coef(st, kc);
+  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
+  __syncthreads();
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int capQ = a.cap_corner + a.cap_surf;
+  const float4* corner = a.corner + (size_t)s * a.cap_corner;
+  const float4* surf = a.surf + (size_t)s * a.cap_surf;
+  RowOut* rows = a.rows + (size_t)s * capQ;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nC + nS; q += gridDim.x * blockDim.x) {
+    const bool isCorner = q < nC;
+    const float4 p = isCorner ? corner[q] : surf[q - nC];
+    float sx, sy, sz;
+    transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
+    const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+    Top5 best;
+    knn5_search<kOrigIdx>(g, sx, sy, sz, best);
+    RowOut row;
+#pragma unroll
+    for (int k = 0; k < 6; k++) row.a[k] = 0.f;
+    row.b = 0.f; row.flag = 0;
+    const bool gate = best.d[4] < a.prm.knn_gate;
+    if (a.nn) {
+      int* nn = a.nn + ((size_t)s * capQ + q) * 5;
+#pragma unroll
+      for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx[k] : -1;
+    }
+    if (gate) {
+      float4 nb[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) nb[k] = __ldg(g.pts + best.slot[k]);
+      float co[4];
+      int f = isCorner ? corner_row(nb, sx, sy, sz, co) : surf_row(nb, sx, sy, sz, a.prm.plane_max_dist, co);
+      row.flag = f;
+      if (f & 1) {
+        const float x = p.x, y = p.y, z = p.z;
+        float arx = (kc.x1 * y + kc.x2 * z) * co[0] + (kc.x3 * y - kc.x4 * z) * co[1] + (kc.x5 * y - kc.x6 * z) * co[2];
+        float ary = (kc.y1 * x + kc.y2 * y + kc.y3 * z) * co[0] + (kc.y4 * x + kc.y5 * y + kc.y6 * z) * co[1] +
+                    (kc.y7 * x - kc.y8 * y - kc.y9 * z) * co[2];
+        float arz = (kc.z1 * x - kc.x4 * y + kc.z3 * z) * co[0] + (kc.z4 * x + kc.z5 * y + kc.z6 + kc.z7 * z) * co[1] +
+                    0 * co[2];
+        row.a[0] = arx; row.a[1] = ary; row.a[2] = arz; row.a[3] = co[0]; row.a[4] = co[1]; row.a[5] = co[2];
+        row.b = -co[3];
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(rows + q);
+    dst[0] = make_float4(row.a[0], row.a[1], row.a[2], row.a[3]);
+    dst[1] = make_float4(row.a[4], row.a[5], row.b, __int_as_float(row.flag));
+  }
+}
+
+// ============================================================================================================
+// K6: reduce A^T A / A^T b over the rows of one stream (K6a), then solve + degeneracy projection + pose update +
+// convergence test (K6b)  (ScanMatch.cpp:134-260).
+// ============================================================================================================
+struct SolveArgs {
+  const RowOut* rows;
+  const int* n_corner; const int* n_surf;
+  int cap_corner, cap_surf;
+  MatchState* state;
+  IterTrace* trace;   // optional [nstreams][max_iterations]
+  int iter;
+  MatchParamsDev prm;
+};
+
+#define CM_NACC 31   // 21 (AtA upper) + 6 (AtB) + rows + line / plane counted + score
+
+// K6a: deterministic reduction of one stream's rows.  One CTA per stream.  Float products are exact in double and
+// are accumulated in double, so any summation order rounds to the same float A^T A as the oracle's.
+__global__ void __launch_bounds__(512) reduce_rows_kernel(SolveArgs a, double* __restrict__ sums) {
+  const int s = blockIdx.x;
+  if (a.state[s].done) return;
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const RowOut* rows = a.rows + (size_t)s * (a.cap_corner + a.cap_surf);
+  double acc[CM_NACC];
+#pragma unroll
+  for (int k = 0; k < CM_NACC; k++) acc[k] = 0.0;
+  for (int q = threadIdx.x; q < nC + nS; q += blockDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(rows + q);
+    float4 r0 = src[0], r1 = src[1];
+    int flag = __float_as_int(r1.w);
+    if (flag & 2) { if (q < nC) acc[28] += 1.0; else acc[29] += 1.0; }
+    if (flag & 1) {
+      double v[7] = {(double)r0.x, (double)r0.y, (double)r0.z, (double)r0.w, (double)r1.x, (double)r1.y, (double)r1.z};
+      int t = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = r; c < 6; c++) acc[t++] += v[r] * v[c];
+#pragma unroll
+      for (int r = 0; r < 6; r++) acc[21 + r] += v[r] * v[6];
+      acc[27] += 1.0;
+      acc[30] += exp(-fabs(v[6]));
+    }
+  }
+  __shared__ double sm[16][CM_NACC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < CM_NACC; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < CM_NACC) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += sm[w][threadIdx.x];
+    sums[(size_t)s * 32 + threadIdx.x] = v;
+  }
+}
+
+// The 6x6 routines are kept out of line on purpose: each gets its own small stack frame.  Inlined into one large
+// kernel body, nvcc 12.9 (sm_100a) produced a wrong 6x6 solve (see the note in cm_math.h::colpiv_qr_solve).
+__device__ __noinline__ void dev_qr_solve6(const float* A, const float* b, float* x) {
+  float Aw[36], bw[6], xw[6];
+  for (int k = 0; k < 36; k++) Aw[k] = A[k];
+  for (int k = 0; k < 6; k++) bw[k] = b[k];
+  colpiv_qr_solve<6, 6>(Aw, bw, xw);
+  for (int k = 0; k < 6; k++) x[k] = xw[k];
+}
+__device__ __noinline__ void dev_eig6_values(const float* A, float* w) {
+  float Aw[36], ww[6];
+  for (int k = 0; k < 36; k++) Aw[k] = A[k];
+  eig_sym<6>(Aw, ww, (float*)nullptr);
+  for (int k = 0; k < 6; k++) w[k] = ww[k];
+}
+__device__ __noinline__ void dev_eig6_full(const float* A, float* w, float* V) {
+  float Aw[36], ww[6], Vw[36];
+  for (int k = 0; k < 36; k++) Aw[k] = A[k];
+  eig_sym<6>(Aw, ww, Vw);
+  for (int k = 0; k < 6; k++) w[k] = ww[k];
+  for (int k = 0; k < 36; k++) V[k] = Vw[k];
+}
+__device__ __noinline__ bool dev_inverse6(const float* A, float* inv) {
+  float Aw[36], iw[36];
+  for (int k = 0; k < 36; k++) Aw[k] = A[k];
+  bool ok = inverse_lu<6>(Aw, iw);
+  for (int k = 0; k < 36; k++) inv[k] = iw[k];
+  return ok;
+}
+
+// K6b: solve, degeneracy projection, pose update, convergence (ScanMatch.cpp:134-260).  One thread per stream; the
+// 6x6 work goes through cm_math.h, i.e. the same instruction sequence as the oracle's.
+__global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int nstreams) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams) return;
+  MatchState& st = a.state[s];
+  if (st.done) return;
+  const double* tot = sums + (size_t)s * 32;
+  const int nrows = (int)tot[27];
+  const int nline = (int)tot[28], nplane = (int)tot[29];
+  st.rows = nrows; st.line = nline; st.plane = nplane; st.score = tot[30];
+  IterTrace* tr = a.trace ? a.trace + (size_t)s * a.prm.max_iterations + a.iter : nullptr;
+  if (tr) {
+    for (int k = 0; k < 6; k++) tr->pose_in[k] = st.pose[k];
+    tr->rows = nrows; tr->line = nline; tr->plane = nplane; tr->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
+    for (int k = 0; k < 36; k++) tr->AtA[k] = 0.f;
+    for (int k = 0; k < 6; k++) { tr->AtB[k] = 0.f; tr->x[k] = 0.f; }
+  }
+  if (nrows < a.prm.min_rows) {   // ScanMatch.cpp:141-145
+    st.flags |= CM_F_TOO_FEW_MATCHES; st.done = 1;
+    return;
+  }
+  float AtA[36], AtB[6], X[6];
+  {
+    int t = 0;
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) { float v = (float)tot[t++]; AtA[r * 6 + c] = v; AtA[c * 6 + r] = v; }
+    for (int r = 0; r < 6; r++) AtB[r] = (float)tot[21 + r];
+  }
+  dev_qr_solve6(AtA, AtB, X);   // ScanMatch.cpp:209
+  if (a.iter == 0) {   // ScanMatch.cpp:211-235
+    float E[6];
+    dev_eig6_values(AtA, E);
+    if (E[0] < a.prm.eig_threshold) {
+      float V[36], V2[36], Vinv[36];
+      dev_eig6_full(AtA, E, V);
+      for (int k = 0; k < 36; k++) V2[k] = V[k];
+      for (int i = 0; i < 6; i++) {
+        if (E[i] < a.prm.eig_threshold) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; }
+        else break;
+      }
+      if (!dev_inverse6(V, Vinv)) { for (int k = 0; k < 36; k++) Vinv[k] = nanf(""); }
+      for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) {
+          float sum = 0.f;
+          for (int k = 0; k < 6; k++) sum += Vinv[r * 6 + k] * V2[k * 6 + c];
+          st.P[r * 6 + c] = sum;
+        }
+      st.flags |= CM_F_DEGENERATE;
+    }
+  }
+  if (st.flags & CM_F_DEGENERATE) {   // ScanMatch.cpp:237-240
+    float x2[6];
+    for (int k = 0; k < 6; k++) x2[k] = X[k];
+    for (int r = 0; r < 6; r++) {
+      float sum = 0.f;
+      for (int k = 0; k < 6; k++) sum += st.P[r * 6 + k] * x2[k];
+      X[r] = sum;
+    }
+  }
+  float np[6];
+  for (int k = 0; k < 6; k++) np[k] = st.pose[k] + X[k];   // ScanMatch.cpp:242-247
+  state_set_pose(st, np);
+  st.iterations = a.iter + 1;
+  if (tr) {
+    for (int k = 0; k < 36; k++) tr->AtA[k] = AtA[k];
+    for (int k = 0; k < 6; k++) { tr->AtB[k] = AtB[k]; tr->x[k] = X[k]; }
+    tr->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
+  }
+  // ScanMatch.cpp:249-260: rad2deg(float) = (float)(r*180.0/M_PI); pow(., 2) in double; sqrt; narrowed to float
+  const double PI = 3.14159265358979323846;
+  double d0 = (double)(float)((double)X[0] * 180.0 / PI), d1 = (double)(float)((double)X[1] * 180.0 / PI),
+         d2 = (double)(float)((double)X[2] * 180.0 / PI);
+  float deltaR = (float)sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+  double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+  float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+  if (deltaR < a.prm.delta_r_abort && deltaT < a.prm.delta_t_abort) { st.flags |= CM_F_CONVERGED; st.done = 1; }
+}
+
+// ============================================================================================================
+// Stand-alone exact 5-NN (test hook and operator): queries already in the map frame.
+// ============================================================================================================
+__global__ void knn5_kernel(GridView g, const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  Top5 best;
+  knn5_search<true>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], best);
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    idx[5 * i + k] = best.slot[k] < 0 ? -1 : best.idx[k];
+    d2[5 * i + k] = best.d[k];
+  }
+}
+
+// ============================================================================================================
+// Host-side launchers
+// ============================================================================================================
+static inline unsigned int next_pow2(unsigned int v) { unsigned int p = 64; while (p < v) p <<= 1; return p; }
+
+int grid_max_level(float cell, float gate) {
+  int L = (int)ceilf(sqrtf(gate) / cell - 0.48f);
+  return L < 0 ? 0 : L;
+}
+
+void GridStorage::build(const float4* d_pts, int n, float cell_size, float gate, int keep_w, cudaStream_t stream) {
+  unsigned int cap = next_pow2((unsigned int)(2 * (n > 0 ? n : 1)));
+  entries.reserve((size_t)cap * sizeof(CellEntry));
+  pts.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4));
+  cell_of.reserve((size_t)(n > 0 ? n : 1) * sizeof(int));
+  cursor.reserve(sizeof(unsigned int));
+  float inv = 1.0f / cell_size;
+  CM_LAUNCH(grid_clear_kernel, (cap + 255) / 256, 256, 0, stream, (CellEntry*)entries.p, cap);
+  cudaMemsetAsync(cursor.p, 0, sizeof(unsigned int), stream);
+  if (n > 0) {
+    int nb = (n + 255) / 256;
+    CM_LAUNCH(grid_count_kernel, nb, 256, 0, stream, d_pts, n, (CellEntry*)entries.p, cap - 1, 0.f, 0.f, 0.f, inv, (int*)cell_of.p);
+    CM_LAUNCH(grid_offsets_kernel, (cap + 255) / 256, 256, 0, stream, (CellEntry*)entries.p, cap, (unsigned int*)cursor.p);
+    CM_LAUNCH(grid_scatter_kernel, nb, 256, 0, stream, d_pts, n, (CellEntry*)entries.p, (const int*)cell_of.p, (float4*)pts.p, keep_w);
+  }
+  view.entries = (const CellEntry*)entries.p;
+  view.pts = (const float4*)pts.p;
+  view.mask = cap - 1;
+  view.ox = view.oy = view.oz = 0.f;
+  view.cell = cell_size; view.inv_cell = inv;
+  view.npts = n;
+  view.max_level = grid_max_level(cell_size, gate);
+}
+
+void launch_knn5(const GridView& g, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t stream) {
+  if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, d_idx, d_d2);
+}
+
+void launch_match(const MatchLaunch& m, cudaStream_t stream) {
+  CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
+  CorrArgs ca;
+  ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
+  ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
+  ca.state = m.state; ca.rows = m.rows; ca.nn = nullptr; ca.prm = m.prm;
+  SolveArgs sa;
+  sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
+  sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm;
+  int capQ = m.cap_corner + m.cap_surf;
+  int bx = (capQ + 255) / 256;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, m.nstreams);
+  for (int it = 0; it < m.prm.max_iterations; it++) {
+    ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
+    if (m.orig_idx) CM_LAUNCH(corr_kernel<true>, grid, 256, 0, stream, ca);
+    else CM_LAUNCH(corr_kernel<false>, grid, 256, 0, stream, ca);
+    sa.iter = it;
+    CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+    CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, (const double*)m.sums, m.nstreams);
+  }
+}
+
+}  // namespace cm

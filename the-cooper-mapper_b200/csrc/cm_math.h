@@ -131,12 +131,14 @@ CM_HD void tridiagonal_qr_step(float* diag, float* subdiag, int start, int end, 
       z = -s * subdiag[k + 1];
       subdiag[k + 1] = c * subdiag[k + 1];
     }
-    // Q = Q * G : columns k and k+1
+    // Q = Q * G : columns k and k+1 (skipped when only eigenvalues are wanted; diag/subdiag do not depend on Q)
+    if (Q) {
 CM_UNROLL
-    for (int r = 0; r < N; ++r) {
-      float xi = Q[r * N + k], yi = Q[r * N + k + 1];
-      Q[r * N + k] = c * xi - s * yi;
-      Q[r * N + k + 1] = s * xi + c * yi;
+      for (int r = 0; r < N; ++r) {
+        float xi = Q[r * N + k], yi = Q[r * N + k + 1];
+        Q[r * N + k] = c * xi - s * yi;
+        Q[r * N + k + 1] = s * xi + c * yi;
+      }
     }
   }
 }
@@ -169,8 +171,10 @@ CM_HD void tridiagonal_to_eigen(float* diag, float* subdiag, float* Q) {
       if (diag[i + j] < m) { m = diag[i + j]; k = j; }
     if (k > 0) {
       float t = diag[i]; diag[i] = diag[k + i]; diag[k + i] = t;
-      for (int r = 0; r < N; ++r) {
-        float u = Q[r * N + i]; Q[r * N + i] = Q[r * N + k + i]; Q[r * N + k + i] = u;
+      if (Q) {
+        for (int r = 0; r < N; ++r) {
+          float u = Q[r * N + i]; Q[r * N + i] = Q[r * N + k + i]; Q[r * N + k + i] = u;
+        }
       }
     }
   }
@@ -231,7 +235,8 @@ CM_HD void make_householder(float* x, int n, float* tau, float* beta) {
 }
 
 // Symmetric N x N eigen-decomposition (general N; used for the 6x6 degeneracy test, ScanMatch.cpp:216).
-// A is full row-major, only the lower triangle is read.  Eigenvalues ascending, eigenvectors = columns of V.
+// A is full row-major, only the lower triangle is read.  Eigenvalues ascending, eigenvectors = columns of V
+// (V may be nullptr: eigenvalues only, bit-identical to the values of a full solve).
 // Eigen internal::tridiagonalization_inplace (Householder) + HouseholderSequence::evalTo + QR iterations.
 template <int N>
 CM_HD void eig_sym(const float* Ain, float* w, float* V) {
@@ -243,15 +248,14 @@ CM_HD void eig_sym(const float* Ain, float* w, float* V) {
   for (int r = 0; r < N; ++r)
     for (int c = 0; c < N; ++c) A[r * N + c] = (c <= r) ? Ain[r * N + c] / scale : 0.f;
   float hc[N];  // Householder coefficients
+  float col[N], p[N];   // function scope on purpose (see colpiv_qr_solve)
   for (int i = 0; i < N - 1; ++i) {
     int rs = N - i - 1;
-    float col[N];
     for (int j = 0; j < rs; ++j) col[j] = A[(i + 1 + j) * N + i];
     float h, beta;
     make_householder(col, rs, &h, &beta);
     col[0] = 1.f;
     // p = h * (A22 * u)  using the lower triangle of the trailing block as a self-adjoint view
-    float p[N];
     for (int r = 0; r < rs; ++r) {
       float acc = 0.f;
       for (int c = 0; c < rs; ++c) {
@@ -276,6 +280,7 @@ CM_HD void eig_sym(const float* Ain, float* w, float* V) {
   for (int i = 0; i < N; ++i) diag[i] = A[i * N + i];
   for (int i = 0; i < N - 1; ++i) subdiag[i] = A[(i + 1) * N + i];
   // Q = H_0 H_1 ... H_{N-2}, H_k = I - hc[k] v_k v_k^T, v_k = e_{k+1} + essential below
+  if (V) {
   for (int r = 0; r < N; ++r)
     for (int c = 0; c < N; ++c) V[r * N + c] = (r == c) ? 1.f : 0.f;
   for (int k = N - 2; k >= 0; --k) {
@@ -288,6 +293,7 @@ CM_HD void eig_sym(const float* Ain, float* w, float* V) {
       for (int r = r0 + 1; r < N; ++r) V[r * N + c] -= hc[k] * A[r * N + k] * tmp;
     }
   }
+  }
   tridiagonal_to_eigen<N>(diag, subdiag, V);
   for (int i = 0; i < N; ++i) w[i] = diag[i] * scale;
 }
@@ -295,87 +301,134 @@ CM_HD void eig_sym(const float* Ain, float* w, float* V) {
 // Least-squares / square solve A x = b through column-pivoted Householder QR.  A is M x N row-major
 // (destroyed), b has M entries (destroyed), x has N entries.
 // Eigen ColPivHouseholderQR::computeInPlace + _solve_impl (3.3, LAPACK-style norm downdating).
+// Written with compile-time indices only (the data-dependent column pivot is applied through predicated swaps)
+// so that on the GPU every array stays in registers.  This is also a deliberate work-around: a first version
+// that indexed the scratch arrays with the run-time pivot was mis-compiled by nvcc 12.9 for sm_100a (stack
+// slots of two live arrays overlapped; reproduced on a B200, clean under ASan/UBSan on the host).
 template <int M, int N>
 CM_HD void colpiv_qr_solve(float* A, float* b, float* x) {
-  const int size = M < N ? M : N;
-  float normsUpdated[N], normsDirect[N], hco[N];
+  constexpr int size = M < N ? M : N;
+  float nu[N], nd[N], hco[size];   // updated / direct column norms, Householder coefficients
   int perm[N];
   float maxnorm = 0.f;
+CM_UNROLL
   for (int k = 0; k < N; ++k) {
     float s = 0.f;
+CM_UNROLL
     for (int r = 0; r < M; ++r) s += A[r * N + k] * A[r * N + k];
-    normsDirect[k] = sqrtf(s);
-    normsUpdated[k] = normsDirect[k];
-    if (normsUpdated[k] > maxnorm) maxnorm = normsUpdated[k];
+    nd[k] = sqrtf(s);
+    nu[k] = nd[k];
+    if (nu[k] > maxnorm) maxnorm = nu[k];
     perm[k] = k;
   }
   float te = maxnorm * FLT_EPSILON;
   float threshold_helper = (te * te) / (float)M;
   float norm_downdate_threshold = sqrtf(FLT_EPSILON);
   int nonzero_pivots = size;
+CM_UNROLL
   for (int k = 0; k < size; ++k) {
     int big = k;
-    float bigv = normsUpdated[k];
+    float bigv = nu[k];
+CM_UNROLL
     for (int j = k + 1; j < N; ++j)
-      if (normsUpdated[j] > bigv) { bigv = normsUpdated[j]; big = j; }
+      if (nu[j] > bigv) { bigv = nu[j]; big = j; }
     float big_sq = bigv * bigv;
     if (nonzero_pivots == size && big_sq < threshold_helper * (float)(M - k)) nonzero_pivots = k;
-    if (k != big) {
-      for (int r = 0; r < M; ++r) { float t = A[r * N + k]; A[r * N + k] = A[r * N + big]; A[r * N + big] = t; }
-      float t = normsUpdated[k]; normsUpdated[k] = normsUpdated[big]; normsUpdated[big] = t;
-      t = normsDirect[k]; normsDirect[k] = normsDirect[big]; normsDirect[big] = t;
-      int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
+CM_UNROLL
+    for (int j = k + 1; j < N; ++j) {
+      if (big == j) {
+CM_UNROLL
+        for (int r = 0; r < M; ++r) { float t = A[r * N + k]; A[r * N + k] = A[r * N + j]; A[r * N + j] = t; }
+        float t = nu[k]; nu[k] = nu[j]; nu[j] = t;
+        t = nd[k]; nd[k] = nd[j]; nd[j] = t;
+        int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
+      }
     }
-    float col[M];
-    int n = M - k;
-    for (int r = 0; r < n; ++r) col[r] = A[(k + r) * N + k];
+    // Householder reflector of column k, rows k..M-1 (MatrixBase::makeHouseholder); essential part stored below the diagonal
+    float tailSqNorm = 0.f;
+CM_UNROLL
+    for (int r = k + 1; r < M; ++r) tailSqNorm += A[r * N + k] * A[r * N + k];
+    float c0 = A[k * N + k];
     float tau, beta;
-    make_householder(col, n, &tau, &beta);
+    if (k == M - 1 || tailSqNorm <= FLT_MIN) {
+      tau = 0.f; beta = c0;
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) A[r * N + k] = 0.f;
+    } else {
+      float bb = sqrtf(c0 * c0 + tailSqNorm);
+      if (c0 >= 0.f) bb = -bb;
+      float d = c0 - bb;
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) A[r * N + k] = A[r * N + k] / d;
+      tau = (bb - c0) / bb;
+      beta = bb;
+    }
     A[k * N + k] = beta;
-    for (int r = 1; r < n; ++r) A[(k + r) * N + k] = col[r];
     hco[k] = tau;
     // apply H_k to the trailing columns
+CM_UNROLL
     for (int c = k + 1; c < N; ++c) {
       float tmp = A[k * N + c];
-      for (int r = 1; r < n; ++r) tmp += col[r] * A[(k + r) * N + c];
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) tmp += A[r * N + k] * A[r * N + c];
       A[k * N + c] -= tau * tmp;
-      for (int r = 1; r < n; ++r) A[(k + r) * N + c] -= tau * col[r] * tmp;
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) A[r * N + c] -= tau * A[r * N + k] * tmp;
     }
+CM_UNROLL
     for (int j = k + 1; j < N; ++j) {
-      if (normsUpdated[j] != 0.f) {
-        float temp = fabsf(A[k * N + j]) / normsUpdated[j];
+      if (nu[j] != 0.f) {
+        float temp = fabsf(A[k * N + j]) / nu[j];
         temp = (1.f + temp) * (1.f - temp);
         temp = temp < 0.f ? 0.f : temp;
-        float ratio = normsUpdated[j] / normsDirect[j];
+        float ratio = nu[j] / nd[j];
         float temp2 = temp * (ratio * ratio);
         if (temp2 <= norm_downdate_threshold) {
           float s = 0.f;
+CM_UNROLL
           for (int r = k + 1; r < M; ++r) s += A[r * N + j] * A[r * N + j];
-          normsDirect[j] = sqrtf(s);
-          normsUpdated[j] = normsDirect[j];
+          nd[j] = sqrtf(s);
+          nu[j] = nd[j];
         } else {
-          normsUpdated[j] *= sqrtf(temp);
+          nu[j] *= sqrtf(temp);
         }
       }
     }
   }
+CM_UNROLL
   for (int i = 0; i < N; ++i) x[i] = 0.f;
   if (nonzero_pivots == 0) return;
   // c = Q^T b = H_{p-1} ... H_0 b
-  for (int k = 0; k < nonzero_pivots; ++k) {
-    int n = M - k;
-    float tmp = b[k];
-    for (int r = 1; r < n; ++r) tmp += A[(k + r) * N + k] * b[k + r];
-    b[k] -= hco[k] * tmp;
-    for (int r = 1; r < n; ++r) b[k + r] -= hco[k] * A[(k + r) * N + k] * tmp;
+CM_UNROLL
+  for (int k = 0; k < size; ++k) {
+    if (k < nonzero_pivots) {
+      float tmp = b[k];
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) tmp += A[r * N + k] * b[r];
+      b[k] -= hco[k] * tmp;
+CM_UNROLL
+      for (int r = k + 1; r < M; ++r) b[r] -= hco[k] * A[r * N + k] * tmp;
+    }
   }
   // back substitution on the leading nonzero_pivots x nonzero_pivots upper triangle
-  for (int i = nonzero_pivots - 1; i >= 0; --i) {
-    float s = b[i];
-    for (int j = i + 1; j < nonzero_pivots; ++j) s -= A[i * N + j] * b[j];
-    b[i] = s / A[i * N + i];
+CM_UNROLL
+  for (int i = size - 1; i >= 0; --i) {
+    if (i < nonzero_pivots) {
+      float s = b[i];
+CM_UNROLL
+      for (int j = i + 1; j < size; ++j)
+        if (j < nonzero_pivots) s -= A[i * N + j] * b[j];
+      b[i] = s / A[i * N + i];
+    }
   }
-  for (int i = 0; i < nonzero_pivots; ++i) x[perm[i]] = b[i];
+CM_UNROLL
+  for (int i = 0; i < size; ++i) {
+    if (i < nonzero_pivots) {
+CM_UNROLL
+      for (int c = 0; c < N; ++c)
+        if (perm[i] == c) x[c] = b[i];
+    }
+  }
 }
 
 // General N x N inverse by partial-pivot LU (Eigen uses PartialPivLU for sizes > 4).  Returns false if a
@@ -402,8 +455,8 @@ CM_HD bool inverse_lu(const float* Ain, float* inv) {
       for (int c = k + 1; c < N; ++c) A[r * N + c] -= l * A[k * N + c];
     }
   }
+  float y[N];
   for (int col = 0; col < N; ++col) {
-    float y[N];
     for (int r = 0; r < N; ++r) {
       float s = (piv[r] == col) ? 1.f : 0.f;
       for (int c = 0; c < r; ++c) s -= A[r * N + c] * y[c];
