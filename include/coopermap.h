@@ -110,6 +110,13 @@ int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t 
                                 size_t n_ref_surf, const cm_point* corner, size_t n_corner, const cm_point* surf,
                                 size_t n_surf, cm_iso* pose, cm_match_stats* stats);
 
+/* pcl::VoxelGrid<pcl::PointXYZI>::filter with a cubic leaf, batched over nseg independent clouds: cloud s is
+ * in[s*cap_in .. s*cap_in + n_in[s]) and its result out[s*cap_out .. s*cap_out + n_out[s]), ordered by voxel index,
+ * every field (x, y, z, intensity) averaged.  Replaces the filter calls at ScanRegistration.cpp:390-399,
+ * LaserMatcher.cpp:293-300, ScanMatch.cpp:381-394 (semantics: util/voxel_grid_partition.hpp:91-272). */
+int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,
+                         int* n_out, int cap_out);
+
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.
  * op: 0 QR-solve 6x6 (42 -> 6 floats), 1 QR-solve 5x3 (20 -> 3), 2 eig 3x3 (6 -> 12), 3 eig 6x6 (36 -> 42),

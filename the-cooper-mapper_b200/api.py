@@ -123,6 +123,23 @@ class Context:
         self._check(self.L.cm_debug_math_host(self.h, C.c_int(op), _ptr(a), C.c_size_t(len(a)), _ptr(out)))
         return out
 
+    # ---- voxel filter --------------------------------------------------------------------------------------------
+    def voxel_filter_batch(self, clouds, leaf):
+        """clouds: list of (n_i, 4) arrays -> list of filtered (m_i, 4) arrays (pcl::VoxelGrid semantics)."""
+        nseg = len(clouds)
+        n_in = np.array([len(c) for c in clouds], np.int32)
+        cap = max(int(n_in.max()), 1)
+        buf = np.zeros((nseg, cap, 4), np.float32)
+        for i, c in enumerate(clouds):
+            buf[i, :len(c)] = _f32(c, 4)
+        out = np.empty((nseg, cap, 4), np.float32); n_out = np.zeros(nseg, np.int32)
+        self._check(self.L.cm_voxel_filter_host(self.h, _ptr(buf), C.c_int(nseg), _ptr(n_in), C.c_int(cap), C.c_float(leaf),
+                                                _ptr(out), _ptr(n_out), C.c_int(cap)))
+        return [out[i, :n_out[i]].copy() for i in range(nseg)]
+
+    def voxel_filter(self, cloud, leaf):
+        return self.voxel_filter_batch([cloud], leaf)[0]
+
     # ---- exact 5-NN ---------------------------------------------------------------------------------------
     def knn5(self, map_pts, queries, cell=1.2, gate=5.0):
         m = _f32(map_pts, 4); q = _f32(queries, 3)

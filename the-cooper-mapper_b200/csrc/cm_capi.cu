@@ -22,6 +22,8 @@ struct cm_ctx {
   DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
   DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
   GridStorage grid_a, grid_b;
+  VoxelFilter voxel;
+  DeviceBuffer d_vin, d_vout, d_vn_in, d_vn_out, d_flag;
 };
 
 static MatchParamsDev dev_params(const cm_config& c) {
@@ -235,6 +237,35 @@ int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t 
   if (rc < 0) return rc;
   twist_to_iso_host(&tw, pose);
   return rc;
+}
+
+int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,
+                         int* n_out, int cap_out) {
+  if (!ctx || nseg <= 0 || !n_in || cap_in <= 0 || !(leaf > 0.f) || !out || !n_out || cap_out <= 0 || !in)
+    return fail(ctx, CM_ERR_ARG, "bad argument");
+  for (int s = 0; s < nseg; s++) if (n_in[s] < 0 || n_in[s] > cap_in) return fail(ctx, CM_ERR_ARG, "n_in[s] out of range");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    ctx->d_vin.reserve((size_t)nseg * cap_in * sizeof(cm_point));
+    ctx->d_vout.reserve((size_t)nseg * cap_out * sizeof(cm_point));
+    ctx->d_vn_in.reserve(nseg * sizeof(int)); ctx->d_vn_out.reserve(nseg * sizeof(int)); ctx->d_flag.reserve(sizeof(int));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vin.p, in, (size_t)nseg * cap_in * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vn_in.p, n_in, nseg * sizeof(int), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
+    ctx->voxel.run(nseg, (const float4*)ctx->d_vin.p, (const int*)ctx->d_vn_in.p, cap_in, leaf, (float4*)ctx->d_vout.p,
+                   (int*)ctx->d_vn_out.p, cap_out, (int*)ctx->d_flag.p, st);
+    int ovf = 0;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_vout.p, (size_t)nseg * cap_out * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n_out, ctx->d_vn_out.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&ovf, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    if (ovf) return fail(ctx, CM_ERR_CAPACITY, "voxel filter output exceeds cap_out");
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
 }
 
 int cm_debug_math_host(cm_ctx* ctx, int op, const float* in, size_t n, float* out) {

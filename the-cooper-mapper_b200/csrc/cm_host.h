@@ -65,6 +65,14 @@ struct MatchLaunch {
 };
 void launch_match(const MatchLaunch& m, cudaStream_t stream);
 
+// K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes
+// out[s*cap_out .. +n_out[s]).
+struct VoxelFilter {
+  DeviceBuffer box, keys_a, keys_b, vals_a, vals_b, flags, rank, seg_first, temp;
+  void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out, int cap_out,
+           int* d_overflow, cudaStream_t stream);
+};
+
 int debug_math_dims(int op, int* nin, int* nout);
 void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream);
 
