@@ -110,6 +110,27 @@ int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t 
                                 size_t n_ref_surf, const cm_point* corner, size_t n_corner, const cm_point* surf,
                                 size_t n_surf, cm_iso* pose, cm_match_stats* stats);
 
+/* Outputs of scan registration for nstreams independent sweeps.  Clouds carry intensity = ring + relTime, like the
+ * reference's published feature clouds (toXYZI, pcl_util.h:30-37).  Optional members may be NULL. */
+typedef struct cm_scanreg_out {
+  cm_point* pts[4];        /* [nstreams][cap[k]]: 0 /laser_cloud_sharp, 1 /laser_cloud_less_sharp, 2 /laser_cloud_flat,
+                              3 /laser_cloud_less_flat (after the per-ring 0.2 m voxel filter) */
+  int cap[4];
+  int* n;                  /* [nstreams][5]: sizes of the four clouds + number of less-flat points before the filter */
+  cm_point* cloud;         /* optional [nstreams][rows*cols]: ring-major full-resolution cloud (/velodyne_cloud_2) */
+  float* cloud_curvature;  /* optional, with cloud: its curvature field (= ring + relTime) */
+  int* scan_ranges;        /* optional [nstreams][rows][2]: inclusive index range of every ring (_scanIndices) */
+  int* idx[4];             /* optional [nstreams][rows*cols]: cloud indices of sharp, less_sharp, flat, UNFILTERED less-flat */
+  signed char* picked;     /* optional [nstreams][rows*cols]: final _scanNeighborPicked */
+  float* curvature;        /* optional [nstreams][rows*cols]: region curvature, -1 outside the regions */
+  signed char* label;      /* optional [nstreams][rows*cols]: pointClassify label where evaluated, 127 elsewhere */
+} cm_scanreg_out;
+
+/* OrganisedScanRegistration::process (OrganizedScanRegistration.cpp:82-150) + ScanRegistration::extractFeatures
+ * (ScanRegistration.cpp:190-418) for nstreams organised sweeps of rows x cols points (ring = row, missing returns
+ * NaN), frames[s][row][col]. */
+int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out);
+
 /* pcl::VoxelGrid<pcl::PointXYZI>::filter with a cubic leaf, batched over nseg independent clouds: cloud s is
  * in[s*cap_in .. s*cap_in + n_in[s]) and its result out[s*cap_out .. s*cap_out + n_out[s]), ordered by voxel index,
  * every field (x, y, z, intensity) averaged.  Replaces the filter calls at ScanRegistration.cpp:390-399,

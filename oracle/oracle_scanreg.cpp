@@ -177,7 +177,8 @@ struct Ctx {
 // ScanRegistration.cpp:190-418
 void extract_features(const ScanRegParams& prm, ScanRegResult& r) {
   Ctx cx{prm, r, {}, {}, {}, {}, 0.f};
-  cx.blindThreshold = (float)std::cos(deg2radf(prm.blindDegreeThreshold));   // ScanRegistration.cpp:46
+  // ScanRegistration.cpp:27,46: cos() is unqualified there -> the C double overload, narrowed into the float member
+  cx.blindThreshold = (float)std::cos((double)deg2radf(prm.blindDegreeThreshold));
   const int R = prm.curvatureRegion;
   r.picked.assign(r.cloud.size(), 0);
   r.curvature.assign(r.cloud.size(), -1.f);

@@ -1,0 +1,66 @@
+"""GPU parity: scan registration (mask, curvature, feature selection, per-ring voxel filter) bit-exact vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check(g, o):
+    ncloud = len(o["cloud"])
+    assert np.array_equal(g["scanStart"], o["scanStart"]) and np.array_equal(g["scanEnd"], o["scanEnd"])
+    assert np.array_equal(g["cloud"][:ncloud].view(np.uint32), o["cloud"].view(np.uint32))
+    assert np.array_equal(g["picked"][:ncloud], o["picked"])                        # unreliable-point mask + picks
+    assert np.array_equal(g["curvature"][:ncloud].view(np.uint32), o["curvature"].view(np.uint32))
+    assert np.array_equal(g["classLabel"][:ncloud], o["classLabel"])                # pointClassify labels
+    for k in ("sharpIdx", "lessSharpIdx", "flatIdx", "lessFlatRawIdx"):            # membership AND order of the lists
+        assert np.array_equal(g[k], o[k]), k
+    for k in ("sharp", "lessSharp", "flat", "lessFlat"):
+        assert g[k].shape == o[k].shape and np.array_equal(g[k].view(np.uint32), o[k].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("model,cols", [("VLP-16", None), ("HDL-64E", None), ("VLP-16", 601), ("HDL-32", 1000)])
+def test_scanreg_bit_exact(ctx, oracle, synth, scene_small, model, cols):
+    sc, _, _ = scene_small
+    R, t = synth.pose_matrix(0.3, 0.01, -0.02, (2.0, -0.5, 0.1))
+    fr = synth.simulate_scan(sc, R, t, model, seed=11, cols=cols)
+    _check(ctx.scanreg_organised(fr, debug=True), oracle.scanreg_organised(fr))
+
+
+def test_scanreg_batch_of_streams(ctx, oracle, synth, scene_small):
+    sc, _, _ = scene_small
+    frames = []
+    for k, (R, t) in enumerate(synth.trajectory(5, speed=2.0)):
+        frames.append(synth.simulate_scan(sc, R, t, "VLP-16", seed=40 + k, cols=900, dropout=0.02 * k))
+    frames[3][5, 12:, :] = np.nan        # ring with 12 points left
+    frames[3][7, :, :] = np.nan          # empty ring
+    frames[4][:, :, :3] = np.nan         # a stream with no returns at all
+    outs = ctx.scanreg_organised(np.stack(frames), debug=True)
+    for fr, g in zip(frames, outs):
+        _check(g, oracle.scanreg_organised(fr))
+
+
+def test_scanreg_golden(ctx):
+    g = np.load(os.path.join(GOLD, "scanreg_vlp16_600.npz"))
+    r = ctx.scanreg_organised(g["frame"], debug=True)
+    n = len(g["picked"])
+    for k in ("sharpIdx", "lessSharpIdx", "flatIdx", "lessFlatRawIdx"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["picked"][:n], g["picked"].astype(np.int32))
+    assert np.array_equal(r["classLabel"][:n], g["classLabel"].astype(np.int32))
+    assert np.array_equal(r["lessFlat"].view(np.uint32), g["lessFlat"].view(np.uint32))
+
+
+def test_scanreg_params(cmb, oracle, synth, scene_small):
+    sc, _, _ = scene_small
+    R, t = synth.pose_matrix(-0.2, 0, 0, (0, 1, 0))
+    fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=13, cols=1200)
+    c2 = cmb.Context(surface_curvature_threshold=0.1, max_surface_flat=2, max_corner_sharp=4, n_feature_regions=4,
+                     less_flat_filter_size=0.4, blind_radius=1.0, blind_degree_threshold=1.0)
+    o = oracle.scanreg_organised(fr, params=dict(surfaceCurvatureThreshold=0.1, maxSurfaceFlat=2, maxCornerSharp=4,
+                                                 nFeatureRegions=4, lessFlatFilterSize=0.4, blindRadius=1.0,
+                                                 blindDegreeThreshold=1.0))
+    _check(c2.scanreg_organised(fr, debug=True), o)
+    c2.close()

@@ -41,6 +41,12 @@ class MatchStats(C.Structure):
                 ("score", C.c_double)]
 
 
+class ScanRegOut(C.Structure):
+    _fields_ = [("pts", C.c_void_p * 4), ("cap", C.c_int * 4), ("n", C.c_void_p), ("cloud", C.c_void_p),
+                ("cloud_curvature", C.c_void_p), ("scan_ranges", C.c_void_p), ("idx", C.c_void_p * 4),
+                ("picked", C.c_void_p), ("curvature", C.c_void_p), ("label", C.c_void_p)]
+
+
 class IterTrace(C.Structure):
     _fields_ = [("pose_in", C.c_float * 6), ("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("x", C.c_float * 6),
                 ("rows", C.c_int), ("line_matches", C.c_int), ("plane_matches", C.c_int), ("degenerate", C.c_int)]
@@ -122,6 +128,52 @@ class Context:
         out = np.empty((len(a), nout), np.float32)
         self._check(self.L.cm_debug_math_host(self.h, C.c_int(op), _ptr(a), C.c_size_t(len(a)), _ptr(out)))
         return out
+
+    # ---- scan registration -----------------------------------------------------------------------------------------
+    def scanreg_organised(self, frames, debug=False):
+        """frames: (S, rows, cols, 4) or (rows, cols, 4) organised sweeps -> list of per-stream dicts with the four
+        feature clouds (sharp, lessSharp, flat, lessFlat); debug=True adds the full cloud, ring ranges, index lists,
+        mask, curvature and pointClassify labels (what the oracle returns)."""
+        fr = _f32(frames)
+        single = fr.ndim == 3
+        if single:
+            fr = fr[None]
+        S, rows, cols = fr.shape[:3]
+        npts = rows * cols
+        out = ScanRegOut()
+        bufs = [np.empty((S, npts, 4), np.float32) for _ in range(4)]
+        n = np.zeros((S, 5), np.int32)
+        for k in range(4):
+            out.pts[k] = bufs[k].ctypes.data; out.cap[k] = npts
+        out.n = n.ctypes.data
+        dbg = {}
+        if debug:
+            dbg = dict(cloud=np.empty((S, npts, 4), np.float32), ccurv=np.empty((S, npts), np.float32),
+                       ranges=np.empty((S, rows, 2), np.int32), idx=[np.empty((S, npts), np.int32) for _ in range(4)],
+                       picked=np.empty((S, npts), np.int8), curvature=np.empty((S, npts), np.float32),
+                       label=np.empty((S, npts), np.int8))
+            out.cloud = dbg["cloud"].ctypes.data; out.cloud_curvature = dbg["ccurv"].ctypes.data
+            out.scan_ranges = dbg["ranges"].ctypes.data
+            for k in range(4):
+                out.idx[k] = dbg["idx"][k].ctypes.data
+            out.picked = dbg["picked"].ctypes.data; out.curvature = dbg["curvature"].ctypes.data; out.label = dbg["label"].ctypes.data
+        self._check(self.L.cm_scanreg_organised_host(self.h, _ptr(fr), C.c_int(S), C.c_int(rows), C.c_int(cols), C.byref(out)))
+        res = []
+        names = ["sharp", "lessSharp", "flat", "lessFlat"]
+        for s_ in range(S):
+            d = {names[k]: bufs[k][s_, :n[s_, k]].copy() for k in range(4)}
+            if debug:
+                ncloud = int(dbg["ranges"][s_, -1, 1]) + 1 if dbg["ranges"][s_, :, 1].max() > 0 or n[s_].sum() > 0 else 0
+                total = int(sum(max(0, int(e) - int(b) + 1) for b, e in dbg["ranges"][s_] if not (b == 0 and e == 0)))
+                # ring sizes: a ring is empty when its range is (first, first-1) collapsed to (first, max(first-1, 0))
+                d["scanStart"] = dbg["ranges"][s_, :, 0].copy(); d["scanEnd"] = dbg["ranges"][s_, :, 1].copy()
+                d["cloud"] = np.concatenate([dbg["cloud"][s_], dbg["ccurv"][s_][:, None]], 1)
+                d["sharpIdx"] = dbg["idx"][0][s_, :n[s_, 0]].copy(); d["lessSharpIdx"] = dbg["idx"][1][s_, :n[s_, 1]].copy()
+                d["flatIdx"] = dbg["idx"][2][s_, :n[s_, 2]].copy(); d["lessFlatRawIdx"] = dbg["idx"][3][s_, :n[s_, 4]].copy()
+                d["picked"] = dbg["picked"][s_].astype(np.int32); d["curvature"] = dbg["curvature"][s_].copy()
+                d["classLabel"] = dbg["label"][s_].astype(np.int32)
+            res.append(d)
+        return res[0] if single else res
 
     # ---- voxel filter --------------------------------------------------------------------------------------------
     def voxel_filter_batch(self, clouds, leaf):

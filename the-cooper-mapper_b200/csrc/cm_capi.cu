@@ -23,6 +23,8 @@ struct cm_ctx {
   DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
   GridStorage grid_a, grid_b;
   VoxelFilter voxel;
+  ScanRegistrationGpu scanreg;
+  DeviceBuffer d_frames, d_sr_pts[4], d_sr_idx[4], d_sr_n, d_sr_cloud, d_sr_ccurv, d_sr_picked, d_sr_curv, d_sr_label, d_sr_range;
   DeviceBuffer d_vin, d_vout, d_vn_in, d_vn_out, d_flag;
 };
 
@@ -237,6 +239,74 @@ int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t 
   if (rc < 0) return rc;
   twist_to_iso_host(&tw, pose);
   return rc;
+}
+
+static void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
+  L.scan_period = c.scan_period; L.blind_radius = c.blind_radius;
+  // ScanRegistration.cpp:27,46: blindThreshold = cos(deg2rad(blindDegreeThreshold)), deg2rad(float) math_utils.h:38
+  float rad = (float)(c.blind_degree_threshold * M_PI / 180.0);
+  L.blind_thr = (float)cos((double)rad);
+  L.curv_thr = c.surface_curvature_threshold; L.less_flat_leaf = c.less_flat_filter_size;
+  L.R = c.curvature_region; L.nregions = c.n_feature_regions; L.max_sharp = c.max_corner_sharp; L.max_flat = c.max_surface_flat;
+  // ScanRegistration.cpp:653-655: cos(deg2rad(175.0)) ... in double
+  L.cos175 = cos(175.0 * M_PI / 180.0); L.cos5 = cos(5.0 * M_PI / 180.0);
+  L.cos135 = cos(135.0 * M_PI / 180.0); L.cos45 = cos(45.0 * M_PI / 180.0);
+}
+
+int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out) {
+  if (!ctx || !frames || !out || nstreams <= 0 || rows <= 0 || cols <= 0 || !out->n) return fail(ctx, CM_ERR_ARG, "bad argument");
+  for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
+  const cm_config& cfg = ctx->cfg;
+  if (cols > 65535 || cfg.curvature_region < 1 || cfg.curvature_region > 8 || cfg.n_feature_regions < 1 || cfg.n_feature_regions > 16 ||
+      cfg.max_surface_flat < 0 || cfg.max_surface_flat > 8 || cfg.max_corner_sharp < 0)
+    return fail(ctx, CM_ERR_UNSUPPORTED, "scan registration parameters outside the supported range");
+  if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
+  try {
+    cudaSetDevice(cfg.device);
+    cudaStream_t st = ctx->stream;
+    const size_t npts = (size_t)nstreams * rows * cols;
+    ctx->d_frames.reserve(npts * sizeof(cm_point));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_frames.p, frames, npts * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    ScanRegLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.nstreams = nstreams; L.rows = rows; L.cols = cols; L.frames = (const float4*)ctx->d_frames.p;
+    fill_scanreg_params(cfg, L);
+    for (int k = 0; k < 4; k++) {
+      ctx->d_sr_pts[k].reserve((size_t)nstreams * out->cap[k] * sizeof(cm_point));
+      L.out_pts[k] = (float4*)ctx->d_sr_pts[k].p; L.cap[k] = out->cap[k];
+    }
+    ctx->d_sr_n.reserve(sizeof(int) * 5 * nstreams); L.out_n = (int*)ctx->d_sr_n.p;
+    ctx->d_flag.reserve(sizeof(int)); L.overflow = (int*)ctx->d_flag.p;
+    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
+    L.want_idx = (out->idx[0] || out->idx[1] || out->idx[2] || out->idx[3]) ? 1 : 0;
+    if (L.want_idx) for (int k = 0; k < 4; k++) { ctx->d_sr_idx[k].reserve(npts * sizeof(int)); L.out_idx[k] = (int*)ctx->d_sr_idx[k].p; }
+    if (out->cloud) { ctx->d_sr_cloud.reserve(npts * sizeof(cm_point)); ctx->d_sr_ccurv.reserve(npts * sizeof(float));
+                      L.cloud = (float4*)ctx->d_sr_cloud.p; L.cloud_curv = (float*)ctx->d_sr_ccurv.p; }
+    if (out->picked) { ctx->d_sr_picked.reserve(npts); L.picked = (signed char*)ctx->d_sr_picked.p; }
+    if (out->curvature) { ctx->d_sr_curv.reserve(npts * sizeof(float)); L.curvature = (float*)ctx->d_sr_curv.p; }
+    if (out->label) { ctx->d_sr_label.reserve(npts); L.label = (signed char*)ctx->d_sr_label.p; }
+    if (out->scan_ranges) { ctx->d_sr_range.reserve(sizeof(int) * 2 * nstreams * rows); L.scan_range = (int*)ctx->d_sr_range.p; }
+    ctx->scanreg.run(L, st);
+    for (int k = 0; k < 4; k++)
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->pts[k], L.out_pts[k], (size_t)nstreams * out->cap[k] * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->n, L.out_n, sizeof(int) * 5 * nstreams, cudaMemcpyDeviceToHost, st));
+    if (L.want_idx) for (int k = 0; k < 4; k++) if (out->idx[k])
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->idx[k], L.out_idx[k], npts * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out->cloud) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud, L.cloud, npts * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
+    if (out->cloud && out->cloud_curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud_curvature, L.cloud_curv, npts * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out->picked) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->picked, L.picked, npts, cudaMemcpyDeviceToHost, st));
+    if (out->curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->curvature, L.curvature, npts * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out->label) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->label, L.label, npts, cudaMemcpyDeviceToHost, st));
+    if (out->scan_ranges) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->scan_ranges, L.scan_range, sizeof(int) * 2 * nstreams * rows, cudaMemcpyDeviceToHost, st));
+    int ovf = 0;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&ovf, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    if (ovf) return fail(ctx, CM_ERR_CAPACITY, "a feature cloud exceeds its output capacity");
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
 }
 
 int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,

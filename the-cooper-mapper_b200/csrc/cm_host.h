@@ -73,6 +73,27 @@ struct VoxelFilter {
            int* d_overflow, cudaStream_t stream);
 };
 
+// K1/K2: scan registration for organised sweeps (cm_scanreg.cu)
+struct ScanRegLaunch {
+  int nstreams, rows, cols;
+  const float4* frames;                       // device [S][rows][cols]
+  float scan_period, blind_radius, blind_thr, curv_thr, less_flat_leaf;
+  int R, nregions, max_sharp, max_flat;
+  double cos175, cos5, cos135, cos45;
+  float4* out_pts[4]; int cap[4];             // device [S][cap[k]]: sharp, lessSharp, flat, lessFlat
+  int* out_n;                                 // device [S][5]
+  int* overflow;                              // device flag (optional)
+  int want_idx; int* out_idx[4];              // device [S][rows*cols] (parity / diagnostics)
+  float4* cloud; float* cloud_curv;           // optional device [S][rows*cols]
+  signed char* picked; float* curvature; signed char* label;   // optional device [S][rows*cols]
+  int* scan_range;                            // optional device [S][rows][2]
+};
+struct ScanRegistrationGpu {
+  DeviceBuffer ring_count, ring_n, ring_pts[4], ring_idx[4];
+  void run(const ScanRegLaunch& L, cudaStream_t stream);
+};
+size_t scanreg_smem_bytes(int cols);
+
 int debug_math_dims(int op, int* nin, int* nout);
 void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream);
 
