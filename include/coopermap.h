@@ -138,6 +138,41 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
 int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,
                          int* n_out, int cap_out);
 
+/* ---- the scan-to-map STAGE with a device-resident map ------------------------------------------------------------
+ * One context drives nstreams independent LiDAR streams (each with its own pose chain and its own map); every call
+ * below processes one frame of every stream in one batch of launches.  Arrays are indexed [stream]... */
+
+/* Allocate the per-stream maps (replaces `new FeatureMap<PointI>(map_cube_x, map_cube_y, map_cube_z)` +
+ * setupFilterSize, LaserMatcher.cpp:107-116).  Capacities are in points per stream and class. */
+int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_t max_surf_points);
+
+/* LaserMapping::process (LaserMapping.cpp:39-59) for one frame per stream.  odom[s]: /laser_odom_to_init pose;
+ * corner / surf: /laser_cloud_corner_last and /laser_cloud_surf_last as [nstreams][cap_*] with counts n_*[s];
+ * mapped[s]: /aft_mapped_to_init pose.  Steps: transformMerge (LaserMatcher.cpp:333-340), voxel-filter the frame
+ * (:288-301), FeatureMap::update + surround selection (:303-325), ScanMatch::scanMatchScan on the map (:327-331),
+ * transformUpdate (:342-347), FeatureMap::addFeatureCloud (:349-355).  Returns CM_ERR_UNSUPPORTED where the
+ * reference would shift() its cube grid (sensor within 3 cubes of the grid border). */
+int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                            const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
+
+/* Scan registration + mapping in one call: frames[s][row][col] organised sweeps -> mapped poses.  The less-sharp and
+ * less-flat clouds of cm_scanreg_organised feed cm_mapping_process without leaving the device.  _dev: `frames` is a
+ * DEVICE pointer (inputs already resident in HBM); poses and stats stay host arrays. */
+int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
+                          cm_match_stats* stats);
+int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
+                         cm_match_stats* stats);
+
+/* FeatureMap::addFeatureCloud(cornerCloud, surfCloud, tf) (FeatureMap.h:219-230): transform by tf[s], push into the
+ * 50 m cubes, merge per voxel (= downsizeValidCloud, :289-306, restricted to the voxels that received points). */
+int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner, int cap_corner, const cm_point* surf,
+                       const int* n_surf, int cap_surf, const cm_iso* tf);
+
+/* Every resident point of one stream's map (cls 0 corner, 1 surf) with the index of its cube (i + j*W + k*W*H), in
+ * storage order; *n_out is the total even when it exceeds cap.  Sorting by (cube, voxel) gives the reference's
+ * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
+int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
+
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.
  * op: 0 QR-solve 6x6 (42 -> 6 floats), 1 QR-solve 5x3 (20 -> 3), 2 eig 3x3 (6 -> 12), 3 eig 6x6 (36 -> 42),

@@ -1,0 +1,96 @@
+"""GPU parity: device-resident map (insert + voxel merge), the mapping stage and the full pipeline vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MAP_CFG = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+ORACLE_MAP = dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)
+
+
+def _same(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def _frames(synth, sc, n, model="VLP-16", cols=900, seed=100, speed=0.5):
+    out = []
+    for k, (R, t) in enumerate(synth.trajectory(n, speed=speed)):
+        out.append((R, t, synth.simulate_scan(sc, R, t, model, seed=seed + k, cols=cols)))
+    return out
+
+
+def test_map_insert_matches_oracle_cubes(cmb, oracle, synth):
+    sc = synth.make_scene(seed=51, extent=70.0, n_boxes=20, n_poles=10)
+    mc, ms = synth.sample_map(sc, 0.23, seed=52)          # denser than the map leaf: many points per voxel
+    rng = np.random.default_rng(1)
+    ctx = cmb.Context(**MAP_CFG)
+    ctx.mapping_create(1, 100000, 1500000)
+    om = oracle.Mapping(map_params=ORACLE_MAP)
+    om.map_update(np.zeros(3, np.float32))                # valid cubes around the origin (the GPU merges everywhere)
+    R, t = synth.pose_matrix(0.3, 0.02, -0.01, (1.0, -2.0, 0.3))
+    for part in range(3):                                 # three inserts: later ones merge into resident voxels
+        c = mc[rng.permutation(len(mc))[: len(mc) // 2]]; s = ms[rng.permutation(len(ms))[: len(ms) // 3]]
+        ctx.map_insert([c], [s], [(R, t)])
+        om.map_add(c, s, R, t)
+    for cls, which in ((0, 4), (1, 5)):
+        g, _ = ctx.map_export_sorted(0, cls)
+        assert _same(g, om.cloud(which))
+
+
+def test_mapping_stage_sequence_bit_exact(cmb, oracle, synth):
+    sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
+    S = 3
+    ctx = cmb.Context(**MAP_CFG)
+    ctx.mapping_create(S, 100000, 600000)
+    oms = [oracle.Mapping(map_params=ORACLE_MAP) for _ in range(S)]
+    frames = [_frames(synth, sc, 6, seed=100 + 50 * s, speed=0.4 + 0.2 * s) for s in range(S)]
+    for k in range(6):
+        odoms, corners, surfs = [], [], []
+        for s in range(S):
+            R, t, fr = frames[s][k]
+            f = oracle.scanreg_organised(fr)
+            odoms.append((R.astype(np.float32), (t + np.array([0.02, -0.02, 0.01]) * k).astype(np.float32)))
+            corners.append(f["lessSharp"]); surfs.append(f["lessFlat"])
+        isos, stats = ctx.mapping_process(odoms, corners, surfs)
+        for s in range(S):
+            oR, ot, ost = oms[s].process(odoms[s][0], odoms[s][1], corners[s], surfs[s])
+            gR, gt = isos[s]
+            assert stats[s]["iterations"] == ost["iterations"], (k, s, stats[s], ost)
+            assert (stats[s]["status"] == 1) == bool(ost["tooFewRef"])
+            assert stats[s]["rows"] == ost["rows"]
+            assert np.all(np.abs(gt - ot) <= 1e-4) and np.all(np.abs(gR - oR) <= 1e-5)      # north-star tolerance
+            assert np.array_equal(gR, oR) and np.array_equal(gt, ot)                        # in practice: bit-identical
+    for s in range(S):
+        for cls, which in ((0, 4), (1, 5)):
+            g, _ = ctx.map_export_sorted(s, cls)
+            assert _same(g, oms[s].cloud(which))
+    assert stats[0]["converged"]
+
+
+def test_pipeline_step_equals_scanreg_plus_mapping(cmb, oracle, synth):
+    sc = synth.make_scene(seed=61, extent=40.0, n_boxes=12, n_poles=10)
+    S = 2
+    ctx = cmb.Context(**MAP_CFG)
+    ctx.mapping_create(S, 100000, 600000)
+    oms = [oracle.Mapping(map_params=ORACLE_MAP) for _ in range(S)]
+    seqs = [_frames(synth, sc, 4, seed=300 + 40 * s, cols=720) for s in range(S)]
+    for k in range(4):
+        fr = np.stack([seqs[s][k][2] for s in range(S)])
+        odoms = [(seqs[s][k][0].astype(np.float32), seqs[s][k][1].astype(np.float32)) for s in range(S)]
+        isos, stats = ctx.pipeline_step(fr, odoms)
+        for s in range(S):
+            f = oracle.scanreg_organised(fr[s])
+            oR, ot, ost = oms[s].process(odoms[s][0], odoms[s][1], f["lessSharp"], f["lessFlat"])
+            assert np.array_equal(isos[s][0], oR) and np.array_equal(isos[s][1], ot)
+            assert stats[s]["iterations"] == ost["iterations"]
+
+
+def test_lasermapping_mirror_and_shift_unsupported(cmb, oracle, synth):
+    sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
+    lm = cmb.LaserMapping(max_corner_points=50000, max_surf_points=300000, **MAP_CFG)
+    R, t, fr = _frames(synth, sc, 1)[0]
+    f = oracle.scanreg_organised(fr)
+    gR, gt = lm.process(R.astype(np.float32), t.astype(np.float32), f["lessSharp"], f["lessFlat"])
+    assert lm.last_stats["status"] == 1                      # empty map: "reference cloud points too few"
+    with pytest.raises(cmb.CoopermapError):                  # 200 m up: the reference would shift() its cube grid
+        lm.process(R.astype(np.float32), np.array([0, 0, 200], np.float32), f["lessSharp"], f["lessFlat"])

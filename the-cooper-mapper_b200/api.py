@@ -129,6 +129,86 @@ class Context:
         self._check(self.L.cm_debug_math_host(self.h, C.c_int(op), _ptr(a), C.c_size_t(len(a)), _ptr(out)))
         return out
 
+    # ---- mapping stage (device-resident map) -------------------------------------------------------------------------
+    def mapping_create(self, nstreams, max_corner_points=200000, max_surf_points=2000000):
+        self.nstreams = int(nstreams)
+        self._check(self.L.cm_mapping_create(self.h, C.c_int(nstreams), C.c_size_t(max_corner_points), C.c_size_t(max_surf_points)))
+
+    @staticmethod
+    def _pack_isos(isos):
+        a = np.empty((len(isos), 12), np.float32)
+        for i, (R, t) in enumerate(isos):
+            a[i, :9] = np.asarray(R, np.float32).ravel(); a[i, 9:] = np.asarray(t, np.float32).ravel()
+        return a
+
+    @staticmethod
+    def _pack_clouds(clouds):
+        n = np.array([len(c) for c in clouds], np.int32)
+        cap = max(int(n.max()), 1)
+        buf = np.zeros((len(clouds), cap, 4), np.float32)
+        for i, c in enumerate(clouds):
+            buf[i, :len(c)] = _f32(c, 4)
+        return buf, n, cap
+
+    def _unpack_results(self, mapped, stats):
+        out_iso = [(mapped[i, :9].reshape(3, 3).copy(), mapped[i, 9:].copy()) for i in range(len(mapped))]
+        out_st = [dict(status=s.status, ret=bool(s.ret), converged=bool(s.converged), degenerate=bool(s.degenerate),
+                       iterations=s.iterations, rows=s.rows, line=s.line_matches, plane=s.plane_matches, score=s.score)
+                  for s in stats]
+        return out_iso, out_st
+
+    def mapping_process(self, odoms, corners, surfs):
+        """LaserMapping::process for one frame per stream.  odoms: [(R, t)], corners / surfs: lists of (n, 4) clouds."""
+        S = self.nstreams
+        od = self._pack_isos(odoms)
+        cb, cn, ccap = self._pack_clouds(corners); sb, sn, scap = self._pack_clouds(surfs)
+        mapped = np.empty((S, 12), np.float32); stats = (MatchStats * S)()
+        self._check(self.L.cm_mapping_process_host(self.h, _ptr(od), _ptr(cb), _ptr(cn), C.c_int(ccap), _ptr(sb), _ptr(sn),
+                                                   C.c_int(scap), _ptr(mapped), stats))
+        return self._unpack_results(mapped, stats)
+
+    def pipeline_step(self, frames, odoms):
+        """Scan registration + mapping for one organised sweep per stream: frames (S, rows, cols, 4)."""
+        fr = _f32(frames)
+        S, rows, cols = fr.shape[:3]
+        od = self._pack_isos(odoms)
+        mapped = np.empty((S, 12), np.float32); stats = (MatchStats * S)()
+        self._check(self.L.cm_pipeline_step_host(self.h, _ptr(fr), C.c_int(rows), C.c_int(cols), _ptr(od), _ptr(mapped), stats))
+        return self._unpack_results(mapped, stats)
+
+    def pipeline_step_dev(self, frames_dev_ptr, rows, cols, odoms_packed, mapped_out, stats_out):
+        """Same with the frames already resident in device memory (raw pointer); pre-packed host arrays, no allocation."""
+        return self._check(self.L.cm_pipeline_step_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols),
+                                                       _ptr(odoms_packed), _ptr(mapped_out), stats_out))
+
+    def pipeline_step_packed(self, frames, odoms_packed, mapped_out, stats_out):
+        fr = frames
+        return self._check(self.L.cm_pipeline_step_host(self.h, _ptr(fr), C.c_int(fr.shape[1]), C.c_int(fr.shape[2]),
+                                                        _ptr(odoms_packed), _ptr(mapped_out), stats_out))
+
+    def map_insert(self, corners, surfs, tfs):
+        """FeatureMap::addFeatureCloud per stream."""
+        cb, cn, ccap = self._pack_clouds(corners); sb, sn, scap = self._pack_clouds(surfs)
+        tf = self._pack_isos(tfs)
+        self._check(self.L.cm_map_insert_host(self.h, _ptr(cb), _ptr(cn), C.c_int(ccap), _ptr(sb), _ptr(sn), C.c_int(scap), _ptr(tf)))
+
+    def map_export(self, stream, cls):
+        """All resident points of one stream's map (cls 0 corner / 1 surf) + cube index, in storage order."""
+        n = C.c_size_t(0)
+        self._check(self.L.cm_map_export_host(self.h, C.c_int(stream), C.c_int(cls), None, None, C.c_size_t(0), C.byref(n)))
+        pts = np.empty((max(n.value, 1), 4), np.float32); cube = np.empty(max(n.value, 1), np.int32)
+        self._check(self.L.cm_map_export_host(self.h, C.c_int(stream), C.c_int(cls), _ptr(pts), _ptr(cube), C.c_size_t(len(pts)), C.byref(n)))
+        return pts[:n.value].copy(), cube[:n.value].copy()
+
+    def map_export_sorted(self, stream, cls):
+        """Export ordered like the reference's cube clouds: by cube index, then by voxel (z, y, x)."""
+        pts, cube = self.map_export(stream, cls)
+        leaf = self.cfg.map_filter_corner if cls == 0 else self.cfg.map_filter_surf
+        inv = np.float32(1.0) / np.float32(leaf)
+        v = np.floor(pts[:, :3] * inv).astype(np.int64)
+        order = np.lexsort((v[:, 0], v[:, 1], v[:, 2], cube))
+        return pts[order], cube[order]
+
     # ---- scan registration -----------------------------------------------------------------------------------------
     def scanreg_organised(self, frames, debug=False):
         """frames: (S, rows, cols, 4) or (rows, cols, 4) organised sweeps -> list of per-stream dicts with the four
@@ -233,6 +313,23 @@ class Context:
             self.h, _ptr(rc_), C.c_size_t(len(rc_)), _ptr(rs), C.c_size_t(len(rs)), _ptr(c), C.c_size_t(len(c)), _ptr(s),
             C.c_size_t(len(s)), _ptr(iso), C.byref(st)))
         return iso[:9].reshape(3, 3).copy(), iso[9:].copy(), rc, st
+
+
+class LaserMapping:
+    """Mirror of lidar_slam::LaserMapping (LaserMapping.h / LaserMatcher.h): the scan-to-map stage with its own map.
+
+    process(odom, corner, surf) -> (R, t) of /aft_mapped_to_init.  One instance = one LiDAR stream; use
+    Context.mapping_process directly to drive many streams in one batch."""
+
+    def __init__(self, ctx=None, max_corner_points=200000, max_surf_points=2000000, **cfg):
+        self.ctx = ctx or Context(**cfg)
+        self.ctx.mapping_create(1, max_corner_points, max_surf_points)
+        self.last_stats = None
+
+    def process(self, odom_R, odom_t, laserCloudCornerLast, laserCloudSurfLast):
+        isos, stats = self.ctx.mapping_process([(odom_R, odom_t)], [laserCloudCornerLast], [laserCloudSurfLast])
+        self.last_stats = stats[0]
+        return isos[0]
 
 
 class ScanMatch:

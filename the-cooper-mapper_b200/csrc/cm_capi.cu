@@ -1,6 +1,5 @@
 // cm_capi.cu -- the extern "C" boundary declared in include/coopermap.h.
-#include "../../include/coopermap.h"
-#include "cm_host.h"
+#include "cm_ctx.h"
 #include "cm_math.h"
 #include <math.h>
 #include <stdio.h>
@@ -10,25 +9,8 @@
 
 namespace cm {
 unsigned long long g_launch_count = 0;
-}
 
-using namespace cm;
-
-struct cm_ctx {
-  cm_config cfg;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  // scratch for the host-buffer entry points
-  DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
-  DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
-  GridStorage grid_a, grid_b;
-  VoxelFilter voxel;
-  ScanRegistrationGpu scanreg;
-  DeviceBuffer d_frames, d_sr_pts[4], d_sr_idx[4], d_sr_n, d_sr_cloud, d_sr_ccurv, d_sr_picked, d_sr_curv, d_sr_label, d_sr_range;
-  DeviceBuffer d_vin, d_vout, d_vn_in, d_vn_out, d_flag;
-};
-
-static MatchParamsDev dev_params(const cm_config& c) {
+MatchParamsDev dev_params(const cm_config& c) {
   MatchParamsDev p;
   p.max_iterations = c.max_iterations;
   p.delta_t_abort = c.delta_t_abort; p.delta_r_abort = c.delta_r_abort;
@@ -36,16 +18,14 @@ static MatchParamsDev dev_params(const cm_config& c) {
   p.min_ref_corner = 50; p.min_ref_surf = 100; p.min_rows = 50; p.eig_threshold = 100.f;
   return p;
 }
-
-static int fail(cm_ctx* ctx, int code, const std::string& msg) {
+int ctx_fail(cm_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
 }
-#define CM_CUDA_CHECK(ctx, expr)                                                                         \
-  do {                                                                                                   \
-    cudaError_t e__ = (expr);                                                                            \
-    if (e__ != cudaSuccess) return fail(ctx, CM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
+}  // namespace cm
+
+using namespace cm;
+static int fail(cm_ctx* ctx, int code, const std::string& msg) { return ctx_fail(ctx, code, msg); }
 
 extern "C" {
 
@@ -115,7 +95,9 @@ int cm_knn5_host(cm_ctx* ctx, const cm_point* map, size_t n_map, float cell, flo
   return CM_OK;
 }
 
-static void fill_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out) {
+}  // extern "C"
+namespace cm {
+void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out) {
   out->converged = (st.flags & CM_F_CONVERGED) ? 1 : 0;
   out->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
   out->iterations = st.iterations;
@@ -135,6 +117,8 @@ static void fill_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm
     }
   }
 }
+}  // namespace cm
+extern "C" {
 
 int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, const cm_point* ref_surf, size_t nrs,
                             const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, cm_pose* pose,
@@ -208,7 +192,7 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2];
     pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
     cm_match_stats local;
-    fill_stats(cfg, hs, nc + ns, &local);
+    fill_match_stats(cfg, hs, nc + ns, &local);
     if (stats) *stats = local;
     return local.status;
   } catch (const CudaError& e) {
@@ -241,7 +225,9 @@ int cm_match_stateless_iso_host(cm_ctx* ctx, const cm_point* ref_corner, size_t 
   return rc;
 }
 
-static void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
+}  // extern "C"
+namespace cm {
+void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
   L.scan_period = c.scan_period; L.blind_radius = c.blind_radius;
   // ScanRegistration.cpp:27,46: blindThreshold = cos(deg2rad(blindDegreeThreshold)), deg2rad(float) math_utils.h:38
   float rad = (float)(c.blind_degree_threshold * M_PI / 180.0);
@@ -252,6 +238,8 @@ static void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
   L.cos175 = cos(175.0 * M_PI / 180.0); L.cos5 = cos(5.0 * M_PI / 180.0);
   L.cos135 = cos(135.0 * M_PI / 180.0); L.cos45 = cos(45.0 * M_PI / 180.0);
 }
+}  // namespace cm
+extern "C" {
 
 int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out) {
   if (!ctx || !frames || !out || nstreams <= 0 || rows <= 0 || cols <= 0 || !out->n) return fail(ctx, CM_ERR_ARG, "bad argument");

@@ -1,0 +1,54 @@
+// cm_ctx.h -- the opaque context behind include/coopermap.h (internal).
+#pragma once
+#include "../../include/coopermap.h"
+#include "cm_host.h"
+#include <string>
+#include <vector>
+
+namespace cm {
+
+// Host mirror of the per-stream state LaserMatcher keeps (LaserMatcher.h:100-117): poses + the cube lattice position.
+struct HostIso { float R[9]; float t[3]; };
+struct MappingStream {
+  HostIso mappedLast, mappedNew, odomLast;
+  int origin[3];   // _cubeOriginWidth/Height/Depth
+  int cur[3];      // _curCubeWidth/Height/Depth
+};
+
+}  // namespace cm
+
+struct cm_ctx {
+  cm_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // scratch for the host-buffer entry points
+  cm::DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
+  cm::DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
+  cm::GridStorage grid_a, grid_b;
+  cm::VoxelFilter voxel;
+  cm::ScanRegistrationGpu scanreg;
+  cm::DeviceBuffer d_frames, d_sr_pts[4], d_sr_idx[4], d_sr_n, d_sr_cloud, d_sr_ccurv, d_sr_picked, d_sr_curv, d_sr_label, d_sr_range;
+  cm::DeviceBuffer d_vin, d_vout, d_vn_in, d_vn_out, d_flag;
+  // mapping stage (cm_mapping.cu)
+  int map_streams = 0;
+  cm::DeviceMap map;
+  std::vector<cm::MappingStream> mstreams;
+  cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
+  int m_cap_corner = 0, m_cap_surf = 0;
+  // pipeline (scan registration -> mapping), cm_mapping.cu
+  cm::DeviceBuffer p_frames, p_pts[4], p_n;
+  int p_cap = 0;
+};
+
+namespace cm {
+MatchParamsDev dev_params(const cm_config& c);
+int ctx_fail(cm_ctx* ctx, int code, const std::string& msg);
+void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L);
+void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out);
+}  // namespace cm
+
+#define CM_CUDA_CHECK(ctx, expr)                                                                                    \
+  do {                                                                                                              \
+    cudaError_t e__ = (expr);                                                                                       \
+    if (e__ != cudaSuccess) return cm::ctx_fail(ctx, CM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)

@@ -24,16 +24,32 @@ struct __align__(16) CellEntry {
   unsigned int count;
 };
 
-// Read-only view of one grid (one map cloud of one stream).
+// The reference's cube lattice around the sensor (FeatureMap.h:232-254, 308-352, 475-487): which 50 m cubes are
+// "valid" (searched).  Uploaded by the host every frame; NULL for stateless clouds (everything is searched).
+struct CubeWindow {
+  int origin[3];              // _cubeOriginWidth/Height/Depth
+  int dims[3];                // _cubeWidth/Height/Depth
+  int w0[3];                  // lowest cube index of the 7x7x7 window (_curCube* - 3)
+  float cube_size;            // _worldCubeSize
+  unsigned char active[343];  // cube in _cubeValidInd
+  unsigned char interior[343];// cube and its 26 neighbours all active -> no per-point test needed
+};
+
+// Read-only view of one grid (one map cloud of one stream).  A point p lives in voxel v = floor(p * inv_leaf)
+// (PCL's voxel lattice) and in cell floor_div(v, kdiv); stateless clouds use kdiv = 1 and inv_leaf = 1 / cell.
 struct GridView {
   const CellEntry* entries;   // open addressing, linear probing, capacity = mask + 1 (power of two)
   const float4* pts;          // x, y, z, w  (w = original index bits for stateless clouds, intensity for the map)
   unsigned int mask;
-  float ox, oy, oz;           // lattice origin
-  float cell, inv_cell;       // cell edge and 1/edge (float, computed once on the host)
-  int npts;                   // number of points in the cloud (the reference gates on it, ScanMatch.cpp:57-58)
+  float inv_leaf;             // 1 / leaf (float, computed once on the host like PCL's inverse_leaf_size_)
+  int kdiv;                   // cell edge = kdiv * leaf
+  float cell;                 // cell edge in metres
+  int npts;                   // number of searchable points (the reference gates on it, ScanMatch.cpp:57-58)
   int max_level;              // last shell to visit so that (max_level + 0.48) * cell >= sqrt(gate)
+  const CubeWindow* window;   // NULL: no cube filtering
 };
+
+__host__ __device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
 __host__ __device__ __forceinline__ unsigned long long pack_cell(int x, int y, int z) {
   const unsigned long long B = 1ull << 20;
@@ -44,7 +60,6 @@ __host__ __device__ __forceinline__ unsigned int hash_cell(unsigned long long k)
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (unsigned int)k;
 }
-__device__ __forceinline__ int cell_coord(float p, float o, float inv) { return (int)floorf((p - o) * inv); }
 
 __device__ __forceinline__ bool grid_probe(const GridView& g, int x, int y, int z, unsigned int* start, unsigned int* count) {
   unsigned long long key = pack_cell(x, y, z);
@@ -83,13 +98,28 @@ __device__ __forceinline__ void top5_insert(Top5& t, float d, int idx, int slot)
   t.d[0] = c0 ? d : t.d[0];            t.idx[0] = c0 ? idx : t.idx[0];            t.slot[0] = c0 ? slot : t.slot[0];
 }
 
+// worldToCube (FeatureMap.h:475-487) -> index into the 7x7x7 window, -1 outside it
+__device__ __forceinline__ int window_index(const CubeWindow& w, float x, float y, float z) {
+  int i = (int)(roundf(x / w.cube_size) + (float)w.origin[0]) - w.w0[0];
+  int j = (int)(roundf(y / w.cube_size) + (float)w.origin[1]) - w.w0[1];
+  int k = (int)(roundf(z / w.cube_size) + (float)w.origin[2]) - w.w0[2];
+  if (i < 0 || i > 6 || j < 0 || j > 6 || k < 0 || k > 6) return -1;
+  return (i * 7 + j) * 7 + k;
+}
+
 // kOrigIdx: tie-break index = original cloud index stored in pts[].w (stateless clouds); otherwise the pool slot.
+// filter: test every candidate's cube against the active window (only for queries near an inactive cube).
 template <bool kOrigIdx>
-__device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, Top5& best) {
+__device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, bool filter,
+                                          Top5& best) {
   unsigned int start, count;
   if (!grid_probe(g, x, y, z, &start, &count)) return;
   for (unsigned int j = start; j < start + count; j++) {
     float4 p = __ldg(g.pts + j);
+    if (filter) {
+      int wi = window_index(*g.window, p.x, p.y, p.z);
+      if (wi < 0 || !g.window->active[wi]) continue;
+    }
     float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
     float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     top5_insert(best, d, kOrigIdx ? __float_as_int(p.w) : (int)j, (int)j);
@@ -101,19 +131,28 @@ __device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z
 template <bool kOrigIdx>
 __device__ __forceinline__ void knn5_search(const GridView& g, float qx, float qy, float qz, Top5& best) {
   top5_init(best);
-  float fx = (qx - g.ox) * g.inv_cell, fy = (qy - g.oy) * g.inv_cell, fz = (qz - g.oz) * g.inv_cell;
+  float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
   float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
   // keep the cast defined for absurd coordinates
   if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return;
-  int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+  const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
+  const int cx = floor_div(vx, g.kdiv), cy = floor_div(vy, g.kdiv), cz = floor_div(vz, g.kdiv);
+  const float half = 0.5f * (float)g.kdiv;
   // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
-  int lx = cx + ((fx - flx) < 0.5f ? -1 : 0), ly = cy + ((fy - fly) < 0.5f ? -1 : 0), lz = cz + ((fz - flz) < 0.5f ? -1 : 0);
+  int lx = cx + (((float)(vx - cx * g.kdiv) + (fx - flx)) < half ? -1 : 0);
+  int ly = cy + (((float)(vy - cy * g.kdiv) + (fy - fly)) < half ? -1 : 0);
+  int lz = cz + (((float)(vz - cz * g.kdiv) + (fz - flz)) < half ? -1 : 0);
+  bool filter = false;
+  if (g.window) {
+    int wi = window_index(*g.window, qx, qy, qz);
+    filter = (wi < 0) || !g.window->interior[wi];
+  }
 #pragma unroll
   for (int dz = 0; dz < 2; dz++)
 #pragma unroll
     for (int dy = 0; dy < 2; dy++)
 #pragma unroll
-      for (int dx = 0; dx < 2; dx++) scan_cell<kOrigIdx>(g, lx + dx, ly + dy, lz + dz, qx, qy, qz, best);
+      for (int dx = 0; dx < 2; dx++) scan_cell<kOrigIdx>(g, lx + dx, ly + dy, lz + dz, qx, qy, qz, filter, best);
   for (int L = 1; L <= g.max_level; L++) {
     float r = ((float)(L - 1) + 0.48f) * g.cell;   // radius guaranteed by the previous level
     if (best.d[4] < r * r) return;
@@ -122,10 +161,10 @@ __device__ __forceinline__ void knn5_search(const GridView& g, float qx, float q
       for (int dy = 0; dy < n; dy++) {
         bool shell_row = (dz == 0 || dz == n - 1 || dy == 0 || dy == n - 1);
         if (shell_row) {
-          for (int dx = 0; dx < n; dx++) scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, best);
+          for (int dx = 0; dx < n; dx++) scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
         } else {
-          scan_cell<kOrigIdx>(g, lx - L, ly - L + dy, lz - L + dz, qx, qy, qz, best);
-          scan_cell<kOrigIdx>(g, lx - L + n - 1, ly - L + dy, lz - L + dz, qx, qy, qz, best);
+          scan_cell<kOrigIdx>(g, lx - L, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
+          scan_cell<kOrigIdx>(g, lx - L + n - 1, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
         }
       }
   }

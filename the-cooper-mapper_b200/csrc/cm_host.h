@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <string>
+#include <vector>
 #include "cm_match.cuh"
 
 namespace cm {
@@ -71,6 +72,33 @@ struct VoxelFilter {
   DeviceBuffer box, keys_a, keys_b, vals_a, vals_b, flags, rank, seg_first, temp;
   void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out, int cap_out,
            int* d_overflow, cudaStream_t stream);
+};
+
+// K7: device-resident local map (cm_map.cu)
+struct MapClassDev {            // one class (corner / surf) of one stream, lives in device memory
+  CellEntry* entries; unsigned int* cellcap; unsigned int* pending; unsigned int mask;
+  float4* pts; unsigned int pool_cap; unsigned int* cursor; int* total;
+  int* cube_count;              // points per 50 m cube [W*H*D]
+  float leaf, inv_leaf; int kdiv;
+  float cube_size; int dims[3]; int origin[3];
+};
+struct MapConfig {
+  size_t max_corner, max_surf;  // capacity in points per stream
+  float leaf_corner, leaf_surf; // map_filter_corner / map_filter_surf
+  int kdiv_corner, kdiv_surf;   // search cell = kdiv voxels
+  float cube_size; int dims[3]; int origin[3];
+};
+struct DeviceMap {
+  int nstreams = 0;
+  MapConfig cfg;
+  DeviceBuffer entries[2], cellcap[2], pending_cnt[2], pts[2], cube_count[2], cursor[2], dev[2], views[2];
+  DeviceBuffer windows, flags, n_pending, world, keys_a, keys_b, vals_a, vals_b, pending, temp;
+  unsigned int table_cap[2] = {0, 0}, pool_cap[2] = {0, 0};
+  void create(int nstreams, const MapConfig& c, cudaStream_t stream);
+  void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream);   // also refreshes the GridViews
+  // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
+  void insert(int cls, const float4* d_pts, const int* d_n, int cap, const MatchState* d_state, const float* d_tf, cudaStream_t stream);
+  size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);
 };
 
 // K1/K2: scan registration for organised sweeps (cm_scanreg.cu)

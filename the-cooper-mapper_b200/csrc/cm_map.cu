@@ -1,0 +1,316 @@
+// cm_map.cu -- K7: device-resident local feature map (a GPU voxel hash) with on-device insertion + voxel merge.
+//
+// Replaces FeatureMap<PointT>::addFeatureCloud / pushCornerPoint / pushSurfPoint / downsizeValidCloud
+// (L_SLAM/src/util/FeatureMap.h:189-230, 289-306) and the map side of getSurroundFeature (:256-265).
+// Reference semantics restated: a point pushed into the map goes to the 50 m cube round(p / 50) + origin
+// (:475-487); after every insert each valid cube is re-filtered with pcl::VoxelGrid, i.e. within a cube all points
+// that share the voxel floor(p * inv_leaf) are replaced by their mean (old centroid + new points, equal weight,
+// old first).  Voxels that receive no new point keep their single point unchanged, so only voxels hit by the new
+// cloud need work: O(inserted points) instead of the reference's O(map) re-sort.
+//
+// Layout: one open-addressing table of cells (cell = kdiv^3 voxels, CellEntry{key, start, count}) over a point pool
+// with a bump allocator; a cell owns a contiguous block of `cellcap` slots and is moved to a larger block when it
+// overflows (the old block is abandoned; compaction is left to a rebuild).  The same table is what the matcher's
+// 5-NN search reads (cm_device.cuh), so an insert is immediately searchable.
+//
+// Known deviations (documented in DESIGN.md): (1) points landing in a cube that is outside the valid window are
+// merged immediately, the reference leaves them unmerged until the cube becomes valid (needs ranges > ~106 m);
+// (2) FeatureMap::shift (the grid re-centring when the sensor comes within 3 cubes of the grid border, i.e. after
+// ~3 km / +-125 m vertically) is not implemented: cm_map_update reports CM_ERR_UNSUPPORTED.
+#include "cm_host.h"
+#include "cm_math.h"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace cm {
+
+#define CM_MAP_PAD 0xFFFFFFFFFFFFFFFFull
+#define CM_VOX_BIAS 65536   // voxel coordinates must stay within +-65536 (17 bits per axis)
+
+__device__ __forceinline__ int world_to_cube_axis(float x, float cube_size, int origin) { return (int)(roundf(x / cube_size) + (float)origin); }
+
+// ---- 1. transform + key ------------------------------------------------------------------------------------------
+// key = stream (8 bits) | cube parity (3 bits) | voxel z, y, x (17 bits each, biased)
+__global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int nstreams,
+                               const MatchState* __restrict__ state, const float* __restrict__ tf_override, MapClassDev* maps,
+                               float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
+                               int* __restrict__ flags) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)nstreams * cap) return;
+  int s = (int)(g / cap), i = (int)(g - (size_t)s * cap);
+  unsigned long long key = CM_MAP_PAD;
+  if (i < n_pts[s]) {
+    const MapClassDev& m = maps[s];
+    float4 p = pts[g];
+    float R[9], t[3];
+    if (tf_override) { for (int k = 0; k < 9; k++) R[k] = tf_override[s * 12 + k]; for (int k = 0; k < 3; k++) t[k] = tf_override[s * 12 + 9 + k]; }
+    else { for (int k = 0; k < 9; k++) R[k] = state[s].R[k]; for (int k = 0; k < 3; k++) t[k] = state[s].pose[3 + k]; }
+    float4 w;
+    transform_point(R, t, p.x, p.y, p.z, &w.x, &w.y, &w.z);   // transformPointCloud, transform_utils.h:601-614
+    w.w = p.w;
+    world[g] = w;
+    // non-finite points: PCL's filter drops them from the cube (is_dense == false branch); dropped here at insert
+    if (isfinite(w.x) && isfinite(w.y) && isfinite(w.z)) {
+      int ci = world_to_cube_axis(w.x, m.cube_size, m.origin[0]);
+      int cj = world_to_cube_axis(w.y, m.cube_size, m.origin[1]);
+      int ck = world_to_cube_axis(w.z, m.cube_size, m.origin[2]);
+      if (ci >= 0 && ci < m.dims[0] && cj >= 0 && cj < m.dims[1] && ck >= 0 && ck < m.dims[2]) {   // isIndexValid, :102-108
+        float vx = floorf(w.x * m.inv_leaf), vy = floorf(w.y * m.inv_leaf), vz = floorf(w.z * m.inv_leaf);
+        if (fabsf(vx) < (float)CM_VOX_BIAS && fabsf(vy) < (float)CM_VOX_BIAS && fabsf(vz) < (float)CM_VOX_BIAS) {
+          unsigned long long kx = (unsigned long long)((int)vx + CM_VOX_BIAS), ky = (unsigned long long)((int)vy + CM_VOX_BIAS),
+                             kz = (unsigned long long)((int)vz + CM_VOX_BIAS);
+          unsigned long long par = (unsigned long long)((ci & 1) | ((cj & 1) << 1) | ((ck & 1) << 2));
+          key = ((unsigned long long)s << 54) | (par << 51) | (kz << 34) | (ky << 17) | kx;
+        } else {
+          atomicExch(flags, 1);   // outside the supported voxel range
+        }
+      }
+    }
+  }
+  keys[g] = key;
+  vals[g] = (unsigned int)g;
+}
+
+// ---- 2. one thread per (stream, cube, voxel) group: merge with the resident point or queue an append ---------------
+struct PendingAdd { float4 p; unsigned int entry; int stream; int cube; };
+
+__device__ __forceinline__ unsigned int map_find_or_create_cell(MapClassDev& m, int cx, int cy, int cz) {
+  unsigned long long key = pack_cell(cx, cy, cz);
+  unsigned int h = hash_cell(key) & m.mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&m.entries[h].key, CM_EMPTY_KEY, key);
+    if (prev == CM_EMPTY_KEY || prev == key) return h;
+    h = (h + 1) & m.mask;
+  }
+}
+
+__global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals, size_t n,
+                                 const float4* __restrict__ world, MapClassDev* maps, PendingAdd* __restrict__ pending,
+                                 unsigned int* __restrict__ n_pending, unsigned int pending_cap, int* __restrict__ flags) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const unsigned long long key = keys[g];
+  if (key == CM_MAP_PAD) return;
+  if (g > 0 && keys[g - 1] == key) return;   // not the head of its group
+  const int s = (int)(key >> 54);
+  MapClassDev& m = maps[s];
+  const float4 first = world[vals[g]];
+  const int vx = (int)floorf(first.x * m.inv_leaf), vy = (int)floorf(first.y * m.inv_leaf), vz = (int)floorf(first.z * m.inv_leaf);
+  const int ci = world_to_cube_axis(first.x, m.cube_size, m.origin[0]), cj = world_to_cube_axis(first.y, m.cube_size, m.origin[1]),
+            ck = world_to_cube_axis(first.z, m.cube_size, m.origin[2]);
+  const unsigned int e = map_find_or_create_cell(m, floor_div(vx, m.kdiv), floor_div(vy, m.kdiv), floor_div(vz, m.kdiv));
+  // resident point(s) of this voxel in this cube come first in the sum (they precede the pushed points in the cube cloud)
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  int cnt = 0, keep = -1;
+  const unsigned int start = m.entries[e].start, count = m.entries[e].count;
+  for (unsigned int j = 0; j < count; j++) {
+    float4 q = m.pts[start + j];
+    if ((int)floorf(q.x * m.inv_leaf) == vx && (int)floorf(q.y * m.inv_leaf) == vy && (int)floorf(q.z * m.inv_leaf) == vz &&
+        world_to_cube_axis(q.x, m.cube_size, m.origin[0]) == ci && world_to_cube_axis(q.y, m.cube_size, m.origin[1]) == cj &&
+        world_to_cube_axis(q.z, m.cube_size, m.origin[2]) == ck) {
+      sx += q.x; sy += q.y; sz += q.z; si += q.w; cnt++;
+      if (keep < 0) keep = (int)j;
+      else atomicExch(flags + 1, 1);   // two resident points in one voxel (rounding drift): not merged here, only reported
+    }
+  }
+  for (size_t j = g; j < n && keys[j] == key; j++) {
+    float4 q = world[vals[j]];
+    sx += q.x; sy += q.y; sz += q.z; si += q.w; cnt++;
+  }
+  const float c = (float)cnt;
+  const float4 cen = make_float4(sx / c, sy / c, sz / c, si / c);
+  if (keep >= 0) {
+    m.pts[start + keep] = cen;
+  } else {
+    unsigned int slot = atomicAdd(n_pending, 1u);
+    if (slot < pending_cap) {
+      PendingAdd pa; pa.p = cen; pa.entry = e; pa.stream = s; pa.cube = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
+      pending[slot] = pa;
+      atomicAdd(&m.pending[e], 1u);
+    } else atomicExch(flags + 2, 1);
+  }
+}
+
+// ---- 3. grow the cells that would overflow (first pending item of a cell does it) -----------------------------------
+__global__ void map_grow_kernel(const PendingAdd* __restrict__ pending, const unsigned int* __restrict__ n_pending,
+                                unsigned int pending_cap, MapClassDev* maps, int* __restrict__ flags) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int np = *n_pending; if (np > pending_cap) np = pending_cap;
+  if (i >= np) return;
+  const PendingAdd pa = pending[i];
+  MapClassDev& m = maps[pa.stream];
+  const unsigned int e = pa.entry;
+  const unsigned int want = atomicExch(&m.pending[e], 0u);   // only one thread per cell sees a non-zero value
+  if (want == 0) return;
+  const unsigned int count = m.entries[e].count, cap = m.cellcap[e];
+  if (count + want <= cap) return;
+  unsigned int ncap = cap ? cap : 8u;
+  while (ncap < count + want) ncap <<= 1;
+  const unsigned int nstart = atomicAdd(m.cursor, ncap);
+  if (nstart + ncap > m.pool_cap) { atomicExch(flags + 3, 1); return; }   // pool exhausted: the appends are dropped
+  const unsigned int ostart = m.entries[e].start;
+  for (unsigned int j = 0; j < count; j++) m.pts[nstart + j] = m.pts[ostart + j];
+  m.entries[e].start = nstart;
+  m.cellcap[e] = ncap;
+}
+
+// ---- 4. append ---------------------------------------------------------------------------------------------------------
+__global__ void map_append_kernel(const PendingAdd* __restrict__ pending, const unsigned int* __restrict__ n_pending,
+                                  unsigned int pending_cap, MapClassDev* maps) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int np = *n_pending; if (np > pending_cap) np = pending_cap;
+  if (i >= np) return;
+  const PendingAdd pa = pending[i];
+  MapClassDev& m = maps[pa.stream];
+  const unsigned int e = pa.entry;
+  if (m.entries[e].count >= m.cellcap[e]) return;   // growth failed (pool exhausted, already flagged)
+  const unsigned int j = atomicAdd(&m.entries[e].count, 1u);
+  if (j < m.cellcap[e]) {
+    m.pts[m.entries[e].start + j] = pa.p;
+    atomicAdd(&m.cube_count[pa.cube], 1);
+    atomicAdd(m.total, 1);
+  } else {
+    atomicSub(&m.entries[e].count, 1u);
+  }
+}
+
+__global__ void map_clear_kernel(CellEntry* e, unsigned int* cellcap, unsigned int* pend, unsigned int cap) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { e[i].key = CM_EMPTY_KEY; e[i].start = 0; e[i].count = 0; cellcap[i] = 0; pend[i] = 0; }
+}
+
+// searchable size of the surround map (sum of the valid cubes) -> GridView.npts, and the rest of the view
+__global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, GridView* views, int nstreams, float gate) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams) return;
+  MapClassDev& m = maps[s];
+  const CubeWindow& w = windows[s];
+  m.origin[0] = w.origin[0]; m.origin[1] = w.origin[1]; m.origin[2] = w.origin[2];
+  int total = 0;
+  for (int a = 0; a < 343; a++) {
+    if (!w.active[a]) continue;
+    int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
+    total += m.cube_count[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
+  }
+  GridView v;
+  v.entries = m.entries; v.pts = m.pts; v.mask = m.mask; v.inv_leaf = m.inv_leaf; v.kdiv = m.kdiv; v.cell = (float)m.kdiv * m.leaf;
+  v.npts = total;
+  int L = (int)ceilf(sqrtf(gate) / v.cell - 0.48f);
+  v.max_level = L < 0 ? 0 : L;
+  v.window = windows + s;
+  views[s] = v;
+}
+
+// export every resident point with its cube index (diagnostics, publishing, tests)
+__global__ void map_export_kernel(const MapClassDev* maps, int s, float4* out, int* cube_out, unsigned int* n_out, unsigned int cap) {
+  const MapClassDev& m = maps[s];
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > m.mask) return;
+  if (m.entries[i].key == CM_EMPTY_KEY) return;
+  const unsigned int start = m.entries[i].start, count = m.entries[i].count;
+  for (unsigned int j = 0; j < count; j++) {
+    float4 p = m.pts[start + j];
+    unsigned int o = atomicAdd(n_out, 1u);
+    if (o < cap) {
+      out[o] = p;
+      int ci = world_to_cube_axis(p.x, m.cube_size, m.origin[0]), cj = world_to_cube_axis(p.y, m.cube_size, m.origin[1]),
+          ck = world_to_cube_axis(p.z, m.cube_size, m.origin[2]);
+      cube_out[o] = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static unsigned int pow2_at_least(size_t v) { unsigned int p = 1024; while (p < v) p <<= 1; return p; }
+
+void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
+  nstreams = nstreams_; cfg = c;
+  const int ncubes = c.dims[0] * c.dims[1] * c.dims[2];
+  for (int cls = 0; cls < 2; cls++) {
+    const size_t maxpts = cls == 0 ? c.max_corner : c.max_surf;
+    const unsigned int tcap = pow2_at_least(maxpts);            // cells <= points; load factor <= 0.5 when cells hold >= 2 points
+    const unsigned int pool = (unsigned int)(maxpts * 4 + 1024);   // blocks are powers of two >= 8 slots: slack for sparse cells
+    table_cap[cls] = tcap; pool_cap[cls] = pool;
+    entries[cls].reserve((size_t)nstreams * tcap * sizeof(CellEntry));
+    cellcap[cls].reserve((size_t)nstreams * tcap * sizeof(unsigned int));
+    pending_cnt[cls].reserve((size_t)nstreams * tcap * sizeof(unsigned int));
+    pts[cls].reserve((size_t)nstreams * pool * sizeof(float4));
+    cube_count[cls].reserve((size_t)nstreams * ncubes * sizeof(int));
+    cursor[cls].reserve((size_t)nstreams * 2 * sizeof(unsigned int));
+    dev[cls].reserve((size_t)nstreams * sizeof(MapClassDev));
+    views[cls].reserve((size_t)nstreams * sizeof(GridView));
+    cudaMemsetAsync(cube_count[cls].p, 0, (size_t)nstreams * ncubes * sizeof(int), stream);
+    cudaMemsetAsync(cursor[cls].p, 0, (size_t)nstreams * 2 * sizeof(unsigned int), stream);
+    const size_t tot = (size_t)nstreams * tcap;
+    CM_LAUNCH(map_clear_kernel, (unsigned int)((tot + 255) / 256), 256, 0, stream, (CellEntry*)entries[cls].p,
+              (unsigned int*)cellcap[cls].p, (unsigned int*)pending_cnt[cls].p, (unsigned int)tot);
+    std::vector<MapClassDev> h(nstreams);
+    const float leaf = cls == 0 ? c.leaf_corner : c.leaf_surf;
+    for (int s = 0; s < nstreams; s++) {
+      MapClassDev& m = h[s];
+      m.entries = (CellEntry*)entries[cls].p + (size_t)s * tcap;
+      m.cellcap = (unsigned int*)cellcap[cls].p + (size_t)s * tcap;
+      m.pending = (unsigned int*)pending_cnt[cls].p + (size_t)s * tcap;
+      m.mask = tcap - 1;
+      m.pts = (float4*)pts[cls].p + (size_t)s * pool;
+      m.pool_cap = pool;
+      m.cursor = (unsigned int*)cursor[cls].p + s * 2;
+      m.total = (int*)cursor[cls].p + s * 2 + 1;
+      m.cube_count = (int*)cube_count[cls].p + (size_t)s * ncubes;
+      m.leaf = leaf; m.inv_leaf = 1.0f / leaf;
+      m.kdiv = cls == 0 ? c.kdiv_corner : c.kdiv_surf;
+      m.cube_size = c.cube_size;
+      for (int k = 0; k < 3; k++) { m.dims[k] = c.dims[k]; m.origin[k] = c.origin[k]; }
+    }
+    cudaMemcpyAsync(dev[cls].p, h.data(), sizeof(MapClassDev) * nstreams, cudaMemcpyHostToDevice, stream);
+  }
+  windows.reserve(sizeof(CubeWindow) * nstreams);
+  flags.reserve(sizeof(int) * 8);
+  n_pending.reserve(sizeof(unsigned int));
+  cudaMemsetAsync(flags.p, 0, sizeof(int) * 8, stream);
+  cudaStreamSynchronize(stream);   // h goes out of scope
+}
+
+void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream) {
+  cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
+  for (int cls = 0; cls < 2; cls++)
+    CM_LAUNCH(map_view_kernel, (nstreams + 63) / 64, 64, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
+              (GridView*)views[cls].p, nstreams, gate);
+}
+
+void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, const MatchState* d_state, const float* d_tf,
+                       cudaStream_t stream) {
+  if (cap <= 0) return;
+  const size_t n = (size_t)nstreams * cap;
+  world.reserve(n * sizeof(float4));
+  keys_a.reserve(n * 8); keys_b.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4);
+  pending.reserve(n * sizeof(PendingAdd));
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr,
+                                  (unsigned int*)nullptr, (long long)n, 0, 62, stream);
+  temp.reserve(tb);
+  const unsigned int nb = (unsigned int)((n + 255) / 256);
+  cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), stream);
+  CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
+            (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)flags.p);
+  tb = temp.cap;
+  cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
+                                  (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 62, stream);
+  g_launch_count += 9;
+  CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_b.p, (const unsigned int*)vals_b.p, n,
+            (const float4*)world.p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending.p, (unsigned int*)n_pending.p, (unsigned int)n,
+            (int*)flags.p);
+  CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
+            (MapClassDev*)dev[cls].p, (int*)flags.p);
+  CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
+            (MapClassDev*)dev[cls].p);
+}
+
+size_t DeviceMap::export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream) {
+  cudaMemsetAsync(d_n, 0, sizeof(unsigned int), stream);
+  CM_LAUNCH(map_export_kernel, (table_cap[cls] + 255) / 256, 256, 0, stream, (const MapClassDev*)dev[cls].p, s, d_out, d_cube, d_n, cap);
+  return 0;
+}
+
+}  // namespace cm

@@ -1,0 +1,338 @@
+// cm_mapping.cu -- the scan-to-map STAGE on top of the kernels: host mirror of LaserMapping::process
+// (L_SLAM/src/odometry/LaserMapping.cpp:39-59) = transformMerge (LaserMatcher.cpp:333-340), prepareFeatureFrame
+// (:288-301), prepareFeatureSurround (:303-325 -> FeatureMap::update FeatureMap.h:232-254, 308-352),
+// optimizeTransform (:327-331 -> ScanMatch.cpp:349-360), transformUpdate (:342-347), featureMapUpdate (:349-355),
+// batched over independent streams; plus the full pipeline entry (scan registration -> mapping).
+// The host part is a few dozen float operations per stream and frame (pose chaining, cube window); everything that
+// touches points runs on the device.
+#include "cm_ctx.h"
+#include "cm_math.h"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace cm {
+
+// ---- Eigen::Isometry3f algebra (same operation order as Transform * Transform / inverse(Isometry)) ---------------------
+static HostIso iso_identity() { HostIso i; for (int k = 0; k < 9; k++) i.R[k] = (k % 4 == 0) ? 1.f : 0.f; i.t[0] = i.t[1] = i.t[2] = 0.f; return i; }
+static HostIso iso_mul(const HostIso& a, const HostIso& b) {
+  HostIso r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.R[i * 3 + j] = (a.R[i * 3 + 0] * b.R[0 * 3 + j] + a.R[i * 3 + 1] * b.R[1 * 3 + j]) + a.R[i * 3 + 2] * b.R[2 * 3 + j];
+    r.t[i] = ((a.R[i * 3 + 0] * b.t[0] + a.R[i * 3 + 1] * b.t[1]) + a.R[i * 3 + 2] * b.t[2]) + a.t[i];
+  }
+  return r;
+}
+static HostIso iso_inverse(const HostIso& a) {
+  HostIso r;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.R[i * 3 + j] = a.R[j * 3 + i];
+  for (int i = 0; i < 3; i++) r.t[i] = -((r.R[i * 3 + 0] * a.t[0] + r.R[i * 3 + 1] * a.t[1]) + r.R[i * 3 + 2] * a.t[2]);
+  return r;
+}
+// convertTransform(Isometry3f&, Twist&), transform_utils.h:313-331 (getEulerAngles :54-60)
+static void iso_to_twist(const HostIso& it, float pose[6]) {
+  pose[3] = it.t[0]; pose[4] = it.t[1]; pose[5] = it.t[2];
+  pose[0] = atan2f(it.R[7], it.R[8]);
+  pose[1] = asinf(-it.R[6]);
+  pose[2] = atan2f(it.R[3], it.R[0]);
+}
+static void twist_to_iso(const float pose[6], HostIso& it) { pose_to_matrix(pose, it.R); it.t[0] = pose[3]; it.t[1] = pose[4]; it.t[2] = pose[5]; }
+
+// FeatureMap::update + computeActiveAera (FeatureMap.h:232-254, 308-352).  Returns false when the reference would
+// shift() the cube grid (not implemented).
+static bool update_window(const cm_config& cfg, MappingStream& st, const float sensor[3], CubeWindow& w) {
+  const int dims[3] = {cfg.cube_w, cfg.cube_h, cfg.cube_d};
+  int g[3];
+  for (int k = 0; k < 3; k++) g[k] = (int)(roundf(sensor[k] / cfg.cube_size) + (float)st.origin[k]);   // worldToCube :479-481
+  const int PAD = 3;
+  for (int k = 0; k < 3; k++) {
+    int ng = std::min(std::max(g[k], PAD), dims[k] - PAD - 1);
+    if (ng != g[k]) return false;   // shift(newGrid - grid) would move the cubes
+    st.cur[k] = ng;
+  }
+  memset(&w, 0, sizeof(w));
+  for (int k = 0; k < 3; k++) { w.origin[k] = st.origin[k]; w.dims[k] = dims[k]; w.w0[k] = st.cur[k] - 3; }
+  w.cube_size = cfg.cube_size;
+  const int window = (int)ceilf(cfg.valid_distance / cfg.cube_size);   // 3 with the reference's 150 / 50
+  for (int i = st.cur[0] - window; i <= st.cur[0] + window; i++)
+    for (int j = st.cur[1] - window; j <= st.cur[1] + window; j++)
+      for (int k = st.cur[2] - window; k <= st.cur[2] + window; k++) {
+        if (!(0 <= i && i < dims[0] && 0 <= j && j < dims[1] && 0 <= k && k < dims[2])) continue;
+        float centerX = cfg.cube_size * (i - st.origin[0]);
+        float centerY = cfg.cube_size * (j - st.origin[1]);
+        float centerZ = cfg.cube_size * (k - st.origin[2]);
+        bool inFov = false;
+        for (int ii = -1; ii <= 1 && !inFov; ii += 2)
+          for (int jj = -1; jj <= 1 && !inFov; jj += 2)
+            for (int kk = -1; kk <= 1 && !inFov; kk += 2) {
+              float cx = (float)(centerX + cfg.cube_size / 2.0 * ii);
+              float cy = (float)(centerY + cfg.cube_size / 2.0 * jj);
+              float cz = (float)(centerZ + cfg.cube_size / 2.0 * kk);
+              float dx = sensor[0] - cx, dy = sensor[1] - cy, dz = sensor[2] - cz;
+              float sq = dx * dx + dy * dy + dz * dz;
+              if (sqrt((double)sq) < cfg.valid_distance) inFov = true;
+            }
+        int wi = i - w.w0[0], wj = j - w.w0[1], wk = k - w.w0[2];
+        if (inFov && wi >= 0 && wi < 7 && wj >= 0 && wj < 7 && wk >= 0 && wk < 7) w.active[(wi * 7 + wj) * 7 + wk] = 1;
+      }
+  for (int a = 0; a < 343; a++) {
+    int i = a / 49, j = (a / 7) % 7, k = a % 7;
+    bool all = true;
+    for (int di = -1; di <= 1 && all; di++)
+      for (int dj = -1; dj <= 1 && all; dj++)
+        for (int dk = -1; dk <= 1 && all; dk++) {
+          int x = i + di, y = j + dj, z = k + dk;
+          if (x < 0 || x > 6 || y < 0 || y > 6 || z < 0 || z > 6 || !w.active[(x * 7 + y) * 7 + z]) all = false;
+        }
+    w.interior[a] = all ? 1 : 0;
+  }
+  return true;
+}
+
+__global__ void gather_counts_kernel(const int* __restrict__ n5, int* __restrict__ n2, int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) { n2[s] = n5[s * 5 + 1]; n2[S + s] = n5[s * 5 + 3]; }   // lessSharp -> corner, lessFlat -> surf
+}
+
+static int default_kdiv(float cell, float leaf, int mult) {
+  if (cell > 0.f) { int k = (int)floorf(cell / leaf + 0.5f); return k < 1 ? 1 : k; }
+  return mult;
+}
+
+}  // namespace cm
+
+using namespace cm;
+static int fail(cm_ctx* ctx, int code, const std::string& msg) { return ctx_fail(ctx, code, msg); }
+
+extern "C" {
+
+int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_t max_surf_points) {
+  if (!ctx || nstreams <= 0 || nstreams > 256 || max_corner_points == 0 || max_surf_points == 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const cm_config& c = ctx->cfg;
+  if (ceilf(c.valid_distance / c.cube_size) > 3.f) return fail(ctx, CM_ERR_UNSUPPORTED, "valid_distance / cube_size > 3");
+  try {
+    cudaSetDevice(c.device);
+    MapConfig mc;
+    mc.max_corner = max_corner_points; mc.max_surf = max_surf_points;
+    mc.leaf_corner = c.map_filter_corner; mc.leaf_surf = c.map_filter_surf;
+    mc.kdiv_corner = default_kdiv(c.cell_corner, c.map_filter_corner, 6);
+    mc.kdiv_surf = default_kdiv(c.cell_surf, c.map_filter_surf, 3);
+    mc.cube_size = c.cube_size;
+    mc.dims[0] = c.cube_w; mc.dims[1] = c.cube_h; mc.dims[2] = c.cube_d;
+    for (int k = 0; k < 3; k++) mc.origin[k] = (int)round((mc.dims[k] - 1) / 2.0);   // FeatureMap.h:63-65
+    ctx->map.create(nstreams, mc, ctx->stream);
+    ctx->map_streams = nstreams;
+    ctx->mstreams.assign(nstreams, MappingStream());
+    for (auto& st : ctx->mstreams) {
+      st.mappedLast = st.mappedNew = st.odomLast = iso_identity();   // LaserMatcher.cpp:31-32
+      for (int k = 0; k < 3; k++) { st.origin[k] = mc.origin[k]; st.cur[k] = 0; }
+    }
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+// Core of the stage on DEVICE clouds.  d_corner/d_surf: [S][cap] with device counts d_n (corner counts then surf counts,
+// [2][S]).  h_odom: S odometry poses (host).  Outputs on the host: mapped poses and stats.
+static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, const float4* d_surf, int cap_s, const int* d_n,
+                               const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats) {
+  const cm_config& cfg = ctx->cfg;
+  const int S = ctx->map_streams;
+  cudaStream_t st = ctx->stream;
+  MatchParamsDev prm = dev_params(cfg);
+  // transformMerge
+  std::vector<float> pose_in(6 * S);
+  std::vector<CubeWindow> wins(S);
+  for (int s = 0; s < S; s++) {
+    MappingStream& ms = ctx->mstreams[s];
+    HostIso odomNew; memcpy(odomNew.R, h_odom[s].R, 36); memcpy(odomNew.t, h_odom[s].t, 12);
+    HostIso L2W = iso_mul(ms.mappedLast, iso_inverse(ms.odomLast));   // transformAssociate, transform_utils.h:502-507
+    ms.mappedNew = iso_mul(L2W, odomNew);
+    if (!update_window(cfg, ms, ms.mappedNew.t, wins[s]))
+      return fail(ctx, CM_ERR_UNSUPPORTED, "sensor left the supported part of the cube grid (FeatureMap::shift not implemented)");
+    iso_to_twist(ms.mappedNew, &pose_in[6 * s]);
+  }
+  // prepareFeatureFrame: voxel filters
+  ctx->m_corner_ds.reserve((size_t)S * cap_c * sizeof(float4));
+  ctx->m_surf_ds.reserve((size_t)S * cap_s * sizeof(float4));
+  ctx->m_n_ds.reserve(sizeof(int) * 2 * S);
+  ctx->d_flag.reserve(sizeof(int));
+  CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
+  int* d_nds = (int*)ctx->m_n_ds.p;
+  ctx->voxel.run(S, d_corner, d_n, cap_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, st);
+  ctx->voxel.run(S, d_surf, d_n + S, cap_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st);
+  // prepareFeatureSurround: cube window -> searchable views
+  ctx->map.set_windows(wins.data(), prm.knn_gate, st);
+  // optimizeTransform
+  ctx->m_pose.reserve(sizeof(float) * 6 * S);
+  ctx->m_state.reserve(sizeof(MatchState) * S);
+  ctx->m_rows.reserve((size_t)S * (cap_c + cap_s) * sizeof(RowOut));
+  ctx->m_sums.reserve(sizeof(double) * 32 * S);
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_pose.p, pose_in.data(), sizeof(float) * 6 * S, cudaMemcpyHostToDevice, st));
+  MatchLaunch m;
+  m.nstreams = S;
+  m.corner = (const float4*)ctx->m_corner_ds.p; m.surf = (const float4*)ctx->m_surf_ds.p;
+  m.n_corner = d_nds; m.n_surf = d_nds + S; m.cap_corner = cap_c; m.cap_surf = cap_s;
+  m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
+  m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p;
+  m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm;
+  launch_match(m, st);
+  // featureMapUpdate
+  ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, (const MatchState*)ctx->m_state.p, nullptr, st);
+  ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+  // results
+  std::vector<MatchState> hs(S);
+  std::vector<int> nds(2 * S);
+  int flags[8];
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  CM_CUDA_CHECK(ctx, cudaGetLastError());
+  if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
+  if (flags[2] || flags[3]) return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+  for (int s = 0; s < S; s++) {
+    MappingStream& ms = ctx->mstreams[s];
+    twist_to_iso(hs[s].pose, ms.mappedNew);   // ScanMatch.cpp:358 (always, also when the map was too small)
+    ms.mappedLast = ms.mappedNew;             // transformUpdate
+    memcpy(ms.odomLast.R, h_odom[s].R, 36); memcpy(ms.odomLast.t, h_odom[s].t, 12);
+    if (h_mapped) { memcpy(h_mapped[s].R, ms.mappedNew.R, 36); memcpy(h_mapped[s].t, ms.mappedNew.t, 12); }
+    if (h_stats) fill_match_stats(cfg, hs[s], (size_t)(nds[s] + nds[S + s]), &h_stats[s]);
+  }
+  return CM_OK;
+}
+
+int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                            const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!odom || !corner || !surf || !n_corner || !n_surf || cap_corner <= 0 || cap_surf <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const int S = ctx->map_streams;
+  for (int s = 0; s < S; s++)
+    if (n_corner[s] < 0 || n_corner[s] > cap_corner || n_surf[s] < 0 || n_surf[s] > cap_surf) return fail(ctx, CM_ERR_ARG, "count out of range");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    ctx->m_corner_in.reserve((size_t)S * cap_corner * sizeof(cm_point));
+    ctx->m_surf_in.reserve((size_t)S * cap_surf * sizeof(cm_point));
+    ctx->m_n_in.reserve(sizeof(int) * 2 * S);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_corner_in.p, corner, (size_t)S * cap_corner * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_surf_in.p, surf, (size_t)S * cap_surf * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_n_in.p, n_corner, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync((int*)ctx->m_n_in.p + S, n_surf, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    return mapping_process_dev(ctx, (const float4*)ctx->m_corner_in.p, cap_corner, (const float4*)ctx->m_surf_in.p, cap_surf,
+                               (const int*)ctx->m_n_in.p, odom, mapped, stats);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+// Full pipeline: OrganisedScanRegistration::process -> (/laser_cloud_less_sharp, /laser_cloud_less_flat) ->
+// LaserMapping::process, for the S streams of the context.  (The reference routes the clouds through LaserOdometry,
+// which re-projects them to the sweep end; with instantaneous synthetic sweeps that projection is the identity.)
+static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped, cm_match_stats* stats) {
+  const cm_config& cfg = ctx->cfg;
+  const int S = ctx->map_streams;
+  const int cap = rows * cols;
+  cudaStream_t st = ctx->stream;
+  for (int k = 0; k < 4; k++) ctx->p_pts[k].reserve((size_t)S * cap * sizeof(float4));
+  ctx->p_n.reserve(sizeof(int) * 7 * S);
+  ScanRegLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.nstreams = S; L.rows = rows; L.cols = cols; L.frames = d_frames;
+  fill_scanreg_params(cfg, L);
+  for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)ctx->p_pts[k].p; L.cap[k] = cap; }
+  L.out_n = (int*)ctx->p_n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
+  ctx->scanreg.run(L, st);
+  CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)ctx->p_n.p + 2 * S, (int*)ctx->p_n.p, S);
+  return mapping_process_dev(ctx, (const float4*)ctx->p_pts[1].p, cap, (const float4*)ctx->p_pts[3].p, cap, (const int*)ctx->p_n.p, odom,
+                             mapped, stats);
+}
+
+int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
+                          cm_match_stats* stats) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!frames || !odom || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
+    ctx->p_frames.reserve(bytes);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->p_frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return pipeline_dev(ctx, (const float4*)ctx->p_frames.p, rows, cols, odom, mapped, stats);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
+                         cm_match_stats* stats) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!d_frames || !odom || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    return pipeline_dev(ctx, (const float4*)d_frames, rows, cols, odom, mapped, stats);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner, int cap_corner, const cm_point* surf,
+                       const int* n_surf, int cap_surf, const cm_iso* tf) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!corner || !surf || !n_corner || !n_surf || !tf || cap_corner <= 0 || cap_surf <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const int S = ctx->map_streams;
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    ctx->m_corner_in.reserve((size_t)S * cap_corner * sizeof(cm_point));
+    ctx->m_surf_in.reserve((size_t)S * cap_surf * sizeof(cm_point));
+    ctx->m_n_in.reserve(sizeof(int) * 2 * S);
+    ctx->m_tf.reserve(sizeof(float) * 12 * S);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_corner_in.p, corner, (size_t)S * cap_corner * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_surf_in.p, surf, (size_t)S * cap_surf * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_n_in.p, n_corner, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync((int*)ctx->m_n_in.p + S, n_surf, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_tf.p, tf, sizeof(float) * 12 * S, cudaMemcpyHostToDevice, st));
+    ctx->map.insert(0, (const float4*)ctx->m_corner_in.p, (const int*)ctx->m_n_in.p, cap_corner, nullptr, (const float*)ctx->m_tf.p, st);
+    ctx->map.insert(1, (const float4*)ctx->m_surf_in.p, (const int*)ctx->m_n_in.p + S, cap_surf, nullptr, (const float*)ctx->m_tf.p, st);
+    int flags[8];
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
+    if (flags[2] || flags[3]) return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (stream_index < 0 || stream_index >= ctx->map_streams || cls < 0 || cls > 1 || !n_out) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const size_t c = cap ? cap : 1;
+    ctx->m_exp_pts.reserve(c * sizeof(float4)); ctx->m_exp_cube.reserve(c * sizeof(int)); ctx->m_exp_n.reserve(sizeof(unsigned int));
+    ctx->map.export_points(cls, stream_index, (float4*)ctx->m_exp_pts.p, (int*)ctx->m_exp_cube.p, (unsigned int*)ctx->m_exp_n.p,
+                           (unsigned int)cap, st);
+    unsigned int n = 0;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&n, ctx->m_exp_n.p, sizeof(n), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    *n_out = n;
+    size_t m = n < cap ? n : cap;
+    if (m && out) CM_CUDA_CHECK(ctx, cudaMemcpy(out, ctx->m_exp_pts.p, m * sizeof(cm_point), cudaMemcpyDeviceToHost));
+    if (m && cube_index) CM_CUDA_CHECK(ctx, cudaMemcpy(cube_index, ctx->m_exp_cube.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+}  // extern "C"

@@ -19,13 +19,13 @@ __global__ void grid_clear_kernel(CellEntry* e, unsigned int cap) {
   if (i < cap) { e[i].key = CM_EMPTY_KEY; e[i].start = 0; e[i].count = 0; }
 }
 
-__global__ void grid_count_kernel(const float4* __restrict__ pts, int n, CellEntry* entries, unsigned int mask, float ox,
-                                  float oy, float oz, float inv, int* __restrict__ cell_of) {
+__global__ void grid_count_kernel(const float4* __restrict__ pts, int n, CellEntry* entries, unsigned int mask, float inv,
+                                  int* __restrict__ cell_of) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = pts[i];
   if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { cell_of[i] = -1; return; }
-  float fx = floorf((p.x - ox) * inv), fy = floorf((p.y - oy) * inv), fz = floorf((p.z - oz) * inv);
+  float fx = floorf(p.x * inv), fy = floorf(p.y * inv), fz = floorf(p.z * inv);
   if (!(fabsf(fx) < 1.0e6f && fabsf(fy) < 1.0e6f && fabsf(fz) < 1.0e6f)) { cell_of[i] = -1; return; }
   unsigned long long key = pack_cell((int)fx, (int)fy, (int)fz);
   unsigned int h = hash_cell(key) & mask;
@@ -437,16 +437,16 @@ void GridStorage::build(const float4* d_pts, int n, float cell_size, float gate,
   cudaMemsetAsync(cursor.p, 0, sizeof(unsigned int), stream);
   if (n > 0) {
     int nb = (n + 255) / 256;
-    CM_LAUNCH(grid_count_kernel, nb, 256, 0, stream, d_pts, n, (CellEntry*)entries.p, cap - 1, 0.f, 0.f, 0.f, inv, (int*)cell_of.p);
+    CM_LAUNCH(grid_count_kernel, nb, 256, 0, stream, d_pts, n, (CellEntry*)entries.p, cap - 1, inv, (int*)cell_of.p);
     CM_LAUNCH(grid_offsets_kernel, (cap + 255) / 256, 256, 0, stream, (CellEntry*)entries.p, cap, (unsigned int*)cursor.p);
     CM_LAUNCH(grid_scatter_kernel, nb, 256, 0, stream, d_pts, n, (CellEntry*)entries.p, (const int*)cell_of.p, (float4*)pts.p, keep_w);
   }
   view.entries = (const CellEntry*)entries.p;
   view.pts = (const float4*)pts.p;
   view.mask = cap - 1;
-  view.ox = view.oy = view.oz = 0.f;
-  view.cell = cell_size; view.inv_cell = inv;
+  view.inv_leaf = inv; view.kdiv = 1; view.cell = cell_size;
   view.npts = n;
+  view.window = nullptr;
   view.max_level = grid_max_level(cell_size, gate);
 }
 
