@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- LiDAR points registered / s (scan registration + scan-to-map registration, whole box).
+
+Workload (BASELINE.json configs[1]): HDL-64E-shaped sweeps (64 x 2048 = 131,072 points) registered against a
+~1M-point local map per stream.  One step = one sweep of EVERY stream through the full hot path
+(scan registration -> frame voxel filters -> <= 10 Gauss-Newton iterations of exact-5-NN correspondence + solve ->
+map insertion).  Streams are independent LiDARs (own pose chain, own map); ranks shard streams (weak scaling,
+no data-path collective).  `value` = inputs resident in HBM; `e2e` = host buffers through the C ABI
+(cm_pipeline_step_host), H2D of the sweeps and D2H of the poses inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--streams S]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "the-cooper-mapper_b200"
+ROWS, COLS = 64, 2048
+NPTS = ROWS * COLS
+SEED = 0x5EED0002
+CFG = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+ORACLE_MAP = dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------------------------
+def make_workload(n_pool, synth):
+    """Scene, ~1M-point map (corner, surf) and a pool of HDL-64E sweeps with their true poses."""
+    sc = synth.make_scene(seed=SEED & 0xFFFF, extent=125.0, n_boxes=44, n_poles=40)
+    mc, ms = synth.sample_map(sc, 0.4, seed=2)
+    traj = synth.trajectory(n_pool, speed=2.0)
+    frames = np.empty((n_pool, ROWS, COLS, 4), np.float32)
+    poses = []
+    for k, (R, t) in enumerate(traj):
+        frames[k] = synth.simulate_scan(sc, R, t, "HDL-64E", seed=1000 + k)
+        poses.append((R.astype(np.float32), t.astype(np.float32)))
+    return mc, ms, frames, poses
+
+
+def noisy_odom(poses, idx, rng, synth):
+    """Odometry prediction = truth + U(+-0.1 m, +-0.5 deg)."""
+    R, t = poses[idx]
+    d = np.deg2rad(rng.uniform(-0.5, 0.5, 3))
+    dR, _ = synth.pose_matrix(d[2], d[1], d[0])
+    return (R @ dR.astype(np.float32)).astype(np.float32), (t + rng.uniform(-0.1, 0.1, 3)).astype(np.float32)
+
+
+def pack_isos(isos):
+    a = np.empty((len(isos), 12), np.float32)
+    for i, (R, t) in enumerate(isos):
+        a[i, :9] = np.asarray(R, np.float32).ravel(); a[i, 9:] = t
+    return a
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (the reference restated line by line + the reference's own nanoflann) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wid, mc, ms, frames, poses, order, warm = args
+    from oracle import oracle_py as O
+    synth = importlib.import_module(PKG + ".synth")
+    rng = np.random.default_rng(500 + wid)
+    m = O.Mapping(map_params=ORACLE_MAP, nanoflann=True, fast=True)
+    m.map_update(np.zeros(3, np.float32))
+    m.map_add(mc, ms, np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+    times = []
+    for k, fi in enumerate(order):
+        oR, ot = noisy_odom(poses, fi, rng, synth)
+        t0 = time.perf_counter()
+        f = O.scanreg_organised(frames[fi], fast=True)
+        m.process(oR, ot, f["lessSharp"], f["lessFlat"])
+        dt = time.perf_counter() - t0
+        if k >= warm:
+            times.append(dt)
+    return times
+
+
+def cpu_arm(mc, ms, frames, poses, frames_per_worker, warm=1, workers=None):
+    """Runs `workers` independent streams, one per process / core.  Returns (points/s, cores, per-frame seconds)."""
+    import multiprocessing as mp
+    workers = workers or min(os.cpu_count() or 1, 32)
+    ctx = mp.get_context("fork")
+    jobs = []
+    for w in range(workers):
+        order = [(3 * w + k) % len(frames) for k in range(warm + frames_per_worker)]
+        jobs.append((w, mc, ms, frames, poses, order, warm))
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    per_frame = [x for r in res for x in r]
+    # throughput from the timed frames only: every worker runs concurrently, so the box rate is workers / mean frame time
+    rate = workers * NPTS / float(np.mean(per_frame))
+    return rate, workers, per_frame, wall
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index; self.stop_flag = False; self.samples = []; self.reasons = set(); self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "corr_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=16, help="LiDAR streams per GPU")
+    ap.add_argument("--pool", type=int, default=12, help="distinct synthetic sweeps generated on the host")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W, S = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0), args.streams
+    synth = importlib.import_module(PKG + ".synth")
+    workload = "HDL-64E 64x2048 sweeps, scan registration + scan-to-map vs ~1M-point local map per stream"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        mc, ms, frames, poses = make_workload(min(args.pool, 6), synth)
+        rate, cores, per_frame, wall = cpu_arm(mc, ms, frames, poses, frames_per_worker=max(K, 1), warm=max(args.warmup, 1))
+        line = {"impl": "reference", "metric": "lidar_points_registered_per_s", "value": rate, "unit": "points/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_frame)),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "map_points": int(len(mc) + len(ms)), "streams": cores,
+                           "note": "CPU oracle (line-by-line restatement + the reference's vendored nanoflann), one stream per core"},
+                "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
+                                 "sample": "%d sweeps per core after %d warm-up, wall %.1f s" % (max(K, 1), max(args.warmup, 1), wall)},
+                "p50_latency_ms": 1e3 * float(np.median(per_frame)),
+                "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- workload on the host (before CUDA is touched: the CPU baseline forks) -------------------------------------
+    t_setup = time.time()
+    mc, ms, frames, poses = make_workload(args.pool, synth)
+    log("[bench] workload: map %d corner + %d surf points, %d sweeps (%.1f s)" % (len(mc), len(ms), len(frames), time.time() - t_setup))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, per_frame, wall = cpu_arm(mc, ms, frames[:6], poses[:6], frames_per_worker=2, warm=1)
+        cpu = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
+               "sample": "2 sweeps per core after 1 warm-up (oracle -O3 + reference nanoflann), wall %.1f s, p50 %.0f ms/sweep"
+                         % (wall, 1e3 * float(np.median(per_frame)))}
+        log("[bench] cpu baseline: %.3e points/s on %d cores" % (rate, cores))
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cmb = importlib.import_module(PKG)
+    ctx = cmb.Context(device=local_rank, **CFG)
+    ctx.mapping_create(S, max_corner_points=max(4 * len(mc), 100000), max_surf_points=int(1.6 * len(ms)) + 200000)
+    eye = (np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+    # prebuilt ~1M-point map in every stream (inserted through the product's own insert kernels, in chunks)
+    chunk = 1 << 18
+    for o in range(0, len(ms), chunk):
+        c_part = mc if o == 0 else mc[:0]
+        ctx.map_insert([c_part] * S, [ms[o:o + chunk]] * S, [eye] * S)
+    map_pts = [len(ctx.map_export(0, 0)[0]), len(ctx.map_export(0, 1)[0])]
+    log("[bench] rank %d: %d streams, resident map per stream: %d corner + %d surf points" % (rank, S, map_pts[0], map_pts[1]))
+
+    rng = np.random.default_rng(77 + rank)
+    n_steps = W + K
+    order = [[(3 * s + 5 * rank + k) % len(frames) for s in range(S)] for k in range(2 * n_steps + 4)]
+    odom = [pack_isos([noisy_odom(poses, order[k][s], rng, synth) for s in range(S)]) for k in range(len(order))]
+    pool_dev = torch.from_numpy(frames).to(dev)
+    step_dev = [pool_dev[torch.tensor(order[k], device=dev)].contiguous() for k in range(n_steps)]
+    torch.cuda.synchronize()
+    mapped = np.empty((S, 12), np.float32); stats = (cmb.MatchStats * S)()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ------------------------------------------------------------------------------------
+    for k in range(W):
+        ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ctx.prof_enable(True); ctx.prof_drain()
+    launches0 = ctx.launch_count()
+    qi = q = ins = feat = 0
+    iters = []
+    ctx.timer_record(0)
+    for k in range(W, W + K):
+        ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
+        c = ctx.last_step_counters()
+        qi += c["query_iters"]; q += c["queries"]; ins += c["inserted"]; feat += c["features"]
+        iters += [st.iterations for st in stats]
+    ctx.timer_record(1)
+    ms_total = ctx.timer_elapsed_ms()
+    barrier()
+    corr_ms, corr_launches = ctx.prof_drain()
+    ctx.prof_enable(False)
+    launches = ctx.launch_count() - launches0
+    conv = float(np.mean([st.converged for st in stats]))
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * S * K * NPTS / (ms_max * 1e-3)
+
+    # ---- end-to-end arm: pinned host sweeps through the C ABI --------------------------------------------------------
+    host_steps = [torch.from_numpy(np.ascontiguousarray(frames[order[n_steps + k]])).pin_memory() for k in range(n_steps)]
+    for k in range(W):
+        ctx.pipeline_step_packed(host_steps[k].numpy(), odom[n_steps + k], mapped, stats)
+    barrier()
+    ctx.timer_record(0)
+    for k in range(W, W + K):
+        ctx.pipeline_step_packed(host_steps[k].numpy(), odom[n_steps + k], mapped, stats)
+    ctx.timer_record(1)
+    e2e_ms = ctx.timer_elapsed_ms()
+    barrier()
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * K * NPTS / (float(t.item()) * 1e-3)
+
+    # ---- single-stream latency (one LiDAR, host sweep in -> host pose out) ---------------------------------------------
+    p50 = None
+    if rank == 0 and not args.no_latency:
+        c1 = cmb.Context(device=local_rank, **CFG)
+        c1.mapping_create(1, max_corner_points=max(4 * len(mc), 100000), max_surf_points=int(1.6 * len(ms)) + 200000)
+        for o in range(0, len(ms), chunk):
+            c1.map_insert([mc if o == 0 else mc[:0]], [ms[o:o + chunk]], [eye])
+        m1 = np.empty((1, 12), np.float32); s1 = (cmb.MatchStats * 1)()
+        lat = []
+        for k in range(4 + 20):
+            fi = k % len(frames)
+            fr = torch.from_numpy(np.ascontiguousarray(frames[fi:fi + 1])).pin_memory()
+            od = pack_isos([noisy_odom(poses, fi, rng, synth)])
+            t0 = time.perf_counter()
+            c1.pipeline_step_packed(fr.numpy(), od, m1, s1)
+            if k >= 4:
+                lat.append(1e3 * (time.perf_counter() - t0))
+        p50 = float(np.median(lat))
+        c1.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        corr_bytes = 96.0 * qi                              # 16 B query + 5 x 16 B neighbours per query-iteration
+        achieved = corr_bytes / (corr_ms * 1e-3) / 1e9 if corr_ms > 0 else 0.0
+        step_bytes = 16.0 * S * K * NPTS + 16.0 * feat + 96.0 * qi + 32.0 * ins
+        step_gbs = step_bytes / (ms_total * 1e-3) / 1e9
+        line = {
+            "metric": "lidar_points_registered_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "streams_per_gpu": S, "points_per_sweep": NPTS, "map_points_per_stream": int(sum(map_pts)),
+                       "frame_leaf": [CFG["filter_corner"], CFG["filter_surf"]], "map_leaf": [CFG["map_filter_corner"], CFG["map_filter_surf"]],
+                       "mean_gn_iterations": float(np.mean(iters)), "converged_frac": conv,
+                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush",
+                       "parallelism": "streams sharded over ranks, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "corr_kernel (fused transform + exact 5-NN + line/plane fit + Jacobian row)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "kernel_ms_per_step": corr_ms / K, "kernel_share_of_step": corr_ms / ms_total,
+                         "kernel_launches": corr_launches, "algorithmic_bytes_per_query_iteration": 96,
+                         "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(S * NPTS * 16 + S * 48),
+                    "d2h_bytes_per_step": int(S * 48 + S * 48)},
+            "p50_latency_ms": p50,
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,7 @@ typedef struct cm_config {
   int cube_w, cube_h, cube_d;                /* 121, 121, 11  LaserMatcher.cpp:107-113 */
   float cube_size, valid_distance;           /* 50, 150  FeatureMap.h:65-66 */
   /* search grid (implementation parameters; results do not depend on them) */
-  float cell_corner, cell_surf;       /* edge of the hash cells; <= 0: 6 x / 3 x the matching map leaf */
+  float cell_corner, cell_surf;       /* edge of the hash cells; <= 0: 8 x / 4 x the matching map leaf */
 } cm_config;
 
 typedef struct cm_match_stats {
@@ -172,6 +172,18 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
  * storage order; *n_out is the total even when it exceeds cap.  Sorting by (cube, voxel) gives the reference's
  * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
 int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
+
+/* ---- measurement helpers (no reference counterpart; used by bench.py) ------------------------------------------------
+ * cm_timer_record(ctx, 0 | 1) records a CUDA event on the context's stream; cm_timer_elapsed_ms returns event 1 - event 0.
+ * cm_prof_enable brackets every launch of the dominant kernel (the fused correspondence kernel) with CUDA events on
+ * the launching stream; cm_prof_drain returns their summed duration and count since the last drain.
+ * cm_last_step_counters: {query-iterations, queries, inserted points, (reserved)} of the last mapping / pipeline step,
+ * summed over the streams -- the run-time counts the algorithmic-bytes formula needs. */
+int cm_timer_record(cm_ctx* ctx, int which);
+int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms);
+int cm_prof_enable(cm_ctx* ctx, int on);
+int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches);
+int cm_last_step_counters(cm_ctx* ctx, unsigned long long* out4);
 
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.

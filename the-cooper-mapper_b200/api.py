@@ -209,6 +209,28 @@ class Context:
         order = np.lexsort((v[:, 0], v[:, 1], v[:, 2], cube))
         return pts[order], cube[order]
 
+    # ---- measurement helpers -------------------------------------------------------------------------------------
+    def timer_record(self, which):
+        self._check(self.L.cm_timer_record(self.h, C.c_int(which)))
+
+    def timer_elapsed_ms(self):
+        ms = C.c_float(0)
+        self._check(self.L.cm_timer_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def prof_enable(self, on):
+        self._check(self.L.cm_prof_enable(self.h, C.c_int(int(on))))
+
+    def prof_drain(self):
+        ms = C.c_double(0); n = C.c_int(0)
+        self._check(self.L.cm_prof_drain(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_step_counters(self):
+        a = (C.c_ulonglong * 4)()
+        self._check(self.L.cm_last_step_counters(self.h, a))
+        return dict(query_iters=a[0], queries=a[1], inserted=a[2], features=a[3])
+
     # ---- scan registration -----------------------------------------------------------------------------------------
     def scanreg_organised(self, frames, debug=False):
         """frames: (S, rows, cols, 4) or (rows, cols, 4) organised sweeps -> list of per-stream dicts with the four

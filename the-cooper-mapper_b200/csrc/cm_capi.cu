@@ -84,7 +84,7 @@ int cm_knn5_host(cm_ctx* ctx, const cm_point* map, size_t n_map, float cell, flo
     if (n_map) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, map, n_map * sizeof(cm_point), cudaMemcpyHostToDevice, ctx->stream));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_q.p, q, nq * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     ctx->grid_a.build((const float4*)ctx->d_ref_surf.p, (int)n_map, cell, gate, 0, ctx->stream);
-    launch_knn5(ctx->grid_a.view, (const float*)ctx->d_q.p, (int)nq, (int*)ctx->d_idx.p, (float*)ctx->d_d2.p, ctx->stream);
+    launch_knn5(ctx->grid_a.view, (const float*)ctx->d_q.p, (int)nq, gate, (int*)ctx->d_idx.p, (float*)ctx->d_d2.p, ctx->stream);
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(idx_out, ctx->d_idx.p, nq * 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(d2_out, ctx->d_d2.p, nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -151,8 +151,8 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     int counts[2] = {(int)nc, (int)ns};
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, pose, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nrc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 6.f), prm.knn_gate, 0, st);
-    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)nrs, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 3.f), prm.knn_gate, 0, st);
+    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nrc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), prm.knn_gate, 0, st);
+    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)nrs, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), prm.knn_gate, 0, st);
     GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
     if (trace) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, sizeof(IterTrace) * prm.max_iterations, st));
@@ -170,6 +170,7 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     m.trace = trace ? (IterTrace*)ctx->d_trace.p : nullptr;
     m.nn = want_nn ? (int*)ctx->d_nn.p : nullptr;
     m.orig_idx = 1;
+    m.max_queries = (int)(nc + ns);
     m.prm = prm;
     launch_match(m, st);
     MatchState hs;
@@ -311,7 +312,7 @@ int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vin.p, in, (size_t)nseg * cap_in * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vn_in.p, n_in, nseg * sizeof(int), cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
-    ctx->voxel.run(nseg, (const float4*)ctx->d_vin.p, (const int*)ctx->d_vn_in.p, cap_in, leaf, (float4*)ctx->d_vout.p,
+    ctx->voxel.run(nseg, (const float4*)ctx->d_vin.p, (const int*)ctx->d_vn_in.p, cap_in, 0, leaf, (float4*)ctx->d_vout.p,
                    (int*)ctx->d_vn_out.p, cap_out, (int*)ctx->d_flag.p, st);
     int ovf = 0;
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->d_vout.p, (size_t)nseg * cap_out * sizeof(cm_point), cudaMemcpyDeviceToHost, st));

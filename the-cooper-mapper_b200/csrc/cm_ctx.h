@@ -35,6 +35,10 @@ struct cm_ctx {
   std::vector<cm::MappingStream> mstreams;
   cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
+  cm::KernelProfiler prof;
+  cudaEvent_t timer[2] = {nullptr, nullptr};
+  // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
+  unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;
   // pipeline (scan registration -> mapping), cm_mapping.cu
   cm::DeviceBuffer p_frames, p_pts[4], p_n;
   int p_cap = 0;

@@ -107,64 +107,119 @@ __device__ __forceinline__ int window_index(const CubeWindow& w, float x, float 
   return (i * 7 + j) * 7 + k;
 }
 
+// Squared distance from u (voxel units) to the slab [lo, hi) of a cell along one axis, 0 inside.
+__device__ __forceinline__ float slab_dist(float u, float lo, float hi) { float d = fmaxf(fmaxf(lo - u, u - hi), 0.f); return d; }
+
+__device__ __forceinline__ unsigned long long entry_key(const uint4& e) { return (unsigned long long)e.x | ((unsigned long long)e.y << 32); }
+
+// Candidates of one cell [start, start + count): loads are issued four at a time so they overlap.
 // kOrigIdx: tie-break index = original cloud index stored in pts[].w (stateless clouds); otherwise the pool slot.
 // filter: test every candidate's cube against the active window (only for queries near an inactive cube).
+template <bool kOrigIdx>
+__device__ __forceinline__ void scan_points(const GridView& g, unsigned int start, unsigned int count, float qx, float qy, float qz,
+                                            bool filter, Top5& best) {
+  for (unsigned int j0 = 0; j0 < count; j0 += 4) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (j0 + u < count) p[u] = __ldg(g.pts + start + j0 + u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j0 + u < count) {
+        if (filter) {
+          int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z);
+          if (wi < 0 || !g.window->active[wi]) continue;
+        }
+        float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
+        float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const int j = (int)(start + j0 + u);
+        top5_insert(best, d, kOrigIdx ? __float_as_int(p[u].w) : j, j);
+      }
+    }
+  }
+}
+
 template <bool kOrigIdx>
 __device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, bool filter,
                                           Top5& best) {
   unsigned int start, count;
   if (!grid_probe(g, x, y, z, &start, &count)) return;
-  for (unsigned int j = start; j < start + count; j++) {
-    float4 p = __ldg(g.pts + j);
-    if (filter) {
-      int wi = window_index(*g.window, p.x, p.y, p.z);
-      if (wi < 0 || !g.window->active[wi]) continue;
-    }
-    float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-    float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    top5_insert(best, d, kOrigIdx ? __float_as_int(p.w) : (int)j, (int)j);
-  }
+  scan_points<kOrigIdx>(g, start, count, qx, qy, qz, filter, best);
 }
 
-// Exact 5-NN of (qx,qy,qz) among the grid's points, provided the 5th neighbour lies within
-// (max_level + 0.48) * cell; beyond that the returned 5th distance is only an upper bound (>= the bound).
+// Exact 5-NN of (qx,qy,qz) among the grid's points, provided the 5th neighbour lies within sqrt(gate) (the
+// reference's 5.0 gate); beyond that the returned 5th distance is only an upper bound that is >= gate.
+// Level 0 visits the 2x2x2 cells nearest to the query (8 independent probes in flight), level L the shell that
+// extends the block by L cells on every side.  After level L every unseen point is farther than
+//   r_L = 0.98 * leaf * (min over axes of the distance, in voxels, from the query to the faces of the level-0 block
+//                        + L * kdiv)
+// (cells are unions of PCL voxels and the voxel index floor(p * inv_leaf) is monotone in p; the 2 % margin covers
+// the float rounding of p * inv_leaf).  Shell cells whose box lies farther than the current 5th distance (or the
+// gate) are skipped without a probe.
 template <bool kOrigIdx>
-__device__ __forceinline__ void knn5_search(const GridView& g, float qx, float qy, float qz, Top5& best) {
+__device__ __forceinline__ void knn5_search(const GridView& g, float qx, float qy, float qz, float gate, Top5& best) {
   top5_init(best);
-  float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
-  float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  const float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
+  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
   // keep the cast defined for absurd coordinates
   if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return;
   const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
-  const int cx = floor_div(vx, g.kdiv), cy = floor_div(vy, g.kdiv), cz = floor_div(vz, g.kdiv);
-  const float half = 0.5f * (float)g.kdiv;
+  const int k = g.kdiv;
+  const int cx = floor_div(vx, k), cy = floor_div(vy, k), cz = floor_div(vz, k);
+  const float half = 0.5f * (float)k;
   // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
-  int lx = cx + (((float)(vx - cx * g.kdiv) + (fx - flx)) < half ? -1 : 0);
-  int ly = cy + (((float)(vy - cy * g.kdiv) + (fy - fly)) < half ? -1 : 0);
-  int lz = cz + (((float)(vz - cz * g.kdiv) + (fz - flz)) < half ? -1 : 0);
+  const int lx = cx + (((float)(vx - cx * k) + (fx - flx)) < half ? -1 : 0);
+  const int ly = cy + (((float)(vy - cy * k) + (fy - fly)) < half ? -1 : 0);
+  const int lz = cz + (((float)(vz - cz * k) + (fz - flz)) < half ? -1 : 0);
   bool filter = false;
   if (g.window) {
     int wi = window_index(*g.window, qx, qy, qz);
     filter = (wi < 0) || !g.window->interior[wi];
   }
+  // ---- level 0: 8 probes issued together ----
+  {
+    unsigned long long key[8]; unsigned int h[8]; uint4 e[8];
 #pragma unroll
-  for (int dz = 0; dz < 2; dz++)
+    for (int c = 0; c < 8; c++) {
+      key[c] = pack_cell(lx + (c & 1), ly + ((c >> 1) & 1), lz + (c >> 2));
+      h[c] = hash_cell(key[c]) & g.mask;
+      e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h[c]));
+    }
 #pragma unroll
-    for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-      for (int dx = 0; dx < 2; dx++) scan_cell<kOrigIdx>(g, lx + dx, ly + dy, lz + dz, qx, qy, qz, filter, best);
+    for (int c = 0; c < 8; c++) {
+      unsigned long long kk = entry_key(e[c]);
+      while (kk != key[c] && kk != CM_EMPTY_KEY) {   // linear probing
+        h[c] = (h[c] + 1) & g.mask;
+        e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h[c]));
+        kk = entry_key(e[c]);
+      }
+      if (kk == key[c]) scan_points<kOrigIdx>(g, e[c].z, e[c].w, qx, qy, qz, filter, best);
+    }
+  }
+  // distance (voxel units) from the query to the nearest face of the level-0 block
+  const float lox = (float)(lx * k), loy = (float)(ly * k), loz = (float)(lz * k);
+  const float span = (float)(2 * k);
+  float m0 = fminf(fminf(fx - lox, lox + span - fx), fminf(fminf(fy - loy, loy + span - fy), fminf(fz - loz, loz + span - fz)));
+  const float leaf = g.cell / (float)k;
   for (int L = 1; L <= g.max_level; L++) {
-    float r = ((float)(L - 1) + 0.48f) * g.cell;   // radius guaranteed by the previous level
+    const float r = 0.98f * leaf * (m0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
     if (best.d[4] < r * r) return;
-    int n = 2 + 2 * L;
+    const int n = 2 + 2 * L;
+    const float kf = (float)k;
     for (int dz = 0; dz < n; dz++)
       for (int dy = 0; dy < n; dy++) {
-        bool shell_row = (dz == 0 || dz == n - 1 || dy == 0 || dy == n - 1);
-        if (shell_row) {
-          for (int dx = 0; dx < n; dx++) scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
-        } else {
-          scan_cell<kOrigIdx>(g, lx - L, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
-          scan_cell<kOrigIdx>(g, lx - L + n - 1, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
+        const bool shell_row = (dz == 0 || dz == n - 1 || dy == 0 || dy == n - 1);
+        const int step = shell_row ? 1 : (n - 1);
+        const float cyl = (float)((ly - L + dy) * k), czl = (float)((lz - L + dz) * k);
+        const float dyv = slab_dist(fy, cyl, cyl + kf), dzv = slab_dist(fz, czl, czl + kf);
+        for (int dx = 0; dx < n; dx += step) {
+          const float cxl = (float)((lx - L + dx) * k);
+          const float dxv = slab_dist(fx, cxl, cxl + kf);
+          // lower bound (2 % margin) of the distance from the query to anything in this cell
+          const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);
+          const float bound = fminf(best.d[4], gate);
+          if (lb * lb >= bound) continue;
+          scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
         }
       }
   }

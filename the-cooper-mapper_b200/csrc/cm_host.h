@@ -47,7 +47,7 @@ struct GridStorage {
 };
 
 int grid_max_level(float cell, float gate);
-void launch_knn5(const GridView& g, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t stream);
+void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d_idx, float* d_d2, cudaStream_t stream);
 
 struct MatchLaunch {
   int nstreams;
@@ -62,15 +62,32 @@ struct MatchLaunch {
   IterTrace* trace;                           // optional device [nstreams][max_iterations]
   int* nn;                                    // optional device [max_iterations][nstreams][cap][5]
   int orig_idx;                               // grids carry original indices in pts[].w
+  int max_queries = 0;                        // host-known upper bound of n_corner[s] + n_surf[s] (0: use the capacities)
   MatchParamsDev prm;
 };
-void launch_match(const MatchLaunch& m, cudaStream_t stream);
+// optional per-kernel timing of the dominant kernel (corr_kernel): event pairs recorded on the launching stream
+struct KernelProfiler {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  void begin(cudaStream_t s) { if (!enabled) return; grow(); cudaEventRecord(ev[used], s); }
+  void end(cudaStream_t s) { if (!enabled) return; cudaEventRecord(ev[used + 1], s); used += 2; }
+  void grow() { while (ev.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); } }
+  // sums the recorded intervals (call after the stream is synchronized) and resets
+  double drain_ms(int* launches) {
+    double tot = 0; int n = 0;
+    for (size_t i = 0; i + 1 < used; i += 2) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { tot += ms; n++; } }
+    used = 0; if (launches) *launches = n; return tot;
+  }
+};
+void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
 
 // K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes
 // out[s*cap_out .. +n_out[s]).
 struct VoxelFilter {
   DeviceBuffer box, keys_a, keys_b, vals_a, vals_b, flags, rank, seg_first, temp;
-  void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out, int cap_out,
+  // max_n: host-known upper bound of n_in[s] (<= 0: cap_in)
+  void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, int max_n, float leaf, float4* d_out, int* d_n_out, int cap_out,
            int* d_overflow, cudaStream_t stream);
 };
 
@@ -97,7 +114,7 @@ struct DeviceMap {
   void create(int nstreams, const MapConfig& c, cudaStream_t stream);
   void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream);   // also refreshes the GridViews
   // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
-  void insert(int cls, const float4* d_pts, const int* d_n, int cap, const MatchState* d_state, const float* d_tf, cudaStream_t stream);
+  void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream);
   size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);
 };
 

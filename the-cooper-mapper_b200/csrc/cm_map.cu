@@ -30,17 +30,17 @@ __device__ __forceinline__ int world_to_cube_axis(float x, float cube_size, int 
 
 // ---- 1. transform + key ------------------------------------------------------------------------------------------
 // key = stream (8 bits) | cube parity (3 bits) | voxel z, y, x (17 bits each, biased)
-__global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int nstreams,
+__global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int max_n, int nstreams,
                                const MatchState* __restrict__ state, const float* __restrict__ tf_override, MapClassDev* maps,
                                float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
                                int* __restrict__ flags) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (size_t)nstreams * cap) return;
-  int s = (int)(g / cap), i = (int)(g - (size_t)s * cap);
+  if (g >= (size_t)nstreams * max_n) return;
+  int s = (int)(g / max_n), i = (int)(g - (size_t)s * max_n);
   unsigned long long key = CM_MAP_PAD;
   if (i < n_pts[s]) {
     const MapClassDev& m = maps[s];
-    float4 p = pts[g];
+    float4 p = pts[(size_t)s * cap + i];
     float R[9], t[3];
     if (tf_override) { for (int k = 0; k < 9; k++) R[k] = tf_override[s * 12 + k]; for (int k = 0; k < 3; k++) t[k] = tf_override[s * 12 + 9 + k]; }
     else { for (int k = 0; k < 9; k++) R[k] = state[s].R[k]; for (int k = 0; k < 3; k++) t[k] = state[s].pose[3 + k]; }
@@ -178,23 +178,27 @@ __global__ void map_clear_kernel(CellEntry* e, unsigned int* cellcap, unsigned i
   if (i < cap) { e[i].key = CM_EMPTY_KEY; e[i].start = 0; e[i].count = 0; cellcap[i] = 0; pend[i] = 0; }
 }
 
-// searchable size of the surround map (sum of the valid cubes) -> GridView.npts, and the rest of the view
+// searchable size of the surround map (sum of the valid cubes) -> GridView.npts, and the rest of the view.
+// One warp per stream.
 __global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, GridView* views, int nstreams, float gate) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nstreams) return;
   MapClassDev& m = maps[s];
   const CubeWindow& w = windows[s];
-  m.origin[0] = w.origin[0]; m.origin[1] = w.origin[1]; m.origin[2] = w.origin[2];
   int total = 0;
-  for (int a = 0; a < 343; a++) {
+  for (int a = lane; a < 343; a += 32) {
     if (!w.active[a]) continue;
     int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
     total += m.cube_count[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane != 0) return;
+  m.origin[0] = w.origin[0]; m.origin[1] = w.origin[1]; m.origin[2] = w.origin[2];
   GridView v;
   v.entries = m.entries; v.pts = m.pts; v.mask = m.mask; v.inv_leaf = m.inv_leaf; v.kdiv = m.kdiv; v.cell = (float)m.kdiv * m.leaf;
   v.npts = total;
-  int L = (int)ceilf(sqrtf(gate) / v.cell - 0.48f);
+  int L = (int)ceilf(sqrtf(gate) / (0.98f * v.cell) - 0.5f);
   v.max_level = L < 0 ? 0 : L;
   v.window = windows + s;
   views[s] = v;
@@ -275,14 +279,15 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
 void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream) {
   cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
   for (int cls = 0; cls < 2; cls++)
-    CM_LAUNCH(map_view_kernel, (nstreams + 63) / 64, 64, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
+    CM_LAUNCH(map_view_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
               (GridView*)views[cls].p, nstreams, gate);
 }
 
-void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, const MatchState* d_state, const float* d_tf,
+void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf,
                        cudaStream_t stream) {
   if (cap <= 0) return;
-  const size_t n = (size_t)nstreams * cap;
+  if (max_n <= 0 || max_n > cap) max_n = cap;   // host-known upper bound of d_n[s]
+  const size_t n = (size_t)nstreams * max_n;
   world.reserve(n * sizeof(float4));
   keys_a.reserve(n * 8); keys_b.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4);
   pending.reserve(n * sizeof(PendingAdd));
@@ -292,7 +297,7 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, co
   temp.reserve(tb);
   const unsigned int nb = (unsigned int)((n + 255) / 256);
   cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), stream);
-  CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
+  CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
             (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)flags.p);
   tb = temp.cap;
   cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,

@@ -115,8 +115,8 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
     MapConfig mc;
     mc.max_corner = max_corner_points; mc.max_surf = max_surf_points;
     mc.leaf_corner = c.map_filter_corner; mc.leaf_surf = c.map_filter_surf;
-    mc.kdiv_corner = default_kdiv(c.cell_corner, c.map_filter_corner, 6);
-    mc.kdiv_surf = default_kdiv(c.cell_surf, c.map_filter_surf, 3);
+    mc.kdiv_corner = default_kdiv(c.cell_corner, c.map_filter_corner, 8);
+    mc.kdiv_surf = default_kdiv(c.cell_surf, c.map_filter_surf, 4);
     mc.cube_size = c.cube_size;
     mc.dims[0] = c.cube_w; mc.dims[1] = c.cube_h; mc.dims[2] = c.cube_d;
     for (int k = 0; k < 3; k++) mc.origin[k] = (int)round((mc.dims[k] - 1) / 2.0);   // FeatureMap.h:63-65
@@ -137,8 +137,9 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
 
 // Core of the stage on DEVICE clouds.  d_corner/d_surf: [S][cap] with device counts d_n (corner counts then surf counts,
 // [2][S]).  h_odom: S odometry poses (host).  Outputs on the host: mapped poses and stats.
+// max_in_c / max_in_s: host-known upper bounds of the input counts (sizes the sorts).
 static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, const float4* d_surf, int cap_s, const int* d_n,
-                               const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats) {
+                               int max_in_c, int max_in_s, const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   cudaStream_t st = ctx->stream;
@@ -162,8 +163,14 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   ctx->d_flag.reserve(sizeof(int));
   CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
   int* d_nds = (int*)ctx->m_n_ds.p;
-  ctx->voxel.run(S, d_corner, d_n, cap_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, st);
-  ctx->voxel.run(S, d_surf, d_n + S, cap_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st);
+  ctx->voxel.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, st);
+  ctx->voxel.run(S, d_surf, d_n + S, cap_s, max_in_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st);
+  // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
+  std::vector<int> nds(2 * S);
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  int max_c = 1, max_s = 1, max_q = 1;
+  for (int s = 0; s < S; s++) { max_c = std::max(max_c, nds[s]); max_s = std::max(max_s, nds[S + s]); max_q = std::max(max_q, nds[s] + nds[S + s]); }
   // prepareFeatureSurround: cube window -> searchable views
   ctx->map.set_windows(wins.data(), prm.knn_gate, st);
   // optimizeTransform
@@ -178,22 +185,26 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.n_corner = d_nds; m.n_surf = d_nds + S; m.cap_corner = cap_c; m.cap_surf = cap_s;
   m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
   m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p;
-  m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm;
-  launch_match(m, st);
+  m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm; m.max_queries = max_q;
+  launch_match(m, st, &ctx->prof);
   // featureMapUpdate
-  ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, (const MatchState*)ctx->m_state.p, nullptr, st);
-  ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+  ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
+  ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);
   // results
   std::vector<MatchState> hs(S);
-  std::vector<int> nds(2 * S);
   int flags[8];
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   CM_CUDA_CHECK(ctx, cudaGetLastError());
   if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
   if (flags[2] || flags[3]) return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+  ctx->last_query_iters = 0; ctx->last_queries = 0; ctx->last_inserted = 0;
+  for (int s = 0; s < S; s++) {
+    const unsigned long long q = (unsigned long long)(nds[s] + nds[S + s]);
+    const int evals = hs[s].iterations + ((hs[s].flags & CM_F_TOO_FEW_MATCHES) ? 1 : 0);   // correspondence passes actually run
+    ctx->last_query_iters += q * (unsigned long long)evals; ctx->last_queries += q; ctx->last_inserted += q;
+  }
   for (int s = 0; s < S; s++) {
     MappingStream& ms = ctx->mstreams[s];
     twist_to_iso(hs[s].pose, ms.mappedNew);   // ScanMatch.cpp:358 (always, also when the map was too small)
@@ -222,8 +233,10 @@ int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* cor
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_surf_in.p, surf, (size_t)S * cap_surf * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_n_in.p, n_corner, sizeof(int) * S, cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync((int*)ctx->m_n_in.p + S, n_surf, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    int mc_ = 1, ms_ = 1;
+    for (int s = 0; s < S; s++) { mc_ = std::max(mc_, n_corner[s]); ms_ = std::max(ms_, n_surf[s]); }
     return mapping_process_dev(ctx, (const float4*)ctx->m_corner_in.p, cap_corner, (const float4*)ctx->m_surf_in.p, cap_surf,
-                               (const int*)ctx->m_n_in.p, odom, mapped, stats);
+                               (const int*)ctx->m_n_in.p, mc_, ms_, odom, mapped, stats);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
@@ -247,8 +260,18 @@ static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols,
   L.out_n = (int*)ctx->p_n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
   ctx->scanreg.run(L, st);
   CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)ctx->p_n.p + 2 * S, (int*)ctx->p_n.p, S);
-  return mapping_process_dev(ctx, (const float4*)ctx->p_pts[1].p, cap, (const float4*)ctx->p_pts[3].p, cap, (const int*)ctx->p_n.p, odom,
-                             mapped, stats);
+  // feature-cloud sizes: needed on the host to size the frame voxel filters (and for the byte accounting)
+  std::vector<int> n5(5 * S);
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5.data(), (const int*)ctx->p_n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  int max_c = 1, max_s = 1;
+  ctx->last_features = 0;
+  for (int s = 0; s < S; s++) {
+    max_c = std::max(max_c, n5[s * 5 + 1]); max_s = std::max(max_s, n5[s * 5 + 3]);
+    for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)n5[s * 5 + k];
+  }
+  return mapping_process_dev(ctx, (const float4*)ctx->p_pts[1].p, cap, (const float4*)ctx->p_pts[3].p, cap, (const int*)ctx->p_n.p, max_c,
+                             max_s, odom, mapped, stats);
 }
 
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
@@ -297,8 +320,8 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_n_in.p, n_corner, sizeof(int) * S, cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync((int*)ctx->m_n_in.p + S, n_surf, sizeof(int) * S, cudaMemcpyHostToDevice, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_tf.p, tf, sizeof(float) * 12 * S, cudaMemcpyHostToDevice, st));
-    ctx->map.insert(0, (const float4*)ctx->m_corner_in.p, (const int*)ctx->m_n_in.p, cap_corner, nullptr, (const float*)ctx->m_tf.p, st);
-    ctx->map.insert(1, (const float4*)ctx->m_surf_in.p, (const int*)ctx->m_n_in.p + S, cap_surf, nullptr, (const float*)ctx->m_tf.p, st);
+    ctx->map.insert(0, (const float4*)ctx->m_corner_in.p, (const int*)ctx->m_n_in.p, cap_corner, 0, nullptr, (const float*)ctx->m_tf.p, st);
+    ctx->map.insert(1, (const float4*)ctx->m_surf_in.p, (const int*)ctx->m_n_in.p + S, cap_surf, 0, nullptr, (const float*)ctx->m_tf.p, st);
     int flags[8];
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
@@ -332,6 +355,35 @@ int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, in
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
+  return CM_OK;
+}
+
+/* ---- measurement helpers (bench.py) -------------------------------------------------------------------------------- */
+int cm_timer_record(cm_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 1) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->timer[which]) CM_CUDA_CHECK(ctx, cudaEventCreate(&ctx->timer[which]));
+  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->timer[which], ctx->stream));
+  return CM_OK;
+}
+int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms) {
+  if (!ctx || !ms || !ctx->timer[0] || !ctx->timer[1]) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->timer[1]));
+  CM_CUDA_CHECK(ctx, cudaEventElapsedTime(ms, ctx->timer[0], ctx->timer[1]));
+  return CM_OK;
+}
+int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = on != 0; return CM_OK; }
+int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches) {
+  if (!ctx || !kernel_ms) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *kernel_ms = ctx->prof.drain_ms(launches);
+  return CM_OK;
+}
+int cm_last_step_counters(cm_ctx* ctx, unsigned long long* out4) {
+  if (!ctx || !out4) return CM_ERR_ARG;
+  out4[0] = ctx->last_query_iters; out4[1] = ctx->last_queries; out4[2] = ctx->last_inserted; out4[3] = ctx->last_features;
   return CM_OK;
 }
 

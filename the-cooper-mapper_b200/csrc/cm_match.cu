@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) corr_kernel(CorrArgs a) {
     transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
     const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
     Top5 best;
-    knn5_search<kOrigIdx>(g, sx, sy, sz, best);
+    knn5_search<kOrigIdx>(g, sx, sy, sz, a.prm.knn_gate, best);
     RowOut row;
 #pragma unroll
     for (int k = 0; k < 6; k++) row.a[k] = 0.f;
@@ -404,11 +404,11 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // ============================================================================================================
 // Stand-alone exact 5-NN (test hook and operator): queries already in the map frame.
 // ============================================================================================================
-__global__ void knn5_kernel(GridView g, const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+__global__ void knn5_kernel(GridView g, const float* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ d2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   Top5 best;
-  knn5_search<true>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], best);
+  knn5_search<true>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], gate, best);
 #pragma unroll
   for (int k = 0; k < 5; k++) {
     idx[5 * i + k] = best.slot[k] < 0 ? -1 : best.idx[k];
@@ -421,8 +421,9 @@ __global__ void knn5_kernel(GridView g, const float* __restrict__ q, int nq, int
 // ============================================================================================================
 static inline unsigned int next_pow2(unsigned int v) { unsigned int p = 64; while (p < v) p <<= 1; return p; }
 
+// last shell so that 0.98 * cell * (0.5 + L) >= sqrt(gate) (worst case: query in the middle of the level-0 block)
 int grid_max_level(float cell, float gate) {
-  int L = (int)ceilf(sqrtf(gate) / cell - 0.48f);
+  int L = (int)ceilf(sqrtf(gate) / (0.98f * cell) - 0.5f);
   return L < 0 ? 0 : L;
 }
 
@@ -450,11 +451,11 @@ void GridStorage::build(const float4* d_pts, int n, float cell_size, float gate,
   view.max_level = grid_max_level(cell_size, gate);
 }
 
-void launch_knn5(const GridView& g, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t stream) {
-  if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, d_idx, d_d2);
+void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d_idx, float* d_d2, cudaStream_t stream) {
+  if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, gate, d_idx, d_d2);
 }
 
-void launch_match(const MatchLaunch& m, cudaStream_t stream) {
+void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof) {
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
   CorrArgs ca;
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
@@ -464,13 +465,15 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream) {
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm;
   int capQ = m.cap_corner + m.cap_surf;
-  int bx = (capQ + 255) / 256;
+  int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 255) / 256;
   if (bx < 1) bx = 1;
   dim3 grid(bx, m.nstreams);
   for (int it = 0; it < m.prm.max_iterations; it++) {
     ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
+    if (prof) prof->begin(stream);
     if (m.orig_idx) CM_LAUNCH(corr_kernel<true>, grid, 256, 0, stream, ca);
     else CM_LAUNCH(corr_kernel<false>, grid, 256, 0, stream, ca);
+    if (prof) prof->end(stream);
     sa.iter = it;
     CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
     CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, (const double*)m.sums, m.nstreams);

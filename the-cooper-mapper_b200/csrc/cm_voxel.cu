@@ -79,15 +79,16 @@ __global__ void __launch_bounds__(256) vox_bbox_kernel(const float4* __restrict_
 
 #define CM_VOX_PAD 0xFFFFFFFFFFFFFFFFull
 
-__global__ void vox_key_kernel(const float4* __restrict__ in, const int* __restrict__ n_in, int cap_in, int nseg, float inv,
+__global__ void vox_key_kernel(const float4* __restrict__ in, const int* __restrict__ n_in, int cap_in, int max_n, int nseg, float inv,
                                const VoxBox* __restrict__ box, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (size_t)nseg * cap_in) return;
-  int s = (int)(g / cap_in), i = (int)(g - (size_t)s * cap_in);
+  if (g >= (size_t)nseg * max_n) return;
+  int s = (int)(g / max_n), i = (int)(g - (size_t)s * max_n);
+  const size_t src = (size_t)s * cap_in + i;
   unsigned long long key = CM_VOX_PAD;
   if (i < n_in[s]) {
     const VoxBox b = box[s];
-    float4 q = in[g];
+    float4 q = in[src];
     if (b.passthrough) {
       key = ((unsigned long long)s << 32) | (unsigned int)i;   // identity order
     } else if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
@@ -100,7 +101,7 @@ __global__ void vox_key_kernel(const float4* __restrict__ in, const int* __restr
     }
   }
   keys[g] = key;
-  vals[g] = (unsigned int)g;
+  vals[g] = (unsigned int)src;
 }
 
 // head flag = first element of a (segment, idx) run among the sorted keys
@@ -150,10 +151,11 @@ __global__ void vox_zero_counts_kernel(const int* __restrict__ n_in, const VoxBo
   if (s < nseg) n_out[s] = 0;
 }
 
-void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out,
+void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, int max_n, float leaf, float4* d_out, int* d_n_out,
                       int cap_out, int* d_overflow, cudaStream_t stream) {
   if (nseg <= 0 || cap_in <= 0) return;
-  const size_t n = (size_t)nseg * cap_in;
+  if (max_n <= 0 || max_n > cap_in) max_n = cap_in;   // host-known upper bound of n_in[s]: only that many slots per segment are sorted
+  const size_t n = (size_t)nseg * max_n;
   const float inv = 1.0f / leaf;   // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
   box.reserve(sizeof(VoxBox) * nseg);
   keys_a.reserve(n * 8); keys_b.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4);
@@ -169,7 +171,7 @@ void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_i
   const unsigned int nb = (unsigned int)((n + T - 1) / T);
   CM_LAUNCH(vox_bbox_kernel, nseg, 256, 0, stream, d_in, d_n_in, cap_in, inv, (VoxBox*)box.p);
   CM_LAUNCH(vox_zero_counts_kernel, (nseg + 63) / 64, 64, 0, stream, d_n_in, (const VoxBox*)box.p, nseg, d_n_out);
-  CM_LAUNCH(vox_key_kernel, nb, T, 0, stream, d_in, d_n_in, cap_in, nseg, inv, (const VoxBox*)box.p, (unsigned long long*)keys_a.p,
+  CM_LAUNCH(vox_key_kernel, nb, T, 0, stream, d_in, d_n_in, cap_in, max_n, nseg, inv, (const VoxBox*)box.p, (unsigned long long*)keys_a.p,
             (unsigned int*)vals_a.p);
   size_t tb = temp.cap;
   cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
