@@ -140,6 +140,7 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     ctx->d_pose.reserve(6 * sizeof(float));
     ctx->d_state.reserve(sizeof(MatchState));
     ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
+    ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int));
     ctx->d_sums.reserve(32 * sizeof(double));
     const bool want_nn = nn_corner || nn_surf;
     if (trace) ctx->d_trace.reserve(sizeof(IterTrace) * prm.max_iterations);
@@ -166,6 +167,7 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     m.pose_in = (const float*)ctx->d_pose.p;
     m.state = (MatchState*)ctx->d_state.p;
     m.rows = (RowOut*)ctx->d_rows.p;
+    m.nn_slot = (int*)ctx->d_slots.p;
     m.sums = (double*)ctx->d_sums.p;
     m.trace = trace ? (IterTrace*)ctx->d_trace.p : nullptr;
     m.nn = want_nn ? (int*)ctx->d_nn.p : nullptr;

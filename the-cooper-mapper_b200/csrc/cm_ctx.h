@@ -23,7 +23,7 @@ struct cm_ctx {
   std::string err;
   // scratch for the host-buffer entry points
   cm::DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
-  cm::DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_sums, d_trace, d_nn;
+  cm::DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_slots, d_sums, d_trace, d_nn;
   cm::GridStorage grid_a, grid_b;
   cm::VoxelFilter voxel;
   cm::ScanRegistrationGpu scanreg;
@@ -33,7 +33,7 @@ struct cm_ctx {
   int map_streams = 0;
   cm::DeviceMap map;
   std::vector<cm::MappingStream> mstreams;
-  cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
+  cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_slots, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
   cm::KernelProfiler prof;
   cudaEvent_t timer[2] = {nullptr, nullptr};

@@ -147,81 +147,152 @@ __device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z
   scan_points<kOrigIdx>(g, start, count, qx, qy, qz, filter, best);
 }
 
-// Exact 5-NN of (qx,qy,qz) among the grid's points, provided the 5th neighbour lies within sqrt(gate) (the
-// reference's 5.0 gate); beyond that the returned 5th distance is only an upper bound that is >= gate.
-// Level 0 visits the 2x2x2 cells nearest to the query (8 independent probes in flight), level L the shell that
-// extends the block by L cells on every side.  After level L every unseen point is farther than
+// ------------------------------------------------------------------------------------------------------------------
+// Exact 5-NN of one query per thread, executed by FULL WARPS (every lane must call, `valid` masks idle lanes).
+// Exact provided the 5th neighbour lies within sqrt(gate) (the reference's 5.0 gate); beyond that the returned 5th
+// distance is only an upper bound that is >= gate.
+//
+// Level 0 (per thread): the 2x2x2 cells nearest to the query -- 8 probes in two batches of 4 independent loads, the
+// hit cells' point ranges are staged in shared memory and scanned in ONE flattened loop (a warp iterates
+// max-over-lanes of the total candidate count, not the sum over cells of the per-cell maxima).
+// Level L >= 1 (per warp): the few queries whose 5th distance is not yet provably final are finished one at a time
+// by the whole warp: the lanes split the cells of the shell that extends the block by L cells on every side, keep
+// lane-local 5-best lists, and a shuffle merge feeds the owning lane.  After level L every unseen point is farther than
 //   r_L = 0.98 * leaf * (min over axes of the distance, in voxels, from the query to the faces of the level-0 block
 //                        + L * kdiv)
 // (cells are unions of PCL voxels and the voxel index floor(p * inv_leaf) is monotone in p; the 2 % margin covers
 // the float rounding of p * inv_leaf).  Shell cells whose box lies farther than the current 5th distance (or the
 // gate) are skipped without a probe.
+// rng: shared memory, 8 * blockDim.x uint2 (this thread uses rng[c * blockDim.x + threadIdx.x]).
 template <bool kOrigIdx>
-__device__ __forceinline__ void knn5_search(const GridView& g, float qx, float qy, float qz, float gate, Top5& best) {
+__device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float qx, float qy, float qz, float gate, uint2* rng,
+                                            Top5& best) {
   top5_init(best);
+  const unsigned int FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int k = g.kdiv;
   const float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
   const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-  // keep the cast defined for absurd coordinates
-  if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return;
-  const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
-  const int k = g.kdiv;
-  const int cx = floor_div(vx, k), cy = floor_div(vy, k), cz = floor_div(vz, k);
-  const float half = 0.5f * (float)k;
-  // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
-  const int lx = cx + (((float)(vx - cx * k) + (fx - flx)) < half ? -1 : 0);
-  const int ly = cy + (((float)(vy - cy * k) + (fy - fly)) < half ? -1 : 0);
-  const int lz = cz + (((float)(vz - cz * k) + (fz - flz)) < half ? -1 : 0);
+  // keep the casts defined for absurd coordinates
+  valid = valid && (fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f);
+  int lx = 0, ly = 0, lz = 0;
   bool filter = false;
-  if (g.window) {
-    int wi = window_index(*g.window, qx, qy, qz);
-    filter = (wi < 0) || !g.window->interior[wi];
-  }
-  // ---- level 0: 8 probes issued together ----
-  {
-    unsigned long long key[8]; unsigned int h[8]; uint4 e[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      key[c] = pack_cell(lx + (c & 1), ly + ((c >> 1) & 1), lz + (c >> 2));
-      h[c] = hash_cell(key[c]) & g.mask;
-      e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h[c]));
+  float m0 = 0.f;
+  if (valid) {
+    const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
+    const int cx = floor_div(vx, k), cy = floor_div(vy, k), cz = floor_div(vz, k);
+    const float half = 0.5f * (float)k;
+    // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
+    lx = cx + (((float)(vx - cx * k) + (fx - flx)) < half ? -1 : 0);
+    ly = cy + (((float)(vy - cy * k) + (fy - fly)) < half ? -1 : 0);
+    lz = cz + (((float)(vz - cz * k) + (fz - flz)) < half ? -1 : 0);
+    if (g.window) {
+      int wi = window_index(*g.window, qx, qy, qz);
+      filter = (wi < 0) || !g.window->interior[wi];
     }
+    // ---- level 0: probes ----
+    int nr = 0;
+    uint2* my = rng + threadIdx.x;
+    const int stride = blockDim.x;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      unsigned long long kk = entry_key(e[c]);
-      while (kk != key[c] && kk != CM_EMPTY_KEY) {   // linear probing
-        h[c] = (h[c] + 1) & g.mask;
-        e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h[c]));
-        kk = entry_key(e[c]);
+    for (int b = 0; b < 2; b++) {
+      unsigned long long key[4]; uint4 e[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int cc = b * 4 + c;
+        key[c] = pack_cell(lx + (cc & 1), ly + ((cc >> 1) & 1), lz + (cc >> 2));
+        e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + (hash_cell(key[c]) & g.mask)));
       }
-      if (kk == key[c]) scan_points<kOrigIdx>(g, e[c].z, e[c].w, qx, qy, qz, filter, best);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        unsigned long long kk = entry_key(e[c]);
+        if (kk != key[c] && kk != CM_EMPTY_KEY) {   // linear probing (rare)
+          unsigned int h = hash_cell(key[c]) & g.mask;
+          do { h = (h + 1) & g.mask; e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h)); kk = entry_key(e[c]); }
+          while (kk != key[c] && kk != CM_EMPTY_KEY);
+        }
+        if (kk == key[c] && e[c].w > 0) { my[nr * stride] = make_uint2(e[c].z, e[c].w); nr++; }
+      }
     }
-  }
-  // distance (voxel units) from the query to the nearest face of the level-0 block
-  const float lox = (float)(lx * k), loy = (float)(ly * k), loz = (float)(lz * k);
-  const float span = (float)(2 * k);
-  float m0 = fminf(fminf(fx - lox, lox + span - fx), fminf(fminf(fy - loy, loy + span - fy), fminf(fz - loz, loz + span - fz)));
-  const float leaf = g.cell / (float)k;
-  for (int L = 1; L <= g.max_level; L++) {
-    const float r = 0.98f * leaf * (m0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
-    if (best.d[4] < r * r) return;
-    const int n = 2 + 2 * L;
-    const float kf = (float)k;
-    for (int dz = 0; dz < n; dz++)
-      for (int dy = 0; dy < n; dy++) {
-        const bool shell_row = (dz == 0 || dz == n - 1 || dy == 0 || dy == n - 1);
-        const int step = shell_row ? 1 : (n - 1);
-        const float cyl = (float)((ly - L + dy) * k), czl = (float)((lz - L + dz) * k);
-        const float dyv = slab_dist(fy, cyl, cyl + kf), dzv = slab_dist(fz, czl, czl + kf);
-        for (int dx = 0; dx < n; dx += step) {
-          const float cxl = (float)((lx - L + dx) * k);
-          const float dxv = slab_dist(fx, cxl, cxl + kf);
-          // lower bound (2 % margin) of the distance from the query to anything in this cell
-          const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);
-          const float bound = fminf(best.d[4], gate);
-          if (lb * lb >= bound) continue;
-          scan_cell<kOrigIdx>(g, lx - L + dx, ly - L + dy, lz - L + dz, qx, qy, qz, filter, best);
+    // ---- level 0: one flattened candidate loop ----
+    int ci = 0; unsigned int j0 = 0;
+    uint2 r = nr ? my[0] : make_uint2(0u, 0u);
+    while (ci < nr) {
+      const unsigned int left = r.y - j0;
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((unsigned int)u < left) p[u] = __ldg(g.pts + r.x + j0 + u);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if ((unsigned int)u < left) {
+          bool ok = true;
+          if (filter) { int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z); ok = (wi >= 0) && g.window->active[wi]; }
+          if (ok) {
+            float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
+            float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const int j = (int)(r.x + j0 + u);
+            top5_insert(best, d, kOrigIdx ? __float_as_int(p[u].w) : j, j);
+          }
         }
       }
+      j0 += 4;
+      if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
+    }
+    // distance (voxel units) from the query to the nearest face of the level-0 block
+    const float lox = (float)(lx * k), loy = (float)(ly * k), loz = (float)(lz * k);
+    const float span = (float)(2 * k);
+    m0 = fminf(fminf(fx - lox, lox + span - fx), fminf(fminf(fy - loy, loy + span - fy), fminf(fz - loz, loz + span - fz)));
+  }
+  // ---- levels >= 1: warp-cooperative, one unresolved query at a time ----
+  const float leaf = g.cell / (float)k;
+  bool need = false;
+  if (valid && g.max_level >= 1) { const float r0 = 0.98f * leaf * m0; need = !(best.d[4] < r0 * r0); }
+  unsigned int hard = __ballot_sync(FULL, need);
+  while (hard) {
+    const int h = __ffs(hard) - 1;
+    hard &= hard - 1;
+    const float bqx = __shfl_sync(FULL, qx, h), bqy = __shfl_sync(FULL, qy, h), bqz = __shfl_sync(FULL, qz, h);
+    const float bfx = __shfl_sync(FULL, fx, h), bfy = __shfl_sync(FULL, fy, h), bfz = __shfl_sync(FULL, fz, h);
+    const int blx = __shfl_sync(FULL, lx, h), bly = __shfl_sync(FULL, ly, h), blz = __shfl_sync(FULL, lz, h);
+    const float bm0 = __shfl_sync(FULL, m0, h);
+    const bool bfilter = __shfl_sync(FULL, filter ? 1 : 0, h) != 0;
+    float bd5 = __shfl_sync(FULL, best.d[4], h);
+    const float kf = (float)k;
+    for (int L = 1; L <= g.max_level; L++) {
+      const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
+      if (bd5 < rr * rr) break;
+      const int n = 2 + 2 * L, ncells = n * n * n;
+      const float bound = fminf(bd5, gate);
+      Top5 loc;
+      top5_init(loc);
+      for (int t = lane; t < ncells; t += 32) {
+        const int dz = t / (n * n), dy = (t / n) % n, dx = t % n;
+        if (dx > 0 && dx < n - 1 && dy > 0 && dy < n - 1 && dz > 0 && dz < n - 1) continue;   // visited at the previous levels
+        const float cxl = (float)((blx - L + dx) * k), cyl = (float)((bly - L + dy) * k), czl = (float)((blz - L + dz) * k);
+        const float dxv = slab_dist(bfx, cxl, cxl + kf), dyv = slab_dist(bfy, cyl, cyl + kf), dzv = slab_dist(bfz, czl, czl + kf);
+        const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);   // lower bound of the distance to this cell
+        if (lb * lb >= bound) continue;
+        scan_cell<kOrigIdx>(g, blx - L + dx, bly - L + dy, blz - L + dz, bqx, bqy, bqz, bfilter, loc);
+      }
+      // merge the lane-local lists into the owner's list: at most 5 winners can enter
+      for (int round = 0; round < 5; round++) {
+        const unsigned int dbits = __float_as_uint(loc.d[0]);   // distances are >= 0: the bit pattern orders like the value
+        const unsigned int mind = __reduce_min_sync(FULL, dbits);
+        if (mind == __float_as_uint(FLT_MAX)) break;
+        const unsigned int cand = (dbits == mind) ? (unsigned int)loc.idx[0] : 0xFFFFFFFFu;
+        const unsigned int mini = __reduce_min_sync(FULL, cand);
+        const int src = __ffs(__ballot_sync(FULL, dbits == mind && (unsigned int)loc.idx[0] == mini)) - 1;
+        const int wslot = __shfl_sync(FULL, loc.slot[0], src);
+        if (lane == h) top5_insert(best, __uint_as_float(mind), (int)mini, wslot);
+        if (lane == src) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) { loc.d[u] = loc.d[u + 1]; loc.idx[u] = loc.idx[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
+          loc.d[4] = FLT_MAX; loc.idx[4] = 0x7fffffff; loc.slot[4] = -1;
+        }
+      }
+      bd5 = __shfl_sync(FULL, best.d[4], h);
+    }
   }
 }
 

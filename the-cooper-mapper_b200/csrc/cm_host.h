@@ -58,6 +58,7 @@ struct MatchLaunch {
   const float* pose_in;                       // device [nstreams][6]
   MatchState* state;                          // device [nstreams]
   RowOut* rows;                               // device [nstreams][cap_corner + cap_surf]
+  int* nn_slot;                               // device [nstreams][cap_corner + cap_surf][5]
   double* sums;                               // device [nstreams][32] (A^T A / A^T b partial sums)
   IterTrace* trace;                           // optional device [nstreams][max_iterations]
   int* nn;                                    // optional device [max_iterations][nstreams][cap][5]

@@ -177,6 +177,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   ctx->m_pose.reserve(sizeof(float) * 6 * S);
   ctx->m_state.reserve(sizeof(MatchState) * S);
   ctx->m_rows.reserve((size_t)S * (cap_c + cap_s) * sizeof(RowOut));
+  ctx->m_slots.reserve((size_t)S * (cap_c + cap_s) * 5 * sizeof(int));
   ctx->m_sums.reserve(sizeof(double) * 32 * S);
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_pose.p, pose_in.data(), sizeof(float) * 6 * S, cudaMemcpyHostToDevice, st));
   MatchLaunch m;
@@ -184,7 +185,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.corner = (const float4*)ctx->m_corner_ds.p; m.surf = (const float4*)ctx->m_surf_ds.p;
   m.n_corner = d_nds; m.n_surf = d_nds + S; m.cap_corner = cap_c; m.cap_surf = cap_s;
   m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
-  m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p;
+  m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p; m.nn_slot = (int*)ctx->m_slots.p;
   m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm; m.max_queries = max_q;
   launch_match(m, st, &ctx->prof);
   // featureMapUpdate

@@ -78,8 +78,9 @@ __global__ void match_init_kernel(MatchState* states, const float* __restrict__ 
 }
 
 // ============================================================================================================
-// K5: fused correspondence.  One thread per query: transform -> exact 5-NN -> line / plane fit -> residual and
-// Jacobian row (ScanMatch.cpp:97-132 and :154-204 fused).
+// K5: correspondence (ScanMatch.cpp:97-132 and :154-204): K5a transform -> exact 5-NN (memory-latency bound, divergent,
+// wants occupancy) and K5b line / plane fit -> residual -> Jacobian row (uniform arithmetic) are separate launches so
+// that each gets the register budget and occupancy it needs; the 20 bytes per query between them stay in L2.
 // ============================================================================================================
 struct CorrArgs {
   const float4* corner; const float4* surf;   // [nstreams][cap*]
@@ -88,6 +89,7 @@ struct CorrArgs {
   const GridView* grid_corner; const GridView* grid_surf;
   const MatchState* state;
   RowOut* rows;                               // [nstreams][cap_corner + cap_surf]
+  int* nn_slot;                               // [nstreams][cap_corner + cap_surf][5] pool slots of the neighbours, -1: gated out
   int* nn;                                    // optional [nstreams][cap_corner + cap_surf][5], -1 where gated out
   MatchParamsDev prm;
 };
@@ -173,8 +175,59 @@ __device__ __forceinline__ int surf_row(const float4 nb[5], float sx, float sy, 
   return ((double)weight > 0.1) ? 3 : 2;
 }
 
+// Query index space of one stream: corner queries first, padded to a multiple of 32 so that a warp never mixes the
+// corner grid with the surf grid (the search finishes hard queries warp-cooperatively on ONE grid).
+__device__ __forceinline__ bool decode_query(int t, int nC, int nS, bool* isCorner, int* src, int* row) {
+  const int nCpad = (nC + 31) & ~31;
+  if (t < nC) { *isCorner = true; *src = t; *row = t; return true; }
+  if (t >= nCpad && t - nCpad < nS) { *isCorner = false; *src = t - nCpad; *row = nC + (t - nCpad); return true; }
+  *isCorner = t < nCpad; *src = 0; *row = 0;
+  return false;
+}
+
+// K5a: transform + exact 5-NN.  Writes the pool slots of the 5 neighbours (or -1 when the 5.0 gate rejects the
+// query, ScanMatch.cpp:102,120).
 template <bool kOrigIdx>
-__global__ void __launch_bounds__(256) corr_kernel(CorrArgs a) {
+__global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
+  const int s = blockIdx.y;
+  const MatchState& st = a.state[s];
+  if (st.done) return;
+  __shared__ float sR[9], sT[3];
+  __shared__ uint2 rng[8 * 256];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
+  __syncthreads();
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int capQ = a.cap_corner + a.cap_surf;
+  const int nT = ((nC + 31) & ~31) + nS;
+  const float4* corner = a.corner + (size_t)s * a.cap_corner;
+  const float4* surf = a.surf + (size_t)s * a.cap_surf;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t & ~31) >= nT) return;   // whole warp idle
+  bool isCorner; int src, row;
+  const bool valid = decode_query(t, nC, nS, &isCorner, &src, &row);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (valid) {
+    const float4 p = isCorner ? corner[src] : surf[src];
+    transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
+  }
+  const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+  Top5 best;
+  knn5_search<kOrigIdx>(g, valid, sx, sy, sz, a.prm.knn_gate, rng, best);
+  if (!valid) return;
+  const bool gate = best.d[4] < a.prm.knn_gate;
+  int* out = a.nn_slot + ((size_t)s * capQ + row) * 5;
+#pragma unroll
+  for (int k = 0; k < 5; k++) out[k] = gate ? best.slot[k] : -1;
+  if (a.nn) {
+    int* nn = a.nn + ((size_t)s * capQ + row) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx[k] : -1;
+  }
+}
+
+// K5b: line / plane fit on the 5 neighbours, residual and Jacobian row (ScanMatch.cpp:103-112, 121-130, 154-204).
+__global__ void __launch_bounds__(256) fit_kernel(CorrArgs a) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
   if (st.done) return;
@@ -186,49 +239,42 @@ __global__ void __launch_bounds__(256) corr_kernel(CorrArgs a) {
   __syncthreads();
   const int nC = a.n_corner[s], nS = a.n_surf[s];
   const int capQ = a.cap_corner + a.cap_surf;
-  const float4* corner = a.corner + (size_t)s * a.cap_corner;
-  const float4* surf = a.surf + (size_t)s * a.cap_surf;
-  RowOut* rows = a.rows + (size_t)s * capQ;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nC + nS; q += gridDim.x * blockDim.x) {
-    const bool isCorner = q < nC;
-    const float4 p = isCorner ? corner[q] : surf[q - nC];
-    float sx, sy, sz;
-    transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool isCorner; int src, row;
+  if (!decode_query(t, nC, nS, &isCorner, &src, &row)) return;
+  const float4 p = isCorner ? a.corner[(size_t)s * a.cap_corner + src] : a.surf[(size_t)s * a.cap_surf + src];
+  const int* slots = a.nn_slot + ((size_t)s * capQ + row) * 5;
+  RowOut rowv;
+#pragma unroll
+  for (int k = 0; k < 6; k++) rowv.a[k] = 0.f;
+  rowv.b = 0.f; rowv.flag = 0;
+  int sl[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) sl[k] = slots[k];
+  if (sl[0] >= 0) {
     const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
-    Top5 best;
-    knn5_search<kOrigIdx>(g, sx, sy, sz, a.prm.knn_gate, best);
-    RowOut row;
+    float sx, sy, sz;
+    transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);
+    float4 nb[5];
 #pragma unroll
-    for (int k = 0; k < 6; k++) row.a[k] = 0.f;
-    row.b = 0.f; row.flag = 0;
-    const bool gate = best.d[4] < a.prm.knn_gate;
-    if (a.nn) {
-      int* nn = a.nn + ((size_t)s * capQ + q) * 5;
-#pragma unroll
-      for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx[k] : -1;
+    for (int k = 0; k < 5; k++) nb[k] = __ldg(g.pts + sl[k]);
+    float co[4];
+    int f = isCorner ? corner_row(nb, sx, sy, sz, co) : surf_row(nb, sx, sy, sz, a.prm.plane_max_dist, co);
+    rowv.flag = f;
+    if (f & 1) {
+      const float x = p.x, y = p.y, z = p.z;
+      float arx = (kc.x1 * y + kc.x2 * z) * co[0] + (kc.x3 * y - kc.x4 * z) * co[1] + (kc.x5 * y - kc.x6 * z) * co[2];
+      float ary = (kc.y1 * x + kc.y2 * y + kc.y3 * z) * co[0] + (kc.y4 * x + kc.y5 * y + kc.y6 * z) * co[1] +
+                  (kc.y7 * x - kc.y8 * y - kc.y9 * z) * co[2];
+      float arz = (kc.z1 * x - kc.x4 * y + kc.z3 * z) * co[0] + (kc.z4 * x + kc.z5 * y + kc.z6 + kc.z7 * z) * co[1] +
+                  0 * co[2];
+      rowv.a[0] = arx; rowv.a[1] = ary; rowv.a[2] = arz; rowv.a[3] = co[0]; rowv.a[4] = co[1]; rowv.a[5] = co[2];
+      rowv.b = -co[3];
     }
-    if (gate) {
-      float4 nb[5];
-#pragma unroll
-      for (int k = 0; k < 5; k++) nb[k] = __ldg(g.pts + best.slot[k]);
-      float co[4];
-      int f = isCorner ? corner_row(nb, sx, sy, sz, co) : surf_row(nb, sx, sy, sz, a.prm.plane_max_dist, co);
-      row.flag = f;
-      if (f & 1) {
-        const float x = p.x, y = p.y, z = p.z;
-        float arx = (kc.x1 * y + kc.x2 * z) * co[0] + (kc.x3 * y - kc.x4 * z) * co[1] + (kc.x5 * y - kc.x6 * z) * co[2];
-        float ary = (kc.y1 * x + kc.y2 * y + kc.y3 * z) * co[0] + (kc.y4 * x + kc.y5 * y + kc.y6 * z) * co[1] +
-                    (kc.y7 * x - kc.y8 * y - kc.y9 * z) * co[2];
-        float arz = (kc.z1 * x - kc.x4 * y + kc.z3 * z) * co[0] + (kc.z4 * x + kc.z5 * y + kc.z6 + kc.z7 * z) * co[1] +
-                    0 * co[2];
-        row.a[0] = arx; row.a[1] = ary; row.a[2] = arz; row.a[3] = co[0]; row.a[4] = co[1]; row.a[5] = co[2];
-        row.b = -co[3];
-      }
-    }
-    float4* dst = reinterpret_cast<float4*>(rows + q);
-    dst[0] = make_float4(row.a[0], row.a[1], row.a[2], row.a[3]);
-    dst[1] = make_float4(row.a[4], row.a[5], row.b, __int_as_float(row.flag));
   }
+  float4* dst = reinterpret_cast<float4*>(a.rows + (size_t)s * capQ + row);
+  dst[0] = make_float4(rowv.a[0], rowv.a[1], rowv.a[2], rowv.a[3]);
+  dst[1] = make_float4(rowv.a[4], rowv.a[5], rowv.b, __int_as_float(rowv.flag));
 }
 
 // ============================================================================================================
@@ -404,11 +450,14 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // ============================================================================================================
 // Stand-alone exact 5-NN (test hook and operator): queries already in the map frame.
 // ============================================================================================================
-__global__ void knn5_kernel(GridView g, const float* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ d2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
+__global__ void __launch_bounds__(128) knn5_kernel(GridView g, const float* __restrict__ q, int nq, float gate, int* __restrict__ idx,
+                                                   float* __restrict__ d2) {
+  __shared__ uint2 rng[8 * 128];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < nq;
   Top5 best;
-  knn5_search<true>(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], gate, best);
+  knn5_search<true>(g, valid, valid ? q[3 * i] : 0.f, valid ? q[3 * i + 1] : 0.f, valid ? q[3 * i + 2] : 0.f, gate, rng, best);
+  if (!valid) return;
 #pragma unroll
   for (int k = 0; k < 5; k++) {
     idx[5 * i + k] = best.slot[k] < 0 ? -1 : best.idx[k];
@@ -460,20 +509,21 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
   CorrArgs ca;
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
-  ca.state = m.state; ca.rows = m.rows; ca.nn = nullptr; ca.prm = m.prm;
+  ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.prm = m.prm;
   SolveArgs sa;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm;
   int capQ = m.cap_corner + m.cap_surf;
-  int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 255) / 256;
+  int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 32 + 255) / 256;   // + 32: the corner block is padded to a warp
   if (bx < 1) bx = 1;
   dim3 grid(bx, m.nstreams);
   for (int it = 0; it < m.prm.max_iterations; it++) {
     ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
     if (prof) prof->begin(stream);
-    if (m.orig_idx) CM_LAUNCH(corr_kernel<true>, grid, 256, 0, stream, ca);
-    else CM_LAUNCH(corr_kernel<false>, grid, 256, 0, stream, ca);
+    if (m.orig_idx) CM_LAUNCH(search_kernel<true>, grid, 256, 0, stream, ca);
+    else CM_LAUNCH(search_kernel<false>, grid, 256, 0, stream, ca);
     if (prof) prof->end(stream);
+    CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
     sa.iter = it;
     CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
     CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, (const double*)m.sums, m.nstreams);

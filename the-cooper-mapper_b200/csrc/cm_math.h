@@ -180,6 +180,92 @@ CM_HD void tridiagonal_to_eigen(float* diag, float* subdiag, float* Q) {
   }
 }
 
+// N = 3 specialisation of tridiagonal_qr_step / tridiagonal_to_eigen with compile-time indices only (identical
+// arithmetic, operation for operation): diag / subdiag / Q stay in registers on the GPU instead of local memory.
+// This is the hot eigen-solve (one per corner query and two per classified scan point).
+template <int START, int END>
+CM_HD void tridiag3_qr_sweep(float* diag, float* subdiag, float* Q) {
+  float td = (diag[END - 1] - diag[END]) * 0.5f;
+  float e = subdiag[END - 1];
+  float mu = diag[END];
+  if (td == 0.f) {
+    mu -= fabsf(e);
+  } else if (e != 0.f) {
+    float e2 = e * e;
+    float h = cm_hypot(td, e);
+    if (e2 == 0.f) mu -= e / ((td + (td > 0.f ? h : -h)) / e);
+    else mu -= e2 / (td + (td > 0.f ? h : -h));
+  }
+  float x = diag[START] - mu;
+  float z = subdiag[START];
+  bool alive = true;
+CM_UNROLL
+  for (int k = START; k < END; ++k) {
+    alive = alive && (z != 0.f);
+    if (alive) {
+      float c, s;
+      make_givens(x, z, &c, &s);
+      float sdk = s * diag[k] + c * subdiag[k];
+      float dkp1 = s * subdiag[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
+      diag[k + 1] = s * sdk + c * dkp1;
+      subdiag[k] = c * sdk - s * dkp1;
+      if (k > START) subdiag[k - 1] = c * subdiag[k - 1] - s * z;
+      x = subdiag[k];
+      if (k < END - 1) {
+        z = -s * subdiag[k + 1];
+        subdiag[k + 1] = c * subdiag[k + 1];
+      }
+CM_UNROLL
+      for (int r = 0; r < 3; ++r) {
+        float xi = Q[r * 3 + k], yi = Q[r * 3 + k + 1];
+        Q[r * 3 + k] = c * xi - s * yi;
+        Q[r * 3 + k + 1] = s * xi + c * yi;
+      }
+    }
+  }
+}
+
+CM_HD bool tridiag3_negligible(float sub, float da, float db) {
+  return fabsf(sub) <= (fabsf(da) + fabsf(db)) * (2.f * FLT_EPSILON) || fabsf(sub) <= FLT_MIN;
+}
+
+CM_HD void tridiagonal_to_eigen3(float* diag, float* subdiag, float* Q) {
+  int end = 2, start = 0, iter = 0;
+  while (end > 0) {
+    if (start <= 0 && 0 < end) { if (tridiag3_negligible(subdiag[0], diag[0], diag[1])) subdiag[0] = 0.f; }
+    if (start <= 1 && 1 < end) { if (tridiag3_negligible(subdiag[1], diag[1], diag[2])) subdiag[1] = 0.f; }
+    if (end == 2 && subdiag[1] == 0.f) end = 1;
+    if (end == 1 && subdiag[0] == 0.f) end = 0;
+    if (end <= 0) break;
+    iter++;
+    if (iter > 30 * 3) break;
+    if (end == 2) {
+      if (subdiag[0] != 0.f) { start = 0; tridiag3_qr_sweep<0, 2>(diag, subdiag, Q); }
+      else { start = 1; tridiag3_qr_sweep<1, 2>(diag, subdiag, Q); }
+    } else {
+      start = 0; tridiag3_qr_sweep<0, 1>(diag, subdiag, Q);
+    }
+  }
+  // ascending selection sort with column swaps (i = 0, then i = 1)
+  {
+    int k = 0; float m = diag[0];
+    if (diag[1] < m) { m = diag[1]; k = 1; }
+    if (diag[2] < m) { m = diag[2]; k = 2; }
+    if (k == 1) { float t = diag[0]; diag[0] = diag[1]; diag[1] = t;
+CM_UNROLL
+      for (int r = 0; r < 3; ++r) { float u = Q[r * 3]; Q[r * 3] = Q[r * 3 + 1]; Q[r * 3 + 1] = u; } }
+    else if (k == 2) { float t = diag[0]; diag[0] = diag[2]; diag[2] = t;
+CM_UNROLL
+      for (int r = 0; r < 3; ++r) { float u = Q[r * 3]; Q[r * 3] = Q[r * 3 + 2]; Q[r * 3 + 2] = u; } }
+  }
+  if (diag[2] < diag[1]) {
+    float t = diag[1]; diag[1] = diag[2]; diag[2] = t;
+CM_UNROLL
+    for (int r = 0; r < 3; ++r) { float u = Q[r * 3 + 1]; Q[r * 3 + 1] = Q[r * 3 + 2]; Q[r * 3 + 2] = u; }
+  }
+}
+
 // Symmetric 3x3 eigen-decomposition.  Input: lower triangle {a00,a10,a20,a11,a21,a22}; output: eigenvalues
 // ascending in w, eigenvectors as COLUMNS of V (V[r*3+c]).
 // Eigen SelfAdjointEigenSolver::compute + tridiagonalization_inplace_selector<MatrixType,3,false>.
@@ -211,7 +297,7 @@ CM_HD void eig3_sym(const float A[6], float w[3], float V[9]) {
     subdiag[1] = m21 - m01 * q;
     V[0] = 1.f; V[1] = 0.f; V[2] = 0.f; V[3] = 0.f; V[4] = m01; V[5] = m02; V[6] = 0.f; V[7] = m02; V[8] = -m01;
   }
-  tridiagonal_to_eigen<3>(diag, subdiag, V);
+  tridiagonal_to_eigen3(diag, subdiag, V);
   w[0] = diag[0] * scale; w[1] = diag[1] * scale; w[2] = diag[2] * scale;
 }
 
