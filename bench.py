@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--pool", type=int, default=12, help="distinct synthetic sweeps generated on the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="after the timed arms, run 2 more steps with every launch event-timed and print per-kernel totals to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -277,6 +278,17 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * K * NPTS / (float(t.item()) * 1e-3)
+
+    if args.timeline and rank == 0:
+        ctx.timeline_enable(True)
+        for k in range(W, min(W + 2, n_steps)):
+            ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
+        rep = ctx.timeline_report(); ctx.timeline_enable(False)
+        tot = sum(float(l.split()[-2]) for l in rep.strip().splitlines())
+        log("[timeline] 2 steps, %.1f us of kernel time per step" % (tot / 2))
+        for l in rep.strip().splitlines():
+            name, us, n = l.rsplit(" ", 2)
+            log("  %-40s %9.1f us/step  x%-4d %5.1f%%" % (name[:40], float(us) / 2, int(n) // 2, 100 * float(us) / tot))
 
     # ---- single-stream latency (one LiDAR, host sweep in -> host pose out) ---------------------------------------------
     p50 = None

@@ -184,6 +184,9 @@ int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms);
 int cm_prof_enable(cm_ctx* ctx, int on);
 int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches);
 int cm_last_step_counters(cm_ctx* ctx, unsigned long long* out4);
+/* development aid: bracket EVERY kernel launch with CUDA events and report "name total_us launches" lines (sorted) */
+int cm_timeline_enable(cm_ctx* ctx, int on);
+int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap);
 
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.

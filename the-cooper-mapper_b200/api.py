@@ -226,6 +226,14 @@ class Context:
         self._check(self.L.cm_prof_drain(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def timeline_enable(self, on):
+        self._check(self.L.cm_timeline_enable(self.h, C.c_int(int(on))))
+
+    def timeline_report(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.L.cm_timeline_report(self.h, buf, C.c_size_t(len(buf))))
+        return buf.value.decode()
+
     def last_step_counters(self):
         a = (C.c_ulonglong * 4)()
         self._check(self.L.cm_last_step_counters(self.h, a))

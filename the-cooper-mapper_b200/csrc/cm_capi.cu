@@ -4,11 +4,14 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
 namespace cm {
 unsigned long long g_launch_count = 0;
+Timeline g_timeline;
 
 MatchParamsDev dev_params(const cm_config& c) {
   MatchParamsDev p;
@@ -297,6 +300,28 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
+  return CM_OK;
+}
+
+int cm_timeline_enable(cm_ctx* ctx, int on) { (void)ctx; g_timeline.on = on != 0; return CM_OK; }
+// writes "name total_us launches" lines, sorted by time, into buf; resets the timeline
+int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx || !buf || cap == 0) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& r : g_timeline.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = agg[r.name]; e.first += ms * 1e3; e.second++; }
+    g_timeline.pool.push_back(r.a); g_timeline.pool.push_back(r.b);
+  }
+  g_timeline.recs.clear();
+  std::vector<std::pair<double, std::string>> v;
+  for (auto& kv : agg) v.push_back({kv.second.first, kv.first});
+  std::sort(v.begin(), v.end(), [](const std::pair<double, std::string>& a, const std::pair<double, std::string>& b) { return a.first > b.first; });
+  std::string out;
+  for (auto& e : v) { char line[256]; snprintf(line, sizeof(line), "%s %.1f %d\n", e.second.c_str(), e.first, agg[e.second].second); out += line; }
+  snprintf(buf, cap, "%s", out.c_str());
   return CM_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "cm_match.cuh"
@@ -10,12 +11,32 @@ namespace cm {
 
 struct CudaError { cudaError_t code; const char* what; };
 
-// Every kernel launch goes through CM_LAUNCH so that cm_launch_count() reports what actually ran.
+// Every kernel launch goes through CM_LAUNCH so that cm_launch_count() reports what actually ran.  With the
+// timeline enabled (cm_timeline_enable) every launch is additionally bracketed by CUDA events on its stream and
+// cm_timeline_report() aggregates the device time per kernel name (development aid: warm caches, real clocks).
 extern unsigned long long g_launch_count;
-#define CM_LAUNCH(kern, grid, block, smem, stream, ...)        \
-  do {                                                         \
-    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
-    ++cm::g_launch_count;                                      \
+struct Timeline {
+  bool on = false;
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() { if (pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  void begin(const char* name, cudaStream_t s) { Rec r; r.name = name; r.a = get(); r.b = get(); cudaEventRecord(r.a, s); recs.push_back(r); }
+  void end(cudaStream_t s) { cudaEventRecord(recs.back().b, s); }
+};
+extern Timeline g_timeline;
+#define CM_LAUNCH(kern, grid, block, smem, stream, ...)                 \
+  do {                                                                  \
+    if (cm::g_timeline.on) cm::g_timeline.begin(#kern, (stream));       \
+    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    if (cm::g_timeline.on) cm::g_timeline.end((stream));                \
+    ++cm::g_launch_count;                                               \
+  } while (0)
+#define CM_TIMED(name, stream, stmt)                                    \
+  do {                                                                  \
+    if (cm::g_timeline.on) cm::g_timeline.begin(name, (stream));        \
+    stmt;                                                               \
+    if (cm::g_timeline.on) cm::g_timeline.end((stream));                \
   } while (0)
 
 // Grow-only device allocation.

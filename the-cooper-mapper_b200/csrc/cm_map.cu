@@ -300,8 +300,9 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
             (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)flags.p);
   tb = temp.cap;
-  cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
-                                  (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 62, stream);
+  CM_TIMED("cub_radix_sort(map)", stream,
+           cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
+                                           (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 62, stream));
   g_launch_count += 9;
   CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_b.p, (const unsigned int*)vals_b.p, n,
             (const float4*)world.p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending.p, (unsigned int*)n_pending.p, (unsigned int)n,

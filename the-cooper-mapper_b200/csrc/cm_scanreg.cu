@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   float* px = reinterpret_cast<float*>(sr_smem);
   float* py = px + cap; float* pz = py + cap; float* pin = pz + cap; float* curv = pin + cap;
   unsigned long long* key = reinterpret_cast<unsigned long long*>(curv + cap);
-  unsigned short* colv = reinterpret_cast<unsigned short*>(key + P2);
+  const int KEYN = (8 * P2 >= 10 * cap) ? P2 : (10 * cap + 7) / 8;   // `key` doubles as five u16 prefix arrays
+  unsigned short* colv = reinterpret_cast<unsigned short*>(key + KEYN);
   unsigned short* lst[4] = {colv + cap, colv + 2 * cap, colv + 3 * cap, colv + 4 * cap};
   unsigned short* nfl = colv + 5 * cap;
   unsigned short* ord = colv + 6 * cap;
@@ -330,132 +331,197 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   }
   __syncthreads();
 
-  // ---- pass 1 chained over the regions: greedy flat picks with +-R suppression (:267-284, 524-545) ---------------
-  // flat picks go to lst[2]; per-region counts are kept to interleave with the pass-3 picks later
-  __shared__ int flat_p1_begin[SR_MAXREG + 1];
-  if (tid == 0) flat_p1_begin[0] = 0;
-  for (int j = 0; j < prm.nregions; j++) {
-    const int sp = reg_sp[j], ep = reg_ep[j];
-    int picked_n = 0;
-    if (ep >= sp) {
-      for (int k = 0; k < prm.max_flat; k++) {
-        unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
-        for (int c = sp + tid; c <= ep; c += SR_THREADS) {
-          float cv = curv[c];
-          if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) {
-            unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned int)c;
-            best = kk < best ? kk : best;
-          }
-        }
-        best = block_min_u64(best, s_min);
-        if (best == 0xFFFFFFFFFFFFFFFFull) break;   // uniform
-        const int c = (int)(best & 0xFFFFFFFFu);
-        if (tid <= 2 * R) { state[c - R + tid] = P_SURF_PICKED_NEAR; }   // markAsPicked: c-R .. c+R
-        if (tid == 0) { lst[2][s_cnt[2] + picked_n] = (unsigned short)c; }
-        picked_n++;
-        __syncthreads();
-      }
-    }
-    if (tid == 0) { s_cnt[2] += picked_n; flat_p1_begin[j + 1] = s_cnt[2]; }
-    __syncthreads();
-    if (ep >= sp)
-      for (int c = sp + tid; c <= ep; c += SR_THREADS) snap[c] = state[c];   // what passes 2 and 3 of region j see
-    __syncthreads();
-  }
-  // pass-1 picks of all regions are now in lst[2][0 .. s_cnt[2]); move them to a side buffer (nfl is free until pass 3)
-  const int n_p1 = s_cnt[2];
+  // From here on the regions of the ring are processed TOGETHER.  Per-region quantities live in small arrays; per-cell
+  // work runs over the whole ring so that all 512 threads stay busy.
+  __shared__ int nf_begin[SR_MAXREG + 1];      // region j's cells above the threshold: nfl[nf_begin[j] .. nf_begin[j+1])
+  __shared__ int p1_begin[SR_MAXREG + 1];      // region j's pass-1 picks: p1buf[p1_begin[j] .. p1_begin[j+1])
   __shared__ unsigned short p1buf[SR_MAXREG * 8];
-  for (int i = tid; i < n_p1 && i < SR_MAXREG * 8; i += SR_THREADS) p1buf[i] = lst[2][i];
-  __syncthreads();
-  if (tid == 0) s_cnt[2] = 0;
-  __syncthreads();
-
-  // ---- passes 2 and 3 per region, emission in the reference's order ---------------------------------------------
-  for (int j = 0; j < prm.nregions; j++) {
-    const int sp = reg_sp[j], ep = reg_ep[j];
-    if (ep < sp) continue;
-    // flat list: pass-1 picks of this region first
-    {
-      int b = flat_p1_begin[j], e = flat_p1_begin[j + 1];
-      int base = s_cnt[2];
-      for (int i = b + tid; i < e; i += SR_THREADS) lst[2][base + (i - b)] = p1buf[i];
-      __syncthreads();
-      if (tid == 0) s_cnt[2] = base + (e - b);
-      __syncthreads();
+  __shared__ int cnt2[4][SR_MAXREG], cnt3[4][SR_MAXREG];   // per list (sharp, lessSharp, flat, lessFlatRaw) and region
+  __shared__ int start2[2][SR_MAXREG], start3[3][SR_MAXREG];   // exclusive prefixes at region starts
+  __shared__ int base[4][SR_MAXREG + 1];
+  const int NR = prm.nregions;
+  // region of a cell (regions are contiguous and ordered; skipped regions have ep < sp)
+  auto region_of = [&](int c) -> int {
+    for (int j = 0; j < NR; j++) if (reg_ep[j] >= reg_sp[j] && c >= reg_sp[j] && c <= reg_ep[j]) return j;
+    return -1;
+  };
+  if (tid < 4 * SR_MAXREG) { (&cnt2[0][0])[tid] = 0; (&cnt3[0][0])[tid] = 0; }
+  // ---- cells above the curvature threshold, in index order (they are the pass-3 candidates, :305-314) -------------
+  {
+    int total = 0;
+    for (int c0 = 0; c0 < n; c0 += SR_THREADS) {
+      const int c = c0 + tid;
+      const int rj = c < n ? region_of(c) : -1;
+      const bool isnf = rj >= 0 && !(curv[c] < prm.curv_thr);
+      int tot;
+      const int pos = block_scan_excl(isnf ? 1 : 0, s_scan, &tot);
+      if (isnf) nfl[total + pos] = (unsigned short)c;
+      if (rj >= 0 && c == reg_sp[rj]) nf_begin[rj] = total + pos;
+      total += tot;
     }
-    // pass 2 (:286-303): index order; c < thr -> lessFlatRaw; EDGE_BROKEN -> sharp + lessSharp.  Also collect the
-    // cells above the threshold for pass 3.
-    {
-      int base_lf = s_cnt[3], base_sh = s_cnt[0], base_ls = s_cnt[1];
-      int nf_total = 0;
-      for (int c0 = sp; c0 <= ep; c0 += SR_THREADS) {
-        int c = c0 + tid;
-        bool in = c <= ep;
-        bool isflat = in && (curv[c] < prm.curv_thr);
-        bool isedge = in && (snap[c] == P_EDGE_BROKEN);
-        bool isnf = in && !isflat;
-        int t1, t2, t3;
-        int p1 = block_scan_excl(isflat ? 1 : 0, s_scan, &t1);
-        int p2 = block_scan_excl(isedge ? 1 : 0, s_scan, &t2);
-        int p3 = block_scan_excl(isnf ? 1 : 0, s_scan, &t3);
-        if (isflat) lst[3][base_lf + p1] = (unsigned short)c;
-        if (isedge) { lst[0][base_sh + p2] = (unsigned short)c; lst[1][base_ls + p2] = (unsigned short)c; }
-        if (isnf) nfl[nf_total + p3] = (unsigned short)c;
-        base_lf += t1; base_sh += t2; base_ls += t2; nf_total += t3;
+    if (tid == 0) {
+      nf_begin[NR] = total;
+      for (int j = NR - 1; j >= 0; j--) if (reg_ep[j] < reg_sp[j]) nf_begin[j] = nf_begin[j + 1];   // skipped regions are empty
+    }
+  }
+  __syncthreads();
+  const int m_all = nf_begin[NR];
+  // ---- warp 0: pass 1, chained over the regions (greedy flat picks with +-R suppression, :267-284, 524-545);
+  //      warps 1..15: pointClassify of every pass-3 candidate (:316, 547-666) -- independent of the picks ------------
+  if (tid < 32) {
+    const int lane = tid;
+    int np1 = 0;
+    for (int j = 0; j < NR; j++) {
+      const int sp = reg_sp[j], ep = reg_ep[j];
+      if (lane == 0) p1_begin[j] = np1;
+      if (ep >= sp) {
+        for (int k = 0; k < prm.max_flat; k++) {
+          unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
+          for (int c = sp + lane; c <= ep; c += 32) {
+            const float cv = curv[c];
+            if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) {
+              const unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned int)c;
+              best = kk < best ? kk : best;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+          if (best == 0xFFFFFFFFFFFFFFFFull) break;
+          const int c = (int)(best & 0xFFFFFFFFu);
+          if (lane <= 2 * R) state[c - R + lane] = P_SURF_PICKED_NEAR;   // markAsPicked: c-R .. c+R
+          if (lane == 0 && np1 < SR_MAXREG * 8) p1buf[np1] = (unsigned short)c;
+          np1++;
+          __syncwarp();
+        }
+        for (int c = sp + lane; c <= ep; c += 32) snap[c] = state[c];   // what passes 2 and 3 of region j see
+        __syncwarp();
       }
-      __syncthreads();
-      if (tid == 0) { s_cnt[3] = base_lf; s_cnt[0] = base_sh; s_cnt[1] = base_ls; s_misc[0] = nf_total; }
-      __syncthreads();
     }
-    const int m = s_misc[0];
-    // pass 3 (:305-354): classify every cell above the threshold, order by descending (curvature, index)
-    for (int i = tid; i < m; i += SR_THREADS) {
-      int c = nfl[i];
-      int l = point_classify(px, py, pz, c, prm);
-      lab[c] = (signed char)l;
+    if (lane == 0) p1_begin[NR] = np1;
+  } else {
+    for (int i = tid - 32; i < m_all; i += SR_THREADS - 32) {
+      const int c = nfl[i];
+      lab[c] = (signed char)point_classify(px, py, pz, c, prm);
       key[i] = ((unsigned long long)__float_as_uint(curv[c]) << 32) | (unsigned int)c;
     }
-    __syncthreads();
-    for (int i = tid; i < m; i += SR_THREADS) {
-      unsigned long long ki = key[i];
-      int rank = 0;
-      for (int k = 0; k < m; k++) rank += (key[k] > ki) ? 1 : 0;
-      ord[rank] = nfl[i];
-    }
-    __syncthreads();
-    {
-      int base_sh = s_cnt[0], base_ls = s_cnt[1], base_fl = s_cnt[2], base_lf = s_cnt[3];
-      int run_corner = 0, run_surf = 0;
-      for (int i0 = 0; i0 < m; i0 += SR_THREADS) {
-        int i = i0 + tid;
-        bool in = i < m;
-        int c = in ? ord[i] : 0;
-        int l = in ? lab[c] : L_MESSY;
-        bool is_corner = in && l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN;
-        bool is_surf = in && (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT);
-        int tc, ts, tf;
-        int pc = block_scan_excl(is_corner ? 1 : 0, s_scan, &tc);
-        int ps = block_scan_excl(is_surf ? 1 : 0, s_scan, &ts);
-        // ONESIDE_FLAT is emitted as flat while the shared counter (bumped by SURFACE_FLAT too) is below the cap
-        bool is_flat_emit = is_surf && l == L_ONESIDE_FLAT && (run_surf + ps) < prm.max_flat;
-        int pf = block_scan_excl(is_flat_emit ? 1 : 0, s_scan, &tf);
-        if (is_corner) {
-          lst[1][base_ls + pc] = (unsigned short)c;
-          if (run_corner + pc < prm.max_sharp) lst[0][base_sh + run_corner + pc] = (unsigned short)c;
-        }
-        if (is_surf) lst[3][base_lf + ps] = (unsigned short)c;
-        if (is_flat_emit) lst[2][base_fl + pf] = (unsigned short)c;
-        base_ls += tc; base_lf += ts; base_fl += tf;
-        run_corner += tc; run_surf += ts;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int add_sharp = run_corner < prm.max_sharp ? run_corner : prm.max_sharp;
-        s_cnt[0] = base_sh + add_sharp; s_cnt[1] = base_ls; s_cnt[2] = base_fl; s_cnt[3] = base_lf;
-      }
-      __syncthreads();
+  }
+  __syncthreads();
+  // ---- descending (curvature, index) order inside every region: rank by counting -------------------------------------
+  for (int i = tid; i < m_all; i += SR_THREADS) {
+    const int rj = region_of(nfl[i]);
+    const unsigned long long ki = key[i];
+    int rank = 0;
+    for (int k = nf_begin[rj]; k < nf_begin[rj + 1]; k++) rank += (key[k] > ki) ? 1 : 0;
+    ord[nf_begin[rj] + rank] = nfl[i];
+  }
+  __syncthreads();
+  // `key` is free again: carve four u16 prefix arrays out of it
+  unsigned short* pfa = reinterpret_cast<unsigned short*>(key);
+  unsigned short* pfb = pfa + cap; unsigned short* pfc = pfb + cap;
+  // ---- pass 2 (:286-303), whole ring: c < thr -> lessFlatRaw; EDGE_BROKEN (as seen after the region's picks) -> sharp
+  //      and lessSharp.  Ring-wide exclusive prefixes; the value at a region's first cell is that region's offset. ------
+  {
+    int t1 = 0, t2 = 0;
+    for (int c0 = 0; c0 < n; c0 += SR_THREADS) {
+      const int c = c0 + tid;
+      const int rj = c < n ? region_of(c) : -1;
+      const bool isflat = rj >= 0 && (curv[c] < prm.curv_thr);
+      const bool isedge = rj >= 0 && (snap[c] == P_EDGE_BROKEN);
+      int a1, a2;
+      const int p1 = block_scan_excl(isflat ? 1 : 0, s_scan, &a1);
+      const int p2 = block_scan_excl(isedge ? 1 : 0, s_scan, &a2);
+      if (c < n) { pfa[c] = (unsigned short)(t1 + p1); pfb[c] = (unsigned short)(t2 + p2); }
+      if (rj >= 0 && c == reg_sp[rj]) { start2[0][rj] = t1 + p1; start2[1][rj] = t2 + p2; }
+      if (isflat) atomicAdd(&cnt2[3][rj], 1);
+      if (isedge) { atomicAdd(&cnt2[0][rj], 1); atomicAdd(&cnt2[1][rj], 1); }
+      t1 += a1; t2 += a2;
     }
   }
+  // ---- pass 3 (:305-354) over the descending order of every region: emission counters become prefix sums -----------
+  unsigned short* qfa = pfc; unsigned short* qfb = pfc + cap;   // corner / surf prefixes along `ord`
+  {
+    int t1 = 0, t2 = 0;
+    for (int i0 = 0; i0 < m_all; i0 += SR_THREADS) {
+      const int i = i0 + tid;
+      const bool in = i < m_all;
+      const int c = in ? ord[i] : 0;
+      const int l = in ? lab[c] : L_MESSY;
+      const int rj = in ? region_of(c) : -1;
+      const bool is_corner = in && l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN;
+      const bool is_surf = in && (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT);
+      int a1, a2;
+      const int p1 = block_scan_excl(is_corner ? 1 : 0, s_scan, &a1);
+      const int p2 = block_scan_excl(is_surf ? 1 : 0, s_scan, &a2);
+      if (in) { qfa[i] = (unsigned short)(t1 + p1); qfb[i] = (unsigned short)(t2 + p2); }
+      if (in && i == nf_begin[rj]) { start3[0][rj] = t1 + p1; start3[1][rj] = t2 + p2; }
+      if (is_corner) atomicAdd(&cnt3[1][rj], 1);
+      if (is_surf) atomicAdd(&cnt3[3][rj], 1);
+      t1 += a1; t2 += a2;
+    }
+  }
+  __syncthreads();
+  // flat emissions of pass 3: ONESIDE_FLAT while the shared counter (bumped by SURFACE_FLAT too) is below the cap: at most
+  // max_flat per region, found by walking the first surf elements of the region (tiny: one thread per region)
+  if (tid < NR) {
+    const int j = tid;
+    int nflat = 0;
+    if (reg_ep[j] >= reg_sp[j]) {
+      int seen = 0;
+      for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
+        const int l = lab[ord[i]];
+        if (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT) { if (l == L_ONESIDE_FLAT) nflat++; seen++; }
+      }
+    }
+    cnt3[2][j] = nflat;
+    cnt2[2][j] = p1_begin[j + 1] - p1_begin[j];
+    cnt3[0][j] = cnt3[1][j] < prm.max_sharp ? cnt3[1][j] : prm.max_sharp;
+  }
+  __syncthreads();
+  if (tid < 4) {   // list bases: regions in order, pass-1/2 entries before pass-3 entries
+    int acc = 0;
+    for (int j = 0; j < NR; j++) { base[tid][j] = acc; acc += cnt2[tid][j] + cnt3[tid][j]; }
+    base[tid][NR] = acc;
+    s_cnt[tid] = acc;
+  }
+  __syncthreads();
+  // ---- placement -----------------------------------------------------------------------------------------------------
+  for (int c = tid; c < n; c += SR_THREADS) {   // pass 2
+    const int rj = region_of(c);
+    if (rj < 0) continue;
+    if (curv[c] < prm.curv_thr) lst[3][base[3][rj] + (int)pfa[c] - start2[0][rj]] = (unsigned short)c;
+    if (snap[c] == P_EDGE_BROKEN) {
+      const int o = (int)pfb[c] - start2[1][rj];
+      lst[0][base[0][rj] + o] = (unsigned short)c; lst[1][base[1][rj] + o] = (unsigned short)c;
+    }
+  }
+  for (int i = tid; i < m_all; i += SR_THREADS) {   // pass 3
+    const int c = ord[i];
+    const int l = lab[c];
+    const int rj = region_of(c);
+    if (l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN) {
+      const int o = (int)qfa[i] - start3[0][rj];
+      lst[1][base[1][rj] + cnt2[1][rj] + o] = (unsigned short)c;
+      if (o < prm.max_sharp) lst[0][base[0][rj] + cnt2[0][rj] + o] = (unsigned short)c;
+    }
+    if (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT) {
+      const int o = (int)qfb[i] - start3[1][rj];
+      lst[3][base[3][rj] + cnt2[3][rj] + o] = (unsigned short)c;
+    }
+  }
+  if (tid < NR) {   // flat list: pass-1 picks, then the ONESIDE_FLAT picks of pass 3
+    const int j = tid;
+    int o = base[2][j];
+    for (int i = p1_begin[j]; i < p1_begin[j + 1]; i++) lst[2][o++] = p1buf[i];
+    if (reg_ep[j] >= reg_sp[j]) {
+      int seen = 0;
+      for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
+        const int c = ord[i];
+        const int l = lab[c];
+        if (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT) { if (l == L_ONESIDE_FLAT) lst[2][o++] = (unsigned short)c; seen++; }
+      }
+    }
+  }
+  __syncthreads();
 
   // ---- write the index-based outputs ------------------------------------------------------------------------------
   float4* o_pts[4]; int* o_idx[4];
@@ -628,7 +694,8 @@ __global__ void __launch_bounds__(256) sr_assemble_kernel(AssembleArgs a) {
 size_t scanreg_smem_bytes(int cols) {
   int cap = (cols + 3) & ~3;
   int P2 = 1; while (P2 < cols) P2 <<= 1;
-  return (size_t)cap * 4 * 5 + (size_t)P2 * 8 + (size_t)cap * 2 * 7 + (size_t)cap * 4;
+  int keyn = (8 * P2 >= 10 * cap) ? P2 : (10 * cap + 7) / 8;
+  return (size_t)cap * 4 * 5 + (size_t)keyn * 8 + (size_t)cap * 2 * 7 + (size_t)cap * 4;
 }
 
 void ScanRegistrationGpu::run(const ScanRegLaunch& L, cudaStream_t stream) {

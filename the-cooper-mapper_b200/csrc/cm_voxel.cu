@@ -174,12 +174,13 @@ void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_i
   CM_LAUNCH(vox_key_kernel, nb, T, 0, stream, d_in, d_n_in, cap_in, max_n, nseg, inv, (const VoxBox*)box.p, (unsigned long long*)keys_a.p,
             (unsigned int*)vals_a.p);
   size_t tb = temp.cap;
-  cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
-                                  (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 32 + sbits, stream);
+  CM_TIMED("cub_radix_sort(voxel)", stream,
+           cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
+                                           (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 32 + sbits, stream));
   g_launch_count += (32 + sbits + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
   CM_LAUNCH(vox_head_kernel, nb, T, 0, stream, (const unsigned long long*)keys_b.p, n, (int*)flags.p);
   tb = temp.cap;
-  cub::DeviceScan::ExclusiveSum(temp.p, tb, (const int*)flags.p, (int*)rank.p, (long long)n, stream);
+  CM_TIMED("cub_scan(voxel)", stream, cub::DeviceScan::ExclusiveSum(temp.p, tb, (const int*)flags.p, (int*)rank.p, (long long)n, stream));
   g_launch_count += 2;
   CM_LAUNCH(vox_segstart_kernel, 1, 32, 0, stream, d_n_in, (const VoxBox*)box.p, nseg, (int*)seg_first.p);
   CM_LAUNCH(vox_centroid_kernel, nb, T, 0, stream, d_in, (const unsigned long long*)keys_b.p, (const unsigned int*)vals_b.p,
