@@ -173,6 +173,19 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
  * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
 int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
 
+/* ---- sharded-map matching (BASELINE config 4: one map split over ranks) ---------------------------------------------------
+ * ScanMatch::scanMatchScan with the reference clouds partitioned in space: rank r holds the map points of its region plus a
+ * sqrt(5) m halo (cm_shard_set_map_host), evaluates per iteration only the queries whose map-frame position lies in its
+ * own box [own_lo, own_hi) (cm_shard_partial_host -> 32 doubles: 21 A^T A upper triangle, 6 A^T b, rows, line / plane
+ * counts, score), the caller all-reduces (sum) those doubles over the ranks (NCCL / gloo) and every rank calls
+ * cm_shard_solve_host with the total: identical input, identical pose on every rank, no broadcast.  Because the sums are
+ * exact-product double accumulations the result equals cm_match_stateless_host on the unsplit map bit for bit. */
+int cm_shard_set_map_host(cm_ctx* ctx, const cm_point* corner, size_t n_corner, const cm_point* surf, size_t n_surf);
+int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t n_corner, const cm_point* surf, size_t n_surf,
+                        const cm_pose* init, size_t total_ref_corner, size_t total_ref_surf);
+int cm_shard_partial_host(cm_ctx* ctx, int iter, const float* own_lo, const float* own_hi, double* sums32);
+int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* pose, int* done, cm_match_stats* stats);
+
 /* ---- measurement helpers (no reference counterpart; used by bench.py) ------------------------------------------------
  * cm_timer_record(ctx, 0 | 1) records a CUDA event on the context's stream; cm_timer_elapsed_ms returns event 1 - event 0.
  * cm_prof_enable brackets every launch of the dominant kernel (the fused correspondence kernel) with CUDA events on

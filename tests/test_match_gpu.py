@@ -132,3 +132,62 @@ def test_scanmatch_mirror_class(cmb, oracle, synth, scene_small):
     po, so, _ = oracle.scan_match(mc, ms, c, s, truth + np.float32(0.01), params=dict(deltaTAbort=0.05, deltaRAbort=0.05, useScore=1))
     assert ok2 == so["ok"] and np.array_equal(pose2, po)
     assert abs(sm2.last_stats["score"] - so["score"]) <= 1e-9 * max(1.0, so["score"]) or not so["converged"]
+
+
+def test_sharded_map_equals_unsharded(cmb, ctx, oracle, synth, scene_small):
+    """BASELINE config 4 in miniature: the map split into 3 x-slabs (+ halo), per-iteration sum of the partial normal
+    equations, redundant solve -> the pose is bit-identical to the single-map solve."""
+    import importlib
+    dmod = importlib.import_module("the-cooper-mapper_b200.dist")
+    sc, mc, ms = scene_small
+    c, s, truth = frame_features(synth, oracle, sc, (0.05, 0.01, -0.008, (3.0, 0.4, 0.1)), "HDL-64E")
+    init = truth + np.array([0.005, -0.004, 0.008, 0.08, -0.06, 0.05], np.float32)
+    ref_pose, ref_stats, _ = ctx.match_stateless(mc, ms, c, s, init)
+    world = 3
+    bounds = dmod.slab_bounds(ms, world)
+    ranks = []
+    pending = []
+
+    def make_reduce(r):
+        def red(sums):            # emulate the all-reduce in one process: every rank contributes before anyone solves
+            pending.append(sums)
+            return sums
+        return red
+
+    ctxs = [cmb.Context() for _ in range(world)]
+    sms = []
+    for r in range(world):
+        lo, hi = dmod.own_box(bounds, r)
+        sms.append(dmod.ShardedScanMatch(ctxs[r], dmod.shard_cloud(mc, bounds, r), dmod.shard_cloud(ms, bounds, r), len(mc), len(ms), lo, hi))
+    # lock-step iteration over the "ranks"
+    import ctypes as C
+    from conftest import frame_features as _ff  # noqa: F401
+    poses = [init.copy() for _ in range(world)]
+    cc = np.ascontiguousarray(c, np.float32); ss = np.ascontiguousarray(s, np.float32)
+    for r in range(world):
+        sm = sms[r]
+        sm.ctx._check(sm.L.cm_shard_begin_host(sm.ctx.h, cc.ctypes.data_as(C.c_void_p), C.c_size_t(len(cc)), ss.ctypes.data_as(C.c_void_p),
+                                               C.c_size_t(len(ss)), poses[r].ctypes.data_as(C.c_void_p), C.c_size_t(len(mc)), C.c_size_t(len(ms))))
+    done = False; iters = 0
+    while not done and iters < ctx.cfg.max_iterations:
+        parts = []
+        for r in range(world):
+            sums = np.zeros(32, np.float64); sm = sms[r]
+            sm.ctx._check(sm.L.cm_shard_partial_host(sm.ctx.h, C.c_int(iters), sm.lo.ctypes.data_as(C.c_void_p), sm.hi.ctypes.data_as(C.c_void_p),
+                                                     sums.ctypes.data_as(C.c_void_p)))
+            parts.append(sums)
+        total = np.sum(parts, axis=0)
+        assert total[27] == sum(p[27] for p in parts)
+        flags = []
+        for r in range(world):
+            d = C.c_int(0); st = cmb.MatchStats(); sm = sms[r]
+            sm.ctx._check(sm.L.cm_shard_solve_host(sm.ctx.h, C.c_int(iters), total.ctypes.data_as(C.c_void_p), poses[r].ctypes.data_as(C.c_void_p),
+                                                   C.byref(d), C.byref(st)))
+            flags.append(d.value)
+        assert len(set(flags)) == 1                       # every rank takes the same decision
+        done = bool(flags[0]); iters += 1
+    for r in range(world):
+        assert np.array_equal(poses[r], ref_pose)         # bit-identical to the unsharded solve, on every rank
+    assert iters == ref_stats["iterations"]
+    for cx in ctxs:
+        cx.close()

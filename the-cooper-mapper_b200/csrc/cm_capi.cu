@@ -303,6 +303,106 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
   return CM_OK;
 }
 
+/* ---- sharded-map matching: one rank's part of ScanMatch::scanMatchScan when the reference map is split over ranks ---- */
+int cm_shard_set_map_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns) {
+  if (!ctx || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const cm_config& cfg = ctx->cfg;
+    cudaStream_t st = ctx->stream;
+    ctx->d_ref_corner.reserve((nc ? nc : 1) * sizeof(cm_point));
+    ctx->d_ref_surf.reserve((ns ? ns : 1) * sizeof(cm_point));
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), 5.0f, 0, st);
+    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)ns, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), 5.0f, 0, st);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    ctx->shard_ready = true;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, const cm_pose* init,
+                        size_t total_ref_corner, size_t total_ref_surf) {
+  if (!ctx || !ctx->shard_ready || !init || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument / no shard map");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    MatchParamsDev prm = dev_params(ctx->cfg);
+    const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
+    ctx->d_corner.reserve(capC * sizeof(cm_point)); ctx->d_surf.reserve(capS * sizeof(cm_point));
+    ctx->d_counts.reserve(2 * sizeof(int)); ctx->d_views.reserve(2 * sizeof(GridView)); ctx->d_pose.reserve(6 * sizeof(float));
+    ctx->d_state.reserve(sizeof(MatchState)); ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
+    ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int)); ctx->d_sums.reserve(32 * sizeof(double)); ctx->d_box.reserve(6 * sizeof(float));
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    int counts[2] = {(int)nc, (int)ns};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, init, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
+    views[0].npts = (int)total_ref_corner; views[1].npts = (int)total_ref_surf;   // the 50 / 100 gate looks at the WHOLE map
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
+    MatchLaunch& m = ctx->shard;
+    m = MatchLaunch();
+    m.nstreams = 1;
+    m.corner = (const float4*)ctx->d_corner.p; m.surf = (const float4*)ctx->d_surf.p;
+    m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
+    m.cap_corner = capC; m.cap_surf = capS;
+    m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
+    m.pose_in = (const float*)ctx->d_pose.p; m.state = (MatchState*)ctx->d_state.p; m.rows = (RowOut*)ctx->d_rows.p;
+    m.nn_slot = (int*)ctx->d_slots.p; m.sums = (double*)ctx->d_sums.p; m.trace = nullptr; m.nn = nullptr;
+    m.orig_idx = 1; m.max_queries = (int)(nc + ns); m.own_box = (const float*)ctx->d_box.p; m.prm = prm;
+    ctx->shard_nq = nc + ns;
+    launch_match_init(m, st);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_partial_host(cm_ctx* ctx, int iter, const float* own_lo, const float* own_hi, double* sums32) {
+  if (!ctx || !ctx->shard_ready || !own_lo || !own_hi || !sums32 || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    float box[6] = {own_lo[0], own_lo[1], own_lo[2], own_hi[0], own_hi[1], own_hi[2]};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_box.p, box, sizeof(box), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_sums.p, 0, 32 * sizeof(double), st));
+    launch_match_partial(ctx->shard, iter, st, nullptr);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(sums32, ctx->d_sums.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* pose, int* done, cm_match_stats* stats) {
+  if (!ctx || !ctx->shard_ready || !sums32 || !pose || !done || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sums.p, sums32, 32 * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_match_solve(ctx->shard, iter, (const double*)ctx->d_sums.p, st);
+    MatchState hs;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2]; pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
+    *done = hs.done;
+    if (stats) fill_match_stats(ctx->cfg, hs, ctx->shard_nq, stats);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
 int cm_timeline_enable(cm_ctx* ctx, int on) { (void)ctx; g_timeline.on = on != 0; return CM_OK; }
 // writes "name total_us launches" lines, sorted by time, into buf; resets the timeline
 int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap) {

@@ -35,6 +35,9 @@ struct cm_ctx {
   std::vector<cm::MappingStream> mstreams;
   cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_slots, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
+  // sharded-map matching (cm_shard_*): persistent grids in grid_a / grid_b
+  cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
+  cm::DeviceBuffer d_box;
   cm::KernelProfiler prof;
   cudaEvent_t timer[2] = {nullptr, nullptr};
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)

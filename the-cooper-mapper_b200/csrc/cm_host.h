@@ -85,6 +85,7 @@ struct MatchLaunch {
   int* nn;                                    // optional device [max_iterations][nstreams][cap][5]
   int orig_idx;                               // grids carry original indices in pts[].w
   int max_queries = 0;                        // host-known upper bound of n_corner[s] + n_surf[s] (0: use the capacities)
+  const float* own_box = nullptr;             // device {lo[3], hi[3]}: evaluate only queries inside (sharded map), else all
   MatchParamsDev prm;
 };
 // optional per-kernel timing of the dominant kernel (corr_kernel): event pairs recorded on the launching stream
@@ -103,6 +104,9 @@ struct KernelProfiler {
   }
 };
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
+void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr);
+void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);
 
 // K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes
 // out[s*cap_out .. +n_out[s]).

@@ -91,6 +91,7 @@ struct CorrArgs {
   RowOut* rows;                               // [nstreams][cap_corner + cap_surf]
   int* nn_slot;                               // [nstreams][cap_corner + cap_surf][5] pool slots of the neighbours, -1: gated out
   int* nn;                                    // optional [nstreams][cap_corner + cap_surf][5], -1 where gated out
+  const float* own_box;                       // optional {lo[3], hi[3]}: only queries whose map-frame position is inside are evaluated (sharded map)
   MatchParamsDev prm;
 };
 
@@ -205,17 +206,22 @@ __global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((t & ~31) >= nT) return;   // whole warp idle
   bool isCorner; int src, row;
-  const bool valid = decode_query(t, nC, nS, &isCorner, &src, &row);
+  const bool in_range = decode_query(t, nC, nS, &isCorner, &src, &row);
+  bool valid = in_range;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   if (valid) {
     const float4 p = isCorner ? corner[src] : surf[src];
     transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
+    if (a.own_box) {
+      const float* b = a.own_box;
+      valid = sx >= b[0] && sx < b[3] && sy >= b[1] && sy < b[4] && sz >= b[2] && sz < b[5];
+    }
   }
   const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
   Top5 best;
   knn5_search<kOrigIdx>(g, valid, sx, sy, sz, a.prm.knn_gate, rng, best);
-  if (!valid) return;
-  const bool gate = best.d[4] < a.prm.knn_gate;
+  if (!in_range) return;
+  const bool gate = valid && best.d[4] < a.prm.knn_gate;
   int* out = a.nn_slot + ((size_t)s * capQ + row) * 5;
 #pragma unroll
   for (int k = 0; k < 5; k++) out[k] = gate ? best.slot[k] : -1;
@@ -504,29 +510,49 @@ void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d
   if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, gate, d_idx, d_d2);
 }
 
-void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof) {
-  CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
-  CorrArgs ca;
+static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
-  ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.prm = m.prm;
-  SolveArgs sa;
+  ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
-  sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm;
-  int capQ = m.cap_corner + m.cap_surf;
+  sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
+}
+
+void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
+  CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
+}
+
+// one Gauss-Newton evaluation: correspondences + rows + (partial) normal-equation sums into m.sums
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  const int capQ = m.cap_corner + m.cap_surf;
   int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 32 + 255) / 256;   // + 32: the corner block is padded to a warp
   if (bx < 1) bx = 1;
   dim3 grid(bx, m.nstreams);
+  ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
+  if (prof) prof->begin(stream);
+  if (m.orig_idx) CM_LAUNCH(search_kernel<true>, grid, 256, 0, stream, ca);
+  else CM_LAUNCH(search_kernel<false>, grid, 256, 0, stream, ca);
+  if (prof) prof->end(stream);
+  CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
+  sa.iter = it;
+  CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+}
+
+// solve + pose update + convergence test from the (complete) sums
+void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  sa.iter = it;
+  CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, sums, m.nstreams);
+}
+
+void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof) {
+  launch_match_init(m, stream);
   for (int it = 0; it < m.prm.max_iterations; it++) {
-    ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
-    if (prof) prof->begin(stream);
-    if (m.orig_idx) CM_LAUNCH(search_kernel<true>, grid, 256, 0, stream, ca);
-    else CM_LAUNCH(search_kernel<false>, grid, 256, 0, stream, ca);
-    if (prof) prof->end(stream);
-    CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
-    sa.iter = it;
-    CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
-    CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, (const double*)m.sums, m.nstreams);
+    launch_match_partial(m, it, stream, prof);
+    launch_match_solve(m, it, (const double*)m.sums, stream);
   }
 }
 
