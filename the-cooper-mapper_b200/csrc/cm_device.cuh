@@ -187,10 +187,23 @@ __device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float
     ly = cy + (((float)(vy - cy * k) + (fy - fly)) < half ? -1 : 0);
     lz = cz + (((float)(vz - cz * k) + (fz - flz)) < half ? -1 : 0);
     if (g.window) {
-      int wi = window_index(*g.window, qx, qy, qz);
-      filter = (wi < 0) || !g.window->interior[wi];
+      // candidates can only lie within sqrt(gate) of the query: per-point cube tests are needed only if one of the
+      // (at most 8) cubes touched by that box is not searched
+      const CubeWindow& w = *g.window;
+      const float rg = sqrtf(gate) * 1.0001f;
+      int i0 = (int)(roundf((qx - rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0], i1 = (int)(roundf((qx + rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0];
+      int j0 = (int)(roundf((qy - rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1], j1 = (int)(roundf((qy + rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1];
+      int k0 = (int)(roundf((qz - rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2], k1 = (int)(roundf((qz + rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2];
+      if (i0 < 0 || i1 > 6 || j0 < 0 || j1 > 6 || k0 < 0 || k1 > 6) filter = true;
+      else {
+        for (int i = i0; i <= i1; i++)
+          for (int j = j0; j <= j1; j++)
+            for (int kk = k0; kk <= k1; kk++) filter = filter || !w.active[(i * 7 + j) * 7 + kk];
+      }
     }
-    // ---- level 0: probes ----
+    // ---- level 0: probes, the query's own cell first, then face / edge / corner neighbours (near-to-far: later
+    //      candidates mostly fail the cheap "worse than the 5th" test) ----
+    const int own = (cx - lx) | ((cy - ly) << 1) | ((cz - lz) << 2);
     int nr = 0;
     uint2* my = rng + threadIdx.x;
     const int stride = blockDim.x;
@@ -199,7 +212,7 @@ __device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float
       unsigned long long key[4]; uint4 e[4];
 #pragma unroll
       for (int c = 0; c < 4; c++) {
-        const int cc = b * 4 + c;
+        const int cc = own ^ ((0x76534210 >> (4 * (b * 4 + c))) & 7);   // xor masks 0, 1, 2, 4, 3, 5, 6, 7
         key[c] = pack_cell(lx + (cc & 1), ly + ((cc >> 1) & 1), lz + (cc >> 2));
         e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + (hash_cell(key[c]) & g.mask)));
       }

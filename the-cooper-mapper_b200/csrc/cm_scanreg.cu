@@ -233,11 +233,14 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   const size_t cbase = (size_t)s * rows * cols + S0;   // this ring's slice of the full-resolution arrays
   for (int i = tid; i < n; i += SR_THREADS) {
     state[i] = 0; snap[i] = 0; ev[i] = 0; lab[i] = L_NONE; curv[i] = -1.f;
+    // curvature field of the point = ring + relTime (OrganizedScanRegistration.cpp:109-110); kept in pin[] from here on
+    const float relTime = (float)((double)prm.scan_period * (double)colv[i] / (double)cols);
+    const float tag = (float)ring + relTime;
     if (a.cloud) {
-      float relTime = (float)((double)prm.scan_period * (double)colv[i] / (double)cols);
       a.cloud[cbase + i] = make_float4(px[i], py[i], pz[i], pin[i]);
-      a.cloud_curv[cbase + i] = (float)ring + relTime;
+      a.cloud_curv[cbase + i] = tag;
     }
+    pin[i] = tag;
   }
   __syncthreads();
   const bool ring_ok = !(E0 <= S0 + 2 * R) && n > 0;   // "skip empty scans", ScanRegistration.cpp:205
@@ -341,10 +344,13 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   __shared__ int base[4][SR_MAXREG + 1];
   const int NR = prm.nregions;
   // region of a cell (regions are contiguous and ordered; skipped regions have ep < sp)
-  auto region_of = [&](int c) -> int {
-    for (int j = 0; j < NR; j++) if (reg_ep[j] >= reg_sp[j] && c >= reg_sp[j] && c <= reg_ep[j]) return j;
-    return -1;
-  };
+  for (int c = tid; c < n; c += SR_THREADS) {   // ev[] is free after the mask replay: region id of every cell (-1: none)
+    int rj = -1;
+    for (int j = 0; j < NR; j++) if (reg_ep[j] >= reg_sp[j] && c >= reg_sp[j] && c <= reg_ep[j]) rj = j;
+    ev[c] = (signed char)rj;
+  }
+  __syncthreads();
+  auto region_of = [&](int c) -> int { return (int)ev[c]; };
   if (tid < 4 * SR_MAXREG) { (&cnt2[0][0])[tid] = 0; (&cnt3[0][0])[tid] = 0; }
   // ---- cells above the curvature threshold, in index order (they are the pass-3 candidates, :305-314) -------------
   {
@@ -527,13 +533,11 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   float4* o_pts[4]; int* o_idx[4];
   const size_t rbase = ((size_t)s * rows + ring) * cols;
   for (int l = 0; l < 4; l++) { o_pts[l] = a.ring_pts[l] + rbase; o_idx[l] = a.ring_idx[l] ? a.ring_idx[l] + rbase : nullptr; }
-  const float ringf = (float)ring;
   for (int l = 0; l < 3; l++) {
     int cnt = s_cnt[l];
     for (int i = tid; i < cnt; i += SR_THREADS) {
       int c = lst[l][i];
-      float relTime = (float)((double)prm.scan_period * (double)colv[c] / (double)cols);
-      o_pts[l][i] = make_float4(px[c], py[c], pz[c], ringf + relTime);   // toXYZI: intensity := curvature field
+      o_pts[l][i] = make_float4(px[c], py[c], pz[c], pin[c]);   // toXYZI: intensity := curvature field
       if (o_idx[l]) o_idx[l][i] = S0 + c;
     }
   }
@@ -608,13 +612,11 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     // bitonic sort of key[0..P)
     for (int kk = 2; kk <= P; kk <<= 1)
       for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-        for (int i = tid; i < P; i += SR_THREADS) {
-          int ixj = i ^ jj;
-          if (ixj > i) {
-            unsigned long long x = key[i], y = key[ixj];
-            bool up = (i & kk) == 0;
-            if ((x > y) == up) { key[i] = y; key[ixj] = x; }
-          }
+        for (int pr = tid; pr < (P >> 1); pr += SR_THREADS) {   // one compare-exchange per pair: every lane works
+          const int i = ((pr & ~(jj - 1)) << 1) | (pr & (jj - 1)), ixj = i | jj;
+          const unsigned long long x = key[i], y = key[ixj];
+          const bool up = (i & kk) == 0;
+          if ((x > y) == up) { key[i] = y; key[ixj] = x; }
         }
         __syncthreads();
       }
@@ -631,8 +633,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
         int jx = i;
         for (; jx < nlf && (unsigned int)(key[jx] >> 32) == v; jx++) {
           int c = lst[3][(int)(key[jx] & 0xFFFFFFFFu)];
-          float relTime = (float)((double)prm.scan_period * (double)colv[c] / (double)cols);
-          cx += px[c]; cy += py[c]; cz += pz[c]; ci += ringf + relTime;
+          cx += px[c]; cy += py[c]; cz += pz[c]; ci += pin[c];
         }
         float cnt = (float)(jx - i);
         o_pts[3][base + pos] = make_float4(cx / cnt, cy / cnt, cz / cnt, ci / cnt);

@@ -35,6 +35,8 @@ def main():
             thr = int(r[h.index("Thread Instructions Executed")] or 0)
         except (ValueError, IndexError):
             continue
+        if not ln.strip():
+            continue   # SASS rows under a CUDA line: already included in the line's totals
         key = (fpath.split("/")[-1], ln)
         e = cur["lines"][key]; e[0] += smp; e[1] += ins; e[2] += thr
         if src.strip():
