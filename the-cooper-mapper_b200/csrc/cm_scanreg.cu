@@ -590,23 +590,46 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   }
   const bool passthrough = vb_i[6] != 0;
   {
+    // PCL sorts the points by voxel index (stable here: emission order inside a voxel).  Consecutive list entries
+    // very often share a voxel (the list follows the scan), so the sort is done on RUNS of equal voxel index:
+    // key = (voxel, position of the run's first entry); a voxel's runs then come out in emission order and summing
+    // run after run reproduces the per-point order exactly, with ~3-5x fewer keys to sort.
     const float inv = 1.0f / prm.less_flat_leaf;
-    int P = 1; while (P < nlf) P <<= 1;
-    for (int i = tid; i < P; i += SR_THREADS) {
-      unsigned long long k = 0xFFFFFFFFFFFFFFFFull;
-      if (i < nlf) {
-        int c = lst[3][i];
-        unsigned int idx;
-        if (passthrough) idx = (unsigned int)i;
-        else {
-          int ijk0 = (int)(floorf(px[c] * inv) - (float)vb_i[0]);
-          int ijk1 = (int)(floorf(py[c] * inv) - (float)vb_i[1]);
-          int ijk2 = (int)(floorf(pz[c] * inv) - (float)vb_i[2]);
-          idx = (unsigned int)(ijk0 + ijk1 * vb_i[3] + ijk2 * vb_i[4]);
-        }
-        k = ((unsigned long long)idx << 32) | (unsigned int)i;   // (voxel, emission order): a stable sort by voxel
+    unsigned int* vidx = reinterpret_cast<unsigned int*>(curv);   // curv[] has been written out: reuse as voxel index per entry
+    unsigned short* run_start = nfl;                                // nfl / ord are free as well
+    unsigned short* run_end = ord;                                  // indexed by the run's start position
+    for (int i = tid; i < nlf; i += SR_THREADS) {
+      const int c = lst[3][i];
+      unsigned int idx;
+      if (passthrough) idx = (unsigned int)i;
+      else {
+        int ijk0 = (int)(floorf(px[c] * inv) - (float)vb_i[0]);
+        int ijk1 = (int)(floorf(py[c] * inv) - (float)vb_i[1]);
+        int ijk2 = (int)(floorf(pz[c] * inv) - (float)vb_i[2]);
+        idx = (unsigned int)(ijk0 + ijk1 * vb_i[3] + ijk2 * vb_i[4]);
       }
-      key[i] = k;
+      vidx[i] = idx;
+    }
+    __syncthreads();
+    int nruns = 0;
+    for (int i0 = 0; i0 < nlf; i0 += SR_THREADS) {
+      const int i = i0 + tid;
+      const bool rs = i < nlf && (i == 0 || vidx[i] != vidx[i - 1]);
+      int tot;
+      const int pos = block_scan_excl(rs ? 1 : 0, s_scan, &tot);
+      if (rs) run_start[nruns + pos] = (unsigned short)i;
+      nruns += tot;
+    }
+    __syncthreads();
+    int P = 1; while (P < nruns) P <<= 1;
+    for (int r = tid; r < P; r += SR_THREADS) {
+      unsigned long long k = 0xFFFFFFFFFFFFFFFFull;
+      if (r < nruns) {
+        const int st = run_start[r];
+        run_end[st] = (unsigned short)(r + 1 < nruns ? run_start[r + 1] : nlf);
+        k = ((unsigned long long)vidx[st] << 32) | (unsigned int)st;
+      }
+      key[r] = k;
     }
     __syncthreads();
     // bitonic sort of key[0..P)
@@ -620,22 +643,26 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
         }
         __syncthreads();
       }
-    // heads -> ranks -> centroids
+    // voxel heads among the sorted runs -> output rank -> centroid (runs in order, entries of a run in order)
     int base = 0;
-    for (int i0 = 0; i0 < nlf; i0 += SR_THREADS) {
-      int i = i0 + tid;
-      bool head = i < nlf && (i == 0 || (key[i] >> 32) != (key[i - 1] >> 32));
+    for (int r0 = 0; r0 < nruns; r0 += SR_THREADS) {
+      const int r = r0 + tid;
+      const bool head = r < nruns && (r == 0 || (key[r] >> 32) != (key[r - 1] >> 32));
       int tot;
-      int pos = block_scan_excl(head ? 1 : 0, s_scan, &tot);
+      const int pos = block_scan_excl(head ? 1 : 0, s_scan, &tot);
       if (head) {
-        unsigned int v = (unsigned int)(key[i] >> 32);
+        const unsigned int v = (unsigned int)(key[r] >> 32);
         float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
-        int jx = i;
-        for (; jx < nlf && (unsigned int)(key[jx] >> 32) == v; jx++) {
-          int c = lst[3][(int)(key[jx] & 0xFFFFFFFFu)];
-          cx += px[c]; cy += py[c]; cz += pz[c]; ci += pin[c];
+        int cntp = 0;
+        for (int rr = r; rr < nruns && (unsigned int)(key[rr] >> 32) == v; rr++) {
+          const int st = (int)(key[rr] & 0xFFFFFFFFu), en = run_end[st];
+          for (int j = st; j < en; j++) {
+            const int c = lst[3][j];
+            cx += px[c]; cy += py[c]; cz += pz[c]; ci += pin[c];
+          }
+          cntp += en - st;
         }
-        float cnt = (float)(jx - i);
+        const float cnt = (float)cntp;
         o_pts[3][base + pos] = make_float4(cx / cnt, cy / cnt, cz / cnt, ci / cnt);
       }
       base += tot;
