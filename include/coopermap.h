@@ -131,6 +131,13 @@ typedef struct cm_scanreg_out {
  * NaN), frames[s][row][col]. */
 int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out);
 
+/* MultiScanRegistration::process (MultiScanRegistration.cpp:95-200) + extractFeatures for ONE raw azimuth-major sweep of
+ * n points of a spinning multi-beam LiDAR (lidar: 0 VLP-16, 1 HDL-32, 2 HDL-64E; ring mappers MultiScanRegistration.h:90-102).
+ * The O(n) trigonometric front end (axis swap, ring from the elevation angle, azimuth unwrap, relTime) runs on the host
+ * with libm exactly like the reference; feature extraction runs on the device.  rows_out / cols_out return the ring-major
+ * layout (rings x longest ring) that the optional full-resolution outputs of `out` use (size them for n entries). */
+int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out);
+
 /* pcl::VoxelGrid<pcl::PointXYZI>::filter with a cubic leaf, batched over nseg independent clouds: cloud s is
  * in[s*cap_in .. s*cap_in + n_in[s]) and its result out[s*cap_out .. s*cap_out + n_out[s]), ordered by voxel index,
  * every field (x, y, z, intensity) averaged.  Replaces the filter calls at ScanRegistration.cpp:390-399,

@@ -64,3 +64,15 @@ def test_scanreg_params(cmb, oracle, synth, scene_small):
                                                  blindDegreeThreshold=1.0))
     _check(c2.scanreg_organised(fr, debug=True), o)
     c2.close()
+
+
+@pytest.mark.parametrize("model,lidar", [("VLP-16", 0), ("HDL-64E", 2)])
+def test_scanreg_raw_sweep_entry(ctx, oracle, synth, scene_small, model, lidar):
+    """MultiScanRegistration::process: host trig front end + device feature extraction == oracle, bit for bit."""
+    sc, _, _ = scene_small
+    R, t = synth.pose_matrix(0.4, 0.0, 0.0, (1.0, 0.5, 0.0))
+    fr = synth.simulate_scan(sc, R, t, model, seed=21, cols=1024 if lidar == 2 else None)
+    sweep = synth.organised_to_sweep(fr)
+    ok = np.where(np.isfinite(sweep[:, 0]))[0]
+    sweep = sweep[ok[0]:ok[-1] + 1]      # a driver never starts / ends a sweep on a missing return (startOri / endOri would be NaN)
+    _check(ctx.scanreg_sweep(sweep, lidar, debug=True), oracle.scanreg_sweep(sweep, lidar))

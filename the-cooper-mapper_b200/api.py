@@ -285,6 +285,40 @@ class Context:
             res.append(d)
         return res[0] if single else res
 
+    def scanreg_sweep(self, sweep, lidar, debug=False):
+        """MultiScanRegistration::process for one raw azimuth-major sweep (n, 4); lidar 0 VLP-16, 1 HDL-32, 2 HDL-64E."""
+        sw = _f32(sweep, 4)
+        n = max(len(sw), 1)
+        out = ScanRegOut()
+        bufs = [np.empty((n, 4), np.float32) for _ in range(4)]
+        cnt = np.zeros(5, np.int32)
+        for k in range(4):
+            out.pts[k] = bufs[k].ctypes.data; out.cap[k] = n
+        out.n = cnt.ctypes.data
+        dbg = {}
+        if debug:
+            rings = {0: 16, 1: 32, 2: 64}[lidar]
+            dbg = dict(cloud=np.empty((n, 4), np.float32), ccurv=np.empty(n, np.float32), ranges=np.empty((rings, 2), np.int32),
+                       idx=[np.empty(n, np.int32) for _ in range(4)], picked=np.empty(n, np.int8),
+                       curvature=np.empty(n, np.float32), label=np.empty(n, np.int8))
+            out.cloud = dbg["cloud"].ctypes.data; out.cloud_curvature = dbg["ccurv"].ctypes.data
+            out.scan_ranges = dbg["ranges"].ctypes.data
+            for k in range(4):
+                out.idx[k] = dbg["idx"][k].ctypes.data
+            out.picked = dbg["picked"].ctypes.data; out.curvature = dbg["curvature"].ctypes.data; out.label = dbg["label"].ctypes.data
+        rows = C.c_int(0); cols = C.c_int(0)
+        self._check(self.L.cm_scanreg_sweep_host(self.h, _ptr(sw), C.c_size_t(len(sw)), C.c_int(lidar), C.byref(out), C.byref(rows), C.byref(cols)))
+        names = ["sharp", "lessSharp", "flat", "lessFlat"]
+        d = {names[k]: bufs[k][:cnt[k]].copy() for k in range(4)}
+        if debug:
+            d["scanStart"] = dbg["ranges"][:, 0].copy(); d["scanEnd"] = dbg["ranges"][:, 1].copy()
+            d["cloud"] = np.concatenate([dbg["cloud"], dbg["ccurv"][:, None]], 1)
+            d["sharpIdx"] = dbg["idx"][0][:cnt[0]].copy(); d["lessSharpIdx"] = dbg["idx"][1][:cnt[1]].copy()
+            d["flatIdx"] = dbg["idx"][2][:cnt[2]].copy(); d["lessFlatRawIdx"] = dbg["idx"][3][:cnt[4]].copy()
+            d["picked"] = dbg["picked"].astype(np.int32); d["curvature"] = dbg["curvature"].copy()
+            d["classLabel"] = dbg["label"].astype(np.int32)
+        return d
+
     # ---- voxel filter --------------------------------------------------------------------------------------------
     def voxel_filter_batch(self, clouds, leaf):
         """clouds: list of (n_i, 4) arrays -> list of filtered (m_i, 4) arrays (pcl::VoxelGrid semantics)."""

@@ -247,9 +247,9 @@ void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
 }  // namespace cm
 extern "C" {
 
-int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out) {
-  if (!ctx || !frames || !out || nstreams <= 0 || rows <= 0 || cols <= 0 || !out->n) return fail(ctx, CM_ERR_ARG, "bad argument");
-  for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
+// shared by the organised and the raw-sweep entries: frames (and optional tags) are HOST arrays [S][rows][cols]
+static int scanreg_run_host(cm_ctx* ctx, const cm_point* frames, const float* tags, float blind_sq_override, int nstreams, int rows,
+                            int cols, cm_scanreg_out* out, size_t full_res_entries) {
   const cm_config& cfg = ctx->cfg;
   if (cols > 65535 || cfg.curvature_region < 1 || cfg.curvature_region > 8 || cfg.n_feature_regions < 1 || cfg.n_feature_regions > 16 ||
       cfg.max_surface_flat < 0 || cfg.max_surface_flat > 8 || cfg.max_corner_sharp < 0)
@@ -265,6 +265,12 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
     memset(&L, 0, sizeof(L));
     L.nstreams = nstreams; L.rows = rows; L.cols = cols; L.frames = (const float4*)ctx->d_frames.p;
     fill_scanreg_params(cfg, L);
+    L.blind_sq_override = blind_sq_override;
+    if (tags) {
+      ctx->d_tags.reserve(npts * sizeof(float));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_tags.p, tags, npts * sizeof(float), cudaMemcpyHostToDevice, st));
+      L.tags = (const float*)ctx->d_tags.p;
+    }
     for (int k = 0; k < 4; k++) {
       ctx->d_sr_pts[k].reserve((size_t)nstreams * out->cap[k] * sizeof(cm_point));
       L.out_pts[k] = (float4*)ctx->d_sr_pts[k].p; L.cap[k] = out->cap[k];
@@ -281,16 +287,17 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
     if (out->label) { ctx->d_sr_label.reserve(npts); L.label = (signed char*)ctx->d_sr_label.p; }
     if (out->scan_ranges) { ctx->d_sr_range.reserve(sizeof(int) * 2 * nstreams * rows); L.scan_range = (int*)ctx->d_sr_range.p; }
     ctx->scanreg.run(L, st);
+    const size_t fr = full_res_entries < npts ? full_res_entries : npts;   // full-resolution outputs: entries the caller sized
     for (int k = 0; k < 4; k++)
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->pts[k], L.out_pts[k], (size_t)nstreams * out->cap[k] * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->n, L.out_n, sizeof(int) * 5 * nstreams, cudaMemcpyDeviceToHost, st));
     if (L.want_idx) for (int k = 0; k < 4; k++) if (out->idx[k])
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->idx[k], L.out_idx[k], npts * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (out->cloud) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud, L.cloud, npts * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
-    if (out->cloud && out->cloud_curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud_curvature, L.cloud_curv, npts * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out->picked) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->picked, L.picked, npts, cudaMemcpyDeviceToHost, st));
-    if (out->curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->curvature, L.curvature, npts * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out->label) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->label, L.label, npts, cudaMemcpyDeviceToHost, st));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->idx[k], L.out_idx[k], fr * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out->cloud) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud, L.cloud, fr * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
+    if (out->cloud && out->cloud_curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->cloud_curvature, L.cloud_curv, fr * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out->picked) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->picked, L.picked, fr, cudaMemcpyDeviceToHost, st));
+    if (out->curvature) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->curvature, L.curvature, fr * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out->label) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->label, L.label, fr, cudaMemcpyDeviceToHost, st));
     if (out->scan_ranges) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out->scan_ranges, L.scan_range, sizeof(int) * 2 * nstreams * rows, cudaMemcpyDeviceToHost, st));
     int ovf = 0;
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&ovf, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -303,126 +310,67 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
   return CM_OK;
 }
 
-/* ---- sharded-map matching: one rank's part of ScanMatch::scanMatchScan when the reference map is split over ranks ---- */
-int cm_shard_set_map_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns) {
-  if (!ctx || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument");
-  try {
-    cudaSetDevice(ctx->cfg.device);
-    const cm_config& cfg = ctx->cfg;
-    cudaStream_t st = ctx->stream;
-    ctx->d_ref_corner.reserve((nc ? nc : 1) * sizeof(cm_point));
-    ctx->d_ref_surf.reserve((ns ? ns : 1) * sizeof(cm_point));
-    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), 5.0f, 0, st);
-    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)ns, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), 5.0f, 0, st);
-    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    CM_CUDA_CHECK(ctx, cudaGetLastError());
-    ctx->shard_ready = true;
-  } catch (const CudaError& e) {
-    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
-  }
-  return CM_OK;
+int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out) {
+  if (!ctx || !frames || !out || nstreams <= 0 || rows <= 0 || cols <= 0 || !out->n) return fail(ctx, CM_ERR_ARG, "bad argument");
+  for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
+  return scanreg_run_host(ctx, frames, nullptr, -1.f, nstreams, rows, cols, out, (size_t)nstreams * rows * cols);
 }
 
-int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, const cm_pose* init,
-                        size_t total_ref_corner, size_t total_ref_surf) {
-  if (!ctx || !ctx->shard_ready || !init || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument / no shard map");
-  try {
-    cudaSetDevice(ctx->cfg.device);
-    cudaStream_t st = ctx->stream;
-    MatchParamsDev prm = dev_params(ctx->cfg);
-    const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
-    ctx->d_corner.reserve(capC * sizeof(cm_point)); ctx->d_surf.reserve(capS * sizeof(cm_point));
-    ctx->d_counts.reserve(2 * sizeof(int)); ctx->d_views.reserve(2 * sizeof(GridView)); ctx->d_pose.reserve(6 * sizeof(float));
-    ctx->d_state.reserve(sizeof(MatchState)); ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
-    ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int)); ctx->d_sums.reserve(32 * sizeof(double)); ctx->d_box.reserve(6 * sizeof(float));
-    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    int counts[2] = {(int)nc, (int)ns};
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, init, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-    GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
-    views[0].npts = (int)total_ref_corner; views[1].npts = (int)total_ref_surf;   // the 50 / 100 gate looks at the WHOLE map
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
-    MatchLaunch& m = ctx->shard;
-    m = MatchLaunch();
-    m.nstreams = 1;
-    m.corner = (const float4*)ctx->d_corner.p; m.surf = (const float4*)ctx->d_surf.p;
-    m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
-    m.cap_corner = capC; m.cap_surf = capS;
-    m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
-    m.pose_in = (const float*)ctx->d_pose.p; m.state = (MatchState*)ctx->d_state.p; m.rows = (RowOut*)ctx->d_rows.p;
-    m.nn_slot = (int*)ctx->d_slots.p; m.sums = (double*)ctx->d_sums.p; m.trace = nullptr; m.nn = nullptr;
-    m.orig_idx = 1; m.max_queries = (int)(nc + ns); m.own_box = (const float*)ctx->d_box.p; m.prm = prm;
-    ctx->shard_nq = nc + ns;
-    launch_match_init(m, st);
-    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    CM_CUDA_CHECK(ctx, cudaGetLastError());
-  } catch (const CudaError& e) {
-    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+// Raw-sweep front end, MultiScanRegistration::process (MultiScanRegistration.cpp:95-190): per point axis swap, validity,
+// ring from the elevation angle, azimuth unwrap with the half-sweep flag, relTime -- O(N) libm trigonometry whose
+// half-sweep flag is order dependent; it runs on the host (so it is bit-identical to the reference's libm), the rings are
+// handed to the same device kernels as ring-major rows with their precomputed curvature field.
+int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out) {
+  if (!ctx || (!sweep && n) || !out || !out->n || lidar < 0 || lidar > 2) return fail(ctx, CM_ERR_ARG, "bad argument");
+  for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
+  float lower, upper; int nRings;                       // MultiScanRegistration.h:90-102
+  if (lidar == 0) { lower = -15; upper = 15; nRings = 16; }
+  else if (lidar == 1) { lower = -30.67f; upper = 10.67f; nRings = 32; }
+  else { lower = -24.9f; upper = 2; nRings = 64; }
+  const float factor = (nRings - 1) / (upper - lower);  // MultiScanRegistration.h:63
+  const float scanPeriod = ctx->cfg.scan_period;
+  std::vector<std::vector<cm_point>> ring_pts(nRings);
+  std::vector<std::vector<float>> ring_tag(nRings);
+  if (n > 0) {
+    float startOri = -atan2f(sweep[0].y, sweep[0].x);                                   // :103-110
+    float endOri = -atan2f(sweep[n - 1].y, sweep[n - 1].x) + 2 * float(M_PI);
+    if (endOri - startOri > 3 * M_PI) endOri -= 2 * M_PI;
+    else if (endOri - startOri < M_PI) endOri += 2 * M_PI;
+    bool halfPassed = false;
+    for (size_t i = 0; i < n; i++) {
+      cm_point p;
+      p.x = sweep[i].y; p.y = sweep[i].z; p.z = sweep[i].x; p.intensity = sweep[i].intensity;   // :120-123
+      if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+      if (p.x * p.x + p.y * p.y + p.z * p.z < 0.0001) continue;
+      float angle = atanf(p.y / sqrtf(p.x * p.x + p.z * p.z));
+      int scanID = int(((angle * 180 / M_PI) - lower) * factor + 0.5);                   // MultiScanRegistration.h:85-87
+      if (scanID >= nRings || scanID < 0) continue;
+      float ori = -atan2f(p.x, p.z);
+      if (!halfPassed) {
+        if (ori < startOri - M_PI / 2) ori += 2 * M_PI;
+        else if (ori > startOri + M_PI * 3 / 2) ori -= 2 * M_PI;
+        if (ori - startOri > M_PI) halfPassed = true;
+      } else {
+        ori += 2 * M_PI;
+        if (ori < endOri - M_PI * 3 / 2) ori += 2 * M_PI;
+        else if (ori > endOri + M_PI / 2) ori -= 2 * M_PI;
+      }
+      float relTime = scanPeriod * (ori - startOri) / (endOri - startOri);
+      ring_pts[scanID].push_back(p);
+      ring_tag[scanID].push_back(scanID + relTime);                                      // point.curvature, :167-168
+    }
   }
-  return CM_OK;
-}
-
-int cm_shard_partial_host(cm_ctx* ctx, int iter, const float* own_lo, const float* own_hi, double* sums32) {
-  if (!ctx || !ctx->shard_ready || !own_lo || !own_hi || !sums32 || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
-  try {
-    cudaSetDevice(ctx->cfg.device);
-    cudaStream_t st = ctx->stream;
-    float box[6] = {own_lo[0], own_lo[1], own_lo[2], own_hi[0], own_hi[1], own_hi[2]};
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_box.p, box, sizeof(box), cudaMemcpyHostToDevice, st));
-    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_sums.p, 0, 32 * sizeof(double), st));
-    launch_match_partial(ctx->shard, iter, st, nullptr);
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(sums32, ctx->d_sums.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    CM_CUDA_CHECK(ctx, cudaGetLastError());
-  } catch (const CudaError& e) {
-    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
-  }
-  return CM_OK;
-}
-
-int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* pose, int* done, cm_match_stats* stats) {
-  if (!ctx || !ctx->shard_ready || !sums32 || !pose || !done || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
-  try {
-    cudaSetDevice(ctx->cfg.device);
-    cudaStream_t st = ctx->stream;
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sums.p, sums32, 32 * sizeof(double), cudaMemcpyHostToDevice, st));
-    launch_match_solve(ctx->shard, iter, (const double*)ctx->d_sums.p, st);
-    MatchState hs;
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    CM_CUDA_CHECK(ctx, cudaGetLastError());
-    pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2]; pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
-    *done = hs.done;
-    if (stats) fill_match_stats(ctx->cfg, hs, ctx->shard_nq, stats);
-  } catch (const CudaError& e) {
-    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
-  }
-  return CM_OK;
-}
-
-int cm_timeline_enable(cm_ctx* ctx, int on) { (void)ctx; g_timeline.on = on != 0; return CM_OK; }
-// writes "name total_us launches" lines, sorted by time, into buf; resets the timeline
-int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap) {
-  if (!ctx || !buf || cap == 0) return CM_ERR_ARG;
-  cudaSetDevice(ctx->cfg.device);
-  cudaDeviceSynchronize();
-  std::map<std::string, std::pair<double, int>> agg;
-  for (auto& r : g_timeline.recs) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = agg[r.name]; e.first += ms * 1e3; e.second++; }
-    g_timeline.pool.push_back(r.a); g_timeline.pool.push_back(r.b);
-  }
-  g_timeline.recs.clear();
-  std::vector<std::pair<double, std::string>> v;
-  for (auto& kv : agg) v.push_back({kv.second.first, kv.first});
-  std::sort(v.begin(), v.end(), [](const std::pair<double, std::string>& a, const std::pair<double, std::string>& b) { return a.first > b.first; });
-  std::string out;
-  for (auto& e : v) { char line[256]; snprintf(line, sizeof(line), "%s %.1f %d\n", e.second.c_str(), e.first, agg[e.second].second); out += line; }
-  snprintf(buf, cap, "%s", out.c_str());
-  return CM_OK;
+  size_t cols = 1;
+  for (int r = 0; r < nRings; r++) cols = std::max(cols, ring_pts[r].size());
+  const float qnan = nanf("");
+  std::vector<cm_point> frame((size_t)nRings * cols, cm_point{qnan, qnan, qnan, 0.f});
+  std::vector<float> tags((size_t)nRings * cols, 0.f);
+  for (int r = 0; r < nRings; r++)
+    for (size_t i = 0; i < ring_pts[r].size(); i++) { frame[r * cols + i] = ring_pts[r][i]; tags[r * cols + i] = ring_tag[r][i]; }
+  if (rows_out) *rows_out = nRings;
+  if (cols_out) *cols_out = (int)cols;
+  // the caller's optional full-resolution buffers must hold rows * cols entries; report the shape first when they are absent
+  return scanreg_run_host(ctx, frame.data(), tags.data(), 0.f, 1, nRings, (int)cols, out, n);
 }
 
 int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,

@@ -148,6 +148,8 @@ struct DeviceMap {
 struct ScanRegLaunch {
   int nstreams, rows, cols;
   const float4* frames;                       // device [S][rows][cols]
+  const float* tags;                          // optional device [S][rows][cols] (raw-sweep front end), else NULL
+  float blind_sq_override;                    // >= 0: use instead of blind_radius^2 (the sweep front end filtered already)
   float scan_period, blind_radius, blind_thr, curv_thr, less_flat_leaf;
   int R, nregions, max_sharp, max_flat;
   double cos175, cos5, cos135, cos45;

@@ -257,6 +257,7 @@ static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols,
   memset(&L, 0, sizeof(L));
   L.nstreams = S; L.rows = rows; L.cols = cols; L.frames = d_frames;
   fill_scanreg_params(cfg, L);
+  L.blind_sq_override = -1.f;
   for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)ctx->p_pts[k].p; L.cap[k] = cap; }
   L.out_n = (int*)ctx->p_n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
   ctx->scanreg.run(L, st);

@@ -101,6 +101,8 @@ struct ScanRegParamsDev {
 
 struct ScanRegArgs {
   const float4* frames;      // [S][rows][cols] x, y, z, intensity
+  const float* tags;         // optional [S][rows][cols]: the curvature field (ring + relTime) of every slot, precomputed
+                             // by the raw-sweep front end; NULL: ring + scanPeriod * col / cols (organised sweeps)
   int rows, cols;
   const int* ring_count;     // [S][rows]
   ScanRegParamsDev prm;
@@ -234,8 +236,12 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   for (int i = tid; i < n; i += SR_THREADS) {
     state[i] = 0; snap[i] = 0; ev[i] = 0; lab[i] = L_NONE; curv[i] = -1.f;
     // curvature field of the point = ring + relTime (OrganizedScanRegistration.cpp:109-110); kept in pin[] from here on
-    const float relTime = (float)((double)prm.scan_period * (double)colv[i] / (double)cols);
-    const float tag = (float)ring + relTime;
+    float tag;
+    if (a.tags) tag = a.tags[((size_t)s * rows + ring) * cols + colv[i]];
+    else {
+      const float relTime = (float)((double)prm.scan_period * (double)colv[i] / (double)cols);
+      tag = (float)ring + relTime;
+    }
     if (a.cloud) {
       a.cloud[cbase + i] = make_float4(px[i], py[i], pz[i], pin[i]);
       a.cloud_curv[cbase + i] = tag;
@@ -736,13 +742,13 @@ void ScanRegistrationGpu::run(const ScanRegLaunch& L, cudaStream_t stream) {
     if (L.want_idx) ring_idx[l].reserve(ring_slots * sizeof(int));
   }
   ScanRegParamsDev p;
-  p.scan_period = L.scan_period; p.blind_sq = L.blind_radius * L.blind_radius; p.blind_thr = L.blind_thr; p.curv_thr = L.curv_thr;
+  p.scan_period = L.scan_period; p.blind_sq = L.blind_sq_override >= 0.f ? L.blind_sq_override : L.blind_radius * L.blind_radius; p.blind_thr = L.blind_thr; p.curv_thr = L.curv_thr;
   p.less_flat_leaf = L.less_flat_leaf; p.R = L.R; p.nregions = L.nregions; p.max_sharp = L.max_sharp; p.max_flat = L.max_flat;
   p.cos175 = L.cos175; p.cos5 = L.cos5; p.cos135 = L.cos135; p.cos45 = L.cos45;
   dim3 grid(rows, S);
   CM_LAUNCH(sr_count_kernel, grid, 256, 0, stream, L.frames, rows, cols, p.blind_sq, (int*)ring_count.p);
   ScanRegArgs a;
-  a.frames = L.frames; a.rows = rows; a.cols = cols; a.ring_count = (const int*)ring_count.p; a.prm = p;
+  a.frames = L.frames; a.tags = L.tags; a.rows = rows; a.cols = cols; a.ring_count = (const int*)ring_count.p; a.prm = p;
   for (int l = 0; l < 4; l++) { a.ring_pts[l] = (float4*)ring_pts[l].p; a.ring_idx[l] = L.want_idx ? (int*)ring_idx[l].p : nullptr; }
   a.ring_n = (int*)ring_n.p;
   a.cloud = L.cloud; a.cloud_curv = L.cloud_curv; a.picked = L.picked; a.curvature = L.curvature; a.label = L.label;
