@@ -208,6 +208,14 @@ int cm_last_step_counters(cm_ctx* ctx, unsigned long long* out4);
 int cm_timeline_enable(cm_ctx* ctx, int on);
 int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap);
 
+/* ScanMatch::scanMatchLocal(refCorner, refSurf, corner, surf, Twist&) (ScanMatch.h:38-46, ScanMatch.cpp:375-398): all four
+ * clouds are voxel-filtered first (corner 0.2 m, surf 0.4 m, ScanMatch.cpp:29-30), then scanMatchScan.  This is the call
+ * the pose-graph consumers make (pose_graph/loop_detector.hpp:206-208) with the class defaults use_score = 1 and abort
+ * thresholds 0.05 / 0.05 -- set them in cm_config; stats->ret is the reference's bool. */
+int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_corner, const cm_point* ref_surf, size_t n_ref_surf,
+                        const cm_point* corner, size_t n_corner, const cm_point* surf, size_t n_surf, cm_pose* pose,
+                        cm_match_stats* stats);
+
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.
  * op: 0 QR-solve 6x6 (42 -> 6 floats), 1 QR-solve 5x3 (20 -> 3), 2 eig 3x3 (6 -> 12), 3 eig 6x6 (36 -> 42),

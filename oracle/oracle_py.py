@@ -218,6 +218,15 @@ def scan_match(ref_corner, ref_surf, corner, surf, pose, params=None, nanoflann=
     return p, stats, log
 
 
+def scan_match_local(ref_corner, ref_surf, corner, surf, pose, params=None, nanoflann=True):
+    """ScanMatch::scanMatchLocal (ScanMatch.cpp:375-398): voxel-filter the four clouds (corner 0.2, surf 0.4, :29-30), then
+    scanMatchScan with the class defaults (use score, abort thresholds 0.05, ScanMatch.cpp:22-24)."""
+    d = dict(deltaTAbort=0.05, deltaRAbort=0.05, useScore=1)
+    d.update(params or {})
+    return scan_match(voxel_filter(ref_corner, 0.2), voxel_filter(ref_surf, 0.4), voxel_filter(corner, 0.2), voxel_filter(surf, 0.4),
+                      pose, params=d, nanoflann=nanoflann)
+
+
 # ---- mapping loop -----------------------------------------------------------------------------------------
 class Mapping:
     """LaserMapping::process restated (oracle_map.cpp)."""

@@ -191,3 +191,19 @@ def test_sharded_map_equals_unsharded(cmb, ctx, oracle, synth, scene_small):
     assert iters == ref_stats["iterations"]
     for cx in ctxs:
         cx.close()
+
+
+def test_scan_match_local_with_score_gate(cmb, oracle, synth, scene_small):
+    """ScanMatch::scanMatchLocal as the pose-graph consumers call it: pre-voxelised clouds, score / percentage gate."""
+    sc, mc, ms = scene_small
+    R, t = synth.pose_matrix(0.03, 0.0, 0.0, (2.0, -0.3, 0.05))
+    f = oracle.scanreg_organised(synth.simulate_scan(sc, R, t, "HDL-64E", seed=31))
+    truth = np.array([0.0, 0.0, 0.03, 2.0, -0.3, 0.05], np.float32)
+    sm = cmb.ScanMatch(10)                                   # class defaults: useScore, thresholds 0.05
+    for delta in (np.float32(0.02), np.array([0.01, -0.01, 0.02, 0.3, -0.2, 0.1], np.float32)):
+        ok, pose = sm.scanMatchLocal(mc, ms, f["lessSharp"], f["lessFlat"], truth + delta)
+        po, so, _ = oracle.scan_match_local(mc, ms, f["lessSharp"], f["lessFlat"], truth + delta)
+        assert ok == so["ok"] and np.array_equal(pose, po)
+        assert sm.last_stats["iterations"] == so["iterations"]
+        if so["converged"]:
+            assert abs(sm.last_stats["score"] - so["score"]) <= 1e-9 * max(1.0, so["score"])

@@ -369,6 +369,15 @@ class Context:
                                 nnCorner=nnc[it], nnSurf=nns[it]))
         return p, stats, log
 
+    def match_local(self, ref_corner, ref_surf, corner, surf, pose):
+        """ScanMatch::scanMatchLocal: voxel-filter the four clouds (0.2 / 0.4) then scanMatchScan."""
+        rc_ = _f32(ref_corner, 4); rs = _f32(ref_surf, 4); c = _f32(corner, 4); s = _f32(surf, 4)
+        p = _f32(pose).copy(); st = MatchStats()
+        rc = self._check(self.L.cm_match_local_host(self.h, _ptr(rc_), C.c_size_t(len(rc_)), _ptr(rs), C.c_size_t(len(rs)), _ptr(c),
+                                                    C.c_size_t(len(c)), _ptr(s), C.c_size_t(len(s)), _ptr(p), C.byref(st)))
+        return p, dict(status=rc, ret=bool(st.ret), converged=bool(st.converged), degenerate=bool(st.degenerate),
+                       iterations=st.iterations, rows=st.rows, line=st.line_matches, plane=st.plane_matches, score=st.score)
+
     def match_stateless_iso(self, ref_corner, ref_surf, corner, surf, R, t):
         rc_ = _f32(ref_corner, 4); rs = _f32(ref_surf, 4); c = _f32(corner, 4); s = _f32(surf, 4)
         iso = np.concatenate([_f32(R).ravel(), _f32(t).ravel()]).astype(np.float32)
@@ -432,6 +441,16 @@ class ScanMatch:
 
     def scanMatchScan(self, referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform):
         pose, stats, _ = self.ctx.match_stateless(referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform)
+        self.last_stats = stats
+        if stats["ret"]:
+            self._match_count += 1
+            self._total_score += stats["score"]
+        elif stats["status"] != CM_TOO_FEW_REF:
+            self._fail_match_count += 1
+        return bool(stats["ret"]), pose
+
+    def scanMatchLocal(self, referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform):   # ScanMatch.h:38-46
+        pose, stats = self.ctx.match_local(referenceCornerCloud, referenceSurfCloud, CornerCloud, SurfCloud, transform)
         self.last_stats = stats
         if stats["ret"]:
             self._match_count += 1

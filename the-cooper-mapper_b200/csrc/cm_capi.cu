@@ -123,6 +123,75 @@ void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_
 }  // namespace cm
 extern "C" {
 
+// ScanMatch::scanMatchScan on clouds that are already in device memory (host counts).
+static int match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,
+                               const float4* d_s, size_t ns, cm_pose* pose, cm_match_stats* stats, cm_iter_trace* trace,
+                               int* nn_corner, int* nn_surf) {
+  const cm_config& cfg = ctx->cfg;
+  MatchParamsDev prm = dev_params(cfg);
+  cudaStream_t st = ctx->stream;
+  const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
+  ctx->d_counts.reserve(2 * sizeof(int));
+  ctx->d_views.reserve(2 * sizeof(GridView));
+  ctx->d_pose.reserve(6 * sizeof(float));
+  ctx->d_state.reserve(sizeof(MatchState));
+  ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
+  ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int));
+  ctx->d_sums.reserve(32 * sizeof(double));
+  const bool want_nn = nn_corner || nn_surf;
+  if (trace) ctx->d_trace.reserve(sizeof(IterTrace) * prm.max_iterations);
+  if (want_nn) ctx->d_nn.reserve((size_t)prm.max_iterations * capQ * 5 * sizeof(int));
+  int counts[2] = {(int)nc, (int)ns};
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, pose, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+  ctx->grid_a.build(d_rc, (int)nrc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), prm.knn_gate, 0, st);
+  ctx->grid_b.build(d_rs, (int)nrs, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), prm.knn_gate, 0, st);
+  GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
+  if (trace) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, sizeof(IterTrace) * prm.max_iterations, st));
+  if (want_nn) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_nn.p, 0xFF, (size_t)prm.max_iterations * capQ * 5 * sizeof(int), st));
+  MatchLaunch m;
+  m.nstreams = 1;
+  m.corner = d_c; m.surf = d_s;
+  m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
+  m.cap_corner = capC; m.cap_surf = capS;
+  m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
+  m.pose_in = (const float*)ctx->d_pose.p;
+  m.state = (MatchState*)ctx->d_state.p;
+  m.rows = (RowOut*)ctx->d_rows.p;
+  m.nn_slot = (int*)ctx->d_slots.p;
+  m.sums = (double*)ctx->d_sums.p;
+  m.trace = trace ? (IterTrace*)ctx->d_trace.p : nullptr;
+  m.nn = want_nn ? (int*)ctx->d_nn.p : nullptr;
+  m.orig_idx = 1;
+  m.max_queries = (int)(nc + ns);
+  m.prm = prm;
+  launch_match(m, st);
+  MatchState hs;
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  std::vector<int> hnn;
+  if (want_nn) {
+    hnn.resize((size_t)prm.max_iterations * capQ * 5);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hnn.data(), ctx->d_nn.p, hnn.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  if (trace) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(trace, ctx->d_trace.p, sizeof(IterTrace) * prm.max_iterations, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  CM_CUDA_CHECK(ctx, cudaGetLastError());
+  if (want_nn) {
+    for (int it = 0; it < prm.max_iterations; it++) {
+      const int* src = hnn.data() + (size_t)it * capQ * 5;
+      if (nn_corner && nc) memcpy(nn_corner + (size_t)it * nc * 5, src, nc * 5 * sizeof(int));
+      if (nn_surf && ns) memcpy(nn_surf + (size_t)it * ns * 5, src + nc * 5, ns * 5 * sizeof(int));
+    }
+  }
+  pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2];
+  pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
+  cm_match_stats local;
+  fill_match_stats(cfg, hs, nc + ns, &local);
+  if (stats) *stats = local;
+  return local.status;
+}
+
 int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, const cm_point* ref_surf, size_t nrs,
                             const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, cm_pose* pose,
                             cm_match_stats* stats, cm_iter_trace* trace, int* nn_corner, int* nn_surf) {
@@ -130,77 +199,51 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     return fail(ctx, CM_ERR_ARG, "bad argument");
   try {
     cudaSetDevice(ctx->cfg.device);
-    const cm_config& cfg = ctx->cfg;
-    MatchParamsDev prm = dev_params(cfg);
     cudaStream_t st = ctx->stream;
-    const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
     ctx->d_ref_corner.reserve((nrc ? nrc : 1) * sizeof(cm_point));
     ctx->d_ref_surf.reserve((nrs ? nrs : 1) * sizeof(cm_point));
-    ctx->d_corner.reserve(capC * sizeof(cm_point));
-    ctx->d_surf.reserve(capS * sizeof(cm_point));
-    ctx->d_counts.reserve(2 * sizeof(int));
-    ctx->d_views.reserve(2 * sizeof(GridView));
-    ctx->d_pose.reserve(6 * sizeof(float));
-    ctx->d_state.reserve(sizeof(MatchState));
-    ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
-    ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int));
-    ctx->d_sums.reserve(32 * sizeof(double));
-    const bool want_nn = nn_corner || nn_surf;
-    if (trace) ctx->d_trace.reserve(sizeof(IterTrace) * prm.max_iterations);
-    if (want_nn) ctx->d_nn.reserve((size_t)prm.max_iterations * capQ * 5 * sizeof(int));
+    ctx->d_corner.reserve((nc ? nc : 1) * sizeof(cm_point));
+    ctx->d_surf.reserve((ns ? ns : 1) * sizeof(cm_point));
     if (nrc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_corner.p, ref_corner, nrc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     if (nrs) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, ref_surf, nrs * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    int counts[2] = {(int)nc, (int)ns};
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, pose, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nrc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), prm.knn_gate, 0, st);
-    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)nrs, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), prm.knn_gate, 0, st);
-    GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
-    if (trace) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, sizeof(IterTrace) * prm.max_iterations, st));
-    if (want_nn) CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_nn.p, 0xFF, (size_t)prm.max_iterations * capQ * 5 * sizeof(int), st));
-    MatchLaunch m;
-    m.nstreams = 1;
-    m.corner = (const float4*)ctx->d_corner.p; m.surf = (const float4*)ctx->d_surf.p;
-    m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
-    m.cap_corner = capC; m.cap_surf = capS;
-    m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
-    m.pose_in = (const float*)ctx->d_pose.p;
-    m.state = (MatchState*)ctx->d_state.p;
-    m.rows = (RowOut*)ctx->d_rows.p;
-    m.nn_slot = (int*)ctx->d_slots.p;
-    m.sums = (double*)ctx->d_sums.p;
-    m.trace = trace ? (IterTrace*)ctx->d_trace.p : nullptr;
-    m.nn = want_nn ? (int*)ctx->d_nn.p : nullptr;
-    m.orig_idx = 1;
-    m.max_queries = (int)(nc + ns);
-    m.prm = prm;
-    launch_match(m, st);
-    MatchState hs;
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    std::vector<int> hnn;
-    if (want_nn) {
-      hnn.resize((size_t)prm.max_iterations * capQ * 5);
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hnn.data(), ctx->d_nn.p, hnn.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return match_stateless_dev(ctx, (const float4*)ctx->d_ref_corner.p, nrc, (const float4*)ctx->d_ref_surf.p, nrs,
+                               (const float4*)ctx->d_corner.p, nc, (const float4*)ctx->d_surf.p, ns, pose, stats, trace, nn_corner, nn_surf);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+// ScanMatch::scanMatchLocal (ScanMatch.cpp:375-398): voxel-filter all four clouds (corner 0.2, surf 0.4, ScanMatch.cpp:29-30)
+// on the device, then scanMatchScan.
+int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, const cm_point* ref_surf, size_t nrs,
+                        const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, cm_pose* pose, cm_match_stats* stats) {
+  if (!ctx || !pose || (!ref_corner && nrc) || (!ref_surf && nrs) || (!corner && nc) || (!surf && ns))
+    return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const cm_point* src[4] = {ref_corner, ref_surf, corner, surf};
+    const size_t n[4] = {nrc, nrs, nc, ns};
+    const float leaf[4] = {0.2f, 0.4f, 0.2f, 0.4f};
+    DeviceBuffer* raw[4] = {&ctx->d_ref_corner, &ctx->d_ref_surf, &ctx->d_corner, &ctx->d_surf};
+    DeviceBuffer* ds[4] = {&ctx->d_l_ds[0], &ctx->d_l_ds[1], &ctx->d_l_ds[2], &ctx->d_l_ds[3]};
+    ctx->d_vn_in.reserve(4 * sizeof(int)); ctx->d_vn_out.reserve(4 * sizeof(int)); ctx->d_flag.reserve(sizeof(int));
+    int nin[4] = {(int)nrc, (int)nrs, (int)nc, (int)ns};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vn_in.p, nin, sizeof(nin), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; k++) {
+      const size_t cap = n[k] ? n[k] : 1;
+      raw[k]->reserve(cap * sizeof(cm_point)); ds[k]->reserve(cap * sizeof(cm_point));
+      if (n[k]) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(raw[k]->p, src[k], n[k] * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+      ctx->voxel.run(1, (const float4*)raw[k]->p, (const int*)ctx->d_vn_in.p + k, (int)cap, (int)n[k], leaf[k], (float4*)ds[k]->p,
+                     (int*)ctx->d_vn_out.p + k, (int)cap, (int*)ctx->d_flag.p, st);
     }
-    if (trace) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(trace, ctx->d_trace.p, sizeof(IterTrace) * prm.max_iterations, cudaMemcpyDeviceToHost, st));
+    int nout[4];
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nout, ctx->d_vn_out.p, sizeof(nout), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    CM_CUDA_CHECK(ctx, cudaGetLastError());
-    if (want_nn) {
-      for (int it = 0; it < prm.max_iterations; it++) {
-        const int* src = hnn.data() + (size_t)it * capQ * 5;
-        if (nn_corner && nc) memcpy(nn_corner + (size_t)it * nc * 5, src, nc * 5 * sizeof(int));
-        if (nn_surf && ns) memcpy(nn_surf + (size_t)it * ns * 5, src + nc * 5, ns * 5 * sizeof(int));
-      }
-    }
-    pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2];
-    pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
-    cm_match_stats local;
-    fill_match_stats(cfg, hs, nc + ns, &local);
-    if (stats) *stats = local;
-    return local.status;
+    return match_stateless_dev(ctx, (const float4*)ds[0]->p, nout[0], (const float4*)ds[1]->p, nout[1], (const float4*)ds[2]->p, nout[2],
+                               (const float4*)ds[3]->p, nout[3], pose, stats, nullptr, nullptr, nullptr);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
@@ -371,6 +414,128 @@ int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lida
   if (cols_out) *cols_out = (int)cols;
   // the caller's optional full-resolution buffers must hold rows * cols entries; report the shape first when they are absent
   return scanreg_run_host(ctx, frame.data(), tags.data(), 0.f, 1, nRings, (int)cols, out, n);
+}
+
+/* ---- sharded-map matching: one rank's part of ScanMatch::scanMatchScan when the reference map is split over ranks ---- */
+int cm_shard_set_map_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns) {
+  if (!ctx || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const cm_config& cfg = ctx->cfg;
+    cudaStream_t st = ctx->stream;
+    ctx->d_ref_corner.reserve((nc ? nc : 1) * sizeof(cm_point));
+    ctx->d_ref_surf.reserve((ns ? ns : 1) * sizeof(cm_point));
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    ctx->grid_a.build((const float4*)ctx->d_ref_corner.p, (int)nc, cell_or_default(cfg.cell_corner, cfg.map_filter_corner, 8.f), 5.0f, 0, st);
+    ctx->grid_b.build((const float4*)ctx->d_ref_surf.p, (int)ns, cell_or_default(cfg.cell_surf, cfg.map_filter_surf, 4.f), 5.0f, 0, st);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    ctx->shard_ready = true;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns, const cm_pose* init,
+                        size_t total_ref_corner, size_t total_ref_surf) {
+  if (!ctx || !ctx->shard_ready || !init || (!corner && nc) || (!surf && ns)) return fail(ctx, CM_ERR_ARG, "bad argument / no shard map");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    MatchParamsDev prm = dev_params(ctx->cfg);
+    const int capC = (int)(nc ? nc : 1), capS = (int)(ns ? ns : 1), capQ = capC + capS;
+    ctx->d_corner.reserve(capC * sizeof(cm_point)); ctx->d_surf.reserve(capS * sizeof(cm_point));
+    ctx->d_counts.reserve(2 * sizeof(int)); ctx->d_views.reserve(2 * sizeof(GridView)); ctx->d_pose.reserve(6 * sizeof(float));
+    ctx->d_state.reserve(sizeof(MatchState)); ctx->d_rows.reserve((size_t)capQ * sizeof(RowOut));
+    ctx->d_slots.reserve((size_t)capQ * 5 * sizeof(int)); ctx->d_sums.reserve(32 * sizeof(double)); ctx->d_box.reserve(6 * sizeof(float));
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    int counts[2] = {(int)nc, (int)ns};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pose.p, init, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    GridView views[2] = {ctx->grid_a.view, ctx->grid_b.view};
+    views[0].npts = (int)total_ref_corner; views[1].npts = (int)total_ref_surf;   // the 50 / 100 gate looks at the WHOLE map
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_views.p, views, sizeof(views), cudaMemcpyHostToDevice, st));
+    MatchLaunch& m = ctx->shard;
+    m = MatchLaunch();
+    m.nstreams = 1;
+    m.corner = (const float4*)ctx->d_corner.p; m.surf = (const float4*)ctx->d_surf.p;
+    m.n_corner = (const int*)ctx->d_counts.p; m.n_surf = (const int*)ctx->d_counts.p + 1;
+    m.cap_corner = capC; m.cap_surf = capS;
+    m.grid_corner = (const GridView*)ctx->d_views.p; m.grid_surf = (const GridView*)ctx->d_views.p + 1;
+    m.pose_in = (const float*)ctx->d_pose.p; m.state = (MatchState*)ctx->d_state.p; m.rows = (RowOut*)ctx->d_rows.p;
+    m.nn_slot = (int*)ctx->d_slots.p; m.sums = (double*)ctx->d_sums.p; m.trace = nullptr; m.nn = nullptr;
+    m.orig_idx = 1; m.max_queries = (int)(nc + ns); m.own_box = (const float*)ctx->d_box.p; m.prm = prm;
+    ctx->shard_nq = nc + ns;
+    launch_match_init(m, st);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_partial_host(cm_ctx* ctx, int iter, const float* own_lo, const float* own_hi, double* sums32) {
+  if (!ctx || !ctx->shard_ready || !own_lo || !own_hi || !sums32 || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    float box[6] = {own_lo[0], own_lo[1], own_lo[2], own_hi[0], own_hi[1], own_hi[2]};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_box.p, box, sizeof(box), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_sums.p, 0, 32 * sizeof(double), st));
+    launch_match_partial(ctx->shard, iter, st, nullptr);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(sums32, ctx->d_sums.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* pose, int* done, cm_match_stats* stats) {
+  if (!ctx || !ctx->shard_ready || !sums32 || !pose || !done || iter < 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sums.p, sums32, 32 * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_match_solve(ctx->shard, iter, (const double*)ctx->d_sums.p, st);
+    MatchState hs;
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    pose->rx = hs.pose[0]; pose->ry = hs.pose[1]; pose->rz = hs.pose[2]; pose->tx = hs.pose[3]; pose->ty = hs.pose[4]; pose->tz = hs.pose[5];
+    *done = hs.done;
+    if (stats) fill_match_stats(ctx->cfg, hs, ctx->shard_nq, stats);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_timeline_enable(cm_ctx* ctx, int on) { (void)ctx; g_timeline.on = on != 0; return CM_OK; }
+// writes "name total_us launches" lines, sorted by time, into buf; resets the timeline
+int cm_timeline_report(cm_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx || !buf || cap == 0) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& r : g_timeline.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = agg[r.name]; e.first += ms * 1e3; e.second++; }
+    g_timeline.pool.push_back(r.a); g_timeline.pool.push_back(r.b);
+  }
+  g_timeline.recs.clear();
+  std::vector<std::pair<double, std::string>> v;
+  for (auto& kv : agg) v.push_back({kv.second.first, kv.first});
+  std::sort(v.begin(), v.end(), [](const std::pair<double, std::string>& a, const std::pair<double, std::string>& b) { return a.first > b.first; });
+  std::string out;
+  for (auto& e : v) { char line[256]; snprintf(line, sizeof(line), "%s %.1f %d\n", e.second.c_str(), e.first, agg[e.second].second); out += line; }
+  snprintf(buf, cap, "%s", out.c_str());
+  return CM_OK;
 }
 
 int cm_voxel_filter_host(cm_ctx* ctx, const cm_point* in, int nseg, const int* n_in, int cap_in, float leaf, cm_point* out,
