@@ -180,6 +180,24 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
  * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
 int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
 
+/* ---- scan-to-scan odometry ------------------------------------------------------------------------------------------ */
+typedef struct cm_odom_stats {
+  int initialising;   /* first frame: clouds stored, no motion estimated (LaserOdometry.cpp:295-303) */
+  int matched;        /* scanMatch ran (last clouds had > 10 corner and > 100 surf points, :338) */
+  int iterations, rows, converged, degenerate;
+} cm_odom_stats;
+
+/* LaserOdometry::process (LaserOdometry.cpp:288-326) for one frame of the context's stream: the four feature clouds of scan
+ * registration in (intensity = ring + relTime), /laser_odom_to_init (`odom` = _Tsum) and the clouds projected to the sweep
+ * end, /laser_cloud_corner_last and /laser_cloud_surf_last (n_less_sharp / n_less_flat points), out.  `transform` returns
+ * the frame-to-frame Twist _transform, which persists as the next initial guess; trace (optional, 25 entries) exposes the
+ * Gauss-Newton iterations.  cm_odometry_reset forgets the previous frame. */
+int cm_odometry_process_host(cm_ctx* ctx, const cm_point* sharp, int n_sharp, const cm_point* less_sharp, int n_less_sharp,
+                             const cm_point* flat, int n_flat, const cm_point* less_flat, int n_less_flat, cm_iso* odom,
+                             cm_pose* transform, cm_point* corner_last, cm_point* surf_last, cm_odom_stats* stats,
+                             cm_iter_trace* trace);
+int cm_odometry_reset(cm_ctx* ctx);
+
 /* ---- sharded-map matching (BASELINE config 4: one map split over ranks) ---------------------------------------------------
  * ScanMatch::scanMatchScan with the reference clouds partitioned in space: rank r holds the map points of its region plus a
  * sqrt(5) m halo (cm_shard_set_map_host), evaluates per iteration only the queries whose map-frame position lies in its

@@ -163,4 +163,25 @@ class LaserMapping {
   MapParams _mp; MatchParams _sp; KnnBackend _knn;
 };
 
+// ---- scan-to-scan odometry (LaserOdometry.cpp) -------------------------------------------------------------------
+struct OdomIterLog { float pose_in[6]; float x[6]; int rows; };
+class LaserOdometry {
+ public:
+  LaserOdometry();
+  // one frame: the four feature clouds of scan registration (sensor frame, intensity = ring + relTime)
+  void process(const std::vector<PointI>& sharp, const std::vector<PointI>& lessSharp, const std::vector<PointI>& flat,
+               const std::vector<PointI>& lessFlat, const KnnBackend& knn);
+  int maxIterations = 25;          // LaserOdometry.cpp:24
+  float deltaTAbort = 0.1f, deltaRAbort = 0.1f;
+  bool systemInited = false;
+  float transform[6];              // _transform (persists across frames)
+  Iso Tsum;                        // /laser_odom_to_init
+  std::vector<PointI> lastCorner, lastSurf;   // /laser_cloud_corner_last, /laser_cloud_surf_last
+  int iterations = 0, lastRows = 0;
+  std::vector<OdomIterLog> log;
+  std::vector<int> ind;            // correspondence indices of the last scanMatch: corner {1,2}, surf {1,2,3}
+ private:
+  void scanMatch(const std::vector<PointI>& sharp, const std::vector<PointI>& flat, const KnnBackend& knn);
+};
+
 }  // namespace cmo

@@ -232,4 +232,32 @@ size_t cmo_mapping_map_surround(void* hh, int which, float* out, size_t cap) {
   return v.size();
 }
 
+// ---- odometry ---------------------------------------------------------------------------------------------------
+struct OdomHandle { LaserOdometry o; KnnBackend knn; };
+void* cmo_odom_create(int useNanoflann) { OdomHandle* h = new OdomHandle(); h->knn = pick_backend(useNanoflann); return h; }
+void cmo_odom_free(void* h) { delete (OdomHandle*)h; }
+// out: transform[6], Tsum R[9] t[3]; counts: iterations, lastRows, nLastCorner, nLastSurf, nLog
+void cmo_odom_process(void* hh, const float* sharp, size_t n0, const float* lessSharp, size_t n1, const float* flat, size_t n2,
+                      const float* lessFlat, size_t n3, float* transform, float* R, float* t, int* counts) {
+  OdomHandle* h = (OdomHandle*)hh;
+  auto vec = [](const float* p, size_t n) { return std::vector<PointI>((const PointI*)p, (const PointI*)p + n); };
+  h->o.process(vec(sharp, n0), vec(lessSharp, n1), vec(flat, n2), vec(lessFlat, n3), h->knn);
+  std::memcpy(transform, h->o.transform, 24); std::memcpy(R, h->o.Tsum.R, 36); std::memcpy(t, h->o.Tsum.t, 12);
+  counts[0] = h->o.iterations; counts[1] = h->o.lastRows; counts[2] = (int)h->o.lastCorner.size(); counts[3] = (int)h->o.lastSurf.size();
+  counts[4] = (int)h->o.log.size();
+}
+void cmo_odom_last_clouds(void* hh, float* corner, float* surf) {
+  OdomHandle* h = (OdomHandle*)hh;
+  copy_out(h->o.lastCorner, corner); copy_out(h->o.lastSurf, surf);
+}
+void cmo_odom_log(void* hh, int it, float* pose_in, float* x, int* rows) {
+  const OdomIterLog& l = ((OdomHandle*)hh)->o.log[it];
+  std::memcpy(pose_in, l.pose_in, 24); std::memcpy(x, l.x, 24); *rows = l.rows;
+}
+size_t cmo_odom_indices(void* hh, int* out, size_t cap) {
+  OdomHandle* h = (OdomHandle*)hh;
+  if (out) std::memcpy(out, h->o.ind.data(), std::min(cap, h->o.ind.size()) * sizeof(int));
+  return h->o.ind.size();
+}
+
 }  // extern "C"

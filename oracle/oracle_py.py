@@ -34,6 +34,8 @@ def lib(fast=False):
     L.cmo_voxel_filter.restype = C.c_size_t
     L.cmo_scan_match.restype = C.c_void_p
     L.cmo_mapping_create.restype = C.c_void_p
+    L.cmo_odom_create.restype = C.c_void_p
+    L.cmo_odom_indices.restype = C.c_size_t
     L.cmo_mapping_cloud.restype = C.c_size_t
     L.cmo_mapping_map_surround.restype = C.c_size_t
     L.has_nanoflann = bool(os.path.exists(REF_SO) and L.cmo_load_nanoflann(REF_SO.encode()))
@@ -275,3 +277,34 @@ class Mapping:
         out = np.empty((max(n, 1), 4), np.float32)
         self.L.cmo_mapping_map_surround(C.c_void_p(self.h), C.c_int(which), _p(out), C.c_size_t(len(out)))
         return out[:n].copy()
+
+
+# ---- scan-to-scan odometry -----------------------------------------------------------------------------------
+class Odometry:
+    """LaserOdometry::process restated (oracle_odom.cpp)."""
+
+    def __init__(self, nanoflann=True, fast=False):
+        self.L = lib(fast)
+        self.h = self.L.cmo_odom_create(C.c_int(int(nanoflann and self.L.has_nanoflann)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.cmo_odom_free(C.c_void_p(self.h)); self.h = None
+
+    def process(self, sharp, less_sharp, flat, less_flat):
+        a = [_f32(x).reshape(-1, 4) for x in (sharp, less_sharp, flat, less_flat)]
+        tf = np.empty(6, np.float32); R = np.empty((3, 3), np.float32); t = np.empty(3, np.float32); cnt = np.zeros(5, np.int32)
+        self.L.cmo_odom_process(C.c_void_p(self.h), _p(a[0]), C.c_size_t(len(a[0])), _p(a[1]), C.c_size_t(len(a[1])), _p(a[2]),
+                                C.c_size_t(len(a[2])), _p(a[3]), C.c_size_t(len(a[3])), _p(tf), _p(R), _p(t), _p(cnt))
+        corner = np.empty((max(int(cnt[2]), 1), 4), np.float32); surf = np.empty((max(int(cnt[3]), 1), 4), np.float32)
+        self.L.cmo_odom_last_clouds(C.c_void_p(self.h), _p(corner), _p(surf))
+        log = []
+        for it in range(int(cnt[4])):
+            pin = np.empty(6, np.float32); x = np.empty(6, np.float32); rows = C.c_int(0)
+            self.L.cmo_odom_log(C.c_void_p(self.h), C.c_int(it), _p(pin), _p(x), C.byref(rows))
+            log.append(dict(pose_in=pin, x=x, rows=rows.value))
+        n = self.L.cmo_odom_indices(C.c_void_p(self.h), None, C.c_size_t(0))
+        ind = np.empty(max(n, 1), np.int32)
+        self.L.cmo_odom_indices(C.c_void_p(self.h), _p(ind), C.c_size_t(len(ind)))
+        return dict(transform=tf, R=R, t=t, iterations=int(cnt[0]), rows=int(cnt[1]), corner_last=corner[:cnt[2]].copy(),
+                    surf_last=surf[:cnt[3]].copy(), log=log, ind=ind[:n].copy())

@@ -47,6 +47,11 @@ class ScanRegOut(C.Structure):
                 ("picked", C.c_void_p), ("curvature", C.c_void_p), ("label", C.c_void_p)]
 
 
+class OdomStats(C.Structure):
+    _fields_ = [("initialising", C.c_int), ("matched", C.c_int), ("iterations", C.c_int), ("rows", C.c_int),
+                ("converged", C.c_int), ("degenerate", C.c_int)]
+
+
 class IterTrace(C.Structure):
     _fields_ = [("pose_in", C.c_float * 6), ("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("x", C.c_float * 6),
                 ("rows", C.c_int), ("line_matches", C.c_int), ("plane_matches", C.c_int), ("degenerate", C.c_int)]
@@ -208,6 +213,28 @@ class Context:
         v = np.floor(pts[:, :3] * inv).astype(np.int64)
         order = np.lexsort((v[:, 0], v[:, 1], v[:, 2], cube))
         return pts[order], cube[order]
+
+    # ---- scan-to-scan odometry -------------------------------------------------------------------------------------
+    def odometry_reset(self):
+        self._check(self.L.cm_odometry_reset(self.h))
+
+    def odometry_process(self, sharp, less_sharp, flat, less_flat, trace=False):
+        """LaserOdometry::process for one frame -> dict(R, t, transform, corner_last, surf_last, stats, log)."""
+        a = [_f32(x, 4) for x in (sharp, less_sharp, flat, less_flat)]
+        iso = np.empty(12, np.float32); tf = np.empty(6, np.float32); st = OdomStats()
+        cl = np.empty((max(len(a[1]), 1), 4), np.float32); sl = np.empty((max(len(a[3]), 1), 4), np.float32)
+        tr = (IterTrace * 25)() if trace else None
+        self._check(self.L.cm_odometry_process_host(self.h, _ptr(a[0]), C.c_int(len(a[0])), _ptr(a[1]), C.c_int(len(a[1])), _ptr(a[2]),
+                                                    C.c_int(len(a[2])), _ptr(a[3]), C.c_int(len(a[3])), _ptr(iso), _ptr(tf), _ptr(cl), _ptr(sl),
+                                                    C.byref(st), tr))
+        log = []
+        if trace:
+            for it in range(25):
+                t = tr[it]
+                log.append(dict(pose_in=np.array(t.pose_in[:], np.float32), x=np.array(t.x[:], np.float32), rows=t.rows))
+        return dict(R=iso[:9].reshape(3, 3).copy(), t=iso[9:].copy(), transform=tf, corner_last=cl[:len(a[1])].copy(),
+                    surf_last=sl[:len(a[3])].copy(), iterations=st.iterations, rows=st.rows, matched=bool(st.matched),
+                    initialising=bool(st.initialising), converged=bool(st.converged), log=log)
 
     # ---- measurement helpers -------------------------------------------------------------------------------------
     def timer_record(self, which):
@@ -403,6 +430,17 @@ class LaserMapping:
         isos, stats = self.ctx.mapping_process([(odom_R, odom_t)], [laserCloudCornerLast], [laserCloudSurfLast])
         self.last_stats = stats[0]
         return isos[0]
+
+
+class LaserOdometry:
+    """Mirror of lidar_slam::LaserOdometry (LaserOdometry.h): frame-to-frame odometry on the four feature clouds."""
+
+    def __init__(self, ctx=None, **cfg):
+        self.ctx = ctx or Context(**cfg)
+        self.ctx.odometry_reset()
+
+    def process(self, cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat, surfPointsLessFlat):
+        return self.ctx.odometry_process(cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat, surfPointsLessFlat)
 
 
 class ScanMatch:

@@ -36,6 +36,13 @@ struct cm_ctx {
   std::vector<cm::MappingStream> mstreams;
   cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_slots, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
+  // scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members
+  bool odom_inited = false;
+  float odom_tf[6] = {0, 0, 0, 0, 0, 0};           // _transform (persists across frames, LaserOdometry.cpp never resets it)
+  cm::HostIso odom_Tsum;                            // _Tsum
+  int o_n_last_c = 0, o_n_last_s = 0;
+  cm::DeviceBuffer o_last_c, o_last_s, o_sharp, o_flat, o_ind, o_rows, o_state, o_sums, o_pose, o_trace, o_counts, o_views, o_tf, o_inv, o_slots;
+  cm::GridStorage o_grid_c, o_grid_s;
   // sharded-map matching (cm_shard_*): persistent grids in grid_a / grid_b
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;

@@ -107,6 +107,17 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
 void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr);
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);
+void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream);
+
+// K8: scan-to-scan odometry (cm_odom.inl)
+struct OdomLaunch {
+  const float4* sharp; const float4* flat; int n_sharp, n_flat;
+  const float4* last_corner; const float4* last_surf; int bound_corner, bound_surf;
+  GridView grid_corner, grid_surf;
+  const MatchState* state; int* ind; RowOut* rows;
+};
+void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream);
+void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float* d_inv12, cudaStream_t stream);
 
 // K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes
 // out[s*cap_out .. +n_out[s]).

@@ -392,8 +392,9 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
     for (int k = 0; k < 36; k++) tr->AtA[k] = 0.f;
     for (int k = 0; k < 6; k++) { tr->AtB[k] = 0.f; tr->x[k] = 0.f; }
   }
-  if (nrows < a.prm.min_rows) {   // ScanMatch.cpp:141-145
-    st.flags |= CM_F_TOO_FEW_MATCHES; st.done = 1;
+  if (nrows < a.prm.min_rows) {
+    if (a.prm.few_rows_continue) return;                 // LaserOdometry.cpp:501-503: skip this iteration
+    st.flags |= CM_F_TOO_FEW_MATCHES; st.done = 1;       // ScanMatch.cpp:141-145: leave the loop
     return;
   }
   float AtA[36], AtB[6], X[6];
@@ -436,6 +437,7 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
   }
   float np[6];
   for (int k = 0; k < 6; k++) np[k] = st.pose[k] + X[k];   // ScanMatch.cpp:242-247
+  if (a.prm.nan_guard) for (int k = 0; k < 6; k++) if (!isfinite(np[k])) np[k] = 0.f;   // LaserOdometry.cpp:622-634
   state_set_pose(st, np);
   st.iterations = a.iter + 1;
   if (tr) {
@@ -452,6 +454,8 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
   float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
   if (deltaR < a.prm.delta_r_abort && deltaT < a.prm.delta_t_abort) { st.flags |= CM_F_CONVERGED; st.done = 1; }
 }
+
+#include "cm_odom.inl"
 
 // ============================================================================================================
 // Stand-alone exact 5-NN (test hook and operator): queries already in the map frame.
@@ -541,11 +545,31 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
 }
 
 // solve + pose update + convergence test from the (complete) sums
+// reduce the rows already written to m.rows (used by the odometry, whose correspondence kernel is its own)
+void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  sa.iter = it;
+  CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+}
+
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream) {
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
   sa.iter = it;
   CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, sums, m.nstreams);
+}
+
+void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
+  OdomArgs a;
+  a.sharp = o.sharp; a.flat = o.flat; a.n_sharp = o.n_sharp; a.n_flat = o.n_flat;
+  a.last_corner = o.last_corner; a.last_surf = o.last_surf; a.bound_corner = o.bound_corner; a.bound_surf = o.bound_surf;
+  a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter;
+  const int nT = ((o.n_sharp + 31) & ~31) + o.n_flat;
+  CM_LAUNCH(odom_corr_kernel, (nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, 128, 0, stream, a);
+}
+void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float* d_inv12, cudaStream_t stream) {
+  if (n > 0) CM_LAUNCH(odom_to_end_kernel, (n + 255) / 256, 256, 0, stream, d_cloud, n, d_tf6, d_inv12);
 }
 
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof) {

@@ -17,7 +17,10 @@ struct MatchParamsDev {
   int min_ref_corner;      // 50, ScanMatch.cpp:57
   int min_ref_surf;        // 100, ScanMatch.cpp:58
   int min_rows;            // 50, ScanMatch.cpp:142
-  float eig_threshold;     // 100, ScanMatch.cpp:223
+  float eig_threshold;     // 100, ScanMatch.cpp:223 (10 in LaserOdometry.cpp:596)
+  int few_rows_continue;   // 0: fewer than min_rows rows ends the loop (ScanMatch.cpp:141-145); 1: the iteration is skipped
+                           //    (LaserOdometry.cpp:501-503)
+  int nan_guard;           // 1: non-finite pose components are reset to 0 (LaserOdometry.cpp:622-634)
 };
 
 // One per stream.  pose = Twist (rot_x, rot_y, rot_z, pos) with the Angle class' cached sin/cos (Angle.h).

@@ -1,0 +1,172 @@
+// cm_odom.inl -- K8: scan-to-scan odometry correspondences (included by cm_match.cu; shares its helpers).
+//
+// Replaces the data-parallel inner loops of LaserOdometry::scanMatch (L_SLAM/src/odometry/LaserOdometry.cpp:355-497,
+// 524-577), transformToStart / transformToEnd (:135-190) and the 4-argument coefficient overloads
+// (util/feature_utils.h:28-61, 77-95).  The reduction and the 6x6 step are the mapping solver's kernels with the
+// odometry's constants (b = -0.05 d, eigenvalue threshold 10, "< 10 rows -> skip the iteration", NaN guards).
+
+struct OdomArgs {
+  const float4* sharp; const float4* flat; int n_sharp, n_flat;
+  const float4* last_corner; const float4* last_surf; int bound_corner, bound_surf;   // scan bounds (clamped)
+  GridView grid_corner, grid_surf;      // over the last clouds, pts[].w = original index
+  const MatchState* state;
+  int* ind;                             // [2 * n_sharp + 3 * n_flat]: corner {closest, second}, surf {closest, second, third}
+  RowOut* rows;                         // [n_sharp + n_flat]
+  int iter;
+};
+
+// transformToStart (LaserOdometry.cpp:135-142): s = 10 * frac(intensity); po = T(_transform * s) * pi
+__device__ __forceinline__ void odom_to_start(const float tf[6], const float4& p, float* x, float* y, float* z) {
+  const float s = 10 * (p.w - (float)(int)p.w);
+  float t[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) t[k] = tf[k] * s;   // Twist::operator*(scale), Twist.h:28-35
+  float R[9];
+  pose_to_matrix(t, R);
+  transform_point(R, t + 3, p.x, p.y, p.z, x, y, z);
+}
+
+__device__ __forceinline__ float odom_sqdiff(const float4& a, float bx, float by, float bz) {   // calcSquaredDiff(a, pointSel)
+  float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
+  __shared__ uint2 rng[8 * 128];
+  __shared__ PoseCoef kc;
+  __shared__ float tf[6];
+  const MatchState& st = *a.state;
+  if (st.done) return;
+  if (threadIdx.x == 0) make_pose_coef(st, kc);
+  if (threadIdx.x < 6) tf[threadIdx.x] = st.pose[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nT = ((a.n_sharp + 31) & ~31) + a.n_flat;
+  if ((t & ~31) >= nT) return;
+  bool isCorner; int src, row;
+  const bool valid = decode_query(t, a.n_sharp, a.n_flat, &isCorner, &src, &row);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (valid) { p = isCorner ? a.sharp[src] : a.flat[src]; odom_to_start(tf, p, &sx, &sy, &sz); }
+  int* ind = isCorner ? a.ind + 2 * src : a.ind + 2 * a.n_sharp + 3 * src;
+  if (a.iter % 5 == 0) {   // LaserOdometry.cpp:358,424: correspondences are refreshed every 5th iteration
+    Top5 best;
+    knn5_search<true>(isCorner ? a.grid_corner : a.grid_surf, valid, sx, sy, sz, 25.0f, rng, best);
+    if (valid) {
+      int closest = -1, min2 = -1, min3 = -1;
+      if (best.d[0] < 25.f && best.slot[0] >= 0) {
+        closest = best.idx[0];
+        if (isCorner) {   // :363-398
+          const float4* lc = a.last_corner;
+          const int scan = (int)lc[closest].w;
+          float minD2 = 25.f;
+          for (int j = closest + 1; j < a.bound_corner; j++) {
+            const float4 q = lc[j];
+            if ((double)(int)q.w > (double)scan + 2.5) break;
+            const float d = odom_sqdiff(q, sx, sy, sz);
+            if ((int)q.w > scan && d < minD2) { minD2 = d; min2 = j; }
+          }
+          for (int j = closest - 1; j >= 0; j--) {
+            const float4 q = lc[j];
+            if ((double)(int)q.w < (double)scan - 2.5) break;
+            const float d = odom_sqdiff(q, sx, sy, sz);
+            if ((int)q.w < scan && d < minD2) { minD2 = d; min2 = j; }
+          }
+        } else {          // :427-476
+          const float4* ls = a.last_surf;
+          const int scan = (int)ls[closest].w;
+          float minD2 = 25.f, minD3 = 25.f;
+          for (int j = closest + 1; j < a.bound_surf; j++) {
+            const float4 q = ls[j];
+            if ((double)(int)q.w > (double)scan + 2.5) break;
+            const float d = odom_sqdiff(q, sx, sy, sz);
+            if ((int)q.w <= scan) { if (d < minD2) { minD2 = d; min2 = j; } }
+            else { if (d < minD3) { minD3 = d; min3 = j; } }
+          }
+          for (int j = closest - 1; j >= 0; j--) {
+            const float4 q = ls[j];
+            if ((double)(int)q.w < (double)scan - 2.5) break;
+            const float d = odom_sqdiff(q, sx, sy, sz);
+            if ((int)q.w >= scan) { if (d < minD2) { minD2 = d; min2 = j; } }
+            else { if (d < minD3) { minD3 = d; min3 = j; } }
+          }
+        }
+      }
+      ind[0] = closest; ind[1] = min2;
+      if (!isCorner) ind[2] = min3;
+    }
+  }
+  if (!valid) return;
+  RowOut rowv;
+#pragma unroll
+  for (int k = 0; k < 6; k++) rowv.a[k] = 0.f;
+  rowv.b = 0.f; rowv.flag = 0;
+  float co[4];
+  bool keep = false;
+  if (isCorner) {
+    if (ind[1] >= 0) {   // getLinePointDistance + getCornerFeatureCoefficients(A, B, X, iter), feature_utils.h:17-26, 42-61
+      const float4 A = a.last_corner[ind[0]], B = a.last_corner[ind[1]];
+      float bx = sx - B.x, by = sy - B.y, bz = sz - B.z;
+      float ax = sx - A.x, ay = sy - A.y, az = sz - A.z;
+      float kx = by * az - bz * ay, ky = bz * ax - bx * az, kz = bx * ay - by * ax;
+      float knorm = norm3f(kx, ky, kz);
+      float lengthAB = norm3f(A.x - B.x, A.y - B.y, A.z - B.z);
+      float ex = B.x - A.x, ey = B.y - A.y, ez = B.z - A.z;
+      float ux = ky * ez - kz * ey, uy = kz * ex - kx * ez, uz = kx * ey - ky * ex;
+      float den = knorm * lengthAB;
+      float dirx = -ux / den, diry = -uy / den, dirz = -uz / den;
+      float distance = knorm / lengthAB;
+      float weight = 1.0f;
+      if (a.iter >= 5) weight = (float)(1 - 1.8 * fabs((double)distance));
+      co[0] = dirx * weight; co[1] = diry * weight; co[2] = dirz * weight; co[3] = distance * weight;
+      keep = ((double)weight > 0.1 && distance != 0);
+    }
+  } else {
+    if (ind[1] >= 0 && ind[2] >= 0) {   // getSurfacePointDistance + getSurfaceFeatureCoefficients(A, B, C, X, iter), :28-40, 77-95
+      const float4 A = a.last_surf[ind[0]], B = a.last_surf[ind[1]], C = a.last_surf[ind[2]];
+      float b0 = B.x - A.x, b1 = B.y - A.y, b2 = B.z - A.z, c0 = C.x - A.x, c1 = C.y - A.y, c2 = C.z - A.z;
+      float nx = b1 * c2 - b2 * c1, ny = b2 * c0 - b0 * c2, nz = b0 * c1 - b1 * c0;
+      float nn = norm3f(nx, ny, nz);
+      if (nn > 0.f) { nx /= nn; ny /= nn; nz /= nn; }
+      float dsigned = ((sx - A.x) * nx + (sy - A.y) * ny) + (sz - A.z) * nz;
+      float cosv = dsigned / norm3f(nx, ny, nz) / norm3f(A.x - sx, A.y - sy, A.z - sz);
+      if (cosv < 0) { nx *= -1.0f; ny *= -1.0f; nz *= -1.0f; }
+      float distance = (float)fabs((double)dsigned);
+      float weight = 1.f;
+      if (a.iter >= 5) weight = (float)(1 - 1.8 * fabs((double)distance) / sqrt((double)norm3f(sx, sy, sz)));
+      co[0] = weight * nx; co[1] = weight * ny; co[2] = weight * nz; co[3] = weight * distance;
+      keep = ((double)weight > 0.1 && distance != 0);
+    }
+  }
+  if (keep) {
+    const float x = p.x, y = p.y, z = p.z;   // LaserOdometry.cpp:556-577 (same Jacobian text as the mapping solver)
+    float arx = (kc.x1 * y + kc.x2 * z) * co[0] + (kc.x3 * y - kc.x4 * z) * co[1] + (kc.x5 * y - kc.x6 * z) * co[2];
+    float ary = (kc.y1 * x + kc.y2 * y + kc.y3 * z) * co[0] + (kc.y4 * x + kc.y5 * y + kc.y6 * z) * co[1] +
+                (kc.y7 * x - kc.y8 * y - kc.y9 * z) * co[2];
+    float arz = (kc.z1 * x - kc.x4 * y + kc.z3 * z) * co[0] + (kc.z4 * x + kc.z5 * y + kc.z6 + kc.z7 * z) * co[1] + 0 * co[2];
+    rowv.a[0] = arx; rowv.a[1] = ary; rowv.a[2] = arz; rowv.a[3] = co[0]; rowv.a[4] = co[1]; rowv.a[5] = co[2];
+    rowv.b = (float)(-0.05 * (double)co[3]);
+    rowv.flag = 3;
+  }
+  float4* dst = reinterpret_cast<float4*>(a.rows + row);
+  dst[0] = make_float4(rowv.a[0], rowv.a[1], rowv.a[2], rowv.a[3]);
+  dst[1] = make_float4(rowv.a[4], rowv.a[5], rowv.b, __int_as_float(rowv.flag));
+}
+
+// transformToEnd (LaserOdometry.cpp:156-168): every point to the sweep start, then through the inverse of the full transform
+__global__ void odom_to_end_kernel(float4* __restrict__ cloud, int n, const float* __restrict__ tf6, const float* __restrict__ inv12) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float tf[6], R[9], t[3];
+#pragma unroll
+  for (int k = 0; k < 6; k++) tf[k] = tf6[k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = inv12[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) t[k] = inv12[9 + k];
+  float4 p = cloud[i];
+  float sx, sy, sz, x, y, z;
+  odom_to_start(tf, p, &sx, &sy, &sz);
+  transform_point(R, t, sx, sy, sz, &x, &y, &z);
+  cloud[i] = make_float4(x, y, z, p.w);
+}
