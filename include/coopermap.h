@@ -234,6 +234,12 @@ int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_co
                         const cm_point* corner, size_t n_corner, const cm_point* surf, size_t n_surf, cm_pose* pose,
                         cm_match_stats* stats);
 
+/* Development aid (no reference counterpart): per-warp trace of the 5-NN search kernel in Gauss-Newton evaluation `iter` of
+ * the following cm_pipeline_step / cm_mapping_process calls (iter < 0: off).  4 words per warp: start ns, end ns,
+ * (max << 32 | sum) level-0 candidates over the lanes, (hard queries << 32 | smid << 16 | is_corner). */
+int cm_debug_search_trace_enable(cm_ctx* ctx, int iter);
+int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_words, size_t* n_words);
+
 /* Self-test hook (no reference counterpart): run one of the shared small-matrix routines (csrc/cm_math.h -- the restated
  * Eigen algorithms) over n packed inputs ON THE DEVICE, so a test can compare with the same header compiled for the host.
  * op: 0 QR-solve 6x6 (42 -> 6 floats), 1 QR-solve 5x3 (20 -> 3), 2 eig 3x3 (6 -> 12), 3 eig 6x6 (36 -> 42),

@@ -167,6 +167,7 @@ static int match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, cons
   m.orig_idx = 1;
   m.max_queries = (int)(nc + ns);
   m.prm = prm;
+  ctx->hardq.attach(m, nc + ns + 32);
   launch_match(m, st);
   MatchState hs;
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -470,6 +471,7 @@ int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t nc, const cm
     m.nn_slot = (int*)ctx->d_slots.p; m.sums = (double*)ctx->d_sums.p; m.trace = nullptr; m.nn = nullptr;
     m.orig_idx = 1; m.max_queries = (int)(nc + ns); m.own_box = (const float*)ctx->d_box.p; m.prm = prm;
     ctx->shard_nq = nc + ns;
+    ctx->hardq.attach(m, nc + ns + 32);
     launch_match_init(m, st);
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     CM_CUDA_CHECK(ctx, cudaGetLastError());

@@ -36,6 +36,8 @@ struct cm_ctx {
   std::vector<cm::MappingStream> mstreams;
   cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_slots, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
+  cm::DeviceBuffer dbg_trace; bool dbg_on = false; int dbg_iter = 0; size_t dbg_words = 0;   // cm_debug_search_trace
+  cm::HardQueue hardq;                              // deferred hard 5-NN queries of the current match (cm_match.cu)
   // scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members
   bool odom_inited = false;
   float odom_tf[6] = {0, 0, 0, 0, 0, 0};           // _transform (persists across frames, LaserOdometry.cpp never resets it)

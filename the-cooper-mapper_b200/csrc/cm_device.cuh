@@ -163,149 +163,199 @@ __device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z
 // (cells are unions of PCL voxels and the voxel index floor(p * inv_leaf) is monotone in p; the 2 % margin covers
 // the float rounding of p * inv_leaf).  Shell cells whose box lies farther than the current 5th distance (or the
 // gate) are skipped without a probe.
-// rng: shared memory, 8 * blockDim.x uint2 (this thread uses rng[c * blockDim.x + threadIdx.x]).
+
+// Geometry of one query relative to the grid: low cell of its 2x2x2 level-0 block, distance to the block faces.
+struct KnnGeom {
+  float fx, fy, fz;     // query in voxel units
+  int lx, ly, lz;       // low cell of the level-0 block
+  int own;              // position of the query's own cell inside the block (bit per axis)
+  float m0;             // distance (voxel units) from the query to the nearest face of the block
+  bool filter;          // candidates need the per-point cube test
+};
+
+// returns false when the coordinates are too large for the cell arithmetic (the query then has no neighbours)
+__device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy, float qz, float gate, KnnGeom& c) {
+  const int k = g.kdiv;
+  c.fx = qx * g.inv_leaf; c.fy = qy * g.inv_leaf; c.fz = qz * g.inv_leaf;
+  const float flx = floorf(c.fx), fly = floorf(c.fy), flz = floorf(c.fz);
+  c.lx = c.ly = c.lz = 0; c.own = 0; c.m0 = 0.f; c.filter = false;
+  // keep the casts defined for absurd coordinates
+  if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return false;
+  const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
+  const int cx = floor_div(vx, k), cy = floor_div(vy, k), cz = floor_div(vz, k);
+  const float half = 0.5f * (float)k;
+  // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
+  c.lx = cx + (((float)(vx - cx * k) + (c.fx - flx)) < half ? -1 : 0);
+  c.ly = cy + (((float)(vy - cy * k) + (c.fy - fly)) < half ? -1 : 0);
+  c.lz = cz + (((float)(vz - cz * k) + (c.fz - flz)) < half ? -1 : 0);
+  c.own = (cx - c.lx) | ((cy - c.ly) << 1) | ((cz - c.lz) << 2);
+  if (g.window) {
+    // candidates can only lie within sqrt(gate) of the query: per-point cube tests are needed only if one of the
+    // (at most 8) cubes touched by that box is not searched
+    const CubeWindow& w = *g.window;
+    const float rg = sqrtf(gate) * 1.0001f;
+    int i0 = (int)(roundf((qx - rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0], i1 = (int)(roundf((qx + rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0];
+    int j0 = (int)(roundf((qy - rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1], j1 = (int)(roundf((qy + rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1];
+    int k0 = (int)(roundf((qz - rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2], k1 = (int)(roundf((qz + rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2];
+    if (i0 < 0 || i1 > 6 || j0 < 0 || j1 > 6 || k0 < 0 || k1 > 6) c.filter = true;
+    else {
+      for (int i = i0; i <= i1; i++)
+        for (int j = j0; j <= j1; j++)
+          for (int kk = k0; kk <= k1; kk++) c.filter = c.filter || !w.active[(i * 7 + j) * 7 + kk];
+    }
+  }
+  // distance (voxel units) from the query to the nearest face of the level-0 block
+  const float lox = (float)(c.lx * k), loy = (float)(c.ly * k), loz = (float)(c.lz * k);
+  const float span = (float)(2 * k);
+  c.m0 = fminf(fminf(c.fx - lox, lox + span - c.fx), fminf(fminf(c.fy - loy, loy + span - c.fy), fminf(c.fz - loz, loz + span - c.fz)));
+  return true;
+}
+
+// Level 0 of one query (per thread).  Returns true when the list is not yet provably final (levels >= 1 needed).
+// The 8 cells are probed together; their point ranges are staged in shared memory with the squared lower bound of
+// the distance from the query to the cell's box, own cell first, then face / edge / corner neighbours.  A range is
+// skipped when that bound already exceeds the current 5th distance (every point of the cell is then strictly
+// farther than five known points) -- on a 0.4 m map this drops about half of the candidate loads.
+// rng: shared memory, 8 * blockDim.x uint4 (this thread uses rng[c * blockDim.x + threadIdx.x]).
 template <bool kOrigIdx>
-__device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float qx, float qy, float qz, float gate, uint2* rng,
-                                            Top5& best) {
-  top5_init(best);
+__device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c, float qx, float qy, float qz, uint4* rng, Top5& best,
+                                            unsigned int* ncand = nullptr) {
+  const int k = g.kdiv;
+  const float kf = (float)k;
+  const float leaf98 = 0.98f * (g.cell / kf);
+  int nr = 0;
+  uint4* my = rng + threadIdx.x;
+  const int stride = blockDim.x;
+#pragma unroll
+  for (int b = 0; b < 2; b++) {
+    unsigned long long key[4]; uint4 e[4];
+#pragma unroll
+    for (int cI = 0; cI < 4; cI++) {
+      const int cc = c.own ^ ((0x76534210 >> (4 * (b * 4 + cI))) & 7);   // xor masks 0, 1, 2, 4, 3, 5, 6, 7
+      key[cI] = pack_cell(c.lx + (cc & 1), c.ly + ((cc >> 1) & 1), c.lz + (cc >> 2));
+      e[cI] = __ldg(reinterpret_cast<const uint4*>(g.entries + (hash_cell(key[cI]) & g.mask)));
+    }
+#pragma unroll
+    for (int cI = 0; cI < 4; cI++) {
+      unsigned long long kk = entry_key(e[cI]);
+      if (kk != key[cI] && kk != CM_EMPTY_KEY) {   // linear probing (rare)
+        unsigned int h = hash_cell(key[cI]) & g.mask;
+        do { h = (h + 1) & g.mask; e[cI] = __ldg(reinterpret_cast<const uint4*>(g.entries + h)); kk = entry_key(e[cI]); }
+        while (kk != key[cI] && kk != CM_EMPTY_KEY);
+      }
+      if (kk == key[cI] && e[cI].w > 0) {
+        const int cc = c.own ^ ((0x76534210 >> (4 * (b * 4 + cI))) & 7);
+        const float x0 = (float)((c.lx + (cc & 1)) * k), y0 = (float)((c.ly + ((cc >> 1) & 1)) * k), z0 = (float)((c.lz + (cc >> 2)) * k);
+        const float dxv = slab_dist(c.fx, x0, x0 + kf), dyv = slab_dist(c.fy, y0, y0 + kf), dzv = slab_dist(c.fz, z0, z0 + kf);
+        const float lb = leaf98 * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);
+        my[nr * stride] = make_uint4(e[cI].z, e[cI].w, __float_as_uint(lb * lb), 0u);
+        nr++;
+      }
+    }
+  }
+  // ---- one flattened candidate loop ----
+  unsigned int scanned = 0;
+  int ci = 0; unsigned int j0 = 0;
+  uint4 r = nr ? my[0] : make_uint4(0u, 0u, 0u, 0u);
+  while (ci < nr) {
+    if (j0 == 0 && __uint_as_float(r.z) > best.d[4]) {   // the whole cell is farther than the current 5th neighbour
+      ci++; if (ci < nr) r = my[ci * stride];
+      continue;
+    }
+    const unsigned int left = r.y - j0;
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if ((unsigned int)u < left) p[u] = __ldg(g.pts + r.x + j0 + u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if ((unsigned int)u < left) {
+        bool ok = true;
+        if (c.filter) { int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z); ok = (wi >= 0) && g.window->active[wi]; }
+        if (ok) {
+          float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
+          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          const int j = (int)(r.x + j0 + u);
+          top5_insert(best, d, kOrigIdx ? __float_as_int(p[u].w) : j, j);
+        }
+      }
+    }
+    if (ncand) scanned += left < 4u ? left : 4u;
+    j0 += 4;
+    if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
+  }
+  if (ncand) *ncand = scanned;
+  if (g.max_level < 1) return false;
+  const float r0 = leaf98 * c.m0;
+  return !(best.d[4] < r0 * r0);
+}
+
+// Levels >= 1 of ONE query, executed by a whole warp.  The query (position, geometry, current list) lives in lane h;
+// on return lane h's list is final.
+template <bool kOrigIdx>
+__device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const KnnGeom& c, float qx, float qy, float qz, float gate,
+                                                 Top5& best) {
   const unsigned int FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = g.kdiv;
-  const float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
-  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-  // keep the casts defined for absurd coordinates
-  valid = valid && (fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f);
-  int lx = 0, ly = 0, lz = 0;
-  bool filter = false;
-  float m0 = 0.f;
-  if (valid) {
-    const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
-    const int cx = floor_div(vx, k), cy = floor_div(vy, k), cz = floor_div(vz, k);
-    const float half = 0.5f * (float)k;
-    // low cell of the 2-cell span that keeps the query >= cell/2 away from both ends
-    lx = cx + (((float)(vx - cx * k) + (fx - flx)) < half ? -1 : 0);
-    ly = cy + (((float)(vy - cy * k) + (fy - fly)) < half ? -1 : 0);
-    lz = cz + (((float)(vz - cz * k) + (fz - flz)) < half ? -1 : 0);
-    if (g.window) {
-      // candidates can only lie within sqrt(gate) of the query: per-point cube tests are needed only if one of the
-      // (at most 8) cubes touched by that box is not searched
-      const CubeWindow& w = *g.window;
-      const float rg = sqrtf(gate) * 1.0001f;
-      int i0 = (int)(roundf((qx - rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0], i1 = (int)(roundf((qx + rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0];
-      int j0 = (int)(roundf((qy - rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1], j1 = (int)(roundf((qy + rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1];
-      int k0 = (int)(roundf((qz - rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2], k1 = (int)(roundf((qz + rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2];
-      if (i0 < 0 || i1 > 6 || j0 < 0 || j1 > 6 || k0 < 0 || k1 > 6) filter = true;
-      else {
-        for (int i = i0; i <= i1; i++)
-          for (int j = j0; j <= j1; j++)
-            for (int kk = k0; kk <= k1; kk++) filter = filter || !w.active[(i * 7 + j) * 7 + kk];
-      }
-    }
-    // ---- level 0: probes, the query's own cell first, then face / edge / corner neighbours (near-to-far: later
-    //      candidates mostly fail the cheap "worse than the 5th" test) ----
-    const int own = (cx - lx) | ((cy - ly) << 1) | ((cz - lz) << 2);
-    int nr = 0;
-    uint2* my = rng + threadIdx.x;
-    const int stride = blockDim.x;
-#pragma unroll
-    for (int b = 0; b < 2; b++) {
-      unsigned long long key[4]; uint4 e[4];
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int cc = own ^ ((0x76534210 >> (4 * (b * 4 + c))) & 7);   // xor masks 0, 1, 2, 4, 3, 5, 6, 7
-        key[c] = pack_cell(lx + (cc & 1), ly + ((cc >> 1) & 1), lz + (cc >> 2));
-        e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + (hash_cell(key[c]) & g.mask)));
-      }
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        unsigned long long kk = entry_key(e[c]);
-        if (kk != key[c] && kk != CM_EMPTY_KEY) {   // linear probing (rare)
-          unsigned int h = hash_cell(key[c]) & g.mask;
-          do { h = (h + 1) & g.mask; e[c] = __ldg(reinterpret_cast<const uint4*>(g.entries + h)); kk = entry_key(e[c]); }
-          while (kk != key[c] && kk != CM_EMPTY_KEY);
-        }
-        if (kk == key[c] && e[c].w > 0) { my[nr * stride] = make_uint2(e[c].z, e[c].w); nr++; }
-      }
-    }
-    // ---- level 0: one flattened candidate loop ----
-    int ci = 0; unsigned int j0 = 0;
-    uint2 r = nr ? my[0] : make_uint2(0u, 0u);
-    while (ci < nr) {
-      const unsigned int left = r.y - j0;
-      float4 p[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if ((unsigned int)u < left) p[u] = __ldg(g.pts + r.x + j0 + u);
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if ((unsigned int)u < left) {
-          bool ok = true;
-          if (filter) { int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z); ok = (wi >= 0) && g.window->active[wi]; }
-          if (ok) {
-            float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
-            float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const int j = (int)(r.x + j0 + u);
-            top5_insert(best, d, kOrigIdx ? __float_as_int(p[u].w) : j, j);
-          }
-        }
-      }
-      j0 += 4;
-      if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
-    }
-    // distance (voxel units) from the query to the nearest face of the level-0 block
-    const float lox = (float)(lx * k), loy = (float)(ly * k), loz = (float)(lz * k);
-    const float span = (float)(2 * k);
-    m0 = fminf(fminf(fx - lox, lox + span - fx), fminf(fminf(fy - loy, loy + span - fy), fminf(fz - loz, loz + span - fz)));
-  }
-  // ---- levels >= 1: warp-cooperative, one unresolved query at a time ----
   const float leaf = g.cell / (float)k;
+  const float bqx = __shfl_sync(FULL, qx, h), bqy = __shfl_sync(FULL, qy, h), bqz = __shfl_sync(FULL, qz, h);
+  const float bfx = __shfl_sync(FULL, c.fx, h), bfy = __shfl_sync(FULL, c.fy, h), bfz = __shfl_sync(FULL, c.fz, h);
+  const int blx = __shfl_sync(FULL, c.lx, h), bly = __shfl_sync(FULL, c.ly, h), blz = __shfl_sync(FULL, c.lz, h);
+  const float bm0 = __shfl_sync(FULL, c.m0, h);
+  const bool bfilter = __shfl_sync(FULL, c.filter ? 1 : 0, h) != 0;
+  float bd5 = __shfl_sync(FULL, best.d[4], h);
+  const float kf = (float)k;
+  for (int L = 1; L <= g.max_level; L++) {
+    const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
+    if (bd5 < rr * rr) break;
+    const int n = 2 + 2 * L, ncells = n * n * n;
+    const float bound = fminf(bd5, gate);
+    Top5 loc;
+    top5_init(loc);
+    for (int t = lane; t < ncells; t += 32) {
+      const int dz = t / (n * n), dy = (t / n) % n, dx = t % n;
+      if (dx > 0 && dx < n - 1 && dy > 0 && dy < n - 1 && dz > 0 && dz < n - 1) continue;   // visited at the previous levels
+      const float cxl = (float)((blx - L + dx) * k), cyl = (float)((bly - L + dy) * k), czl = (float)((blz - L + dz) * k);
+      const float dxv = slab_dist(bfx, cxl, cxl + kf), dyv = slab_dist(bfy, cyl, cyl + kf), dzv = slab_dist(bfz, czl, czl + kf);
+      const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);   // lower bound of the distance to this cell
+      if (lb * lb >= bound) continue;
+      scan_cell<kOrigIdx>(g, blx - L + dx, bly - L + dy, blz - L + dz, bqx, bqy, bqz, bfilter, loc);
+    }
+    // merge the lane-local lists into the owner's list: at most 5 winners can enter
+    for (int round = 0; round < 5; round++) {
+      const unsigned int dbits = __float_as_uint(loc.d[0]);   // distances are >= 0: the bit pattern orders like the value
+      const unsigned int mind = __reduce_min_sync(FULL, dbits);
+      if (mind == __float_as_uint(FLT_MAX)) break;
+      const unsigned int cand = (dbits == mind) ? (unsigned int)loc.idx[0] : 0xFFFFFFFFu;
+      const unsigned int mini = __reduce_min_sync(FULL, cand);
+      const int src = __ffs(__ballot_sync(FULL, dbits == mind && (unsigned int)loc.idx[0] == mini)) - 1;
+      const int wslot = __shfl_sync(FULL, loc.slot[0], src);
+      if (lane == h) top5_insert(best, __uint_as_float(mind), (int)mini, wslot);
+      if (lane == src) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) { loc.d[u] = loc.d[u + 1]; loc.idx[u] = loc.idx[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
+        loc.d[4] = FLT_MAX; loc.idx[4] = 0x7fffffff; loc.slot[4] = -1;
+      }
+    }
+    bd5 = __shfl_sync(FULL, best.d[4], h);
+  }
+}
+
+// Level 0 per thread, then the warp finishes its unresolved queries one at a time (callers without a deferred pass).
+template <bool kOrigIdx>
+__device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float qx, float qy, float qz, float gate, uint4* rng,
+                                            Top5& best) {
+  top5_init(best);
+  KnnGeom c;
+  valid = knn5_geom(g, qx, qy, qz, gate, c) && valid;
   bool need = false;
-  if (valid && g.max_level >= 1) { const float r0 = 0.98f * leaf * m0; need = !(best.d[4] < r0 * r0); }
-  unsigned int hard = __ballot_sync(FULL, need);
+  if (valid) need = knn5_level0<kOrigIdx>(g, c, qx, qy, qz, rng, best);
+  unsigned int hard = __ballot_sync(0xffffffffu, need);
   while (hard) {
     const int h = __ffs(hard) - 1;
     hard &= hard - 1;
-    const float bqx = __shfl_sync(FULL, qx, h), bqy = __shfl_sync(FULL, qy, h), bqz = __shfl_sync(FULL, qz, h);
-    const float bfx = __shfl_sync(FULL, fx, h), bfy = __shfl_sync(FULL, fy, h), bfz = __shfl_sync(FULL, fz, h);
-    const int blx = __shfl_sync(FULL, lx, h), bly = __shfl_sync(FULL, ly, h), blz = __shfl_sync(FULL, lz, h);
-    const float bm0 = __shfl_sync(FULL, m0, h);
-    const bool bfilter = __shfl_sync(FULL, filter ? 1 : 0, h) != 0;
-    float bd5 = __shfl_sync(FULL, best.d[4], h);
-    const float kf = (float)k;
-    for (int L = 1; L <= g.max_level; L++) {
-      const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
-      if (bd5 < rr * rr) break;
-      const int n = 2 + 2 * L, ncells = n * n * n;
-      const float bound = fminf(bd5, gate);
-      Top5 loc;
-      top5_init(loc);
-      for (int t = lane; t < ncells; t += 32) {
-        const int dz = t / (n * n), dy = (t / n) % n, dx = t % n;
-        if (dx > 0 && dx < n - 1 && dy > 0 && dy < n - 1 && dz > 0 && dz < n - 1) continue;   // visited at the previous levels
-        const float cxl = (float)((blx - L + dx) * k), cyl = (float)((bly - L + dy) * k), czl = (float)((blz - L + dz) * k);
-        const float dxv = slab_dist(bfx, cxl, cxl + kf), dyv = slab_dist(bfy, cyl, cyl + kf), dzv = slab_dist(bfz, czl, czl + kf);
-        const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);   // lower bound of the distance to this cell
-        if (lb * lb >= bound) continue;
-        scan_cell<kOrigIdx>(g, blx - L + dx, bly - L + dy, blz - L + dz, bqx, bqy, bqz, bfilter, loc);
-      }
-      // merge the lane-local lists into the owner's list: at most 5 winners can enter
-      for (int round = 0; round < 5; round++) {
-        const unsigned int dbits = __float_as_uint(loc.d[0]);   // distances are >= 0: the bit pattern orders like the value
-        const unsigned int mind = __reduce_min_sync(FULL, dbits);
-        if (mind == __float_as_uint(FLT_MAX)) break;
-        const unsigned int cand = (dbits == mind) ? (unsigned int)loc.idx[0] : 0xFFFFFFFFu;
-        const unsigned int mini = __reduce_min_sync(FULL, cand);
-        const int src = __ffs(__ballot_sync(FULL, dbits == mind && (unsigned int)loc.idx[0] == mini)) - 1;
-        const int wslot = __shfl_sync(FULL, loc.slot[0], src);
-        if (lane == h) top5_insert(best, __uint_as_float(mind), (int)mini, wslot);
-        if (lane == src) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) { loc.d[u] = loc.d[u + 1]; loc.idx[u] = loc.idx[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
-          loc.d[4] = FLT_MAX; loc.idx[4] = 0x7fffffff; loc.slot[4] = -1;
-        }
-      }
-      bd5 = __shfl_sync(FULL, best.d[4], h);
-    }
+    knn5_warp_finish<kOrigIdx>(g, h, c, qx, qy, qz, gate, best);
   }
 }
 

@@ -70,6 +70,13 @@ struct GridStorage {
 int grid_max_level(float cell, float gate);
 void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d_idx, float* d_d2, cudaStream_t stream);
 
+#define CM_MAX_EVALS 32          // upper bound of Gauss-Newton evaluations per call (max_iterations <= 32)
+#define CM_HARD_ITEM_BYTES 72
+// storage of the deferred-query list of one MatchLaunch
+struct HardQueue {
+  DeviceBuffer items, count;
+  void attach(struct MatchLaunch& m, size_t capacity);
+};
 struct MatchLaunch {
   int nstreams;
   const float4* corner; const float4* surf;   // [nstreams][cap]
@@ -86,6 +93,10 @@ struct MatchLaunch {
   int orig_idx;                               // grids carry original indices in pts[].w
   int max_queries = 0;                        // host-known upper bound of n_corner[s] + n_surf[s] (0: use the capacities)
   const float* own_box = nullptr;             // device {lo[3], hi[3]}: evaluate only queries inside (sharded map), else all
+  void* hard = nullptr;                       // optional device list of deferred "hard" queries (hard_cap * CM_HARD_ITEM_BYTES)
+  int* hard_count = nullptr;                  // device [CM_MAX_EVALS] counters, one per Gauss-Newton evaluation
+  int hard_cap = 0, hard_blocks = 0;
+  unsigned long long* dbg = nullptr; int dbg_iter = 0;   // per-warp trace of search_kernel in evaluation dbg_iter (development aid)
   MatchParamsDev prm;
 };
 // optional per-kernel timing of the dominant kernel (corr_kernel): event pairs recorded on the launching stream
@@ -103,6 +114,11 @@ struct KernelProfiler {
     used = 0; if (launches) *launches = n; return tot;
   }
 };
+inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
+  if (capacity < 1) capacity = 1;
+  items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS);
+  m.hard = items.p; m.hard_count = (int*)count.p; m.hard_cap = (int)capacity;
+}
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
 void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr);

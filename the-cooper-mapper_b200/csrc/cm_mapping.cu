@@ -187,6 +187,12 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
   m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p; m.nn_slot = (int*)ctx->m_slots.p;
   m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm; m.max_queries = max_q;
+  ctx->hardq.attach(m, (size_t)S * (max_q + 32));
+  if (ctx->dbg_on) {
+    ctx->dbg_words = (size_t)((max_q + 32 + 255) / 256) * S * 8 * 4;
+    ctx->dbg_trace.reserve(ctx->dbg_words * sizeof(unsigned long long));
+    m.dbg = (unsigned long long*)ctx->dbg_trace.p; m.dbg_iter = ctx->dbg_iter;
+  }
   launch_match(m, st, &ctx->prof);
   // featureMapUpdate
   ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
@@ -373,6 +379,18 @@ int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms) {
   cudaSetDevice(ctx->cfg.device);
   CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->timer[1]));
   CM_CUDA_CHECK(ctx, cudaEventElapsedTime(ms, ctx->timer[0], ctx->timer[1]));
+  return CM_OK;
+}
+/* development aid: per-warp trace of search_kernel (4 words per warp: t0 ns, t1 ns, max<<32|sum candidates, hard<<32|smid<<16|corner)
+ * of Gauss-Newton evaluation `iter` of the following cm_pipeline_step / cm_mapping_process calls; iter < 0 switches it off. */
+int cm_debug_search_trace_enable(cm_ctx* ctx, int iter) { if (!ctx) return CM_ERR_ARG; ctx->dbg_on = iter >= 0; ctx->dbg_iter = iter; return CM_OK; }
+int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_words, size_t* n_words) {
+  if (!ctx || !n_words) return CM_ERR_ARG;
+  *n_words = ctx->dbg_words;
+  if (out && ctx->dbg_words) {
+    cudaSetDevice(ctx->cfg.device);
+    CM_CUDA_CHECK(ctx, cudaMemcpy(out, ctx->dbg_trace.p, sizeof(unsigned long long) * (cap_words < ctx->dbg_words ? cap_words : ctx->dbg_words), cudaMemcpyDeviceToHost));
+  }
   return CM_OK;
 }
 int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = on != 0; return CM_OK; }

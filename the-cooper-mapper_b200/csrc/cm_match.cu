@@ -92,6 +92,8 @@ struct CorrArgs {
   int* nn_slot;                               // [nstreams][cap_corner + cap_surf][5] pool slots of the neighbours, -1: gated out
   int* nn;                                    // optional [nstreams][cap_corner + cap_surf][5], -1 where gated out
   const float* own_box;                       // optional {lo[3], hi[3]}: only queries whose map-frame position is inside are evaluated (sharded map)
+  unsigned long long* dbg;                    // optional per-warp trace of search_kernel (development aid, cm_debug_search_trace)
+  void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
   MatchParamsDev prm;
 };
 
@@ -187,41 +189,17 @@ __device__ __forceinline__ bool decode_query(int t, int nC, int nS, bool* isCorn
 }
 
 // K5a: transform + exact 5-NN.  Writes the pool slots of the 5 neighbours (or -1 when the 5.0 gate rejects the
-// query, ScanMatch.cpp:102,120).
+// query, ScanMatch.cpp:102,120).  Level 0 (the 2x2x2 cells around the query) runs one query per thread.  Queries whose
+// list is not provably final after level 0 ("hard": sparse surroundings, typically corner queries far from any map
+// edge) need the next shell of cells, which a whole warp scans cooperatively.  With a hard queue (a.hard != NULL) they
+// are appended to a device-wide list and finished by search_hard_kernel, one warp per query, spread over the whole
+// GPU -- otherwise a warp made of 32 hard queries would serialise 32 shell scans while the rest of the SMs idle (ncu:
+// 15 % warps active, issue slots 6 % busy over the kernel's duration before this split).
+struct HardItem { int s, t; float d[5]; int idx[5]; int slot[5]; int pad; };   // 72 bytes
+
 template <bool kOrigIdx>
-__global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
-  const int s = blockIdx.y;
-  const MatchState& st = a.state[s];
-  if (st.done) return;
-  __shared__ float sR[9], sT[3];
-  __shared__ uint2 rng[8 * 256];
-  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
-  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
-  __syncthreads();
-  const int nC = a.n_corner[s], nS = a.n_surf[s];
+__device__ __forceinline__ void search_store(const CorrArgs& a, int s, int row, bool gate, const Top5& best) {
   const int capQ = a.cap_corner + a.cap_surf;
-  const int nT = ((nC + 31) & ~31) + nS;
-  const float4* corner = a.corner + (size_t)s * a.cap_corner;
-  const float4* surf = a.surf + (size_t)s * a.cap_surf;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t & ~31) >= nT) return;   // whole warp idle
-  bool isCorner; int src, row;
-  const bool in_range = decode_query(t, nC, nS, &isCorner, &src, &row);
-  bool valid = in_range;
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  if (valid) {
-    const float4 p = isCorner ? corner[src] : surf[src];
-    transform_point(sR, sT, p.x, p.y, p.z, &sx, &sy, &sz);   // pointAssociateToMap
-    if (a.own_box) {
-      const float* b = a.own_box;
-      valid = sx >= b[0] && sx < b[3] && sy >= b[1] && sy < b[4] && sz >= b[2] && sz < b[5];
-    }
-  }
-  const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
-  Top5 best;
-  knn5_search<kOrigIdx>(g, valid, sx, sy, sz, a.prm.knn_gate, rng, best);
-  if (!in_range) return;
-  const bool gate = valid && best.d[4] < a.prm.knn_gate;
   int* out = a.nn_slot + ((size_t)s * capQ + row) * 5;
 #pragma unroll
   for (int k = 0; k < 5; k++) out[k] = gate ? best.slot[k] : -1;
@@ -229,6 +207,124 @@ __global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
     int* nn = a.nn + ((size_t)s * capQ + row) * 5;
 #pragma unroll
     for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx[k] : -1;
+  }
+}
+
+// the query of thread slot t of stream s in the map frame; false: idle slot / outside this rank's box
+__device__ __forceinline__ bool search_query(const CorrArgs& a, int s, int t, const float* sR, const float* sT, bool* in_range,
+                                             bool* isCorner, int* row, float* sx, float* sy, float* sz) {
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  int src;
+  *in_range = decode_query(t, nC, nS, isCorner, &src, row);
+  bool valid = *in_range;
+  *sx = *sy = *sz = 0.f;
+  if (valid) {
+    const float4 p = *isCorner ? a.corner[(size_t)s * a.cap_corner + src] : a.surf[(size_t)s * a.cap_surf + src];
+    transform_point(sR, sT, p.x, p.y, p.z, sx, sy, sz);   // pointAssociateToMap
+    if (a.own_box) {
+      const float* b = a.own_box;
+      valid = *sx >= b[0] && *sx < b[3] && *sy >= b[1] && *sy < b[4] && *sz >= b[2] && *sz < b[5];
+    }
+  }
+  return valid;
+}
+
+template <bool kOrigIdx>
+__global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
+  const int s = blockIdx.y;
+  const MatchState& st = a.state[s];
+  if (st.done) return;
+  __shared__ float sR[9], sT[3];
+  __shared__ uint4 rng[8 * 256];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
+  __syncthreads();
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int nT = ((nC + 31) & ~31) + nS;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t & ~31) >= nT) return;   // whole warp idle
+  unsigned long long t0 = 0;
+  if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  bool in_range, isCorner; int row;
+  float sx, sy, sz;
+  bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
+  const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+  Top5 best;
+  top5_init(best);
+  KnnGeom c;
+  valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c) && valid;
+  bool need = false;
+  unsigned int ncand = 0;
+  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr);
+  const unsigned int FULL = 0xffffffffu;
+  unsigned int hard = __ballot_sync(FULL, need);
+  if (a.dbg) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const unsigned int mx = __reduce_max_sync(FULL, ncand), sm = __reduce_add_sync(FULL, ncand);
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* d = a.dbg + 4 * ((size_t)(s * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
+      unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      d[0] = t0; d[1] = t1; d[2] = ((unsigned long long)mx << 32) | sm;
+      d[3] = ((unsigned long long)__popc(hard) << 32) | ((unsigned long long)smid << 16) | (isCorner ? 1u : 0u);
+    }
+  }
+  if (a.hard) {
+    // deferred: one warp-aggregated reservation, every hard lane writes its own item
+    if (hard) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(a.hard_count, __popc(hard));
+      base = __shfl_sync(FULL, base, 0);
+      if (need) {
+        const int pos = base + __popc(hard & ((1u << lane) - 1));
+        if (pos < a.hard_cap) {
+          HardItem it;
+          it.s = s; it.t = t; it.pad = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) { it.d[k] = best.d[k]; it.idx[k] = best.idx[k]; it.slot[k] = best.slot[k]; }
+          reinterpret_cast<HardItem*>(a.hard)[pos] = it;
+        }
+      }
+    }
+    if (!in_range || need) return;
+  } else {
+    while (hard) {
+      const int h = __ffs(hard) - 1;
+      hard &= hard - 1;
+      knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
+    }
+    if (!in_range) return;
+  }
+  search_store<kOrigIdx>(a, s, row, valid && best.d[4] < a.prm.knn_gate, best);
+}
+
+// K5a': the hard queries of one Gauss-Newton evaluation, one warp per query (grid-stride over the list).
+template <bool kOrigIdx>
+__global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
+  const int n = min(*a.hard_count, a.hard_cap);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const HardItem* item = reinterpret_cast<const HardItem*>(a.hard) + i;
+    const int s = item->s, t = item->t;
+    const MatchState& st = a.state[s];
+    float R[9], T[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = st.R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) T[k] = st.pose[3 + k];
+    bool in_range, isCorner; int row;
+    float sx, sy, sz;
+    search_query(a, s, t, R, T, &in_range, &isCorner, &row, &sx, &sy, &sz);
+    const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+    KnnGeom c;
+    knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c);
+    Top5 best;
+#pragma unroll
+    for (int k = 0; k < 5; k++) { best.d[k] = item->d[k]; best.idx[k] = item->idx[k]; best.slot[k] = item->slot[k]; }
+    knn5_warp_finish<kOrigIdx>(g, 0, c, sx, sy, sz, a.prm.knn_gate, best);
+    if (lane == 0) search_store<kOrigIdx>(a, s, row, best.d[4] < a.prm.knn_gate, best);
   }
 }
 
@@ -462,7 +558,7 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // ============================================================================================================
 __global__ void __launch_bounds__(128) knn5_kernel(GridView g, const float* __restrict__ q, int nq, float gate, int* __restrict__ idx,
                                                    float* __restrict__ d2) {
-  __shared__ uint2 rng[8 * 128];
+  __shared__ uint4 rng[8 * 128];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < nq;
   Top5 best;
@@ -518,11 +614,13 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
   ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
+  ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
 
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
+  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS, stream);
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
 }
 
@@ -536,8 +634,16 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   dim3 grid(bx, m.nstreams);
   ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
   if (prof) prof->begin(stream);
+  if (m.dbg && it == m.dbg_iter) { ca.dbg = m.dbg; cudaMemsetAsync(m.dbg, 0, (size_t)bx * m.nstreams * 8 * 4 * sizeof(unsigned long long), stream); }
+  if (it >= CM_MAX_EVALS) ca.hard = nullptr;       // no counter left: finish hard queries inside their own warp
+  if (ca.hard) ca.hard_count = m.hard_count + it;  // one counter per evaluation, zeroed by launch_match_init
   if (m.orig_idx) CM_LAUNCH(search_kernel<true>, grid, 256, 0, stream, ca);
   else CM_LAUNCH(search_kernel<false>, grid, 256, 0, stream, ca);
+  if (ca.hard) {
+    const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
+    if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
+    else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
+  }
   if (prof) prof->end(stream);
   CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
   sa.iter = it;

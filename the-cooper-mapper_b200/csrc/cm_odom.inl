@@ -32,7 +32,7 @@ __device__ __forceinline__ float odom_sqdiff(const float4& a, float bx, float by
 }
 
 __global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
-  __shared__ uint2 rng[8 * 128];
+  __shared__ uint4 rng[8 * 128];
   __shared__ PoseCoef kc;
   __shared__ float tf[6];
   const MatchState& st = *a.state;
