@@ -72,9 +72,9 @@ void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d
 
 #define CM_MAX_EVALS 32          // upper bound of Gauss-Newton evaluations per call (max_iterations <= 32)
 #define CM_HARD_ITEM_BYTES 72
-// storage of the deferred-query list of one MatchLaunch
+// scratch of one MatchLaunch: the deferred-query list and the per-CTA partial sums / tickets of the fused fit + solve
 struct HardQueue {
-  DeviceBuffer items, count;
+  DeviceBuffer items, count, partials, tickets;
   void attach(struct MatchLaunch& m, size_t capacity);
 };
 struct MatchLaunch {
@@ -96,6 +96,7 @@ struct MatchLaunch {
   void* hard = nullptr;                       // optional device list of deferred "hard" queries (hard_cap * CM_HARD_ITEM_BYTES)
   int* hard_count = nullptr;                  // device [CM_MAX_EVALS] counters, one per Gauss-Newton evaluation
   int hard_cap = 0, hard_blocks = 0;
+  double* partials = nullptr; int* tickets = nullptr; int partial_blocks = 0;   // fused fit + reduce + solve (launch_match only)
   unsigned long long* dbg = nullptr; int dbg_iter = 0;   // per-warp trace of search_kernel in evaluation dbg_iter (development aid)
   MatchParamsDev prm;
 };
@@ -118,10 +119,14 @@ inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   if (capacity < 1) capacity = 1;
   items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS);
   m.hard = items.p; m.hard_count = (int*)count.p; m.hard_cap = (int)capacity;
+  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
+  m.partial_blocks = (maxq + 32 + 255) / 256;
+  partials.reserve((size_t)m.nstreams * m.partial_blocks * 32 * sizeof(double)); tickets.reserve(sizeof(int) * m.nstreams);
+  m.partials = (double*)partials.p; m.tickets = (int*)tickets.p;
 }
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
-void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr);
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr, bool fused = false);
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);
 void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream);
 

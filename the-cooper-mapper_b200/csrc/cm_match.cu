@@ -329,21 +329,9 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
 }
 
 // K5b: line / plane fit on the 5 neighbours, residual and Jacobian row (ScanMatch.cpp:103-112, 121-130, 154-204).
-__global__ void __launch_bounds__(256) fit_kernel(CorrArgs a) {
-  const int s = blockIdx.y;
-  const MatchState& st = a.state[s];
-  if (st.done) return;
-  __shared__ PoseCoef kc;
-  __shared__ float sR[9], sT[3];
-  if (threadIdx.x == 0) make_pose_coef(st, kc);
-  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
-  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
-  __syncthreads();
-  const int nC = a.n_corner[s], nS = a.n_surf[s];
+__device__ __forceinline__ void fit_row(const CorrArgs& a, int s, const PoseCoef& kc, const float* sR, const float* sT, bool isCorner, int src,
+                                        int row, float4* o0, float4* o1) {
   const int capQ = a.cap_corner + a.cap_surf;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool isCorner; int src, row;
-  if (!decode_query(t, nC, nS, &isCorner, &src, &row)) return;
   const float4 p = isCorner ? a.corner[(size_t)s * a.cap_corner + src] : a.surf[(size_t)s * a.cap_surf + src];
   const int* slots = a.nn_slot + ((size_t)s * capQ + row) * 5;
   RowOut rowv;
@@ -374,9 +362,29 @@ __global__ void __launch_bounds__(256) fit_kernel(CorrArgs a) {
       rowv.b = -co[3];
     }
   }
+  *o0 = make_float4(rowv.a[0], rowv.a[1], rowv.a[2], rowv.a[3]);
+  *o1 = make_float4(rowv.a[4], rowv.a[5], rowv.b, __int_as_float(rowv.flag));
+}
+
+__global__ void __launch_bounds__(256) fit_kernel(CorrArgs a) {
+  const int s = blockIdx.y;
+  const MatchState& st = a.state[s];
+  if (st.done) return;
+  __shared__ PoseCoef kc;
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x == 0) make_pose_coef(st, kc);
+  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
+  __syncthreads();
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int capQ = a.cap_corner + a.cap_surf;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool isCorner; int src, row;
+  if (!decode_query(t, nC, nS, &isCorner, &src, &row)) return;
+  float4 r0, r1;
+  fit_row(a, s, kc, sR, sT, isCorner, src, row, &r0, &r1);
   float4* dst = reinterpret_cast<float4*>(a.rows + (size_t)s * capQ + row);
-  dst[0] = make_float4(rowv.a[0], rowv.a[1], rowv.a[2], rowv.a[3]);
-  dst[1] = make_float4(rowv.a[4], rowv.a[5], rowv.b, __int_as_float(rowv.flag));
+  dst[0] = r0; dst[1] = r1;
 }
 
 // ============================================================================================================
@@ -472,12 +480,9 @@ __device__ __noinline__ bool dev_inverse6(const float* A, float* inv) {
 
 // K6b: solve, degeneracy projection, pose update, convergence (ScanMatch.cpp:134-260).  One thread per stream; the
 // 6x6 work goes through cm_math.h, i.e. the same instruction sequence as the oracle's.
-__global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int nstreams) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nstreams) return;
+__device__ __noinline__ void solve_stream(const SolveArgs& a, int s, const double* tot) {
   MatchState& st = a.state[s];
   if (st.done) return;
-  const double* tot = sums + (size_t)s * 32;
   const int nrows = (int)tot[27];
   const int nline = (int)tot[28], nplane = (int)tot[29];
   st.rows = nrows; st.line = nline; st.plane = nplane; st.score = tot[30];
@@ -551,6 +556,92 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
   if (deltaR < a.prm.delta_r_abort && deltaT < a.prm.delta_t_abort) { st.flags |= CM_F_CONVERGED; st.done = 1; }
 }
 
+__global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int nstreams) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams) return;
+  solve_stream(a, s, sums + (size_t)s * 32);
+}
+
+// K5b + K6 in one launch: fit_kernel's rows are reduced inside the CTA (double, fixed order), the per-CTA partial sums
+// go to global memory, and the LAST CTA of a stream to finish (ticket counter) adds the partials in CTA order and runs the
+// 6x6 step -- streams solve concurrently on different SMs instead of one after the other in a single warp, and two
+// launches per Gauss-Newton iteration disappear.  Determinism: every sum has a fixed order (row -> 32-row group -> CTA).
+struct FusedArgs { double* partials; int* tickets; double* sums; };
+
+__global__ void __launch_bounds__(256) fit_solve_kernel(CorrArgs a, SolveArgs sa, FusedArgs f) {
+  const int s = blockIdx.y;
+  const MatchState& st = a.state[s];
+  if (st.done) return;
+  __shared__ PoseCoef kc;
+  __shared__ float sR[9], sT[3];
+  __shared__ float4 srow[2 * 256];
+  __shared__ double sacc[8][32];
+  __shared__ double stot[32];
+  __shared__ int s_last;
+  if (threadIdx.x == 0) make_pose_coef(st, kc);
+  if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
+  __syncthreads();
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int capQ = a.cap_corner + a.cap_surf;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool isCorner; int src, row;
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+  if (decode_query(t, nC, nS, &isCorner, &src, &row)) {
+    fit_row(a, s, kc, sR, sT, isCorner, src, row, &r0, &r1);
+    float4* dst = reinterpret_cast<float4*>(a.rows + (size_t)s * capQ + row);
+    dst[0] = r0; dst[1] = r1;
+    if (isCorner) r1.w = __int_as_float(__float_as_int(r1.w) | 4);
+  }
+  srow[2 * threadIdx.x] = r0; srow[2 * threadIdx.x + 1] = r1;
+  __syncthreads();
+  // accumulator k of row group grp: 0..20 upper triangle of A^T A, 21..26 A^T b, 27 rows, 28 / 29 counted corner / surf, 30 score
+  const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  {
+    int ra = 0, rb = 0;
+    if (k < 21) { int tt = k; while (tt >= 6 - ra) { tt -= 6 - ra; ra++; } rb = ra + tt; }
+    else if (k < 27) { ra = k - 21; rb = 6; }
+    double acc = 0.0;
+    const float* rows = reinterpret_cast<const float*>(srow);
+    for (int i = grp * 32; i < grp * 32 + 32; i++) {
+      const float* rv = rows + 8 * i;
+      const int flag = __float_as_int(rv[7]);
+      if (k < 27) { if (flag & 1) acc += (double)rv[ra] * (double)rv[rb]; }
+      else if (k == 27) { if (flag & 1) acc += 1.0; }
+      else if (k == 28) { if ((flag & 2) && (flag & 4)) acc += 1.0; }
+      else if (k == 29) { if ((flag & 2) && !(flag & 4)) acc += 1.0; }
+      else if (k == 30) { if (flag & 1) acc += exp(-fabs((double)rv[6])); }
+    }
+    sacc[grp][k] = acc;
+  }
+  __syncthreads();
+  double* mine = f.partials + ((size_t)s * gridDim.x + blockIdx.x) * 32;
+  if (threadIdx.x < 32) {
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) v += sacc[g][threadIdx.x];
+    __stcg(mine + threadIdx.x, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(f.tickets + s, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    const double* p = f.partials + (size_t)s * gridDim.x * 32 + threadIdx.x;
+    double v = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++) v += __ldcg(p + (size_t)b * 32);
+    stot[threadIdx.x] = v;
+    f.sums[(size_t)s * 32 + threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    f.tickets[s] = 0;
+    solve_stream(sa, s, stot);
+  }
+}
+
 #include "cm_odom.inl"
 
 // ============================================================================================================
@@ -621,11 +712,12 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
 
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
   if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS, stream);
+  if (m.tickets) cudaMemsetAsync(m.tickets, 0, sizeof(int) * m.nstreams, stream);
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
 }
 
 // one Gauss-Newton evaluation: correspondences + rows + (partial) normal-equation sums into m.sums
-void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof) {
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof, bool fused) {
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
   const int capQ = m.cap_corner + m.cap_surf;
@@ -645,8 +737,13 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
     else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
   }
   if (prof) prof->end(stream);
-  CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
   sa.iter = it;
+  if (fused) {
+    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums;
+    CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
+    return;
+  }
+  CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
   CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
 }
 
@@ -680,9 +777,10 @@ void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float*
 
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof) {
   launch_match_init(m, stream);
+  const bool fused = m.partials && m.tickets && (((m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf) + 32 + 255) / 256) <= m.partial_blocks;
   for (int it = 0; it < m.prm.max_iterations; it++) {
-    launch_match_partial(m, it, stream, prof);
-    launch_match_solve(m, it, (const double*)m.sums, stream);
+    launch_match_partial(m, it, stream, prof, fused);
+    if (!fused) launch_match_solve(m, it, (const double*)m.sums, stream);
   }
 }
 
