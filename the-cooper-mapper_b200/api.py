@@ -18,7 +18,8 @@ class CoopermapError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libcoopermap.so")
+    # COOPERMAP_LIB: development override (kernel variants built side by side); the product library is in-tree
+    return os.environ.get("COOPERMAP_LIB") or os.path.join(_HERE, "libcoopermap.so")
 
 
 class Config(C.Structure):
@@ -185,6 +186,10 @@ class Context:
         """Same with the frames already resident in device memory (raw pointer); pre-packed host arrays, no allocation."""
         return self._check(self.L.cm_pipeline_step_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols),
                                                        _ptr(odoms_packed), _ptr(mapped_out), stats_out))
+
+    def pipeline_prefetch(self, frames):
+        """Start the host-to-device upload of the NEXT step's sweeps (pinned (S, rows, cols, 4) float32 array)."""
+        return self._check(self.L.cm_pipeline_prefetch_host(self.h, _ptr(frames), C.c_int(frames.shape[1]), C.c_int(frames.shape[2])))
 
     def pipeline_step_packed(self, frames, odoms_packed, mapped_out, stats_out):
         fr = frames

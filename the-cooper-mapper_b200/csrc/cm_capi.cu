@@ -65,6 +65,8 @@ int cm_ctx_create(const cm_config* cfg, cm_ctx** out) {
 void cm_ctx_destroy(cm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int i = 0; i < 2; i++) if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   delete ctx;
 }

@@ -54,6 +54,10 @@ struct cm_ctx {
   unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;
   // pipeline (scan registration -> mapping), cm_mapping.cu
   cm::DeviceBuffer p_frames, p_pts[4], p_n;
+  // double-buffered sweep upload (cm_pipeline_prefetch_host): the NEXT step's sweeps travel on copy_stream while the
+  // current step computes
+  cm::DeviceBuffer p_prefetch[2]; const void* prefetch_src[2] = {nullptr, nullptr}; size_t prefetch_bytes[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done[2] = {nullptr, nullptr};
   int p_cap = 0;
 };
 

@@ -73,29 +73,36 @@ __device__ __forceinline__ bool grid_probe(const GridView& g, int x, int y, int 
   }
 }
 
-// Sorted 5-best list by (d2, idx).  slot = position in the point pool (to fetch the coordinates afterwards).
+// Sorted 5-best list by (d2, idx), held as packed 64-bit keys: (bits of d2) << 32 | idx.  d2 >= 0, so the bit pattern of
+// the float orders like its value and ONE unsigned 64-bit comparison is the lexicographic (d2, idx) comparison.
+// slot = position in the point pool (to fetch the coordinates afterwards); for map grids idx == slot and the slot
+// array is dead code.
 struct Top5 {
-  float d[5];
-  int idx[5];
+  unsigned long long key[5];
   int slot[5];
+  __device__ __forceinline__ float d(int k) const { return __uint_as_float((unsigned int)(key[k] >> 32)); }
+  __device__ __forceinline__ int idx(int k) const { return (int)(unsigned int)(key[k] & 0xFFFFFFFFull); }
 };
+#define CM_TOP5_EMPTY ((((unsigned long long)0x7f7fffffu) << 32) | 0x7fffffffull)   // (FLT_MAX, INT_MAX)
+__device__ __forceinline__ unsigned long long top5_key(float d, int idx) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)idx; }
 __device__ __forceinline__ void top5_init(Top5& t) {
 #pragma unroll
-  for (int k = 0; k < 5; k++) { t.d[k] = FLT_MAX; t.idx[k] = 0x7fffffff; t.slot[k] = -1; }
+  for (int k = 0; k < 5; k++) { t.key[k] = CM_TOP5_EMPTY; t.slot[k] = -1; }
 }
-__device__ __forceinline__ bool lex_less(float d, int i, float d2, int i2) { return d < d2 || (d == d2 && i < i2); }
-__device__ __forceinline__ void top5_insert(Top5& t, float d, int idx, int slot) {
-  if (!lex_less(d, idx, t.d[4], t.idx[4])) return;
-  bool c0 = lex_less(d, idx, t.d[0], t.idx[0]);
-  bool c1 = lex_less(d, idx, t.d[1], t.idx[1]);
-  bool c2 = lex_less(d, idx, t.d[2], t.idx[2]);
-  bool c3 = lex_less(d, idx, t.d[3], t.idx[3]);
+__device__ __forceinline__ void top5_insert_key(Top5& t, unsigned long long key, int slot) {
+  if (!(key < t.key[4])) return;
+  const bool c0 = key < t.key[0], c1 = key < t.key[1], c2 = key < t.key[2], c3 = key < t.key[3];
   // new slot k = c_{k-1} ? old[k-1] : (c_k ? new : old[k])
-  t.d[4] = c3 ? t.d[3] : d;            t.idx[4] = c3 ? t.idx[3] : idx;            t.slot[4] = c3 ? t.slot[3] : slot;
-  t.d[3] = c2 ? t.d[2] : (c3 ? d : t.d[3]); t.idx[3] = c2 ? t.idx[2] : (c3 ? idx : t.idx[3]); t.slot[3] = c2 ? t.slot[2] : (c3 ? slot : t.slot[3]);
-  t.d[2] = c1 ? t.d[1] : (c2 ? d : t.d[2]); t.idx[2] = c1 ? t.idx[1] : (c2 ? idx : t.idx[2]); t.slot[2] = c1 ? t.slot[1] : (c2 ? slot : t.slot[2]);
-  t.d[1] = c0 ? t.d[0] : (c1 ? d : t.d[1]); t.idx[1] = c0 ? t.idx[0] : (c1 ? idx : t.idx[1]); t.slot[1] = c0 ? t.slot[0] : (c1 ? slot : t.slot[1]);
-  t.d[0] = c0 ? d : t.d[0];            t.idx[0] = c0 ? idx : t.idx[0];            t.slot[0] = c0 ? slot : t.slot[0];
+  t.key[4] = c3 ? t.key[3] : key;                    t.slot[4] = c3 ? t.slot[3] : slot;
+  t.key[3] = c2 ? t.key[2] : (c3 ? key : t.key[3]);  t.slot[3] = c2 ? t.slot[2] : (c3 ? slot : t.slot[3]);
+  t.key[2] = c1 ? t.key[1] : (c2 ? key : t.key[2]);  t.slot[2] = c1 ? t.slot[1] : (c2 ? slot : t.slot[2]);
+  t.key[1] = c0 ? t.key[0] : (c1 ? key : t.key[1]);  t.slot[1] = c0 ? t.slot[0] : (c1 ? slot : t.slot[1]);
+  t.key[0] = c0 ? key : t.key[0];                    t.slot[0] = c0 ? slot : t.slot[0];
+}
+// d must not be NaN (a NaN never enters the reference's result set either: nanoflann compares dist < worst)
+__device__ __forceinline__ void top5_insert(Top5& t, float d, int idx, int slot) {
+  if (d != d) return;
+  top5_insert_key(t, top5_key(d, idx), slot);
 }
 
 // worldToCube (FeatureMap.h:475-487) -> index into the 7x7x7 window, -1 outside it
@@ -258,7 +265,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
   int ci = 0; unsigned int j0 = 0;
   uint4 r = nr ? my[0] : make_uint4(0u, 0u, 0u, 0u);
   while (ci < nr) {
-    if (j0 == 0 && __uint_as_float(r.z) > best.d[4]) {   // the whole cell is farther than the current 5th neighbour
+    if (j0 == 0 && __uint_as_float(r.z) > best.d(4)) {   // the whole cell is farther than the current 5th neighbour
       ci++; if (ci < nr) r = my[ci * stride];
       continue;
     }
@@ -287,7 +294,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
   if (ncand) *ncand = scanned;
   if (g.max_level < 1) return false;
   const float r0 = leaf98 * c.m0;
-  return !(best.d[4] < r0 * r0);
+  return !(best.d(4) < r0 * r0);
 }
 
 // Levels >= 1 of ONE query, executed by a whole warp.  The query (position, geometry, current list) lives in lane h;
@@ -304,7 +311,7 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
   const int blx = __shfl_sync(FULL, c.lx, h), bly = __shfl_sync(FULL, c.ly, h), blz = __shfl_sync(FULL, c.lz, h);
   const float bm0 = __shfl_sync(FULL, c.m0, h);
   const bool bfilter = __shfl_sync(FULL, c.filter ? 1 : 0, h) != 0;
-  float bd5 = __shfl_sync(FULL, best.d[4], h);
+  float bd5 = __shfl_sync(FULL, best.d(4), h);
   const float kf = (float)k;
   for (int L = 1; L <= g.max_level; L++) {
     const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
@@ -324,21 +331,21 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
     }
     // merge the lane-local lists into the owner's list: at most 5 winners can enter
     for (int round = 0; round < 5; round++) {
-      const unsigned int dbits = __float_as_uint(loc.d[0]);   // distances are >= 0: the bit pattern orders like the value
+      const unsigned int dbits = (unsigned int)(loc.key[0] >> 32), ibits = (unsigned int)(loc.key[0] & 0xFFFFFFFFull);
       const unsigned int mind = __reduce_min_sync(FULL, dbits);
       if (mind == __float_as_uint(FLT_MAX)) break;
-      const unsigned int cand = (dbits == mind) ? (unsigned int)loc.idx[0] : 0xFFFFFFFFu;
+      const unsigned int cand = (dbits == mind) ? ibits : 0xFFFFFFFFu;
       const unsigned int mini = __reduce_min_sync(FULL, cand);
-      const int src = __ffs(__ballot_sync(FULL, dbits == mind && (unsigned int)loc.idx[0] == mini)) - 1;
+      const int src = __ffs(__ballot_sync(FULL, dbits == mind && ibits == mini)) - 1;
       const int wslot = __shfl_sync(FULL, loc.slot[0], src);
-      if (lane == h) top5_insert(best, __uint_as_float(mind), (int)mini, wslot);
+      if (lane == h) top5_insert_key(best, ((unsigned long long)mind << 32) | mini, wslot);
       if (lane == src) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) { loc.d[u] = loc.d[u + 1]; loc.idx[u] = loc.idx[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
-        loc.d[4] = FLT_MAX; loc.idx[4] = 0x7fffffff; loc.slot[4] = -1;
+        for (int u = 0; u < 4; u++) { loc.key[u] = loc.key[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
+        loc.key[4] = CM_TOP5_EMPTY; loc.slot[4] = -1;
       }
     }
-    bd5 = __shfl_sync(FULL, best.d[4], h);
+    bd5 = __shfl_sync(FULL, best.d(4), h);
   }
 }
 

@@ -282,6 +282,30 @@ static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols,
                              max_s, odom, mapped, stats);
 }
 
+int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!frames || rows <= 0 || cols <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
+    if (!ctx->copy_stream) {
+      CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+    }
+    int slot = -1;
+    for (int i = 0; i < 2; i++) if (!ctx->prefetch_src[i]) { slot = i; break; }
+    if (slot < 0) return fail(ctx, CM_ERR_ARG, "two uploads are already pending: run cm_pipeline_step_host on one of them first");
+    // a free slot was the input of a step that has returned (the pipeline entries synchronise): nothing reads it any more
+    ctx->p_prefetch[slot].reserve(bytes);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->p_prefetch[slot].p, frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->copy_done[slot], ctx->copy_stream));
+    ctx->prefetch_src[slot] = frames; ctx->prefetch_bytes[slot] = bytes;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                           cm_match_stats* stats) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
@@ -290,6 +314,15 @@ int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int col
   try {
     cudaSetDevice(ctx->cfg.device);
     const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
+    int slot = -1;
+    for (int i = 0; i < 2; i++) if (ctx->prefetch_src[i] == (const void*)frames && ctx->prefetch_bytes[i] == bytes) slot = i;
+    if (slot >= 0) {
+      // uploaded by cm_pipeline_prefetch_host: wait for that copy on the device, no second transfer
+      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[slot], 0));
+      const int rc = pipeline_dev(ctx, (const float4*)ctx->p_prefetch[slot].p, rows, cols, odom, mapped, stats);
+      ctx->prefetch_src[slot] = nullptr; ctx->prefetch_bytes[slot] = 0;
+      return rc;
+    }
     ctx->p_frames.reserve(bytes);
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->p_frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return pipeline_dev(ctx, (const float4*)ctx->p_frames.p, rows, cols, odom, mapped, stats);

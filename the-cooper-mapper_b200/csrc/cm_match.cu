@@ -202,11 +202,11 @@ __device__ __forceinline__ void search_store(const CorrArgs& a, int s, int row, 
   const int capQ = a.cap_corner + a.cap_surf;
   int* out = a.nn_slot + ((size_t)s * capQ + row) * 5;
 #pragma unroll
-  for (int k = 0; k < 5; k++) out[k] = gate ? best.slot[k] : -1;
+  for (int k = 0; k < 5; k++) out[k] = gate ? (kOrigIdx ? best.slot[k] : best.idx(k)) : -1;   // map grids: idx == slot
   if (a.nn) {
     int* nn = a.nn + ((size_t)s * capQ + row) * 5;
 #pragma unroll
-    for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx[k] : -1;
+    for (int k = 0; k < 5; k++) nn[k] = gate ? best.idx(k) : -1;
   }
 }
 
@@ -229,13 +229,19 @@ __device__ __forceinline__ bool search_query(const CorrArgs& a, int s, int t, co
   return valid;
 }
 
+#ifndef CM_SEARCH_THREADS
+#define CM_SEARCH_THREADS 128
+#endif
+#ifndef CM_SEARCH_MINB
+#define CM_SEARCH_MINB 6
+#endif
 template <bool kOrigIdx>
-__global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
+__global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kernel(CorrArgs a) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
   if (st.done) return;
   __shared__ float sR[9], sT[3];
-  __shared__ uint4 rng[8 * 256];
+  __shared__ uint4 rng[8 * CM_SEARCH_THREADS];
   if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
   if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
   __syncthreads();
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
           HardItem it;
           it.s = s; it.t = t; it.pad = 0;
 #pragma unroll
-          for (int k = 0; k < 5; k++) { it.d[k] = best.d[k]; it.idx[k] = best.idx[k]; it.slot[k] = best.slot[k]; }
+          for (int k = 0; k < 5; k++) { it.d[k] = best.d(k); it.idx[k] = best.idx(k); it.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
           reinterpret_cast<HardItem*>(a.hard)[pos] = it;
         }
       }
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(256, 3) search_kernel(CorrArgs a) {
     }
     if (!in_range) return;
   }
-  search_store<kOrigIdx>(a, s, row, valid && best.d[4] < a.prm.knn_gate, best);
+  search_store<kOrigIdx>(a, s, row, valid && best.d(4) < a.prm.knn_gate, best);
 }
 
 // K5a': the hard queries of one Gauss-Newton evaluation, one warp per query (grid-stride over the list).
@@ -322,9 +328,9 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
     knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c);
     Top5 best;
 #pragma unroll
-    for (int k = 0; k < 5; k++) { best.d[k] = item->d[k]; best.idx[k] = item->idx[k]; best.slot[k] = item->slot[k]; }
+    for (int k = 0; k < 5; k++) { best.key[k] = top5_key(item->d[k], item->idx[k]); best.slot[k] = item->slot[k]; }
     knn5_warp_finish<kOrigIdx>(g, 0, c, sx, sy, sz, a.prm.knn_gate, best);
-    if (lane == 0) search_store<kOrigIdx>(a, s, row, best.d[4] < a.prm.knn_gate, best);
+    if (lane == 0) search_store<kOrigIdx>(a, s, row, best.d(4) < a.prm.knn_gate, best);
   }
 }
 
@@ -576,6 +582,7 @@ __global__ void __launch_bounds__(256) fit_solve_kernel(CorrArgs a, SolveArgs sa
   __shared__ float sR[9], sT[3];
   __shared__ float4 srow[2 * 256];
   __shared__ double sacc[8][32];
+  __shared__ double sexp[256];
   __shared__ double stot[32];
   __shared__ int s_last;
   if (threadIdx.x == 0) make_pose_coef(st, kc);
@@ -593,6 +600,8 @@ __global__ void __launch_bounds__(256) fit_solve_kernel(CorrArgs a, SolveArgs sa
     dst[0] = r0; dst[1] = r1;
     if (isCorner) r1.w = __int_as_float(__float_as_int(r1.w) | 4);
   }
+  // score term of the row (ScanMatch.cpp:277-286), evaluated by the row's own thread
+  sexp[threadIdx.x] = (__float_as_int(r1.w) & 1) ? exp(-fabs((double)r1.z)) : 0.0;
   srow[2 * threadIdx.x] = r0; srow[2 * threadIdx.x + 1] = r1;
   __syncthreads();
   // accumulator k of row group grp: 0..20 upper triangle of A^T A, 21..26 A^T b, 27 rows, 28 / 29 counted corner / surf, 30 score
@@ -610,7 +619,7 @@ __global__ void __launch_bounds__(256) fit_solve_kernel(CorrArgs a, SolveArgs sa
       else if (k == 27) { if (flag & 1) acc += 1.0; }
       else if (k == 28) { if ((flag & 2) && (flag & 4)) acc += 1.0; }
       else if (k == 29) { if ((flag & 2) && !(flag & 4)) acc += 1.0; }
-      else if (k == 30) { if (flag & 1) acc += exp(-fabs((double)rv[6])); }
+      else if (k == 30) { if (flag & 1) acc += sexp[i]; }
     }
     sacc[grp][k] = acc;
   }
@@ -657,8 +666,8 @@ __global__ void __launch_bounds__(128) knn5_kernel(GridView g, const float* __re
   if (!valid) return;
 #pragma unroll
   for (int k = 0; k < 5; k++) {
-    idx[5 * i + k] = best.slot[k] < 0 ? -1 : best.idx[k];
-    d2[5 * i + k] = best.d[k];
+    idx[5 * i + k] = best.slot[k] < 0 ? -1 : best.idx(k);
+    d2[5 * i + k] = best.d(k);
   }
 }
 
@@ -726,11 +735,12 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   dim3 grid(bx, m.nstreams);
   ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
   if (prof) prof->begin(stream);
-  if (m.dbg && it == m.dbg_iter) { ca.dbg = m.dbg; cudaMemsetAsync(m.dbg, 0, (size_t)bx * m.nstreams * 8 * 4 * sizeof(unsigned long long), stream); }
+  if (m.dbg && it == m.dbg_iter) { ca.dbg = m.dbg; cudaMemsetAsync(m.dbg, 0, (size_t)bx * m.nstreams * 8 * 4 * sizeof(unsigned long long), stream);   /* bx * 8 warps per stream */ }
   if (it >= CM_MAX_EVALS) ca.hard = nullptr;       // no counter left: finish hard queries inside their own warp
   if (ca.hard) ca.hard_count = m.hard_count + it;  // one counter per evaluation, zeroed by launch_match_init
-  if (m.orig_idx) CM_LAUNCH(search_kernel<true>, grid, 256, 0, stream, ca);
-  else CM_LAUNCH(search_kernel<false>, grid, 256, 0, stream, ca);
+  dim3 sgrid((bx * 256 + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, m.nstreams);
+  if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
+  else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   if (ca.hard) {
     const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
     if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);

@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
     knn5_search<true>(isCorner ? a.grid_corner : a.grid_surf, valid, sx, sy, sz, 25.0f, rng, best);
     if (valid) {
       int closest = -1, min2 = -1, min3 = -1;
-      if (best.d[0] < 25.f && best.slot[0] >= 0) {
-        closest = best.idx[0];
+      if (best.d(0) < 25.f && best.slot[0] >= 0) {
+        closest = best.idx(0);
         if (isCorner) {   // :363-398
           const float4* lc = a.last_corner;
           const int scan = (int)lc[closest].w;
