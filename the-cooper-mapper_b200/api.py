@@ -33,7 +33,7 @@ class Config(C.Structure):
                 ("filter_corner", C.c_float), ("filter_surf", C.c_float), ("map_filter_corner", C.c_float),
                 ("map_filter_surf", C.c_float), ("cube_w", C.c_int), ("cube_h", C.c_int), ("cube_d", C.c_int),
                 ("cube_size", C.c_float), ("valid_distance", C.c_float), ("cell_corner", C.c_float),
-                ("cell_surf", C.c_float)]
+                ("cell_surf", C.c_float), ("gn_groups", C.c_int)]
 
 
 class MatchStats(C.Structure):

@@ -43,6 +43,7 @@ void cm_config_default(cm_config* c) {
   c->filter_corner = 1.0f; c->filter_surf = 1.0f; c->map_filter_corner = 1.0f; c->map_filter_surf = 1.0f;
   c->cube_w = 121; c->cube_h = 121; c->cube_d = 11; c->cube_size = 50.f; c->valid_distance = 150.f;
   c->cell_corner = 0.f; c->cell_surf = 0.f;
+  c->gn_groups = 0;
 }
 
 int cm_ctx_create(const cm_config* cfg, cm_ctx** out) {
@@ -66,6 +67,11 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int g = 0; g < CM_MAX_GN_GROUPS; g++) {
+    if (ctx->gn_stream[g]) { cudaStreamSynchronize(ctx->gn_stream[g]); cudaStreamDestroy(ctx->gn_stream[g]); }
+    if (ctx->gn_join[g]) cudaEventDestroy(ctx->gn_join[g]);
+  }
+  if (ctx->gn_fork) cudaEventDestroy(ctx->gn_fork);
   for (int i = 0; i < 2; i++) if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   delete ctx;

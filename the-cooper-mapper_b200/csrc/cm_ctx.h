@@ -37,6 +37,9 @@ struct cm_ctx {
   cm::DeviceBuffer m_corner_in, m_surf_in, m_n_in, m_corner_ds, m_surf_ds, m_n_ds, m_pose, m_state, m_rows, m_slots, m_sums, m_tf, m_exp_pts, m_exp_cube, m_exp_n;
   int m_cap_corner = 0, m_cap_surf = 0;
   cm::DeviceBuffer dbg_trace; bool dbg_on = false; int dbg_iter = 0; size_t dbg_words = 0;   // cm_debug_search_trace
+  // Gauss-Newton stream groups of the batched mapping stage (cm_mapping.cu)
+#define CM_MAX_GN_GROUPS 8
+  cudaStream_t gn_stream[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_join[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_fork = nullptr;
   cm::HardQueue hardq;                              // deferred hard 5-NN queries of the current match (cm_match.cu)
   // scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members
   bool odom_inited = false;

@@ -117,7 +117,7 @@ struct KernelProfiler {
 };
 inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   if (capacity < 1) capacity = 1;
-  items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS);
+  items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS * 8);   // x8: one counter row per stream group
   m.hard = items.p; m.hard_count = (int*)count.p; m.hard_cap = (int)capacity;
   const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
   m.partial_blocks = (maxq + 32 + 255) / 256;
@@ -125,6 +125,9 @@ inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   m.partials = (double*)partials.p; m.tickets = (int*)tickets.p;
 }
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
+// the same with the streams split into `ngroups` groups whose iteration loops run concurrently on gs[0..ngroups)
+void launch_match_groups(const MatchLaunch& m, cudaStream_t stream, int ngroups, cudaStream_t* gs, cudaEvent_t fork, cudaEvent_t* join,
+                         KernelProfiler* prof = nullptr);
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
 void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr, bool fused = false);
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);

@@ -9,6 +9,7 @@
 #include "cm_math.h"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace cm {
@@ -193,7 +194,22 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     ctx->dbg_trace.reserve(ctx->dbg_words * sizeof(unsigned long long));
     m.dbg = (unsigned long long*)ctx->dbg_trace.p; m.dbg_iter = ctx->dbg_iter;
   }
-  launch_match(m, st, &ctx->prof);
+  {
+    int G = cfg.gn_groups > 0 ? cfg.gn_groups : 1;
+    if (const char* e = getenv("COOPERMAP_GN_GROUPS")) G = atoi(e);   // development override
+    if (G > CM_MAX_GN_GROUPS) G = CM_MAX_GN_GROUPS;
+    if (G > S) G = S;
+    if (G > 1) {
+      if (!ctx->gn_fork) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->gn_fork, cudaEventDisableTiming));
+      for (int g = 0; g < G; g++) {
+        if (!ctx->gn_stream[g]) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->gn_stream[g], cudaStreamNonBlocking));
+        if (!ctx->gn_join[g]) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->gn_join[g], cudaEventDisableTiming));
+      }
+      launch_match_groups(m, st, G, ctx->gn_stream, ctx->gn_fork, ctx->gn_join, &ctx->prof);
+    } else {
+      launch_match(m, st, &ctx->prof);
+    }
+  }
   // featureMapUpdate
   ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
   ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);

@@ -7,6 +7,7 @@
 #include "cm_match.cuh"
 #include "cm_math.h"
 #include "cm_host.h"
+#include <vector>
 
 namespace cm {
 
@@ -720,7 +721,7 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
 }
 
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
-  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS, stream);
+  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS * 8, stream);
   if (m.tickets) cudaMemsetAsync(m.tickets, 0, sizeof(int) * m.nstreams, stream);
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
 }
@@ -792,6 +793,53 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
     launch_match_partial(m, it, stream, prof, fused);
     if (!fused) launch_match_solve(m, it, (const double*)m.sums, stream);
   }
+}
+
+// Streams [s0, s1) of m as a launch of its own (every per-stream array is indexed by blockIdx.y).
+static MatchLaunch match_slice(const MatchLaunch& m, int g, int s0, int s1) {
+  MatchLaunch r = m;
+  const int capQ = m.cap_corner + m.cap_surf;
+  r.nstreams = s1 - s0;
+  r.corner = m.corner + (size_t)s0 * m.cap_corner; r.surf = m.surf + (size_t)s0 * m.cap_surf;
+  r.n_corner = m.n_corner + s0; r.n_surf = m.n_surf + s0;
+  r.grid_corner = m.grid_corner + s0; r.grid_surf = m.grid_surf + s0;
+  r.pose_in = m.pose_in + 6 * (size_t)s0; r.state = m.state + s0; r.rows = m.rows + (size_t)s0 * capQ;
+  r.nn_slot = m.nn_slot ? m.nn_slot + (size_t)s0 * capQ * 5 : nullptr;
+  r.sums = m.sums + (size_t)s0 * 32;
+  r.trace = m.trace ? m.trace + (size_t)s0 * m.prm.max_iterations : nullptr;
+  r.nn = nullptr;
+  if (m.hard) {
+    const size_t per_stream = (size_t)m.hard_cap / (size_t)m.nstreams;
+    r.hard = (char*)m.hard + (size_t)s0 * per_stream * CM_HARD_ITEM_BYTES;
+    r.hard_cap = (int)(per_stream * (size_t)(s1 - s0));
+    r.hard_count = m.hard_count + g * CM_MAX_EVALS;
+  }
+  if (m.partials) { r.partials = m.partials + (size_t)s0 * m.partial_blocks * 32; r.tickets = m.tickets + s0; }
+  if (g != 0) r.dbg = nullptr;
+  return r;
+}
+
+void launch_match_groups(const MatchLaunch& m, cudaStream_t stream, int ngroups, cudaStream_t* gs, cudaEvent_t fork, cudaEvent_t* join,
+                         KernelProfiler* prof) {
+  if (ngroups <= 1 || m.nstreams < 2 || m.nn) { launch_match(m, stream, prof); return; }
+  if (ngroups > m.nstreams) ngroups = m.nstreams;
+  if (ngroups > 8) ngroups = 8;
+  launch_match_init(m, stream);
+  cudaEventRecord(fork, stream);
+  const bool fused = m.partials && m.tickets && (((m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf) + 32 + 255) / 256) <= m.partial_blocks;
+  std::vector<MatchLaunch> part;
+  for (int g = 0; g < ngroups; g++) {
+    const int s0 = (int)((long long)m.nstreams * g / ngroups), s1 = (int)((long long)m.nstreams * (g + 1) / ngroups);
+    part.push_back(match_slice(m, g, s0, s1));
+    cudaStreamWaitEvent(gs[g], fork, 0);
+  }
+  // issue iteration by iteration, round-robin over the groups, so that the host feeds all group streams evenly
+  for (int it = 0; it < m.prm.max_iterations; it++)
+    for (int g = 0; g < ngroups; g++) {
+      launch_match_partial(part[g], it, gs[g], prof, fused);
+      if (!fused) launch_match_solve(part[g], it, (const double*)part[g].sums, gs[g]);
+    }
+  for (int g = 0; g < ngroups; g++) { cudaEventRecord(join[g], gs[g]); cudaStreamWaitEvent(stream, join[g], 0); }
 }
 
 }  // namespace cm
