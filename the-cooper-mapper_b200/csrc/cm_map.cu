@@ -19,7 +19,6 @@
 // ~3 km / +-125 m vertically) is not implemented: cm_map_update reports CM_ERR_UNSUPPORTED.
 #include "cm_host.h"
 #include "cm_math.h"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace cm {
 
@@ -28,12 +27,23 @@ namespace cm {
 
 __device__ __forceinline__ int world_to_cube_axis(float x, float cube_size, int origin) { return (int)(roundf(x / cube_size) + (float)origin); }
 
-// ---- 1. transform + key ------------------------------------------------------------------------------------------
-// key = stream (8 bits) | cube parity (3 bits) | voxel z, y, x (17 bits each, biased)
+// ---- 1. transform + key + grouping -----------------------------------------------------------------------------------
+// key = stream (8 bits) | cube parity (3 bits) | voxel z, y, x (17 bits each, biased).  Points with equal keys form one
+// merge group.  Groups are found WITHOUT sorting: every point inserts its key into a scratch hash table whose entry keeps
+// the smallest point index of the group (its head) and a linked list of the members; the head's thread later walks the
+// list in ascending index order, which reproduces the input-order sum of a stable sort.  (A frame inserts ~1 point per
+// map voxel, so the lists are almost always of length 1; the 62-bit radix sort this replaces cost 8 passes per class.)
+struct GroupEntry { unsigned long long key; int head; int tail; };
+
+__global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { tab[i].key = CM_MAP_PAD; tab[i].head = 0x7fffffff; tab[i].tail = -1; }
+}
+
 __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int max_n, int nstreams,
                                const MatchState* __restrict__ state, const float* __restrict__ tf_override, MapClassDev* maps,
-                               float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
-                               int* __restrict__ flags) {
+                               float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ slot_of,
+                               int* __restrict__ next, GroupEntry* __restrict__ gtab, unsigned int gmask, int* __restrict__ flags) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (size_t)nstreams * max_n) return;
   int s = (int)(g / max_n), i = (int)(g - (size_t)s * max_n);
@@ -67,7 +77,17 @@ __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __rest
     }
   }
   keys[g] = key;
-  vals[g] = (unsigned int)g;
+  if (key != CM_MAP_PAD) {
+    unsigned int h = hash_cell(key) & gmask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&gtab[h].key, CM_MAP_PAD, key);
+      if (prev == CM_MAP_PAD || prev == key) break;
+      h = (h + 1) & gmask;
+    }
+    atomicMin(&gtab[h].head, (int)g);
+    next[g] = atomicExch(&gtab[h].tail, (int)g);
+    slot_of[g] = h;
+  }
 }
 
 // ---- 2. one thread per (stream, cube, voxel) group: merge with the resident point or queue an append ---------------
@@ -83,17 +103,19 @@ __device__ __forceinline__ unsigned int map_find_or_create_cell(MapClassDev& m, 
   }
 }
 
-__global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals, size_t n,
+__global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ slot_of,
+                                 const int* __restrict__ next, const GroupEntry* __restrict__ gtab, size_t n,
                                  const float4* __restrict__ world, MapClassDev* maps, PendingAdd* __restrict__ pending,
                                  unsigned int* __restrict__ n_pending, unsigned int pending_cap, int* __restrict__ flags) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   const unsigned long long key = keys[g];
   if (key == CM_MAP_PAD) return;
-  if (g > 0 && keys[g - 1] == key) return;   // not the head of its group
+  const GroupEntry ge = gtab[slot_of[g]];
+  if (ge.head != (int)g) return;   // not the head (smallest index) of its group
   const int s = (int)(key >> 54);
   MapClassDev& m = maps[s];
-  const float4 first = world[vals[g]];
+  const float4 first = world[g];
   const int vx = (int)floorf(first.x * m.inv_leaf), vy = (int)floorf(first.y * m.inv_leaf), vz = (int)floorf(first.z * m.inv_leaf);
   const int ci = world_to_cube_axis(first.x, m.cube_size, m.origin[0]), cj = world_to_cube_axis(first.y, m.cube_size, m.origin[1]),
             ck = world_to_cube_axis(first.z, m.cube_size, m.origin[2]);
@@ -112,9 +134,14 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
       else atomicExch(flags + 1, 1);   // two resident points in one voxel (rounding drift): not merged here, only reported
     }
   }
-  for (size_t j = g; j < n && keys[j] == key; j++) {
-    float4 q = world[vals[j]];
+  // members in ascending index order (= the order of the pushed cloud): repeated minimum over the (short) list
+  for (int last = -1;;) {
+    int best = 0x7fffffff;
+    for (int j = ge.tail; j >= 0; j = next[j]) if (j > last && j < best) best = j;
+    if (best == 0x7fffffff) break;
+    const float4 q = world[best];
     sx += q.x; sy += q.y; sz += q.z; si += q.w; cnt++;
+    last = best;
   }
   const float c = (float)cnt;
   const float4 cen = make_float4(sx / c, sy / c, sz / c, si / c);
@@ -289,24 +316,18 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   if (max_n <= 0 || max_n > cap) max_n = cap;   // host-known upper bound of d_n[s]
   const size_t n = (size_t)nstreams * max_n;
   world.reserve(n * sizeof(float4));
-  keys_a.reserve(n * 8); keys_b.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4);
+  unsigned int gcap = 1024;
+  while ((size_t)gcap < 2 * n) gcap <<= 1;
+  keys_a.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4); keys_b.reserve((size_t)gcap * sizeof(GroupEntry));
   pending.reserve(n * sizeof(PendingAdd));
-  size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr,
-                                  (unsigned int*)nullptr, (long long)n, 0, 62, stream);
-  temp.reserve(tb);
   const unsigned int nb = (unsigned int)((n + 255) / 256);
   cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), stream);
+  CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b.p, gcap);
   CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
-            (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)flags.p);
-  tb = temp.cap;
-  CM_TIMED("cub_radix_sort(map)", stream,
-           cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
-                                           (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, 62, stream));
-  g_launch_count += 9;
-  CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_b.p, (const unsigned int*)vals_b.p, n,
-            (const float4*)world.p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending.p, (unsigned int*)n_pending.p, (unsigned int)n,
-            (int*)flags.p);
+            (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)vals_b.p, (GroupEntry*)keys_b.p, gcap - 1, (int*)flags.p);
+  CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a.p, (const unsigned int*)vals_a.p, (const int*)vals_b.p,
+            (const GroupEntry*)keys_b.p, n, (const float4*)world.p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending.p,
+            (unsigned int*)n_pending.p, (unsigned int)n, (int*)flags.p);
   CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
             (MapClassDev*)dev[cls].p, (int*)flags.p);
   CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
