@@ -149,7 +149,7 @@ def measured_peak():
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "corr_kernel_traffic.json")))["dram_bytes_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         return None
 
