@@ -166,6 +166,15 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
 int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
                             const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
 
+/* LaserLocalization::process (LaserLocalization.cpp:163-188) for one frame per stream against the map held by the context
+ * (built with cm_map_insert_host / cm_map_load_host): same frame preparation as cm_mapping_process_host, but the pose is
+ * refined by the localisation matcher FeatureMap::scanMatchScan (FeatureMap.h:490-690) -- the 5 neighbours of a query
+ * come from the query's own 50 m cube only, which must hold >= 5 points (:521-527); no reference-size gate; 10
+ * iterations; converged below 0.05 deg and 0.05 cm -- and the map is left untouched (featureMapUpdate is commented out
+ * in the reference).  The IMU blending of LaserLocalization::transformUpdate stays with the caller. */
+int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                                 const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
+
 /* Scan registration + mapping in one call: frames[s][row][col] organised sweeps -> mapped poses.  The less-sharp and
  * less-flat clouds of cm_scanreg_organised feed cm_mapping_process without leaving the device.  _dev: `frames` is a
  * DEVICE pointer (inputs already resident in HBM); poses and stats stay host arrays. */
@@ -188,6 +197,15 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
  * storage order; *n_out is the total even when it exceeds cap.  Sorting by (cube, voxel) gives the reference's
  * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
 int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
+
+/* FeatureMap::saveCloudToFiles / loadCloudFromFiles (FeatureMap.h:378-462): <dir>/index.txt ("count type i j k size" per
+ * file, type 0 corner / 1 surf, cubes enumerated i, j, k with corner before surf) + <dir>/<count>.pcd, binary PCD files as
+ * pcl::io::savePCDFileBinary writes them for pcl::PointXYZI; a cube's points are stored in VoxelGrid order.  Loading pushes
+ * every file through the map voxel filter like the reference; n_misplaced counts points whose coordinates put them into
+ * another cube than the index line says (the reference keeps them in the named cube, here they follow their coordinates --
+ * zero for files written by either implementation).  ascii and binary PCD are read, binary_compressed is not. */
+int cm_map_save_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files);
+int cm_map_load_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files, size_t* n_points, size_t* n_misplaced);
 
 /* ---- scan-to-scan odometry ------------------------------------------------------------------------------------------ */
 typedef struct cm_odom_stats {

@@ -13,6 +13,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <functional>
+#include <map>
 #include <vector>
 
 namespace cmo {
@@ -104,6 +106,10 @@ struct MatchResult {
 void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* refCorner, size_t nRefCorner,
                 const PointI* refSurf, size_t nRefSurf, const PointI* corner, size_t nCorner,
                 const PointI* surf, size_t nSurf, float pose[6], MatchResult& res, bool keepLog);
+// neighbour source of one query: fills ind[5] / sq[5] and returns the cloud the indices refer to (NULL: query skipped)
+typedef std::function<const PointI*(bool isCorner, const float sel[3], int* ind, float* sq)> NeighbourLookup;
+void scan_match_impl(const MatchParams& prm, const NeighbourLookup& lookup, const PointI* corner, size_t nCorner, const PointI* surf,
+                     size_t nSurf, float pose[6], MatchResult& res, bool keepLog);
 bool find_line(const PointI* cloud, const int* idx, float A[3], float B[3]);                    // feature_utils.h:108-154
 bool find_plane(const PointI* cloud, const int* idx, float maxDistance, float plane[4]);        // :157-204
 bool corner_coefficients(const float A[3], const float B[3], const float X[3], float coeff[4]); // :63-75
@@ -131,7 +137,15 @@ class FeatureMap {
   void update(const float sensor[3]);                                            // FeatureMap.h:232-254
   void getSurroundFeature(std::vector<PointI>& corner, std::vector<PointI>& surf) const;   // :256-265
   void addFeatureCloud(const std::vector<PointI>& corner, const std::vector<PointI>& surf, const Iso& tf);  // :219-230
+  // localisation matcher FeatureMap::scanMatchScan(corner, surf, Twist&), FeatureMap.h:490-690: neighbours from the
+  // query's own cube (KD-trees per cube, :437,451), fixed 10 iterations and 0.05 / 0.05 thresholds
+  void scanMatchScan(const KnnBackend& knn, const std::vector<PointI>& corner, const std::vector<PointI>& surf, float pose[6],
+                     MatchResult& res, bool keepLog);
+  // saveCloudToFiles / loadCloudFromFiles cube enumeration (:378-462): non-empty (cube, class) pairs in file order
+  void fileOrder(std::vector<int>& type, std::vector<int>& ci, std::vector<int>& cj, std::vector<int>& ck) const;
+  void loadCube(int type, int i, int j, int k, const std::vector<PointI>& cloud);   // :428-456 (filter, then swap in)
   const std::vector<size_t>& validCubes() const { return _cubeValidInd; }
+  int worldToIndex(float x, float y, float z) const;   // :464-473
   size_t totalPoints() const;
   std::vector<std::vector<PointI>> cornerCube, surfCube;
   int originW, originH, originD;
@@ -151,6 +165,8 @@ class FeatureMap {
 class LaserMapping {
  public:
   LaserMapping(const MapParams& mp, const MatchParams& sp, const KnnBackend& knn);
+  // LaserLocalization::process (LaserLocalization.cpp:163-188): same frame preparation, FeatureMap::scanMatchScan, no map update
+  Iso localize(const Iso& odom, const std::vector<PointI>& corner, const std::vector<PointI>& surf);
   // odom: the odometry pose of this frame (Isometry, /laser_odom_to_init); corner/surf: feature clouds in the
   // sensor frame (/laser_cloud_corner_last, /laser_cloud_surf_last).  Returns the mapped pose.
   Iso process(const Iso& odom, const std::vector<PointI>& corner, const std::vector<PointI>& surf);

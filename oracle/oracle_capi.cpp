@@ -199,6 +199,38 @@ void cmo_mapping_process(void* hh, const float* odomR, const float* odomT, const
     stats[11] = (int)m->surroundCorner.size(); stats[12] = (int)m->surroundSurf.size();
   }
 }
+// LaserLocalization::process
+void cmo_mapping_localize(void* hh, const float* odomR, const float* odomT, const float* corner, size_t nc, const float* surf,
+                          size_t ns, float* outR, float* outT, int* stats) {
+  LaserMapping* m = ((MappingHandle*)hh)->m;
+  Iso od; std::memcpy(od.R, odomR, 36); std::memcpy(od.t, odomT, 12);
+  std::vector<PointI> c((const PointI*)corner, (const PointI*)corner + nc), s((const PointI*)surf, (const PointI*)surf + ns);
+  Iso r = m->localize(od, c, s);
+  std::memcpy(outR, r.R, 36); std::memcpy(outT, r.t, 12);
+  if (stats) {
+    const MatchResult& q = m->lastMatch;
+    stats[0] = q.ok; stats[1] = q.converged; stats[2] = q.tooFewRef; stats[3] = q.tooFewMatches; stats[4] = q.degenerate;
+    stats[5] = q.iterations; stats[6] = q.lastRows; stats[7] = q.lastLine; stats[8] = q.lastPlane;
+    stats[9] = (int)m->cornerDS.size(); stats[10] = (int)m->surfDS.size(); stats[11] = stats[12] = 0;
+  }
+}
+// saveCloudToFiles enumeration: fills type / i / j / k per file (NULL: count only); cube clouds through cmo_mapping_cube
+size_t cmo_mapping_file_order(void* hh, int* type, int* ci, int* cj, int* ck, size_t cap) {
+  std::vector<int> t, a, b, c;
+  ((MappingHandle*)hh)->m->map.fileOrder(t, a, b, c);
+  for (size_t n = 0; n < t.size() && n < cap && type; n++) { type[n] = t[n]; ci[n] = a[n]; cj[n] = b[n]; ck[n] = c[n]; }
+  return t.size();
+}
+size_t cmo_mapping_cube(void* hh, int type, int i, int j, int k, const int* dims, float* out, size_t cap) {
+  LaserMapping* m = ((MappingHandle*)hh)->m;
+  const std::vector<PointI>& v = (type == 0 ? m->map.cornerCube : m->map.surfCube)[i + j * dims[0] + k * dims[0] * dims[1]];
+  if (out) std::memcpy(out, v.data(), std::min(cap, v.size()) * sizeof(PointI));
+  return v.size();
+}
+void cmo_mapping_load_cube(void* hh, int type, int i, int j, int k, const float* cloud, size_t n) {
+  std::vector<PointI> c((const PointI*)cloud, (const PointI*)cloud + n);
+  ((MappingHandle*)hh)->m->map.loadCube(type, i, j, k, c);
+}
 // which: 0 surround corner, 1 surround surf (as used by the last process()), 2 cornerDS, 3 surfDS,
 // 4 all corner cubes concatenated in cube-index order, 5 all surf cubes
 size_t cmo_mapping_cloud(void* hh, int which, float* out, size_t cap) {

@@ -113,6 +113,48 @@ void FeatureMap::addFeatureCloud(const std::vector<PointI>& corner, const std::v
   push(surf, surfCube);
   downsizeValidCloud();
 }
+int FeatureMap::worldToIndex(float x, float y, float z) const {   // FeatureMap.h:464-473
+  int i, j, k;
+  return worldToCube(x, y, z, i, j, k) ? toIndex(i, j, k) : -1;
+}
+// FeatureMap.h:490-690.  The reference builds the per-cube KD-trees when the map is loaded (:437,451); here they are built
+// on first use inside the call (same trees, the map does not change during a match).
+void FeatureMap::scanMatchScan(const KnnBackend& knn, const std::vector<PointI>& corner, const std::vector<PointI>& surf, float pose[6],
+                               MatchResult& res, bool keepLog) {
+  res = MatchResult();
+  MatchParams prm;
+  prm.maxIterations = 10; prm.deltaRAbort = 0.05f; prm.deltaTAbort = 0.05f; prm.useScore = false;   // :514, 676
+  std::map<int, void*> kdCorner, kdSurf;
+  NeighbourLookup lookup = [&](bool isCorner, const float sel[3], int* ind, float* sq) -> const PointI* {
+    const int idx = worldToIndex(sel[0], sel[1], sel[2]);
+    if (idx < 0) return nullptr;                                    // :521-522
+    const std::vector<PointI>& cube = isCorner ? cornerCube[idx] : surfCube[idx];
+    if (cube.size() < 5) return nullptr;                            // :523
+    std::map<int, void*>& trees = isCorner ? kdCorner : kdSurf;
+    auto it = trees.find(idx);
+    if (it == trees.end()) { void* h = nullptr; knn.build(cube.data(), cube.size(), &h); it = trees.insert(std::make_pair(idx, h)).first; }
+    knn.query(it->second, sel, 5, ind, sq);                         // :524
+    return cube.data();
+  };
+  scan_match_impl(prm, lookup, corner.data(), corner.size(), surf.data(), surf.size(), pose, res, keepLog);
+  for (auto& kv : kdCorner) knn.free(kv.second);
+  for (auto& kv : kdSurf) knn.free(kv.second);
+}
+void FeatureMap::fileOrder(std::vector<int>& type, std::vector<int>& ci, std::vector<int>& cj, std::vector<int>& ck) const {
+  type.clear(); ci.clear(); cj.clear(); ck.clear();
+  for (int i = 0; i < _p.cubeW; i++)
+    for (int j = 0; j < _p.cubeH; j++)
+      for (int k = 0; k < _p.cubeD; k++) {
+        if (!cornerCube[toIndex(i, j, k)].empty()) { type.push_back(0); ci.push_back(i); cj.push_back(j); ck.push_back(k); }
+        if (!surfCube[toIndex(i, j, k)].empty()) { type.push_back(1); ci.push_back(i); cj.push_back(j); ck.push_back(k); }
+      }
+}
+void FeatureMap::loadCube(int type, int i, int j, int k, const std::vector<PointI>& cloud) {
+  if (!isIndexValid(i, j, k)) return;
+  std::vector<PointI> ds;
+  voxel_filter(cloud.data(), cloud.size(), type == 0 ? _p.mapFilterCorner : _p.mapFilterSurf, ds);
+  (type == 0 ? cornerCube : surfCube)[toIndex(i, j, k)].swap(ds);
+}
 size_t FeatureMap::totalPoints() const {
   size_t n = 0;
   for (auto& c : cornerCube) n += c.size();
@@ -147,6 +189,22 @@ Iso LaserMapping::process(const Iso& odomNew, const std::vector<PointI>& corner,
   odomLast = odomNew;
   // featureMapUpdate, LaserMatcher.cpp:349-355
   map.addFeatureCloud(cornerDS, surfDS, mappedNew);
+  return mappedNew;
+}
+
+// LaserLocalization::process, LaserLocalization.cpp:163-188 (IMU blending of transformUpdate not restated)
+Iso LaserMapping::localize(const Iso& odomNew, const std::vector<PointI>& corner, const std::vector<PointI>& surf) {
+  Iso L2W = iso_mul(mappedLast, iso_inverse(odomLast));
+  mappedNew = iso_mul(L2W, odomNew);
+  voxel_filter(corner.data(), corner.size(), _mp.filterCorner, cornerDS);
+  voxel_filter(surf.data(), surf.size(), _mp.filterSurf, surfDS);
+  map.update(mappedNew.t);
+  float pose[6];
+  iso_to_twist(mappedNew, pose);
+  map.scanMatchScan(_knn, cornerDS, surfDS, pose, lastMatch, keepLog);   // optimizeTransform, :124-138 -> FeatureMap.h:692-700
+  twist_to_iso(pose, mappedNew);
+  mappedLast = mappedNew;
+  odomLast = odomNew;
   return mappedNew;
 }
 

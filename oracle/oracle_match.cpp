@@ -125,18 +125,14 @@ struct AngleO {
 
 static inline float rad2degf(float r) { return (float)(r * 180.0 / M_PI); }   // math_utils.h:24
 
-// ScanMatch::scanMatchScan(..., Twist&), ScanMatch.cpp:51-347
-void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* refCorner, size_t nRefCorner,
-                const PointI* refSurf, size_t nRefSurf, const PointI* corner, size_t CornerNum,
-                const PointI* surf, size_t SurfNum, float pose[6], MatchResult& res, bool keepLog) {
-  res = MatchResult();
-  if (nRefCorner < 50 || nRefSurf < 100) { res.tooFewRef = true; return; }   // :57-61
+// The Gauss-Newton loop shared by ScanMatch::scanMatchScan (ScanMatch.cpp:51-347) and FeatureMap::scanMatchScan
+// (FeatureMap.h:490-690): the two differ only in where the 5 neighbours of a query come from (`lookup`: returns the cloud
+// the indices refer to, or NULL when the reference `continue`s before searching).
+void scan_match_impl(const MatchParams& prm, const NeighbourLookup& lookup, const PointI* corner, size_t CornerNum,
+                     const PointI* surf, size_t SurfNum, float pose[6], MatchResult& res, bool keepLog) {
   AngleO rot_x, rot_y, rot_z;
   rot_x.set(pose[0]); rot_y.set(pose[1]); rot_z.set(pose[2]);
   float pos[3] = {pose[3], pose[4], pose[5]};
-  void *kdCorner = nullptr, *kdSurf = nullptr;
-  knn.build(refCorner, nRefCorner, &kdCorner);
-  knn.build(refSurf, nRefSurf, &kdSurf);
   bool converge = false, isDegenerate = false;
   float matP[36];
   std::vector<PointI> laserCloudOri, coeffSel;
@@ -154,7 +150,8 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
       const PointI& pointOri = corner[i];
       float sel[3];
       cm::transform_point(Rm, pos, pointOri.x, pointOri.y, pointOri.z, &sel[0], &sel[1], &sel[2]);
-      knn.query(kdCorner, sel, 5, ind, sq);
+      const PointI* refCorner = lookup(true, sel, ind, sq);
+      if (!refCorner) continue;
       if (sq[4] < prm.knnGate) {
         if (keepLog) for (int t = 0; t < 5; t++) lg.nnCorner[5 * i + t] = ind[t];
         float lineA[3], lineB[3];
@@ -172,7 +169,8 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
       const PointI& pointOri = surf[i];
       float sel[3];
       cm::transform_point(Rm, pos, pointOri.x, pointOri.y, pointOri.z, &sel[0], &sel[1], &sel[2]);
-      knn.query(kdSurf, sel, 5, ind, sq);
+      const PointI* refSurf = lookup(false, sel, ind, sq);
+      if (!refSurf) continue;
       if (sq[4] < prm.knnGate) {
         if (keepLog) for (int t = 0; t < 5; t++) lg.nnSurf[5 * i + t] = ind[t];
         float plane[4];
@@ -268,7 +266,6 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
     }
     if (deltaR < prm.deltaRAbort && deltaT < prm.deltaTAbort) { converge = true; break; }
   }
-  knn.free(kdCorner); knn.free(kdSurf);
   res.converged = converge; res.degenerate = isDegenerate;
   pose[0] = rot_x.rad; pose[1] = rot_y.rad; pose[2] = rot_z.rad; pose[3] = pos[0]; pose[4] = pos[1]; pose[5] = pos[2];
   if (converge && prm.useScore) {   // :263-341 (fineScore is always false, ScanMatch.cpp:32)
@@ -283,6 +280,23 @@ void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* ref
     return;
   }
   res.ok = false;   // :342-346 (pose is still written back)
+}
+
+// ScanMatch::scanMatchScan(..., Twist&), ScanMatch.cpp:51-347
+void scan_match(const MatchParams& prm, const KnnBackend& knn, const PointI* refCorner, size_t nRefCorner,
+                const PointI* refSurf, size_t nRefSurf, const PointI* corner, size_t CornerNum,
+                const PointI* surf, size_t SurfNum, float pose[6], MatchResult& res, bool keepLog) {
+  res = MatchResult();
+  if (nRefCorner < 50 || nRefSurf < 100) { res.tooFewRef = true; return; }   // :57-61
+  void *kdCorner = nullptr, *kdSurf = nullptr;
+  knn.build(refCorner, nRefCorner, &kdCorner);   // :75-76
+  knn.build(refSurf, nRefSurf, &kdSurf);
+  NeighbourLookup lookup = [&](bool isCorner, const float sel[3], int* ind, float* sq) -> const PointI* {
+    knn.query(isCorner ? kdCorner : kdSurf, sel, 5, ind, sq);   // :100-101, 119
+    return isCorner ? refCorner : refSurf;
+  };
+  scan_match_impl(prm, lookup, corner, CornerNum, surf, SurfNum, pose, res, keepLog);
+  knn.free(kdCorner); knn.free(kdSurf);
 }
 
 // ---- Isometry helpers --------------------------------------------------------------------------------------

@@ -37,6 +37,8 @@ def lib(fast=False):
     L.cmo_odom_create.restype = C.c_void_p
     L.cmo_odom_indices.restype = C.c_size_t
     L.cmo_mapping_cloud.restype = C.c_size_t
+    L.cmo_mapping_file_order.restype = C.c_size_t
+    L.cmo_mapping_cube.restype = C.c_size_t
     L.cmo_mapping_map_surround.restype = C.c_size_t
     L.has_nanoflann = bool(os.path.exists(REF_SO) and L.cmo_load_nanoflann(REF_SO.encode()))
     _libs[name] = L
@@ -230,6 +232,45 @@ def scan_match_local(ref_corner, ref_surf, corner, surf, pose, params=None, nano
 
 
 # ---- mapping loop -----------------------------------------------------------------------------------------
+def write_pcd_binary(path, pts):
+    """pcl::io::savePCDFileBinary of a pcl::PointCloud<pcl::PointXYZI>: v0.7 header, 16 packed bytes per point."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\n"
+           "COUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(pts), len(pts)))
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii")); f.write(pts.tobytes())
+
+
+def read_pcd(path):
+    """x, y, z, intensity of a binary / ascii PCD file with float32 fields."""
+    raw = open(path, "rb").read()
+    pos = 0; hdr = {}
+    while True:
+        end = raw.index(b"\n", pos); line = raw[pos:end].decode("ascii").strip(); pos = end + 1
+        if line.startswith("#") or not line:
+            continue
+        k, *v = line.split(); hdr[k] = v
+        if k == "DATA":
+            break
+    fields = hdr["FIELDS"]; size = [int(x) for x in hdr["SIZE"]]; cnt = [int(x) for x in hdr.get("COUNT", ["1"] * len(fields))]
+    n = int(hdr["POINTS"][0])
+    if hdr["DATA"][0] == "binary":
+        dt = np.dtype([(f if f != "_" else "_%d" % i, "<f4" if s == 4 else "V%d" % (s * c), ()) if (s == 4 and c == 1) else ("pad%d" % i, "V%d" % (s * c))
+                       for i, (f, s, c) in enumerate(zip(fields, size, cnt))])
+        a = np.frombuffer(raw, dt, count=n, offset=pos)
+        out = np.zeros((n, 4), np.float32)
+        for col, name in enumerate(["x", "y", "z", "intensity"]):
+            if name in a.dtype.names:
+                out[:, col] = a[name]
+        return out
+    rows = np.array(raw[pos:].split(), np.float64).reshape(n, -1)
+    out = np.zeros((n, 4), np.float32)
+    for col, name in enumerate(["x", "y", "z", "intensity"]):
+        if name in fields:
+            out[:, col] = rows[:, fields.index(name)]
+    return out
+
+
 class Mapping:
     """LaserMapping::process restated (oracle_map.cpp)."""
 
@@ -242,6 +283,7 @@ class Mapping:
                    d["filterSurf"]])
         mi = np.array([d["cubeW"], d["cubeH"], d["cubeD"]], np.int32)
         sf, si = _match_params(match_params)
+        self.dims = (d["cubeW"], d["cubeH"], d["cubeD"])
         self.h = self.L.cmo_mapping_create(_p(mf), _p(mi), _p(sf), _p(si), C.c_int(int(nanoflann and self.L.has_nanoflann)))
 
     def __del__(self):
@@ -257,6 +299,47 @@ class Mapping:
         keys = ["ok", "converged", "tooFewRef", "tooFewMatches", "degenerate", "iterations", "rows", "line", "plane",
                 "nCornerDS", "nSurfDS", "nSurroundCorner", "nSurroundSurf"]
         return oR, ot, dict(zip(keys, [int(v) for v in st]))
+
+    def localize(self, odom_R, odom_t, corner, surf):
+        """LaserLocalization::process: FeatureMap::scanMatchScan against the map, no map update."""
+        R = _f32(odom_R); t = _f32(odom_t)
+        c = _f32(corner).reshape(-1, 4); s = _f32(surf).reshape(-1, 4)
+        oR = np.empty((3, 3), np.float32); ot = np.empty(3, np.float32); st = np.zeros(13, np.int32)
+        self.L.cmo_mapping_localize(C.c_void_p(self.h), _p(R), _p(t), _p(c), C.c_size_t(len(c)), _p(s), C.c_size_t(len(s)),
+                                    _p(oR), _p(ot), _p(st))
+        keys = ["ok", "converged", "tooFewRef", "tooFewMatches", "degenerate", "iterations", "rows", "line", "plane",
+                "nCornerDS", "nSurfDS", "nSurroundCorner", "nSurroundSurf"]
+        return oR, ot, dict(zip(keys, [int(v) for v in st]))
+
+    # ---- FeatureMap::saveCloudToFiles / loadCloudFromFiles (FeatureMap.h:378-462), file format restated in numpy ----
+    def save_files(self, directory):
+        """index.txt + <count>.pcd (pcl::io::savePCDFileBinary layout for PointXYZI); returns the number of files."""
+        n = self.L.cmo_mapping_file_order(C.c_void_p(self.h), None, None, None, None, C.c_size_t(0))
+        ty = np.zeros(max(n, 1), np.int32); ci = np.zeros_like(ty); cj = np.zeros_like(ty); ck = np.zeros_like(ty)
+        self.L.cmo_mapping_file_order(C.c_void_p(self.h), _p(ty), _p(ci), _p(cj), _p(ck), C.c_size_t(len(ty)))
+        dims = np.array(self.dims, np.int32)
+        with open(os.path.join(directory, "index.txt"), "w") as idx:
+            for count in range(n):
+                m = self.L.cmo_mapping_cube(C.c_void_p(self.h), C.c_int(int(ty[count])), C.c_int(int(ci[count])), C.c_int(int(cj[count])),
+                                            C.c_int(int(ck[count])), _p(dims), None, C.c_size_t(0))
+                pts = np.empty((m, 4), np.float32)
+                self.L.cmo_mapping_cube(C.c_void_p(self.h), C.c_int(int(ty[count])), C.c_int(int(ci[count])), C.c_int(int(cj[count])),
+                                        C.c_int(int(ck[count])), _p(dims), _p(pts), C.c_size_t(m))
+                write_pcd_binary(os.path.join(directory, "%d.pcd" % count), pts)
+                idx.write("%d %d %d %d %d %d\n" % (count, ty[count], ci[count], cj[count], ck[count], m))
+        return n
+
+    def load_files(self, directory):
+        n = 0
+        for line in open(os.path.join(directory, "index.txt")):
+            f = line.split()
+            if len(f) != 6:
+                continue
+            count, ty, i, j, k, _size = [int(v) for v in f]
+            pts = read_pcd(os.path.join(directory, "%d.pcd" % count))
+            self.L.cmo_mapping_load_cube(C.c_void_p(self.h), C.c_int(ty), C.c_int(i), C.c_int(j), C.c_int(k), _p(pts), C.c_size_t(len(pts)))
+            n += 1
+        return n
 
     def cloud(self, which):
         n = self.L.cmo_mapping_cloud(C.c_void_p(self.h), C.c_int(which), None, C.c_size_t(0))

@@ -290,3 +290,26 @@ def test_capi_fails_loudly_without_gpu(cmb):
         pytest.skip("a GPU is present")
     with pytest.raises(cmb.CoopermapError):
         cmb.Context()
+
+
+def test_oracle_map_files_round_trip(oracle, synth, tmp_path):
+    """FeatureMap::saveCloudToFiles -> loadCloudFromFiles (FeatureMap.h:378-462) restated: index.txt order and PCD payload."""
+    sc = synth.make_scene(seed=61, extent=70.0, n_boxes=16, n_poles=10)
+    mc, ms = synth.sample_map(sc, 0.6, seed=62)
+    P = dict(mapFilterCorner=0.4, mapFilterSurf=0.4)
+    om = oracle.Mapping(map_params=P)
+    om.map_update(np.zeros(3, np.float32))
+    om.map_add(mc, ms, np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+    n = om.save_files(str(tmp_path))
+    lines = [l.split() for l in (tmp_path / "index.txt").read_text().splitlines()]
+    assert n == len(lines) > 2 and [int(l[0]) for l in lines] == list(range(n))
+    order = [(int(l[2]), int(l[3]), int(l[4]), int(l[1])) for l in lines]
+    assert order == sorted(order)                                   # i, then j, then k; corner (0) before surf (1)
+    raw = (tmp_path / "0.pcd").read_bytes()
+    assert raw.startswith(b"# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\n")
+    assert len(raw) - raw.index(b"DATA binary\n") - len(b"DATA binary\n") == 16 * int(lines[0][5])
+    om2 = oracle.Mapping(map_params=P)
+    assert om2.load_files(str(tmp_path)) == n
+    for which in (4, 5):
+        a, b = om.cloud(which), om2.cloud(which)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -173,6 +173,28 @@ class Context:
                                                    C.c_int(scap), _ptr(mapped), stats))
         return self._unpack_results(mapped, stats)
 
+    def localization_process(self, odoms, corners, surfs):
+        """LaserLocalization::process for one frame per stream (FeatureMap::scanMatchScan against the resident map)."""
+        S = self.nstreams
+        od = self._pack_isos(odoms)
+        cb, cn, ccap = self._pack_clouds(corners); sb, sn, scap = self._pack_clouds(surfs)
+        mapped = np.empty((S, 12), np.float32); stats = (MatchStats * S)()
+        self._check(self.L.cm_localization_process_host(self.h, _ptr(od), _ptr(cb), _ptr(cn), C.c_int(ccap), _ptr(sb), _ptr(sn),
+                                                        C.c_int(scap), _ptr(mapped), stats))
+        return self._unpack_results(mapped, stats)
+
+    def map_save(self, stream, directory):
+        """FeatureMap::saveCloudToFiles: index.txt + <count>.pcd; returns the number of files."""
+        n = C.c_int(0)
+        self._check(self.L.cm_map_save_host(self.h, C.c_int(stream), str(directory).encode(), C.byref(n)))
+        return n.value
+
+    def map_load(self, stream, directory):
+        """FeatureMap::loadCloudFromFiles -> (files, points read, points whose coordinates disagree with the index line)."""
+        n = C.c_int(0); npts = C.c_size_t(0); bad = C.c_size_t(0)
+        self._check(self.L.cm_map_load_host(self.h, C.c_int(stream), str(directory).encode(), C.byref(n), C.byref(npts), C.byref(bad)))
+        return n.value, npts.value, bad.value
+
     def pipeline_step(self, frames, odoms):
         """Scan registration + mapping for one organised sweep per stream: frames (S, rows, cols, 4)."""
         fr = _f32(frames)
@@ -433,6 +455,26 @@ class LaserMapping:
 
     def process(self, odom_R, odom_t, laserCloudCornerLast, laserCloudSurfLast):
         isos, stats = self.ctx.mapping_process([(odom_R, odom_t)], [laserCloudCornerLast], [laserCloudSurfLast])
+        self.last_stats = stats[0]
+        return isos[0]
+
+
+class LaserLocalization:
+    """Mirror of lidar_slam::LaserLocalization (LaserLocalization.h): localisation against a prebuilt cube map.
+
+    load(directory) reads the index.txt / PCD layout FeatureMap::saveCloudToFiles writes; process(odom, corner, surf)
+    refines the pose with FeatureMap::scanMatchScan (own-cube neighbours) and leaves the map untouched."""
+
+    def __init__(self, ctx=None, max_corner_points=200000, max_surf_points=2000000, **cfg):
+        self.ctx = ctx or Context(**cfg)
+        self.ctx.mapping_create(1, max_corner_points, max_surf_points)
+        self.last_stats = None
+
+    def load(self, directory):
+        return self.ctx.map_load(0, directory)
+
+    def process(self, odom_R, odom_t, laserCloudCornerLast, laserCloudSurfLast):
+        isos, stats = self.ctx.localization_process([(odom_R, odom_t)], [laserCloudCornerLast], [laserCloudSurfLast])
         self.last_stats = stats[0]
         return isos[0]
 

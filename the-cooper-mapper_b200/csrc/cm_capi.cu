@@ -19,7 +19,7 @@ MatchParamsDev dev_params(const cm_config& c) {
   p.delta_t_abort = c.delta_t_abort; p.delta_r_abort = c.delta_r_abort;
   p.knn_gate = 5.0f; p.plane_max_dist = 0.2f;
   p.min_ref_corner = 50; p.min_ref_surf = 100; p.min_rows = 50; p.eig_threshold = 100.f;
-  p.few_rows_continue = 0; p.nan_guard = 0;
+  p.few_rows_continue = 0; p.nan_guard = 0; p.own_cube_only = 0;
   return p;
 }
 int ctx_fail(cm_ctx* ctx, int code, const std::string& msg) {

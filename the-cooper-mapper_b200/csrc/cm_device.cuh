@@ -47,6 +47,7 @@ struct GridView {
   int npts;                   // number of searchable points (the reference gates on it, ScanMatch.cpp:57-58)
   int max_level;              // last shell to visit so that (max_level + 0.48) * cell >= sqrt(gate)
   const CubeWindow* window;   // NULL: no cube filtering
+  const int* cube_count;      // points per 50 m cube [W*H*D] (map grids; NULL for stateless clouds)
 };
 
 __host__ __device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
@@ -114,6 +115,20 @@ __device__ __forceinline__ int window_index(const CubeWindow& w, float x, float 
   return (i * 7 + j) * 7 + k;
 }
 
+// Candidate filter codes (KnnGeom::filt): CM_FILT_NONE: every point of the grid is searched; CM_FILT_WINDOW: only points
+// whose cube is in the active window (FeatureMap::getSurroundFeature, FeatureMap.h:256-265); >= 0: only points of the
+// cube with that linear index -- the localisation matcher searches the query's own cube (FeatureMap.h:521-527).
+#define CM_FILT_NONE (-1)
+#define CM_FILT_WINDOW (-2)
+__device__ __forceinline__ bool cand_ok(const GridView& g, int filt, const float4& p) {
+  if (filt == CM_FILT_NONE) return true;
+  const CubeWindow& w = *g.window;
+  if (filt == CM_FILT_WINDOW) { const int wi = window_index(w, p.x, p.y, p.z); return wi >= 0 && w.active[wi]; }
+  const int i = (int)(roundf(p.x / w.cube_size) + (float)w.origin[0]), j = (int)(roundf(p.y / w.cube_size) + (float)w.origin[1]),
+            k = (int)(roundf(p.z / w.cube_size) + (float)w.origin[2]);
+  return i >= 0 && i < w.dims[0] && j >= 0 && j < w.dims[1] && k >= 0 && k < w.dims[2] && (i + j * w.dims[0] + k * w.dims[0] * w.dims[1]) == filt;
+}
+
 // Squared distance from u (voxel units) to the slab [lo, hi) of a cell along one axis, 0 inside.
 __device__ __forceinline__ float slab_dist(float u, float lo, float hi) { float d = fmaxf(fmaxf(lo - u, u - hi), 0.f); return d; }
 
@@ -124,7 +139,7 @@ __device__ __forceinline__ unsigned long long entry_key(const uint4& e) { return
 // filter: test every candidate's cube against the active window (only for queries near an inactive cube).
 template <bool kOrigIdx>
 __device__ __forceinline__ void scan_points(const GridView& g, unsigned int start, unsigned int count, float qx, float qy, float qz,
-                                            bool filter, Top5& best) {
+                                            int filt, Top5& best) {
   for (unsigned int j0 = 0; j0 < count; j0 += 4) {
     float4 p[4];
 #pragma unroll
@@ -133,10 +148,7 @@ __device__ __forceinline__ void scan_points(const GridView& g, unsigned int star
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       if (j0 + u < count) {
-        if (filter) {
-          int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z);
-          if (wi < 0 || !g.window->active[wi]) continue;
-        }
+        if (!cand_ok(g, filt, p[u])) continue;
         float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
         float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         const int j = (int)(start + j0 + u);
@@ -147,11 +159,11 @@ __device__ __forceinline__ void scan_points(const GridView& g, unsigned int star
 }
 
 template <bool kOrigIdx>
-__device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, bool filter,
+__device__ __forceinline__ void scan_cell(const GridView& g, int x, int y, int z, float qx, float qy, float qz, int filt,
                                           Top5& best) {
   unsigned int start, count;
   if (!grid_probe(g, x, y, z, &start, &count)) return;
-  scan_points<kOrigIdx>(g, start, count, qx, qy, qz, filter, best);
+  scan_points<kOrigIdx>(g, start, count, qx, qy, qz, filt, best);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -177,15 +189,15 @@ struct KnnGeom {
   int lx, ly, lz;       // low cell of the level-0 block
   int own;              // position of the query's own cell inside the block (bit per axis)
   float m0;             // distance (voxel units) from the query to the nearest face of the block
-  bool filter;          // candidates need the per-point cube test
+  int filt;             // candidate filter code (CM_FILT_*)
 };
 
 // returns false when the coordinates are too large for the cell arithmetic (the query then has no neighbours)
-__device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy, float qz, float gate, KnnGeom& c) {
+__device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy, float qz, float gate, KnnGeom& c, bool own_cube = false) {
   const int k = g.kdiv;
   c.fx = qx * g.inv_leaf; c.fy = qy * g.inv_leaf; c.fz = qz * g.inv_leaf;
   const float flx = floorf(c.fx), fly = floorf(c.fy), flz = floorf(c.fz);
-  c.lx = c.ly = c.lz = 0; c.own = 0; c.m0 = 0.f; c.filter = false;
+  c.lx = c.ly = c.lz = 0; c.own = 0; c.m0 = 0.f; c.filt = CM_FILT_NONE;
   // keep the casts defined for absurd coordinates
   if (!(fabsf(flx) < 1.0e6f && fabsf(fly) < 1.0e6f && fabsf(flz) < 1.0e6f)) return false;
   const int vx = (int)flx, vy = (int)fly, vz = (int)flz;
@@ -196,7 +208,16 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
   c.ly = cy + (((float)(vy - cy * k) + (c.fy - fly)) < half ? -1 : 0);
   c.lz = cz + (((float)(vz - cz * k) + (c.fz - flz)) < half ? -1 : 0);
   c.own = (cx - c.lx) | ((cy - c.ly) << 1) | ((cz - c.lz) << 2);
-  if (g.window) {
+  if (own_cube) {
+    // localisation: worldToIndex of the query (FeatureMap.h:464-487); no cube or fewer than 5 points in it -> no match (:522-523)
+    if (!g.window || !g.cube_count) return false;
+    const CubeWindow& w = *g.window;
+    const int i = (int)(roundf(qx / w.cube_size) + (float)w.origin[0]), j = (int)(roundf(qy / w.cube_size) + (float)w.origin[1]),
+              kk = (int)(roundf(qz / w.cube_size) + (float)w.origin[2]);
+    if (!(i >= 0 && i < w.dims[0] && j >= 0 && j < w.dims[1] && kk >= 0 && kk < w.dims[2])) return false;
+    c.filt = i + j * w.dims[0] + kk * w.dims[0] * w.dims[1];
+    if (g.cube_count[c.filt] < 5) return false;
+  } else if (g.window) {
     // candidates can only lie within sqrt(gate) of the query: per-point cube tests are needed only if one of the
     // (at most 8) cubes touched by that box is not searched
     const CubeWindow& w = *g.window;
@@ -204,12 +225,14 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
     int i0 = (int)(roundf((qx - rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0], i1 = (int)(roundf((qx + rg) / w.cube_size) + (float)w.origin[0]) - w.w0[0];
     int j0 = (int)(roundf((qy - rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1], j1 = (int)(roundf((qy + rg) / w.cube_size) + (float)w.origin[1]) - w.w0[1];
     int k0 = (int)(roundf((qz - rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2], k1 = (int)(roundf((qz + rg) / w.cube_size) + (float)w.origin[2]) - w.w0[2];
-    if (i0 < 0 || i1 > 6 || j0 < 0 || j1 > 6 || k0 < 0 || k1 > 6) c.filter = true;
+    bool f = false;
+    if (i0 < 0 || i1 > 6 || j0 < 0 || j1 > 6 || k0 < 0 || k1 > 6) f = true;
     else {
       for (int i = i0; i <= i1; i++)
         for (int j = j0; j <= j1; j++)
-          for (int kk = k0; kk <= k1; kk++) c.filter = c.filter || !w.active[(i * 7 + j) * 7 + kk];
+          for (int kk = k0; kk <= k1; kk++) f = f || !w.active[(i * 7 + j) * 7 + kk];
     }
+    if (f) c.filt = CM_FILT_WINDOW;
   }
   // distance (voxel units) from the query to the nearest face of the level-0 block
   const float lox = (float)(c.lx * k), loy = (float)(c.ly * k), loz = (float)(c.lz * k);
@@ -277,9 +300,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       if ((unsigned int)u < left) {
-        bool ok = true;
-        if (c.filter) { int wi = window_index(*g.window, p[u].x, p[u].y, p[u].z); ok = (wi >= 0) && g.window->active[wi]; }
-        if (ok) {
+        if (cand_ok(g, c.filt, p[u])) {
           float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           const int j = (int)(r.x + j0 + u);
@@ -310,7 +331,7 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
   const float bfx = __shfl_sync(FULL, c.fx, h), bfy = __shfl_sync(FULL, c.fy, h), bfz = __shfl_sync(FULL, c.fz, h);
   const int blx = __shfl_sync(FULL, c.lx, h), bly = __shfl_sync(FULL, c.ly, h), blz = __shfl_sync(FULL, c.lz, h);
   const float bm0 = __shfl_sync(FULL, c.m0, h);
-  const bool bfilter = __shfl_sync(FULL, c.filter ? 1 : 0, h) != 0;
+  const int bfilter = __shfl_sync(FULL, c.filt, h);
   float bd5 = __shfl_sync(FULL, best.d(4), h);
   const float kf = (float)k;
   for (int L = 1; L <= g.max_level; L++) {
@@ -355,7 +376,7 @@ __device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float
                                             Top5& best) {
   top5_init(best);
   KnnGeom c;
-  valid = knn5_geom(g, qx, qy, qz, gate, c) && valid;
+  valid = knn5_geom(g, qx, qy, qz, gate, c, false) && valid;
   bool need = false;
   if (valid) need = knn5_level0<kOrigIdx>(g, c, qx, qy, qz, rng, best);
   unsigned int hard = __ballot_sync(0xffffffffu, need);

@@ -227,7 +227,7 @@ __global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, Gr
   v.npts = total;
   int L = (int)ceilf(sqrtf(gate) / (0.98f * v.cell) - 0.5f);
   v.max_level = L < 0 ? 0 : L;
-  v.window = windows + s;
+  v.window = windows + s; v.cube_count = m.cube_count;
   views[s] = v;
 }
 

@@ -139,12 +139,20 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
 // Core of the stage on DEVICE clouds.  d_corner/d_surf: [S][cap] with device counts d_n (corner counts then surf counts,
 // [2][S]).  h_odom: S odometry poses (host).  Outputs on the host: mapped poses and stats.
 // max_in_c / max_in_s: host-known upper bounds of the input counts (sizes the sorts).
+// localise: LaserLocalization::process (LaserLocalization.cpp:163-188) instead of LaserMapping::process -- the matcher is
+// FeatureMap::scanMatchScan (FeatureMap.h:490-690: neighbours from the query's own cube only, no reference-size gate,
+// 10 iterations, 0.05 deg / 0.05 cm) and the map is not updated.
 static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, const float4* d_surf, int cap_s, const int* d_n,
-                               int max_in_c, int max_in_s, const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats) {
+                               int max_in_c, int max_in_s, const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats,
+                               bool localise = false) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   cudaStream_t st = ctx->stream;
   MatchParamsDev prm = dev_params(cfg);
+  if (localise) {
+    prm.own_cube_only = 1; prm.max_iterations = 10; prm.delta_t_abort = 0.05f; prm.delta_r_abort = 0.05f;
+    prm.min_ref_corner = 0; prm.min_ref_surf = 0;
+  }
   // transformMerge
   std::vector<float> pose_in(6 * S);
   std::vector<CubeWindow> wins(S);
@@ -210,9 +218,11 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
       launch_match(m, st, &ctx->prof);
     }
   }
-  // featureMapUpdate
-  ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
-  ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+  // featureMapUpdate (commented out in LaserLocalization::process, LaserLocalization.cpp:186)
+  if (!localise) {
+    ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
+    ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+  }
   // results
   std::vector<MatchState> hs(S);
   int flags[8];
@@ -226,7 +236,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   for (int s = 0; s < S; s++) {
     const unsigned long long q = (unsigned long long)(nds[s] + nds[S + s]);
     const int evals = hs[s].iterations + ((hs[s].flags & CM_F_TOO_FEW_MATCHES) ? 1 : 0);   // correspondence passes actually run
-    ctx->last_query_iters += q * (unsigned long long)evals; ctx->last_queries += q; ctx->last_inserted += q;
+    ctx->last_query_iters += q * (unsigned long long)evals; ctx->last_queries += q; ctx->last_inserted += localise ? 0 : q;
   }
   for (int s = 0; s < S; s++) {
     MappingStream& ms = ctx->mstreams[s];
@@ -239,8 +249,8 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   return CM_OK;
 }
 
-int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
-                            const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats) {
+static int mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                                const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats, bool localise) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
   if (!odom || !corner || !surf || !n_corner || !n_surf || cap_corner <= 0 || cap_surf <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
   const int S = ctx->map_streams;
@@ -259,10 +269,19 @@ int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* cor
     int mc_ = 1, ms_ = 1;
     for (int s = 0; s < S; s++) { mc_ = std::max(mc_, n_corner[s]); ms_ = std::max(ms_, n_surf[s]); }
     return mapping_process_dev(ctx, (const float4*)ctx->m_corner_in.p, cap_corner, (const float4*)ctx->m_surf_in.p, cap_surf,
-                               (const int*)ctx->m_n_in.p, mc_, ms_, odom, mapped, stats);
+                               (const int*)ctx->m_n_in.p, mc_, ms_, odom, mapped, stats, localise);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
+}
+
+int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                            const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats) {
+  return mapping_process_host(ctx, odom, corner, n_corner, cap_corner, surf, n_surf, cap_surf, mapped, stats, false);
+}
+int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
+                                 const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats) {
+  return mapping_process_host(ctx, odom, corner, n_corner, cap_corner, surf, n_surf, cap_surf, mapped, stats, true);
 }
 
 // Full pipeline: OrganisedScanRegistration::process -> (/laser_cloud_less_sharp, /laser_cloud_less_flat) ->

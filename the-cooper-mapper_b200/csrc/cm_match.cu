@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   Top5 best;
   top5_init(best);
   KnnGeom c;
-  valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c) && valid;
+  valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
   bool need = false;
   unsigned int ncand = 0;
   if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
     search_query(a, s, t, R, T, &in_range, &isCorner, &row, &sx, &sy, &sz);
     const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
     KnnGeom c;
-    knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c);
+    knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0);
     Top5 best;
 #pragma unroll
     for (int k = 0; k < 5; k++) { best.key[k] = top5_key(item->d[k], item->idx[k]); best.slot[k] = item->slot[k]; }
@@ -703,7 +703,7 @@ void GridStorage::build(const float4* d_pts, int n, float cell_size, float gate,
   view.mask = cap - 1;
   view.inv_leaf = inv; view.kdiv = 1; view.cell = cell_size;
   view.npts = n;
-  view.window = nullptr;
+  view.window = nullptr; view.cube_count = nullptr;
   view.max_level = grid_max_level(cell_size, gate);
 }
 

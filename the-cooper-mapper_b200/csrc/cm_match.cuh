@@ -20,6 +20,8 @@ struct MatchParamsDev {
   float eig_threshold;     // 100, ScanMatch.cpp:223 (10 in LaserOdometry.cpp:596)
   int few_rows_continue;   // 0: fewer than min_rows rows ends the loop (ScanMatch.cpp:141-145); 1: the iteration is skipped
                            //    (LaserOdometry.cpp:501-503)
+  int own_cube_only;       // 1: a query only sees the map points of its own 50 m cube and needs >= 5 of them there -- the
+                           //    localisation matcher FeatureMap::scanMatchScan (FeatureMap.h:490-690); 0: ScanMatch on the surround map
   int nan_guard;           // 1: non-finite pose components are reset to 0 (LaserOdometry.cpp:622-634)
 };
 

@@ -55,7 +55,7 @@ int cm_odometry_process_host(cm_ctx* ctx, const cm_point* sharp, int n_sharp, co
       // ---- scanMatch ----
       MatchParamsDev prm;
       prm.max_iterations = MAXIT; prm.delta_t_abort = 0.1f; prm.delta_r_abort = 0.1f; prm.knn_gate = 25.f; prm.plane_max_dist = 0.f;
-      prm.min_ref_corner = 0; prm.min_ref_surf = 0; prm.min_rows = 10; prm.eig_threshold = 10.f; prm.few_rows_continue = 1; prm.nan_guard = 1;
+      prm.min_ref_corner = 0; prm.min_ref_surf = 0; prm.min_rows = 10; prm.eig_threshold = 10.f; prm.few_rows_continue = 1; prm.nan_guard = 1; prm.own_cube_only = 0;
       const int capC = std::max(n_sharp, 1), capS = std::max(n_flat, 1), capQ = capC + capS;
       ctx->o_sharp.reserve(capC * sizeof(cm_point)); ctx->o_flat.reserve(capS * sizeof(cm_point));
       ctx->o_ind.reserve((size_t)(2 * capC + 3 * capS) * sizeof(int));
