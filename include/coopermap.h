@@ -178,11 +178,14 @@ int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point
 /* Scan registration + mapping in one call: frames[s][row][col] organised sweeps -> mapped poses.  The less-sharp and
  * less-flat clouds of cm_scanreg_organised feed cm_mapping_process without leaving the device.  _dev: `frames` is a
  * DEVICE pointer (inputs already resident in HBM); poses and stats stay host arrays. */
-/* cm_pipeline_prefetch_host starts the upload of the NEXT step's sweeps (pinned host memory) on a second CUDA stream and
- * returns at once; the following cm_pipeline_step_host call with the same `frames` pointer uses that copy instead of
- * uploading again, so the host-to-device transfer of step k+1 overlaps the kernels of step k (the nodelet receives the
- * next PointCloud2 while the current one is being registered).  The host buffer must stay untouched until that step. */
+/* cm_pipeline_prefetch_host / _dev issue the NEXT step's sweeps ahead of time on a second CUDA stream and return at once:
+ * the host variant uploads them (pinned host memory), both run scan registration on them.  The following
+ * cm_pipeline_step_host / _dev call with the same `frames` pointer consumes that work instead of redoing it, so the
+ * host-to-device transfer and the (issue-bound) feature extraction of step k+1 overlap the (latency-bound) matching and map
+ * kernels of step k -- the nodelet receives the next PointCloud2 while the current one is being registered.  At most three
+ * sweeps may be in flight (one being consumed, two pending); the buffer must stay untouched until its step has run.  Results are identical either way. */
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols);
+int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols);
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                           cm_match_stats* stats);
 int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,

@@ -213,6 +213,10 @@ class Context:
         """Start the host-to-device upload of the NEXT step's sweeps (pinned (S, rows, cols, 4) float32 array)."""
         return self._check(self.L.cm_pipeline_prefetch_host(self.h, _ptr(frames), C.c_int(frames.shape[1]), C.c_int(frames.shape[2])))
 
+    def pipeline_prefetch_dev(self, frames_dev_ptr, rows, cols):
+        """Issue scan registration of the NEXT step's device-resident sweeps on the side stream."""
+        return self._check(self.L.cm_pipeline_prefetch_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols)))
+
     def pipeline_step_packed(self, frames, odoms_packed, mapped_out, stats_out):
         fr = frames
         return self._check(self.L.cm_pipeline_step_host(self.h, _ptr(fr), C.c_int(fr.shape[1]), C.c_int(fr.shape[2]),

@@ -67,12 +67,16 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   for (int g = 0; g < CM_MAX_GN_GROUPS; g++) {
     if (ctx->gn_stream[g]) { cudaStreamSynchronize(ctx->gn_stream[g]); cudaStreamDestroy(ctx->gn_stream[g]); }
     if (ctx->gn_join[g]) cudaEventDestroy(ctx->gn_join[g]);
   }
   if (ctx->gn_fork) cudaEventDestroy(ctx->gn_fork);
-  for (int i = 0; i < 2; i++) if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
+  for (int i = 0; i <= CM_PIPE_SLOTS; i++) {
+    if (ctx->pipe[i].done) cudaEventDestroy(ctx->pipe[i].done);
+    if (ctx->pipe[i].copied) cudaEventDestroy(ctx->pipe[i].copied);
+  }
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   delete ctx;
 }

@@ -56,11 +56,18 @@ struct cm_ctx {
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
   unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;
   // pipeline (scan registration -> mapping), cm_mapping.cu
-  cm::DeviceBuffer p_frames, p_pts[4], p_n;
-  // double-buffered sweep upload (cm_pipeline_prefetch_host): the NEXT step's sweeps travel on copy_stream while the
-  // current step computes
-  cm::DeviceBuffer p_prefetch[2]; const void* prefetch_src[2] = {nullptr, nullptr}; size_t prefetch_bytes[2] = {0, 0};
-  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done[2] = {nullptr, nullptr};
+  // Slot 2 is the synchronous path; slots 0 / 1 are filled ahead of time by cm_pipeline_prefetch_host / _dev: the NEXT
+  // step's sweeps are uploaded (host variant) and run through scan registration on side_stream while the current step's
+  // matching and map kernels run on `stream`.  Scan registration is issue-bound, matching is latency-bound: the two overlap.
+  struct PipeSlot {
+    cm::DeviceBuffer frames, pts[4], n;
+    cm::ScanRegistrationGpu scanreg;
+    const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
+    cudaEvent_t done = nullptr, copied = nullptr;
+  };
+#define CM_PIPE_SLOTS 3            // prefetch slots (one being consumed + two pending); pipe[CM_PIPE_SLOTS] is the synchronous path
+  PipeSlot pipe[CM_PIPE_SLOTS + 1];
+  cudaStream_t side_stream = nullptr, copy_stream = nullptr;   // scan registration ahead of time / sweep upload
   int p_cap = 0;
 };
 

@@ -287,25 +287,32 @@ int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point
 // Full pipeline: OrganisedScanRegistration::process -> (/laser_cloud_less_sharp, /laser_cloud_less_flat) ->
 // LaserMapping::process, for the S streams of the context.  (The reference routes the clouds through LaserOdometry,
 // which re-projects them to the sweep end; with instantaneous synthetic sweeps that projection is the identity.)
-static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped, cm_match_stats* stats) {
+// Stage 1 (scan registration into a slot's buffers) only depends on the sweep, so it can be issued ahead of time on the
+// side stream; stage 2 (mapping) consumes the slot on the context's main stream.
+static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* d_frames, int rows, int cols, cudaStream_t st) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   const int cap = rows * cols;
-  cudaStream_t st = ctx->stream;
-  for (int k = 0; k < 4; k++) ctx->p_pts[k].reserve((size_t)S * cap * sizeof(float4));
-  ctx->p_n.reserve(sizeof(int) * 7 * S);
+  for (int k = 0; k < 4; k++) slot.pts[k].reserve((size_t)S * cap * sizeof(float4));
+  slot.n.reserve(sizeof(int) * 7 * S);
   ScanRegLaunch L;
   memset(&L, 0, sizeof(L));
   L.nstreams = S; L.rows = rows; L.cols = cols; L.frames = d_frames;
   fill_scanreg_params(cfg, L);
   L.blind_sq_override = -1.f;
-  for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)ctx->p_pts[k].p; L.cap[k] = cap; }
-  L.out_n = (int*)ctx->p_n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
-  ctx->scanreg.run(L, st);
-  CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)ctx->p_n.p + 2 * S, (int*)ctx->p_n.p, S);
+  for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)slot.pts[k].p; L.cap[k] = cap; }
+  L.out_n = (int*)slot.n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
+  slot.scanreg.run(L, st);
+  CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)slot.n.p + 2 * S, (int*)slot.n.p, S);
+}
+
+static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int cols, const cm_iso* odom, cm_iso* mapped, cm_match_stats* stats) {
+  const int S = ctx->map_streams;
+  const int cap = rows * cols;
+  cudaStream_t st = ctx->stream;
   // feature-cloud sizes: needed on the host to size the frame voxel filters (and for the byte accounting)
   std::vector<int> n5(5 * S);
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5.data(), (const int*)ctx->p_n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5.data(), (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   int max_c = 1, max_s = 1;
   ctx->last_features = 0;
@@ -313,70 +320,85 @@ static int pipeline_dev(cm_ctx* ctx, const float4* d_frames, int rows, int cols,
     max_c = std::max(max_c, n5[s * 5 + 1]); max_s = std::max(max_s, n5[s * 5 + 3]);
     for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)n5[s * 5 + k];
   }
-  return mapping_process_dev(ctx, (const float4*)ctx->p_pts[1].p, cap, (const float4*)ctx->p_pts[3].p, cap, (const int*)ctx->p_n.p, max_c,
+  return mapping_process_dev(ctx, (const float4*)slot.pts[1].p, cap, (const float4*)slot.pts[3].p, cap, (const int*)slot.n.p, max_c,
                              max_s, odom, mapped, stats);
 }
 
-int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) {
+static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
-  if (!frames || rows <= 0 || cols <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (!frames || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
   try {
     cudaSetDevice(ctx->cfg.device);
-    const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
-    if (!ctx->copy_stream) {
-      CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; i++) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+    if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int si = -1;
+    for (int i = 0; i < CM_PIPE_SLOTS; i++) if (!ctx->pipe[i].src) { si = i; break; }
+    if (si < 0) return fail(ctx, CM_ERR_ARG, "three sweeps are already pending: run cm_pipeline_step on one of them first");
+    cm_ctx::PipeSlot& slot = ctx->pipe[si];
+    if (!slot.done) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    if (!slot.copied) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied, cudaEventDisableTiming));
+    // a free slot fed a step that has returned (the pipeline entries synchronise): nothing reads its buffers any more
+    const float4* d_frames = (const float4*)frames;
+    if (is_host) {
+      const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
+      slot.frames.reserve(bytes);
+      // upload on its own stream: the copy of sweep k+2 runs while sweep k+1 is in scan registration
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied, ctx->copy_stream));
+      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, slot.copied, 0));
+      d_frames = (const float4*)slot.frames.p;
     }
-    int slot = -1;
-    for (int i = 0; i < 2; i++) if (!ctx->prefetch_src[i]) { slot = i; break; }
-    if (slot < 0) return fail(ctx, CM_ERR_ARG, "two uploads are already pending: run cm_pipeline_step_host on one of them first");
-    // a free slot was the input of a step that has returned (the pipeline entries synchronise): nothing reads it any more
-    ctx->p_prefetch[slot].reserve(bytes);
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->p_prefetch[slot].p, frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->copy_done[slot], ctx->copy_stream));
-    ctx->prefetch_src[slot] = frames; ctx->prefetch_bytes[slot] = bytes;
+    pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->side_stream);
+    CM_CUDA_CHECK(ctx, cudaEventRecord(slot.done, ctx->side_stream));
+    slot.src = frames; slot.rows = rows; slot.cols = cols; slot.is_host = is_host;
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
   return CM_OK;
 }
 
-int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
-                          cm_match_stats* stats) {
+static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host, const cm_iso* odom, cm_iso* mapped,
+                         cm_match_stats* stats) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
   if (!frames || !odom || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
   if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
   try {
     cudaSetDevice(ctx->cfg.device);
-    const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
-    int slot = -1;
-    for (int i = 0; i < 2; i++) if (ctx->prefetch_src[i] == (const void*)frames && ctx->prefetch_bytes[i] == bytes) slot = i;
-    if (slot >= 0) {
-      // uploaded by cm_pipeline_prefetch_host: wait for that copy on the device, no second transfer
-      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[slot], 0));
-      const int rc = pipeline_dev(ctx, (const float4*)ctx->p_prefetch[slot].p, rows, cols, odom, mapped, stats);
-      ctx->prefetch_src[slot] = nullptr; ctx->prefetch_bytes[slot] = 0;
-      return rc;
+    for (int i = 0; i < CM_PIPE_SLOTS; i++) {
+      cm_ctx::PipeSlot& slot = ctx->pipe[i];
+      if (slot.src == frames && slot.rows == rows && slot.cols == cols && slot.is_host == is_host) {
+        // prefetched: its upload and scan registration were issued on the side stream; wait for them on the device
+        CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, slot.done, 0));
+        const int rc = pipeline_mapping(ctx, slot, rows, cols, odom, mapped, stats);
+        slot.src = nullptr;
+        return rc;
+      }
     }
-    ctx->p_frames.reserve(bytes);
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->p_frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return pipeline_dev(ctx, (const float4*)ctx->p_frames.p, rows, cols, odom, mapped, stats);
+    cm_ctx::PipeSlot& slot = ctx->pipe[CM_PIPE_SLOTS];
+    const float4* d_frames = (const float4*)frames;
+    if (is_host) {
+      const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
+      slot.frames.reserve(bytes);
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      d_frames = (const float4*)slot.frames.p;
+    }
+    pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->stream);
+    return pipeline_mapping(ctx, slot, rows, cols, odom, mapped, stats);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
 }
 
+int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch(ctx, frames, rows, cols, true); }
+int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch(ctx, d_frames, rows, cols, false); }
+int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
+                          cm_match_stats* stats) {
+  return pipeline_step(ctx, frames, rows, cols, true, odom, mapped, stats);
+}
 int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                          cm_match_stats* stats) {
-  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
-  if (!d_frames || !odom || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
-  if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
-  try {
-    cudaSetDevice(ctx->cfg.device);
-    return pipeline_dev(ctx, (const float4*)d_frames, rows, cols, odom, mapped, stats);
-  } catch (const CudaError& e) {
-    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
-  }
+  return pipeline_step(ctx, d_frames, rows, cols, false, odom, mapped, stats);
 }
 
 int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner, int cap_corner, const cm_point* surf,

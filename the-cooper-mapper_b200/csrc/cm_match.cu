@@ -575,7 +575,10 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // launches per Gauss-Newton iteration disappear.  Determinism: every sum has a fixed order (row -> 32-row group -> CTA).
 struct FusedArgs { double* partials; int* tickets; double* sums; };
 
-__global__ void __launch_bounds__(256) fit_solve_kernel(CorrArgs a, SolveArgs sa, FusedArgs f) {
+#ifndef CM_FIT_MINB
+#define CM_FIT_MINB 4
+#endif
+__global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a, SolveArgs sa, FusedArgs f) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
   if (st.done) return;
