@@ -28,6 +28,7 @@ enum { L_CORNER_SHARP = 1, L_SURFACE_FLAT = -1, L_ONESIDE_FLAT = 5, L_MESSY = 9,
 #define SR_THREADS 512
 #define SR_MAXR 8          // curvatureRegion upper bound
 #define SR_MAXREG 16       // nFeatureRegions upper bound
+#define SR_MAXCOLS 8192     // columns per ring the shared-memory layout can hold at most (scanreg_smem_bytes rejects more)
 
 // ------------------------------------------------------------------------------------------------------------
 // kernel 1: valid points per ring (OrganizedScanRegistration.cpp:115-123)
@@ -58,26 +59,25 @@ __global__ void __launch_bounds__(256) sr_count_kernel(const float4* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 // block helpers
 // ------------------------------------------------------------------------------------------------------------
-// exclusive scan of one int per thread; returns the prefix, *total = block sum.  scratch: >= 17 ints.
-__device__ __forceinline__ int block_scan_excl(int v, int* scratch, int* total) {
+// exclusive scan of one int per thread; returns the prefix, *total = block sum.  scratch: >= 32 ints, used as two
+// alternating halves (`phase` flips on every call, uniformly over the CTA) so that ONE barrier per scan is enough: every
+// warp adds up the warp totals itself, and the next scan writes the other half while slow warps still read this one.
+__device__ __forceinline__ int block_scan_excl(int v, int* scratch, int* total, int& phase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int x = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) scratch[warp] = x;
+  int* sc = scratch + 16 * phase;
+  phase ^= 1;
+  if (lane == 31) sc[warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    int w = lane < (SR_THREADS / 32) ? scratch[lane] : 0;
+  int w = lane < (SR_THREADS / 32) ? sc[lane] : 0;   // SR_THREADS / 32 = 16 warp totals
+  int incl = w;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-    if (lane < (SR_THREADS / 32)) scratch[lane] = w;   // inclusive warp totals
-  }
-  __syncthreads();
-  int base = warp ? scratch[warp - 1] : 0;
-  *total = scratch[SR_THREADS / 32 - 1];
-  int r = base + x - v;
-  __syncthreads();
-  return r;
+  for (int o = 1; o < 16; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  const int base = __shfl_sync(0xffffffffu, incl - w, warp);
+  *total = __shfl_sync(0xffffffffu, incl, SR_THREADS / 32 - 1);
+  return base + x - v;
 }
 
 // block-wide minimum of a 64-bit key; scratch: >= 16 u64.
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   signed char* state = reinterpret_cast<signed char*>(colv + 7 * cap);
   signed char* snap = state + cap; signed char* ev = snap + cap; signed char* lab = ev + cap;
   __shared__ int s_scan[32];
+  int scan_phase = 0;   // uniform over the CTA: every thread makes the same sequence of block_scan_excl calls
   __shared__ unsigned long long s_min[16];
   __shared__ int s_cnt[5];          // list lengths: sharp, lessSharp, flat, lessFlatRaw, (spare)
   __shared__ int s_misc[8];
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       bool ok = false;
       if (c < cols) { p = src[c]; ok = point_valid(p, prm.blind_sq); }
       int tot;
-      int pos = block_scan_excl(ok ? 1 : 0, s_scan, &tot);
+      int pos = block_scan_excl(ok ? 1 : 0, s_scan, &tot, scan_phase);
       if (ok) { int d = base + pos; px[d] = p.x; py[d] = p.y; pz[d] = p.z; pin[d] = p.w; colv[d] = (unsigned short)c; }
       base += tot;
     }
@@ -262,7 +263,11 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
 
   // ---- setScanBuffersFor (ScanRegistration.cpp:462-522), parallel replay ----------------------------------------
   // events of the main loop, i in [R, n-1-R): bit0-1 type (1 blind, 2 jump far->near "A", 3 jump "B"), bit2 ratio test
-  for (int i = tid; i < n; i += SR_THREADS) {
+  // s_evmask: one bit per cell "an event happened here" -- events are rare (range jumps, grazing incidence), so most cells
+  // find an empty window and skip the replay loop
+  __shared__ unsigned int s_evmask[SR_MAXCOLS / 32 + 2];
+  for (int i0 = 0; i0 < n; i0 += SR_THREADS) {
+    const int i = i0 + tid;
     int e = 0;
     if (i >= R && i < n - 1 - R) {
       if (cos_angle(px, py, pz, i, i + 1) < prm.blind_thr) e = 1;
@@ -277,8 +282,11 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
         }
       }
     }
-    ev[i] = (signed char)e;
+    if (i < n) ev[i] = (signed char)e;
+    const unsigned int bits = __ballot_sync(0xffffffffu, e != 0);
+    if ((tid & 31) == 0) s_evmask[i >> 5] = bits;     // i is a multiple of 32 here; words past n are zero
   }
+  if (tid == 0) s_evmask[((n + 31) >> 5)] = 0u;
   if (tid < R) {   // head / tail blind tests (:468-484): R + 1 cells each
     s_misc[tid] = 0;
   }
@@ -292,23 +300,32 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   __syncthreads();
   for (int c = tid; c < n; c += SR_THREADS) {
     int st = 0;
-    for (int i = 0; i < R; i++) {
-      int f = s_misc[i];
-      if ((f & 1) && c >= i && c <= i + R) st = P_BLIND_BLOCK;
-      if ((f & 2) && c >= n - 1 - i - R && c <= n - 1 - i) st = P_BLIND_BLOCK;
+    if (c <= 2 * R || c >= n - 1 - 2 * R) {   // only the first / last 2R+1 cells can be hit by the head / tail tests
+      for (int i = 0; i < R; i++) {
+        int f = s_misc[i];
+        if ((f & 1) && c >= i && c <= i + R) st = P_BLIND_BLOCK;
+        if ((f & 2) && c >= n - 1 - i - R && c <= n - 1 - i) st = P_BLIND_BLOCK;
+      }
     }
     int lo = c - R; if (lo < R) lo = R;
     int hi = c + R - 1; if (hi > n - 2 - R) hi = n - 2 - R;
-    for (int i = lo; i <= hi; i++) {
-      int e = ev[i];
-      int type = e & 3;
-      if (type == 1) { if (c >= i - R + 1 && c <= i + R) st = P_BLIND_BLOCK; }
-      else if (type == 2) {
-        if (c == i + 1 && st > P_NEAR_BLOCK && (e & 4)) st = P_EDGE_BROKEN;
-        if (c >= i - R + 1 && c <= i) st = P_NEAR_BLOCK;
-      } else if (type == 3) {
-        if (c == i && st > P_NEAR_BLOCK && (e & 4)) st = P_EDGE_BROKEN;
-        if (c >= i + 1 && c <= i + R) st = P_NEAR_BLOCK;
+    bool any = false;
+    if (lo <= hi) {   // bits lo..hi of the event bitmap (the window spans at most two words: 2R <= 16)
+      const unsigned long long w2 = (unsigned long long)s_evmask[lo >> 5] | ((unsigned long long)s_evmask[(lo >> 5) + 1] << 32);
+      any = ((w2 >> (lo & 31)) & ((1ull << (hi - lo + 1)) - 1ull)) != 0ull;
+    }
+    if (any) {
+      for (int i = lo; i <= hi; i++) {
+        int e = ev[i];
+        int type = e & 3;
+        if (type == 1) { if (c >= i - R + 1 && c <= i + R) st = P_BLIND_BLOCK; }
+        else if (type == 2) {
+          if (c == i + 1 && st > P_NEAR_BLOCK && (e & 4)) st = P_EDGE_BROKEN;
+          if (c >= i - R + 1 && c <= i) st = P_NEAR_BLOCK;
+        } else if (type == 3) {
+          if (c == i && st > P_NEAR_BLOCK && (e & 4)) st = P_EDGE_BROKEN;
+          if (c >= i + 1 && c <= i + R) st = P_NEAR_BLOCK;
+        }
       }
     }
     state[c] = (signed char)st;
@@ -366,11 +383,12 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int rj = c < n ? region_of(c) : -1;
       const bool isnf = rj >= 0 && !(curv[c] < prm.curv_thr);
       int tot;
-      const int pos = block_scan_excl(isnf ? 1 : 0, s_scan, &tot);
+      const int pos = block_scan_excl(isnf ? 1 : 0, s_scan, &tot, scan_phase);
       if (isnf) nfl[total + pos] = (unsigned short)c;
       if (rj >= 0 && c == reg_sp[rj]) nf_begin[rj] = total + pos;
       total += tot;
     }
+    __syncthreads();   // nf_begin[] of the last chunk (the scan itself has a single barrier)
     if (tid == 0) {
       nf_begin[NR] = total;
       for (int j = NR - 1; j >= 0; j--) if (reg_ep[j] < reg_sp[j]) nf_begin[j] = nf_begin[j + 1];   // skipped regions are empty
@@ -411,11 +429,52 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     }
     if (lane == 0) p1_begin[NR] = np1;
   } else {
-    for (int i = tid - 32; i < m_all; i += SR_THREADS - 32) {
+    // pointClassify(c) looks at the window {c, c-1, .., c-R} and at {c+R, .., c} -- the second one IS the first window of
+    // point c+R, summed in the same order, so every window is evaluated once: by its own point when that point is a
+    // candidate too, else by the point R cells before it.  Results per window position: line flag + direction.
+    float2* wxy = reinterpret_cast<float2*>(key);            // `key` and the four index lists are not in use yet
+    float* wz = reinterpret_cast<float*>(lst[0]);            // lst[0..1]
+    signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // 0 not a candidate, 2 candidate (pending), 1 line, 3 no line
+    const int NT = SR_THREADS - 32, t = tid - 32;
+    for (int c = t; c < n; c += NT) wfl[c] = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
+    for (int i = t; i < m_all; i += NT) wfl[nfl[i]] = 2;
+    asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
+    for (int i = t; i < m_all; i += NT) {
       const int c = nfl[i];
-      lab[c] = (signed char)point_classify(px, py, pz, c, prm);
-      key[i] = ((unsigned long long)__float_as_uint(curv[c]) << 32) | (unsigned int)c;
+      float v[3];
+      const bool own_fwd = wfl[c + R] == 0;                  // c+R is not a candidate: this thread owns its window
+      const bool l1 = classify_window(px, py, pz, c, R, false, v);
+      if (l1) { wxy[c] = make_float2(v[0], v[1]); wz[c] = v[2]; }
+      wfl[c] = l1 ? 1 : 3;
+      if (own_fwd) {
+        const bool l2 = classify_window(px, py, pz, c + R, R, false, v);
+        if (l2) { wxy[c + R] = make_float2(v[0], v[1]); wz[c + R] = v[2]; }
+        wfl[c + R] = l2 ? 1 : 3;
+      }
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
+    for (int i = t; i < m_all; i += NT) {                    // ScanRegistration.cpp:651-665
+      const int c = nfl[i];
+      const bool line1 = wfl[c] == 1, line2 = wfl[c + R] == 1;
+      int l = L_MESSY;
+      if (line1 || line2) l = L_ONESIDE_FLAT;
+      if (line1 && line2) {
+        const float2 a = wxy[c], b = wxy[c + R];
+        const float az = wz[c], bz = wz[c + R];
+        float ab = a.x * b.x + a.y * b.y + az * bz;
+        float disab = sqrtf(a.x * a.x + a.y * a.y + az * az) * sqrtf(b.x * b.x + b.y * b.y + bz * bz);
+        float diff = ab / disab;
+        if ((double)diff < prm.cos175 || (double)diff > prm.cos5) l = L_SURFACE_FLAT;
+        else if ((double)diff > prm.cos135 && (double)diff < prm.cos45) l = L_CORNER_SHARP;
+      }
+      lab[c] = (signed char)l;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m_all; i += SR_THREADS) {
+    const int c = nfl[i];
+    key[i] = ((unsigned long long)__float_as_uint(curv[c]) << 32) | (unsigned int)c;
   }
   __syncthreads();
   // ---- descending (curvature, index) order inside every region: rank by counting -------------------------------------
@@ -439,9 +498,10 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int rj = c < n ? region_of(c) : -1;
       const bool isflat = rj >= 0 && (curv[c] < prm.curv_thr);
       const bool isedge = rj >= 0 && (snap[c] == P_EDGE_BROKEN);
-      int a1, a2;
-      const int p1 = block_scan_excl(isflat ? 1 : 0, s_scan, &a1);
-      const int p2 = block_scan_excl(isedge ? 1 : 0, s_scan, &a2);
+      // both counters in one scan: low / high 16 bits (a ring has < 65536 cells)
+      int a12;
+      const int p12 = block_scan_excl((isflat ? 1 : 0) | (isedge ? 0x10000 : 0), s_scan, &a12, scan_phase);
+      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16, a1 = a12 & 0xFFFF, a2 = a12 >> 16;
       if (c < n) { pfa[c] = (unsigned short)(t1 + p1); pfb[c] = (unsigned short)(t2 + p2); }
       if (rj >= 0 && c == reg_sp[rj]) { start2[0][rj] = t1 + p1; start2[1][rj] = t2 + p2; }
       if (isflat) atomicAdd(&cnt2[3][rj], 1);
@@ -461,9 +521,9 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int rj = in ? region_of(c) : -1;
       const bool is_corner = in && l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN;
       const bool is_surf = in && (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT);
-      int a1, a2;
-      const int p1 = block_scan_excl(is_corner ? 1 : 0, s_scan, &a1);
-      const int p2 = block_scan_excl(is_surf ? 1 : 0, s_scan, &a2);
+      int a12;
+      const int p12 = block_scan_excl((is_corner ? 1 : 0) | (is_surf ? 0x10000 : 0), s_scan, &a12, scan_phase);
+      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16, a1 = a12 & 0xFFFF, a2 = a12 >> 16;
       if (in) { qfa[i] = (unsigned short)(t1 + p1); qfb[i] = (unsigned short)(t2 + p2); }
       if (in && i == nf_begin[rj]) { start3[0][rj] = t1 + p1; start3[1][rj] = t2 + p2; }
       if (is_corner) atomicAdd(&cnt3[1][rj], 1);
@@ -622,7 +682,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int i = i0 + tid;
       const bool rs = i < nlf && (i == 0 || vidx[i] != vidx[i - 1]);
       int tot;
-      const int pos = block_scan_excl(rs ? 1 : 0, s_scan, &tot);
+      const int pos = block_scan_excl(rs ? 1 : 0, s_scan, &tot, scan_phase);
       if (rs) run_start[nruns + pos] = (unsigned short)i;
       nruns += tot;
     }
@@ -655,7 +715,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int r = r0 + tid;
       const bool head = r < nruns && (r == 0 || (key[r] >> 32) != (key[r - 1] >> 32));
       int tot;
-      const int pos = block_scan_excl(head ? 1 : 0, s_scan, &tot);
+      const int pos = block_scan_excl(head ? 1 : 0, s_scan, &tot, scan_phase);
       if (head) {
         const unsigned int v = (unsigned int)(key[r] >> 32);
         float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
