@@ -57,9 +57,12 @@ __host__ __device__ __forceinline__ unsigned long long pack_cell(int x, int y, i
   return ((unsigned long long)(x + (long long)B) & 0x1FFFFF) | (((unsigned long long)(y + (long long)B) & 0x1FFFFF) << 21) |
          (((unsigned long long)(z + (long long)B) & 0x1FFFFF) << 42);
 }
+// 32-bit mix of the two key halves (the GPU has no 64-bit multiplier: a 64-bit finaliser costs ~3x the instructions and
+// the probe sequence is 15 % of the search kernel); lattice coordinates differ in their low bits, which both rounds spread
 __host__ __device__ __forceinline__ unsigned int hash_cell(unsigned long long k) {
-  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-  return (unsigned int)k;
+  unsigned int h = ((unsigned int)k * 0x9E3779B1u) ^ (((unsigned int)(k >> 32) + 0x7F4A7C15u) * 0x85EBCA77u);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
 }
 
 __device__ __forceinline__ bool grid_probe(const GridView& g, int x, int y, int z, unsigned int* start, unsigned int* count) {
