@@ -131,3 +131,38 @@ def test_config5_sparse_tilted_rplidar(cmb, oracle, synth, scene_kind):
         seen.add((stats[0]["status"], bool(stats[0]["degenerate"])))
     assert (cmb.CM_TOO_FEW_REF, False) in seen                              # first frame: empty map
     ctx.close()
+
+
+def test_config1_vlp16_full_chain(cmb, oracle, synth):
+    """BASELINE config 1 (the reference's CPU-runnable case): a VLP-16 16 x 1800 sequence through scan registration ->
+    laserOdometry -> laserMapping, every stage on the GPU, against the same chain of the oracle."""
+    sc = synth.make_scene(seed=0x5EED0001 & 0xFFFF, extent=60.0, n_boxes=24, n_poles=20)
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    c_sr = cmb.Context()                       # stage 1
+    c_od = cmb.Context(); lo = cmb.LaserOdometry(ctx=c_od)          # stage 2
+    c_mp = cmb.Context(**cfg); c_mp.mapping_create(1, 100000, 800000)   # stage 3
+    oo = oracle.Odometry()
+    om = oracle.Mapping(map_params=dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4))
+    NF = 25
+    path = []
+    for k, (R, t) in enumerate(synth.trajectory(NF, speed=0.1, yaw_amp=0.02)):      # 1 m/s at 10 Hz
+        fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=0x1000 + k)
+        g = c_sr.scanreg_organised(fr)
+        o = oracle.scanreg_organised(fr)
+        for name in ("sharp", "lessSharp", "flat", "lessFlat"):
+            assert _same(g[name], o[name]), (k, name)
+        go = c_od.odometry_process(g["sharp"], g["lessSharp"], g["flat"], g["lessFlat"])
+        oo_ = oo.process(o["sharp"], o["lessSharp"], o["flat"], o["lessFlat"])
+        assert np.array_equal(go["R"], oo_["R"]) and np.array_equal(go["t"], oo_["t"]), k
+        assert _same(go["corner_last"], oo_["corner_last"]) and _same(go["surf_last"], oo_["surf_last"]), k
+        isos, stats = c_mp.mapping_process([(go["R"], go["t"])], [go["corner_last"]], [go["surf_last"]])
+        oR, ot, ost = om.process(oo_["R"], oo_["t"], oo_["corner_last"], oo_["surf_last"])
+        assert stats[0]["iterations"] == ost["iterations"], (k, stats[0], ost)
+        assert np.max(np.abs(isos[0][1] - ot)) <= 1e-4 and np.max(np.abs(isos[0][0] - oR)) <= 1e-5      # north-star tolerance
+        assert np.array_equal(isos[0][0], oR) and np.array_equal(isos[0][1], ot), k
+        path.append(isos[0][1].copy())
+    for cls, which in ((0, 4), (1, 5)):
+        assert _same(c_mp.map_export_sorted(0, cls)[0], om.cloud(which))
+    assert np.linalg.norm(path[-1] - path[0]) > 1.0          # the chain did track the motion
+    for c in (c_sr, c_od, c_mp):
+        c.close()

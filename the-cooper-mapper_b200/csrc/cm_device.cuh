@@ -244,6 +244,9 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
   return true;
 }
 
+#ifndef CM_KNN_UNROLL
+#define CM_KNN_UNROLL 4      // candidate loads in flight per thread and loop iteration
+#endif
 // Level 0 of one query (per thread).  Returns true when the list is not yet provably final (levels >= 1 needed).
 // The 8 cells are probed together; their point ranges are staged in shared memory with the squared lower bound of
 // the distance from the query to the cell's box, own cell first, then face / edge / corner neighbours.  A range is
@@ -296,12 +299,12 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
       continue;
     }
     const unsigned int left = r.y - j0;
-    float4 p[4];
+    float4 p[CM_KNN_UNROLL];
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < CM_KNN_UNROLL; u++)
       if ((unsigned int)u < left) p[u] = __ldg(g.pts + r.x + j0 + u);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < CM_KNN_UNROLL; u++) {
       if ((unsigned int)u < left) {
         if (cand_ok(g, c.filt, p[u])) {
           float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
@@ -311,8 +314,8 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
         }
       }
     }
-    if (ncand) scanned += left < 4u ? left : 4u;
-    j0 += 4;
+    if (ncand) scanned += left < (unsigned int)CM_KNN_UNROLL ? left : (unsigned int)CM_KNN_UNROLL;
+    j0 += CM_KNN_UNROLL;
     if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
   }
   if (ncand) *ncand = scanned;
