@@ -66,6 +66,9 @@ int cm_ctx_create(const cm_config* cfg, cm_ctx** out) {
 void cm_ctx_destroy(cm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   for (int g = 0; g < CM_MAX_GN_GROUPS; g++) {

@@ -25,7 +25,10 @@ struct cm_ctx {
   cm::DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
   cm::DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_slots, d_sums, d_trace, d_nn;
   cm::GridStorage grid_a, grid_b;
-  cm::VoxelFilter voxel;
+  cm::VoxelFilter voxel, voxel_aux;
+  // aux_stream: the corner-class half of the mapping stage's voxel filters and map insertion runs here, concurrently with the
+  // surf-class half on `stream` (both are chains of small latency-bound kernels; the corner chain hides behind the surf chain)
+  cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   cm::ScanRegistrationGpu scanreg;
   cm::DeviceBuffer d_tags, d_l_ds[4];
   cm::DeviceBuffer d_frames, d_sr_pts[4], d_sr_idx[4], d_sr_n, d_sr_cloud, d_sr_ccurv, d_sr_picked, d_sr_curv, d_sr_label, d_sr_range;

@@ -170,7 +170,8 @@ struct DeviceMap {
   int nstreams = 0;
   MapConfig cfg;
   DeviceBuffer entries[2], cellcap[2], pending_cnt[2], pts[2], cube_count[2], cursor[2], dev[2], views[2];
-  DeviceBuffer windows, flags, n_pending, world, keys_a, keys_b, vals_a, vals_b, pending, temp;
+  DeviceBuffer windows, flags;
+  DeviceBuffer n_pending[2], world[2], keys_a[2], keys_b[2], vals_a[2], vals_b[2], pending[2];   // insert scratch per class: the two classes may run on different streams
   unsigned int table_cap[2] = {0, 0}, pool_cap[2] = {0, 0};
   void create(int nstreams, const MapConfig& c, cudaStream_t stream);
   void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream);   // also refreshes the GridViews

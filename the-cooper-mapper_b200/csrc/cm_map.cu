@@ -298,7 +298,7 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
   }
   windows.reserve(sizeof(CubeWindow) * nstreams);
   flags.reserve(sizeof(int) * 8);
-  n_pending.reserve(sizeof(unsigned int));
+  for (int c = 0; c < 2; c++) n_pending[c].reserve(sizeof(unsigned int));
   cudaMemsetAsync(flags.p, 0, sizeof(int) * 8, stream);
   cudaStreamSynchronize(stream);   // h goes out of scope
 }
@@ -315,22 +315,22 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   if (cap <= 0) return;
   if (max_n <= 0 || max_n > cap) max_n = cap;   // host-known upper bound of d_n[s]
   const size_t n = (size_t)nstreams * max_n;
-  world.reserve(n * sizeof(float4));
+  world[cls].reserve(n * sizeof(float4));
   unsigned int gcap = 1024;
   while ((size_t)gcap < 2 * n) gcap <<= 1;
-  keys_a.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4); keys_b.reserve((size_t)gcap * sizeof(GroupEntry));
-  pending.reserve(n * sizeof(PendingAdd));
+  keys_a[cls].reserve(n * 8); vals_a[cls].reserve(n * 4); vals_b[cls].reserve(n * 4); keys_b[cls].reserve((size_t)gcap * sizeof(GroupEntry));
+  pending[cls].reserve(n * sizeof(PendingAdd));
   const unsigned int nb = (unsigned int)((n + 255) / 256);
-  cudaMemsetAsync(n_pending.p, 0, sizeof(unsigned int), stream);
-  CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b.p, gcap);
-  CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world.p,
-            (unsigned long long*)keys_a.p, (unsigned int*)vals_a.p, (int*)vals_b.p, (GroupEntry*)keys_b.p, gcap - 1, (int*)flags.p);
-  CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a.p, (const unsigned int*)vals_a.p, (const int*)vals_b.p,
-            (const GroupEntry*)keys_b.p, n, (const float4*)world.p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending.p,
-            (unsigned int*)n_pending.p, (unsigned int)n, (int*)flags.p);
-  CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
+  cudaMemsetAsync(n_pending[cls].p, 0, sizeof(unsigned int), stream);
+  CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b[cls].p, gcap);
+  CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world[cls].p,
+            (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p);
+  CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a[cls].p, (const unsigned int*)vals_a[cls].p, (const int*)vals_b[cls].p,
+            (const GroupEntry*)keys_b[cls].p, n, (const float4*)world[cls].p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending[cls].p,
+            (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p);
+  CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
             (MapClassDev*)dev[cls].p, (int*)flags.p);
-  CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending.p, (const unsigned int*)n_pending.p, (unsigned int)n,
+  CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
             (MapClassDev*)dev[cls].p);
 }
 

@@ -172,8 +172,18 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   ctx->d_flag.reserve(sizeof(int));
   CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
   int* d_nds = (int*)ctx->m_n_ds.p;
-  ctx->voxel.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, st);
+  if (!ctx->aux_stream) {
+    CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+  }
+  cudaStream_t aux = ctx->aux_stream;
+  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
+  CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
+  ctx->voxel_aux.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux);
+  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
   ctx->voxel.run(S, d_surf, d_n + S, cap_s, max_in_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st);
+  CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
   std::vector<int> nds(2 * S);
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
@@ -220,8 +230,12 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   }
   // featureMapUpdate (commented out in LaserLocalization::process, LaserLocalization.cpp:186)
   if (!localise) {
-    ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, st);
+    CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
+    CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
+    ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, aux);
+    CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
     ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+    CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   }
   // results
   std::vector<MatchState> hs(S);

@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
           for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
           if (best == 0xFFFFFFFFFFFFFFFFull) break;
           const int c = (int)(best & 0xFFFFFFFFu);
+          __syncwarp();   // every lane has finished reading state[] (the shuffles order execution, this orders memory)
           if (lane <= 2 * R) state[c - R + lane] = P_SURF_PICKED_NEAR;   // markAsPicked: c-R .. c+R
           if (lane == 0 && np1 < SR_MAXREG * 8) p1buf[np1] = (unsigned short)c;
           np1++;
@@ -434,16 +435,17 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     // candidate too, else by the point R cells before it.  Results per window position: line flag + direction.
     float2* wxy = reinterpret_cast<float2*>(key);            // `key` and the four index lists are not in use yet
     float* wz = reinterpret_cast<float*>(lst[0]);            // lst[0..1]
-    signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // 0 not a candidate, 2 candidate (pending), 1 line, 3 no line
+    signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // window result: 1 line, 3 no line   (first half of lst[2])
+    signed char* wcand = wfl + cap;                               // 1: the cell is a candidate itself (second half of lst[2])
     const int NT = SR_THREADS - 32, t = tid - 32;
-    for (int c = t; c < n; c += NT) wfl[c] = 0;
+    for (int c = t; c < n; c += NT) wcand[c] = 0;
     asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
-    for (int i = t; i < m_all; i += NT) wfl[nfl[i]] = 2;
+    for (int i = t; i < m_all; i += NT) wcand[nfl[i]] = 1;
     asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
     for (int i = t; i < m_all; i += NT) {
       const int c = nfl[i];
       float v[3];
-      const bool own_fwd = wfl[c + R] == 0;                  // c+R is not a candidate: this thread owns its window
+      const bool own_fwd = wcand[c + R] == 0;                // c+R is not a candidate: this thread owns its window
       const bool l1 = classify_window(px, py, pz, c, R, false, v);
       if (l1) { wxy[c] = make_float2(v[0], v[1]); wz[c] = v[2]; }
       wfl[c] = l1 ? 1 : 3;
