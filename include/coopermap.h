@@ -251,6 +251,7 @@ int cm_timer_record(cm_ctx* ctx, int which);
 int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms);
 int cm_prof_enable(cm_ctx* ctx, int on);
 int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches);
+int cm_prof_drain_scanreg(cm_ctx* ctx, double* kernel_ms, int* launches);   /* same for the sr_ring_kernel launches */
 int cm_last_step_counters(cm_ctx* ctx, unsigned long long* out4);
 /* development aid: bracket EVERY kernel launch with CUDA events and report "name total_us launches" lines (sorted) */
 int cm_timeline_enable(cm_ctx* ctx, int on);

@@ -284,6 +284,11 @@ class Context:
         self._check(self.L.cm_prof_drain(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def prof_drain_scanreg(self):
+        ms = C.c_double(0); n = C.c_int(0)
+        self._check(self.L.cm_prof_drain_scanreg(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def timeline_enable(self, on):
         self._check(self.L.cm_timeline_enable(self.h, C.c_int(int(on))))
 

@@ -54,7 +54,7 @@ struct cm_ctx {
   // sharded-map matching (cm_shard_*): persistent grids in grid_a / grid_b
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
-  cm::KernelProfiler prof;
+  cm::KernelProfiler prof, prof_sr;   // search_kernel + search_hard_kernel / sr_ring_kernel launches of the pipeline
   cudaEvent_t timer[2] = {nullptr, nullptr};
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
   unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;

@@ -182,6 +182,7 @@ struct DeviceMap {
 
 // K1/K2: scan registration for organised sweeps (cm_scanreg.cu)
 struct ScanRegLaunch {
+  KernelProfiler* prof;                       // optional: event pair around sr_ring_kernel (bench.py's per-kernel timing)
   int nstreams, rows, cols;
   const float4* frames;                       // device [S][rows][cols]
   const float* tags;                          // optional device [S][rows][cols] (raw-sweep front end), else NULL

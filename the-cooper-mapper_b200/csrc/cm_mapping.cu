@@ -314,6 +314,7 @@ static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* 
   L.nstreams = S; L.rows = rows; L.cols = cols; L.frames = d_frames;
   fill_scanreg_params(cfg, L);
   L.blind_sq_override = -1.f;
+  L.prof = &ctx->prof_sr;
   for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)slot.pts[k].p; L.cap[k] = cap; }
   L.out_n = (int*)slot.n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
   slot.scanreg.run(L, st);
@@ -497,7 +498,15 @@ int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_
   }
   return CM_OK;
 }
-int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = on != 0; return CM_OK; }
+int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = ctx->prof_sr.enabled = on != 0; return CM_OK; }
+int cm_prof_drain_scanreg(cm_ctx* ctx, double* kernel_ms, int* launches) {
+  if (!ctx || !kernel_ms) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->side_stream));
+  *kernel_ms = ctx->prof_sr.drain_ms(launches);
+  return CM_OK;
+}
 int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches) {
   if (!ctx || !kernel_ms) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);

@@ -821,7 +821,9 @@ void ScanRegistrationGpu::run(const ScanRegLaunch& L, cudaStream_t stream) {
     cudaFuncSetAttribute(sr_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
+  if (L.prof) L.prof->begin(stream);
   CM_LAUNCH(sr_ring_kernel, grid, SR_THREADS, smem, stream, a);
+  if (L.prof) L.prof->end(stream);
   AssembleArgs as;
   for (int l = 0; l < 4; l++) {
     as.ring_pts[l] = (const float4*)ring_pts[l].p; as.ring_idx[l] = L.want_idx ? (const int*)ring_idx[l].p : nullptr;
