@@ -166,3 +166,63 @@ def test_config1_vlp16_full_chain(cmb, oracle, synth):
     assert np.linalg.norm(path[-1] - path[0]) > 1.0          # the chain did track the motion
     for c in (c_sr, c_od, c_mp):
         c.close()
+
+
+def test_knn5_full_size_vs_nanoflann(cmb, oracle, synth):
+    """Exact 5-NN at the headline size: the ~1M-point surf map of the bench workload, 20,000 queries, against the reference's
+    own KD-tree (nanoflann) -- neighbour sets and float distances identical, both map cell sizes (surf and corner default)."""
+    bench = importlib.import_module("bench")
+    sc = synth.make_scene(seed=bench.SEED & 0xFFFF, extent=125.0, n_boxes=44, n_poles=40)
+    _, ms = synth.sample_map(sc, 0.4, seed=2)
+    assert len(ms) > 900000
+    rng = np.random.default_rng(9)
+    q = ms[rng.integers(0, len(ms), 20000), :3] + rng.normal(0, 0.4, (20000, 3)).astype(np.float32)
+    q[:500] += 30.0                                                     # far from every surface: gate rejects
+    if not oracle.lib().has_nanoflann:
+        pytest.skip("oracle/_ref/libcm_ref_nanoflann.so not built")
+    ni, nd = oracle.knn(ms, q, 5, nanoflann=True)
+    ok = nd[:, 4] < 5.0
+    assert 15000 < ok.sum() < 20000
+    ctx = cmb.Context()
+    for cell in (1.6, 3.2):
+        idx, d2 = ctx.knn5(ms, q, cell=cell, gate=5.0)
+        assert np.array_equal(d2[ok], nd[ok])                           # bit-exact distances, ascending
+        assert np.array_equal(np.sort(idx[ok], 1), np.sort(ni[ok], 1))  # same neighbour sets
+        assert np.all(d2[~ok][:, 4] >= 5.0)
+    ctx.close()
+
+
+def test_prefetched_steps_equal_synchronous_steps(cmb, synth):
+    """cm_pipeline_prefetch_host / _dev (upload + scan registration issued ahead on side streams) change nothing but timing."""
+    sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    S, NF = 3, 5
+    frames, odoms = [], []
+    for k in range(NF):
+        fr, od = [], []
+        for s in range(S):
+            R, t = list(synth.trajectory(NF, seed=s, speed=0.4))[k]
+            fr.append(synth.simulate_scan(sc, R, t, "VLP-16", seed=900 + 10 * s + k, cols=512))
+            od.append((R.astype(np.float32), t.astype(np.float32)))
+        frames.append(np.ascontiguousarray(np.stack(fr), np.float32)); odoms.append(od)
+    a = cmb.Context(**cfg); a.mapping_create(S, 60000, 300000)
+    b = cmb.Context(**cfg); b.mapping_create(S, 60000, 300000)
+    mapped = np.empty((S, 12), np.float32); stats = (cmb.MatchStats * S)()
+    b.pipeline_prefetch(frames[0]); b.pipeline_prefetch(frames[1])
+    for k in range(NF):
+        ref_isos, ref_stats = a.pipeline_step(frames[k], odoms[k])
+        if k + 2 < NF:
+            b.pipeline_prefetch(frames[k + 2])
+        b.pipeline_step_packed(frames[k], b._pack_isos(odoms[k]), mapped, stats)
+        for s in range(S):
+            assert np.array_equal(mapped[s, :9].reshape(3, 3), ref_isos[s][0]) and np.array_equal(mapped[s, 9:], ref_isos[s][1]), (k, s)
+            assert stats[s].iterations == ref_stats[s]["iterations"]
+    for s in range(S):
+        for cls in (0, 1):
+            assert _same(a.map_export_sorted(s, cls)[0], b.map_export_sorted(s, cls)[0])
+    # at most three sweeps in flight
+    for k in range(3):
+        b.pipeline_prefetch(frames[k])
+    with pytest.raises(cmb.CoopermapError):
+        b.pipeline_prefetch(frames[3])
+    a.close(); b.close()
