@@ -70,6 +70,7 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
   if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->copy_stream2) { cudaStreamSynchronize(ctx->copy_stream2); cudaStreamDestroy(ctx->copy_stream2); }
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   for (int g = 0; g < CM_MAX_GN_GROUPS; g++) {
     if (ctx->gn_stream[g]) { cudaStreamSynchronize(ctx->gn_stream[g]); cudaStreamDestroy(ctx->gn_stream[g]); }
@@ -79,6 +80,7 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   for (int i = 0; i <= CM_PIPE_SLOTS; i++) {
     if (ctx->pipe[i].done) cudaEventDestroy(ctx->pipe[i].done);
     if (ctx->pipe[i].copied) cudaEventDestroy(ctx->pipe[i].copied);
+    if (ctx->pipe[i].copied2) cudaEventDestroy(ctx->pipe[i].copied2);
   }
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   delete ctx;

@@ -43,6 +43,7 @@ struct cm_ctx {
   // Gauss-Newton stream groups of the batched mapping stage (cm_mapping.cu)
 #define CM_MAX_GN_GROUPS 8
   cudaStream_t gn_stream[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_join[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_fork = nullptr;
+  cm::MatchGraphCache match_graphs;                 // CUDA graphs of the mapping stage's Gauss-Newton loop
   cm::HardQueue hardq;                              // deferred hard 5-NN queries of the current match (cm_match.cu)
   // scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members
   bool odom_inited = false;
@@ -63,14 +64,17 @@ struct cm_ctx {
   // step's sweeps are uploaded (host variant) and run through scan registration on side_stream while the current step's
   // matching and map kernels run on `stream`.  Scan registration is issue-bound, matching is latency-bound: the two overlap.
   struct PipeSlot {
-    cm::DeviceBuffer frames, pts[4], n;
+    cm::DeviceBuffer frames, pts[4], n, box;   // box: [2][S] VoxBox of the less-sharp / less-flat clouds (frame voxel filters)
     cm::ScanRegistrationGpu scanreg;
     const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
-    cudaEvent_t done = nullptr, copied = nullptr;
+    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr;
+    size_t frames_valid = 0;
   };
 #define CM_PIPE_SLOTS 3            // prefetch slots (one being consumed + two pending); pipe[CM_PIPE_SLOTS] is the synchronous path
   PipeSlot pipe[CM_PIPE_SLOTS + 1];
-  cudaStream_t side_stream = nullptr, copy_stream = nullptr;   // scan registration ahead of time / sweep upload
+  // scan registration ahead of time / sweep upload.  The upload is split over TWO copy streams: one host-to-device stream
+  // reaches 36.6 GB/s on the B200 boxes measured, two concurrent ones 53.6 GB/s (tools/h2d_bandwidth.py)
+  cudaStream_t side_stream = nullptr, copy_stream = nullptr, copy_stream2 = nullptr;
   int p_cap = 0;
 };
 

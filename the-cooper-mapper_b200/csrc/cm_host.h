@@ -125,6 +125,17 @@ inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   m.partials = (double*)partials.p; m.tickets = (int*)tickets.p;
 }
 void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* prof = nullptr);
+// The same launch sequence replayed from a CUDA graph: the <= 10 x (search, hard-search, fit+solve) kernels of one match are
+// captured once per distinct argument set (buffers are grow-only, so the set is stable after the first steps) and then
+// submitted with ONE call -- the Gauss-Newton loop no longer pays a host launch per kernel, which matters most while the
+// PCIe link is busy with the next sweeps (tools/pcie_interference.py: +25 % step time with per-kernel launches).
+struct MatchGraphCache {
+  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; };
+  std::vector<Entry> entries;
+  bool launch(const MatchLaunch& m, cudaStream_t stream);   // false: capture failed, nothing was launched
+  void clear();
+  ~MatchGraphCache() { clear(); }
+};
 // the same with the streams split into `ngroups` groups whose iteration loops run concurrently on gs[0..ngroups)
 void launch_match_groups(const MatchLaunch& m, cudaStream_t stream, int ngroups, cudaStream_t* gs, cudaEvent_t fork, cudaEvent_t* join,
                          KernelProfiler* prof = nullptr);
@@ -145,11 +156,22 @@ void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float*
 
 // K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes
 // out[s*cap_out .. +n_out[s]).
+struct VoxBox {          // per segment: PCL's min_b_ / divb_mul_ of the cloud's bounding box
+  int minb[3];
+  int mul1, mul2;        // divb_mul_[1], divb_mul_[2]
+  int passthrough;       // index overflow: copy input to output
+  int nfinite;
+  long long cells;       // dx * dy * dz: the voxel index of the segment is < cells
+};
+void launch_vox_bbox(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, VoxBox* d_box, cudaStream_t stream);
+int vox_index_bits(long long cells);
 struct VoxelFilter {
   DeviceBuffer box, keys_a, keys_b, vals_a, vals_b, flags, rank, seg_first, temp;
-  // max_n: host-known upper bound of n_in[s] (<= 0: cap_in)
+  // max_n: host-known upper bound of n_in[s] (<= 0: cap_in).  d_box_ready + idx_bits: bounding boxes computed earlier by
+  // launch_vox_bbox and the number of bits their largest index space needs (read back by the caller) -- the radix sort then
+  // runs over segment + idx_bits bits instead of segment + 32 (one 8-bit pass less for a LiDAR frame at 0.8 m).
   void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, int max_n, float leaf, float4* d_out, int* d_n_out, int cap_out,
-           int* d_overflow, cudaStream_t stream);
+           int* d_overflow, cudaStream_t stream, const VoxBox* d_box_ready = nullptr, int idx_bits = 32);
 };
 
 // K7: device-resident local map (cm_map.cu)

@@ -144,7 +144,7 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
 // 10 iterations, 0.05 deg / 0.05 cm) and the map is not updated.
 static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, const float4* d_surf, int cap_s, const int* d_n,
                                int max_in_c, int max_in_s, const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats,
-                               bool localise = false) {
+                               bool localise = false, const VoxBox* d_box = nullptr, int bits_c = 32, int bits_s = 32) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   cudaStream_t st = ctx->stream;
@@ -180,9 +180,11 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   cudaStream_t aux = ctx->aux_stream;
   CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
   CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
-  ctx->voxel_aux.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux);
+  ctx->voxel_aux.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux,
+                     d_box, bits_c);
   CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
-  ctx->voxel.run(S, d_surf, d_n + S, cap_s, max_in_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st);
+  ctx->voxel.run(S, d_surf, d_n + S, cap_s, max_in_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st,
+                 d_box ? d_box + S : nullptr, bits_s);
   CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
   std::vector<int> nds(2 * S);
@@ -225,7 +227,10 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
       }
       launch_match_groups(m, st, G, ctx->gn_stream, ctx->gn_fork, ctx->gn_join, &ctx->prof);
     } else {
-      launch_match(m, st, &ctx->prof);
+      // replay from a CUDA graph unless per-launch events are wanted (bench.py's kernel timing, the timeline, the search trace)
+      static const bool no_graph = getenv("COOPERMAP_NO_GRAPH") != nullptr;
+      const bool want_events = ctx->prof.enabled || g_timeline.on || ctx->dbg_on || no_graph;
+      if (want_events || !ctx->match_graphs.launch(m, st)) launch_match(m, st, &ctx->prof);
     }
   }
   // featureMapUpdate (commented out in LaserLocalization::process, LaserLocalization.cpp:186)
@@ -319,6 +324,11 @@ static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* 
   L.out_n = (int*)slot.n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
   slot.scanreg.run(L, st);
   CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)slot.n.p + 2 * S, (int*)slot.n.p, S);
+  // bounding boxes of the two clouds the mapping stage voxel-filters: the host reads them back with the counts and sizes
+  // the radix sort keys by the index space they span
+  slot.box.reserve(sizeof(VoxBox) * 2 * S);
+  launch_vox_bbox(S, (const float4*)slot.pts[1].p, (const int*)slot.n.p, cap, cfg.filter_corner, (VoxBox*)slot.box.p, st);
+  launch_vox_bbox(S, (const float4*)slot.pts[3].p, (const int*)slot.n.p + S, cap, cfg.filter_surf, (VoxBox*)slot.box.p + S, st);
 }
 
 static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int cols, const cm_iso* odom, cm_iso* mapped, cm_match_stats* stats) {
@@ -327,16 +337,20 @@ static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int c
   cudaStream_t st = ctx->stream;
   // feature-cloud sizes: needed on the host to size the frame voxel filters (and for the byte accounting)
   std::vector<int> n5(5 * S);
+  std::vector<VoxBox> boxes(2 * S);
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5.data(), (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(boxes.data(), slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   int max_c = 1, max_s = 1;
+  long long cells_c = 1, cells_s = 1;
   ctx->last_features = 0;
   for (int s = 0; s < S; s++) {
     max_c = std::max(max_c, n5[s * 5 + 1]); max_s = std::max(max_s, n5[s * 5 + 3]);
+    cells_c = std::max(cells_c, boxes[s].cells); cells_s = std::max(cells_s, boxes[S + s].cells);
     for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)n5[s * 5 + k];
   }
   return mapping_process_dev(ctx, (const float4*)slot.pts[1].p, cap, (const float4*)slot.pts[3].p, cap, (const int*)slot.n.p, max_c,
-                             max_s, odom, mapped, stats);
+                             max_s, odom, mapped, stats, false, (const VoxBox*)slot.box.p, vox_index_bits(cells_c), vox_index_bits(cells_s));
 }
 
 static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
@@ -347,21 +361,34 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
     cudaSetDevice(ctx->cfg.device);
     if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
     if (!ctx->copy_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_stream2) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
     int si = -1;
     for (int i = 0; i < CM_PIPE_SLOTS; i++) if (!ctx->pipe[i].src) { si = i; break; }
     if (si < 0) return fail(ctx, CM_ERR_ARG, "three sweeps are already pending: run cm_pipeline_step on one of them first");
     cm_ctx::PipeSlot& slot = ctx->pipe[si];
     if (!slot.done) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
     if (!slot.copied) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied, cudaEventDisableTiming));
+    if (!slot.copied2) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied2, cudaEventDisableTiming));
     // a free slot fed a step that has returned (the pipeline entries synchronise): nothing reads its buffers any more
     const float4* d_frames = (const float4*)frames;
     if (is_host) {
       const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
       slot.frames.reserve(bytes);
       // upload on its own stream: the copy of sweep k+2 runs while sweep k+1 is in scan registration
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      // (in two halves on two copy streams: two concurrent transfers move ~1.5x the bytes per second of one)
+      const size_t half = (bytes / 2) & ~(size_t)255;
+      static const bool skip_upload = getenv("COOPERMAP_SKIP_UPLOAD") != nullptr;   // development aid: time the pipeline without PCIe
+      if (!skip_upload || slot.frames_valid != bytes) {
+        CM_TIMED("h2d_upload(first half)", ctx->copy_stream,
+                 CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, half, cudaMemcpyHostToDevice, ctx->copy_stream)));
+        CM_TIMED("h2d_upload(second half)", ctx->copy_stream2,
+                 CM_CUDA_CHECK(ctx, cudaMemcpyAsync((char*)slot.frames.p + half, (const char*)frames + half, bytes - half, cudaMemcpyHostToDevice, ctx->copy_stream2)));
+        slot.frames_valid = bytes;
+      }
       CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied, ctx->copy_stream));
+      CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied2, ctx->copy_stream2));
       CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, slot.copied, 0));
+      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, slot.copied2, 0));
       d_frames = (const float4*)slot.frames.p;
     }
     pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->side_stream);

@@ -8,6 +8,8 @@
 #include "cm_math.h"
 #include "cm_host.h"
 #include <vector>
+#include <stdint.h>
+#include <string.h>
 
 namespace cm {
 
@@ -796,6 +798,52 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
     launch_match_partial(m, it, stream, prof, fused);
     if (!fused) launch_match_solve(m, it, (const double*)m.sums, stream);
   }
+}
+
+static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
+  std::vector<unsigned long long> k;
+  auto P = [&](const void* p) { k.push_back((unsigned long long)(uintptr_t)p); };
+  auto I = [&](long long v) { k.push_back((unsigned long long)v); };
+  auto F = [&](float v) { unsigned int u; memcpy(&u, &v, 4); k.push_back(u); };
+  I(m.nstreams); P(m.corner); P(m.surf); P(m.n_corner); P(m.n_surf); I(m.cap_corner); I(m.cap_surf); P(m.grid_corner); P(m.grid_surf);
+  P(m.pose_in); P(m.state); P(m.rows); P(m.nn_slot); P(m.sums); P(m.trace); P(m.nn); I(m.orig_idx);
+  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
+  I((maxq + 32 + 255) / 256);   // the grids depend on max_queries only through this
+  P(m.own_box); P(m.hard); P(m.hard_count); I(m.hard_cap); I(m.hard_blocks); P(m.partials); P(m.tickets); I(m.partial_blocks);
+  I(m.prm.max_iterations); F(m.prm.delta_t_abort); F(m.prm.delta_r_abort); F(m.prm.knn_gate); F(m.prm.plane_max_dist);
+  I(m.prm.min_ref_corner); I(m.prm.min_ref_surf); I(m.prm.min_rows); F(m.prm.eig_threshold); I(m.prm.few_rows_continue);
+  I(m.prm.own_cube_only); I(m.prm.nan_guard);
+  return k;
+}
+
+bool MatchGraphCache::launch(const MatchLaunch& m, cudaStream_t stream) {
+  if (m.dbg || m.nn || m.trace) return false;   // diagnostics are not replayable
+  const std::vector<unsigned long long> key = match_graph_key(m);
+  for (Entry& e : entries)
+    if (e.key == key) {
+      if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) return false;
+      g_launch_count += e.launches;
+      return true;
+    }
+  if (entries.size() >= 32) clear();   // buffers were re-allocated many times: start over
+  const unsigned long long before = g_launch_count;
+  if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+  launch_match(m, stream, nullptr);
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+  Entry e; e.key = key; e.exec = nullptr; e.launches = g_launch_count - before;
+  g_launch_count = before;
+  const cudaError_t rc = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (rc != cudaSuccess) { cudaGetLastError(); return false; }
+  entries.push_back(e);
+  if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) return false;
+  g_launch_count += e.launches;
+  return true;
+}
+void MatchGraphCache::clear() {
+  for (Entry& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec);
+  entries.clear();
 }
 
 // Streams [s0, s1) of m as a launch of its own (every per-stream array is indexed by blockIdx.y).

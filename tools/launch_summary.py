@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list into per-kernel totals for ONE bench step.
-usage: tools/launch_summary.py launches.csv [step_index]   (a step starts at each sr_count_kernel launch)"""
+usage: tools/launch_summary.py launches.csv [step_index]   (a period runs from one match_init_kernel launch to the next = one step worth of launches in steady state)"""
 import collections
 import csv
 import re
@@ -14,7 +14,7 @@ def main():
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    starts = [i for i, n in enumerate(names) if "sr_count_kernel" in n]
+    starts = [i for i, n in enumerate(names) if "match_init_kernel" in n]   # one per step; with prefetching the scan registration of a later step interleaves, every period still holds one launch set
     a = starts[step]; b = starts[step + 1] if step + 1 < len(starts) and step + 1 != 0 else len(rows)
     agg = collections.OrderedDict(); tot = 0.0
     for r in rows[a:b]:
