@@ -616,16 +616,20 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
     int ra = 0, rb = 0;
     if (k < 21) { int tt = k; while (tt >= 6 - ra) { tt -= 6 - ra; ra++; } rb = ra + tt; }
     else if (k < 27) { ra = k - 21; rb = 6; }
+    // branch-free inner loop: every lane adds term(i) when (flag & need) == want, with per-lane constants
+    //   k < 27: term = row[ra] * row[rb] (kept rows);  27: 1 (kept rows);  28 / 29: 1 (counted corner / surf rows);  30: score term
+    const bool prod = k < 27;
+    const int ia = prod ? ra : 7, ib = prod ? rb : 7;
+    const int need = (k == 28 || k == 29) ? 6 : 1, want = (k == 28) ? 6 : (k == 29 ? 2 : 1);
     double acc = 0.0;
     const float* rows = reinterpret_cast<const float*>(srow);
     for (int i = grp * 32; i < grp * 32 + 32; i++) {
       const float* rv = rows + 8 * i;
       const int flag = __float_as_int(rv[7]);
-      if (k < 27) { if (flag & 1) acc += (double)rv[ra] * (double)rv[rb]; }
-      else if (k == 27) { if (flag & 1) acc += 1.0; }
-      else if (k == 28) { if ((flag & 2) && (flag & 4)) acc += 1.0; }
-      else if (k == 29) { if ((flag & 2) && !(flag & 4)) acc += 1.0; }
-      else if (k == 30) { if (flag & 1) acc += sexp[i]; }
+      const float fa = rv[ia], fb = rv[ib];
+      double term = prod ? (double)fa * (double)fb : 1.0;
+      if (k == 30) term = sexp[i];
+      if (k < 31 && (flag & need) == want) acc += term;
     }
     sacc[grp][k] = acc;
   }
