@@ -347,14 +347,36 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
     const float bound = fminf(bd5, gate);
     Top5 loc;
     top5_init(loc);
-    for (int t = lane; t < ncells; t += 32) {
-      const int dz = t / (n * n), dy = (t / n) % n, dx = t % n;
-      if (dx > 0 && dx < n - 1 && dy > 0 && dy < n - 1 && dz > 0 && dz < n - 1) continue;   // visited at the previous levels
-      const float cxl = (float)((blx - L + dx) * k), cyl = (float)((bly - L + dy) * k), czl = (float)((blz - L + dz) * k);
-      const float dxv = slab_dist(bfx, cxl, cxl + kf), dyv = slab_dist(bfy, cyl, cyl + kf), dzv = slab_dist(bfz, czl, czl + kf);
-      const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);   // lower bound of the distance to this cell
-      if (lb * lb >= bound) continue;
-      scan_cell<kOrigIdx>(g, blx - L + dx, bly - L + dy, blz - L + dz, bqx, bqy, bqz, bfilter, loc);
+    // the lanes probe 32 shell cells at a time; the non-empty ones are then scanned by the WHOLE warp, one cell after the
+    // other, lane j taking every 32nd point (coalesced loads).  Hard queries live where the map is sparse: few of the 56
+    // shell cells hold points, so "every lane scans its own cell" would leave 2-5 lanes busy.
+    for (int t0 = 0; t0 < ncells; t0 += 32) {
+      const int t = t0 + lane;
+      unsigned int start = 0, count = 0;
+      if (t < ncells) {
+        const int dz = t / (n * n), dy = (t / n) % n, dx = t % n;
+        const bool interior = dx > 0 && dx < n - 1 && dy > 0 && dy < n - 1 && dz > 0 && dz < n - 1;   // visited at the previous levels
+        if (!interior) {
+          const float cxl = (float)((blx - L + dx) * k), cyl = (float)((bly - L + dy) * k), czl = (float)((blz - L + dz) * k);
+          const float dxv = slab_dist(bfx, cxl, cxl + kf), dyv = slab_dist(bfy, cyl, cyl + kf), dzv = slab_dist(bfz, czl, czl + kf);
+          const float lb = 0.98f * leaf * sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);   // lower bound of the distance to this cell
+          if (lb * lb < bound && !grid_probe(g, blx - L + dx, bly - L + dy, blz - L + dz, &start, &count)) count = 0;
+        }
+      }
+      unsigned int full = __ballot_sync(FULL, count > 0);
+      while (full) {
+        const int src = __ffs(full) - 1;
+        full &= full - 1;
+        const unsigned int st = __shfl_sync(FULL, start, src), ct = __shfl_sync(FULL, count, src);
+        for (unsigned int j = lane; j < ct; j += 32) {
+          const float4 p = __ldg(g.pts + st + j);
+          if (!cand_ok(g, bfilter, p)) continue;
+          float ddx = bqx - p.x, ddy = bqy - p.y, ddz = bqz - p.z;
+          float d = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+          const int jj = (int)(st + j);
+          top5_insert(loc, d, kOrigIdx ? __float_as_int(p.w) : jj, jj);
+        }
+      }
     }
     // merge the lane-local lists into the owner's list: at most 5 winners can enter
     for (int round = 0; round < 5; round++) {

@@ -80,19 +80,6 @@ __device__ __forceinline__ int block_scan_excl(int v, int* scratch, int* total, 
   return base + x - v;
 }
 
-// block-wide minimum of a 64-bit key; scratch: >= 16 u64.
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* scratch) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(0xffffffffu, v, o); v = y < v ? y : v; }
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  unsigned long long r = scratch[0];
-#pragma unroll
-  for (int w = 1; w < SR_THREADS / 32; w++) { unsigned long long y = scratch[w]; r = y < r ? y : r; }
-  __syncthreads();
-  return r;
-}
-
 struct ScanRegParamsDev {
   float scan_period, blind_sq, blind_thr, curv_thr, less_flat_leaf;
   int R, nregions, max_sharp, max_flat;
@@ -203,7 +190,6 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   signed char* snap = state + cap; signed char* ev = snap + cap; signed char* lab = ev + cap;
   __shared__ int s_scan[32];
   int scan_phase = 0;   // uniform over the CTA: every thread makes the same sequence of block_scan_excl calls
-  __shared__ unsigned long long s_min[16];
   __shared__ int s_cnt[5];          // list lengths: sharp, lessSharp, flat, lessFlatRaw, (spare)
   __shared__ int s_misc[8];
 
@@ -619,7 +605,6 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
 
   // ---- per-ring voxel filter of the less-flat points (ScanRegistration.cpp:390-399; cm_voxel.cu semantics) -------
   // reuse px..: the member points are addressed through lst[3]; intensity of a member = ring + relTime
-  __shared__ float vb_min[3], vb_max[3];
   __shared__ int vb_i[8];
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = tid; i < nlf; i += SR_THREADS) {
