@@ -1,0 +1,219 @@
+// coopermap.hpp -- header-only C++ facade over the C ABI (coopermap.h): the reference's stage classes with the same names and
+// the same setup / process split, so that a nodelet written against lidar_slam::{OrganisedScanRegistration,
+// MultiScanRegistration, LaserOdometry, LaserMapping, LaserLocalization, ScanMatch} keeps its shape
+// (L_SLAM/src/odometry/*.h, scan_to_scan_match/ScanMatch.h, nodelet/*.cpp).  Clouds are std::vector<cm_point> (the payload
+// of pcl::PointCloud<pcl::PointXYZI>), poses are cm_iso (Eigen::Isometry3f, row-major rotation + translation) or cm_pose
+// (lidar_slam::Twist).  No PCL / Eigen / ROS types: the conversion helpers a nodelet needs are in INTEGRATION.md section 2.
+// Every object owns one context = one CUDA stream; like the reference's stages, an object is driven by one thread.
+#pragma once
+#include "coopermap.h"
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace coopermap {
+
+typedef std::vector<cm_point> PointCloud;
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+// RAII owner of a cm_ctx.  There is no CPU fallback: construction throws without a CUDA device.
+class Context {
+ public:
+  explicit Context(const cm_config& cfg) : cfg_(cfg), ctx_(nullptr) {
+    const int rc = cm_ctx_create(&cfg_, &ctx_);
+    if (rc != CM_OK) throw Error(rc, "cm_ctx_create failed (no CUDA device?)");
+  }
+  ~Context() { if (ctx_) cm_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  cm_ctx* get() const { return ctx_; }
+  const cm_config& config() const { return cfg_; }
+  // hard errors (< 0) throw; soft outcomes (>= 0: CM_OK, CM_TOO_FEW_REF, ...) are returned like the reference's bool / warnings
+  int check(int rc) const { if (rc < 0) throw Error(rc, cm_last_error(ctx_)); return rc; }
+  static cm_config defaults() { cm_config c; cm_config_default(&c); return c; }
+
+ private:
+  cm_config cfg_;
+  cm_ctx* ctx_;
+};
+
+// ---- stage 1 ---------------------------------------------------------------------------------------------------------------
+// ScanRegistration (ScanRegistration.h): the four feature clouds of a sweep.
+class ScanRegistration {
+ public:
+  explicit ScanRegistration(const cm_config& cfg = Context::defaults()) : ctx_(cfg) {}
+  const PointCloud& cornerPointsSharp() const { return clouds_[0]; }       // /laser_cloud_sharp
+  const PointCloud& cornerPointsLessSharp() const { return clouds_[1]; }   // /laser_cloud_less_sharp
+  const PointCloud& surfacePointsFlat() const { return clouds_[2]; }       // /laser_cloud_flat
+  const PointCloud& surfacePointsLessFlat() const { return clouds_[3]; }   // /laser_cloud_less_flat
+  const PointCloud& laserCloud() const { return full_; }                   // /velodyne_cloud_2 (ring-major)
+  Context& context() { return ctx_; }
+
+ protected:
+  void prepare(size_t n, cm_scanreg_out& out) {
+    for (int k = 0; k < 4; k++) { clouds_[k].resize(n ? n : 1); out.pts[k] = clouds_[k].data(); out.cap[k] = (int)clouds_[k].size(); }
+    full_.resize(n ? n : 1); curv_.resize(n ? n : 1);
+    out.n = n_; out.cloud = full_.data(); out.cloud_curvature = curv_.data();
+  }
+  void finish(int n_full) {
+    for (int k = 0; k < 4; k++) clouds_[k].resize(n_[k]);
+    full_.resize(n_full);
+  }
+  Context ctx_;
+  PointCloud clouds_[4], full_;
+  std::vector<float> curv_;
+  int n_[5] = {0, 0, 0, 0, 0};
+};
+
+// OrganisedScanRegistration::process (OrganizedScanRegistration.cpp:82-150): ring = row, missing returns = NaN.
+class OrganisedScanRegistration : public ScanRegistration {
+ public:
+  using ScanRegistration::ScanRegistration;
+  void process(const PointCloud& organised, int height, int width) {
+    if ((size_t)height * width != organised.size()) throw Error(CM_ERR_ARG, "cloud is not height x width");
+    cm_scanreg_out out = cm_scanreg_out();
+    prepare(organised.size(), out);
+    ctx_.check(cm_scanreg_organised_host(ctx_.get(), organised.data(), 1, height, width, &out));
+    // size of the ring-major cloud = returns that are finite and outside the blind radius (OrganizedScanRegistration.cpp:115-123)
+    const float b2 = ctx_.config().blind_radius * ctx_.config().blind_radius;
+    int kept = 0;
+    for (const cm_point& p : organised)
+      if (p.x - p.x == 0.f && p.y - p.y == 0.f && p.z - p.z == 0.f && !(p.x * p.x + p.y * p.y + p.z * p.z < b2)) kept++;
+    finish(kept);
+  }
+};
+
+// MultiScanRegistration::process (MultiScanRegistration.cpp:95-200): raw azimuth-major sweep of a spinning multi-beam LiDAR.
+class MultiScanRegistration : public ScanRegistration {
+ public:
+  enum Lidar { VLP16 = 0, HDL32 = 1, HDL64E = 2 };   // MultiScanRegistration.h:90-102
+  using ScanRegistration::ScanRegistration;
+  void process(const PointCloud& sweep, Lidar lidar) {
+    cm_scanreg_out out = cm_scanreg_out();
+    prepare(sweep.size(), out);
+    int rows = 0, cols = 0;
+    ctx_.check(cm_scanreg_sweep_host(ctx_.get(), sweep.data(), sweep.size(), (int)lidar, &out, &rows, &cols));
+    finish((int)sweep.size());
+  }
+};
+
+// ---- stage 2 ---------------------------------------------------------------------------------------------------------------
+// LaserOdometry::process (LaserOdometry.cpp:288-326)
+class LaserOdometry {
+ public:
+  explicit LaserOdometry(const cm_config& cfg = Context::defaults()) : ctx_(cfg) { ctx_.check(cm_odometry_reset(ctx_.get())); }
+  void process(const PointCloud& sharp, const PointCloud& lessSharp, const PointCloud& flat, const PointCloud& lessFlat) {
+    corner_.resize(lessSharp.size() ? lessSharp.size() : 1); surf_.resize(lessFlat.size() ? lessFlat.size() : 1);
+    ctx_.check(cm_odometry_process_host(ctx_.get(), sharp.data(), (int)sharp.size(), lessSharp.data(), (int)lessSharp.size(), flat.data(),
+                                        (int)flat.size(), lessFlat.data(), (int)lessFlat.size(), &sum_, &tf_, corner_.data(), surf_.data(),
+                                        &stats_, nullptr));
+    corner_.resize(lessSharp.size()); surf_.resize(lessFlat.size());
+  }
+  const cm_iso& transformSum() const { return sum_; }              // /laser_odom_to_init
+  const cm_pose& transform() const { return tf_; }                 // frame-to-frame Twist (_transform)
+  const PointCloud& lastCornerCloud() const { return corner_; }    // /laser_cloud_corner_last
+  const PointCloud& lastSurfaceCloud() const { return surf_; }     // /laser_cloud_surf_last
+  const cm_odom_stats& stats() const { return stats_; }
+
+ private:
+  Context ctx_;
+  cm_iso sum_ = cm_iso();
+  cm_pose tf_ = cm_pose();
+  cm_odom_stats stats_ = cm_odom_stats();
+  PointCloud corner_, surf_;
+};
+
+// ---- stage 3 ---------------------------------------------------------------------------------------------------------------
+// LaserMapping::process (LaserMapping.cpp:39-59) with the cube map resident on the GPU.
+class LaserMapping {
+ public:
+  explicit LaserMapping(const cm_config& cfg = Context::defaults(), size_t maxCornerPoints = 400000, size_t maxSurfPoints = 4000000)
+      : ctx_(cfg) { ctx_.check(cm_mapping_create(ctx_.get(), 1, maxCornerPoints, maxSurfPoints)); }
+  // odom: /laser_odom_to_init; returns /aft_mapped_to_init.  lastStatus(): CM_OK, CM_TOO_FEW_REF, CM_TOO_FEW_MATCHES, CM_NOT_CONVERGED
+  cm_iso process(const cm_iso& odom, const PointCloud& cornerLast, const PointCloud& surfLast) {
+    cm_iso mapped; int nc = (int)cornerLast.size(), ns = (int)surfLast.size();
+    const cm_point dummy = cm_point();
+    ctx_.check(cm_mapping_process_host(ctx_.get(), &odom, nc ? cornerLast.data() : &dummy, &nc, nc ? nc : 1, ns ? surfLast.data() : &dummy, &ns,
+                                       ns ? ns : 1, &mapped, &stats_));
+    return mapped;
+  }
+  int lastStatus() const { return stats_.status; }
+  const cm_match_stats& stats() const { return stats_; }
+  // saveMap service (LaserMatcher.cpp:357-394 -> FeatureMap::saveCloudToFiles)
+  int saveMap(const std::string& dir) { int n = 0; ctx_.check(cm_map_save_host(ctx_.get(), 0, dir.c_str(), &n)); return n; }
+  // /laser_cloud_surround_* style export: all resident points of a class (0 corner, 1 surf)
+  PointCloud mapCloud(int cls) {
+    size_t n = 0;
+    ctx_.check(cm_map_export_host(ctx_.get(), 0, cls, nullptr, nullptr, 0, &n));
+    PointCloud out(n ? n : 1);
+    ctx_.check(cm_map_export_host(ctx_.get(), 0, cls, out.data(), nullptr, out.size(), &n));
+    out.resize(n);
+    return out;
+  }
+  Context& context() { return ctx_; }
+
+ protected:
+  Context ctx_;
+  cm_match_stats stats_ = cm_match_stats();
+};
+
+// LaserLocalization::process (LaserLocalization.cpp:163-188): FeatureMap::scanMatchScan against a prebuilt map, no map update.
+class LaserLocalization : public LaserMapping {
+ public:
+  using LaserMapping::LaserMapping;
+  // FeatureMap::loadCloudFromFiles; returns the number of files read
+  int loadMap(const std::string& dir) {
+    int n = 0; size_t pts = 0, bad = 0;
+    ctx_.check(cm_map_load_host(ctx_.get(), 0, dir.c_str(), &n, &pts, &bad));
+    return n;
+  }
+  cm_iso process(const cm_iso& odom, const PointCloud& cornerLast, const PointCloud& surfLast) {
+    cm_iso mapped; int nc = (int)cornerLast.size(), ns = (int)surfLast.size();
+    const cm_point dummy = cm_point();
+    ctx_.check(cm_localization_process_host(ctx_.get(), &odom, nc ? cornerLast.data() : &dummy, &nc, nc ? nc : 1,
+                                            ns ? surfLast.data() : &dummy, &ns, ns ? ns : 1, &mapped, &stats_));
+    return mapped;
+  }
+};
+
+// ---- the operator ------------------------------------------------------------------------------------------------------------
+// ScanMatch (ScanMatch.h:22-86).  The class defaults are the reference's (ScanMatch.cpp:21-33): 0.05 / 0.05, useScore = true.
+class ScanMatch {
+ public:
+  explicit ScanMatch(int maxIterations = 10) : ctx_(make_cfg(maxIterations)) {}
+  explicit ScanMatch(const cm_config& cfg) : ctx_(cfg) {}
+  // scanMatchScan(refCorner, refSurf, corner, surf, Twist&): transform is the initial guess and receives the result, also when
+  // false is returned (ScanMatch.cpp:342-346)
+  bool scanMatchScan(const PointCloud& refCorner, const PointCloud& refSurf, const PointCloud& corner, const PointCloud& surf, cm_pose& transform) {
+    ctx_.check(cm_match_stateless_host(ctx_.get(), refCorner.data(), refCorner.size(), refSurf.data(), refSurf.size(), corner.data(),
+                                       corner.size(), surf.data(), surf.size(), &transform, &stats_, nullptr, nullptr, nullptr));
+    return stats_.ret != 0;
+  }
+  bool scanMatchScan(const PointCloud& refCorner, const PointCloud& refSurf, const PointCloud& corner, const PointCloud& surf, cm_iso& pose) {
+    ctx_.check(cm_match_stateless_iso_host(ctx_.get(), refCorner.data(), refCorner.size(), refSurf.data(), refSurf.size(), corner.data(),
+                                           corner.size(), surf.data(), surf.size(), &pose, &stats_));
+    return stats_.ret != 0;
+  }
+  // scanMatchLocal (ScanMatch.cpp:375-398): voxel-filters the four clouds (0.2 / 0.4) first
+  bool scanMatchLocal(const PointCloud& refCorner, const PointCloud& refSurf, const PointCloud& corner, const PointCloud& surf, cm_pose& transform) {
+    ctx_.check(cm_match_local_host(ctx_.get(), refCorner.data(), refCorner.size(), refSurf.data(), refSurf.size(), corner.data(), corner.size(),
+                                   surf.data(), surf.size(), &transform, &stats_));
+    return stats_.ret != 0;
+  }
+  const cm_match_stats& stats() const { return stats_; }
+
+ private:
+  static cm_config make_cfg(int maxIterations) {
+    cm_config c = Context::defaults();
+    c.max_iterations = maxIterations; c.delta_t_abort = 0.05f; c.delta_r_abort = 0.05f; c.use_score = 1;
+    return c;
+  }
+  Context ctx_;
+  cm_match_stats stats_ = cm_match_stats();
+};
+
+}  // namespace coopermap
