@@ -68,13 +68,14 @@ __host__ __device__ __forceinline__ unsigned int hash_cell(unsigned long long k)
 __device__ __forceinline__ bool grid_probe(const GridView& g, int x, int y, int z, unsigned int* start, unsigned int* count) {
   unsigned long long key = pack_cell(x, y, z);
   unsigned int h = hash_cell(key) & g.mask;
-  while (true) {
+  for (unsigned int probes = 0; probes <= g.mask; probes++) {   // bounded even if the table were completely full
     uint4 e = __ldg(reinterpret_cast<const uint4*>(g.entries + h));
     unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     if (k == key) { *start = e.z; *count = e.w; return true; }
     if (k == CM_EMPTY_KEY) return false;
     h = (h + 1) & g.mask;
   }
+  return false;
 }
 
 // Sorted 5-best list by (d2, idx), held as packed 64-bit keys: (bits of d2) << 32 | idx.  d2 >= 0, so the bit pattern of
@@ -275,9 +276,9 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
     for (int cI = 0; cI < 4; cI++) {
       unsigned long long kk = entry_key(e[cI]);
       if (kk != key[cI] && kk != CM_EMPTY_KEY) {   // linear probing (rare)
-        unsigned int h = hash_cell(key[cI]) & g.mask;
+        unsigned int h = hash_cell(key[cI]) & g.mask, probes = 0;
         do { h = (h + 1) & g.mask; e[cI] = __ldg(reinterpret_cast<const uint4*>(g.entries + h)); kk = entry_key(e[cI]); }
-        while (kk != key[cI] && kk != CM_EMPTY_KEY);
+        while (kk != key[cI] && kk != CM_EMPTY_KEY && ++probes <= g.mask);
       }
       if (kk == key[cI] && e[cI].w > 0) {
         const int cc = c.own ^ ((0x76534210 >> (4 * (b * 4 + cI))) & 7);

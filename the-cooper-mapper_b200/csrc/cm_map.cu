@@ -96,11 +96,12 @@ struct PendingAdd { float4 p; unsigned int entry; int stream; int cube; };
 __device__ __forceinline__ unsigned int map_find_or_create_cell(MapClassDev& m, int cx, int cy, int cz) {
   unsigned long long key = pack_cell(cx, cy, cz);
   unsigned int h = hash_cell(key) & m.mask;
-  while (true) {
+  for (unsigned int probes = 0; probes <= m.mask; probes++) {   // bounded: a full table is a capacity error, not a hang
     unsigned long long prev = atomicCAS(&m.entries[h].key, CM_EMPTY_KEY, key);
     if (prev == CM_EMPTY_KEY || prev == key) return h;
     h = (h + 1) & m.mask;
   }
+  return 0xFFFFFFFFu;
 }
 
 __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ slot_of,
@@ -120,6 +121,7 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
   const int ci = world_to_cube_axis(first.x, m.cube_size, m.origin[0]), cj = world_to_cube_axis(first.y, m.cube_size, m.origin[1]),
             ck = world_to_cube_axis(first.z, m.cube_size, m.origin[2]);
   const unsigned int e = map_find_or_create_cell(m, floor_div(vx, m.kdiv), floor_div(vy, m.kdiv), floor_div(vz, m.kdiv));
+  if (e == 0xFFFFFFFFu) { atomicExch(flags + 2, 1); return; }   // cell table full: reported as CM_ERR_CAPACITY
   // resident point(s) of this voxel in this cube come first in the sum (they precede the pushed points in the cube cloud)
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
   int cnt = 0, keep = -1;
