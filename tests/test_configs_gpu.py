@@ -220,6 +220,11 @@ def test_prefetched_steps_equal_synchronous_steps(cmb, synth):
     for s in range(S):
         for cls in (0, 1):
             assert _same(a.map_export_sorted(s, cls)[0], b.map_export_sorted(s, cls)[0])
+    # the Gauss-Newton loop of these steps was submitted as a CUDA graph with a conditional WHILE node (CUDA >= 12.4)
+    import ctypes as C
+    ng = C.c_int(0); wl = C.c_int(0)
+    b._check(b.L.cm_debug_graph_info(b.h, C.byref(ng), C.byref(wl)))
+    assert ng.value >= 1 and wl.value == 1
     # at most three sweeps in flight
     for k in range(3):
         b.pipeline_prefetch(frames[k])

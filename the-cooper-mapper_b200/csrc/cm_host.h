@@ -132,9 +132,14 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
 struct MatchGraphCache {
   struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; };
   std::vector<Entry> entries;
+  // use_while: build the loop as a conditional WHILE node (CUDA 12.4+) whose body reads the evaluation index from device memory
+  // and whose last node (gn_advance_kernel) calls cudaGraphSetConditional -- the graph then runs exactly as many evaluations as
+  // the slowest stream needs instead of max_iterations mostly empty ones; falls back to the unrolled graph when unavailable
+  bool use_while = true;
+  int* d_iter = nullptr;
   bool launch(const MatchLaunch& m, cudaStream_t stream);   // false: capture failed, nothing was launched
   void clear();
-  ~MatchGraphCache() { clear(); }
+  ~MatchGraphCache();
 };
 // the same with the streams split into `ngroups` groups whose iteration loops run concurrently on gs[0..ngroups)
 void launch_match_groups(const MatchLaunch& m, cudaStream_t stream, int ngroups, cudaStream_t* gs, cudaEvent_t fork, cudaEvent_t* join,

@@ -525,6 +525,14 @@ int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_
   }
   return CM_OK;
 }
+/* development aid: how the mapping stage's Gauss-Newton loop is being submitted: n_graphs cached CUDA graphs, while_loop = 1 when
+ * they are conditional WHILE graphs (0: unrolled max_iterations graphs, the fallback) */
+int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop) {
+  if (!ctx) return CM_ERR_ARG;
+  if (n_graphs) *n_graphs = (int)ctx->match_graphs.entries.size();
+  if (while_loop) *while_loop = ctx->match_graphs.use_while ? 1 : 0;
+  return CM_OK;
+}
 int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = ctx->prof_sr.enabled = on != 0; return CM_OK; }
 int cm_prof_drain_scanreg(cm_ctx* ctx, double* kernel_ms, int* launches) {
   if (!ctx || !kernel_ms) return CM_ERR_ARG;

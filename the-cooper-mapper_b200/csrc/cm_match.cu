@@ -96,6 +96,7 @@ struct CorrArgs {
   int* nn;                                    // optional [nstreams][cap_corner + cap_surf][5], -1 where gated out
   const float* own_box;                       // optional {lo[3], hi[3]}: only queries whose map-frame position is inside are evaluated (sharded map)
   unsigned long long* dbg;                    // optional per-warp trace of search_kernel (development aid, cm_debug_search_trace)
+  const int* iter_dev;                        // optional: the evaluation index lives in device memory (graph WHILE loop); hard_count is then the row base
   void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
   MatchParamsDev prm;
 };
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
     if (hard) {
       const int lane = threadIdx.x & 31;
       int base = 0;
-      if (lane == 0) base = atomicAdd(a.hard_count, __popc(hard));
+      if (lane == 0) base = atomicAdd(a.iter_dev ? a.hard_count + *a.iter_dev : a.hard_count, __popc(hard));
       base = __shfl_sync(FULL, base, 0);
       if (need) {
         const int pos = base + __popc(hard & ((1u << lane) - 1));
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
 // K5a': the hard queries of one Gauss-Newton evaluation, one warp per query (grid-stride over the list).
 template <bool kOrigIdx>
 __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
-  const int n = min(*a.hard_count, a.hard_cap);
+  const int n = min(a.iter_dev ? a.hard_count[*a.iter_dev] : *a.hard_count, a.hard_cap);
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
@@ -407,6 +408,7 @@ struct SolveArgs {
   MatchState* state;
   IterTrace* trace;   // optional [nstreams][max_iterations]
   int iter;
+  const int* iter_dev;   // optional: overrides iter (graph WHILE loop)
   MatchParamsDev prm;
 };
 
@@ -489,7 +491,9 @@ __device__ __noinline__ bool dev_inverse6(const float* A, float* inv) {
 
 // K6b: solve, degeneracy projection, pose update, convergence (ScanMatch.cpp:134-260).  One thread per stream; the
 // 6x6 work goes through cm_math.h, i.e. the same instruction sequence as the oracle's.
-__device__ __noinline__ void solve_stream(const SolveArgs& a, int s, const double* tot) {
+__device__ __noinline__ void solve_stream(const SolveArgs& a_in, int s, const double* tot) {
+  SolveArgs a = a_in;
+  if (a.iter_dev) a.iter = *a.iter_dev;
   MatchState& st = a.state[s];
   if (st.done) return;
   const int nrows = (int)tot[27];
@@ -724,7 +728,7 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
   ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
-  ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr;
+  ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr; ca.iter_dev = nullptr; sa.iter_dev = nullptr;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
@@ -804,6 +808,78 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
   }
 }
 
+// Last node of the WHILE body: next evaluation index, loop again while some stream is still iterating.
+__global__ void gn_advance_kernel(cudaGraphConditionalHandle handle, int* iter, const MatchState* state, int nstreams, int max_iterations) {
+  const int it = *iter + 1;
+  *iter = it;
+  int active = 0;
+  for (int s = 0; s < nstreams; s++) active |= state[s].done ? 0 : 1;
+  cudaGraphSetConditional(handle, (active && it < max_iterations) ? 1u : 0u);
+}
+
+// One Gauss-Newton evaluation with the evaluation index read from device memory (body of the WHILE node).
+static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStream_t stream) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  ca.iter_dev = d_iter; sa.iter_dev = d_iter; sa.iter = 0;
+  const int capQ = m.cap_corner + m.cap_surf;
+  int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 32 + 255) / 256;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, m.nstreams);
+  dim3 sgrid((bx * 256 + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, m.nstreams);
+  if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
+  else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
+  const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
+  if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
+  else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
+  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums;
+  CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
+}
+
+// init -> WHILE { search, hard search, fit + solve, advance }: as many evaluations as the slowest stream needs, one submission
+static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cudaStream_t stream, unsigned long long* launches_per_eval) {
+  if (!(m.partials && m.tickets && m.hard) || m.prm.max_iterations > CM_MAX_EVALS) return nullptr;
+  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
+  if ((maxq + 32 + 255) / 256 > m.partial_blocks) return nullptr;
+  cudaGraph_t g = nullptr, gi = nullptr, tmp = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const unsigned long long before = g_launch_count;
+  bool ok = cudaGraphCreate(&g, 0) == cudaSuccess;
+  // init part as a child graph
+  if (ok) ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    launch_match_init(m, stream);
+    cudaMemsetAsync(d_iter, 0, sizeof(int), stream);
+    ok = cudaStreamEndCapture(stream, &gi) == cudaSuccess && gi;
+  }
+  cudaGraphNode_t n_init = nullptr, n_cond = nullptr;
+  if (ok) ok = cudaGraphAddChildGraphNode(&n_init, g, nullptr, 0, gi) == cudaSuccess;
+  cudaGraphConditionalHandle handle = 0;
+  if (ok) ok = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+  cudaGraphNodeParams prm = {cudaGraphNodeTypeConditional};
+  if (ok) {
+    prm.conditional.handle = handle; prm.conditional.type = cudaGraphCondTypeWhile; prm.conditional.size = 1;
+    ok = cudaGraphAddNode(&n_cond, g, &n_init, 1, &prm) == cudaSuccess && prm.conditional.phGraph_out;
+  }
+  if (ok) {
+    cudaGraph_t body = prm.conditional.phGraph_out[0];
+    ok = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const unsigned long long b0 = g_launch_count;
+      launch_match_body(m, d_iter, stream);
+      CM_LAUNCH(gn_advance_kernel, 1, 1, 0, stream, handle, d_iter, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations);
+      *launches_per_eval = g_launch_count - b0;
+      ok = cudaStreamEndCapture(stream, &tmp) == cudaSuccess;
+    }
+  }
+  if (ok) ok = cudaGraphInstantiate(&exec, g, 0) == cudaSuccess;
+  if (gi) cudaGraphDestroy(gi);
+  if (g) cudaGraphDestroy(g);
+  g_launch_count = before;
+  if (!ok) { cudaGetLastError(); if (exec) cudaGraphExecDestroy(exec); return nullptr; }
+  return exec;
+}
+
 static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
   std::vector<unsigned long long> k;
   auto P = [&](const void* p) { k.push_back((unsigned long long)(uintptr_t)p); };
@@ -830,6 +906,21 @@ bool MatchGraphCache::launch(const MatchLaunch& m, cudaStream_t stream) {
       return true;
     }
   if (entries.size() >= 32) clear();   // buffers were re-allocated many times: start over
+  if (use_while) {
+    if (!d_iter) { if (cudaMalloc(&d_iter, sizeof(int)) != cudaSuccess) { cudaGetLastError(); d_iter = nullptr; use_while = false; } }
+    if (use_while) {
+      Entry e; e.key = key; e.launches = 2; unsigned long long per_eval = 4;
+      e.exec = build_while_graph(m, d_iter, stream, &per_eval);
+      if (e.exec) {
+        e.launches = 1 + per_eval;   // at least one evaluation runs; the real count is data dependent (a lower bound for gpu_launches)
+        entries.push_back(e);
+        if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) { cudaGetLastError(); return false; }
+        g_launch_count += e.launches;
+        return true;
+      }
+      use_while = false;   // conditional nodes unavailable on this driver: fall back to the unrolled graph for good
+    }
+  }
   const unsigned long long before = g_launch_count;
   if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
   launch_match(m, stream, nullptr);
@@ -849,6 +940,7 @@ void MatchGraphCache::clear() {
   for (Entry& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec);
   entries.clear();
 }
+MatchGraphCache::~MatchGraphCache() { clear(); if (d_iter) cudaFree(d_iter); }
 
 // Streams [s0, s1) of m as a launch of its own (every per-stream array is indexed by blockIdx.y).
 static MatchLaunch match_slice(const MatchLaunch& m, int g, int s0, int s1) {
