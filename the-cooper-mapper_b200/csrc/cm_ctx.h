@@ -43,6 +43,7 @@ struct cm_ctx {
   // Gauss-Newton stream groups of the batched mapping stage (cm_mapping.cu)
 #define CM_MAX_GN_GROUPS 8
   cudaStream_t gn_stream[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_join[CM_MAX_GN_GROUPS] = {}; cudaEvent_t gn_fork = nullptr;
+  cm::GraphCache stage_graphs;                      // voxel-filter and map-insert chains of the mapping stage
   cm::MatchGraphCache match_graphs;                 // CUDA graphs of the mapping stage's Gauss-Newton loop
   cm::HardQueue hardq;                              // deferred hard 5-NN queries of the current match (cm_match.cu)
   // scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members

@@ -59,6 +59,51 @@ struct DeviceBuffer {
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
 };
 
+// Capture-once / replay-many helper for fixed launch sequences (a chain of small kernels whose arguments repeat from step to
+// step).  The first time a key is seen the sequence runs normally (grow-only buffers reach their size: cudaMalloc cannot be
+// captured), the second time it is captured into a CUDA graph, afterwards it is ONE submission.
+struct GraphCache {
+  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; };
+  std::vector<Entry> entries;
+  template <class F>
+  void run(const std::vector<unsigned long long>& key, cudaStream_t stream, F&& issue) {
+    for (Entry& e : entries)
+      if (e.key == key) {
+        if (e.exec) {
+          if (cudaGraphLaunch(e.exec, stream) == cudaSuccess) { g_launch_count += e.launches; return; }
+          cudaGetLastError();
+          issue();
+          return;
+        }
+        // seen once: capture now
+        const unsigned long long before = g_launch_count;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); issue(); return; }
+        issue();
+        cudaGraph_t graph = nullptr;
+        const bool ok = cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph;
+        e.launches = g_launch_count - before;
+        g_launch_count = before;
+        if (ok && cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(e.exec, stream) == cudaSuccess) {
+          cudaGraphDestroy(graph);
+          g_launch_count += e.launches;
+          return;
+        }
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
+        e.key.clear();   // never try this key again
+        issue();
+        return;
+      }
+    if (entries.size() >= 64) clear();
+    Entry e; e.key = key; e.exec = nullptr; e.launches = 0;
+    entries.push_back(e);
+    issue();
+  }
+  void clear() { for (Entry& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec); entries.clear(); }
+  ~GraphCache() { clear(); }
+};
+
 // Storage behind one GridView built from a caller-supplied cloud (stateless matching / knn).
 struct GridStorage {
   DeviceBuffer entries, pts, cell_of, cursor;

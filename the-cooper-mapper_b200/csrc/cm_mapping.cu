@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <stdint.h>
 #include <algorithm>
 
 namespace cm {
@@ -178,13 +179,36 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
   }
   cudaStream_t aux = ctx->aux_stream;
+  // the two filter chains (and, below, the two insert chains) are fixed launch sequences: replayed from CUDA graphs keyed by
+  // their arguments, with the element bounds rounded up so that the keys repeat from step to step
+  static const bool no_graph = getenv("COOPERMAP_NO_GRAPH") != nullptr;
+  const bool use_graphs = !no_graph && !g_timeline.on;
+  auto P = [](const void* p) { return (unsigned long long)(uintptr_t)p; };
+  auto FB = [](float v) { unsigned int u; memcpy(&u, &v, 4); return (unsigned long long)u; };
+  const int mc_r = std::min(cap_c, (std::max(max_in_c, 1) + 255) & ~255), ms_r = std::min(cap_s, (std::max(max_in_s, 1) + 1023) & ~1023);
   CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
   CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
-  ctx->voxel_aux.run(S, d_corner, d_n, cap_c, max_in_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux,
-                     d_box, bits_c);
-  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
-  ctx->voxel.run(S, d_surf, d_n + S, cap_s, max_in_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st,
-                 d_box ? d_box + S : nullptr, bits_s);
+  {
+    auto issue_c = [&]() {
+      ctx->voxel_aux.run(S, d_corner, d_n, cap_c, mc_r, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux,
+                         d_box, bits_c);
+    };
+    auto issue_s = [&]() {
+      ctx->voxel.run(S, d_surf, d_n + S, cap_s, ms_r, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st,
+                     d_box ? d_box + S : nullptr, bits_s);
+    };
+    if (use_graphs) {
+      ctx->stage_graphs.run({1, (unsigned long long)S, P(d_corner), P(d_n), (unsigned long long)cap_c, (unsigned long long)mc_r, FB(cfg.filter_corner),
+                             P(ctx->m_corner_ds.p), P(d_nds), P(ctx->d_flag.p), P(d_box), (unsigned long long)bits_c, P(aux)}, aux, issue_c);
+      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
+      ctx->stage_graphs.run({2, (unsigned long long)S, P(d_surf), P(d_n), (unsigned long long)cap_s, (unsigned long long)ms_r, FB(cfg.filter_surf),
+                             P(ctx->m_surf_ds.p), P(d_nds), P(ctx->d_flag.p), P(d_box), (unsigned long long)bits_s, P(st)}, st, issue_s);
+    } else {
+      issue_c();
+      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
+      issue_s();
+    }
+  }
   CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
   std::vector<int> nds(2 * S);
@@ -228,7 +252,6 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
       launch_match_groups(m, st, G, ctx->gn_stream, ctx->gn_fork, ctx->gn_join, &ctx->prof);
     } else {
       // replay from a CUDA graph unless per-launch events are wanted (bench.py's kernel timing, the timeline, the search trace)
-      static const bool no_graph = getenv("COOPERMAP_NO_GRAPH") != nullptr;
       const bool want_events = ctx->prof.enabled || g_timeline.on || ctx->dbg_on || no_graph;
       if (want_events || !ctx->match_graphs.launch(m, st)) launch_match(m, st, &ctx->prof);
     }
@@ -237,9 +260,18 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   if (!localise) {
     CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
-    ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, max_c, (const MatchState*)ctx->m_state.p, nullptr, aux);
-    CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
-    ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, max_s, (const MatchState*)ctx->m_state.p, nullptr, st);
+    const int ic_r = std::min(cap_c, (max_c + 255) & ~255), is_r = std::min(cap_s, (max_s + 1023) & ~1023);
+    auto ins_c = [&]() { ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, ic_r, (const MatchState*)ctx->m_state.p, nullptr, aux); };
+    auto ins_s = [&]() { ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, is_r, (const MatchState*)ctx->m_state.p, nullptr, st); };
+    if (use_graphs) {
+      ctx->stage_graphs.run({3, (unsigned long long)S, P(ctx->m_corner_ds.p), P(d_nds), (unsigned long long)cap_c, (unsigned long long)ic_r, P(ctx->m_state.p), P(aux)}, aux, ins_c);
+      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
+      ctx->stage_graphs.run({4, (unsigned long long)S, P(ctx->m_surf_ds.p), P(d_nds), (unsigned long long)cap_s, (unsigned long long)is_r, P(ctx->m_state.p), P(st)}, st, ins_s);
+    } else {
+      ins_c();
+      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
+      ins_s();
+    }
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   }
   // results
