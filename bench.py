@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.2)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -246,7 +246,11 @@ def main():
             ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS)
         ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    # clocks are sampled by rank 0 only (its own GPU): one nvidia-smi process per rank every 0.1 s would take the driver's global
+    # lock 80 times a second on an 8-GPU box and perturb the launch-bound part of every rank's step
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     ctx.prof_enable(True); ctx.prof_drain()
     launches0 = ctx.launch_count()
     qi = q = ins = feat = 0
@@ -301,7 +305,9 @@ def main():
     ctx.timer_record(1)
     e2e_ms = ctx.timer_elapsed_ms()
     barrier()
-    sampler.stop_flag = True; sampler.join(timeout=2)
+    sampler.stop_flag = True
+    if rank == 0:
+        sampler.join(timeout=2)
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -175,6 +175,24 @@ int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* cor
 int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
                                  const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
 
+/* LaserMappingLocal (odometry/LaserMappingLocal.cpp:33-78): the mapping stage over LocalFeatureMap
+ * (io_module/LocalFeatureMap.h:28-99) instead of the cube map -- a sliding window of voxel-filtered frames.  One frame:
+ * transformMerge, prepareFeatureFrame (cfg.filter_corner / filter_surf), surround = VoxelGrid(0.2 corner / 0.4 surf) of the
+ * concatenated window (getSurroundFeature, :84-99), ScanMatch::scanMatchScan, transformUpdate, then the filtered frame is
+ * appended to the window (addDataFrame :62-69) with FrameUpdater's travelled distance (io_module/FrameUpdater.hpp:17-42), and
+ * clean() (:70-82) drops the frames more than 30 m of travel behind -- one more than it counts, as the reference does.
+ * use_mapped_pose = 0 is the reference as written: the frame is placed with `_transformTobeMapped`, a Twist that is declared
+ * (LaserMatcher.h:121) and never assigned, i.e. the identity -- frames stay in the sensor frame, the travelled distance stays
+ * 0 and nothing is ever dropped.  use_mapped_pose = 1 places the frame with the mapped pose (_lidarMappedNew).
+ * The window lives on the device; one window per context. */
+int cm_mapping_local_create(cm_ctx* ctx, int use_mapped_pose);
+int cm_mapping_local_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, size_t n_corner, const cm_point* surf,
+                                  size_t n_surf, cm_iso* mapped, cm_match_stats* stats);
+/* window state: frames in the queue, their corner / surf point totals, sizes of the last surround clouds (corner, surf) and
+ * FrameUpdater's accumulated distance; corner_out / surf_out (may be NULL): the window clouds in queue order */
+int cm_mapping_local_window_host(cm_ctx* ctx, int* n_frames, size_t* n_corner, size_t* n_surf, int* n_surround2, double* accum_distance,
+                                 cm_point* corner_out, size_t cap_corner, cm_point* surf_out, size_t cap_surf);
+
 /* Scan registration + mapping in one call: frames[s][row][col] organised sweeps -> mapped poses.  The less-sharp and
  * less-flat clouds of cm_scanreg_organised feed cm_mapping_process without leaving the device.  _dev: `frames` is a
  * DEVICE pointer (inputs already resident in HBM); poses and stats stay host arrays. */

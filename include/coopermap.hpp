@@ -1,6 +1,6 @@
 // coopermap.hpp -- header-only C++ facade over the C ABI (coopermap.h): the reference's stage classes with the same names and
 // the same setup / process split, so that a nodelet written against lidar_slam::{OrganisedScanRegistration,
-// MultiScanRegistration, LaserOdometry, LaserMapping, LaserLocalization, ScanMatch} keeps its shape
+// MultiScanRegistration, LaserOdometry, LaserMapping, LaserMappingLocal, LaserLocalization, ScanMatch} keeps its shape
 // (L_SLAM/src/odometry/*.h, scan_to_scan_match/ScanMatch.h, nodelet/*.cpp).  Clouds are std::vector<cm_point> (the payload
 // of pcl::PointCloud<pcl::PointXYZI>), poses are cm_iso (Eigen::Isometry3f, row-major rotation + translation) or cm_pose
 // (lidar_slam::Twist).  No PCL / Eigen / ROS types: the conversion helpers a nodelet needs are in INTEGRATION.md section 2.
@@ -178,6 +178,31 @@ class LaserLocalization : public LaserMapping {
                                             ns ? surfLast.data() : &dummy, &ns, ns ? ns : 1, &mapped, &stats_));
     return mapped;
   }
+};
+
+// LaserMappingLocal::process (LaserMappingLocal.cpp:33-78): the mapping stage over LocalFeatureMap, a sliding window of
+// voxel-filtered frames.  useMappedPose = false is the reference as written (frames placed with the never-assigned
+// _transformTobeMapped = identity), true places them with the mapped pose.
+class LaserMappingLocal {
+ public:
+  explicit LaserMappingLocal(const cm_config& cfg = Context::defaults(), bool useMappedPose = false) : ctx_(cfg) {
+    ctx_.check(cm_mapping_local_create(ctx_.get(), useMappedPose ? 1 : 0));
+  }
+  cm_iso process(const cm_iso& odom, const PointCloud& cornerLast, const PointCloud& surfLast) {
+    cm_iso mapped;
+    ctx_.check(cm_mapping_local_process_host(ctx_.get(), &odom, cornerLast.data(), cornerLast.size(), surfLast.data(), surfLast.size(),
+                                             &mapped, &stats_));
+    return mapped;
+  }
+  // frames in LocalFeatureMap's queue
+  int windowFrames() { int n = 0; ctx_.check(cm_mapping_local_window_host(ctx_.get(), &n, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0)); return n; }
+  int lastStatus() const { return stats_.status; }
+  const cm_match_stats& stats() const { return stats_; }
+  Context& context() { return ctx_; }
+
+ private:
+  Context ctx_;
+  cm_match_stats stats_ = cm_match_stats();
 };
 
 // ---- the operator ------------------------------------------------------------------------------------------------------------

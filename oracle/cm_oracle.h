@@ -179,6 +179,27 @@ class LaserMapping {
   MapParams _mp; MatchParams _sp; KnnBackend _knn;
 };
 
+// LaserMappingLocal::process (LaserMappingLocal.cpp:33-78) over LocalFeatureMap (io_module/LocalFeatureMap.h:62-99) and
+// FrameUpdater (io_module/FrameUpdater.hpp:17-42): the map is a sliding window of voxel-filtered frames, the surround cloud
+// the voxel-filtered (corner 0.2, surf 0.4, LocalFeatureMap.h:29-32) union of the window.
+// The reference places a frame in the window with `_transformTobeMapped`, a Twist that is declared (LaserMatcher.h:121) and
+// never assigned: frames enter untransformed with the identity as key pose, the travelled distance stays 0 and clean() never
+// drops a frame.  useMappedPose = false restates that literally; true uses _lidarMappedNew (the evident intent).
+struct LocalFrame { std::vector<PointI> corner, surf; double accum; };
+class LaserMappingLocal {
+ public:
+  LaserMappingLocal(const MapParams& mp, const MatchParams& sp, const KnnBackend& knn, bool useMappedPose);
+  Iso process(const Iso& odom, const std::vector<PointI>& corner, const std::vector<PointI>& surf);
+  std::vector<LocalFrame> window;     // data_queue
+  double accumDistance = 0.0;         // FrameUpdater::accum_distance
+  MatchResult lastMatch;
+  std::vector<PointI> cornerDS, surfDS, surroundCorner, surroundSurf;
+  Iso mappedLast, mappedNew, odomLast;
+ private:
+  MapParams _mp; MatchParams _sp; KnnBackend _knn; bool _useMapped;
+  bool _first = true; double _prevR[9], _prevT[3];   // FrameUpdater::is_first / prev_keypose (Isometry3d)
+};
+
 // ---- scan-to-scan odometry (LaserOdometry.cpp) -------------------------------------------------------------------
 struct OdomIterLog { float pose_in[6]; float x[6]; int rows; };
 class LaserOdometry {

@@ -214,6 +214,49 @@ void cmo_mapping_localize(void* hh, const float* odomR, const float* odomT, cons
     stats[9] = (int)m->cornerDS.size(); stats[10] = (int)m->surfDS.size(); stats[11] = stats[12] = 0;
   }
 }
+// ---- LaserMappingLocal (sliding-window map) ----------------------------------------------------------------------
+struct MappingLocalHandle { LaserMappingLocal* m; };
+void* cmo_mapping_local_create(const float* mfparams, const float* sfparams, const int* siparams, int useNanoflann, int useMappedPose) {
+  MapParams mp; MatchParams sp;
+  if (mfparams) { mp.filterCorner = mfparams[4]; mp.filterSurf = mfparams[5]; }
+  if (sfparams) { sp.deltaTAbort = sfparams[0]; sp.deltaRAbort = sfparams[1]; sp.knnGate = sfparams[2]; sp.planeMaxDistance = sfparams[3]; }
+  if (siparams) { sp.maxIterations = siparams[0]; sp.useScore = siparams[1] != 0; }
+  MappingLocalHandle* h = new MappingLocalHandle();
+  h->m = new LaserMappingLocal(mp, sp, pick_backend(useNanoflann), useMappedPose != 0);
+  return h;
+}
+void cmo_mapping_local_free(void* hh) { MappingLocalHandle* h = (MappingLocalHandle*)hh; delete h->m; delete h; }
+// stats as cmo_mapping_process, then [13] frames in the window, [14] corner points, [15] surf points of the window; accum: travelled distance
+void cmo_mapping_local_process(void* hh, const float* odomR, const float* odomT, const float* corner, size_t nc, const float* surf,
+                               size_t ns, float* outR, float* outT, int* stats, double* accum) {
+  LaserMappingLocal* m = ((MappingLocalHandle*)hh)->m;
+  Iso od; std::memcpy(od.R, odomR, 36); std::memcpy(od.t, odomT, 12);
+  std::vector<PointI> c((const PointI*)corner, (const PointI*)corner + nc), s((const PointI*)surf, (const PointI*)surf + ns);
+  Iso r = m->process(od, c, s);
+  std::memcpy(outR, r.R, 36); std::memcpy(outT, r.t, 12);
+  if (stats) {
+    const MatchResult& q = m->lastMatch;
+    stats[0] = q.ok; stats[1] = q.converged; stats[2] = q.tooFewRef; stats[3] = q.tooFewMatches; stats[4] = q.degenerate;
+    stats[5] = q.iterations; stats[6] = q.lastRows; stats[7] = q.lastLine; stats[8] = q.lastPlane;
+    stats[9] = (int)m->cornerDS.size(); stats[10] = (int)m->surfDS.size();
+    stats[11] = (int)m->surroundCorner.size(); stats[12] = (int)m->surroundSurf.size();
+    size_t wc = 0, ws = 0;
+    for (const LocalFrame& f : m->window) { wc += f.corner.size(); ws += f.surf.size(); }
+    stats[13] = (int)m->window.size(); stats[14] = (int)wc; stats[15] = (int)ws;
+  }
+  if (accum) *accum = m->accumDistance;
+}
+// window contents in queue order (which: 0 corner, 1 surf); NULL out: count only
+size_t cmo_mapping_local_window(void* hh, int which, float* out, size_t cap) {
+  LaserMappingLocal* m = ((MappingLocalHandle*)hh)->m;
+  size_t n = 0;
+  for (const LocalFrame& f : m->window) {
+    const std::vector<PointI>& v = which == 0 ? f.corner : f.surf;
+    if (out && n + v.size() <= cap) std::memcpy(out + 4 * n, v.data(), v.size() * sizeof(PointI));
+    n += v.size();
+  }
+  return n;
+}
 // saveCloudToFiles enumeration: fills type / i / j / k per file (NULL: count only); cube clouds through cmo_mapping_cube
 size_t cmo_mapping_file_order(void* hh, int* type, int* ci, int* cj, int* ck, size_t cap) {
   std::vector<int> t, a, b, c;

@@ -5,6 +5,7 @@
 #include "cm_oracle.h"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace cmo {
 
@@ -207,5 +208,82 @@ Iso LaserMapping::localize(const Iso& odomNew, const std::vector<PointI>& corner
   odomLast = odomNew;
   return mappedNew;
 }
+
+// ---- LaserMappingLocal (LaserMappingLocal.cpp:33-78) over LocalFeatureMap (io_module/LocalFeatureMap.h) -------------------
+LaserMappingLocal::LaserMappingLocal(const MapParams& mp, const MatchParams& sp, const KnnBackend& knn, bool useMappedPose)
+    : _mp(mp), _sp(sp), _knn(knn), _useMapped(useMappedPose) {
+  mappedLast = mappedNew = odomLast = iso_identity();   // LaserMatcher.cpp:31-32
+}
+
+Iso LaserMappingLocal::process(const Iso& odomNew, const std::vector<PointI>& corner, const std::vector<PointI>& surf) {
+  // transformMerge, LaserMatcher.cpp:333-340
+  Iso L2W = iso_mul(mappedLast, iso_inverse(odomLast));
+  mappedNew = iso_mul(L2W, odomNew);
+  // prepareFeatureFrame, LaserMatcher.cpp:288-301
+  voxel_filter(corner.data(), corner.size(), _mp.filterCorner, cornerDS);
+  voxel_filter(surf.data(), surf.size(), _mp.filterSurf, surfDS);
+  // prepareFeatureSurround, LaserMappingLocal.cpp:55-60 -> LocalFeatureMap::getSurroundFeature, LocalFeatureMap.h:84-99:
+  // concatenation of the window in queue order, then VoxelGrid 0.2 (corner) / 0.4 (surf), :29-31
+  std::vector<PointI> catC, catS;
+  for (const LocalFrame& f : window) {
+    catC.insert(catC.end(), f.corner.begin(), f.corner.end());
+    catS.insert(catS.end(), f.surf.begin(), f.surf.end());
+  }
+  voxel_filter(catC.data(), catC.size(), 0.2f, surroundCorner);
+  voxel_filter(catS.data(), catS.size(), 0.4f, surroundSurf);
+  // optimizeTransform, LaserMatcher.cpp:327-331
+  float pose[6];
+  iso_to_twist(mappedNew, pose);
+  scan_match(_sp, _knn, surroundCorner.data(), surroundCorner.size(), surroundSurf.data(), surroundSurf.size(),
+             cornerDS.data(), cornerDS.size(), surfDS.data(), surfDS.size(), pose, lastMatch, false);
+  twist_to_iso(pose, mappedNew);
+  // transformUpdate, LaserMatcher.cpp:342-347
+  mappedLast = mappedNew;
+  odomLast = odomNew;
+  // featureMapUpdate, LaserMappingLocal.cpp:62-76: the frame clouds are transformed IN PLACE by _transformTobeMapped
+  Iso tf = iso_identity();
+  if (_useMapped) tf = mappedNew;
+  else { const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; twist_to_iso(zero, tf); }   // convertTransform of the untouched Twist
+  LocalFrame fr;
+  auto xform = [&](const std::vector<PointI>& in, std::vector<PointI>& out) {   // transform_utils.h:601-614
+    out = in;
+    for (size_t i = 0; i < in.size(); i++) {
+      const PointI& p = in[i];
+      out[i].x = ((tf.R[0] * p.x + tf.R[1] * p.y) + tf.R[2] * p.z) + tf.t[0];
+      out[i].y = ((tf.R[3] * p.x + tf.R[4] * p.y) + tf.R[5] * p.z) + tf.t[1];
+      out[i].z = ((tf.R[6] * p.x + tf.R[7] * p.y) + tf.R[8] * p.z) + tf.t[2];
+    }
+  };
+  xform(cornerDS, fr.corner);
+  xform(surfDS, fr.surf);
+  // LocalFeatureMap::addDataFrame, :62-69 -> FrameUpdater::update, FrameUpdater.hpp:17-42 (Isometry3d of the float pose)
+  double R[9], t[3];
+  for (int k = 0; k < 9; k++) R[k] = (double)tf.R[k];
+  for (int k = 0; k < 3; k++) t[k] = (double)tf.t[k];
+  if (_first) {
+    _first = false;
+  } else {
+    // delta = prev_keypose.inverse() * pose: translation = Rp^T * t + (-(Rp^T * tp))
+    double a[3], b[3], v[3];
+    for (int r = 0; r < 3; r++) {
+      a[r] = (_prevR[0 + r] * t[0] + _prevR[3 + r] * t[1]) + _prevR[6 + r] * t[2];
+      b[r] = -((_prevR[0 + r] * _prevT[0] + _prevR[3 + r] * _prevT[1]) + _prevR[6 + r] * _prevT[2]);
+      v[r] = a[r] + b[r];
+    }
+    accumDistance += std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+  }
+  std::memcpy(_prevR, R, sizeof(R)); std::memcpy(_prevT, t, sizeof(t));
+  fr.accum = accumDistance;
+  window.push_back(std::move(fr));
+  // LocalFeatureMap::clean, :70-82 (erases one frame more than it counted)
+  int deleteNum = 0;
+  for (const LocalFrame& f : window) {
+    if (f.accum > (accumDistance - 30.0)) break;   // queue_distance_threshold(30.0), :28
+    ++deleteNum;
+  }
+  if (deleteNum > 0) window.erase(window.begin(), window.begin() + deleteNum + 1);
+  return mappedNew;
+}
+
 
 }  // namespace cmo

@@ -40,6 +40,8 @@ def lib(fast=False):
     L.cmo_mapping_file_order.restype = C.c_size_t
     L.cmo_mapping_cube.restype = C.c_size_t
     L.cmo_mapping_map_surround.restype = C.c_size_t
+    L.cmo_mapping_local_create.restype = C.c_void_p
+    L.cmo_mapping_local_window.restype = C.c_size_t
     L.has_nanoflann = bool(os.path.exists(REF_SO) and L.cmo_load_nanoflann(REF_SO.encode()))
     _libs[name] = L
     return L
@@ -359,6 +361,41 @@ class Mapping:
         n = self.L.cmo_mapping_map_surround(C.c_void_p(self.h), C.c_int(which), None, C.c_size_t(0))
         out = np.empty((max(n, 1), 4), np.float32)
         self.L.cmo_mapping_map_surround(C.c_void_p(self.h), C.c_int(which), _p(out), C.c_size_t(len(out)))
+        return out[:n].copy()
+
+
+class MappingLocal:
+    """LaserMappingLocal::process over LocalFeatureMap restated (oracle_map.cpp): sliding window of voxel-filtered frames.
+    use_mapped_pose=False is the literal reference (frames placed with the never-assigned _transformTobeMapped = identity)."""
+
+    def __init__(self, map_params=None, match_params=None, nanoflann=True, use_mapped_pose=False, fast=False):
+        self.L = lib(fast)
+        d = dict(filterCorner=1.0, filterSurf=1.0)
+        d.update(map_params or {})
+        mf = _f32([50.0, 150.0, 1.0, 1.0, d["filterCorner"], d["filterSurf"]])
+        sf, si = _match_params(match_params)
+        self.h = self.L.cmo_mapping_local_create(_p(mf), _p(sf), _p(si), C.c_int(int(nanoflann and self.L.has_nanoflann)),
+                                                 C.c_int(int(use_mapped_pose)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.cmo_mapping_local_free(C.c_void_p(self.h)); self.h = None
+
+    def process(self, odom_R, odom_t, corner, surf):
+        R = _f32(odom_R); t = _f32(odom_t)
+        c = _f32(corner).reshape(-1, 4); s = _f32(surf).reshape(-1, 4)
+        oR = np.empty((3, 3), np.float32); ot = np.empty(3, np.float32); st = np.zeros(16, np.int32); acc = C.c_double(0.0)
+        self.L.cmo_mapping_local_process(C.c_void_p(self.h), _p(R), _p(t), _p(c), C.c_size_t(len(c)), _p(s), C.c_size_t(len(s)),
+                                         _p(oR), _p(ot), _p(st), C.byref(acc))
+        keys = ["ok", "converged", "tooFewRef", "tooFewMatches", "degenerate", "iterations", "rows", "line", "plane",
+                "nCornerDS", "nSurfDS", "nSurroundCorner", "nSurroundSurf", "frames", "nWindowCorner", "nWindowSurf"]
+        d = dict(zip(keys, [int(v) for v in st])); d["accumDistance"] = float(acc.value)
+        return oR, ot, d
+
+    def window(self, which):
+        n = self.L.cmo_mapping_local_window(C.c_void_p(self.h), C.c_int(which), None, C.c_size_t(0))
+        out = np.empty((max(n, 1), 4), np.float32)
+        self.L.cmo_mapping_local_window(C.c_void_p(self.h), C.c_int(which), _p(out), C.c_size_t(len(out)))
         return out[:n].copy()
 
 

@@ -271,6 +271,38 @@ def test_mapping_loop_bootstraps_and_tracks(oracle, synth):
     assert errs[-1] < 0.08                              # mapping corrects the 5 x (0.02, 0.02, 0.01) odometry drift
 
 
+def test_mapping_local_window_literal_and_intended(oracle, synth):
+    """LaserMappingLocal over LocalFeatureMap (LaserMappingLocal.cpp:33-78, LocalFeatureMap.h:62-99).  As written the frames
+    enter the window with the never-assigned _transformTobeMapped (identity): nothing moves, nothing is dropped.  With the
+    mapped pose the window tracks, accumulates FrameUpdater's distance and clean() erases one frame more than it counted."""
+    sc = synth.make_scene(seed=41, extent=60.0, n_boxes=16, n_poles=12)
+    prm = dict(filterCorner=0.4, filterSurf=0.8)
+    lit = oracle.MappingLocal(map_params=prm, use_mapped_pose=False)
+    itd = oracle.MappingLocal(map_params=prm, use_mapped_pose=True)
+    frames_seen = []
+    for k, (R, t) in enumerate(synth.trajectory(6, speed=8.0, yaw_amp=0.02)):
+        fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=300 + k, cols=600)
+        f = oracle.scanreg_organised(fr)
+        R = R.astype(np.float32); t = t.astype(np.float32)
+        _, _, sl = lit.process(R, t, f["lessSharp"], f["lessFlat"])
+        oR, ot, si = itd.process(R, t, f["lessSharp"], f["lessFlat"])
+        assert sl["frames"] == k + 1 and sl["accumDistance"] == 0.0          # literal: identity key pose, clean() never fires
+        if k == 0:
+            assert sl["tooFewRef"] == 1 and si["tooFewRef"] == 1            # empty window on the first frame
+            assert np.array_equal(ot, t)
+        else:
+            assert si["nSurroundSurf"] > 0 and np.linalg.norm(ot - t) < 0.15
+        frames_seen.append(si["frames"])
+        # window clouds of the literal mode are the voxel-filtered frames, untransformed
+        if k == 1:
+            c0 = oracle.voxel_filter(f["lessSharp"], 0.4)
+            assert np.array_equal(lit.window(0)[-len(c0):], c0)
+    # 8 m per frame: accum 0, 8, 16, 24, 32 -> at the fifth push frame 0 is <= 32 - 30, clean() erases TWO frames (deleteNum + 1)
+    assert abs(si["accumDistance"] - 40.0) < 1.5
+    assert frames_seen[:4] == [1, 2, 3, 4] and frames_seen[4] == 3, frames_seen
+    assert frames_seen[5] == 4, frames_seen                                   # accum 40: the oldest frame (16) is > 40 - 30, nothing dropped
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the C ABI
 # ---------------------------------------------------------------------------------------------------------------

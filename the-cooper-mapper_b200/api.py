@@ -183,6 +183,31 @@ class Context:
                                                         C.c_int(scap), _ptr(mapped), stats))
         return self._unpack_results(mapped, stats)
 
+    def mapping_local_create(self, use_mapped_pose=False):
+        self._check(self.L.cm_mapping_local_create(self.h, C.c_int(int(use_mapped_pose))))
+
+    def mapping_local_process(self, odom, corner, surf):
+        """LaserMappingLocal::process for one frame: odom (R, t), corner / surf (n, 4) clouds -> ((R, t), stats)."""
+        od = self._pack_isos([odom]); c = _f32(corner, 4); s = _f32(surf, 4)
+        mapped = np.empty((1, 12), np.float32); stats = (MatchStats * 1)()
+        self._check(self.L.cm_mapping_local_process_host(self.h, _ptr(od), _ptr(c), C.c_size_t(len(c)), _ptr(s), C.c_size_t(len(s)),
+                                                         _ptr(mapped), stats))
+        isos, st = self._unpack_results(mapped, stats)
+        return isos[0], st[0]
+
+    def mapping_local_window(self, clouds=False):
+        """State of LocalFeatureMap's queue: dict(frames, nCorner, nSurf, nSurroundCorner, nSurroundSurf, accumDistance[, corner, surf])."""
+        nf = C.c_int(0); nc = C.c_size_t(0); ns = C.c_size_t(0); sur = (C.c_int * 2)(); acc = C.c_double(0.0)
+        self._check(self.L.cm_mapping_local_window_host(self.h, C.byref(nf), C.byref(nc), C.byref(ns), sur, C.byref(acc), None,
+                                                        C.c_size_t(0), None, C.c_size_t(0)))
+        d = dict(frames=nf.value, nCorner=nc.value, nSurf=ns.value, nSurroundCorner=sur[0], nSurroundSurf=sur[1], accumDistance=acc.value)
+        if clouds:
+            c = np.empty((max(nc.value, 1), 4), np.float32); s = np.empty((max(ns.value, 1), 4), np.float32)
+            self._check(self.L.cm_mapping_local_window_host(self.h, None, None, None, None, None, _ptr(c), C.c_size_t(len(c)), _ptr(s),
+                                                            C.c_size_t(len(s))))
+            d["corner"] = c[:nc.value].copy(); d["surf"] = s[:ns.value].copy()
+        return d
+
     def map_save(self, stream, directory):
         """FeatureMap::saveCloudToFiles: index.txt + <count>.pcd; returns the number of files."""
         n = C.c_int(0)
@@ -466,6 +491,21 @@ class LaserMapping:
         isos, stats = self.ctx.mapping_process([(odom_R, odom_t)], [laserCloudCornerLast], [laserCloudSurfLast])
         self.last_stats = stats[0]
         return isos[0]
+
+
+class LaserMappingLocal:
+    """Mirror of lidar_slam::LaserMappingLocal (LaserMappingLocal.h): the mapping stage over LocalFeatureMap, a sliding
+    window of voxel-filtered frames (30 m of travel).  use_mapped_pose=False is the reference as written (frames placed with
+    the never-assigned _transformTobeMapped, i.e. the identity); True places them with the mapped pose."""
+
+    def __init__(self, ctx=None, use_mapped_pose=False, **cfg):
+        self.ctx = ctx or Context(**cfg)
+        self.ctx.mapping_local_create(use_mapped_pose)
+        self.last_stats = None
+
+    def process(self, odom_R, odom_t, laserCloudCornerLast, laserCloudSurfLast):
+        iso, self.last_stats = self.ctx.mapping_local_process((odom_R, odom_t), laserCloudCornerLast, laserCloudSurfLast)
+        return iso
 
 
 class LaserLocalization:

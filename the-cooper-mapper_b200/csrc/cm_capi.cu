@@ -141,8 +141,8 @@ void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_
 }  // namespace cm
 extern "C" {
 
-// ScanMatch::scanMatchScan on clouds that are already in device memory (host counts).
-static int match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,
+// ScanMatch::scanMatchScan on clouds that are already in device memory (host counts).  Internal (declared in cm_ctx.h).
+int cm_match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,
                                const float4* d_s, size_t ns, cm_pose* pose, cm_match_stats* stats, cm_iter_trace* trace,
                                int* nn_corner, int* nn_surf) {
   const cm_config& cfg = ctx->cfg;
@@ -227,7 +227,7 @@ int cm_match_stateless_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc,
     if (nrs) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_surf.p, ref_surf, nrs * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_corner.p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
     if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_surf.p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    return match_stateless_dev(ctx, (const float4*)ctx->d_ref_corner.p, nrc, (const float4*)ctx->d_ref_surf.p, nrs,
+    return cm_match_stateless_dev(ctx, (const float4*)ctx->d_ref_corner.p, nrc, (const float4*)ctx->d_ref_surf.p, nrs,
                                (const float4*)ctx->d_corner.p, nc, (const float4*)ctx->d_surf.p, ns, pose, stats, trace, nn_corner, nn_surf);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
@@ -261,7 +261,7 @@ int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t nrc, con
     int nout[4];
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nout, ctx->d_vn_out.p, sizeof(nout), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    return match_stateless_dev(ctx, (const float4*)ds[0]->p, nout[0], (const float4*)ds[1]->p, nout[1], (const float4*)ds[2]->p, nout[2],
+    return cm_match_stateless_dev(ctx, (const float4*)ds[0]->p, nout[0], (const float4*)ds[1]->p, nout[1], (const float4*)ds[2]->p, nout[2],
                                (const float4*)ds[3]->p, nout[3], pose, stats, nullptr, nullptr, nullptr);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));

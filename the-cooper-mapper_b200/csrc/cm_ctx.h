@@ -2,6 +2,8 @@
 #pragma once
 #include "../../include/coopermap.h"
 #include "cm_host.h"
+#include <deque>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -13,6 +15,16 @@ struct MappingStream {
   HostIso mappedLast, mappedNew, odomLast;
   int origin[3];   // _cubeOriginWidth/Height/Depth
   int cur[3];      // _curCubeWidth/Height/Depth
+};
+
+// LaserMappingLocal (cm_mapping.cu): one DataFrame of LocalFeatureMap's data_queue, clouds resident on the device
+struct LocalFrame { DeviceBuffer corner, surf; int nc = 0, ns = 0; double accum = 0.0; };
+struct LocalWindow {
+  bool created = false, use_mapped = false;
+  std::deque<std::unique_ptr<LocalFrame>> frames;   // LocalFeatureMap::data_queue
+  double accum = 0.0; bool first = true; double prevR[9], prevT[3];   // FrameUpdater: accum_distance, is_first, prev_keypose
+  HostIso mappedLast, mappedNew, odomLast;
+  int n_surround[2] = {0, 0};
 };
 
 }  // namespace cm
@@ -56,6 +68,7 @@ struct cm_ctx {
   // sharded-map matching (cm_shard_*): persistent grids in grid_a / grid_b
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
+  cm::LocalWindow local;               // cm_mapping_local_*
   cm::KernelProfiler prof, prof_sr;   // search_kernel + search_hard_kernel / sr_ring_kernel launches of the pipeline
   cudaEvent_t timer[2] = {nullptr, nullptr};
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
@@ -85,6 +98,10 @@ int ctx_fail(cm_ctx* ctx, int code, const std::string& msg);
 void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L);
 void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out);
 }  // namespace cm
+
+extern "C" int cm_match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,
+                                      const float4* d_s, size_t ns, cm_pose* pose, cm_match_stats* stats, cm_iter_trace* trace,
+                                      int* nn_corner, int* nn_surf);
 
 #define CM_CUDA_CHECK(ctx, expr)                                                                                    \
   do {                                                                                                              \

@@ -96,6 +96,17 @@ __global__ void gather_counts_kernel(const int* __restrict__ n5, int* __restrict
   if (s < S) { n2[s] = n5[s * 5 + 1]; n2[S + s] = n5[s * 5 + 3]; }   // lessSharp -> corner, lessFlat -> surf
 }
 
+// transformPointCloud (transform_utils.h:601-614) of a filtered frame cloud into a window frame (LaserMappingLocal.cpp:67-70)
+struct IsoArg { float R[9]; float t[3]; };
+__global__ void local_transform_kernel(const float4* __restrict__ in, int n, IsoArg tf, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  float4 q; q.w = p.w;
+  transform_point(tf.R, tf.t, p.x, p.y, p.z, &q.x, &q.y, &q.z);
+  out[i] = q;
+}
+
 static int default_kdiv(float cell, float leaf, int mult) {
   if (cell > 0.f) { int k = (int)floorf(cell / leaf + 0.5f); return k < 1 ? 1 : k; }
   return mult;
@@ -333,6 +344,146 @@ int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* cor
 int cm_localization_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
                                  const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats) {
   return mapping_process_host(ctx, odom, corner, n_corner, cap_corner, surf, n_surf, cap_surf, mapped, stats, true);
+}
+
+// ---- LaserMappingLocal: the mapping stage over a sliding window of frames (LocalFeatureMap) ---------------------------------
+int cm_mapping_local_create(cm_ctx* ctx, int use_mapped_pose) {
+  if (!ctx) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  LocalWindow& w = ctx->local;
+  w.frames.clear();
+  w.created = true; w.use_mapped = use_mapped_pose != 0;
+  w.accum = 0.0; w.first = true;
+  w.mappedLast = w.mappedNew = w.odomLast = iso_identity();   // LaserMatcher.cpp:31-32
+  w.n_surround[0] = w.n_surround[1] = 0;
+  return CM_OK;
+}
+
+int cm_mapping_local_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, size_t nc, const cm_point* surf, size_t ns,
+                                  cm_iso* mapped, cm_match_stats* stats) {
+  if (!ctx || !ctx->local.created) return fail(ctx, CM_ERR_ARG, "cm_mapping_local_create has not been called");
+  if (!odom || (!corner && nc) || (!surf && ns) || nc > 0x7fffffffu || ns > 0x7fffffffu) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const cm_config& cfg = ctx->cfg;
+    cudaStream_t st = ctx->stream;
+    LocalWindow& w = ctx->local;
+    // transformMerge, LaserMatcher.cpp:333-340
+    HostIso odomNew; memcpy(odomNew.R, odom->R, 36); memcpy(odomNew.t, odom->t, 12);
+    w.mappedNew = iso_mul(iso_mul(w.mappedLast, iso_inverse(w.odomLast)), odomNew);
+    // window totals; the concatenation (LocalFeatureMap.h:88-92) is a device-to-device gather in queue order
+    size_t wc = 0, wsn = 0;
+    for (auto& f : w.frames) { wc += (size_t)f->nc; wsn += (size_t)f->ns; }
+    if (wc > 0x7fffffffu || wsn > 0x7fffffffu) return fail(ctx, CM_ERR_CAPACITY, "window too large");
+    // slots: 0 window corner, 1 window surf (leaf 0.2 / 0.4, LocalFeatureMap.h:29-31), 2 frame corner, 3 frame surf (prepareFeatureFrame)
+    const size_t n[4] = {wc, wsn, nc, ns};
+    const float leaf[4] = {0.2f, 0.4f, cfg.filter_corner, cfg.filter_surf};
+    DeviceBuffer* raw[4] = {&ctx->d_ref_corner, &ctx->d_ref_surf, &ctx->d_corner, &ctx->d_surf};
+    DeviceBuffer* ds[4] = {&ctx->d_l_ds[0], &ctx->d_l_ds[1], &ctx->d_l_ds[2], &ctx->d_l_ds[3]};
+    ctx->d_vn_in.reserve(4 * sizeof(int)); ctx->d_vn_out.reserve(4 * sizeof(int)); ctx->d_flag.reserve(sizeof(int));
+    int nin[4] = {(int)wc, (int)wsn, (int)nc, (int)ns};
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vn_in.p, nin, sizeof(nin), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; k++) { const size_t cap = n[k] ? n[k] : 1; raw[k]->reserve(cap * sizeof(cm_point)); ds[k]->reserve(cap * sizeof(cm_point)); }
+    {
+      size_t oc = 0, os = 0;
+      for (auto& f : w.frames) {
+        if (f->nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync((float4*)raw[0]->p + oc, f->corner.p, (size_t)f->nc * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        if (f->ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync((float4*)raw[1]->p + os, f->surf.p, (size_t)f->ns * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        oc += (size_t)f->nc; os += (size_t)f->ns;
+      }
+    }
+    if (nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(raw[2]->p, corner, nc * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(raw[3]->p, surf, ns * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; k++) {
+      const size_t cap = n[k] ? n[k] : 1;
+      ctx->voxel.run(1, (const float4*)raw[k]->p, (const int*)ctx->d_vn_in.p + k, (int)cap, (int)n[k], leaf[k], (float4*)ds[k]->p,
+                     (int*)ctx->d_vn_out.p + k, (int)cap, (int*)ctx->d_flag.p, st);
+    }
+    int nout[4];
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nout, ctx->d_vn_out.p, sizeof(nout), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    w.n_surround[0] = nout[0]; w.n_surround[1] = nout[1];
+    // optimizeTransform, LaserMatcher.cpp:327-331
+    float pose6[6];
+    iso_to_twist(w.mappedNew, pose6);
+    cm_pose tw; tw.rx = pose6[0]; tw.ry = pose6[1]; tw.rz = pose6[2]; tw.tx = pose6[3]; tw.ty = pose6[4]; tw.tz = pose6[5];
+    const int rc = cm_match_stateless_dev(ctx, (const float4*)ds[0]->p, (size_t)nout[0], (const float4*)ds[1]->p, (size_t)nout[1],
+                                          (const float4*)ds[2]->p, (size_t)nout[2], (const float4*)ds[3]->p, (size_t)nout[3], &tw, stats,
+                                          nullptr, nullptr, nullptr);
+    if (rc < 0) return rc;
+    pose6[0] = tw.rx; pose6[1] = tw.ry; pose6[2] = tw.rz; pose6[3] = tw.tx; pose6[4] = tw.ty; pose6[5] = tw.tz;
+    twist_to_iso(pose6, w.mappedNew);   // ScanMatch.cpp:358
+    // transformUpdate, LaserMatcher.cpp:342-347
+    w.mappedLast = w.mappedNew;
+    w.odomLast = odomNew;
+    if (mapped) { memcpy(mapped->R, w.mappedNew.R, 36); memcpy(mapped->t, w.mappedNew.t, 12); }
+    // featureMapUpdate, LaserMappingLocal.cpp:62-76
+    HostIso tf;
+    if (w.use_mapped) tf = w.mappedNew;
+    else { const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; twist_to_iso(zero, tf); }   // convertTransform of the never-assigned Twist
+    std::unique_ptr<LocalFrame> fr(new LocalFrame());
+    fr->nc = nout[2]; fr->ns = nout[3];
+    fr->corner.reserve((size_t)(fr->nc ? fr->nc : 1) * sizeof(float4));
+    fr->surf.reserve((size_t)(fr->ns ? fr->ns : 1) * sizeof(float4));
+    IsoArg ta; memcpy(ta.R, tf.R, 36); memcpy(ta.t, tf.t, 12);
+    if (fr->nc) CM_LAUNCH(local_transform_kernel, (fr->nc + 255) / 256, 256, 0, st, (const float4*)ds[2]->p, fr->nc, ta, (float4*)fr->corner.p);
+    if (fr->ns) CM_LAUNCH(local_transform_kernel, (fr->ns + 255) / 256, 256, 0, st, (const float4*)ds[3]->p, fr->ns, ta, (float4*)fr->surf.p);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    // LocalFeatureMap::addDataFrame (:62-69) -> FrameUpdater::update (FrameUpdater.hpp:17-42) on the Isometry3d of the float pose
+    double R[9], t[3];
+    for (int k = 0; k < 9; k++) R[k] = (double)tf.R[k];
+    for (int k = 0; k < 3; k++) t[k] = (double)tf.t[k];
+    if (w.first) {
+      w.first = false;
+    } else {
+      // delta = prev_keypose.inverse() * pose; its translation = Rp^T * t + (-(Rp^T * tp))
+      double v[3];
+      for (int r = 0; r < 3; r++) {
+        const double a = (w.prevR[0 + r] * t[0] + w.prevR[3 + r] * t[1]) + w.prevR[6 + r] * t[2];
+        const double b = -((w.prevR[0 + r] * w.prevT[0] + w.prevR[3 + r] * w.prevT[1]) + w.prevR[6 + r] * w.prevT[2]);
+        v[r] = a + b;
+      }
+      w.accum += sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    }
+    memcpy(w.prevR, R, sizeof(R)); memcpy(w.prevT, t, sizeof(t));
+    fr->accum = w.accum;
+    w.frames.push_back(std::move(fr));
+    // LocalFeatureMap::clean (:70-82): counts the leading frames more than queue_distance_threshold (30 m) behind and erases
+    // one more than it counted
+    int del = 0;
+    for (auto& f : w.frames) {
+      if (f->accum > (w.accum - 30.0)) break;
+      ++del;
+    }
+    if (del > 0) w.frames.erase(w.frames.begin(), w.frames.begin() + del + 1);
+    return rc;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+int cm_mapping_local_window_host(cm_ctx* ctx, int* n_frames, size_t* n_corner, size_t* n_surf, int* n_surround2, double* accum_distance,
+                                 cm_point* corner_out, size_t cap_corner, cm_point* surf_out, size_t cap_surf) {
+  if (!ctx || !ctx->local.created) return fail(ctx, CM_ERR_ARG, "cm_mapping_local_create has not been called");
+  cudaSetDevice(ctx->cfg.device);
+  LocalWindow& w = ctx->local;
+  size_t wc = 0, wsn = 0;
+  for (auto& f : w.frames) { wc += (size_t)f->nc; wsn += (size_t)f->ns; }
+  if (n_frames) *n_frames = (int)w.frames.size();
+  if (n_corner) *n_corner = wc;
+  if (n_surf) *n_surf = wsn;
+  if (n_surround2) { n_surround2[0] = w.n_surround[0]; n_surround2[1] = w.n_surround[1]; }
+  if (accum_distance) *accum_distance = w.accum;
+  if ((corner_out && cap_corner < wc) || (surf_out && cap_surf < wsn)) return fail(ctx, CM_ERR_CAPACITY, "output buffer too small");
+  size_t oc = 0, os = 0;
+  for (auto& f : w.frames) {
+    if (corner_out && f->nc) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(corner_out + oc, f->corner.p, (size_t)f->nc * sizeof(cm_point), cudaMemcpyDeviceToHost, ctx->stream));
+    if (surf_out && f->ns) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(surf_out + os, f->surf.p, (size_t)f->ns * sizeof(cm_point), cudaMemcpyDeviceToHost, ctx->stream));
+    oc += (size_t)f->nc; os += (size_t)f->ns;
+  }
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return CM_OK;
 }
 
 // Full pipeline: OrganisedScanRegistration::process -> (/laser_cloud_less_sharp, /laser_cloud_less_flat) ->
