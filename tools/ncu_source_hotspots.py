@@ -44,7 +44,7 @@ def main():
     L = launches[which]["lines"]
     ts = sum(v[0] for v in L.values()); ti = sum(v[1] for v in L.values()); tt = sum(v[2] for v in L.values())
     print("launch %d/%d: samples %d, warp-instr %d, thread-instr %d (lanes/instr %.1f)" % (which, len(launches), ts, ti, tt, tt / max(ti, 1)))
-    for (f, ln), v in sorted(L.items(), key=lambda kv: -kv[1][0])[:top_n]:
+    for (f, ln), v in sorted(L.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("HOTSPOT_SORT", "0"))])[:top_n]:
         print("%5.1f%% smp %5.1f%% inst lanes %4.1f  %s:%s  %s" % (100.0 * v[0] / max(ts, 1), 100.0 * v[1] / max(ti, 1), v[2] / max(v[1], 1), f, ln, v[3][:90]))
 
 
