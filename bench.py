@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="LiDAR streams per GPU")
     ap.add_argument("--pool", type=int, default=12, help="distinct synthetic sweeps generated on the host")
+    ap.add_argument("--ahead", type=int, default=2, help="end-to-end arm: sweeps uploaded ahead of the one being registered (1..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="after the timed arms, run 2 more steps with every launch event-timed and print per-kernel totals to stderr")
@@ -283,25 +284,22 @@ def main():
     # ---- end-to-end arm: pinned host sweeps through the C ABI --------------------------------------------------------
     ring_host = [torch.from_numpy(np.ascontiguousarray(frames[order[NBUF + b]])).pin_memory() for b in range(NBUF)]
     host_np = [ring_host[k % NBUF].numpy() for k in range(n_steps)]
-    ctx.pipeline_prefetch(host_np[0])
-    if W > 1:
-        ctx.pipeline_prefetch(host_np[1])
-    for k in range(W):
-        if k + 2 < W:
-            ctx.pipeline_prefetch(host_np[k + 2])
-        ctx.pipeline_step_packed(host_np[k], odom[n_steps + k], mapped, stats)
+    A = min(max(args.ahead, 1), 3)
+
+    def e2e_steps(first, count):
+        # `A` sweeps ahead: upload of step k+A (copy streams) | scan registration of the steps before it (side stream) | matching
+        # of step k (main stream); every step's sweeps cross PCIe, the poses of step k are read back before step k+1 is issued
+        for j in range(first, min(first + A, first + count)):
+            ctx.pipeline_prefetch(host_np[j])
+        for k in range(first, first + count):
+            if k + A < first + count:
+                ctx.pipeline_prefetch(host_np[k + A])
+            ctx.pipeline_step_packed(host_np[k], odom[n_steps + k], mapped, stats)
+
+    e2e_steps(0, W)
     barrier()
     ctx.timer_record(0)
-    # every step's sweeps cross PCIe inside the timed region; the upload of step k+1 (cm_pipeline_prefetch_host, second
-    # CUDA stream) overlaps the kernels of step k, the poses of step k are read back before step k+1 is issued
-    # two sweeps ahead: upload of step k+2 (copy stream) | scan registration of step k+1 (side stream) | matching of step k
-    ctx.pipeline_prefetch(host_np[W])
-    if K > 1:
-        ctx.pipeline_prefetch(host_np[W + 1])
-    for k in range(W, W + K):
-        if k + 2 < W + K:
-            ctx.pipeline_prefetch(host_np[k + 2])
-        ctx.pipeline_step_packed(host_np[k], odom[n_steps + k], mapped, stats)
+    e2e_steps(W, K)
     ctx.timer_record(1)
     e2e_ms = ctx.timer_elapsed_ms()
     barrier()
@@ -357,7 +355,7 @@ def main():
             "config": {"workload": workload, "streams_per_gpu": S, "points_per_sweep": NPTS, "map_points_per_stream": int(sum(map_pts)),
                        "frame_leaf": [CFG["filter_corner"], CFG["filter_surf"]], "map_leaf": [CFG["map_filter_corner"], CFG["map_filter_surf"]],
                        "mean_gn_iterations": float(np.mean(iters)), "converged_frac": conv,
-                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush",
+                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush", "e2e_sweeps_ahead": A,
                        "parallelism": "streams sharded over ranks, no collective"},
             "roofline": {"bound": "hbm", "kernel": "search_kernel + search_hard_kernel (pointAssociateToMap + exact 5-NN on the voxel-cell hash map)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),

@@ -200,8 +200,8 @@ int cm_mapping_local_window_host(cm_ctx* ctx, int* n_frames, size_t* n_corner, s
  * the host variant uploads them (pinned host memory), both run scan registration on them.  The following
  * cm_pipeline_step_host / _dev call with the same `frames` pointer consumes that work instead of redoing it, so the
  * host-to-device transfer and the (issue-bound) feature extraction of step k+1 overlap the (latency-bound) matching and map
- * kernels of step k -- the nodelet receives the next PointCloud2 while the current one is being registered.  At most three
- * sweeps may be in flight (one being consumed, two pending); the buffer must stay untouched until its step has run.  Results are identical either way. */
+ * kernels of step k -- the nodelet receives the next PointCloud2 while the current one is being registered.  At most four
+ * sweeps may be in flight (one being consumed, three pending); the buffer must stay untouched until its step has run.  Results are identical either way. */
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols);
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols);
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,

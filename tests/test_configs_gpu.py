@@ -225,9 +225,9 @@ def test_prefetched_steps_equal_synchronous_steps(cmb, synth):
     ng = C.c_int(0); wl = C.c_int(0)
     b._check(b.L.cm_debug_graph_info(b.h, C.byref(ng), C.byref(wl)))
     assert ng.value >= 1 and wl.value == 1
-    # at most three sweeps in flight
-    for k in range(3):
+    # at most four sweeps in flight
+    for k in range(4):
         b.pipeline_prefetch(frames[k])
     with pytest.raises(cmb.CoopermapError):
-        b.pipeline_prefetch(frames[3])
+        b.pipeline_prefetch(frames[4])
     a.close(); b.close()

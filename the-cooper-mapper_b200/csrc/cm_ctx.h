@@ -84,7 +84,7 @@ struct cm_ctx {
     cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr;
     size_t frames_valid = 0;
   };
-#define CM_PIPE_SLOTS 3            // prefetch slots (one being consumed + two pending); pipe[CM_PIPE_SLOTS] is the synchronous path
+#define CM_PIPE_SLOTS 4            // prefetch slots (one being consumed + three pending); pipe[CM_PIPE_SLOTS] is the synchronous path
   PipeSlot pipe[CM_PIPE_SLOTS + 1];
   // scan registration ahead of time / sweep upload.  The upload is split over TWO copy streams: one host-to-device stream
   // reaches 36.6 GB/s on the B200 boxes measured, two concurrent ones 53.6 GB/s (tools/h2d_bandwidth.py)

@@ -547,7 +547,7 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
     if (!ctx->copy_stream2) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
     int si = -1;
     for (int i = 0; i < CM_PIPE_SLOTS; i++) if (!ctx->pipe[i].src) { si = i; break; }
-    if (si < 0) return fail(ctx, CM_ERR_ARG, "three sweeps are already pending: run cm_pipeline_step on one of them first");
+    if (si < 0) return fail(ctx, CM_ERR_ARG, "four sweeps are already pending: run cm_pipeline_step on one of them first");
     cm_ctx::PipeSlot& slot = ctx->pipe[si];
     if (!slot.done) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
     if (!slot.copied) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied, cudaEventDisableTiming));
