@@ -112,30 +112,68 @@ def cpu_arm(mc, ms, frames, poses, frames_per_worker, warm=1, workers=None):
 # ---------------------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu = gpu_index; self.stop_flag = False; self.samples = []; self.reasons = set(); self.max_mhz = None
+class ClockSampler:
+    """The profiling recipe's clocks line: ONE `nvidia-smi -lms` process, started before the warm-up (its start-up takes the
+    driver's lock for tens of ms and must not land in a timed region) and killed after the last timed step; the summary uses
+    the samples that fall inside the timed regions (mark_begin() / mark_end())."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+    def __init__(self, gpu_index, period_ms=50):
+        self.gpu = gpu_index; self.period_ms = period_ms; self.rows = []; self.proc = None; self.thread = None
+        self.windows = []
+
+    def start(self):
+        try:
+            import shutil
+            pre = ["stdbuf", "-oL"] if shutil.which("stdbuf") else []   # line-buffered pipe: samples arrive as they are taken
+            self.proc = subprocess.Popen(pre + ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                                "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    try:   # nvidia-smi's own sample time (local time, ms resolution); arrival time if it does not parse
+                        ts = time.mktime(time.strptime(f[0][:19], "%Y/%m/%d %H:%M:%S")) + float("0" + f[0][19:])
+                    except ValueError:
+                        ts = time.time()
+                    self.rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(self.NAMES, f[3:]) if v.lower().startswith("active")]))
+                except (ValueError, IndexError):
+                    pass
+        except Exception:
+            pass
+
+    def mark_begin(self):
+        self.windows.append([time.time(), None])
+
+    def mark_end(self):
+        self.windows[-1][1] = time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self.proc.wait(timeout=2)
             except Exception:
-                pass
-            time.sleep(0.2)
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        rows = [r for r in self.rows if any(w[1] is not None and w[0] - 0.03 <= r[0] <= w[1] + 0.03 for w in self.windows)]
+        where = "timed regions"
+        if not rows:
+            rows = self.rows; where = "whole run (no sample fell inside the timed regions)"
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": rows[-1][2] if rows else None,
+                "reasons": reasons, "samples": len(rows), "window": where}
 
 
 def measured_peak():
@@ -158,7 +196,7 @@ def ncu_traffic():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="LiDAR streams per GPU")
@@ -240,6 +278,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled by rank 0 only (its own GPU): the other ranks' GPUs run the same work at the same time
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # ---- device-resident arm ------------------------------------------------------------------------------------
     ctx.pipeline_prefetch_dev(step_dev[0].data_ptr(), ROWS, COLS)
     for k in range(W):                                       # warm-up through the same (pipelined) path as the timed steps
@@ -247,11 +290,7 @@ def main():
             ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS)
         ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
     barrier()
-    # clocks are sampled by rank 0 only (its own GPU): one nvidia-smi process per rank every 0.1 s would take the driver's global
-    # lock 80 times a second on an 8-GPU box and perturb the launch-bound part of every rank's step
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ctx.prof_enable(True); ctx.prof_drain()
     launches0 = ctx.launch_count()
     qi = q = ins = feat = 0
@@ -269,6 +308,7 @@ def main():
         iters += [st.iterations for st in stats]
     ctx.timer_record(1)
     ms_total = ctx.timer_elapsed_ms()
+    sampler.mark_end()
     barrier()
     corr_ms, corr_launches = ctx.prof_drain()
     sr_ms, sr_launches = ctx.prof_drain_scanreg()
@@ -298,14 +338,14 @@ def main():
 
     e2e_steps(0, W)
     barrier()
+    sampler.mark_begin()
     ctx.timer_record(0)
     e2e_steps(W, K)
     ctx.timer_record(1)
     e2e_ms = ctx.timer_elapsed_ms()
     barrier()
-    sampler.stop_flag = True
-    if rank == 0:
-        sampler.join(timeout=2)
+    sampler.mark_end()
+    sampler.stop()
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,8 +404,8 @@ def main():
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
                          # the other large kernel of the step, same accounting (16 B per raw point read + 16 B per
                          # feature point written); it runs on the side stream concurrently with the matching kernels
-                         "scan_registration": {"kernel": "sr_ring_kernel", "ms_per_step": sr_ms / max(sr_launches, 1),
-                                               "achieved": (16.0 * S * NPTS + 16.0 * feat / K) / (sr_ms / max(sr_launches, 1) * 1e-3) / 1e9 if sr_ms > 0 else 0.0,
+                         "scan_registration": {"kernel": "sr_ring_kernel", "ms_per_step": sr_ms / K,
+                                               "achieved": (16.0 * S * NPTS + 16.0 * feat / K) / (sr_ms / K * 1e-3) / 1e9 if sr_ms > 0 else 0.0,
                                                "unit": "GB/s", "launches": sr_launches}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(S * NPTS * 16 + S * 48),

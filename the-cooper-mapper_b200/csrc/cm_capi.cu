@@ -71,6 +71,7 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->copy_stream2) { cudaStreamSynchronize(ctx->copy_stream2); cudaStreamDestroy(ctx->copy_stream2); }
+  for (int i = 0; i < 2; i++) if (ctx->copy_stream_x[i]) { cudaStreamSynchronize(ctx->copy_stream_x[i]); cudaStreamDestroy(ctx->copy_stream_x[i]); }
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   for (int g = 0; g < CM_MAX_GN_GROUPS; g++) {
     if (ctx->gn_stream[g]) { cudaStreamSynchronize(ctx->gn_stream[g]); cudaStreamDestroy(ctx->gn_stream[g]); }
@@ -81,8 +82,10 @@ void cm_ctx_destroy(cm_ctx* ctx) {
     if (ctx->pipe[i].done) cudaEventDestroy(ctx->pipe[i].done);
     if (ctx->pipe[i].copied) cudaEventDestroy(ctx->pipe[i].copied);
     if (ctx->pipe[i].copied2) cudaEventDestroy(ctx->pipe[i].copied2);
+    for (int j = 0; j < 2; j++) if (ctx->pipe[i].copied_x[j]) cudaEventDestroy(ctx->pipe[i].copied_x[j]);
   }
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;
 }
 

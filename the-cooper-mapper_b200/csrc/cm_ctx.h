@@ -69,6 +69,10 @@ struct cm_ctx {
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
   cm::LocalWindow local;               // cm_mapping_local_*
+  // pinned, device-accessible host staging for the per-step parameter uploads of the mapping stage (poses, cube windows): they
+  // are copied by a kernel, not by the copy engine that the sweep uploads keep busy
+  void* h_stage = nullptr; size_t h_stage_cap = 0;
+  std::vector<unsigned char> wins_shadow;   // the cube windows last sent to the device (they rarely change from sweep to sweep)
   cm::KernelProfiler prof, prof_sr;   // search_kernel + search_hard_kernel / sr_ring_kernel launches of the pipeline
   cudaEvent_t timer[2] = {nullptr, nullptr};
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
@@ -81,7 +85,7 @@ struct cm_ctx {
     cm::DeviceBuffer frames, pts[4], n, box;   // box: [2][S] VoxBox of the less-sharp / less-flat clouds (frame voxel filters)
     cm::ScanRegistrationGpu scanreg;
     const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
-    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr;
+    cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, copied_x[2] = {nullptr, nullptr};
     size_t frames_valid = 0;
   };
 #define CM_PIPE_SLOTS 4            // prefetch slots (one being consumed + three pending); pipe[CM_PIPE_SLOTS] is the synchronous path
@@ -89,6 +93,7 @@ struct cm_ctx {
   // scan registration ahead of time / sweep upload.  The upload is split over TWO copy streams: one host-to-device stream
   // reaches 36.6 GB/s on the B200 boxes measured, two concurrent ones 53.6 GB/s (tools/h2d_bandwidth.py)
   cudaStream_t side_stream = nullptr, copy_stream = nullptr, copy_stream2 = nullptr;
+  cudaStream_t copy_stream_x[2] = {nullptr, nullptr};   // optional third / fourth copy stream (COOPERMAP_COPY_STREAMS)
   int p_cap = 0;
 };
 

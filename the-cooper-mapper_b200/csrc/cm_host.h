@@ -224,6 +224,10 @@ struct VoxelFilter {
            int* d_overflow, cudaStream_t stream, const VoxBox* d_box_ready = nullptr, int idx_bits = 32);
 };
 
+// Small parameter uploads without the copy engine: `pinned` is device-accessible pinned host memory, a kernel reads it over
+// PCIe and writes `d_dst`.  (cm_map.cu)
+void staged_upload(void* d_dst, const void* pinned, size_t bytes, cudaStream_t stream);
+
 // K7: device-resident local map (cm_map.cu)
 struct MapClassDev {            // one class (corner / surf) of one stream, lives in device memory
   CellEntry* entries; unsigned int* cellcap; unsigned int* pending; unsigned int mask;
@@ -246,7 +250,10 @@ struct DeviceMap {
   DeviceBuffer n_pending[2], world[2], keys_a[2], keys_b[2], vals_a[2], vals_b[2], pending[2];   // insert scratch per class: the two classes may run on different streams
   unsigned int table_cap[2] = {0, 0}, pool_cap[2] = {0, 0};
   void create(int nstreams, const MapConfig& c, cudaStream_t stream);
-  void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream);   // also refreshes the GridViews
+  // also refreshes the GridViews.  staged: h_windows is pinned, device-accessible host memory -> copied by a kernel instead of
+  // a host-to-device memcpy (a small memcpy queues behind the sweep uploads that keep the copy engine busy)
+  // h_windows == NULL: the windows on the device are still current (only the views are refreshed)
+  void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream, bool staged = false);
   // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
   void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream);
   size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);

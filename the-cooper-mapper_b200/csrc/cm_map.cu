@@ -19,6 +19,7 @@
 // ~3 km / +-125 m vertically) is not implemented: cm_map_update reports CM_ERR_UNSUPPORTED.
 #include "cm_host.h"
 #include "cm_math.h"
+#include <algorithm>
 
 namespace cm {
 
@@ -305,8 +306,20 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
   cudaStreamSynchronize(stream);   // h goes out of scope
 }
 
-void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream) {
-  cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
+__global__ void stage_copy_kernel(const unsigned int* __restrict__ src, unsigned int* __restrict__ dst, size_t nwords) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void staged_upload(void* d_dst, const void* pinned, size_t bytes, cudaStream_t stream) {
+  const size_t nwords = (bytes + 3) / 4;   // both buffers are allocated in multiples of 4 bytes
+  if (!nwords) return;
+  const unsigned int nb = (unsigned int)std::min<size_t>((nwords + 255) / 256, 64);
+  CM_LAUNCH(stage_copy_kernel, nb, 256, 0, stream, (const unsigned int*)pinned, (unsigned int*)d_dst, nwords);
+}
+
+void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream, bool staged) {
+  if (!h_windows) {}
+  else if (staged) staged_upload(windows.p, h_windows, sizeof(CubeWindow) * nstreams, stream);
+  else cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
   for (int cls = 0; cls < 2; cls++)
     CM_LAUNCH(map_view_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
               (GridView*)views[cls].p, nstreams, gate);

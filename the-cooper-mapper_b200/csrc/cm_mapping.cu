@@ -134,6 +134,7 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
     mc.dims[0] = c.cube_w; mc.dims[1] = c.cube_h; mc.dims[2] = c.cube_d;
     for (int k = 0; k < 3; k++) mc.origin[k] = (int)round((mc.dims[k] - 1) / 2.0);   // FeatureMap.h:63-65
     ctx->map.create(nstreams, mc, ctx->stream);
+    ctx->wins_shadow.clear();
     ctx->map_streams = nstreams;
     ctx->mstreams.assign(nstreams, MappingStream());
     for (auto& st : ctx->mstreams) {
@@ -166,8 +167,17 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     prm.min_ref_corner = 0; prm.min_ref_surf = 0;
   }
   // transformMerge
-  std::vector<float> pose_in(6 * S);
-  std::vector<CubeWindow> wins(S);
+  // poses and cube windows go to the device through pinned staging + a copy kernel (COOPERMAP_STAGED_UPLOAD=0: plain memcpys)
+  static const bool staged = !(getenv("COOPERMAP_STAGED_UPLOAD") && atoi(getenv("COOPERMAP_STAGED_UPLOAD")) == 0);
+  const size_t pose_bytes = (sizeof(float) * 6 * S + 255) & ~(size_t)255, stage_bytes = pose_bytes + sizeof(CubeWindow) * S;
+  if (ctx->h_stage_cap < stage_bytes) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+    CM_CUDA_CHECK(ctx, cudaHostAlloc(&ctx->h_stage, stage_bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    ctx->h_stage_cap = stage_bytes;
+  }
+  float* pose_in = (float*)ctx->h_stage;
+  CubeWindow* wins = (CubeWindow*)((char*)ctx->h_stage + pose_bytes);
   for (int s = 0; s < S; s++) {
     MappingStream& ms = ctx->mstreams[s];
     HostIso odomNew; memcpy(odomNew.R, h_odom[s].R, 36); memcpy(odomNew.t, h_odom[s].t, 12);
@@ -228,14 +238,21 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   int max_c = 1, max_s = 1, max_q = 1;
   for (int s = 0; s < S; s++) { max_c = std::max(max_c, nds[s]); max_s = std::max(max_s, nds[S + s]); max_q = std::max(max_q, nds[s] + nds[S + s]); }
   // prepareFeatureSurround: cube window -> searchable views
-  ctx->map.set_windows(wins.data(), prm.knn_gate, st);
+  {
+    // the window only changes when a sensor crosses a cube face: skip the upload when the device copy is current
+    const size_t wb = sizeof(CubeWindow) * S;
+    const bool same = ctx->wins_shadow.size() == wb && memcmp(ctx->wins_shadow.data(), wins, wb) == 0;
+    if (!same) ctx->wins_shadow.assign((const unsigned char*)wins, (const unsigned char*)wins + wb);
+    ctx->map.set_windows(same ? nullptr : wins, prm.knn_gate, st, staged);
+  }
   // optimizeTransform
   ctx->m_pose.reserve(sizeof(float) * 6 * S);
   ctx->m_state.reserve(sizeof(MatchState) * S);
   ctx->m_rows.reserve((size_t)S * (cap_c + cap_s) * sizeof(RowOut));
   ctx->m_slots.reserve((size_t)S * (cap_c + cap_s) * 5 * sizeof(int));
   ctx->m_sums.reserve(sizeof(double) * 32 * S);
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_pose.p, pose_in.data(), sizeof(float) * 6 * S, cudaMemcpyHostToDevice, st));
+  if (staged) staged_upload(ctx->m_pose.p, pose_in, sizeof(float) * 6 * S, st);
+  else CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->m_pose.p, pose_in, sizeof(float) * 6 * S, cudaMemcpyHostToDevice, st));
   MatchLaunch m;
   m.nstreams = S;
   m.corner = (const float4*)ctx->m_corner_ds.p; m.surf = (const float4*)ctx->m_surf_ds.p;
@@ -557,21 +574,29 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
     if (is_host) {
       const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
       slot.frames.reserve(bytes);
-      // upload on its own stream: the copy of sweep k+2 runs while sweep k+1 is in scan registration
-      // (in two halves on two copy streams: two concurrent transfers move ~1.5x the bytes per second of one)
-      const size_t half = (bytes / 2) & ~(size_t)255;
+      // upload on its own streams: the copy of sweep k+2 runs while sweep k+1 is in scan registration
+      // (in NC parts on NC copy streams: two concurrent transfers move ~1.5x the bytes per second of one)
+      static const int NC = []() { const char* e = getenv("COOPERMAP_COPY_STREAMS"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 4 ? 4 : n); }();
+      for (int c = 2; c < NC; c++) {
+        if (!ctx->copy_stream_x[c - 2]) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream_x[c - 2], cudaStreamNonBlocking));
+        if (!slot.copied_x[c - 2]) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied_x[c - 2], cudaEventDisableTiming));
+      }
+      cudaStream_t cs[4] = {ctx->copy_stream, ctx->copy_stream2, ctx->copy_stream_x[0], ctx->copy_stream_x[1]};
+      cudaEvent_t ce[4] = {slot.copied, slot.copied2, slot.copied_x[0], slot.copied_x[1]};
+      const size_t part = (bytes / NC) & ~(size_t)255;
       static const bool skip_upload = getenv("COOPERMAP_SKIP_UPLOAD") != nullptr;   // development aid: time the pipeline without PCIe
       if (!skip_upload || slot.frames_valid != bytes) {
-        CM_TIMED("h2d_upload(first half)", ctx->copy_stream,
-                 CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, half, cudaMemcpyHostToDevice, ctx->copy_stream)));
-        CM_TIMED("h2d_upload(second half)", ctx->copy_stream2,
-                 CM_CUDA_CHECK(ctx, cudaMemcpyAsync((char*)slot.frames.p + half, (const char*)frames + half, bytes - half, cudaMemcpyHostToDevice, ctx->copy_stream2)));
+        for (int c = 0; c < NC; c++) {
+          const size_t off = (size_t)c * part, len = (c == NC - 1) ? bytes - off : part;
+          CM_TIMED("h2d_upload(part)", cs[c],
+                   CM_CUDA_CHECK(ctx, cudaMemcpyAsync((char*)slot.frames.p + off, (const char*)frames + off, len, cudaMemcpyHostToDevice, cs[c])));
+        }
         slot.frames_valid = bytes;
       }
-      CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied, ctx->copy_stream));
-      CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied2, ctx->copy_stream2));
-      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, slot.copied, 0));
-      CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, slot.copied2, 0));
+      for (int c = 0; c < NC; c++) {
+        CM_CUDA_CHECK(ctx, cudaEventRecord(ce[c], cs[c]));
+        CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->side_stream, ce[c], 0));
+      }
       d_frames = (const float4*)slot.frames.p;
     }
     pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->side_stream);
