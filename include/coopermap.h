@@ -204,6 +204,11 @@ int cm_mapping_local_window_host(cm_ctx* ctx, int* n_frames, size_t* n_corner, s
  * sweeps may be in flight (one being consumed, three pending); the buffer must stay untouched until its step has run.  Results are identical either way. */
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols);
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols);
+/* The same, but only REGISTERED now and issued by the next cm_pipeline_step_* call right after it has submitted its
+ * Gauss-Newton loop: the host time of the submission (two copies, six launches) hides behind device work instead of delaying
+ * the step.  One registration at a time; an error of the deferred prefetch is returned by that step call. */
+int cm_pipeline_prefetch_deferred_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols);
+int cm_pipeline_prefetch_deferred_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols);
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                           cm_match_stats* stats);
 int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,

@@ -208,15 +208,21 @@ def test_prefetched_steps_equal_synchronous_steps(cmb, synth):
     a = cmb.Context(**cfg); a.mapping_create(S, 60000, 300000)
     b = cmb.Context(**cfg); b.mapping_create(S, 60000, 300000)
     mapped = np.empty((S, 12), np.float32); stats = (cmb.MatchStats * S)()
+    c = cmb.Context(**cfg); c.mapping_create(S, 60000, 300000)   # deferred prefetches (issued behind the Gauss-Newton submission)
     b.pipeline_prefetch(frames[0]); b.pipeline_prefetch(frames[1])
+    c.pipeline_prefetch(frames[0]); c.pipeline_prefetch(frames[1])
     for k in range(NF):
         ref_isos, ref_stats = a.pipeline_step(frames[k], odoms[k])
         if k + 2 < NF:
             b.pipeline_prefetch(frames[k + 2])
-        b.pipeline_step_packed(frames[k], b._pack_isos(odoms[k]), mapped, stats)
-        for s in range(S):
-            assert np.array_equal(mapped[s, :9].reshape(3, 3), ref_isos[s][0]) and np.array_equal(mapped[s, 9:], ref_isos[s][1]), (k, s)
-            assert stats[s].iterations == ref_stats[s]["iterations"]
+            c.pipeline_prefetch(frames[k + 2], deferred=True)
+            with pytest.raises(cmb.CoopermapError):              # one registration at a time
+                c.pipeline_prefetch(frames[k + 2], deferred=True)
+        for ctx_ in (b, c):
+            ctx_.pipeline_step_packed(frames[k], ctx_._pack_isos(odoms[k]), mapped, stats)
+            for s in range(S):
+                assert np.array_equal(mapped[s, :9].reshape(3, 3), ref_isos[s][0]) and np.array_equal(mapped[s, 9:], ref_isos[s][1]), (k, s)
+                assert stats[s].iterations == ref_stats[s]["iterations"]
     for s in range(S):
         for cls in (0, 1):
             assert _same(a.map_export_sorted(s, cls)[0], b.map_export_sorted(s, cls)[0])
@@ -230,4 +236,4 @@ def test_prefetched_steps_equal_synchronous_steps(cmb, synth):
         b.pipeline_prefetch(frames[k])
     with pytest.raises(cmb.CoopermapError):
         b.pipeline_prefetch(frames[4])
-    a.close(); b.close()
+    a.close(); b.close(); c.close()

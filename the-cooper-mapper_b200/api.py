@@ -234,13 +234,16 @@ class Context:
         return self._check(self.L.cm_pipeline_step_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols),
                                                        _ptr(odoms_packed), _ptr(mapped_out), stats_out))
 
-    def pipeline_prefetch(self, frames):
-        """Start the host-to-device upload of the NEXT step's sweeps (pinned (S, rows, cols, 4) float32 array)."""
-        return self._check(self.L.cm_pipeline_prefetch_host(self.h, _ptr(frames), C.c_int(frames.shape[1]), C.c_int(frames.shape[2])))
+    def pipeline_prefetch(self, frames, deferred=False):
+        """Start the host-to-device upload of the NEXT step's sweeps (pinned (S, rows, cols, 4) float32 array).
+        deferred: only registered now, issued by the next pipeline_step right after it has submitted its Gauss-Newton loop."""
+        fn = self.L.cm_pipeline_prefetch_deferred_host if deferred else self.L.cm_pipeline_prefetch_host
+        return self._check(fn(self.h, _ptr(frames), C.c_int(frames.shape[1]), C.c_int(frames.shape[2])))
 
-    def pipeline_prefetch_dev(self, frames_dev_ptr, rows, cols):
+    def pipeline_prefetch_dev(self, frames_dev_ptr, rows, cols, deferred=False):
         """Issue scan registration of the NEXT step's device-resident sweeps on the side stream."""
-        return self._check(self.L.cm_pipeline_prefetch_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols)))
+        fn = self.L.cm_pipeline_prefetch_deferred_dev if deferred else self.L.cm_pipeline_prefetch_dev
+        return self._check(fn(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols)))
 
     def pipeline_step_packed(self, frames, odoms_packed, mapped_out, stats_out):
         fr = frames

@@ -87,6 +87,9 @@ struct cm_ctx {
     const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
     cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, copied_x[2] = {nullptr, nullptr};
     size_t frames_valid = 0;
+    // feature counts and bounding boxes read back by the prefetch itself (side stream -> pinned host memory): the step that
+    // consumes the slot starts without a host round trip
+    int* h_n5 = nullptr; cm::VoxBox* h_box = nullptr; int h_streams = 0; bool counts_ready = false;
   };
 #define CM_PIPE_SLOTS 4            // prefetch slots (one being consumed + three pending); pipe[CM_PIPE_SLOTS] is the synchronous path
   PipeSlot pipe[CM_PIPE_SLOTS + 1];
@@ -95,6 +98,9 @@ struct cm_ctx {
   cudaStream_t side_stream = nullptr, copy_stream = nullptr, copy_stream2 = nullptr;
   cudaStream_t copy_stream_x[2] = {nullptr, nullptr};   // optional third / fourth copy stream (COOPERMAP_COPY_STREAMS)
   int p_cap = 0;
+  // a prefetch registered with cm_pipeline_prefetch_deferred_*: issued by the next cm_pipeline_step right after it has submitted
+  // its Gauss-Newton loop, so that the host time of the submission hides behind device work
+  const void* defer_frames = nullptr; int defer_rows = 0, defer_cols = 0; bool defer_is_host = false; int defer_rc = 0;
 };
 
 namespace cm {

@@ -149,6 +149,15 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
   return CM_OK;
 }
 
+static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host);
+// the prefetch registered with cm_pipeline_prefetch_deferred_* (if any): submitted while the device works on the current step
+static void issue_deferred_prefetch(cm_ctx* ctx) {
+  if (!ctx->defer_frames) return;
+  const void* f = ctx->defer_frames;
+  ctx->defer_frames = nullptr;
+  ctx->defer_rc = pipeline_prefetch(ctx, f, ctx->defer_rows, ctx->defer_cols, ctx->defer_is_host);
+}
+
 // Core of the stage on DEVICE clouds.  d_corner/d_surf: [S][cap] with device counts d_n (corner counts then surf counts,
 // [2][S]).  h_odom: S odometry poses (host).  Outputs on the host: mapped poses and stats.
 // max_in_c / max_in_s: host-known upper bounds of the input counts (sizes the sorts).
@@ -284,6 +293,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
       if (want_events || !ctx->match_graphs.launch(m, st)) launch_match(m, st, &ctx->prof);
     }
   }
+  issue_deferred_prefetch(ctx);   // the Gauss-Newton loop is on its way: submit the next sweep's upload + scan registration now
   // featureMapUpdate (commented out in LaserLocalization::process, LaserLocalization.cpp:186)
   if (!localise) {
     CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
@@ -536,11 +546,20 @@ static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int c
   const int cap = rows * cols;
   cudaStream_t st = ctx->stream;
   // feature-cloud sizes: needed on the host to size the frame voxel filters (and for the byte accounting)
-  std::vector<int> n5(5 * S);
-  std::vector<VoxBox> boxes(2 * S);
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5.data(), (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(boxes.data(), slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  std::vector<int> n5v; std::vector<VoxBox> boxv;
+  const int* n5; const VoxBox* boxes;
+  if (slot.counts_ready) {
+    // read back by the prefetch on the side stream: normally complete long before the step starts
+    CM_CUDA_CHECK(ctx, cudaEventSynchronize(slot.done));
+    n5 = slot.h_n5; boxes = slot.h_box;
+    slot.counts_ready = false;
+  } else {
+    n5v.resize(5 * S); boxv.resize(2 * S);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5v.data(), (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(boxv.data(), slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    n5 = n5v.data(); boxes = boxv.data();
+  }
   int max_c = 1, max_s = 1;
   long long cells_c = 1, cells_s = 1;
   ctx->last_features = 0;
@@ -600,6 +619,20 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
       d_frames = (const float4*)slot.frames.p;
     }
     pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->side_stream);
+    {
+      const int S = ctx->map_streams;
+      if (slot.h_streams < S) {
+        if (slot.h_n5) cudaFreeHost(slot.h_n5);
+        if (slot.h_box) cudaFreeHost(slot.h_box);
+        slot.h_n5 = nullptr; slot.h_box = nullptr; slot.h_streams = 0;
+        CM_CUDA_CHECK(ctx, cudaHostAlloc((void**)&slot.h_n5, sizeof(int) * 5 * S, cudaHostAllocDefault));
+        CM_CUDA_CHECK(ctx, cudaHostAlloc((void**)&slot.h_box, sizeof(VoxBox) * 2 * S, cudaHostAllocDefault));
+        slot.h_streams = S;
+      }
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.h_n5, (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, ctx->side_stream));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.h_box, slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, ctx->side_stream));
+      slot.counts_ready = true;
+    }
     CM_CUDA_CHECK(ctx, cudaEventRecord(slot.done, ctx->side_stream));
     slot.src = frames; slot.rows = rows; slot.cols = cols; slot.is_host = is_host;
   } catch (const CudaError& e) {
@@ -620,9 +653,11 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
       if (slot.src == frames && slot.rows == rows && slot.cols == cols && slot.is_host == is_host) {
         // prefetched: its upload and scan registration were issued on the side stream; wait for them on the device
         CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, slot.done, 0));
+        ctx->defer_rc = 0;
         const int rc = pipeline_mapping(ctx, slot, rows, cols, odom, mapped, stats);
         slot.src = nullptr;
-        return rc;
+        issue_deferred_prefetch(ctx);   // (only still pending when the step failed before its Gauss-Newton loop)
+        return (rc >= 0 && ctx->defer_rc < 0) ? ctx->defer_rc : rc;
       }
     }
     cm_ctx::PipeSlot& slot = ctx->pipe[CM_PIPE_SLOTS];
@@ -634,7 +669,11 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
       d_frames = (const float4*)slot.frames.p;
     }
     pipeline_scanreg(ctx, slot, d_frames, rows, cols, ctx->stream);
-    return pipeline_mapping(ctx, slot, rows, cols, odom, mapped, stats);
+    slot.counts_ready = false;
+    ctx->defer_rc = 0;
+    const int rc = pipeline_mapping(ctx, slot, rows, cols, odom, mapped, stats);
+    issue_deferred_prefetch(ctx);
+    return (rc >= 0 && ctx->defer_rc < 0) ? ctx->defer_rc : rc;
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
@@ -642,6 +681,15 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
 
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch(ctx, frames, rows, cols, true); }
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch(ctx, d_frames, rows, cols, false); }
+static int pipeline_prefetch_deferred(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!frames || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
+  if (ctx->defer_frames) return fail(ctx, CM_ERR_ARG, "a deferred prefetch is already registered: run cm_pipeline_step first");
+  ctx->defer_frames = frames; ctx->defer_rows = rows; ctx->defer_cols = cols; ctx->defer_is_host = is_host;
+  return CM_OK;
+}
+int cm_pipeline_prefetch_deferred_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch_deferred(ctx, frames, rows, cols, true); }
+int cm_pipeline_prefetch_deferred_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch_deferred(ctx, d_frames, rows, cols, false); }
 int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                           cm_match_stats* stats) {
   return pipeline_step(ctx, frames, rows, cols, true, odom, mapped, stats);
