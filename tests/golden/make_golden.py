@@ -46,6 +46,21 @@ def main():
                         AtA=np.stack([e["AtA"] for e in log]), AtB=np.stack([e["AtB"] for e in log]),
                         x=np.stack([e["x"] for e in log]), counts=np.stack([e["counts"] for e in log]),
                         nnCorner0=log[0]["nnCorner"], nnSurf0=log[0]["nnSurf"])
+    # --- mapping stages over a 5-frame sequence: LaserMapping (cube map) and LaserMappingLocal (sliding window) -----------------
+    seq = {}
+    lm = O.Mapping(map_params=dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4))
+    ll = O.MappingLocal(map_params=dict(filterCorner=0.4, filterSurf=0.8), use_mapped_pose=True)
+    lw = O.MappingLocal(map_params=dict(filterCorner=0.4, filterSurf=0.8), use_mapped_pose=False)
+    for k, (Rk, tk) in enumerate(synth.trajectory(5, speed=0.5)):
+        frk = synth.simulate_scan(sc, Rk, tk, "VLP-16", seed=50 + k, cols=1200)
+        fk = O.scanreg_organised(frk)
+        odomR = Rk.astype(np.float32); odomT = (tk + np.array([0.02, -0.02, 0.01]) * k).astype(np.float32)
+        seq["corner%d" % k] = fk["lessSharp"]; seq["surf%d" % k] = fk["lessFlat"]; seq["odomR%d" % k] = odomR; seq["odomT%d" % k] = odomT
+        for name, m in (("map", lm), ("local", ll), ("literal", lw)):
+            oR, ot, st = m.process(odomR, odomT, fk["lessSharp"], fk["lessFlat"])
+            seq["%sR%d" % (name, k)] = oR; seq["%sT%d" % (name, k)] = ot
+            seq["%sStats%d" % (name, k)] = np.array([st["iterations"], st["rows"], st["tooFewRef"], st["nSurroundCorner"], st["nSurroundSurf"]], np.int32)
+    np.savez_compressed(os.path.join(OUT, "mapping_seq5.npz"), **seq)
     for n in sorted(os.listdir(OUT)):
         if n.endswith(".npz"):
             print(n, os.path.getsize(os.path.join(OUT, n)))

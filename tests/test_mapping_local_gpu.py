@@ -1,5 +1,7 @@
 """GPU parity: LaserMappingLocal (sliding-window map, LaserMappingLocal.cpp:33-78 over io_module/LocalFeatureMap.h) vs the oracle.
 Poses, counters and the window clouds must be bit-identical, in the reference-as-written mode and with the mapped pose."""
+import os
+
 import numpy as np
 import pytest
 
@@ -71,3 +73,19 @@ def test_mapping_local_requires_create_and_handles_empty_clouds(cmb):
     w = ctx.mapping_local_window()
     assert w["frames"] == 1 and w["nCorner"] == 0 and w["nSurf"] == 0
     ctx.close()
+
+
+def test_golden_mapping_sequence_gpu(cmb):
+    """The committed 5-frame sequence (tests/golden/mapping_seq5.npz, made by the oracle): LaserMapping and LaserMappingLocal on the
+    GPU reproduce every pose bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mapping_seq5.npz"))
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    stages = {"map": cmb.LaserMapping(max_corner_points=100000, max_surf_points=600000, **cfg),
+              "local": cmb.LaserMappingLocal(use_mapped_pose=True, **cfg), "literal": cmb.LaserMappingLocal(use_mapped_pose=False, **cfg)}
+    for k in range(5):
+        for name, m in stages.items():
+            R, t = m.process(g["odomR%d" % k], g["odomT%d" % k], g["corner%d" % k], g["surf%d" % k])
+            assert _same(R, g["%sR%d" % (name, k)]) and _same(t, g["%sT%d" % (name, k)]), (name, k)
+            assert [m.last_stats["iterations"], m.last_stats["rows"]] == list(g["%sStats%d" % (name, k)][:2]), (name, k)
+    for m in stages.values():
+        m.ctx.close()

@@ -237,6 +237,20 @@ def test_golden_match(oracle):
         assert np.array_equal(log[0]["nnCorner"], g["nnCorner0"]) and np.array_equal(log[0]["nnSurf"], g["nnSurf0"])
 
 
+def test_golden_mapping_sequence(oracle):
+    """LaserMapping (cube map) and LaserMappingLocal (window; mapped-pose and as-written modes) over the committed 5-frame sequence."""
+    g = np.load(os.path.join(GOLD, "mapping_seq5.npz"))
+    prm = dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)
+    stages = {"map": oracle.Mapping(map_params=prm), "local": oracle.MappingLocal(map_params=prm, use_mapped_pose=True),
+              "literal": oracle.MappingLocal(map_params=prm, use_mapped_pose=False)}
+    for k in range(5):
+        for name, m in stages.items():
+            oR, ot, st = m.process(g["odomR%d" % k], g["odomT%d" % k], g["corner%d" % k], g["surf%d" % k])
+            assert np.array_equal(oR, g["%sR%d" % (name, k)]) and np.array_equal(ot, g["%sT%d" % (name, k)]), (name, k)
+            assert [st["iterations"], st["rows"], st["tooFewRef"], st["nSurroundCorner"], st["nSurroundSurf"]] == list(g["%sStats%d" % (name, k)])
+    assert int(g["mapStats4"][0]) > 0 and int(g["localStats4"][0]) > 0       # the sequence does exercise the solver
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # solver behaviour
 # ---------------------------------------------------------------------------------------------------------------
