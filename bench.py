@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--pool", type=int, default=12, help="distinct synthetic sweeps generated on the host")
     ap.add_argument("--ahead", type=int, default=2, help="end-to-end arm: sweeps uploaded ahead of the one being registered (1..3)")
     ap.add_argument("--defer", action="store_true", help="register the in-loop prefetches (cm_pipeline_prefetch_deferred_*: issued behind the step's Gauss-Newton submission) instead of issuing them before the step")
+    ap.add_argument("--e2e-resident", action="store_true", help="diagnostic: run the end-to-end arm's loop (same prefetch depth, CUDA graphs) on device-resident sweeps, i.e. without PCIe traffic; the e2e figure is then NOT an end-to-end number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="after the timed arms, run 2 more steps with every launch event-timed and print per-kernel totals to stderr")
@@ -331,10 +332,19 @@ def main():
     ring_host = [torch.from_numpy(np.ascontiguousarray(frames[order[NBUF + b]])).pin_memory() for b in range(NBUF)]
     host_np = [ring_host[k % NBUF].numpy() for k in range(n_steps)]
     A = min(max(args.ahead, 1), 3)
+    res_dev = [pool_dev[torch.tensor(order[NBUF + b], device=dev)].contiguous() for b in range(NBUF)] if args.e2e_resident else None
 
     def e2e_steps(first, count):
         # `A` sweeps ahead: upload of step k+A (copy streams) | scan registration of the steps before it (side stream) | matching
         # of step k (main stream); every step's sweeps cross PCIe, the poses of step k are read back before step k+1 is issued
+        if args.e2e_resident:   # diagnostic: the same loop without the uploads
+            for j in range(first, min(first + A, first + count)):
+                ctx.pipeline_prefetch_dev(res_dev[j % NBUF].data_ptr(), ROWS, COLS)
+            for k in range(first, first + count):
+                if k + A < first + count:
+                    ctx.pipeline_prefetch_dev(res_dev[(k + A) % NBUF].data_ptr(), ROWS, COLS, deferred=DEFER)
+                ctx.pipeline_step_dev(res_dev[k % NBUF].data_ptr(), ROWS, COLS, odom[n_steps + k], mapped, stats)
+            return
         for j in range(first, min(first + A, first + count)):
             ctx.pipeline_prefetch(host_np[j])
         for k in range(first, first + count):
@@ -401,7 +411,7 @@ def main():
             "config": {"workload": workload, "streams_per_gpu": S, "points_per_sweep": NPTS, "map_points_per_stream": int(sum(map_pts)),
                        "frame_leaf": [CFG["filter_corner"], CFG["filter_surf"]], "map_leaf": [CFG["map_filter_corner"], CFG["map_filter_surf"]],
                        "mean_gn_iterations": float(np.mean(iters)), "converged_frac": conv,
-                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush", "e2e_sweeps_ahead": A, "deferred_prefetch": DEFER,
+                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush", "e2e_sweeps_ahead": A, "e2e_resident_diagnostic": bool(args.e2e_resident), "deferred_prefetch": DEFER,
                        "parallelism": "streams sharded over ranks, no collective"},
             "roofline": {"bound": "hbm", "kernel": "search_kernel + search_hard_kernel (pointAssociateToMap + exact 5-NN on the voxel-cell hash map)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
