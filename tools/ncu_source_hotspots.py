@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Per-source-line hot spots of one kernel from an ncu report (needs -lineinfo).
-usage: tools/ncu_source_hotspots.py report.ncu-rep kernel_regex [top_n] [launch_index]"""
+usage: tools/ncu_source_hotspots.py report.ncu-rep kernel_regex [top_n] [launch_index]
+HOTSPOT_SORT=1 sorts by executed instructions instead of stall samples."""
 import collections
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -12,6 +14,7 @@ def main():
     rep, rx = sys.argv[1], sys.argv[2]
     top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    sort_col = int(os.environ.get("HOTSPOT_SORT", "0"))
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + rx],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -44,7 +47,7 @@ def main():
     L = launches[which]["lines"]
     ts = sum(v[0] for v in L.values()); ti = sum(v[1] for v in L.values()); tt = sum(v[2] for v in L.values())
     print("launch %d/%d: samples %d, warp-instr %d, thread-instr %d (lanes/instr %.1f)" % (which, len(launches), ts, ti, tt, tt / max(ti, 1)))
-    for (f, ln), v in sorted(L.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("HOTSPOT_SORT", "0"))])[:top_n]:
+    for (f, ln), v in sorted(L.items(), key=lambda kv: -kv[1][sort_col])[:top_n]:
         print("%5.1f%% smp %5.1f%% inst lanes %4.1f  %s:%s  %s" % (100.0 * v[0] / max(ts, 1), 100.0 * v[1] / max(ti, 1), v[2] / max(v[1], 1), f, ln, v[3][:90]))
 
 
