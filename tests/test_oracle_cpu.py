@@ -269,6 +269,41 @@ def test_match_recovers_pose_and_gates(oracle, synth, scene_small):
     assert st3["tooFewMatches"] and st3["iterations"] == 0 and np.array_equal(p3, init)
 
 
+def test_scan_against_its_own_map_converges_at_once(oracle, synth):
+    """Known answer: a frame matched against a map made of ITS OWN features, starting from the true pose, needs no
+    correction -- the first update is below the thresholds and the pose stays put."""
+    sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
+    R, t = synth.pose_matrix(0.05, 0.0, 0.0, (1.0, -0.5, 0.0))
+    f = oracle.scanreg_organised(synth.simulate_scan(sc, R, t, "VLP-16", seed=7, cols=1200))
+    c = oracle.voxel_filter(f["lessSharp"], 0.4); s = oracle.voxel_filter(f["lessFlat"], 0.8)
+
+    def to_map(p):   # the same features in the map frame
+        q = p.copy(); q[:, :3] = (p[:, :3].astype(np.float64) @ R.T + t).astype(np.float32); return q
+    truth = np.array([0.0, 0.0, 0.05, 1.0, -0.5, 0.0], np.float32)
+    p, st, log = oracle.scan_match(to_map(f["lessSharp"]), to_map(f["lessFlat"]), c, s, truth, keep_log=True)
+    assert not st["tooFewRef"] and st["converged"] and st["iterations"] <= 3, st
+    # "~0": the queries are voxel centroids, the map holds the raw (noisy, sigma 1 cm) returns -> residuals of a few mm remain
+    assert np.all(np.abs(p[:3] - truth[:3]) < 5e-4) and np.all(np.abs(p[3:] - truth[3:]) < 1e-2), p - truth
+    assert np.abs(log[0]["x"]).max() < 1e-2                 # the very first Gauss-Newton step is already ~0
+
+
+def test_corridor_is_degenerate_along_its_axis(oracle, synth):
+    """Known answer: two parallel walls leave the along-corridor translation unobservable; the eigenvalue test at
+    iteration 0 (ScanMatch.cpp:211-240) flags it and the projected update does not move the pose along the corridor."""
+    sc = synth.make_scene(seed=1, extent=60.0, corridor=True)
+    mc, ms = synth.sample_map(sc, 0.4, seed=2)
+    pole = np.zeros((80, 4), np.float32); pole[:, 0] = 200.0; pole[:, 2] = np.linspace(-1.8, 6, 80)   # passes the >= 50 corner gate, matches nothing
+    mc = np.concatenate([mc, pole])
+    R, t = synth.pose_matrix(0.0, 0.0, 0.0, (0.0, 0.0, 0.0))
+    r = oracle.scanreg_organised(synth.simulate_scan(sc, R, t, "VLP-16", seed=9))
+    c = oracle.voxel_filter(r["lessSharp"], 0.4); s = oracle.voxel_filter(r["lessFlat"], 0.8)
+    init = np.array([0.002, -0.003, 0.004, 0.05, 0.04, -0.03], np.float32)
+    p, st, log = oracle.scan_match(mc, ms, c, s, init, keep_log=True)
+    assert st["degenerate"] and st["iterations"] >= 1
+    w = np.linalg.eigvalsh(log[0]["AtA"].astype(np.float64))
+    assert w[0] < 100.0 < w[-1]                               # the threshold of ScanMatch.cpp:219
+
+
 def test_mapping_loop_bootstraps_and_tracks(oracle, synth):
     sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
     m = oracle.Mapping(map_params=dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4))
