@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- LiDAR points registered / s (scan registration + scan-to-map registration, whole box).
 
-Workload (BASELINE.json configs[1]): HDL-64E-shaped sweeps (64 x 2048 = 131,072 points) registered against a
-~1M-point local map per stream.  One step = one sweep of EVERY stream through the full hot path
-(scan registration -> frame voxel filters -> <= 10 Gauss-Newton iterations of exact-5-NN correspondence + solve ->
-map insertion).  Streams are independent LiDARs (own pose chain, own map); ranks shard streams (weak scaling,
-no data-path collective).  `value` = inputs resident in HBM; `e2e` = host buffers through the C ABI
-(cm_pipeline_step_host), H2D of the sweeps and D2H of the poses inside the timed region.
+Default workload = BASELINE.json configs[1]: HDL-64E-shaped sweeps (64 x 2048 = 131,072 points) registered against a
+>= 1,000,000-point local map per stream (asserted on the RESIDENT map, after the 0.4 m map voxel merge).  One step = one
+sweep of EVERY stream through the full hot path (scan registration -> frame voxel filters -> <= 10 Gauss-Newton
+iterations of exact-5-NN correspondence + solve -> map insertion).  Streams are independent LiDARs (own pose chain, own
+map) that walk a fresh trajectory: no sweep is registered twice by a stream inside the run, so map growth (new voxels,
+cell growth) happens inside the timed region.  Ranks shard streams (weak scaling, no data-path collective).
+`value` = sweeps resident in HBM, the product path exactly as a caller runs it (Gauss-Newton loop as a WHILE graph);
+`e2e` = pinned host sweeps through the C ABI (cm_pipeline_prefetch_host + cm_pipeline_step_host), H2D of the sweeps and
+D2H of the poses inside the timed region.  Per-kernel times come from a separate event-timed pass after the timed arms.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--streams S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5] [--streams S]
 """
 import argparse
 import ctypes as C
@@ -30,6 +33,8 @@ NPTS = ROWS * COLS
 SEED = 0x5EED0002
 CFG = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
 ORACLE_MAP = dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)
+MAP_SPACING = 0.3          # sampling lattice of the prebuilt map: 1.8 M samples -> 1.02 M resident points at the 0.4 m map leaf
+METRIC = "lidar_points_registered_per_s"
 
 
 def log(*a):
@@ -39,16 +44,30 @@ def log(*a):
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------------------------------------------
+def _sim_one(args):
+    synth = importlib.import_module(PKG + ".synth")
+    sc, R, t, model, seed = args
+    return synth.simulate_scan(sc, R, t, model, seed=seed)
+
+
+def simulate_pool(synth, sc, traj, model, seed0, procs=None):
+    """One sweep per trajectory pose, simulated on `procs` host processes (fork: call before CUDA is initialised)."""
+    jobs = [(sc, R, t, model, seed0 + k) for k, (R, t) in enumerate(traj)]
+    procs = procs or max(1, min(len(jobs), (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if procs <= 1 or len(jobs) <= 2:
+        return [_sim_one(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_sim_one, jobs)
+
+
 def make_workload(n_pool, synth):
-    """Scene, ~1M-point map (corner, surf) and a pool of HDL-64E sweeps with their true poses."""
+    """Scene, map samples (corner, surf; >= 1 M points once voxel-merged at 0.4 m) and a trajectory of n_pool HDL-64E sweeps."""
     sc = synth.make_scene(seed=SEED & 0xFFFF, extent=125.0, n_boxes=44, n_poles=40)
-    mc, ms = synth.sample_map(sc, 0.4, seed=2)
+    mc, ms = synth.sample_map(sc, MAP_SPACING, seed=2)
     traj = synth.trajectory(n_pool, speed=2.0)
-    frames = np.empty((n_pool, ROWS, COLS, 4), np.float32)
-    poses = []
-    for k, (R, t) in enumerate(traj):
-        frames[k] = synth.simulate_scan(sc, R, t, "HDL-64E", seed=1000 + k)
-        poses.append((R.astype(np.float32), t.astype(np.float32)))
+    frames = np.stack(simulate_pool(synth, sc, traj, "HDL-64E", 1000)).astype(np.float32)
+    poses = [(R.astype(np.float32), t.astype(np.float32)) for R, t in traj]
     return mc, ms, frames, poses
 
 
@@ -83,15 +102,16 @@ def _cpu_worker(args):
         oR, ot = noisy_odom(poses, fi, rng, synth)
         t0 = time.perf_counter()
         f = O.scanreg_organised(frames[fi], fast=True)
+        t1 = time.perf_counter()
         m.process(oR, ot, f["lessSharp"], f["lessFlat"])
-        dt = time.perf_counter() - t0
+        t2 = time.perf_counter()
         if k >= warm:
-            times.append(dt)
+            times.append((t2 - t0, t1 - t0, t2 - t1))
     return times
 
 
 def cpu_arm(mc, ms, frames, poses, frames_per_worker, warm=1, workers=None):
-    """Runs `workers` independent streams, one per process / core.  Returns (points/s, cores, per-frame seconds)."""
+    """Runs `workers` independent streams, one per process / core.  Returns (points/s, cores, per-frame seconds [total, stage 1, stage 3], wall)."""
     import multiprocessing as mp
     workers = workers or min(os.cpu_count() or 1, 32)
     ctx = mp.get_context("fork")
@@ -103,9 +123,9 @@ def cpu_arm(mc, ms, frames, poses, frames_per_worker, warm=1, workers=None):
     with ctx.Pool(workers) as pool:
         res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
-    per_frame = [x for r in res for x in r]
+    per_frame = np.array([x for r in res for x in r], np.float64).reshape(-1, 3)
     # throughput from the timed frames only: every worker runs concurrently, so the box rate is workers / mean frame time
-    rate = workers * NPTS / float(np.mean(per_frame))
+    rate = workers * NPTS / float(np.mean(per_frame[:, 0]))
     return rate, workers, per_frame, wall
 
 
@@ -184,94 +204,137 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any (profiles/kernel_traffic.json)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))["dram_bytes_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        for k, v in d.items():
+            if k in kernel:
+                return v
     except Exception:
-        return None
+        pass
+    return None
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank (and the pinned buffers it allocates from now on) to the CPUs of its GPU's NUMA node: the sweeps of 8 ranks
+    then cross 8 different PCIe root ports from node-local memory instead of funnelling through one socket."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        dev = "/sys/bus/pci/devices/" + bus
+        cpus = open(dev + "/local_cpulist").read().strip()
+        node = int(open(dev + "/numa_node").read().strip())
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"pci": bus, "numa_node": node, "cpus": cpus}
+    except Exception as e:   # no sysfs entry (virtualised box): leave the affinity alone
+        return {"error": str(e)[:80]}
+
+
+# per-kernel ALGORITHMIC bytes (DESIGN.md section 5): what a launch must move at least, from the run-time counters of the
+# step it belongs to.  c = {raw: raw sweep points, feat: feature points written by scan registration, qi: query-iterations,
+# q: filtered queries, ins: inserted points, fin: points entering the frame voxel filters}
+KERNEL_BYTES = [
+    ("sr_ring_kernel", lambda c: 16.0 * c["raw"] + 16.0 * c["feat"], "16 B per raw point read + 16 B per feature point written"),
+    ("sr_assemble_kernel", lambda c: 32.0 * c["feat"], "16 B read + 16 B written per feature point"),
+    ("search_kernel", lambda c: 96.0 * c["qi"], "16 B query + 5 x 16 B neighbours per query-iteration (SURVEY 8d)"),
+    ("search_hard_kernel", None, "the sparse-surroundings tail of search_kernel's queries (its bytes are counted there)"),
+    ("fit_solve_kernel", lambda c: 128.0 * c["qi"], "16 B query + 5 x 16 B neighbours read, 32 B row written per query-iteration"),
+    ("vox_", lambda c: None, None),
+    ("map_merge_kernel", lambda c: 32.0 * c["ins"], "16 B new point read, 16 B voxel point written / merged"),
+]
+
+
+def kernel_bytes(name, counters):
+    for key, fn, _ in KERNEL_BYTES:
+        if key in name:
+            try:
+                return fn(counters) if fn else None
+            except Exception:
+                return None
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=64, help="LiDAR streams per GPU")
-    ap.add_argument("--pool", type=int, default=12, help="distinct synthetic sweeps generated on the host")
-    ap.add_argument("--ahead", type=int, default=2, help="end-to-end arm: sweeps uploaded ahead of the one being registered (1..3)")
-    ap.add_argument("--defer", action="store_true", help="register the in-loop prefetches (cm_pipeline_prefetch_deferred_*: issued behind the step's Gauss-Newton submission) instead of issuing them before the step")
-    ap.add_argument("--e2e-resident", action="store_true", help="diagnostic: run the end-to-end arm's loop (same prefetch depth, CUDA graphs) on device-resident sweeps, i.e. without PCIe traffic; the e2e figure is then NOT an end-to-end number")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-latency", action="store_true")
-    ap.add_argument("--timeline", action="store_true", help="after the timed arms, run 2 more steps with every launch event-timed and print per-kernel totals to stderr")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    K, W, S = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0), args.streams
-    synth = importlib.import_module(PKG + ".synth")
-    workload = "HDL-64E 64x2048 sweeps, scan registration + scan-to-map vs ~1M-point local map per stream"
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        mc, ms, frames, poses = make_workload(min(args.pool, 6), synth)
-        rate, cores, per_frame, wall = cpu_arm(mc, ms, frames, poses, frames_per_worker=max(K, 1), warm=max(args.warmup, 1))
-        line = {"impl": "reference", "metric": "lidar_points_registered_per_s", "value": rate, "unit": "points/s",
-                "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_frame)),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "map_points": int(len(mc) + len(ms)), "streams": cores,
-                           "note": "CPU oracle (line-by-line restatement + the reference's vendored nanoflann), one stream per core"},
-                "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
-                                 "sample": "%d sweeps per core after %d warm-up, wall %.1f s" % (max(K, 1), max(args.warmup, 1), wall)},
-                "p50_latency_ms": 1e3 * float(np.median(per_frame)),
-                "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+def run_reference(args, synth, rank):
+    if rank != 0:
         return
+    K = max(args.steps, 1)
+    workload = "HDL-64E 64x2048 sweeps, scan registration + scan-to-map vs >=1M-point local map per stream"
+    mc, ms, frames, poses = make_workload(min(args.pool or 6, 6), synth)
+    rate, cores, per_frame, wall = cpu_arm(mc, ms, frames, poses, frames_per_worker=K, warm=max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_frame[:, 0])),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "map_points_sampled": int(len(mc) + len(ms)), "streams": cores,
+                       "note": "CPU oracle (line-by-line restatement + the reference's vendored nanoflann), one stream per core"},
+            "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": "%d sweeps per core after %d warm-up, wall %.1f s" % (K, max(args.warmup, 1), wall)},
+            "p50_latency_ms": 1e3 * float(np.median(per_frame[:, 0])),
+            "stage1_alone_p50_ms": 1e3 * float(np.median(per_frame[:, 1])), "stage3_alone_p50_ms": 1e3 * float(np.median(per_frame[:, 2])),
+            "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
-    # ---- workload on the host (before CUDA is touched: the CPU baseline forks) -------------------------------------
+
+def run_config2(args, synth, rank, world, local_rank):
+    K, W, S = args.steps, max(args.warmup, 3), args.streams
+    n_steps = W + K
+    workload = "HDL-64E 64x2048 sweeps, scan registration + scan-to-map vs >=1M-point local map per stream"
+    # ---- workload on the host (before CUDA is touched: the simulation and the CPU baseline fork) -------------------
     t_setup = time.time()
-    mc, ms, frames, poses = make_workload(args.pool, synth)
-    log("[bench] workload: map %d corner + %d surf points, %d sweeps (%.1f s)" % (len(mc), len(ms), len(frames), time.time() - t_setup))
+    P = args.pool or (2 * n_steps + 8)                       # one fresh sweep per stream and step over BOTH timed arms
+    mc, ms, frames, poses = make_workload(P, synth)
+    log("[bench] workload: map samples %d corner + %d surf, %d sweeps (%.1f s)" % (len(mc), len(ms), len(frames), time.time() - t_setup))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, per_frame, wall = cpu_arm(mc, ms, frames[:6], poses[:6], frames_per_worker=12, warm=1)
         cpu = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
                "sample": "12 sweeps per core after 1 warm-up (oracle -O3 + reference nanoflann, one stream per core), wall %.1f s, p50 %.0f ms/sweep"
-                         % (wall, 1e3 * float(np.median(per_frame)))}
+                         % (wall, 1e3 * float(np.median(per_frame[:, 0]))),
+               "stage1_alone_points_per_s": cores * NPTS / float(np.mean(per_frame[:, 1])),
+               "stage3_alone_points_per_s": cores * NPTS / float(np.mean(per_frame[:, 2])),
+               "p50_ms": {"end_to_end": 1e3 * float(np.median(per_frame[:, 0])), "stage1": 1e3 * float(np.median(per_frame[:, 1])),
+                          "stage3": 1e3 * float(np.median(per_frame[:, 2]))}}
         log("[bench] cpu baseline: %.3e points/s on %d cores" % (rate, cores))
 
     import torch
     import torch.distributed as dist
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     cmb = importlib.import_module(PKG)
     ctx = cmb.Context(device=local_rank, **CFG)
-    ctx.mapping_create(S, max_corner_points=max(4 * len(mc), 100000), max_surf_points=int(1.6 * len(ms)) + 200000)
+    cap_c, cap_s = max(8 * len(mc), 200000), int(1.2 * len(ms)) + 400000
+    ctx.mapping_create(S, max_corner_points=cap_c, max_surf_points=cap_s)
     eye = (np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
-    # prebuilt ~1M-point map in every stream (inserted through the product's own insert kernels, in chunks)
+    # prebuilt map in every stream (inserted through the product's own insert kernels, in chunks)
     chunk = 1 << 18
     for o in range(0, len(ms), chunk):
         c_part = mc if o == 0 else mc[:0]
         ctx.map_insert([c_part] * S, [ms[o:o + chunk]] * S, [eye] * S)
     map_pts = [len(ctx.map_export(0, 0)[0]), len(ctx.map_export(0, 1)[0])]
     log("[bench] rank %d: %d streams, resident map per stream: %d corner + %d surf points" % (rank, S, map_pts[0], map_pts[1]))
+    assert sum(map_pts) >= 1000000, "BASELINE config 2 asks for a 1M-point local map: resident %d" % sum(map_pts)
 
     rng = np.random.default_rng(77 + rank)
-    n_steps = W + K
-    # distinct input buffers: at most NBUF (x 134 MB at 64 streams, each larger than L2), reused round-robin over the steps;
-    # step k of the device arm registers buffer k % NBUF, step k of the end-to-end arm buffer NBUF + k % NBUF
-    NBUF = min(n_steps, 8)
-    order = [[(3 * s + 5 * rank + b) % len(frames) for s in range(S)] for b in range(2 * NBUF)]
-    odom = [pack_isos([noisy_odom(poses, order[k % NBUF][s], rng, synth) for s in range(S)]) for k in range(n_steps)]
-    odom += [pack_isos([noisy_odom(poses, order[NBUF + k % NBUF][s], rng, synth) for s in range(S)]) for k in range(n_steps)]
+    # stream s registers sweep (7 s + 5 rank + g) mod P at global step g (device arm: g = k, end-to-end arm: g = n_steps + k):
+    # every stream walks the trajectory forward, 2 m per step, and never meets a sweep twice
+    def sweep_of(s, g):
+        return (7 * s + 5 * rank + g) % P
+    G_total = 2 * n_steps + 16
+    idx = np.array([[sweep_of(s, g) for s in range(S)] for g in range(G_total)])
+    odom = [pack_isos([noisy_odom(poses, idx[g][s], rng, synth) for s in range(S)]) for g in range(G_total)]
     pool_dev = torch.from_numpy(frames).to(dev)
-    ring_dev = [pool_dev[torch.tensor(order[b], device=dev)].contiguous() for b in range(NBUF)]
-    step_dev = [ring_dev[k % NBUF] for k in range(n_steps)]
+    step_dev = [pool_dev[torch.from_numpy(idx[g]).to(dev)].contiguous() for g in range(n_steps)]
     torch.cuda.synchronize()
     mapped = np.empty((S, 12), np.float32); stats = (cmb.MatchStats * S)()
 
@@ -285,72 +348,68 @@ def main():
     if rank == 0:
         sampler.start()
 
-    # --defer: in-loop prefetches are only registered before the step and issued by the library right after the step has
-    # submitted its Gauss-Newton loop (cm_pipeline_prefetch_deferred_*).  Measured: no gain end to end, -12 % device-resident
-    # (scan registration of step k+1 starts later and overlaps less of step k), so it is off by default
-    DEFER = args.defer
-
-    # ---- device-resident arm ------------------------------------------------------------------------------------
+    # ---- device-resident arm (the product path: WHILE-graph Gauss-Newton loop, filter / insert chains as graphs) ------
     ctx.pipeline_prefetch_dev(step_dev[0].data_ptr(), ROWS, COLS)
     for k in range(W):                                       # warm-up through the same (pipelined) path as the timed steps
-        if k + 1 < W:
-            ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS, deferred=DEFER)
+        ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS)
         ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
     barrier()
     sampler.mark_begin()
-    ctx.prof_enable(True); ctx.prof_drain()
     launches0 = ctx.launch_count()
-    qi = q = ins = feat = 0
+    gb0 = ctx.graph_builds()
+    cnt = dict(qi=0, q=0, ins=0, feat=0)
     iters = []
     ctx.timer_record(0)
     # software pipeline across steps: scan registration of step k+1 (cm_pipeline_prefetch_dev, side stream) is issued before
     # step k's matching, so the issue-bound feature extraction overlaps the latency-bound Gauss-Newton loop
-    ctx.pipeline_prefetch_dev(step_dev[W].data_ptr(), ROWS, COLS)
+    # (the sweep of step W was prefetched by the last warm-up step)
     for k in range(W, W + K):
         if k + 1 < W + K:
-            ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS, deferred=DEFER)
+            ctx.pipeline_prefetch_dev(step_dev[k + 1].data_ptr(), ROWS, COLS)
         ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
         c = ctx.last_step_counters()
-        qi += c["query_iters"]; q += c["queries"]; ins += c["inserted"]; feat += c["features"]
+        cnt["qi"] += c["query_iters"]; cnt["q"] += c["queries"]; cnt["ins"] += c["inserted"]; cnt["feat"] += c["features"]
         iters += [st.iterations for st in stats]
     ctx.timer_record(1)
     ms_total = ctx.timer_elapsed_ms()
     sampler.mark_end()
     barrier()
-    corr_ms, corr_launches = ctx.prof_drain()
-    sr_ms, sr_launches = ctx.prof_drain_scanreg()
-    ctx.prof_enable(False)
     launches = ctx.launch_count() - launches0
+    gb1 = ctx.graph_builds()
     conv = float(np.mean([st.converged for st in stats]))
+    map_after = [len(ctx.map_export(0, 0)[0]), len(ctx.map_export(0, 1)[0])]
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * S * K * NPTS / (ms_max * 1e-3)
+    del step_dev
+    torch.cuda.empty_cache()
 
     # ---- end-to-end arm: pinned host sweeps through the C ABI --------------------------------------------------------
-    ring_host = [torch.from_numpy(np.ascontiguousarray(frames[order[NBUF + b]])).pin_memory() for b in range(NBUF)]
-    host_np = [ring_host[k % NBUF].numpy() for k in range(n_steps)]
+    # every step has its own pinned buffer (fresh sweeps); beyond --pinned-gb the buffers are reused round-robin
+    per_step = S * NPTS * 16
+    nbuf = max(4, min(n_steps, int(args.pinned_gb * 1e9 // per_step)))
+    host_t = [torch.empty((S, ROWS, COLS, 4), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    host_np = [h.numpy() for h in host_t]
+
+    def fill(b, g):
+        np.take(frames, idx[g], axis=0, out=host_np[b])
+
+    for b in range(min(nbuf, n_steps)):
+        fill(b, n_steps + b)
     A = min(max(args.ahead, 1), 3)
-    res_dev = [pool_dev[torch.tensor(order[NBUF + b], device=dev)].contiguous() for b in range(NBUF)] if args.e2e_resident else None
+    ge = lambda k: n_steps + (k % nbuf)                      # the global step whose sweeps buffer k % nbuf holds
 
     def e2e_steps(first, count):
         # `A` sweeps ahead: upload of step k+A (copy streams) | scan registration of the steps before it (side stream) | matching
         # of step k (main stream); every step's sweeps cross PCIe, the poses of step k are read back before step k+1 is issued
-        if args.e2e_resident:   # diagnostic: the same loop without the uploads
-            for j in range(first, min(first + A, first + count)):
-                ctx.pipeline_prefetch_dev(res_dev[j % NBUF].data_ptr(), ROWS, COLS)
-            for k in range(first, first + count):
-                if k + A < first + count:
-                    ctx.pipeline_prefetch_dev(res_dev[(k + A) % NBUF].data_ptr(), ROWS, COLS, deferred=DEFER)
-                ctx.pipeline_step_dev(res_dev[k % NBUF].data_ptr(), ROWS, COLS, odom[n_steps + k], mapped, stats)
-            return
         for j in range(first, min(first + A, first + count)):
-            ctx.pipeline_prefetch(host_np[j])
+            ctx.pipeline_prefetch(host_np[j % nbuf])
         for k in range(first, first + count):
             if k + A < first + count:
-                ctx.pipeline_prefetch(host_np[k + A], deferred=DEFER)
-            ctx.pipeline_step_packed(host_np[k], odom[n_steps + k], mapped, stats)
+                ctx.pipeline_prefetch(host_np[(k + A) % nbuf])
+            ctx.pipeline_step_packed(host_np[k % nbuf], odom[ge(k)], mapped, stats)
 
     e2e_steps(0, W)
     barrier()
@@ -367,66 +426,128 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * K * NPTS / (float(t.item()) * 1e-3)
 
-    if args.timeline and rank == 0:
+    # ---- per-kernel times: a separate pass with every launch bracketed by CUDA events (launch-by-launch, no graphs) -------
+    kernels = []
+    stage = {}
+    if rank == 0 and not args.no_kernel_pass:
+        T = 3
+        g0 = 2 * n_steps
+        bufs = [pool_dev[torch.from_numpy(idx[g0 + j]).to(dev)].contiguous() for j in range(T + 9)]
+        # stage 3 alone: scan registration finished before the clock starts (no overlap), mapping stage timed on its own stream
+        s3 = []
+        for j in range(4):
+            ctx.pipeline_prefetch_dev(bufs[j].data_ptr(), ROWS, COLS); ctx.pipeline_wait()
+            ctx.timer_record(0)
+            ctx.pipeline_step_dev(bufs[j].data_ptr(), ROWS, COLS, odom[g0 + j], mapped, stats)
+            ctx.timer_record(1)
+            s3.append(ctx.timer_elapsed_ms())
+        # stage 1 alone: four sweeps' scan registration back to back on the side stream
+        ctx.timer_record_side(0)
+        for j in range(4, 8):
+            ctx.pipeline_prefetch_dev(bufs[j].data_ptr(), ROWS, COLS)
+        ctx.timer_record_side(1)
+        ctx.pipeline_wait()
+        s1 = ctx.timer_elapsed_ms() / 4.0
+        for j in range(4, 8):
+            ctx.pipeline_discard(bufs[j].data_ptr())
+        stage = {"stage1_alone_points_per_s": S * NPTS / (s1 * 1e-3), "stage1_alone_ms_per_step": s1,
+                 "stage3_alone_points_per_s": S * NPTS / (float(np.mean(s3[1:])) * 1e-3), "stage3_alone_ms_per_step": float(np.mean(s3[1:]))}
+        ctx.pipeline_prefetch_dev(bufs[8].data_ptr(), ROWS, COLS)
         ctx.timeline_enable(True)
-        for k in range(W, min(W + 2, n_steps)):
-            ctx.pipeline_step_dev(step_dev[k].data_ptr(), ROWS, COLS, odom[k], mapped, stats)
+        tc = dict(qi=0, q=0, ins=0, feat=0)
+        for j in range(T):
+            ctx.pipeline_prefetch_dev(bufs[9 + j].data_ptr() if j + 1 < T else bufs[0].data_ptr(), ROWS, COLS)
+            ctx.pipeline_step_dev(bufs[8 + j].data_ptr(), ROWS, COLS, odom[g0 + 8 + j], mapped, stats)
+            c = ctx.last_step_counters()
+            tc["qi"] += c["query_iters"]; tc["q"] += c["queries"]; tc["ins"] += c["inserted"]; tc["feat"] += c["features"]
         rep = ctx.timeline_report(); ctx.timeline_enable(False)
-        tot = sum(float(l.split()[-2]) for l in rep.strip().splitlines())
-        log("[timeline] 2 steps, %.1f us of kernel time per step" % (tot / 2))
+        ctx.pipeline_discard(bufs[0].data_ptr())
+        peak, _ = measured_peak()
+        counters = dict(raw=float(S * NPTS), feat=tc["feat"] / T, qi=tc["qi"] / T, q=tc["q"] / T, ins=tc["ins"] / T)
+        rows = []
         for l in rep.strip().splitlines():
             name, us, n = l.rsplit(" ", 2)
-            log("  %-40s %9.1f us/step  x%-4d %5.1f%%" % (name[:40], float(us) / 2, int(n) // 2, 100 * float(us) / tot))
+            rows.append((name, float(us) / T / 1e3, int(n) / T))
+        tot = sum(r[1] for r in rows)
+        for name, ms_k, n in rows:
+            b = kernel_bytes(name, counters)
+            e = {"kernel": name, "ms_per_step": ms_k, "launches_per_step": n, "share_of_kernel_time": ms_k / tot if tot else None,
+                 "algorithmic_bytes_per_step": b, "achieved_gbs": (b / (ms_k * 1e-3) / 1e9) if (b and ms_k > 0) else None}
+            e["frac"] = e["achieved_gbs"] / peak if e["achieved_gbs"] else None
+            kernels.append(e)
+        kernels.sort(key=lambda e: -e["ms_per_step"])
+        log("[kernels] %d steps launch by launch, %.3f ms of kernel time per step" % (T, tot))
+        for e in kernels:
+            log("  %-44s %8.1f us/step x%-5.1f %5.1f%%  %s" % (e["kernel"][:44], 1e3 * e["ms_per_step"], e["launches_per_step"], 100 * e["share_of_kernel_time"],
+                                                            ("%.0f GB/s = %.4f of peak" % (e["achieved_gbs"], e["frac"])) if e["frac"] else ""))
 
     # ---- single-stream latency (one LiDAR, host sweep in -> host pose out) ---------------------------------------------
-    p50 = None
+    lat = {}
     if rank == 0 and not args.no_latency:
         c1 = cmb.Context(device=local_rank, **CFG)
-        c1.mapping_create(1, max_corner_points=max(4 * len(mc), 100000), max_surf_points=int(1.6 * len(ms)) + 200000)
+        c1.mapping_create(1, max_corner_points=cap_c, max_surf_points=cap_s)
         for o in range(0, len(ms), chunk):
             c1.map_insert([mc if o == 0 else mc[:0]], [ms[o:o + chunk]], [eye])
-        m1 = np.empty((1, 12), np.float32); s1 = (cmb.MatchStats * 1)()
-        lat = []
+        m1 = np.empty((1, 12), np.float32); s1_ = (cmb.MatchStats * 1)()
+        l_all, l_s1, l_s3 = [], [], []
         for k in range(4 + 20):
             fi = k % len(frames)
             fr = torch.from_numpy(np.ascontiguousarray(frames[fi:fi + 1])).pin_memory()
             od = pack_isos([noisy_odom(poses, fi, rng, synth)])
             t0 = time.perf_counter()
-            c1.pipeline_step_packed(fr.numpy(), od, m1, s1)
+            c1.pipeline_step_packed(fr.numpy(), od, m1, s1_)
+            t1 = time.perf_counter()
+            # the two stages on their own: upload + scan registration until the features are on the device, then the mapping stage
+            fi2 = (k + 7) % len(frames)
+            fr2 = torch.from_numpy(np.ascontiguousarray(frames[fi2:fi2 + 1])).pin_memory()
+            od2 = pack_isos([noisy_odom(poses, fi2, rng, synth)])
+            t2 = time.perf_counter()
+            c1.pipeline_prefetch(fr2.numpy()); c1.pipeline_wait()
+            t3 = time.perf_counter()
+            c1.pipeline_step_packed(fr2.numpy(), od2, m1, s1_)
+            t4 = time.perf_counter()
             if k >= 4:
-                lat.append(1e3 * (time.perf_counter() - t0))
-        p50 = float(np.median(lat))
+                l_all.append(1e3 * (t1 - t0)); l_s1.append(1e3 * (t3 - t2)); l_s3.append(1e3 * (t4 - t3))
+        lat = {"end_to_end": float(np.median(l_all)), "stage1": float(np.median(l_s1)), "stage3": float(np.median(l_s3))}
         c1.close()
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        corr_bytes = 96.0 * qi                              # 16 B query + 5 x 16 B neighbours per query-iteration
-        achieved = corr_bytes / (corr_ms * 1e-3) / 1e9 if corr_ms > 0 else 0.0
-        step_bytes = 16.0 * S * K * NPTS + 16.0 * feat + 96.0 * qi + 32.0 * ins
+        step_bytes = 16.0 * S * K * NPTS + 16.0 * cnt["feat"] + 96.0 * cnt["qi"] + 32.0 * cnt["ins"]
         step_gbs = step_bytes / (ms_total * 1e-3) / 1e9
+        big = [e for e in kernels if e["share_of_kernel_time"] and e["share_of_kernel_time"] >= 0.05]
+        dom = next((e for e in kernels if e["frac"]), None)          # longest kernel with an algorithmic-bytes figure
+        if kernels and kernels[0]["frac"]:
+            dom = kernels[0]
+        roof = {"bound": "hbm", "kernel": dom["kernel"] if dom else None, "achieved": dom["achieved_gbs"] if dom else step_gbs,
+                "peak": peak, "unit": "GB/s", "frac": (dom["frac"] if dom else step_gbs / peak),
+                "traffic": ncu_traffic(dom["kernel"]) if dom else None, "peak_source": peak_src,
+                "kernel_ms_per_step": dom["ms_per_step"] if dom else None,
+                "kernel_share_of_step": (dom["ms_per_step"] / (ms_max / K)) if dom else None,
+                "how": "per-kernel CUDA events on the launching stream in a separate launch-by-launch pass of 3 steps after the timed arms "
+                       "(the timed arms replay CUDA graphs); algorithmic bytes per kernel: DESIGN.md section 5",
+                "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
+                "kernels": big, "kernels_listed_share": sum(e["share_of_kernel_time"] for e in big) if big else None,
+                "kernel_time_ms_per_step": sum(e["ms_per_step"] for e in kernels) if kernels else None}
         line = {
-            "metric": "lidar_points_registered_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload, "streams_per_gpu": S, "points_per_sweep": NPTS, "map_points_per_stream": int(sum(map_pts)),
+            "config": {"workload": workload, "config": 2, "streams_per_gpu": S, "points_per_sweep": NPTS,
+                       "map_points_per_stream": int(sum(map_pts)), "map_points_per_stream_after": int(sum(map_after)),
+                       "map_samples_inserted": int(len(mc) + len(ms)),
                        "frame_leaf": [CFG["filter_corner"], CFG["filter_surf"]], "map_leaf": [CFG["map_filter_corner"], CFG["map_filter_surf"]],
                        "mean_gn_iterations": float(np.mean(iters)), "converged_frac": conv,
-                       "queries_per_sweep": q / float(S * K), "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush", "e2e_sweeps_ahead": A, "e2e_resident_diagnostic": bool(args.e2e_resident), "deferred_prefetch": DEFER,
-                       "parallelism": "streams sharded over ranks, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "search_kernel + search_hard_kernel (pointAssociateToMap + exact 5-NN on the voxel-cell hash map)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "peak_source": peak_src, "kernel_ms_per_step": corr_ms / K, "kernel_share_of_step": corr_ms / ms_total,
-                         "kernel_launches": corr_launches, "algorithmic_bytes_per_query_iteration": 96,
-                         "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
-                         # the other large kernel of the step, same accounting (16 B per raw point read + 16 B per
-                         # feature point written); it runs on the side stream concurrently with the matching kernels
-                         "scan_registration": {"kernel": "sr_ring_kernel", "ms_per_step": sr_ms / K,
-                                               "achieved": (16.0 * S * NPTS + 16.0 * feat / K) / (sr_ms / K * 1e-3) / 1e9 if sr_ms > 0 else 0.0,
-                                               "unit": "GB/s", "launches": sr_launches}},
+                       "queries_per_sweep": cnt["q"] / float(S * K), "sweeps": "fresh trajectory: no stream registers a sweep twice",
+                       "l2": "working set (S maps + S sweeps) > 126 MB L2, no explicit flush", "e2e_sweeps_ahead": A,
+                       "e2e_pinned_buffers": nbuf, "graphs_built_in_timed_region": [gb1[0] - gb0[0], gb1[1] - gb0[1]],
+                       "numa_bind": numa, "parallelism": "streams sharded over ranks, no collective"},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(S * NPTS * 16 + S * 48),
-                    "d2h_bytes_per_step": int(S * 48 + S * 48)},
-            "p50_latency_ms": p50,
+                    "d2h_bytes_per_step": int(S * 48 + S * C.sizeof(cmb.MatchStats))},
+            "stage_alone": stage,
+            "p50_latency_ms": lat.get("end_to_end"), "p50_latency_ms_by_stage": lat,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
@@ -434,6 +555,33 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs (1-based); 2 = the headline")
+    ap.add_argument("--streams", type=int, default=64, help="LiDAR streams per GPU (config 2)")
+    ap.add_argument("--pool", type=int, default=0, help="distinct synthetic sweeps generated on the host (0: one per stream-step)")
+    ap.add_argument("--ahead", type=int, default=2, help="end-to-end arm: sweeps uploaded ahead of the one being registered (1..3)")
+    ap.add_argument("--pinned-gb", type=float, default=6.0, help="end-to-end arm: pinned host memory for sweep buffers per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    synth = importlib.import_module(PKG + ".synth")
+    if args.impl == "reference":
+        return run_reference(args, synth, rank)
+    if args.config == 2:
+        return run_config2(args, synth, rank, world, local_rank)
+    extra = importlib.import_module("bench_configs")
+    return extra.run(args, synth, rank, world, local_rank)
 
 
 if __name__ == "__main__":

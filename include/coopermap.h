@@ -271,6 +271,12 @@ int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* po
  * cm_last_step_counters: {query-iterations, queries, inserted points, (reserved)} of the last mapping / pipeline step,
  * summed over the streams -- the run-time counts the algorithmic-bytes formula needs. */
 int cm_timer_record(cm_ctx* ctx, int which);
+/* stage-alone measurements: cm_timer_record_side records on the stream the prefetched scan registration runs on;
+ * cm_pipeline_wait blocks until every prefetched sweep is uploaded and registered; cm_pipeline_discard frees a prefetched
+ * sweep without running its step */
+int cm_timer_record_side(cm_ctx* ctx, int which);
+int cm_pipeline_wait(cm_ctx* ctx);
+int cm_pipeline_discard(cm_ctx* ctx, const void* frames);
 int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms);
 int cm_prof_enable(cm_ctx* ctx, int on);
 int cm_prof_drain(cm_ctx* ctx, double* kernel_ms, int* launches);
@@ -291,6 +297,7 @@ int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_co
 /* Development aid (no reference counterpart): per-warp trace of the 5-NN search kernel in Gauss-Newton evaluation `iter` of
  * the following cm_pipeline_step / cm_mapping_process calls (iter < 0: off).  4 words per warp: start ns, end ns,
  * (max << 32 | sum) level-0 candidates over the lanes, (hard queries << 32 | smid << 16 | is_corner). */
+int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out2);   /* graphs built so far: {Gauss-Newton loop, filter / insert chains} */
 int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop);   /* CUDA graphs cached for the Gauss-Newton loop; 1 = WHILE-node graphs */
 int cm_debug_search_trace_enable(cm_ctx* ctx, int iter);
 int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_words, size_t* n_words);

@@ -299,6 +299,21 @@ class Context:
     def timer_record(self, which):
         self._check(self.L.cm_timer_record(self.h, C.c_int(which)))
 
+    def timer_record_side(self, which):
+        self._check(self.L.cm_timer_record_side(self.h, C.c_int(which)))
+
+    def pipeline_wait(self):
+        self._check(self.L.cm_pipeline_wait(self.h))
+
+    def pipeline_discard(self, frames_ptr):
+        self._check(self.L.cm_pipeline_discard(self.h, C.c_void_p(frames_ptr)))
+
+    def graph_builds(self):
+        """(Gauss-Newton loop graphs built, filter / insert chain graphs captured) so far."""
+        a = (C.c_ulonglong * 2)()
+        self._check(self.L.cm_debug_graph_builds(self.h, a))
+        return int(a[0]), int(a[1])
+
     def timer_elapsed_ms(self):
         ms = C.c_float(0)
         self._check(self.L.cm_timer_elapsed_ms(self.h, C.byref(ms)))

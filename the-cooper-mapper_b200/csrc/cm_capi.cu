@@ -11,6 +11,7 @@
 
 namespace cm {
 unsigned long long g_launch_count = 0;
+unsigned long long g_alloc_generation = 0;
 Timeline g_timeline;
 
 MatchParamsDev dev_params(const cm_config& c) {

@@ -75,6 +75,7 @@ struct cm_ctx {
   std::vector<unsigned char> wins_shadow;   // the cube windows last sent to the device (they rarely change from sweep to sweep)
   cm::KernelProfiler prof, prof_sr;   // search_kernel + search_hard_kernel / sr_ring_kernel launches of the pipeline
   cudaEvent_t timer[2] = {nullptr, nullptr};
+  unsigned long long dbg_graph_builds = 0, dbg_stage_captures = 0;
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
   unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;
   // pipeline (scan registration -> mapping), cm_mapping.cu

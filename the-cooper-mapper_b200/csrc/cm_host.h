@@ -39,20 +39,22 @@ extern Timeline g_timeline;
     if (cm::g_timeline.on) cm::g_timeline.end((stream));                \
   } while (0)
 
-// Grow-only device allocation.
+// Grow-only device allocation.  g_alloc_generation counts the frees: a CUDA graph that captured a DeviceBuffer pointer is only
+// valid while the generation it was captured under is still current (GraphCache / MatchGraphCache check it).
+extern unsigned long long g_alloc_generation;
 struct DeviceBuffer {
   void* p = nullptr;
   size_t cap = 0;
   void reserve(size_t bytes) {
     if (bytes <= cap) return;
-    if (p) cudaFree(p);
+    if (p) { cudaFree(p); ++g_alloc_generation; }
     p = nullptr; cap = 0;
     size_t want = bytes + bytes / 4 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) throw CudaError{e, "cudaMalloc"};
     cap = want;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) { cudaFree(p); ++g_alloc_generation; } p = nullptr; cap = 0; }
   ~DeviceBuffer() { release(); }
   DeviceBuffer() = default;
   DeviceBuffer(const DeviceBuffer&) = delete;
@@ -62,13 +64,28 @@ struct DeviceBuffer {
 // Capture-once / replay-many helper for fixed launch sequences (a chain of small kernels whose arguments repeat from step to
 // step).  The first time a key is seen the sequence runs normally (grow-only buffers reach their size: cudaMalloc cannot be
 // captured), the second time it is captured into a CUDA graph, afterwards it is ONE submission.
+// The key holds the caller-visible arguments only; the scratch pointers a sequence bakes in (VoxelFilter / DeviceMap::insert
+// buffers) are covered by the allocation generation: an entry captured before ANY DeviceBuffer was re-allocated is dropped and
+// re-captured, so a graph can never replay a freed pointer.
 struct GraphCache {
-  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; };
+  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; unsigned long long gen; };
   std::vector<Entry> entries;
+  unsigned long long captures = 0;   // graphs instantiated so far (tests)
   template <class F>
   void run(const std::vector<unsigned long long>& key, cudaStream_t stream, F&& issue) {
     for (Entry& e : entries)
       if (e.key == key) {
+        if (e.exec && e.gen != g_alloc_generation) {   // some buffer moved since the capture: run plainly, capture again next time
+          cudaGraphExecDestroy(e.exec); e.exec = nullptr;
+          issue();
+          e.gen = g_alloc_generation;
+          return;
+        }
+        if (!e.exec && e.gen != g_alloc_generation) {  // buffers were still growing when this key was first seen
+          issue();
+          e.gen = g_alloc_generation;
+          return;
+        }
         if (e.exec) {
           if (cudaGraphLaunch(e.exec, stream) == cudaSuccess) { g_launch_count += e.launches; return; }
           cudaGetLastError();
@@ -83,22 +100,24 @@ struct GraphCache {
         const bool ok = cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph;
         e.launches = g_launch_count - before;
         g_launch_count = before;
-        if (ok && cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(e.exec, stream) == cudaSuccess) {
+        if (ok && e.gen == g_alloc_generation && cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(e.exec, stream) == cudaSuccess) {
           cudaGraphDestroy(graph);
           g_launch_count += e.launches;
+          ++captures;
           return;
         }
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
         if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
-        e.key.clear();   // never try this key again
+        if (e.gen != g_alloc_generation) e.gen = g_alloc_generation;   // a buffer grew during the capture: try again next time
+        else e.key.clear();                                           // never try this key again
         issue();
         return;
       }
     if (entries.size() >= 64) clear();
-    Entry e; e.key = key; e.exec = nullptr; e.launches = 0;
-    entries.push_back(e);
     issue();
+    Entry e; e.key = key; e.exec = nullptr; e.launches = 0; e.gen = g_alloc_generation;
+    entries.push_back(e);
   }
   void clear() { for (Entry& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec); entries.clear(); }
   ~GraphCache() { clear(); }
@@ -175,7 +194,8 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
 // submitted with ONE call -- the Gauss-Newton loop no longer pays a host launch per kernel, which matters most while the
 // PCIe link is busy with the next sweeps (tools/pcie_interference.py: +25 % step time with per-kernel launches).
 struct MatchGraphCache {
-  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; };
+  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; unsigned long long gen; };
+  unsigned long long builds = 0;   // graphs built so far (tests: stays small over many frames)
   std::vector<Entry> entries;
   // use_while: build the loop as a conditional WHILE node (CUDA 12.4+) whose body reads the evaluation index from device memory
   // and whose last node (gn_advance_kernel) calls cudaGraphSetConditional -- the graph then runs exactly as many evaluations as

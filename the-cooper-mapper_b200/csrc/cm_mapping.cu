@@ -187,14 +187,19 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   }
   float* pose_in = (float*)ctx->h_stage;
   CubeWindow* wins = (CubeWindow*)((char*)ctx->h_stage + pose_bytes);
-  for (int s = 0; s < S; s++) {
-    MappingStream& ms = ctx->mstreams[s];
-    HostIso odomNew; memcpy(odomNew.R, h_odom[s].R, 36); memcpy(odomNew.t, h_odom[s].t, 12);
-    HostIso L2W = iso_mul(ms.mappedLast, iso_inverse(ms.odomLast));   // transformAssociate, transform_utils.h:502-507
-    ms.mappedNew = iso_mul(L2W, odomNew);
-    if (!update_window(cfg, ms, ms.mappedNew.t, wins[s]))
-      return fail(ctx, CM_ERR_UNSUPPORTED, "sensor left the supported part of the cube grid (FeatureMap::shift not implemented)");
-    iso_to_twist(ms.mappedNew, &pose_in[6 * s]);
+  {
+    // every stream's window is validated on a copy first: a failure leaves no stream half-updated
+    std::vector<MappingStream> next(ctx->mstreams.begin(), ctx->mstreams.end());
+    for (int s = 0; s < S; s++) {
+      MappingStream& ms = next[s];
+      HostIso odomNew; memcpy(odomNew.R, h_odom[s].R, 36); memcpy(odomNew.t, h_odom[s].t, 12);
+      HostIso L2W = iso_mul(ms.mappedLast, iso_inverse(ms.odomLast));   // transformAssociate, transform_utils.h:502-507
+      ms.mappedNew = iso_mul(L2W, odomNew);
+      if (!update_window(cfg, ms, ms.mappedNew.t, wins[s]))
+        return fail(ctx, CM_ERR_UNSUPPORTED, "sensor left the supported part of the cube grid (FeatureMap::shift not implemented)");
+      iso_to_twist(ms.mappedNew, &pose_in[6 * s]);
+    }
+    ctx->mstreams.swap(next);
   }
   // prepareFeatureFrame: voxel filters
   ctx->m_corner_ds.reserve((size_t)S * cap_c * sizeof(float4));
@@ -269,7 +274,8 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
   m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p; m.nn_slot = (int*)ctx->m_slots.p;
   m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm; m.max_queries = max_q;
-  ctx->hardq.attach(m, (size_t)S * (max_q + 32));
+  // capacity in whole 256-query CTAs, like partial_blocks: the Gauss-Newton graph key then repeats from frame to frame
+  ctx->hardq.attach(m, (size_t)S * (size_t)(((max_q + 32 + 255) / 256) * 256));
   if (ctx->dbg_on) {
     ctx->dbg_words = (size_t)((max_q + 32 + 255) / 256) * S * 8 * 4;
     ctx->dbg_trace.reserve(ctx->dbg_words * sizeof(unsigned long long));
@@ -319,8 +325,14 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   CM_CUDA_CHECK(ctx, cudaGetLastError());
-  if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
-  if (flags[2] || flags[3]) return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+  if (flags[0] || flags[2] || flags[3]) {
+    // reported once: the flags are cleared so that the context stays usable (the dropped appends of THIS frame are lost, the
+    // poses below are not advanced -- the caller may retry the frame after making room)
+    cudaMemsetAsync(ctx->map.flags.p, 0, sizeof(int) * 8, st);
+    cudaStreamSynchronize(st);
+    if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
+    return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+  }
   ctx->last_query_iters = 0; ctx->last_queries = 0; ctx->last_inserted = 0;
   for (int s = 0; s < S; s++) {
     const unsigned long long q = (unsigned long long)(nds[s] + nds[S + s]);
@@ -722,8 +734,12 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     CM_CUDA_CHECK(ctx, cudaGetLastError());
-    if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
-    if (flags[2] || flags[3]) return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+    if (flags[0] || flags[2] || flags[3]) {
+      cudaMemsetAsync(ctx->map.flags.p, 0, sizeof(int) * 8, st);   // reported once (see mapping_process_dev)
+      cudaStreamSynchronize(st);
+      if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
+      return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+    }
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
@@ -762,6 +778,34 @@ int cm_timer_record(cm_ctx* ctx, int which) {
   CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->timer[which], ctx->stream));
   return CM_OK;
 }
+/* stage-alone measurements (bench.py): events on the SIDE stream, where prefetched scan registration runs; cm_pipeline_wait blocks
+ * until every prefetched sweep is uploaded and registered; cm_pipeline_discard drops a prefetched sweep without running its step */
+int cm_timer_record_side(cm_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 1) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  if (!ctx->timer[which]) CM_CUDA_CHECK(ctx, cudaEventCreate(&ctx->timer[which]));
+  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->timer[which], ctx->side_stream));
+  return CM_OK;
+}
+int cm_pipeline_wait(cm_ctx* ctx) {
+  if (!ctx) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  for (int i = 0; i < CM_PIPE_SLOTS; i++)
+    if (ctx->pipe[i].src && ctx->pipe[i].done) CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->pipe[i].done));
+  return CM_OK;
+}
+int cm_pipeline_discard(cm_ctx* ctx, const void* frames) {
+  if (!ctx || !frames) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  for (int i = 0; i < CM_PIPE_SLOTS; i++)
+    if (ctx->pipe[i].src == frames) {
+      if (ctx->pipe[i].done) CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->pipe[i].done));
+      ctx->pipe[i].src = nullptr; ctx->pipe[i].counts_ready = false;
+      return CM_OK;
+    }
+  return fail(ctx, CM_ERR_ARG, "no prefetched sweep with this address");
+}
 int cm_timer_elapsed_ms(cm_ctx* ctx, float* ms) {
   if (!ctx || !ms || !ctx->timer[0] || !ctx->timer[1]) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
@@ -786,7 +830,14 @@ int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_
 int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop) {
   if (!ctx) return CM_ERR_ARG;
   if (n_graphs) *n_graphs = (int)ctx->match_graphs.entries.size();
+  ctx->dbg_graph_builds = ctx->match_graphs.builds; ctx->dbg_stage_captures = ctx->stage_graphs.captures;
   if (while_loop) *while_loop = ctx->match_graphs.use_while ? 1 : 0;
+  return CM_OK;
+}
+/* graphs built so far: [0] Gauss-Newton loop graphs, [1] voxel-filter / map-insert chain captures (a steady-state pipeline stops building) */
+int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out2) {
+  if (!ctx || !out2) return CM_ERR_ARG;
+  out2[0] = ctx->match_graphs.builds; out2[1] = ctx->stage_graphs.captures;
   return CM_OK;
 }
 int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = ctx->prof_sr.enabled = on != 0; return CM_OK; }

@@ -899,19 +899,27 @@ static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
 bool MatchGraphCache::launch(const MatchLaunch& m, cudaStream_t stream) {
   if (m.dbg || m.nn || m.trace) return false;   // diagnostics are not replayable
   const std::vector<unsigned long long> key = match_graph_key(m);
-  for (Entry& e : entries)
+  for (size_t i = 0; i < entries.size(); i++) {
+    Entry& e = entries[i];
     if (e.key == key) {
+      if (e.gen != g_alloc_generation) {   // a device buffer moved since the capture (the key only holds this launch's own pointers)
+        cudaGraphExecDestroy(e.exec);
+        entries.erase(entries.begin() + i);
+        break;
+      }
       if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) return false;
       g_launch_count += e.launches;
       return true;
     }
+  }
   if (entries.size() >= 32) clear();   // buffers were re-allocated many times: start over
   if (use_while) {
     if (!d_iter) { if (cudaMalloc(&d_iter, sizeof(int)) != cudaSuccess) { cudaGetLastError(); d_iter = nullptr; use_while = false; } }
     if (use_while) {
-      Entry e; e.key = key; e.launches = 2; unsigned long long per_eval = 4;
+      Entry e; e.key = key; e.launches = 2; e.gen = g_alloc_generation; unsigned long long per_eval = 4;
       e.exec = build_while_graph(m, d_iter, stream, &per_eval);
       if (e.exec) {
+        ++builds;
         e.launches = 1 + per_eval;   // at least one evaluation runs; the real count is data dependent (a lower bound for gpu_launches)
         entries.push_back(e);
         if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -926,8 +934,8 @@ bool MatchGraphCache::launch(const MatchLaunch& m, cudaStream_t stream) {
   launch_match(m, stream, nullptr);
   cudaGraph_t graph = nullptr;
   if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return false; }
-  Entry e; e.key = key; e.exec = nullptr; e.launches = g_launch_count - before;
-  g_launch_count = before;
+  Entry e; e.key = key; e.exec = nullptr; e.launches = g_launch_count - before; e.gen = g_alloc_generation;
+  g_launch_count = before; ++builds;
   const cudaError_t rc = cudaGraphInstantiate(&e.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (rc != cudaSuccess) { cudaGetLastError(); return false; }
