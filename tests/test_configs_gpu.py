@@ -59,11 +59,14 @@ def test_config2_hdl64_full_size(cmb, oracle, synth):
         # the reference re-filters them only when they become valid (documented deviation, cm_map.cu header)
         near = lambda a: a[(np.abs(a[:, 0]) < 75.0) & (np.abs(a[:, 1]) < 75.0)]
         assert _same(near(maps2[cls]), near(om.cloud(which)))
-        # one point per (cube, voxel): voxel keys of the exported map are unique
-        v = np.floor(maps2[cls][:, :3] * np.float32(1.0 / 0.4)).astype(np.int64)
-        cube = np.round(maps2[cls][:, :3] / 50.0).astype(np.int64)
-        keys = np.concatenate([v, cube], 1)
-        assert len(np.unique(keys, axis=0)) == len(keys)
+        # one point per (cube, voxel) -- up to centroids that rounding put exactly on a voxel face: such a point shares its new
+        # voxel with the resident one until the next filter pass (also in the reference), a handful per million
+        def dups(a):
+            v = np.floor(a[:, :3] * np.float32(1.0 / 0.4)).astype(np.int64)
+            cube = np.round(a[:, :3] / 50.0).astype(np.int64)
+            keys = np.concatenate([v, cube], 1)
+            return len(keys) - len(np.unique(keys, axis=0))
+        assert dups(maps2[cls]) <= 4 and dups(near(maps2[cls])) == dups(near(om.cloud(which)))
 
 
 def test_config3_batched_streams_equal_single_stream_runs(cmb, oracle, synth):

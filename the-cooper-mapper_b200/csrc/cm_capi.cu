@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <map>
 #include <string>
@@ -59,7 +60,14 @@ int cm_ctx_create(const cm_config* cfg, cm_ctx** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) return CM_ERR_CUDA;
   cm_ctx* ctx = new cm_ctx();
   ctx->cfg = *cfg;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CM_ERR_CUDA; }
+  // the main stream (matching, map kernels: chains of short, latency-bound launches) gets the highest priority: its CTAs are
+  // placed first whenever an SM frees resources, so it interleaves with the long, issue-bound scan registration of the NEXT
+  // sweep on the (default-priority) side stream instead of queueing behind its 4096 CTAs  (COOPERMAP_NO_PRIORITY=1: off)
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (getenv("COOPERMAP_NO_PRIORITY")) prio_greatest = prio_least;
+  ctx->prio_high = prio_greatest; ctx->prio_low = prio_least;
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { delete ctx; return CM_ERR_CUDA; }
   *out = ctx;
   return CM_OK;
 }

@@ -32,6 +32,7 @@ struct LocalWindow {
 struct cm_ctx {
   cm_config cfg;
   cudaStream_t stream = nullptr;
+  int prio_high = 0, prio_low = 0;   // stream priorities: main / aux streams high, prefetch (side) stream low
   std::string err;
   // scratch for the host-buffer entry points
   cm::DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;

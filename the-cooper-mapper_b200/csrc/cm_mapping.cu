@@ -209,7 +209,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
   int* d_nds = (int*)ctx->m_n_ds.p;
   if (!ctx->aux_stream) {
-    CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CM_CUDA_CHECK(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, ctx->prio_high));
     CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
     CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
   }
@@ -590,7 +590,7 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
   if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
   try {
     cudaSetDevice(ctx->cfg.device);
-    if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, ctx->prio_low));
     if (!ctx->copy_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->copy_stream2) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
     int si = -1;
@@ -783,7 +783,7 @@ int cm_timer_record(cm_ctx* ctx, int which) {
 int cm_timer_record_side(cm_ctx* ctx, int which) {
   if (!ctx || which < 0 || which > 1) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
-  if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  if (!ctx->side_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, ctx->prio_low));
   if (!ctx->timer[which]) CM_CUDA_CHECK(ctx, cudaEventCreate(&ctx->timer[which]));
   CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->timer[which], ctx->side_stream));
   return CM_OK;

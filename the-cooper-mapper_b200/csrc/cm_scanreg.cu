@@ -59,26 +59,38 @@ __global__ void __launch_bounds__(256) sr_count_kernel(const float4* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 // block helpers
 // ------------------------------------------------------------------------------------------------------------
-// exclusive scan of one int per thread; returns the prefix, *total = block sum.  scratch: >= 32 ints, used as two
-// alternating halves (`phase` flips on every call, uniformly over the CTA) so that ONE barrier per scan is enough: every
-// warp adds up the warp totals itself, and the next scan writes the other half while slow warps still read this one.
-__device__ __forceinline__ int block_scan_excl(int v, int* scratch, int* total, int& phase) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int x = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  int* sc = scratch + 16 * phase;
-  phase ^= 1;
-  if (lane == 31) sc[warp] = x;
-  __syncthreads();
-  int w = lane < (SR_THREADS / 32) ? sc[lane] : 0;   // SR_THREADS / 32 = 16 warp totals
-  int incl = w;
-#pragma unroll
-  for (int o = 1; o < 16; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-  const int base = __shfl_sync(0xffffffffu, incl - w, warp);
-  *total = __shfl_sync(0xffffffffu, incl, SR_THREADS / 32 - 1);
-  return base + x - v;
-}
+#define SR_WARPS (SR_THREADS / 32)
+#define SR_MAXCH (SR_MAXCOLS / SR_THREADS)   // chunks of SR_THREADS items a ring can have at most
+
+// Ordered compaction offsets for one or two 0/1 flags per item, items e = k * SR_THREADS + tid (chunk-major order).
+// Phase 1: vote(k, f0, f1) for every chunk k (a ballot per flag, one store per warp), then ONE __syncthreads(); phase 2:
+// pos(k, f0, f1) returns the exclusive prefixes packed as lo | hi << 16 (a ring has < 65536 items) and advances the running
+// total.  Compared with a shuffle scan per chunk this is one barrier per scan instead of one per chunk and ~3x fewer
+// instructions.  `wt` alternates between two buffers (the caller flips `buf` between scans) so that the next scan's votes
+// cannot overtake slow readers of this one.
+struct FlagScan {
+  int* wt;          // [SR_MAXCH][SR_WARPS]
+  int run;          // packed totals of the chunks already passed in phase 2
+  int lane, warp;
+  __device__ __forceinline__ void begin(int* buffers, int& buf) {
+    wt = buffers + buf * (SR_MAXCH * SR_WARPS); buf ^= 1; run = 0;
+    lane = threadIdx.x & 31; warp = threadIdx.x >> 5;
+  }
+  __device__ __forceinline__ void vote(int k, bool f0, bool f1 = false) {
+    const unsigned int b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+    if (lane == 0) wt[k * SR_WARPS + warp] = __popc(b0) | (__popc(b1) << 16);
+  }
+  __device__ __forceinline__ int pos(int k, bool f0, bool f1 = false) {
+    const int v = lane < SR_WARPS ? wt[k * SR_WARPS + lane] : 0;
+    const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
+    const int tot = __reduce_add_sync(0xffffffffu, v);
+    const unsigned int b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+    const unsigned int lt = (1u << lane) - 1u;
+    const int p = run + before + (__popc(b0 & lt) | (__popc(b1 & lt) << 16));
+    run += tot;
+    return p;
+  }
+};
 
 struct ScanRegParamsDev {
   float scan_period, blind_sq, blind_thr, curv_thr, less_flat_leaf;
@@ -91,7 +103,7 @@ struct ScanRegArgs {
   const float* tags;         // optional [S][rows][cols]: the curvature field (ring + relTime) of every slot, precomputed
                              // by the raw-sweep front end; NULL: ring + scanPeriod * col / cols (organised sweeps)
   int rows, cols;
-  const int* ring_count;     // [S][rows]
+  const int* ring_count;     // [S][rows] valid points per ring; NULL when no output carries absolute cloud indices
   ScanRegParamsDev prm;
   // per-ring outputs, capacity `cols` each: [S][rows][cols]
   float4* ring_pts[4];       // 0 sharp, 1 lessSharp, 2 flat, 3 lessFlat (after the per-ring voxel filter)
@@ -103,28 +115,44 @@ struct ScanRegArgs {
   int* scan_range;           // [S][rows][2] inclusive start / end (_scanIndices)
 };
 
-// one window of pointClassify (ScanRegistration.cpp:557-602 / 603-649)
-__device__ __forceinline__ bool classify_window(const float* px, const float* py, const float* pz, int c, int R, bool forward,
-                                                float v[3]) {
-  float cx = 0.f, cy = 0.f, cz = 0.f;
-  const int first = forward ? c + R : c;   // forward: c+R, ..., c ; backward: c, c-1, ..., c-R
-  for (int t = 0; t <= R; t++) { int id = first - t; cx += px[id]; cy += py[id]; cz += pz[id]; }
+// mean and covariance of one window of pointClassify (ScanRegistration.cpp:557-581 / 603-627); the window of position c is
+// {c, c-1, .., c-R}, summed in that order
+__device__ __forceinline__ void window_cov(const float* px, const float* py, const float* pz, int c, int R, float& cx, float& cy, float& cz,
+                                           float A[6]) {
+  cx = 0.f; cy = 0.f; cz = 0.f;
+  for (int t = 0; t <= R; t++) { int id = c - t; cx += px[id]; cy += py[id]; cz += pz[id]; }
   float cnt = (float)(R + 1);
   cx /= cnt; cy /= cnt; cz /= cnt;
   float a00 = 0.f, a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f, a22 = 0.f;
   for (int t = 0; t <= R; t++) {
-    int id = first - t;
+    int id = c - t;
     float ax = px[id] - cx, ay = py[id] - cy, az = pz[id] - cz;
     a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
   }
-  float A[6] = {a00 / cnt, a10 / cnt, a20 / cnt, a11 / cnt, a21 / cnt, a22 / cnt};
+  A[0] = a00 / cnt; A[1] = a10 / cnt; A[2] = a20 / cnt; A[3] = a11 / cnt; A[4] = a21 / cnt; A[5] = a22 / cnt;
+}
+
+// true: the window provably FAILS the line test  l2 > 100 l1 && l2 > 10000 l0  (ScanRegistration.cpp:587-588 / 633-634), so its
+// eigen-solve can be skipped.  With m2 = l0 l1 + l0 l2 + l1 l2 (sum of the principal 2x2 minors) and tr = l0 + l1 + l2: a
+// window that passes has l1 < l2 / 100 and l0 < l2 / 10000, hence m2 < 0.010102 l2^2 <= 0.010102 tr^2.  The bound used, 0.0105,
+// leaves 4 %: the float rounding of m2 and tr (~1e-6 tr^2) and the backward error of the iterative solver that makes the real
+// decision (|l_computed - l| <~ 30 eps l2, i.e. 1.8 % of l2 / 10000) are far inside it.  NaN / zero windows fall through to the solver.
+__device__ __forceinline__ bool window_not_line(const float A[6]) {
+  const float tr = A[0] + A[3] + A[5];
+  const float m2 = (A[0] * A[3] - A[1] * A[1]) + (A[0] * A[5] - A[2] * A[2]) + (A[3] * A[5] - A[4] * A[4]);
+  return m2 > 0.0105f * (tr * tr);
+}
+
+// the rest of the window test once the covariance is known: eigen-solve, ratio test, 0.08 m line test (:582-602 / 628-649)
+__device__ __forceinline__ bool window_line(const float* px, const float* py, const float* pz, int c, int R, float cx, float cy, float cz,
+                                            const float A[6], float v[3]) {
   float w[3], V[9];
   eig3_sym(A, w, V);
   if (w[2] > 100.f * w[1] && w[2] > 10000.f * w[0]) {
     v[0] = V[2]; v[1] = V[5]; v[2] = V[8];
     float vnorm = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     for (int t = 0; t <= R; t++) {
-      int id = first - t;
+      int id = c - t;
       float ax = px[id] - cx, ay = py[id] - cy, az = pz[id] - cz;
       float kx = ay * v[2] - az * v[1], ky = az * v[0] - ax * v[2], kz = ax * v[1] - ay * v[0];
       float distance = sqrtf(kx * kx + ky * ky + kz * kz) / vnorm;
@@ -133,21 +161,6 @@ __device__ __forceinline__ bool classify_window(const float* px, const float* py
     return true;
   }
   return false;
-}
-
-__device__ __forceinline__ int point_classify(const float* px, const float* py, const float* pz, int c, const ScanRegParamsDev& prm) {
-  float v1[3], v2[3];
-  bool line1 = classify_window(px, py, pz, c, prm.R, false, v1);
-  bool line2 = classify_window(px, py, pz, c, prm.R, true, v2);
-  if (line1 && line2) {
-    float ab = v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2];
-    float disab = sqrtf(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]) * sqrtf(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
-    float diff = ab / disab;
-    if ((double)diff < prm.cos175 || (double)diff > prm.cos5) return L_SURFACE_FLAT;
-    else if ((double)diff > prm.cos135 && (double)diff < prm.cos45) return L_CORNER_SHARP;
-  }
-  if (line1 || line2) return L_ONESIDE_FLAT;
-  return L_MESSY;
 }
 
 __device__ __forceinline__ float cos_angle(const float* px, const float* py, const float* pz, int a, int b) {   // math_utils.h:82-87
@@ -160,65 +173,195 @@ __device__ __forceinline__ float sq_diff(const float* px, const float* py, const
   return dx * dx + dy * dy + dz * dz;
 }
 
+// ---- in-CTA bitonic sort of P keys (P a power of two, P / E threads hold E consecutive keys each in registers) ------------
+// Compare-exchange partners inside a thread cost a few selects, partners in the same warp one shuffle per key, only the
+// partners in another warp (strides >= 32 E) go through shared memory with barriers: 10 of the 66 stages at P = 2048.
+__device__ __forceinline__ unsigned int shfl_xor_key(unsigned int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ unsigned long long shfl_xor_key(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+template <typename K, int E>
+__device__ __forceinline__ void bitonic_sort_regs(K* key, int P) {
+  const int tid = threadIdx.x;
+  const int e0 = tid * E;
+  const bool act = e0 < P;
+  K v[E];
+#pragma unroll
+  for (int j = 0; j < E; j++) v[j] = act ? key[e0 + j] : (K)~(K)0;
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      if (jj >= 32 * E) {                    // partner in another warp
+        __syncthreads();
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < E; j++) key[e0 + j] = v[j];
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < E; j++) {
+            const int e = e0 + j;
+            const K o = key[e ^ jj];
+            const bool keepmin = ((e & jj) == 0) == ((e & kk) == 0);
+            const bool oless = o < v[j];
+            v[j] = (keepmin == oless) ? o : v[j];
+          }
+        }
+      } else if (jj >= E) {                  // partner in another lane of this warp (every lane executes the shuffle)
+        const int lm = jj / E;
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+          const int e = e0 + j;
+          const K o = shfl_xor_key(v[j], lm);
+          const bool keepmin = ((e & jj) == 0) == ((e & kk) == 0);
+          const bool oless = o < v[j];
+          v[j] = (keepmin == oless) ? o : v[j];
+        }
+      } else {                               // partner inside this thread: jj in {1, 2} (E <= 4), compile-time register indices
+        const bool up = (e0 & kk) == 0;      // e0 .. e0 + E - 1 share every bit >= E, and kk > jj
+        if (E >= 2 && jj == 1) {
+#pragma unroll
+          for (int j = 0; j + 1 < E; j += 2) {
+            const bool up_j = (kk == 2 && E == 4) ? (((e0 + j) & kk) == 0) : up;   // kk = 2 < E = 4: the direction alternates inside the thread
+            const K a = v[j], b = v[j + 1];
+            if ((a > b) == up_j) { v[j] = b; v[j + 1] = a; }
+          }
+        } else if (E >= 4 && jj == 2) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const K a = v[j], b = v[j + 2];
+            if ((a > b) == up) { v[j] = b; v[j + 2] = a; }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < E; j++) key[e0 + j] = v[j];
+  }
+  __syncthreads();
+}
+
+// shared-memory-only version for sizes the register version does not cover (P > 4 * SR_THREADS)
+template <typename K>
+__device__ __forceinline__ void bitonic_sort_smem(K* key, int P) {
+  __syncthreads();
+  for (int kk = 2; kk <= P; kk <<= 1)
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      for (int pr = threadIdx.x; pr < (P >> 1); pr += SR_THREADS) {
+        const int i = ((pr & ~(jj - 1)) << 1) | (pr & (jj - 1)), ixj = i | jj;
+        const K x = key[i], y = key[ixj];
+        const bool up = (i & kk) == 0;
+        if ((x > y) == up) { key[i] = y; key[ixj] = x; }
+      }
+      __syncthreads();
+    }
+}
+
+template <typename K>
+__device__ __forceinline__ void bitonic_sort(K* key, int P) {
+  if (P <= 1) { __syncthreads(); return; }
+  if (P <= SR_THREADS) bitonic_sort_regs<K, 1>(key, P);
+  else if (P == 2 * SR_THREADS) bitonic_sort_regs<K, 2>(key, P);
+  else if (P == 4 * SR_THREADS) bitonic_sort_regs<K, 4>(key, P);
+  else bitonic_sort_smem<K>(key, P);
+}
+
+// smallest power of two >= v (v >= 1)
+__device__ __forceinline__ int pow2_ge(int v) { return v <= 1 ? 1 : 1 << (32 - __clz(v - 1)); }
+
 // ------------------------------------------------------------------------------------------------------------
 // kernel 2: everything for one ring
 // ------------------------------------------------------------------------------------------------------------
-// dynamic shared memory layout, `cap` = cols rounded up to a multiple of 4, P2 = next power of two >= cols
+// dynamic shared memory layout, `cap` = cols rounded up to a multiple of 8, P2 = next power of two >= cols
 //   float px[cap], py[cap], pz[cap], pi[cap], curv[cap]
-//   u64   key[P2]                        (sort keys: rank sort scratch / voxel sort)
-//   u16   col[cap], lst[4][cap], nf[cap], ord[cap]
+//   u16   col[cap]
 //   s8    state[cap], snap[cap], ev[cap], lab[cap]
-extern __shared__ unsigned char sr_smem[];
+//   ---- scratch (first the staging area of the raw ring row: float4 row[cols], filled by ONE bulk copy) ----
+//   u64   key[KEYN]                      (rank keys / prefix arrays / voxel sort)
+//   u16   lst[4][cap], nf[cap], ord[cap]
+extern __shared__ __align__(16) unsigned char sr_smem[];
+
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   const int ring = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const int rows = a.rows, cols = a.cols;
   const ScanRegParamsDev& prm = a.prm;
   const int R = prm.R;
-  const int cap = (cols + 3) & ~3;
-  int P2 = 1; while (P2 < cols) P2 <<= 1;
+  const int cap = (cols + 7) & ~7;
+  const int P2 = pow2_ge(cols);
 
   float* px = reinterpret_cast<float*>(sr_smem);
   float* py = px + cap; float* pz = py + cap; float* pin = pz + cap; float* curv = pin + cap;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(curv + cap);
-  const int KEYN = (8 * P2 >= 10 * cap) ? P2 : (10 * cap + 7) / 8;   // `key` doubles as five u16 prefix arrays
-  unsigned short* colv = reinterpret_cast<unsigned short*>(key + KEYN);
-  unsigned short* lst[4] = {colv + cap, colv + 2 * cap, colv + 3 * cap, colv + 4 * cap};
-  unsigned short* nfl = colv + 5 * cap;
-  unsigned short* ord = colv + 6 * cap;
-  signed char* state = reinterpret_cast<signed char*>(colv + 7 * cap);
+  unsigned short* colv = reinterpret_cast<unsigned short*>(curv + cap);
+  signed char* state = reinterpret_cast<signed char*>(colv + cap);
   signed char* snap = state + cap; signed char* ev = snap + cap; signed char* lab = ev + cap;
-  __shared__ int s_scan[32];
-  int scan_phase = 0;   // uniform over the CTA: every thread makes the same sequence of block_scan_excl calls
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(lab + cap);      // 26 * cap bytes in: a multiple of 16
+  const int KEYN = (8 * P2 >= 10 * cap) ? P2 : (10 * cap + 7) / 8;   // `key` doubles as five u16 prefix arrays
+  unsigned short* lst0 = reinterpret_cast<unsigned short*>(key + KEYN);
+  unsigned short* lst[4] = {lst0, lst0 + cap, lst0 + 2 * cap, lst0 + 3 * cap};
+  unsigned short* nfl = lst0 + 4 * cap;
+  unsigned short* ord = lst0 + 5 * cap;
+  const float4* stage = reinterpret_cast<const float4*>(key);         // 16 * cols bytes <= 8 * KEYN + 12 * cap
+  __shared__ int s_wt[2 * SR_MAXCH * SR_WARPS];
+  __shared__ __align__(8) unsigned long long s_mbar;
+  int fs_buf = 0;   // uniform over the CTA: every thread makes the same sequence of scans
+  FlagScan fs;
   __shared__ int s_cnt[5];          // list lengths: sharp, lessSharp, flat, lessFlatRaw, (spare)
   __shared__ int s_misc[8];
+  const int nch_cols = (cols + SR_THREADS - 1) / SR_THREADS;
 
-  // ---- ring ranges (_scanIndices) -------------------------------------------------------------------------
-  const int* rc = a.ring_count + s * rows;
-  int S0 = 0;
-  for (int r = 0; r < ring; r++) S0 += rc[r];
-  const int n = rc[ring];
-  const int E0 = (S0 + n > 0) ? S0 + n - 1 : 0;   // range.second = cloudSize > 0 ? cloudSize - 1 : 0
-  if (tid == 0 && a.scan_range) { a.scan_range[(s * rows + ring) * 2] = S0; a.scan_range[(s * rows + ring) * 2 + 1] = E0; }
-  int* ring_n = a.ring_n + (s * rows + ring) * 5;
-  if (tid < 5) s_cnt[tid] = 0;
-
-  // ---- ordered compaction of the ring (OrganizedScanRegistration.cpp:102-126) ---------------------------------
+  // ---- the ring row -> shared memory with one bulk copy (TMA, 16 * cols bytes), completion on an mbarrier -------------------
   const float4* src = a.frames + ((size_t)s * rows + ring) * cols;
-  {
-    int base = 0;
-    for (int c0 = 0; c0 < cols; c0 += SR_THREADS) {
-      int c = c0 + tid;
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool ok = false;
-      if (c < cols) { p = src[c]; ok = point_valid(p, prm.blind_sq); }
-      int tot;
-      int pos = block_scan_excl(ok ? 1 : 0, s_scan, &tot, scan_phase);
-      if (ok) { int d = base + pos; px[d] = p.x; py[d] = p.y; pz[d] = p.z; pin[d] = p.w; colv[d] = (unsigned short)c; }
-      base += tot;
-    }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (tid == 0) {
+    const unsigned int bytes = (unsigned int)cols * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(stage)), "l"(src), "r"(bytes), "r"(smem_addr(&s_mbar)) : "memory");
+  }
+  // ---- ring ranges (_scanIndices): only the optional outputs carry absolute cloud indices ---------------------------------
+  int S0 = 0;
+  if (a.ring_count) { const int* rc = a.ring_count + s * rows; for (int r = 0; r < ring; r++) S0 += rc[r]; }
+  int* ring_n = a.ring_n + (s * rows + ring) * 5;
+  if (tid < 5) s_cnt[tid] = 0;
+  {
+    unsigned int done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(smem_addr(&s_mbar)) : "memory");
+    }
+  }
+
+  // ---- ordered compaction of the ring (OrganizedScanRegistration.cpp:102-126) ---------------------------------
+  int n;
+  {
+    unsigned int okmask = 0;
+    fs.begin(s_wt, fs_buf);
+    for (int k = 0; k < nch_cols; k++) {
+      const int c = k * SR_THREADS + tid;
+      const bool ok = c < cols && point_valid(stage[c], prm.blind_sq);
+      okmask |= (ok ? 1u : 0u) << k;
+      fs.vote(k, ok);
+    }
+    __syncthreads();
+    for (int k = 0; k < nch_cols; k++) {
+      const int c = k * SR_THREADS + tid;
+      const bool ok = (okmask >> k) & 1u;
+      const int d = fs.pos(k, ok) & 0xFFFF;
+      if (ok) { const float4 p = stage[c]; px[d] = p.x; py[d] = p.y; pz[d] = p.z; pin[d] = p.w; colv[d] = (unsigned short)c; }
+    }
+    n = fs.run & 0xFFFF;
+  }
+  __syncthreads();   // the staging area is free from here on
+  const int E0 = (S0 + n > 0) ? S0 + n - 1 : 0;   // range.second = cloudSize > 0 ? cloudSize - 1 : 0
+  if (tid == 0 && a.scan_range) { a.scan_range[(s * rows + ring) * 2] = S0; a.scan_range[(s * rows + ring) * 2 + 1] = E0; }
   const size_t cbase = (size_t)s * rows * cols + S0;   // this ring's slice of the full-resolution arrays
   for (int i = tid; i < n; i += SR_THREADS) {
     state[i] = 0; snap[i] = 0; ev[i] = 0; lab[i] = L_NONE; curv[i] = -1.f;
@@ -246,6 +389,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     if (tid < 5) ring_n[tid] = 0;
     return;
   }
+  const int nch = (n + SR_THREADS - 1) / SR_THREADS;
 
   // ---- setScanBuffersFor (ScanRegistration.cpp:462-522), parallel replay ----------------------------------------
   // events of the main loop, i in [R, n-1-R): bit0-1 type (1 blind, 2 jump far->near "A", 3 jump "B"), bit2 ratio test
@@ -332,13 +476,14 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   }
   __syncthreads();
 
-  // ---- region bounds (ScanRegistration.cpp:249-262), size_t integer arithmetic on ABSOLUTE indices --------------
-  __shared__ int reg_sp[SR_MAXREG], reg_ep[SR_MAXREG];   // relative to the ring; ep < sp: skipped
+  // ---- region bounds (ScanRegistration.cpp:249-262), size_t integer arithmetic on ABSOLUTE indices (the bounds relative to
+  //      the ring do not depend on S0: S0 * NR is a multiple of NR and drops out of both floor divisions) ------------------
+  __shared__ int reg_sp[SR_MAXREG], reg_ep[SR_MAXREG];   // relative to the ring; skipped regions: sp = INT_MAX, ep = -1
   if (tid < prm.nregions) {
     unsigned long long s5 = (unsigned long long)S0 + R, e5 = (unsigned long long)E0 - R, NR = prm.nregions, j = tid;
     unsigned long long sp = (s5 * (NR - j) + e5 * j) / NR;
     unsigned long long ep = (s5 * (NR - 1 - j) + e5 * (j + 1)) / NR - 1;
-    if (ep <= sp) { reg_sp[tid] = 1; reg_ep[tid] = 0; }
+    if (ep <= sp) { reg_sp[tid] = 0x7fffffff; reg_ep[tid] = -1; }
     else { reg_sp[tid] = (int)(sp - S0); reg_ep[tid] = (int)(ep - S0); }
   }
   __syncthreads();
@@ -351,37 +496,73 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   __shared__ int cnt2[4][SR_MAXREG], cnt3[4][SR_MAXREG];   // per list (sharp, lessSharp, flat, lessFlatRaw) and region
   __shared__ int start2[2][SR_MAXREG], start3[3][SR_MAXREG];   // exclusive prefixes at region starts
   __shared__ int base[4][SR_MAXREG + 1];
+  __shared__ int s_nw, s_ns;                   // classification work lists: needed windows, windows that need the eigen-solve
   const int NR = prm.nregions;
-  // region of a cell (regions are contiguous and ordered; skipped regions have ep < sp)
+  // region of a cell (regions are contiguous and ordered): the last region that starts at or before the cell
   for (int c = tid; c < n; c += SR_THREADS) {   // ev[] is free after the mask replay: region id of every cell (-1: none)
     int rj = -1;
-    for (int j = 0; j < NR; j++) if (reg_ep[j] >= reg_sp[j] && c >= reg_sp[j] && c <= reg_ep[j]) rj = j;
+    for (int j = 0; j < NR; j++) if (c >= reg_sp[j]) rj = j;
+    if (rj >= 0 && c > reg_ep[rj]) rj = -1;
     ev[c] = (signed char)rj;
   }
+  if (tid < 4 * SR_MAXREG) { (&cnt2[0][0])[tid] = 0; (&cnt3[0][0])[tid] = 0; }
+  if (tid == 0) { s_nw = 0; s_ns = 0; }
   __syncthreads();
   auto region_of = [&](int c) -> int { return (int)ev[c]; };
-  if (tid < 4 * SR_MAXREG) { (&cnt2[0][0])[tid] = 0; (&cnt3[0][0])[tid] = 0; }
+  // window results of pointClassify live in the scratch area until the index lists are built
+  float2* wxy = reinterpret_cast<float2*>(key);            // direction of a line window (x, y)
+  float* wz = reinterpret_cast<float*>(lst[0]);            //   and z                                   (lst[0..1])
+  signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // window result: 1 line, 3 no line      (first half of lst[2])
+  signed char* wcand = wfl + cap;                               // 1: the cell is a pass-3 candidate    (second half of lst[2])
+  unsigned short* wlist = lst[3];                               // windows some candidate needs
+  unsigned short* slist = ord;                                  // windows whose eigen-solve cannot be skipped
   // ---- cells above the curvature threshold, in index order (they are the pass-3 candidates, :305-314) -------------
   {
-    int total = 0;
-    for (int c0 = 0; c0 < n; c0 += SR_THREADS) {
-      const int c = c0 + tid;
+    unsigned int m = 0;
+    fs.begin(s_wt, fs_buf);
+    for (int k = 0; k < nch; k++) {
+      const int c = k * SR_THREADS + tid;
       const int rj = c < n ? region_of(c) : -1;
       const bool isnf = rj >= 0 && !(curv[c] < prm.curv_thr);
-      int tot;
-      const int pos = block_scan_excl(isnf ? 1 : 0, s_scan, &tot, scan_phase);
-      if (isnf) nfl[total + pos] = (unsigned short)c;
-      if (rj >= 0 && c == reg_sp[rj]) nf_begin[rj] = total + pos;
-      total += tot;
+      m |= (isnf ? 1u : 0u) << k;
+      if (c < n) wcand[c] = isnf ? 1 : 0;
+      fs.vote(k, isnf);
     }
-    __syncthreads();   // nf_begin[] of the last chunk (the scan itself has a single barrier)
+    __syncthreads();
+    for (int k = 0; k < nch; k++) {
+      const int c = k * SR_THREADS + tid;
+      const bool isnf = (m >> k) & 1u;
+      const int pos = fs.pos(k, isnf) & 0xFFFF;
+      if (isnf) nfl[pos] = (unsigned short)c;
+      const int rj = c < n ? region_of(c) : -1;
+      if (rj >= 0 && c == reg_sp[rj]) nf_begin[rj] = pos;
+    }
+    if (tid == 0) nf_begin[NR] = fs.run & 0xFFFF;
+    // the windows pointClassify needs: window w = {w, .., w-R} is the backward window of candidate w and the forward window
+    // of candidate w - R (ScanRegistration.cpp:557-649: the second one is summed in the same order), so it is evaluated once
+    m = 0;
+    fs.begin(s_wt, fs_buf);
+    for (int k = 0; k < nch; k++) {
+      const int w = k * SR_THREADS + tid;
+      const bool need = w < n && (wcand[w] != 0 || (w >= R && wcand[w - R] != 0));
+      m |= (need ? 1u : 0u) << k;
+      fs.vote(k, need);
+    }
+    __syncthreads();
+    for (int k = 0; k < nch; k++) {
+      const int w = k * SR_THREADS + tid;
+      const bool need = (m >> k) & 1u;
+      const int pos = fs.pos(k, need) & 0xFFFF;
+      if (need) wlist[pos] = (unsigned short)w;
+    }
     if (tid == 0) {
-      nf_begin[NR] = total;
-      for (int j = NR - 1; j >= 0; j--) if (reg_ep[j] < reg_sp[j]) nf_begin[j] = nf_begin[j + 1];   // skipped regions are empty
+      s_nw = fs.run & 0xFFFF;
+      for (int j = NR - 1; j >= 0; j--) if (reg_ep[j] < 0) nf_begin[j] = nf_begin[j + 1];   // skipped regions are empty
     }
   }
   __syncthreads();
   const int m_all = nf_begin[NR];
+  const int n_win = s_nw;
   // ---- warp 0: pass 1, chained over the regions (greedy flat picks with +-R suppression, :267-284, 524-545);
   //      warps 1..15: pointClassify of every pass-3 candidate (:316, 547-666) -- independent of the picks ------------
   if (tid < 32) {
@@ -390,7 +571,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     for (int j = 0; j < NR; j++) {
       const int sp = reg_sp[j], ep = reg_ep[j];
       if (lane == 0) p1_begin[j] = np1;
-      if (ep >= sp) {
+      if (ep >= 0) {
         for (int k = 0; k < prm.max_flat; k++) {
           unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
           for (int c = sp + lane; c <= ep; c += 32) {
@@ -416,30 +597,25 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     }
     if (lane == 0) p1_begin[NR] = np1;
   } else {
-    // pointClassify(c) looks at the window {c, c-1, .., c-R} and at {c+R, .., c} -- the second one IS the first window of
-    // point c+R, summed in the same order, so every window is evaluated once: by its own point when that point is a
-    // candidate too, else by the point R cells before it.  Results per window position: line flag + direction.
-    float2* wxy = reinterpret_cast<float2*>(key);            // `key` and the four index lists are not in use yet
-    float* wz = reinterpret_cast<float*>(lst[0]);            // lst[0..1]
-    signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // window result: 1 line, 3 no line   (first half of lst[2])
-    signed char* wcand = wfl + cap;                               // 1: the cell is a candidate itself (second half of lst[2])
     const int NT = SR_THREADS - 32, t = tid - 32;
-    for (int c = t; c < n; c += NT) wcand[c] = 0;
+    // phase A: covariance of every needed window + the cheap exact test that rules most of them out (window_not_line)
+    for (int i = t; i < n_win; i += NT) {
+      const int w = wlist[i];
+      float cx, cy, cz, A[6];
+      window_cov(px, py, pz, w, R, cx, cy, cz, A);
+      if (window_not_line(A)) wfl[w] = 3;
+      else slist[atomicAdd(&s_ns, 1)] = (unsigned short)w;
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
-    for (int i = t; i < m_all; i += NT) wcand[nfl[i]] = 1;
-    asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
-    for (int i = t; i < m_all; i += NT) {
-      const int c = nfl[i];
-      float v[3];
-      const bool own_fwd = wcand[c + R] == 0;                // c+R is not a candidate: this thread owns its window
-      const bool l1 = classify_window(px, py, pz, c, R, false, v);
-      if (l1) { wxy[c] = make_float2(v[0], v[1]); wz[c] = v[2]; }
-      wfl[c] = l1 ? 1 : 3;
-      if (own_fwd) {
-        const bool l2 = classify_window(px, py, pz, c + R, R, false, v);
-        if (l2) { wxy[c + R] = make_float2(v[0], v[1]); wz[c + R] = v[2]; }
-        wfl[c + R] = l2 ? 1 : 3;
-      }
+    // phase B: the windows that may be lines, densely packed over the lanes: eigen-solve + 0.08 m line test
+    const int n_sv = s_ns;
+    for (int i = t; i < n_sv; i += NT) {
+      const int w = slist[i];
+      float cx, cy, cz, A[6], v[3];
+      window_cov(px, py, pz, w, R, cx, cy, cz, A);
+      const bool l = window_line(px, py, pz, w, R, cx, cy, cz, A, v);
+      if (l) { wxy[w] = make_float2(v[0], v[1]); wz[w] = v[2]; }
+      wfl[w] = l ? 1 : 3;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
     for (int i = t; i < m_all; i += NT) {                    // ScanRegistration.cpp:651-665
@@ -460,18 +636,20 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     }
   }
   __syncthreads();
+  // ---- descending (curvature, index) order inside every region: rank by counting.  The candidate list is in index order, so
+  //      an equal curvature later in the list wins the tie: two loops of 32-bit compares on the curvature bits ---------------
+  unsigned int* ckey = reinterpret_cast<unsigned int*>(key);
+  for (int i = tid; i < m_all; i += SR_THREADS) ckey[i] = __float_as_uint(curv[nfl[i]]);   // curvatures are >= 0: bit order = value order
+  __syncthreads();
   for (int i = tid; i < m_all; i += SR_THREADS) {
     const int c = nfl[i];
-    key[i] = ((unsigned long long)__float_as_uint(curv[c]) << 32) | (unsigned int)c;
-  }
-  __syncthreads();
-  // ---- descending (curvature, index) order inside every region: rank by counting -------------------------------------
-  for (int i = tid; i < m_all; i += SR_THREADS) {
-    const int rj = region_of(nfl[i]);
-    const unsigned long long ki = key[i];
+    const int rj = region_of(c);
+    const unsigned int ki = ckey[i];
+    const int b0 = nf_begin[rj], b1 = nf_begin[rj + 1];
     int rank = 0;
-    for (int k = nf_begin[rj]; k < nf_begin[rj + 1]; k++) rank += (key[k] > ki) ? 1 : 0;
-    ord[nf_begin[rj] + rank] = nfl[i];
+    for (int k = b0; k < i; k++) rank += (ckey[k] > ki) ? 1 : 0;
+    for (int k = i + 1; k < b1; k++) rank += (ckey[k] >= ki) ? 1 : 0;
+    ord[b0 + rank] = (unsigned short)c;
   }
   __syncthreads();
   // `key` is free again: carve four u16 prefix arrays out of it
@@ -480,43 +658,58 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   // ---- pass 2 (:286-303), whole ring: c < thr -> lessFlatRaw; EDGE_BROKEN (as seen after the region's picks) -> sharp
   //      and lessSharp.  Ring-wide exclusive prefixes; the value at a region's first cell is that region's offset. ------
   {
-    int t1 = 0, t2 = 0;
-    for (int c0 = 0; c0 < n; c0 += SR_THREADS) {
-      const int c = c0 + tid;
+    unsigned int m = 0;
+    fs.begin(s_wt, fs_buf);
+    for (int k = 0; k < nch; k++) {
+      const int c = k * SR_THREADS + tid;
       const int rj = c < n ? region_of(c) : -1;
       const bool isflat = rj >= 0 && (curv[c] < prm.curv_thr);
       const bool isedge = rj >= 0 && (snap[c] == P_EDGE_BROKEN);
-      // both counters in one scan: low / high 16 bits (a ring has < 65536 cells)
-      int a12;
-      const int p12 = block_scan_excl((isflat ? 1 : 0) | (isedge ? 0x10000 : 0), s_scan, &a12, scan_phase);
-      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16, a1 = a12 & 0xFFFF, a2 = a12 >> 16;
-      if (c < n) { pfa[c] = (unsigned short)(t1 + p1); pfb[c] = (unsigned short)(t2 + p2); }
-      if (rj >= 0 && c == reg_sp[rj]) { start2[0][rj] = t1 + p1; start2[1][rj] = t2 + p2; }
+      m |= ((isflat ? 1u : 0u) | (isedge ? 0x10000u : 0u)) << k;
+      fs.vote(k, isflat, isedge);
       if (isflat) atomicAdd(&cnt2[3][rj], 1);
       if (isedge) { atomicAdd(&cnt2[0][rj], 1); atomicAdd(&cnt2[1][rj], 1); }
-      t1 += a1; t2 += a2;
+    }
+    __syncthreads();
+    for (int k = 0; k < nch; k++) {
+      const int c = k * SR_THREADS + tid;
+      const int p12 = fs.pos(k, (m >> k) & 1u, (m >> (16 + k)) & 1u);
+      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16;
+      if (c < n) { pfa[c] = (unsigned short)p1; pfb[c] = (unsigned short)p2; }
+      const int rj = c < n ? region_of(c) : -1;
+      if (rj >= 0 && c == reg_sp[rj]) { start2[0][rj] = p1; start2[1][rj] = p2; }
     }
   }
   // ---- pass 3 (:305-354) over the descending order of every region: emission counters become prefix sums -----------
   unsigned short* qfa = pfc; unsigned short* qfb = pfc + cap;   // corner / surf prefixes along `ord`
   {
-    int t1 = 0, t2 = 0;
-    for (int i0 = 0; i0 < m_all; i0 += SR_THREADS) {
-      const int i = i0 + tid;
+    const int nchm = (m_all + SR_THREADS - 1) / SR_THREADS;
+    unsigned int m = 0;
+    fs.begin(s_wt, fs_buf);
+    for (int k = 0; k < nchm; k++) {
+      const int i = k * SR_THREADS + tid;
       const bool in = i < m_all;
       const int c = in ? ord[i] : 0;
       const int l = in ? lab[c] : L_MESSY;
       const int rj = in ? region_of(c) : -1;
       const bool is_corner = in && l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN;
       const bool is_surf = in && (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT);
-      int a12;
-      const int p12 = block_scan_excl((is_corner ? 1 : 0) | (is_surf ? 0x10000 : 0), s_scan, &a12, scan_phase);
-      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16, a1 = a12 & 0xFFFF, a2 = a12 >> 16;
-      if (in) { qfa[i] = (unsigned short)(t1 + p1); qfb[i] = (unsigned short)(t2 + p2); }
-      if (in && i == nf_begin[rj]) { start3[0][rj] = t1 + p1; start3[1][rj] = t2 + p2; }
+      m |= ((is_corner ? 1u : 0u) | (is_surf ? 0x10000u : 0u)) << k;
+      fs.vote(k, is_corner, is_surf);
       if (is_corner) atomicAdd(&cnt3[1][rj], 1);
       if (is_surf) atomicAdd(&cnt3[3][rj], 1);
-      t1 += a1; t2 += a2;
+    }
+    __syncthreads();
+    for (int k = 0; k < nchm; k++) {
+      const int i = k * SR_THREADS + tid;
+      const bool in = i < m_all;
+      const int p12 = fs.pos(k, (m >> k) & 1u, (m >> (16 + k)) & 1u);
+      const int p1 = p12 & 0xFFFF, p2 = p12 >> 16;
+      if (in) {
+        qfa[i] = (unsigned short)p1; qfb[i] = (unsigned short)p2;
+        const int rj = region_of(ord[i]);
+        if (i == nf_begin[rj]) { start3[0][rj] = p1; start3[1][rj] = p2; }
+      }
     }
   }
   __syncthreads();
@@ -525,7 +718,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   if (tid < NR) {
     const int j = tid;
     int nflat = 0;
-    if (reg_ep[j] >= reg_sp[j]) {
+    if (reg_ep[j] >= 0) {
       int seen = 0;
       for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
         const int l = lab[ord[i]];
@@ -572,7 +765,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     const int j = tid;
     int o = base[2][j];
     for (int i = p1_begin[j]; i < p1_begin[j + 1]; i++) lst[2][o++] = p1buf[i];
-    if (reg_ep[j] >= reg_sp[j]) {
+    if (reg_ep[j] >= 0) {
       int seen = 0;
       for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
         const int c = ord[i];
@@ -597,11 +790,12 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   }
   const int nlf = s_cnt[3];
   if (o_idx[3]) for (int i = tid; i < nlf; i += SR_THREADS) o_idx[3][i] = S0 + lst[3][i];
-  for (int i = tid; i < n; i += SR_THREADS) {
-    if (a.picked) a.picked[cbase + i] = state[i];
-    if (a.curvature) a.curvature[cbase + i] = curv[i];
-    if (a.label) a.label[cbase + i] = lab[i];
-  }
+  if (a.picked || a.curvature || a.label)
+    for (int i = tid; i < n; i += SR_THREADS) {
+      if (a.picked) a.picked[cbase + i] = state[i];
+      if (a.curvature) a.curvature[cbase + i] = curv[i];
+      if (a.label) a.label[cbase + i] = lab[i];
+    }
 
   // ---- per-ring voxel filter of the less-flat points (ScanRegistration.cpp:390-399; cm_voxel.cu semantics) -------
   // reuse px..: the member points are addressed through lst[3]; intensity of a member = ring + relTime
@@ -613,7 +807,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     mx[0] = fmaxf(mx[0], px[c]); mx[1] = fmaxf(mx[1], py[c]); mx[2] = fmaxf(mx[2], pz[c]);
   }
   {
-    float* fs = reinterpret_cast<float*>(key);   // 6 * 16 floats of scratch
+    float* fs_ = reinterpret_cast<float*>(key);   // 6 * 16 floats of scratch
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -622,13 +816,13 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
         mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
       }
     __syncthreads();
-    if ((tid & 31) == 0) for (int k = 0; k < 3; k++) { fs[(tid >> 5) * 6 + k] = mn[k]; fs[(tid >> 5) * 6 + 3 + k] = mx[k]; }
+    if ((tid & 31) == 0) for (int k = 0; k < 3; k++) { fs_[(tid >> 5) * 6 + k] = mn[k]; fs_[(tid >> 5) * 6 + 3 + k] = mx[k]; }
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < SR_THREADS / 32; w++)
-        for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], fs[w * 6 + k]); mx[k] = fmaxf(mx[k], fs[w * 6 + 3 + k]); }
+        for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], fs_[w * 6 + k]); mx[k] = fmaxf(mx[k], fs_[w * 6 + 3 + k]); }
       const float inv = 1.0f / prm.less_flat_leaf;
-      vb_i[6] = 0;
+      vb_i[6] = 0; vb_i[7] = 32;
       if (nlf > 0) {
         long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
                   dz = (long long)((mx[2] - mn[2]) * inv) + 1;
@@ -637,6 +831,10 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
         for (int k = 0; k < 3; k++) { minb[k] = (int)floorf(mn[k] * inv); maxb[k] = (int)floorf(mx[k] * inv); vb_i[k] = minb[k]; }
         int d0 = maxb[0] - minb[0] + 1, d1 = maxb[1] - minb[1] + 1;
         vb_i[3] = d0; vb_i[4] = d0 * d1;
+        // bits of the largest voxel index (passthrough: of the largest list position)
+        const long long cells = vb_i[6] ? (long long)nlf : (long long)d0 * d1 * (maxb[2] - minb[2] + 1);
+        int b = 1; while (b < 32 && (1LL << b) < cells) b++;
+        vb_i[7] = (cells > 0 && cells <= 0x7fffffffLL) ? b : 32;
       }
     }
     __syncthreads();
@@ -664,63 +862,97 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       vidx[i] = idx;
     }
     __syncthreads();
-    int nruns = 0;
-    for (int i0 = 0; i0 < nlf; i0 += SR_THREADS) {
-      const int i = i0 + tid;
-      const bool rs = i < nlf && (i == 0 || vidx[i] != vidx[i - 1]);
-      int tot;
-      const int pos = block_scan_excl(rs ? 1 : 0, s_scan, &tot, scan_phase);
-      if (rs) run_start[nruns + pos] = (unsigned short)i;
-      nruns += tot;
+    const int nchl = (nlf + SR_THREADS - 1) / SR_THREADS;
+    int nruns;
+    {
+      unsigned int m = 0;
+      fs.begin(s_wt, fs_buf);
+      for (int k = 0; k < nchl; k++) {
+        const int i = k * SR_THREADS + tid;
+        const bool rs = i < nlf && (i == 0 || vidx[i] != vidx[i - 1]);
+        m |= (rs ? 1u : 0u) << k;
+        fs.vote(k, rs);
+      }
+      __syncthreads();
+      for (int k = 0; k < nchl; k++) {
+        const int i = k * SR_THREADS + tid;
+        const bool rs = (m >> k) & 1u;
+        const int pos = fs.pos(k, rs) & 0xFFFF;
+        if (rs) run_start[pos] = (unsigned short)i;
+      }
+      nruns = fs.run & 0xFFFF;
     }
     __syncthreads();
-    int P = 1; while (P < nruns) P <<= 1;
+    const int P = pow2_ge(nruns);
+    // 32-bit sort keys (voxel << posbits | start) whenever the voxel index and the list position fit together
+    const int posbits = 32 - __clz(nlf > 1 ? nlf - 1 : 1);
+    const bool narrow = vb_i[7] + posbits <= 31;   // a real key never has bit 31 set, so it cannot equal the padding key
+    unsigned int* key32 = reinterpret_cast<unsigned int*>(key) + P;   // upper half of key[0..P): expanded to 64 bits afterwards
     for (int r = tid; r < P; r += SR_THREADS) {
       unsigned long long k = 0xFFFFFFFFFFFFFFFFull;
+      unsigned int k32 = 0xFFFFFFFFu;
       if (r < nruns) {
         const int st = run_start[r];
         run_end[st] = (unsigned short)(r + 1 < nruns ? run_start[r + 1] : nlf);
         k = ((unsigned long long)vidx[st] << 32) | (unsigned int)st;
+        k32 = (vidx[st] << posbits) | (unsigned int)st;
       }
-      key[r] = k;
+      if (narrow) key32[r] = k32; else key[r] = k;
     }
     __syncthreads();
-    // bitonic sort of key[0..P)
-    for (int kk = 2; kk <= P; kk <<= 1)
-      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-        for (int pr = tid; pr < (P >> 1); pr += SR_THREADS) {   // one compare-exchange per pair: every lane works
-          const int i = ((pr & ~(jj - 1)) << 1) | (pr & (jj - 1)), ixj = i | jj;
-          const unsigned long long x = key[i], y = key[ixj];
-          const bool up = (i & kk) == 0;
-          if ((x > y) == up) { key[i] = y; key[ixj] = x; }
-        }
-        __syncthreads();
+    if (narrow) {
+      bitonic_sort<unsigned int>(key32, P);
+      // expand in place: every thread reads its keys, barrier, writes the 64-bit form the rest of the filter uses
+      unsigned int mine[SR_MAXCH];
+      const unsigned int posmask = (1u << posbits) - 1u;
+#pragma unroll
+      for (int q = 0; q < SR_MAXCH; q++) { const int r = q * SR_THREADS + tid; mine[q] = r < P ? key32[r] : 0xFFFFFFFFu; }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < SR_MAXCH; q++) {
+        const int r = q * SR_THREADS + tid;
+        if (r < P) key[r] = mine[q] == 0xFFFFFFFFu ? 0xFFFFFFFFFFFFFFFFull : (((unsigned long long)(mine[q] >> posbits) << 32) | (mine[q] & posmask));
       }
-    // voxel heads among the sorted runs -> output rank -> centroid (runs in order, entries of a run in order)
-    int base = 0;
-    for (int r0 = 0; r0 < nruns; r0 += SR_THREADS) {
-      const int r = r0 + tid;
-      const bool head = r < nruns && (r == 0 || (key[r] >> 32) != (key[r - 1] >> 32));
-      int tot;
-      const int pos = block_scan_excl(head ? 1 : 0, s_scan, &tot, scan_phase);
-      if (head) {
-        const unsigned int v = (unsigned int)(key[r] >> 32);
-        float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
-        int cntp = 0;
-        for (int rr = r; rr < nruns && (unsigned int)(key[rr] >> 32) == v; rr++) {
-          const int st = (int)(key[rr] & 0xFFFFFFFFu), en = run_end[st];
-          for (int j = st; j < en; j++) {
-            const int c = lst[3][j];
-            cx += px[c]; cy += py[c]; cz += pz[c]; ci += pin[c];
-          }
-          cntp += en - st;
-        }
-        const float cnt = (float)cntp;
-        o_pts[3][base + pos] = make_float4(cx / cnt, cy / cnt, cz / cnt, ci / cnt);
-      }
-      base += tot;
+      __syncthreads();
+    } else {
+      bitonic_sort<unsigned long long>(key, P);
     }
-    if (tid == 0) { ring_n[0] = s_cnt[0]; ring_n[1] = s_cnt[1]; ring_n[2] = s_cnt[2]; ring_n[3] = base; ring_n[4] = nlf; }
+    // voxel heads among the sorted runs -> output rank -> centroid (runs in order, entries of a run in order)
+    const int nchr = (nruns + SR_THREADS - 1) / SR_THREADS;
+    int nvox;
+    {
+      unsigned int m = 0;
+      fs.begin(s_wt, fs_buf);
+      for (int k = 0; k < nchr; k++) {
+        const int r = k * SR_THREADS + tid;
+        const bool head = r < nruns && (r == 0 || (key[r] >> 32) != (key[r - 1] >> 32));
+        m |= (head ? 1u : 0u) << k;
+        fs.vote(k, head);
+      }
+      __syncthreads();
+      for (int k = 0; k < nchr; k++) {
+        const int r = k * SR_THREADS + tid;
+        const bool head = (m >> k) & 1u;
+        const int pos = fs.pos(k, head) & 0xFFFF;
+        if (head) {
+          const unsigned int v = (unsigned int)(key[r] >> 32);
+          float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
+          int cntp = 0;
+          for (int rr = r; rr < nruns && (unsigned int)(key[rr] >> 32) == v; rr++) {
+            const int st = (int)(key[rr] & 0xFFFFFFFFu), en = run_end[st];
+            for (int j = st; j < en; j++) {
+              const int c = lst[3][j];
+              cx += px[c]; cy += py[c]; cz += pz[c]; ci += pin[c];
+            }
+            cntp += en - st;
+          }
+          const float cnt = (float)cntp;
+          o_pts[3][pos] = make_float4(cx / cnt, cy / cnt, cz / cnt, ci / cnt);
+        }
+      }
+      nvox = fs.run & 0xFFFF;
+    }
+    if (tid == 0) { ring_n[0] = s_cnt[0]; ring_n[1] = s_cnt[1]; ring_n[2] = s_cnt[2]; ring_n[3] = nvox; ring_n[4] = nlf; }
   }
 }
 
@@ -773,10 +1005,10 @@ __global__ void __launch_bounds__(256) sr_assemble_kernel(AssembleArgs a) {
 // host side
 // ------------------------------------------------------------------------------------------------------------
 size_t scanreg_smem_bytes(int cols) {
-  int cap = (cols + 3) & ~3;
+  int cap = (cols + 7) & ~7;
   int P2 = 1; while (P2 < cols) P2 <<= 1;
   int keyn = (8 * P2 >= 10 * cap) ? P2 : (10 * cap + 7) / 8;
-  return (size_t)cap * 4 * 5 + (size_t)keyn * 8 + (size_t)cap * 2 * 7 + (size_t)cap * 4;
+  return (size_t)cap * 4 * 5 + (size_t)cap * 2 + (size_t)cap * 4 + (size_t)keyn * 8 + (size_t)cap * 2 * 6;
 }
 
 void ScanRegistrationGpu::run(const ScanRegLaunch& L, cudaStream_t stream) {
@@ -793,9 +1025,12 @@ void ScanRegistrationGpu::run(const ScanRegLaunch& L, cudaStream_t stream) {
   p.less_flat_leaf = L.less_flat_leaf; p.R = L.R; p.nregions = L.nregions; p.max_sharp = L.max_sharp; p.max_flat = L.max_flat;
   p.cos175 = L.cos175; p.cos5 = L.cos5; p.cos135 = L.cos135; p.cos45 = L.cos45;
   dim3 grid(rows, S);
-  CM_LAUNCH(sr_count_kernel, grid, 256, 0, stream, L.frames, rows, cols, p.blind_sq, (int*)ring_count.p);
+  // ring offsets inside the concatenated cloud are only needed by outputs that carry absolute cloud indices (diagnostics / parity):
+  // the feature clouds themselves do not depend on them, so the pipeline skips this pass over the sweep
+  const bool want_abs = L.want_idx || L.cloud || L.picked || L.curvature || L.label || L.scan_range;
+  if (want_abs) CM_LAUNCH(sr_count_kernel, grid, 256, 0, stream, L.frames, rows, cols, p.blind_sq, (int*)ring_count.p);
   ScanRegArgs a;
-  a.frames = L.frames; a.tags = L.tags; a.rows = rows; a.cols = cols; a.ring_count = (const int*)ring_count.p; a.prm = p;
+  a.frames = L.frames; a.tags = L.tags; a.rows = rows; a.cols = cols; a.ring_count = want_abs ? (const int*)ring_count.p : nullptr; a.prm = p;
   for (int l = 0; l < 4; l++) { a.ring_pts[l] = (float4*)ring_pts[l].p; a.ring_idx[l] = L.want_idx ? (int*)ring_idx[l].p : nullptr; }
   a.ring_n = (int*)ring_n.p;
   a.cloud = L.cloud; a.cloud_curv = L.cloud_curv; a.picked = L.picked; a.curvature = L.curvature; a.label = L.label;
