@@ -104,10 +104,16 @@ __device__ __forceinline__ void top5_insert_key(Top5& t, unsigned long long key,
   t.key[1] = c0 ? t.key[0] : (c1 ? key : t.key[1]);  t.slot[1] = c0 ? t.slot[0] : (c1 ? slot : t.slot[1]);
   t.key[0] = c0 ? key : t.key[0];                    t.slot[0] = c0 ? slot : t.slot[0];
 }
-// d must not be NaN (a NaN never enters the reference's result set either: nanoflann compares dist < worst)
+// A NaN or infinite distance never enters the list (nor the reference's result set: nanoflann compares dist < worst with worst =
+// FLT_MAX): the bit patterns of NaN and +inf are larger than FLT_MAX's, the empty key, and d is a sum of squares, never negative.
 __device__ __forceinline__ void top5_insert(Top5& t, float d, int idx, int slot) {
-  if (d != d) return;
   top5_insert_key(t, top5_key(d, idx), slot);
+}
+// the same for a list that may already hold the candidate (warm start from the previous iteration's neighbours)
+__device__ __forceinline__ void top5_insert_key_unique(Top5& t, unsigned long long key, int slot) {
+  if (!(key < t.key[4])) return;
+  if (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3]) return;
+  top5_insert_key(t, key, slot);
 }
 
 // worldToCube (FeatureMap.h:475-487) -> index into the 7x7x7 window, -1 outside it
@@ -254,15 +260,40 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
 // skipped when that bound already exceeds the current 5th distance (every point of the cell is then strictly
 // farther than five known points) -- on a 0.4 m map this drops about half of the candidate loads.
 // rng: shared memory, 8 * blockDim.x uint4 (this thread uses rng[c * blockDim.x + threadIdx.x]).
+// Warm start: prev (optional) = the pool slots of the query's 5 neighbours in the PREVIOUS Gauss-Newton iteration.  The pose moves
+// by centimetres between iterations, so those five real map points give the list a near-final 5th distance before the first
+// cell is opened: most cells are pruned by their lower bound and almost no candidate passes the insert test, which is where
+// the search spent a third of its instructions at 5 of 32 lanes (the divergent sorted insert).  Any five valid points are a
+// correct start: the result is the exact top-5 of (cells scanned) U (start points), the same set either way.
 template <bool kOrigIdx>
 __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c, float qx, float qy, float qz, uint4* rng, Top5& best,
-                                            unsigned int* ncand = nullptr) {
+                                            unsigned int* ncand = nullptr, const int* prev = nullptr) {
   const int k = g.kdiv;
   const float kf = (float)k;
   const float leaf98 = 0.98f * (g.cell / kf);
   int nr = 0;
   uint4* my = rng + threadIdx.x;
   const int stride = blockDim.x;
+  bool warm = false;
+  if (prev) {
+    int sl[5];
+#pragma unroll
+    for (int u = 0; u < 5; u++) sl[u] = prev[u];
+    if (sl[0] >= 0) {
+      float4 q[5];
+#pragma unroll
+      for (int u = 0; u < 5; u++) q[u] = __ldg(g.pts + sl[u]);
+#pragma unroll
+      for (int u = 0; u < 5; u++) {
+        if (cand_ok(g, c.filt, q[u])) {
+          float dx = qx - q[u].x, dy = qy - q[u].y, dz = qz - q[u].z;
+          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          top5_insert_key_unique(best, top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]), sl[u]);
+        }
+      }
+      warm = true;
+    }
+  }
 #pragma unroll
   for (int b = 0; b < 2; b++) {
     unsigned long long key[4]; uint4 e[4];
@@ -304,16 +335,28 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
 #pragma unroll
     for (int u = 0; u < CM_KNN_UNROLL; u++)
       if ((unsigned int)u < left) p[u] = __ldg(g.pts + r.x + j0 + u);
+    // keys of the batch, then ONE divergent region that inserts the (few) candidates below the current 5th distance, lowest
+    // position first: the warp iterates max-over-lanes of the number of passing candidates instead of once per position
+    unsigned long long kk[CM_KNN_UNROLL];
+    unsigned int pass = 0;
 #pragma unroll
     for (int u = 0; u < CM_KNN_UNROLL; u++) {
-      if ((unsigned int)u < left) {
-        if (cand_ok(g, c.filt, p[u])) {
-          float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
-          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          const int j = (int)(r.x + j0 + u);
-          top5_insert(best, d, kOrigIdx ? __float_as_int(p[u].w) : j, j);
-        }
+      kk[u] = CM_TOP5_EMPTY;
+      if ((unsigned int)u < left && cand_ok(g, c.filt, p[u])) {
+        float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
+        float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        kk[u] = top5_key(d, kOrigIdx ? __float_as_int(p[u].w) : (int)(r.x + j0 + u));
+        pass |= (kk[u] < best.key[4] ? 1u : 0u) << u;
       }
+    }
+    while (pass) {
+      const int u = __ffs(pass) - 1;
+      pass &= pass - 1;
+      unsigned long long kq = kk[0];
+#pragma unroll
+      for (int v = 1; v < CM_KNN_UNROLL; v++) kq = (u == v) ? kk[v] : kq;
+      if (warm) top5_insert_key_unique(best, kq, (int)(r.x + j0 + u));
+      else top5_insert_key(best, kq, (int)(r.x + j0 + u));
     }
     if (ncand) scanned += left < (unsigned int)CM_KNN_UNROLL ? left : (unsigned int)CM_KNN_UNROLL;
     j0 += CM_KNN_UNROLL;

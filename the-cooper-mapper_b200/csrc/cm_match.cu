@@ -10,6 +10,7 @@
 #include <vector>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cm {
 
@@ -97,6 +98,8 @@ struct CorrArgs {
   const float* own_box;                       // optional {lo[3], hi[3]}: only queries whose map-frame position is inside are evaluated (sharded map)
   unsigned long long* dbg;                    // optional per-warp trace of search_kernel (development aid, cm_debug_search_trace)
   const int* iter_dev;                        // optional: the evaluation index lives in device memory (graph WHILE loop); hard_count is then the row base
+  int iter;                                   // the evaluation index when iter_dev is NULL
+  int warm;                                   // 1: warm-start the 5-NN lists from the previous iteration (COOPERMAP_NO_WARM=1: off)
   void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
   MatchParamsDev prm;
 };
@@ -265,7 +268,10 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
   bool need = false;
   unsigned int ncand = 0;
-  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr);
+  // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
+  const int it = a.iter_dev ? *a.iter_dev : a.iter;
+  const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
+  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
   const unsigned int FULL = 0xffffffffu;
   unsigned int hard = __ballot_sync(FULL, need);
   if (a.dbg) {
@@ -729,6 +735,8 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
   ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
   ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr; ca.iter_dev = nullptr; sa.iter_dev = nullptr;
+  static const int warm = getenv("COOPERMAP_NO_WARM") ? 0 : 1;
+  ca.iter = 0; ca.warm = warm;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
@@ -748,6 +756,7 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (bx < 1) bx = 1;
   dim3 grid(bx, m.nstreams);
   ca.nn = m.nn ? m.nn + (size_t)it * m.nstreams * capQ * 5 : nullptr;
+  ca.iter = it;
   if (prof) prof->begin(stream);
   if (m.dbg && it == m.dbg_iter) { ca.dbg = m.dbg; cudaMemsetAsync(m.dbg, 0, (size_t)bx * m.nstreams * 8 * 4 * sizeof(unsigned long long), stream);   /* bx * 8 warps per stream */ }
   if (it >= CM_MAX_EVALS) ca.hard = nullptr;       // no counter left: finish hard queries inside their own warp
