@@ -32,6 +32,9 @@ ROWS, COLS = 64, 2048
 NPTS = ROWS * COLS
 SEED = 0x5EED0002
 CFG = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+for _k in ("cell_surf", "cell_corner"):                  # development sweeps of the search-cell size (results do not depend on it)
+    if os.environ.get("BENCH_" + _k.upper()):
+        CFG[_k] = float(os.environ["BENCH_" + _k.upper()])
 ORACLE_MAP = dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)
 MAP_SPACING = 0.3          # sampling lattice of the prebuilt map: 1.8 M samples -> 1.02 M resident points at the 0.4 m map leaf
 METRIC = "lidar_points_registered_per_s"

@@ -325,6 +325,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
   unsigned int scanned = 0;
   int ci = 0; unsigned int j0 = 0;
   uint4 r = nr ? my[0] : make_uint4(0u, 0u, 0u, 0u);
+  const bool nofilt = c.filt == CM_FILT_NONE;
   while (ci < nr) {
     if (j0 == 0 && __uint_as_float(r.z) > best.d(4)) {   // the whole cell is farther than the current 5th neighbour
       ci++; if (ci < nr) r = my[ci * stride];
@@ -339,14 +340,15 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
     // position first: the warp iterates max-over-lanes of the number of passing candidates instead of once per position
     unsigned long long kk[CM_KNN_UNROLL];
     unsigned int pass = 0;
+    const float d5 = best.d(4);   // candidates at or below the 5th distance go to the exact (d2, index) test of the insert
 #pragma unroll
     for (int u = 0; u < CM_KNN_UNROLL; u++) {
       kk[u] = CM_TOP5_EMPTY;
-      if ((unsigned int)u < left && cand_ok(g, c.filt, p[u])) {
+      if ((unsigned int)u < left && (nofilt || cand_ok(g, c.filt, p[u]))) {
         float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
         float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         kk[u] = top5_key(d, kOrigIdx ? __float_as_int(p[u].w) : (int)(r.x + j0 + u));
-        pass |= (kk[u] < best.key[4] ? 1u : 0u) << u;
+        pass |= (d <= d5 ? 1u : 0u) << u;
       }
     }
     while (pass) {
@@ -431,7 +433,8 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
       const unsigned int mini = __reduce_min_sync(FULL, cand);
       const int src = __ffs(__ballot_sync(FULL, dbits == mind && ibits == mini)) - 1;
       const int wslot = __shfl_sync(FULL, loc.slot[0], src);
-      if (lane == h) top5_insert_key(best, ((unsigned long long)mind << 32) | mini, wslot);
+      // unique: a list that was warm-started from the previous iteration's neighbours may already hold points of this shell
+      if (lane == h) top5_insert_key_unique(best, ((unsigned long long)mind << 32) | mini, wslot);
       if (lane == src) {
 #pragma unroll
         for (int u = 0; u < 4; u++) { loc.key[u] = loc.key[u + 1]; loc.slot[u] = loc.slot[u + 1]; }
