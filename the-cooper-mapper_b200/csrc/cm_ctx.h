@@ -38,7 +38,7 @@ struct cm_ctx {
   cm::DeviceBuffer d_ref_corner, d_ref_surf, d_corner, d_surf, d_q, d_idx, d_d2;
   cm::DeviceBuffer d_counts, d_views, d_pose, d_state, d_rows, d_slots, d_sums, d_trace, d_nn;
   cm::GridStorage grid_a, grid_b;
-  cm::VoxelFilter voxel, voxel_aux;
+  cm::VoxelFilter voxel;
   // aux_stream: the corner-class half of the mapping stage's voxel filters and map insertion runs here, concurrently with the
   // surf-class half on `stream` (both are chains of small latency-bound kernels; the corner chain hides behind the surf chain)
   cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
@@ -84,14 +84,14 @@ struct cm_ctx {
   // step's sweeps are uploaded (host variant) and run through scan registration on side_stream while the current step's
   // matching and map kernels run on `stream`.  Scan registration is issue-bound, matching is latency-bound: the two overlap.
   struct PipeSlot {
-    cm::DeviceBuffer frames, pts[4], n, box;   // box: [2][S] VoxBox of the less-sharp / less-flat clouds (frame voxel filters)
+    cm::DeviceBuffer frames, pts[4], n;
     cm::ScanRegistrationGpu scanreg;
     const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
     cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, copied_x[2] = {nullptr, nullptr};
     size_t frames_valid = 0;
-    // feature counts and bounding boxes read back by the prefetch itself (side stream -> pinned host memory): the step that
+    // feature counts read back by the prefetch itself (side stream -> pinned host memory): the step that
     // consumes the slot starts without a host round trip
-    int* h_n5 = nullptr; cm::VoxBox* h_box = nullptr; int h_streams = 0; bool counts_ready = false;
+    int* h_n5 = nullptr; int h_streams = 0; bool counts_ready = false;
   };
 #define CM_PIPE_SLOTS 4            // prefetch slots (one being consumed + three pending); pipe[CM_PIPE_SLOTS] is the synchronous path
   PipeSlot pipe[CM_PIPE_SLOTS + 1];

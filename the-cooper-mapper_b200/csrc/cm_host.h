@@ -233,15 +233,16 @@ struct VoxBox {          // per segment: PCL's min_b_ / divb_mul_ of the cloud's
   int nfinite;
   long long cells;       // dx * dy * dz: the voxel index of the segment is < cells
 };
-void launch_vox_bbox(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, VoxBox* d_box, cudaStream_t stream);
 int vox_index_bits(long long cells);
 struct VoxelFilter {
-  DeviceBuffer box, keys_a, keys_b, vals_a, vals_b, flags, rank, seg_first, temp;
-  // max_n: host-known upper bound of n_in[s] (<= 0: cap_in).  d_box_ready + idx_bits: bounding boxes computed earlier by
-  // launch_vox_bbox and the number of bits their largest index space needs (read back by the caller) -- the radix sort then
-  // runs over segment + idx_bits bits instead of segment + 32 (one 8-bit pass less for a LiDAR frame at 0.8 m).
+  DeviceBuffer scratch;
+  // max_n: host-known upper bound of n_in[s] (<= 0: cap_in); it only sizes the scratch, the counts themselves stay on the device
   void run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, int max_n, float leaf, float4* d_out, int* d_n_out, int cap_out,
-           int* d_overflow, cudaStream_t stream, const VoxBox* d_box_ready = nullptr, int idx_bits = 32);
+           int* d_overflow, cudaStream_t stream);
+  // two batches with different leaves (the corner and the surf clouds of every stream) in ONE launch
+  void run2(int nseg, const float4* d_in0, const int* d_n_in0, int cap_in0, float leaf0, float4* d_out0, int* d_n_out0, int cap_out0,
+            const float4* d_in1, const int* d_n_in1, int cap_in1, float leaf1, float4* d_out1, int* d_n_out1, int cap_out1,
+            int max_n, int* d_overflow, cudaStream_t stream);
 };
 
 // Small parameter uploads without the copy engine: `pinned` is device-accessible pinned host memory, a kernel reads it over

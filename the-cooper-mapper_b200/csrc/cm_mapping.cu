@@ -166,7 +166,7 @@ static void issue_deferred_prefetch(cm_ctx* ctx) {
 // 10 iterations, 0.05 deg / 0.05 cm) and the map is not updated.
 static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, const float4* d_surf, int cap_s, const int* d_n,
                                int max_in_c, int max_in_s, const cm_iso* h_odom, cm_iso* h_mapped, cm_match_stats* h_stats,
-                               bool localise = false, const VoxBox* d_box = nullptr, int bits_c = 32, int bits_s = 32) {
+                               bool localise = false) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   cudaStream_t st = ctx->stream;
@@ -220,31 +220,10 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   const bool use_graphs = !no_graph && !g_timeline.on;
   auto P = [](const void* p) { return (unsigned long long)(uintptr_t)p; };
   auto FB = [](float v) { unsigned int u; memcpy(&u, &v, 4); return (unsigned long long)u; };
-  const int mc_r = std::min(cap_c, (std::max(max_in_c, 1) + 255) & ~255), ms_r = std::min(cap_s, (std::max(max_in_s, 1) + 1023) & ~1023);
-  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
-  CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
-  {
-    auto issue_c = [&]() {
-      ctx->voxel_aux.run(S, d_corner, d_n, cap_c, mc_r, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c, (int*)ctx->d_flag.p, aux,
-                         d_box, bits_c);
-    };
-    auto issue_s = [&]() {
-      ctx->voxel.run(S, d_surf, d_n + S, cap_s, ms_r, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, (int*)ctx->d_flag.p, st,
-                     d_box ? d_box + S : nullptr, bits_s);
-    };
-    if (use_graphs) {
-      ctx->stage_graphs.run({1, (unsigned long long)S, P(d_corner), P(d_n), (unsigned long long)cap_c, (unsigned long long)mc_r, FB(cfg.filter_corner),
-                             P(ctx->m_corner_ds.p), P(d_nds), P(ctx->d_flag.p), P(d_box), (unsigned long long)bits_c, P(aux)}, aux, issue_c);
-      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
-      ctx->stage_graphs.run({2, (unsigned long long)S, P(d_surf), P(d_n), (unsigned long long)cap_s, (unsigned long long)ms_r, FB(cfg.filter_surf),
-                             P(ctx->m_surf_ds.p), P(d_nds), P(ctx->d_flag.p), P(d_box), (unsigned long long)bits_s, P(st)}, st, issue_s);
-    } else {
-      issue_c();
-      CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
-      issue_s();
-    }
-  }
-  CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
+  // both classes of every stream in one launch (one CTA per cloud); the counts never leave the device
+  ctx->voxel.run2(S, d_corner, d_n, cap_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c,
+                  d_surf, d_n + S, cap_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s,
+                  std::max(max_in_c, max_in_s), (int*)ctx->d_flag.p, st);
   // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
   std::vector<int> nds(2 * S);
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
@@ -546,42 +525,34 @@ static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* 
   L.out_n = (int*)slot.n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
   slot.scanreg.run(L, st);
   CM_LAUNCH(gather_counts_kernel, (S + 63) / 64, 64, 0, st, (const int*)slot.n.p + 2 * S, (int*)slot.n.p, S);
-  // bounding boxes of the two clouds the mapping stage voxel-filters: the host reads them back with the counts and sizes
-  // the radix sort keys by the index space they span
-  slot.box.reserve(sizeof(VoxBox) * 2 * S);
-  launch_vox_bbox(S, (const float4*)slot.pts[1].p, (const int*)slot.n.p, cap, cfg.filter_corner, (VoxBox*)slot.box.p, st);
-  launch_vox_bbox(S, (const float4*)slot.pts[3].p, (const int*)slot.n.p + S, cap, cfg.filter_surf, (VoxBox*)slot.box.p + S, st);
 }
 
 static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int cols, const cm_iso* odom, cm_iso* mapped, cm_match_stats* stats) {
   const int S = ctx->map_streams;
   const int cap = rows * cols;
   cudaStream_t st = ctx->stream;
-  // feature-cloud sizes: needed on the host to size the frame voxel filters (and for the byte accounting)
-  std::vector<int> n5v; std::vector<VoxBox> boxv;
-  const int* n5; const VoxBox* boxes;
+  // feature-cloud sizes: upper bounds for the scratch of the frame voxel filters (and the byte accounting)
+  std::vector<int> n5v;
+  const int* n5;
   if (slot.counts_ready) {
     // read back by the prefetch on the side stream: normally complete long before the step starts
     CM_CUDA_CHECK(ctx, cudaEventSynchronize(slot.done));
-    n5 = slot.h_n5; boxes = slot.h_box;
+    n5 = slot.h_n5;
     slot.counts_ready = false;
   } else {
-    n5v.resize(5 * S); boxv.resize(2 * S);
+    n5v.resize(5 * S);
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5v.data(), (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, st));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(boxv.data(), slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    n5 = n5v.data(); boxes = boxv.data();
+    n5 = n5v.data();
   }
   int max_c = 1, max_s = 1;
-  long long cells_c = 1, cells_s = 1;
   ctx->last_features = 0;
   for (int s = 0; s < S; s++) {
     max_c = std::max(max_c, n5[s * 5 + 1]); max_s = std::max(max_s, n5[s * 5 + 3]);
-    cells_c = std::max(cells_c, boxes[s].cells); cells_s = std::max(cells_s, boxes[S + s].cells);
     for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)n5[s * 5 + k];
   }
   return mapping_process_dev(ctx, (const float4*)slot.pts[1].p, cap, (const float4*)slot.pts[3].p, cap, (const int*)slot.n.p, max_c,
-                             max_s, odom, mapped, stats, false, (const VoxBox*)slot.box.p, vox_index_bits(cells_c), vox_index_bits(cells_s));
+                             max_s, odom, mapped, stats, false);
 }
 
 static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
@@ -635,14 +606,11 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
       const int S = ctx->map_streams;
       if (slot.h_streams < S) {
         if (slot.h_n5) cudaFreeHost(slot.h_n5);
-        if (slot.h_box) cudaFreeHost(slot.h_box);
-        slot.h_n5 = nullptr; slot.h_box = nullptr; slot.h_streams = 0;
+        slot.h_n5 = nullptr; slot.h_streams = 0;
         CM_CUDA_CHECK(ctx, cudaHostAlloc((void**)&slot.h_n5, sizeof(int) * 5 * S, cudaHostAllocDefault));
-        CM_CUDA_CHECK(ctx, cudaHostAlloc((void**)&slot.h_box, sizeof(VoxBox) * 2 * S, cudaHostAllocDefault));
         slot.h_streams = S;
       }
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.h_n5, (const int*)slot.n.p + 2 * S, sizeof(int) * 5 * S, cudaMemcpyDeviceToHost, ctx->side_stream));
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.h_box, slot.box.p, sizeof(VoxBox) * 2 * S, cudaMemcpyDeviceToHost, ctx->side_stream));
       slot.counts_ready = true;
     }
     CM_CUDA_CHECK(ctx, cudaEventRecord(slot.done, ctx->side_stream));

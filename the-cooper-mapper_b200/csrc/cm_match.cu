@@ -585,7 +585,7 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // go to global memory, and the LAST CTA of a stream to finish (ticket counter) adds the partials in CTA order and runs the
 // 6x6 step -- streams solve concurrently on different SMs instead of one after the other in a single warp, and two
 // launches per Gauss-Newton iteration disappear.  Determinism: every sum has a fixed order (row -> 32-row group -> CTA).
-struct FusedArgs { double* partials; int* tickets; double* sums; };
+struct FusedArgs { double* partials; int* tickets; double* sums; int solve_inline; };
 
 #ifndef CM_FIT_MINB
 #define CM_FIT_MINB 4
@@ -667,8 +667,15 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
   __syncthreads();
   if (threadIdx.x == 0) {
     f.tickets[s] = 0;
-    solve_stream(sa, s, stot);
+    // the 6x6 step: inline only on request -- inside this kernel it is capped at 64 registers and runs out of local memory
+    // (~45 us per iteration); solve_warp_kernel right behind this launch does it in 128 registers
+    if (f.solve_inline) solve_stream(sa, s, stot);
   }
+}
+
+// K6b for the fused path: one warp per stream (streams diverge: degenerate / first-iteration branches), lane 0 works
+__global__ void __launch_bounds__(32) solve_warp_kernel(SolveArgs a, const double* __restrict__ sums) {
+  if (threadIdx.x == 0) solve_stream(a, blockIdx.x, sums + (size_t)blockIdx.x * 32);
 }
 
 #include "cm_odom.inl"
@@ -730,6 +737,8 @@ void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d
   if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, gate, d_idx, d_d2);
 }
 
+static int solve_inline() { static const int v = getenv("COOPERMAP_SOLVE_INLINE") ? 1 : 0; return v; }   // development: the round-1 fused solve
+
 static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
@@ -772,8 +781,9 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (prof) prof->end(stream);
   sa.iter = it;
   if (fused) {
-    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums;
+    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline();
     CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
+    if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
     return;
   }
   CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
@@ -841,8 +851,9 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
   if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
   else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
-  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums;
+  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline();
   CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
+  if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
 }
 
 // init -> WHILE { search, hard search, fit + solve, advance }: as many evaluations as the slowest stream needs, one submission

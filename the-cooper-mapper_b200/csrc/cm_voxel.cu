@@ -1,6 +1,6 @@
-// cm_voxel.cu -- K3: batched voxel-grid downsampling with pcl::VoxelGrid<PointXYZI> semantics.
+// cm_voxel.cu -- K3: batched voxel-grid downsampling with pcl::VoxelGrid<PointXYZI> semantics, ONE launch.
 //
-// Replaces the pcl::VoxelGrid::filter calls at ScanRegistration.cpp:390-399 (per ring, leaf 0.2),
+// Replaces the pcl::VoxelGrid::filter calls at ScanRegistration.cpp:390-399 (per ring, leaf 0.2: done inside sr_ring_kernel),
 // LaserMatcher.cpp:293-300 (frame, filter_corner / filter_surf) and ScanMatch.cpp:381-394; indexing as stated
 // in-tree by util/voxel_grid_partition.hpp:91-272: bounding box -> min_b = floor(min * inv_leaf) -> ijk =
 // floor(p * inv_leaf) - min_b -> idx = i + j*dx + k*dx*dy -> sort by idx -> one centroid (all four fields) per
@@ -8,191 +8,302 @@
 // in INPUT order (stable sort; PCL's std::sort is unstable).  Non-finite points are skipped; when dx*dy*dz
 // overflows int32 the input is passed through unchanged, like PCL.
 //
-// Segments ("streams") are independent clouds laid out as in[s * cap_in .. s * cap_in + n_in[s]).  The sort is a
-// library primitive (cub::DeviceRadixSort, stable LSD) over 64-bit keys (segment << 32 | idx); everything else is
-// hand-written.
+// Segments ("streams") are independent clouds laid out as in[s * cap_in .. s * cap_in + n_in[s]).  One CTA of 1024
+// threads owns one segment from bounding box to centroids, so a whole batch (both feature classes of every stream) is
+// a single launch whose sizes live on the device only:
+//   1. bounding box (block reduction);
+//   2. voxel index per point, RUNS of consecutive points with equal index (a LiDAR feature cloud follows the scan: ~2.6
+//      points per run), ordered compaction of the runs by ballot prefix sums, digit histograms;
+//   3. stable LSD radix sort of the runs by voxel index, 8 bits per pass, only as many passes as the segment's index space
+//      needs (3 for a 240 m frame at 0.8 m): per tile of 1024 runs the rank of an item is (digit base) + (runs of the
+//      same digit in earlier warps, a 32 x 256 counter matrix in shared memory) + (earlier lanes of its warp,
+//      __match_any_sync); runs with equal index stay in input order, which is what makes the centroid sums reproducible;
+//   4. first run of every voxel -> output rank (ballot prefix sums) -> the head's thread adds up the voxel's runs in order.
+// (Round 1 used cub::DeviceRadixSort over all segments + six helper launches: 486 us per step at 64 HDL-64 streams.)
 #include "cm_host.h"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <float.h>
 
 namespace cm {
 
+#define VS_T 1024
+#define VS_WARPS (VS_T / 32)
+#define VS_PAD 0xFFFFFFFFu
 
-__global__ void __launch_bounds__(1024) vox_bbox_kernel(const float4* __restrict__ in, const int* __restrict__ n_in, int cap_in,
-                                                       float inv, VoxBox* __restrict__ box) {
-  const int s = blockIdx.x;
-  const int n = n_in[s];
-  const float4* p = in + (size_t)s * cap_in;
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  int nf = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float4 q = p[i];
-    if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
-      nf++;
-      mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
-      mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+struct VoxClass {            // one batch of segments filtered with one leaf
+  const float4* in; const int* n_in; int cap_in;
+  float inv;                 // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+  float4* out; int* n_out; int cap_out;
+  unsigned int* scratch;     // [nseg][6][stride]: key A / B, value A / B, run start, run end
+};
+struct VoxSegArgs {
+  VoxClass cls[2];
+  int nseg, ncls;
+  unsigned int stride;       // scratch entries per array and segment (>= the largest n_in)
+  int* overflow;             // optional flag: an output exceeded cap_out (or an input the scratch stride)
+  VoxBox* box_out;           // optional [ncls][nseg]: the bounding boxes (diagnostics)
+};
+
+// voxel_grid_partition.hpp:212-226
+__device__ __forceinline__ unsigned int vox_index_of(const float4& q, const VoxBox& b, float inv, unsigned int i) {
+  if (b.passthrough) return i;   // identity order
+  if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) return VS_PAD;
+  int ijk0 = (int)(floorf(q.x * inv) - (float)b.minb[0]);
+  int ijk1 = (int)(floorf(q.y * inv) - (float)b.minb[1]);
+  int ijk2 = (int)(floorf(q.z * inv) - (float)b.minb[2]);
+  return (unsigned int)(ijk0 + ijk1 * b.mul1 + ijk2 * b.mul2);
+}
+
+__global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
+  const int s = blockIdx.x, ci = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const VoxClass& k = a.cls[ci];
+  const float inv = k.inv;
+  const float4* in = k.in + (size_t)s * k.cap_in;
+  int n = k.n_in[s];
+  if (n < 0) n = 0;
+  if ((unsigned int)n > a.stride) { n = (int)a.stride; if (tid == 0 && a.overflow) atomicExch(a.overflow, 1); }
+  unsigned int* base = k.scratch + (size_t)s * 6 * a.stride;
+  unsigned int* keyb[2] = {base, base + a.stride};
+  unsigned int* valb[2] = {base + 2 * (size_t)a.stride, base + 3 * (size_t)a.stride};
+  unsigned int* run_start = base + 4 * (size_t)a.stride;
+  unsigned int* run_end = base + 5 * (size_t)a.stride;
+
+  __shared__ VoxBox s_box;
+  __shared__ float s_red[VS_WARPS][6];
+  __shared__ int s_redn[VS_WARPS];
+  __shared__ unsigned int s_idx[VS_T + 2];
+  __shared__ unsigned int s_carry;
+  __shared__ int s_wt[2][VS_WARPS];
+  __shared__ unsigned int s_hist[4][256];
+  __shared__ unsigned int s_digit[256];
+  __shared__ unsigned int s_wsum[8];
+  __shared__ unsigned int s_gsum[4][256];
+  __shared__ unsigned short s_wcnt[VS_WARPS][256];
+  const unsigned int lt = (1u << lane) - 1u;
+
+  // ---- 1. bounding box (voxel_grid_partition.hpp:108-137) ------------------------------------------------------------
+  {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int nf = 0;
+    for (int i = tid; i < n; i += VS_T) {
+      const float4 q = in[i];
+      if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+        nf++;
+        mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
+        mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+      }
+      nf += __shfl_xor_sync(0xffffffffu, nf, o);
+    }
+    if (lane == 0) { for (int c = 0; c < 3; c++) { s_red[warp][c] = mn[c]; s_red[warp][3 + c] = mx[c]; } s_redn[warp] = nf; }
+    for (int q = tid; q < 4 * 256; q += VS_T) (&s_hist[0][0])[q] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < VS_WARPS; w++) {
+        for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], s_red[w][c]); mx[c] = fmaxf(mx[c], s_red[w][3 + c]); }
+        nf += s_redn[w];
+      }
+      VoxBox b;
+      b.nfinite = nf; b.passthrough = 0; b.cells = 1;
+      b.minb[0] = b.minb[1] = b.minb[2] = 0; b.mul1 = b.mul2 = 0;
+      if (nf > 0) {
+        long long dx = (long long)((mx[0] - mn[0]) * inv) + 1;
+        long long dy = (long long)((mx[1] - mn[1]) * inv) + 1;
+        long long dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+        if (dx * dy * dz > 2147483647LL) b.passthrough = 1;
+        b.cells = b.passthrough ? (long long)n : dx * dy * dz;   // upper bound of the sort index (identity order when passing through)
+        int maxb[3];
+        for (int c = 0; c < 3; c++) { b.minb[c] = (int)floorf(mn[c] * inv); maxb[c] = (int)floorf(mx[c] * inv); }
+        int d0 = maxb[0] - b.minb[0] + 1, d1 = maxb[1] - b.minb[1] + 1;
+        b.mul1 = d0; b.mul2 = d0 * d1;
+        // the index space actually addressed (floor of the scaled extrema) can exceed the truncated estimate by a cell per axis
+        const long long span = (long long)d0 * d1 * (long long)(maxb[2] - b.minb[2] + 1);
+        if (!b.passthrough && span > b.cells) b.cells = span;
+      }
+      s_box = b;
+      if (a.box_out) a.box_out[ci * a.nseg + s] = b;
+      s_carry = VS_PAD;
+    }
+    __syncthreads();
+  }
+  const VoxBox box = s_box;
+  int bits = 1;
+  while (bits < 32 && (1LL << bits) < box.cells) bits++;
+  const int npass = (bits + 7) / 8;
+  if (box.nfinite == 0 && !box.passthrough) { if (tid == 0) k.n_out[s] = 0; return; }
+
+  // ---- 2. runs of equal voxel index, in input order ---------------------------------------------------------------------
+  unsigned int nruns = 0;
+  {
+    int buf = 0;
+    for (int t0 = 0; t0 < n; t0 += VS_T) {
+      const int i = t0 + tid;
+      unsigned int idx = VS_PAD;
+      if (i < n) idx = vox_index_of(in[i], box, inv, (unsigned int)i);
+      s_idx[1 + tid] = idx;
+      if (tid == 0) {
+        s_idx[0] = s_carry;
+        const int j = t0 + VS_T;
+        s_idx[1 + VS_T] = j < n ? vox_index_of(in[j], box, inv, (unsigned int)j) : VS_PAD;
+      }
+      __syncthreads();
+      const bool valid = idx != VS_PAD;
+      const bool st = valid && s_idx[tid] != idx, en = valid && s_idx[tid + 2] != idx;
+      const unsigned int b0 = __ballot_sync(0xffffffffu, st), b1 = __ballot_sync(0xffffffffu, en);
+      if (lane == 0) s_wt[buf][warp] = __popc(b0) | (__popc(b1) << 16);
+      if (tid == VS_T - 1) s_carry = idx;
+      __syncthreads();
+      const int v = s_wt[buf][lane];
+      const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
+      const int tot = __reduce_add_sync(0xffffffffu, v);
+      const unsigned int ps = nruns + (before & 0xFFFF) + __popc(b0 & lt), pe = nruns + (before >> 16) + __popc(b1 & lt);
+      if (st) {
+        keyb[0][ps] = idx; valb[0][ps] = ps; run_start[ps] = (unsigned int)i;
+        for (int p = 0; p < npass; p++) atomicAdd(&s_hist[p][(idx >> (8 * p)) & 255u], 1u);
+      }
+      if (en) run_end[pe] = (unsigned int)i + 1u;
+      nruns += (unsigned int)(tot & 0xFFFF);
+      buf ^= 1;
     }
   }
-  __shared__ float smn[32][3], smx[32][3];
-  __shared__ int snf[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      mn[k] = fminf(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmaxf(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o));
-    }
-    nf += __shfl_down_sync(0xffffffffu, nf, o);
-  }
-  if (lane == 0) { for (int k = 0; k < 3; k++) { smn[warp][k] = mn[k]; smx[warp][k] = mx[k]; } snf[warp] = nf; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
-      for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], smn[w][k]); mx[k] = fmaxf(mx[k], smx[w][k]); }
-      nf += snf[w];
+
+  // ---- 3. stable LSD radix sort of the runs by voxel index ----------------------------------------------------------------
+  int cur = 0;
+  for (int p = 0; p < npass; p++) {
+    const int shift = 8 * p;
+    if (tid < 256) {   // exclusive scan of the digit histogram
+      const unsigned int v = s_hist[p][tid];
+      unsigned int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (lane == 31) s_wsum[warp] = x;
+      s_digit[tid] = x - v;
     }
-    VoxBox b;
-    b.nfinite = nf; b.passthrough = 0; b.cells = 1;
-    b.minb[0] = b.minb[1] = b.minb[2] = 0; b.mul1 = b.mul2 = 0;
-    if (nf > 0) {
-      // voxel_grid_partition.hpp:108-137
-      long long dx = (long long)((mx[0] - mn[0]) * inv) + 1;
-      long long dy = (long long)((mx[1] - mn[1]) * inv) + 1;
-      long long dz = (long long)((mx[2] - mn[2]) * inv) + 1;
-      if (dx * dy * dz > 2147483647LL) b.passthrough = 1;
-      b.cells = b.passthrough ? (long long)n : dx * dy * dz;   // upper bound of the sort index (identity order when passing through)
-      int maxb[3];
-      for (int k = 0; k < 3; k++) { b.minb[k] = (int)floorf(mn[k] * inv); maxb[k] = (int)floorf(mx[k] * inv); }
-      int d0 = maxb[0] - b.minb[0] + 1, d1 = maxb[1] - b.minb[1] + 1;
-      b.mul1 = d0; b.mul2 = d0 * d1;
+    __syncthreads();
+    if (tid < 256) {
+      unsigned int add = 0;
+      for (int w = 0; w < warp; w++) add += s_wsum[w];
+      s_digit[tid] += add;
     }
-    box[s] = b;
+    // (the first barrier of the tile loop orders these writes before their first use)
+    const unsigned int* sk = keyb[cur]; const unsigned int* sv = valb[cur];
+    unsigned int* dk = keyb[cur ^ 1]; unsigned int* dv = valb[cur ^ 1];
+    for (unsigned int t0 = 0; t0 < nruns; t0 += VS_T) {
+      const unsigned int r = t0 + tid;
+      const bool ok = r < nruns;
+      const unsigned int key = ok ? sk[r] : 0u, val = ok ? sv[r] : 0u;
+      const unsigned int d = ok ? ((key >> shift) & 255u) : (256u + (unsigned int)lane);
+#pragma unroll
+      for (int q = 0; q < 4; q++) reinterpret_cast<unsigned int*>(&s_wcnt[0][0])[tid + q * VS_T] = 0u;
+      __syncthreads();
+      const unsigned int m = __match_any_sync(0xffffffffu, d);
+      const unsigned int rank_w = __popc(m & lt);
+      if (ok && rank_w == 0) s_wcnt[warp][d] = (unsigned short)__popc(m);
+      __syncthreads();
+      {   // per digit: exclusive prefix over the 32 warps, four threads per digit (8 warps each) + their group totals
+        const int d2 = tid & 255, g = tid >> 8;
+        unsigned int acc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned int c = s_wcnt[g * 8 + w][d2]; s_wcnt[g * 8 + w][d2] = (unsigned short)acc; acc += c; }
+        s_gsum[g][d2] = acc;
+      }
+      __syncthreads();
+      if (ok) {
+        unsigned int pos = s_digit[d] + s_wcnt[warp][d] + rank_w;
+        const int g = warp >> 3;
+        if (g > 0) pos += s_gsum[0][d];
+        if (g > 1) pos += s_gsum[1][d];
+        if (g > 2) pos += s_gsum[2][d];
+        dk[pos] = key; dv[pos] = val;
+      }
+      __syncthreads();
+      if (tid < 256) s_digit[tid] += s_gsum[0][tid] + s_gsum[1][tid] + s_gsum[2][tid] + s_gsum[3][tid];
+    }
+    __syncthreads();
+    cur ^= 1;
   }
-}
 
-#define CM_VOX_PAD 0xFFFFFFFFFFFFFFFFull
-
-__global__ void vox_key_kernel(const float4* __restrict__ in, const int* __restrict__ n_in, int cap_in, int max_n, int nseg, float inv,
-                               const VoxBox* __restrict__ box, int shift, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (size_t)nseg * max_n) return;
-  int s = (int)(g / max_n), i = (int)(g - (size_t)s * max_n);
-  const size_t src = (size_t)s * cap_in + i;
-  unsigned long long key = CM_VOX_PAD;
-  if (i < n_in[s]) {
-    const VoxBox b = box[s];
-    float4 q = in[src];
-    if (b.passthrough) {
-      key = ((unsigned long long)s << shift) | (unsigned int)i;   // identity order
-    } else if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
-      // voxel_grid_partition.hpp:212-226
-      int ijk0 = (int)(floorf(q.x * inv) - (float)b.minb[0]);
-      int ijk1 = (int)(floorf(q.y * inv) - (float)b.minb[1]);
-      int ijk2 = (int)(floorf(q.z * inv) - (float)b.minb[2]);
-      int idx = ijk0 + ijk1 * b.mul1 + ijk2 * b.mul2;
-      key = ((unsigned long long)s << shift) | (unsigned int)idx;
+  // ---- 4. voxel heads -> output rank -> centroid (runs in order, points of a run in order) -----------------------------------
+  const unsigned int* sk = keyb[cur]; const unsigned int* sv = valb[cur];
+  float4* out = k.out + (size_t)s * k.cap_out;
+  unsigned int nvox = 0;
+  {
+    int buf = 0;
+    for (unsigned int t0 = 0; t0 < nruns; t0 += VS_T) {
+      const unsigned int r = t0 + tid;
+      const unsigned int key = r < nruns ? sk[r] : VS_PAD;
+      const bool head = r < nruns && (r == 0 || sk[r - 1] != key);
+      const unsigned int b0 = __ballot_sync(0xffffffffu, head);
+      if (lane == 0) s_wt[buf][warp] = __popc(b0);
+      __syncthreads();
+      const int v = s_wt[buf][lane];
+      const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
+      const int tot = __reduce_add_sync(0xffffffffu, v);
+      if (head) {
+        const unsigned int pos = nvox + (unsigned int)before + __popc(b0 & lt);
+        float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
+        unsigned int cnt = 0;
+        for (unsigned int rr = r; rr < nruns && sk[rr] == key; rr++) {
+          const unsigned int id = sv[rr];
+          const unsigned int i0 = run_start[id], i1 = run_end[id];
+          for (unsigned int i = i0; i < i1; i++) {
+            const float4 q = in[i];
+            cx += q.x; cy += q.y; cz += q.z; cw += q.w;   // Eigen::VectorXf centroid += point, in sorted (= input) order
+          }
+          cnt += i1 - i0;
+        }
+        const float c = (float)cnt;
+        if (pos < (unsigned int)k.cap_out) out[pos] = make_float4(cx / c, cy / c, cz / c, cw / c);
+        else if (a.overflow) atomicExch(a.overflow, 1);
+      }
+      nvox += (unsigned int)tot;
+      buf ^= 1;
     }
   }
-  keys[g] = key;
-  vals[g] = (unsigned int)src;
-}
-
-// head flag = first element of a (segment, idx) run among the sorted keys
-__global__ void vox_head_kernel(const unsigned long long* __restrict__ keys, size_t n, int* __restrict__ flags) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n) return;
-  unsigned long long k = keys[g];
-  flags[g] = (k != CM_VOX_PAD && (g == 0 || keys[g - 1] != k)) ? 1 : 0;
-}
-
-// seg_first[s] = position of the segment's first sorted element = number of valid elements of the segments before it
-__global__ void vox_segstart_kernel(const int* __restrict__ n_in, const VoxBox* __restrict__ box, int nseg, int* __restrict__ seg_first) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int acc = 0;
-    for (int s = 0; s < nseg; s++) { seg_first[s] = acc; acc += box[s].passthrough ? n_in[s] : box[s].nfinite; }
-    seg_first[nseg] = acc;
-  }
-}
-
-__global__ void vox_centroid_kernel(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
-                                    const unsigned int* __restrict__ vals, const int* __restrict__ flags,
-                                    const int* __restrict__ rank, const int* __restrict__ seg_first, size_t n, int nseg, int shift,
-                                    float4* __restrict__ out, int cap_out, int* __restrict__ n_out, int* __restrict__ overflow) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n) return;
-  if (!flags[g]) return;
-  unsigned long long k = keys[g];
-  int s = (int)(k >> shift);
-  int first = seg_first[s];
-  int pos = rank[g] - rank[first];
-  // segment total = heads in [first, seg_first[s+1]); the last head of the segment publishes it
-  size_t end = (size_t)seg_first[s + 1];
-  float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
-  size_t j = g;
-  for (; j < end && keys[j] == k; j++) {
-    float4 q = in[vals[j]];
-    cx += q.x; cy += q.y; cz += q.z; ci += q.w;   // Eigen::VectorXf centroid += point, in sorted (= input) order
-  }
-  float cnt = (float)(j - g);
-  if (j == end) n_out[s] = (pos + 1 <= cap_out) ? pos + 1 : cap_out;
-  if (pos < cap_out) out[(size_t)s * cap_out + pos] = make_float4(cx / cnt, cy / cnt, cz / cnt, ci / cnt);
-  else if (overflow) atomicExch(overflow, 1);
-}
-
-__global__ void vox_zero_counts_kernel(const int* __restrict__ n_in, const VoxBox* __restrict__ box, int nseg, int* __restrict__ n_out) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < nseg) n_out[s] = 0;
-}
-
-void launch_vox_bbox(int nseg, const float4* d_in, const int* d_n_in, int cap_in, float leaf, VoxBox* d_box, cudaStream_t stream) {
-  if (nseg <= 0 || cap_in <= 0) return;
-  CM_LAUNCH(vox_bbox_kernel, nseg, 1024, 0, stream, d_in, d_n_in, cap_in, 1.0f / leaf, d_box);
+  if (tid == 0) k.n_out[s] = nvox <= (unsigned int)k.cap_out ? (int)nvox : k.cap_out;
 }
 
 // number of key bits that index `cells` distinct voxel indices
 int vox_index_bits(long long cells) { int b = 1; while (b < 32 && (1LL << b) < cells) b++; return b; }
 
+static void fill_class(VoxClass& c, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out, int cap_out,
+                       unsigned int* scratch) {
+  c.in = d_in; c.n_in = d_n_in; c.cap_in = cap_in; c.inv = 1.0f / leaf; c.out = d_out; c.n_out = d_n_out; c.cap_out = cap_out; c.scratch = scratch;
+}
+
 void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_in, int max_n, float leaf, float4* d_out, int* d_n_out,
-                      int cap_out, int* d_overflow, cudaStream_t stream, const VoxBox* d_box_ready, int idx_bits) {
+                      int cap_out, int* d_overflow, cudaStream_t stream) {
   if (nseg <= 0 || cap_in <= 0) return;
-  if (max_n <= 0 || max_n > cap_in) max_n = cap_in;   // host-known upper bound of n_in[s]: only that many slots per segment are sorted
-  const size_t n = (size_t)nseg * max_n;
-  const float inv = 1.0f / leaf;   // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
-  box.reserve(sizeof(VoxBox) * nseg);
-  keys_a.reserve(n * 8); keys_b.reserve(n * 8); vals_a.reserve(n * 4); vals_b.reserve(n * 4);
-  flags.reserve(n * 4); rank.reserve(n * 4); seg_first.reserve(sizeof(int) * (nseg + 1));
-  // key = segment << shift | voxel index; the all-ones segment code is left to the padding key so that padding can never tie
-  // with a real key inside the sorted bit range
-  if (idx_bits < 1 || idx_bits > 32 || !d_box_ready) idx_bits = 32;
-  const int shift = idx_bits;
-  int sbits = 0;
-  while ((1 << sbits) < nseg + 1) sbits++;
-  size_t t1 = 0, t2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr,
-                                  (unsigned int*)nullptr, (long long)n, 0, shift + sbits, stream);
-  cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, (long long)n, stream);
-  temp.reserve(t1 > t2 ? t1 : t2);
-  const int T = 256;
-  const unsigned int nb = (unsigned int)((n + T - 1) / T);
-  const VoxBox* d_box = d_box_ready;
-  if (!d_box) { CM_LAUNCH(vox_bbox_kernel, nseg, 1024, 0, stream, d_in, d_n_in, cap_in, inv, (VoxBox*)box.p); d_box = (const VoxBox*)box.p; }
-  CM_LAUNCH(vox_zero_counts_kernel, (nseg + 63) / 64, 64, 0, stream, d_n_in, d_box, nseg, d_n_out);
-  CM_LAUNCH(vox_key_kernel, nb, T, 0, stream, d_in, d_n_in, cap_in, max_n, nseg, inv, d_box, shift, (unsigned long long*)keys_a.p,
-            (unsigned int*)vals_a.p);
-  size_t tb = temp.cap;
-  CM_TIMED("cub_radix_sort(voxel)", stream,
-           cub::DeviceRadixSort::SortPairs(temp.p, tb, (const unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
-                                           (const unsigned int*)vals_a.p, (unsigned int*)vals_b.p, (long long)n, 0, shift + sbits, stream));
-  g_launch_count += (shift + sbits + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
-  CM_LAUNCH(vox_head_kernel, nb, T, 0, stream, (const unsigned long long*)keys_b.p, n, (int*)flags.p);
-  tb = temp.cap;
-  CM_TIMED("cub_scan(voxel)", stream, cub::DeviceScan::ExclusiveSum(temp.p, tb, (const int*)flags.p, (int*)rank.p, (long long)n, stream));
-  g_launch_count += 2;
-  CM_LAUNCH(vox_segstart_kernel, 1, 32, 0, stream, d_n_in, d_box, nseg, (int*)seg_first.p);
-  CM_LAUNCH(vox_centroid_kernel, nb, T, 0, stream, d_in, (const unsigned long long*)keys_b.p, (const unsigned int*)vals_b.p,
-            (const int*)flags.p, (const int*)rank.p, (const int*)seg_first.p, n, nseg, shift, d_out, cap_out, d_n_out, d_overflow);
+  if (max_n <= 0 || max_n > cap_in) max_n = cap_in;   // host-known upper bound of n_in[s]: sizes the scratch
+  const size_t stride = ((size_t)max_n + 255) & ~(size_t)255;
+  scratch.reserve((size_t)nseg * 6 * stride * sizeof(unsigned int));
+  VoxSegArgs a;
+  fill_class(a.cls[0], d_in, d_n_in, cap_in, leaf, d_out, d_n_out, cap_out, (unsigned int*)scratch.p);
+  a.cls[1] = a.cls[0];
+  a.nseg = nseg; a.ncls = 1; a.stride = (unsigned int)stride; a.overflow = d_overflow; a.box_out = nullptr;
+  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 1), VS_T, 0, stream, a);
+}
+
+void VoxelFilter::run2(int nseg, const float4* d_in0, const int* d_n_in0, int cap_in0, float leaf0, float4* d_out0, int* d_n_out0, int cap_out0,
+                       const float4* d_in1, const int* d_n_in1, int cap_in1, float leaf1, float4* d_out1, int* d_n_out1, int cap_out1,
+                       int max_n, int* d_overflow, cudaStream_t stream) {
+  if (nseg <= 0 || cap_in0 <= 0 || cap_in1 <= 0) return;
+  const int capmax = cap_in0 > cap_in1 ? cap_in0 : cap_in1;
+  if (max_n <= 0 || max_n > capmax) max_n = capmax;
+  const size_t stride = ((size_t)max_n + 255) & ~(size_t)255;
+  scratch.reserve((size_t)2 * nseg * 6 * stride * sizeof(unsigned int));
+  VoxSegArgs a;
+  fill_class(a.cls[0], d_in0, d_n_in0, cap_in0, leaf0, d_out0, d_n_out0, cap_out0, (unsigned int*)scratch.p);
+  fill_class(a.cls[1], d_in1, d_n_in1, cap_in1, leaf1, d_out1, d_n_out1, cap_out1, (unsigned int*)scratch.p + (size_t)nseg * 6 * stride);
+  a.nseg = nseg; a.ncls = 2; a.stride = (unsigned int)stride; a.overflow = d_overflow; a.box_out = nullptr;
+  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 2), VS_T, 0, stream, a);
 }
 
 }  // namespace cm
