@@ -155,7 +155,9 @@ struct MatchLaunch {
   IterTrace* trace;                           // optional device [nstreams][max_iterations]
   int* nn;                                    // optional device [max_iterations][nstreams][cap][5]
   int orig_idx;                               // grids carry original indices in pts[].w
-  int max_queries = 0;                        // host-known upper bound of n_corner[s] + n_surf[s] (0: use the capacities)
+  int max_queries = 0;                        // what the grids are sized for: n_corner[s] + n_surf[s] of the largest stream, exact or an
+                                              // ESTIMATE (the kernels loop when a stream has more); 0: use the capacities
+  int bound_queries = 0;                      // host-known UPPER BOUND of n_corner[s] + n_surf[s]: sizes the scratch (0: max_queries)
   const float* own_box = nullptr;             // device {lo[3], hi[3]}: evaluate only queries inside (sharded map), else all
   void* hard = nullptr;                       // optional device list of deferred "hard" queries (hard_cap * CM_HARD_ITEM_BYTES)
   int* hard_count = nullptr;                  // device [CM_MAX_EVALS] counters, one per Gauss-Newton evaluation
@@ -183,7 +185,7 @@ inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   if (capacity < 1) capacity = 1;
   items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS * 8);   // x8: one counter row per stream group
   m.hard = items.p; m.hard_count = (int*)count.p; m.hard_cap = (int)capacity;
-  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
+  const int maxq = m.bound_queries > 0 ? m.bound_queries : (m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf);
   m.partial_blocks = (maxq + 32 + 255) / 256;
   partials.reserve((size_t)m.nstreams * m.partial_blocks * 32 * sizeof(double)); tickets.reserve(sizeof(int) * m.nstreams);
   m.partials = (double*)partials.p; m.tickets = (int*)tickets.p;

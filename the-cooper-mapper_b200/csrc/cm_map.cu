@@ -36,7 +36,18 @@ __device__ __forceinline__ int world_to_cube_axis(float x, float cube_size, int 
 // map voxel, so the lists are almost always of length 1; the 62-bit radix sort this replaces cost 8 passes per class.)
 struct GroupEntry { unsigned long long key; int head; int tail; };
 
-__global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap) {
+// The launch sizes of an insert come from an ESTIMATE of the per-stream counts (they live on the device).  If a stream has
+// more points than the estimate, the whole insert is skipped (every kernel below tests the flag first) and the host, which sees
+// the flag with the step's results, repeats it with exact sizes: nothing is ever inserted partially.
+__global__ void map_insert_guard_kernel(const int* __restrict__ n_pts, int nstreams, int max_n, int* __restrict__ skip) {
+  int over = 0;
+  for (int s = threadIdx.x; s < nstreams; s += blockDim.x) over |= n_pts[s] > max_n ? 1 : 0;
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) *skip = over;
+}
+
+__global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap, const int* __restrict__ skip) {
+  if (*skip) return;
   unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) { tab[i].key = CM_MAP_PAD; tab[i].head = 0x7fffffff; tab[i].tail = -1; }
 }
@@ -44,7 +55,9 @@ __global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap) {
 __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int max_n, int nstreams,
                                const MatchState* __restrict__ state, const float* __restrict__ tf_override, MapClassDev* maps,
                                float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ slot_of,
-                               int* __restrict__ next, GroupEntry* __restrict__ gtab, unsigned int gmask, int* __restrict__ flags) {
+                               int* __restrict__ next, GroupEntry* __restrict__ gtab, unsigned int gmask, int* __restrict__ flags,
+                               const int* __restrict__ skip) {
+  if (*skip) return;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (size_t)nstreams * max_n) return;
   int s = (int)(g / max_n), i = (int)(g - (size_t)s * max_n);
@@ -108,7 +121,9 @@ __device__ __forceinline__ unsigned int map_find_or_create_cell(MapClassDev& m, 
 __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ slot_of,
                                  const int* __restrict__ next, const GroupEntry* __restrict__ gtab, size_t n,
                                  const float4* __restrict__ world, MapClassDev* maps, PendingAdd* __restrict__ pending,
-                                 unsigned int* __restrict__ n_pending, unsigned int pending_cap, int* __restrict__ flags) {
+                                 unsigned int* __restrict__ n_pending, unsigned int pending_cap, int* __restrict__ flags,
+                                 const int* __restrict__ skip) {
+  if (*skip) return;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   const unsigned long long key = keys[g];
@@ -336,13 +351,15 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   keys_a[cls].reserve(n * 8); vals_a[cls].reserve(n * 4); vals_b[cls].reserve(n * 4); keys_b[cls].reserve((size_t)gcap * sizeof(GroupEntry));
   pending[cls].reserve(n * sizeof(PendingAdd));
   const unsigned int nb = (unsigned int)((n + 255) / 256);
+  const int* skip = (const int*)flags.p + 4 + cls;   // flags[4 + cls]: this class' insert was skipped (a count exceeded max_n)
   cudaMemsetAsync(n_pending[cls].p, 0, sizeof(unsigned int), stream);
-  CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b[cls].p, gcap);
+  CM_LAUNCH(map_insert_guard_kernel, 1, 256, 0, stream, d_n, nstreams, max_n, (int*)flags.p + 4 + cls);
+  CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b[cls].p, gcap, skip);
   CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world[cls].p,
-            (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p);
+            (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p, skip);
   CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a[cls].p, (const unsigned int*)vals_a[cls].p, (const int*)vals_b[cls].p,
             (const GroupEntry*)keys_b[cls].p, n, (const float4*)world[cls].p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending[cls].p,
-            (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p);
+            (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p, skip);
   CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
             (MapClassDev*)dev[cls].p, (int*)flags.p);
   CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,

@@ -224,12 +224,19 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   ctx->voxel.run2(S, d_corner, d_n, cap_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c,
                   d_surf, d_n + S, cap_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s,
                   std::max(max_in_c, max_in_s), (int*)ctx->d_flag.p, st);
-  // the filtered counts size everything downstream (correspondence grid, insert sorts): one small read-back
-  std::vector<int> nds(2 * S);
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-  int max_c = 1, max_s = 1, max_q = 1;
-  for (int s = 0; s < S; s++) { max_c = std::max(max_c, nds[s]); max_s = std::max(max_s, nds[S + s]); max_q = std::max(max_q, nds[s] + nds[S + s]); }
+  // The filtered counts stay on the device: no host round trip in the middle of a step.  Everything downstream is launched
+  // for an ESTIMATE -- the previous step's largest filtered clouds + 25 % (a LiDAR's feature counts move by a few per cent
+  // from sweep to sweep), never more than the unfiltered counts, which bound them.  The correspondence kernels loop when a
+  // stream exceeds the estimate, the map insertion is skipped as a whole and repeated below (flags[4], [5]).
+  const int bound_c = std::min(cap_c, std::max(max_in_c, 1)), bound_s = std::min(cap_s, std::max(max_in_s, 1));
+  auto estimate = [](int prev, int bound, int round) {
+    if (prev <= 0) return bound;
+    const long long e = ((long long)prev * 5 / 4 + round + round - 1) / round * round;
+    return (int)std::min<long long>(e, bound);
+  };
+  int max_c = estimate(ctx->est_c, bound_c, 256), max_s = estimate(ctx->est_s, bound_s, 1024);
+  if (getenv("COOPERMAP_TEST_UNDERESTIMATE")) { max_c = std::min(max_c, 64); max_s = std::min(max_s, 256); }   // tests: force the overflow paths
+  const int max_q = std::min(max_c + max_s, bound_c + bound_s);
   // prepareFeatureSurround: cube window -> searchable views
   {
     // the window only changes when a sensor crosses a cube face: skip the upload when the device copy is current
@@ -252,9 +259,10 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.n_corner = d_nds; m.n_surf = d_nds + S; m.cap_corner = cap_c; m.cap_surf = cap_s;
   m.grid_corner = (const GridView*)ctx->map.views[0].p; m.grid_surf = (const GridView*)ctx->map.views[1].p;
   m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p; m.nn_slot = (int*)ctx->m_slots.p;
-  m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm; m.max_queries = max_q;
-  // capacity in whole 256-query CTAs, like partial_blocks: the Gauss-Newton graph key then repeats from frame to frame
-  ctx->hardq.attach(m, (size_t)S * (size_t)(((max_q + 32 + 255) / 256) * 256));
+  m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm;
+  m.max_queries = max_q; m.bound_queries = bound_c + bound_s;
+  // capacities from the bound, in whole 256-query tiles: the Gauss-Newton graph key then repeats from frame to frame
+  ctx->hardq.attach(m, (size_t)S * (size_t)(((m.bound_queries + 32 + 255) / 256) * 256));
   if (ctx->dbg_on) {
     ctx->dbg_words = (size_t)((max_q + 32 + 255) / 256) * S * 8 * 4;
     ctx->dbg_trace.reserve(ctx->dbg_words * sizeof(unsigned long long));
@@ -283,7 +291,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   if (!localise) {
     CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
-    const int ic_r = std::min(cap_c, (max_c + 255) & ~255), is_r = std::min(cap_s, (max_s + 1023) & ~1023);
+    const int ic_r = max_c, is_r = max_s;
     auto ins_c = [&]() { ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, ic_r, (const MatchState*)ctx->m_state.p, nullptr, aux); };
     auto ins_s = [&]() { ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, is_r, (const MatchState*)ctx->m_state.p, nullptr, st); };
     if (use_graphs) {
@@ -297,13 +305,29 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     }
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   }
-  // results
+  // results: states, filtered counts and flags come back together -- the step's only host synchronisation
   std::vector<MatchState> hs(S);
+  std::vector<int> nds(2 * S);
   int flags[8];
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   CM_CUDA_CHECK(ctx, cudaGetLastError());
+  {
+    int act_c = 1, act_s = 1;
+    for (int s = 0; s < S; s++) { act_c = std::max(act_c, nds[s]); act_s = std::max(act_s, nds[S + s]); }
+    ctx->est_c = act_c; ctx->est_s = act_s;
+    if (!localise && (flags[4] || flags[5])) {
+      // a stream had more filtered points than the insert was launched for: that class' insert did nothing; repeat it exactly
+      ++ctx->insert_redos;
+      if (flags[4]) ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, std::min(cap_c, act_c), (const MatchState*)ctx->m_state.p, nullptr, st);
+      if (flags[5]) ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, std::min(cap_s, act_s), (const MatchState*)ctx->m_state.p, nullptr, st);
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+      CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      CM_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+  }
   if (flags[0] || flags[2] || flags[3]) {
     // reported once: the flags are cleared so that the context stays usable (the dropped appends of THIS frame are lost, the
     // poses below are not advanced -- the caller may retry the frame after making room)

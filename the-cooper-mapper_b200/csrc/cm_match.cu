@@ -254,65 +254,67 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   __syncthreads();
   const int nC = a.n_corner[s], nS = a.n_surf[s];
   const int nT = ((nC + 31) & ~31) + nS;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t & ~31) >= nT) return;   // whole warp idle
-  unsigned long long t0 = 0;
-  if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  bool in_range, isCorner; int row;
-  float sx, sy, sz;
-  bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
-  const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
-  Top5 best;
-  top5_init(best);
-  KnnGeom c;
-  valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
-  bool need = false;
-  unsigned int ncand = 0;
-  // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
   const int it = a.iter_dev ? *a.iter_dev : a.iter;
-  const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
-  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
   const unsigned int FULL = 0xffffffffu;
-  unsigned int hard = __ballot_sync(FULL, need);
-  if (a.dbg) {
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    const unsigned int mx = __reduce_max_sync(FULL, ncand), sm = __reduce_add_sync(FULL, ncand);
-    if ((threadIdx.x & 31) == 0) {
-      unsigned long long* d = a.dbg + 4 * ((size_t)(s * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
-      unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      d[0] = t0; d[1] = t1; d[2] = ((unsigned long long)mx << 32) | sm;
-      d[3] = ((unsigned long long)__popc(hard) << 32) | ((unsigned long long)smid << 16) | (isCorner ? 1u : 0u);
-    }
-  }
-  if (a.hard) {
-    // deferred: one warp-aggregated reservation, every hard lane writes its own item
-    if (hard) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(a.iter_dev ? a.hard_count + *a.iter_dev : a.hard_count, __popc(hard));
-      base = __shfl_sync(FULL, base, 0);
-      if (need) {
-        const int pos = base + __popc(hard & ((1u << lane) - 1));
-        if (pos < a.hard_cap) {
-          HardItem it;
-          it.s = s; it.t = t; it.pad = 0;
-#pragma unroll
-          for (int k = 0; k < 5; k++) { it.d[k] = best.d(k); it.idx[k] = best.idx(k); it.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
-          reinterpret_cast<HardItem*>(a.hard)[pos] = it;
-        }
+  // the grid is sized from an ESTIMATE of the filtered feature counts (they never leave the device): a stream with more
+  // queries than the grid has threads simply loops
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; (t & ~31) < nT; t += gridDim.x * blockDim.x) {
+    unsigned long long t0 = 0;
+    if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool in_range, isCorner; int row;
+    float sx, sy, sz;
+    bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
+    const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+    Top5 best;
+    top5_init(best);
+    KnnGeom c;
+    valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
+    bool need = false;
+    unsigned int ncand = 0;
+    // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
+    const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
+    if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
+    unsigned int hard = __ballot_sync(FULL, need);
+    if (a.dbg && t < (int)(gridDim.x * blockDim.x)) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      const unsigned int mx = __reduce_max_sync(FULL, ncand), sm = __reduce_add_sync(FULL, ncand);
+      if ((threadIdx.x & 31) == 0) {
+        unsigned long long* d = a.dbg + 4 * ((size_t)(s * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
+        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        d[0] = t0; d[1] = t1; d[2] = ((unsigned long long)mx << 32) | sm;
+        d[3] = ((unsigned long long)__popc(hard) << 32) | ((unsigned long long)smid << 16) | (isCorner ? 1u : 0u);
       }
     }
-    if (!in_range || need) return;
-  } else {
-    while (hard) {
-      const int h = __ffs(hard) - 1;
-      hard &= hard - 1;
-      knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
+    if (a.hard) {
+      // deferred: one warp-aggregated reservation, every hard lane writes its own item
+      if (hard) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.iter_dev ? a.hard_count + it : a.hard_count, __popc(hard));
+        base = __shfl_sync(FULL, base, 0);
+        if (need) {
+          const int pos = base + __popc(hard & ((1u << lane) - 1));
+          if (pos < a.hard_cap) {
+            HardItem item;
+            item.s = s; item.t = t; item.pad = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { item.d[k] = best.d(k); item.idx[k] = best.idx(k); item.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
+            reinterpret_cast<HardItem*>(a.hard)[pos] = item;
+          }
+        }
+      }
+      if (!in_range || need) continue;
+    } else {
+      while (hard) {
+        const int h = __ffs(hard) - 1;
+        hard &= hard - 1;
+        knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
+      }
+      if (!in_range) continue;
     }
-    if (!in_range) return;
+    search_store<kOrigIdx>(a, s, row, valid && best.d(4) < a.prm.knn_gate, best);
   }
-  search_store<kOrigIdx>(a, s, row, valid && best.d(4) < a.prm.knn_gate, best);
 }
 
 // K5a': the hard queries of one Gauss-Newton evaluation, one warp per query (grid-stride over the list).
@@ -585,7 +587,7 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // go to global memory, and the LAST CTA of a stream to finish (ticket counter) adds the partials in CTA order and runs the
 // 6x6 step -- streams solve concurrently on different SMs instead of one after the other in a single warp, and two
 // launches per Gauss-Newton iteration disappear.  Determinism: every sum has a fixed order (row -> 32-row group -> CTA).
-struct FusedArgs { double* partials; int* tickets; double* sums; int solve_inline; };
+struct FusedArgs { double* partials; int* tickets; double* sums; int solve_inline; int ptiles; /* partial slots per stream */ };
 
 #ifndef CM_FIT_MINB
 #define CM_FIT_MINB 4
@@ -594,6 +596,16 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
   if (st.done) return;
+  const int nC = a.n_corner[s], nS = a.n_surf[s];
+  const int capQ = a.cap_corner + a.cap_surf;
+  // tiles of 256 query slots.  The grid comes from an estimate of the filtered counts; a CTA takes tiles blockIdx.x,
+  // blockIdx.x + gridDim.x, ..  Partial sums are kept PER TILE and added in tile order by the last CTA to finish, so the
+  // result does not depend on the grid size.
+  const int nT = ((nC + 31) & ~31) + nS;
+  int ntiles = (nT + 255) >> 8;
+  if (ntiles < 1) ntiles = 1;             // a stream without queries still has to reach its solve ("matched cloud points too few")
+  if (ntiles > f.ptiles) ntiles = f.ptiles;   // cannot happen: ptiles is sized from the INPUT counts, an upper bound
+  if ((int)blockIdx.x >= ntiles) return;
   __shared__ PoseCoef kc;
   __shared__ float sR[9], sT[3];
   __shared__ float4 srow[2 * 256];
@@ -605,71 +617,72 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
   if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
   if (threadIdx.x < 3) sT[threadIdx.x] = st.pose[3 + threadIdx.x];
   __syncthreads();
-  const int nC = a.n_corner[s], nS = a.n_surf[s];
-  const int capQ = a.cap_corner + a.cap_surf;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool isCorner; int src, row;
-  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-  if (decode_query(t, nC, nS, &isCorner, &src, &row)) {
-    fit_row(a, s, kc, sR, sT, isCorner, src, row, &r0, &r1);
-    float4* dst = reinterpret_cast<float4*>(a.rows + (size_t)s * capQ + row);
-    dst[0] = r0; dst[1] = r1;
-    if (isCorner) r1.w = __int_as_float(__float_as_int(r1.w) | 4);
-  }
-  // score term of the row (ScanMatch.cpp:277-286), evaluated by the row's own thread
-  sexp[threadIdx.x] = (__float_as_int(r1.w) & 1) ? exp(-fabs((double)r1.z)) : 0.0;
-  srow[2 * threadIdx.x] = r0; srow[2 * threadIdx.x + 1] = r1;
-  __syncthreads();
-  // accumulator k of row group grp: 0..20 upper triangle of A^T A, 21..26 A^T b, 27 rows, 28 / 29 counted corner / surf, 30 score
-  const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  {
-    int ra = 0, rb = 0;
-    if (k < 21) { int tt = k; while (tt >= 6 - ra) { tt -= 6 - ra; ra++; } rb = ra + tt; }
-    else if (k < 27) { ra = k - 21; rb = 6; }
-    // branch-free inner loop: every lane adds term(i) when (flag & need) == want, with per-lane constants
-    //   k < 27: term = row[ra] * row[rb] (kept rows);  27: 1 (kept rows);  28 / 29: 1 (counted corner / surf rows);  30: score term
-    const bool prod = k < 27;
-    const int ia = prod ? ra : 7, ib = prod ? rb : 7;
-    const int need = (k == 28 || k == 29) ? 6 : 1, want = (k == 28) ? 6 : (k == 29 ? 2 : 1);
-    double acc = 0.0;
-    const float* rows = reinterpret_cast<const float*>(srow);
-    for (int i = grp * 32; i < grp * 32 + 32; i++) {
-      const float* rv = rows + 8 * i;
-      const int flag = __float_as_int(rv[7]);
-      const float fa = rv[ia], fb = rv[ib];
-      double term = prod ? (double)fa * (double)fb : 1.0;
-      if (k == 30) term = sexp[i];
-      if (k < 31 && (flag & need) == want) acc += term;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t = tile * 256 + threadIdx.x;
+    bool isCorner; int src, row;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    if (decode_query(t, nC, nS, &isCorner, &src, &row)) {
+      fit_row(a, s, kc, sR, sT, isCorner, src, row, &r0, &r1);
+      float4* dst = reinterpret_cast<float4*>(a.rows + (size_t)s * capQ + row);
+      dst[0] = r0; dst[1] = r1;
+      if (isCorner) r1.w = __int_as_float(__float_as_int(r1.w) | 4);
     }
-    sacc[grp][k] = acc;
-  }
-  __syncthreads();
-  double* mine = f.partials + ((size_t)s * gridDim.x + blockIdx.x) * 32;
-  if (threadIdx.x < 32) {
-    double v = 0.0;
+    // score term of the row (ScanMatch.cpp:277-286), evaluated by the row's own thread
+    sexp[threadIdx.x] = (__float_as_int(r1.w) & 1) ? exp(-fabs((double)r1.z)) : 0.0;
+    srow[2 * threadIdx.x] = r0; srow[2 * threadIdx.x + 1] = r1;
+    __syncthreads();
+    // accumulator k of row group grp: 0..20 upper triangle of A^T A, 21..26 A^T b, 27 rows, 28 / 29 counted corner / surf, 30 score
+    const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    {
+      int ra = 0, rb = 0;
+      if (k < 21) { int tt = k; while (tt >= 6 - ra) { tt -= 6 - ra; ra++; } rb = ra + tt; }
+      else if (k < 27) { ra = k - 21; rb = 6; }
+      // branch-free inner loop: every lane adds term(i) when (flag & need) == want, with per-lane constants
+      //   k < 27: term = row[ra] * row[rb] (kept rows);  27: 1 (kept rows);  28 / 29: 1 (counted corner / surf rows);  30: score term
+      const bool prod = k < 27;
+      const int ia = prod ? ra : 7, ib = prod ? rb : 7;
+      const int need = (k == 28 || k == 29) ? 6 : 1, want = (k == 28) ? 6 : (k == 29 ? 2 : 1);
+      double acc = 0.0;
+      const float* rows = reinterpret_cast<const float*>(srow);
+      for (int i = grp * 32; i < grp * 32 + 32; i++) {
+        const float* rv = rows + 8 * i;
+        const int flag = __float_as_int(rv[7]);
+        const float fa = rv[ia], fb = rv[ib];
+        double term = prod ? (double)fa * (double)fb : 1.0;
+        if (k == 30) term = sexp[i];
+        if (k < 31 && (flag & need) == want) acc += term;
+      }
+      sacc[grp][k] = acc;
+    }
+    __syncthreads();
+    double* mine = f.partials + ((size_t)s * f.ptiles + tile) * 32;
+    if (threadIdx.x < 32) {
+      double v = 0.0;
 #pragma unroll
-    for (int g = 0; g < 8; g++) v += sacc[g][threadIdx.x];
-    __stcg(mine + threadIdx.x, v);
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(f.tickets + s, 1) == (int)gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < 32) {
-    const double* p = f.partials + (size_t)s * gridDim.x * 32 + threadIdx.x;
-    double v = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; b++) v += __ldcg(p + (size_t)b * 32);
-    stot[threadIdx.x] = v;
-    f.sums[(size_t)s * 32 + threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    f.tickets[s] = 0;
-    // the 6x6 step: inline only on request -- inside this kernel it is capped at 64 registers and runs out of local memory
-    // (~45 us per iteration); solve_warp_kernel right behind this launch does it in 128 registers
-    if (f.solve_inline) solve_stream(sa, s, stot);
+      for (int g = 0; g < 8; g++) v += sacc[g][threadIdx.x];
+      __stcg(mine + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(f.tickets + s, 1) == ntiles - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (threadIdx.x < 32) {
+        const double* p = f.partials + (size_t)s * f.ptiles * 32 + threadIdx.x;
+        double v = 0.0;
+        for (int b = 0; b < ntiles; b++) v += __ldcg(p + (size_t)b * 32);
+        stot[threadIdx.x] = v;
+        f.sums[(size_t)s * 32 + threadIdx.x] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        f.tickets[s] = 0;
+        // the 6x6 step: inline only on request -- inside this kernel it is capped at 64 registers and runs out of local memory
+        // (~45 us per iteration); solve_warp_kernel right behind this launch does it in 128 registers
+        if (f.solve_inline) solve_stream(sa, s, stot);
+      }
+    }
   }
 }
 
@@ -781,7 +794,7 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (prof) prof->end(stream);
   sa.iter = it;
   if (fused) {
-    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline();
+    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline(); f.ptiles = m.partial_blocks;
     CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
     if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
     return;
@@ -851,7 +864,7 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
   if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
   else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
-  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline();
+  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline(); f.ptiles = m.partial_blocks;
   CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
   if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
   if (box.nfinite == 0 && !box.passthrough) { if (tid == 0) k.n_out[s] = 0; return; }
 
   // ---- 2. runs of equal voxel index, in input order ---------------------------------------------------------------------
-  unsigned int nruns = 0;
+  unsigned int nruns = 0, nends = 0;   // a run that spans a tile boundary has started but not ended: two counters
   {
     int buf = 0;
     for (int t0 = 0; t0 < n; t0 += VS_T) {
@@ -162,13 +162,13 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
       const int v = s_wt[buf][lane];
       const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
       const int tot = __reduce_add_sync(0xffffffffu, v);
-      const unsigned int ps = nruns + (before & 0xFFFF) + __popc(b0 & lt), pe = nruns + (before >> 16) + __popc(b1 & lt);
+      const unsigned int ps = nruns + (before & 0xFFFF) + __popc(b0 & lt), pe = nends + (before >> 16) + __popc(b1 & lt);
       if (st) {
         keyb[0][ps] = idx; valb[0][ps] = ps; run_start[ps] = (unsigned int)i;
         for (int p = 0; p < npass; p++) atomicAdd(&s_hist[p][(idx >> (8 * p)) & 255u], 1u);
       }
       if (en) run_end[pe] = (unsigned int)i + 1u;
-      nruns += (unsigned int)(tot & 0xFFFF);
+      nruns += (unsigned int)(tot & 0xFFFF); nends += (unsigned int)(tot >> 16);
       buf ^= 1;
     }
   }
@@ -253,9 +253,18 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
         for (unsigned int rr = r; rr < nruns && sk[rr] == key; rr++) {
           const unsigned int id = sv[rr];
           const unsigned int i0 = run_start[id], i1 = run_end[id];
-          for (unsigned int i = i0; i < i1; i++) {
-            const float4 q = in[i];
-            cx += q.x; cy += q.y; cz += q.z; cw += q.w;   // Eigen::VectorXf centroid += point, in sorted (= input) order
+          // Eigen::VectorXf centroid += point, in sorted (= input) order; four loads in flight, the adds stay sequential
+          for (unsigned int i = i0; i < i1; i += 4) {
+            const unsigned int m = i1 - i;
+            const float4 q0 = in[i];
+            float4 q1, q2, q3;
+            if (m > 1) q1 = in[i + 1];
+            if (m > 2) q2 = in[i + 2];
+            if (m > 3) q3 = in[i + 3];
+            cx += q0.x; cy += q0.y; cz += q0.z; cw += q0.w;
+            if (m > 1) { cx += q1.x; cy += q1.y; cz += q1.z; cw += q1.w; }
+            if (m > 2) { cx += q2.x; cy += q2.y; cz += q2.z; cw += q2.w; }
+            if (m > 3) { cx += q3.x; cy += q3.y; cz += q3.z; cw += q3.w; }
           }
           cnt += i1 - i0;
         }
