@@ -297,7 +297,7 @@ int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_co
 /* Development aid (no reference counterpart): per-warp trace of the 5-NN search kernel in Gauss-Newton evaluation `iter` of
  * the following cm_pipeline_step / cm_mapping_process calls (iter < 0: off).  4 words per warp: start ns, end ns,
  * (max << 32 | sum) level-0 candidates over the lanes, (hard queries << 32 | smid << 16 | is_corner). */
-int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out2);   /* graphs built so far: {Gauss-Newton loop, filter / insert chains} */
+int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out4);   /* {Gauss-Newton loop graphs built, insert chain captures, insert repeats, 0} */
 int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop);   /* CUDA graphs cached for the Gauss-Newton loop; 1 = WHILE-node graphs */
 int cm_debug_search_trace_enable(cm_ctx* ctx, int iter);
 int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_words, size_t* n_words);

@@ -94,3 +94,44 @@ def test_lasermapping_mirror_and_shift_unsupported(cmb, oracle, synth):
     assert lm.last_stats["status"] == 1                      # empty map: "reference cloud points too few"
     with pytest.raises(cmb.CoopermapError):                  # 200 m up: the reference would shift() its cube grid
         lm.process(R.astype(np.float32), np.array([0, 0, 200], np.float32), f["lessSharp"], f["lessFlat"])
+
+
+def test_estimate_sized_launches_change_nothing(cmb, synth, monkeypatch):
+    """The filtered feature counts never leave the device: the correspondence kernels and the map insertion are launched for
+    an ESTIMATE of them.  Forcing a gross under-estimate (search / fit kernels loop over their tiles, the insertion is skipped
+    as a whole and repeated with exact sizes) must give the same poses and the same map, bit for bit; and alternating small /
+    large / small frames must not make the cached CUDA graphs replay stale buffers (graphs are keyed by the allocation
+    generation)."""
+    sc = synth.make_scene(seed=61, extent=40.0, n_boxes=12, n_poles=10)
+    S = 2
+    seq_big = [_frames(synth, sc, 6, seed=300 + 40 * s, cols=900) for s in range(S)]
+    seq_small = [_frames(synth, sc, 6, seed=700 + 40 * s, cols=128) for s in range(S)]
+
+    def run(under):
+        if under:
+            monkeypatch.setenv("COOPERMAP_TEST_UNDERESTIMATE", "1")
+        else:
+            monkeypatch.delenv("COOPERMAP_TEST_UNDERESTIMATE", raising=False)
+        ctx = cmb.Context(**MAP_CFG)
+        ctx.mapping_create(S, 100000, 600000)
+        out = []
+        for k in range(6):
+            seqs = seq_small if k in (1, 4) else seq_big                 # small, LARGE, small feature counts across steps
+            fr = np.stack([seqs[s][k][2] for s in range(S)])
+            odoms = [(seqs[s][k][0].astype(np.float32), seqs[s][k][1].astype(np.float32)) for s in range(S)]
+            out.append(ctx.pipeline_step(fr, odoms))
+        maps = [ctx.map_export_sorted(s, cls)[0] for s in range(S) for cls in (0, 1)]
+        ctx.graph_builds()
+        redos = ctx.insert_redos
+        ctx.close()
+        return out, maps, redos
+
+    ref, maps_ref, redos_ref = run(False)
+    und, maps_und, redos_und = run(True)
+    assert redos_und >= 4 and redos_ref <= 2
+    for (isos_a, st_a), (isos_b, st_b) in zip(ref, und):
+        for s in range(S):
+            assert np.array_equal(isos_a[s][0], isos_b[s][0]) and np.array_equal(isos_a[s][1], isos_b[s][1])
+            assert st_a[s]["iterations"] == st_b[s]["iterations"] and st_a[s]["rows"] == st_b[s]["rows"]
+    for a, b in zip(maps_ref, maps_und):
+        assert _same(a, b)

@@ -310,8 +310,9 @@ class Context:
 
     def graph_builds(self):
         """(Gauss-Newton loop graphs built, filter / insert chain graphs captured) so far."""
-        a = (C.c_ulonglong * 2)()
+        a = (C.c_ulonglong * 4)()
         self._check(self.L.cm_debug_graph_builds(self.h, a))
+        self.insert_redos = int(a[2])
         return int(a[0]), int(a[1])
 
     def timer_elapsed_ms(self):

@@ -826,10 +826,11 @@ int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop) {
   if (while_loop) *while_loop = ctx->match_graphs.use_while ? 1 : 0;
   return CM_OK;
 }
-/* graphs built so far: [0] Gauss-Newton loop graphs, [1] voxel-filter / map-insert chain captures (a steady-state pipeline stops building) */
-int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out2) {
-  if (!ctx || !out2) return CM_ERR_ARG;
-  out2[0] = ctx->match_graphs.builds; out2[1] = ctx->stage_graphs.captures;
+/* [0] Gauss-Newton loop graphs built so far, [1] map-insert chain captures (a steady-state pipeline stops building), [2] steps whose
+ * map insertion was repeated with exact sizes (the estimate of the filtered counts was too small), [3] reserved */
+int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out4) {
+  if (!ctx || !out4) return CM_ERR_ARG;
+  out4[0] = ctx->match_graphs.builds; out4[1] = ctx->stage_graphs.captures; out4[2] = ctx->insert_redos; out4[3] = 0;
   return CM_OK;
 }
 int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = ctx->prof_sr.enabled = on != 0; return CM_OK; }
