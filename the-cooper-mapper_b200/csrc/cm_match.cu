@@ -587,12 +587,12 @@ __global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int n
 // go to global memory, and the LAST CTA of a stream to finish (ticket counter) adds the partials in CTA order and runs the
 // 6x6 step -- streams solve concurrently on different SMs instead of one after the other in a single warp, and two
 // launches per Gauss-Newton iteration disappear.  Determinism: every sum has a fixed order (row -> 32-row group -> CTA).
-struct FusedArgs { double* partials; int* tickets; double* sums; int solve_inline; int ptiles; /* partial slots per stream */ };
+struct FusedArgs { double* partials; int* tickets; double* sums; int ptiles; /* partial slots per stream */ };
 
 #ifndef CM_FIT_MINB
 #define CM_FIT_MINB 4
 #endif
-__global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a, SolveArgs sa, FusedArgs f) {
+__global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a, FusedArgs f) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
   if (st.done) return;
@@ -611,7 +611,6 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
   __shared__ float4 srow[2 * 256];
   __shared__ double sacc[8][32];
   __shared__ double sexp[256];
-  __shared__ double stot[32];
   __shared__ int s_last;
   if (threadIdx.x == 0) make_pose_coef(st, kc);
   if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
@@ -672,16 +671,12 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
         const double* p = f.partials + (size_t)s * f.ptiles * 32 + threadIdx.x;
         double v = 0.0;
         for (int b = 0; b < ntiles; b++) v += __ldcg(p + (size_t)b * 32);
-        stot[threadIdx.x] = v;
         f.sums[(size_t)s * 32 + threadIdx.x] = v;
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        f.tickets[s] = 0;
-        // the 6x6 step: inline only on request -- inside this kernel it is capped at 64 registers and runs out of local memory
-        // (~45 us per iteration); solve_warp_kernel right behind this launch does it in 128 registers
-        if (f.solve_inline) solve_stream(sa, s, stot);
-      }
+      // (the 6x6 step runs in solve_warp_kernel right behind this launch: inside this kernel it was capped at 64 registers and
+      // ran out of local memory, ~45 us per iteration)
+      if (threadIdx.x == 0) f.tickets[s] = 0;
     }
   }
 }
@@ -750,8 +745,6 @@ void launch_knn5(const GridView& g, const float* d_q, int nq, float gate, int* d
   if (nq > 0) CM_LAUNCH(knn5_kernel, (nq + 127) / 128, 128, 0, stream, g, d_q, nq, gate, d_idx, d_d2);
 }
 
-static int solve_inline() { static const int v = getenv("COOPERMAP_SOLVE_INLINE") ? 1 : 0; return v; }   // development: the round-1 fused solve
-
 static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.corner = m.corner; ca.surf = m.surf; ca.n_corner = m.n_corner; ca.n_surf = m.n_surf;
   ca.cap_corner = m.cap_corner; ca.cap_surf = m.cap_surf; ca.grid_corner = m.grid_corner; ca.grid_surf = m.grid_surf;
@@ -794,9 +787,9 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (prof) prof->end(stream);
   sa.iter = it;
   if (fused) {
-    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline(); f.ptiles = m.partial_blocks;
-    CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
-    if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
+    FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.ptiles = m.partial_blocks;
+    CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, f);
+    CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
     return;
   }
   CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
@@ -864,9 +857,9 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
   if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
   else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
-  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.solve_inline = solve_inline(); f.ptiles = m.partial_blocks;
-  CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, sa, f);
-  if (!f.solve_inline) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
+  FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.ptiles = m.partial_blocks;
+  CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, f);
+  CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
 }
 
 // init -> WHILE { search, hard search, fit + solve, advance }: as many evaluations as the slowest stream needs, one submission

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   unsigned short* ord = lst0 + 5 * cap;
   const float4* stage = reinterpret_cast<const float4*>(key);         // 16 * cols bytes <= 8 * KEYN + 12 * cap
   __shared__ int s_wt[2 * SR_MAXCH * SR_WARPS];
+  __shared__ int s_wt2[SR_MAXCH * SR_WARPS];   // a third flag scanned in the same barrier phase (pass 3)
   __shared__ __align__(8) unsigned long long s_mbar;
   int fs_buf = 0;   // uniform over the CTA: every thread makes the same sequence of scans
   FlagScan fs;
@@ -573,18 +574,19 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       if (lane == 0) p1_begin[j] = np1;
       if (ep >= 0) {
         for (int k = 0; k < prm.max_flat; k++) {
-          unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
+          // arg-min on (curvature, index): the lane keeps its first smallest cell (ascending c, strict <), the warp the smaller index on ties
+          float bv = __int_as_float(0x7f800000); int bc = 0x7fffffff;
           for (int c = sp + lane; c <= ep; c += 32) {
             const float cv = curv[c];
-            if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) {
-              const unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned int)c;
-              best = kk < best ? kk : best;
-            }
+            if (cv < prm.curv_thr && cv < bv && state[c] != P_SURF_PICKED_NEAR) { bv = cv; bc = c; }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
-          if (best == 0xFFFFFFFFFFFFFFFFull) break;
-          const int c = (int)(best & 0xFFFFFFFFu);
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+          }
+          if (bc == 0x7fffffff) break;
+          const int c = bc;
           __syncwarp();   // every lane has finished reading state[] (the shuffles order execution, this orders memory)
           if (lane <= 2 * R) state[c - R + lane] = P_SURF_PICKED_NEAR;   // markAsPicked: c-R .. c+R
           if (lane == 0 && np1 < SR_MAXREG * 8) p1buf[np1] = (unsigned short)c;
@@ -681,11 +683,15 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     }
   }
   // ---- pass 3 (:305-354) over the descending order of every region: emission counters become prefix sums -----------
-  unsigned short* qfa = pfc; unsigned short* qfb = pfc + cap;   // corner / surf prefixes along `ord`
+  // flat emissions: ONESIDE_FLAT while the shared counter (bumped by SURFACE_FLAT too) is below the cap, i.e. the ONESIDE_FLAT
+  // elements among the first max_flat surf elements of the region -- decided per element from two prefixes, no serial walk
+  unsigned short* qfa = pfc; unsigned short* qfb = pfc + cap; unsigned short* qfc = pfc + 2 * cap;   // corner / surf / one-sided prefixes along `ord`
   {
     const int nchm = (m_all + SR_THREADS - 1) / SR_THREADS;
-    unsigned int m = 0;
+    unsigned int m = 0, m3 = 0;
+    FlagScan fs2; int b2 = 0;
     fs.begin(s_wt, fs_buf);
+    fs2.begin(s_wt2, b2);
     for (int k = 0; k < nchm; k++) {
       const int i = k * SR_THREADS + tid;
       const bool in = i < m_all;
@@ -694,8 +700,11 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int rj = in ? region_of(c) : -1;
       const bool is_corner = in && l == L_CORNER_SHARP && snap[c] > P_EDGE_BROKEN;
       const bool is_surf = in && (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT);
+      const bool is_one = in && l == L_ONESIDE_FLAT;
       m |= ((is_corner ? 1u : 0u) | (is_surf ? 0x10000u : 0u)) << k;
+      m3 |= (is_one ? 1u : 0u) << k;
       fs.vote(k, is_corner, is_surf);
+      fs2.vote(k, is_one);
       if (is_corner) atomicAdd(&cnt3[1][rj], 1);
       if (is_surf) atomicAdd(&cnt3[3][rj], 1);
     }
@@ -704,28 +713,25 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       const int i = k * SR_THREADS + tid;
       const bool in = i < m_all;
       const int p12 = fs.pos(k, (m >> k) & 1u, (m >> (16 + k)) & 1u);
+      const int p3 = fs2.pos(k, (m3 >> k) & 1u) & 0xFFFF;
       const int p1 = p12 & 0xFFFF, p2 = p12 >> 16;
       if (in) {
-        qfa[i] = (unsigned short)p1; qfb[i] = (unsigned short)p2;
+        qfa[i] = (unsigned short)p1; qfb[i] = (unsigned short)p2; qfc[i] = (unsigned short)p3;
         const int rj = region_of(ord[i]);
-        if (i == nf_begin[rj]) { start3[0][rj] = p1; start3[1][rj] = p2; }
+        if (i == nf_begin[rj]) { start3[0][rj] = p1; start3[1][rj] = p2; start3[2][rj] = p3; }
       }
     }
   }
   __syncthreads();
-  // flat emissions of pass 3: ONESIDE_FLAT while the shared counter (bumped by SURFACE_FLAT too) is below the cap: at most
-  // max_flat per region, found by walking the first surf elements of the region (tiny: one thread per region)
+  for (int i = tid; i < m_all; i += SR_THREADS) {   // ONESIDE_FLAT among the first max_flat surf elements of its region
+    const int c = ord[i];
+    if (lab[c] == L_ONESIDE_FLAT) {
+      const int rj = region_of(c);
+      if ((int)qfb[i] - start3[1][rj] < prm.max_flat) atomicAdd(&cnt3[2][rj], 1);
+    }
+  }
   if (tid < NR) {
     const int j = tid;
-    int nflat = 0;
-    if (reg_ep[j] >= 0) {
-      int seen = 0;
-      for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
-        const int l = lab[ord[i]];
-        if (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT) { if (l == L_ONESIDE_FLAT) nflat++; seen++; }
-      }
-    }
-    cnt3[2][j] = nflat;
     cnt2[2][j] = p1_begin[j + 1] - p1_begin[j];
     cnt3[0][j] = cnt3[1][j] < prm.max_sharp ? cnt3[1][j] : prm.max_sharp;
   }
@@ -761,18 +767,17 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       lst[3][base[3][rj] + cnt2[3][rj] + o] = (unsigned short)c;
     }
   }
-  if (tid < NR) {   // flat list: pass-1 picks, then the ONESIDE_FLAT picks of pass 3
+  for (int i = tid; i < m_all; i += SR_THREADS) {   // flat list, pass-3 part: after the region's pass-1 picks, in `ord` order
+    const int c = ord[i];
+    if (lab[c] == L_ONESIDE_FLAT) {
+      const int rj = region_of(c);
+      if ((int)qfb[i] - start3[1][rj] < prm.max_flat) lst[2][base[2][rj] + cnt2[2][rj] + (int)qfc[i] - start3[2][rj]] = (unsigned short)c;
+    }
+  }
+  if (tid < NR) {   // flat list, pass-1 picks (at most max_flat per region)
     const int j = tid;
     int o = base[2][j];
     for (int i = p1_begin[j]; i < p1_begin[j + 1]; i++) lst[2][o++] = p1buf[i];
-    if (reg_ep[j] >= 0) {
-      int seen = 0;
-      for (int i = nf_begin[j]; i < nf_begin[j + 1] && seen < prm.max_flat; i++) {
-        const int c = ord[i];
-        const int l = lab[c];
-        if (l == L_SURFACE_FLAT || l == L_ONESIDE_FLAT) { if (l == L_ONESIDE_FLAT) lst[2][o++] = (unsigned short)c; seen++; }
-      }
-    }
   }
   __syncthreads();
 
