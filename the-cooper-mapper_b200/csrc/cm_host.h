@@ -157,6 +157,8 @@ struct MatchLaunch {
   int orig_idx;                               // grids carry original indices in pts[].w
   int max_queries = 0;                        // what the grids are sized for: n_corner[s] + n_surf[s] of the largest stream, exact or an
                                               // ESTIMATE (the kernels loop when a stream has more); 0: use the capacities
+  const int* skip = nullptr;                  // optional device flag: non-zero = the grids above were too small for some stream (estimate
+                                              // missed): every kernel of the match returns at once and the caller repeats it with exact sizes
   int bound_queries = 0;                      // host-known UPPER BOUND of n_corner[s] + n_surf[s]: sizes the scratch (0: max_queries)
   const float* own_box = nullptr;             // device {lo[3], hi[3]}: evaluate only queries inside (sharded map), else all
   void* hard = nullptr;                       // optional device list of deferred "hard" queries (hard_cap * CM_HARD_ITEM_BYTES)
@@ -247,6 +249,8 @@ struct VoxelFilter {
             int max_n, int* d_overflow, cudaStream_t stream);
 };
 
+void launch_step_guard(const int* d_n2, int nstreams, int max_c, int max_s, int* d_flag, cudaStream_t stream);
+
 // Small parameter uploads without the copy engine: `pinned` is device-accessible pinned host memory, a kernel reads it over
 // PCIe and writes `d_dst`.  (cm_map.cu)
 void staged_upload(void* d_dst, const void* pinned, size_t bytes, cudaStream_t stream);
@@ -278,7 +282,10 @@ struct DeviceMap {
   // h_windows == NULL: the windows on the device are still current (only the views are refreshed)
   void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream, bool staged = false);
   // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
-  void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream);
+  // max_n: what the launches are sized for (an estimate is fine: if a stream has more, the insert does nothing and sets flags[4 + cls]);
+  // step_skip: optional device flag, non-zero = insert nothing (the caller is about to repeat the step)
+  void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream,
+              const int* step_skip = nullptr);
   size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);
 };
 

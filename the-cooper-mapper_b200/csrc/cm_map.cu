@@ -39,11 +39,23 @@ struct GroupEntry { unsigned long long key; int head; int tail; };
 // The launch sizes of an insert come from an ESTIMATE of the per-stream counts (they live on the device).  If a stream has
 // more points than the estimate, the whole insert is skipped (every kernel below tests the flag first) and the host, which sees
 // the flag with the step's results, repeats it with exact sizes: nothing is ever inserted partially.
-__global__ void map_insert_guard_kernel(const int* __restrict__ n_pts, int nstreams, int max_n, int* __restrict__ skip) {
-  int over = 0;
+__global__ void map_insert_guard_kernel(const int* __restrict__ n_pts, int nstreams, int max_n, int* __restrict__ skip,
+                                        const int* __restrict__ step_skip) {
+  int over = (step_skip && *step_skip) ? 1 : 0;   // the whole step is being repeated: insert nothing
   for (int s = threadIdx.x; s < nstreams; s += blockDim.x) over |= n_pts[s] > max_n ? 1 : 0;
   over = __syncthreads_or(over);
   if (threadIdx.x == 0) *skip = over;
+}
+
+// flags the step when a stream's filtered clouds exceed what the step's launches were sized for (cm_mapping.cu)
+__global__ void step_guard_kernel(const int* __restrict__ n2, int nstreams, int max_c, int max_s, int* __restrict__ flag) {
+  int over = 0;
+  for (int s = threadIdx.x; s < nstreams; s += blockDim.x) over |= (n2[s] > max_c || n2[nstreams + s] > max_s) ? 1 : 0;
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) *flag = over;
+}
+void launch_step_guard(const int* d_n2, int nstreams, int max_c, int max_s, int* d_flag, cudaStream_t stream) {
+  CM_LAUNCH(step_guard_kernel, 1, 256, 0, stream, d_n2, nstreams, max_c, max_s, d_flag);
 }
 
 __global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap, const int* __restrict__ skip) {
@@ -341,7 +353,7 @@ void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_
 }
 
 void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const int* step_skip) {
   if (cap <= 0) return;
   if (max_n <= 0 || max_n > cap) max_n = cap;   // host-known upper bound of d_n[s]
   const size_t n = (size_t)nstreams * max_n;
@@ -353,7 +365,7 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   const unsigned int nb = (unsigned int)((n + 255) / 256);
   const int* skip = (const int*)flags.p + 4 + cls;   // flags[4 + cls]: this class' insert was skipped (a count exceeded max_n)
   cudaMemsetAsync(n_pending[cls].p, 0, sizeof(unsigned int), stream);
-  CM_LAUNCH(map_insert_guard_kernel, 1, 256, 0, stream, d_n, nstreams, max_n, (int*)flags.p + 4 + cls);
+  CM_LAUNCH(map_insert_guard_kernel, 1, 256, 0, stream, d_n, nstreams, max_n, (int*)flags.p + 4 + cls, step_skip);
   CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b[cls].p, gcap, skip);
   CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world[cls].p,
             (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p, skip);

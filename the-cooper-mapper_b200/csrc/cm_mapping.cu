@@ -219,7 +219,6 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   static const bool no_graph = getenv("COOPERMAP_NO_GRAPH") != nullptr;
   const bool use_graphs = !no_graph && !g_timeline.on;
   auto P = [](const void* p) { return (unsigned long long)(uintptr_t)p; };
-  auto FB = [](float v) { unsigned int u; memcpy(&u, &v, 4); return (unsigned long long)u; };
   // both classes of every stream in one launch (one CTA per cloud); the counts never leave the device
   ctx->voxel.run2(S, d_corner, d_n, cap_c, cfg.filter_corner, (float4*)ctx->m_corner_ds.p, d_nds, cap_c,
                   d_surf, d_n + S, cap_s, cfg.filter_surf, (float4*)ctx->m_surf_ds.p, d_nds + S, cap_s,
@@ -237,6 +236,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   int max_c = estimate(ctx->est_c, bound_c, 256), max_s = estimate(ctx->est_s, bound_s, 1024);
   if (getenv("COOPERMAP_TEST_UNDERESTIMATE")) { max_c = std::min(max_c, 64); max_s = std::min(max_s, 256); }   // tests: force the overflow paths
   const int max_q = std::min(max_c + max_s, bound_c + bound_s);
+  launch_step_guard(d_nds, S, max_c, max_s, (int*)ctx->map.flags.p + 6, st);
   // prepareFeatureSurround: cube window -> searchable views
   {
     // the window only changes when a sensor crosses a cube face: skip the upload when the device copy is current
@@ -261,6 +261,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.pose_in = (const float*)ctx->m_pose.p; m.state = (MatchState*)ctx->m_state.p; m.rows = (RowOut*)ctx->m_rows.p; m.nn_slot = (int*)ctx->m_slots.p;
   m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm;
   m.max_queries = max_q; m.bound_queries = bound_c + bound_s;
+  m.skip = (const int*)ctx->map.flags.p + 6;   // set by launch_step_guard below when an estimate was too small
   // capacities from the bound, in whole 256-query tiles: the Gauss-Newton graph key then repeats from frame to frame
   ctx->hardq.attach(m, (size_t)S * (size_t)(((m.bound_queries + 32 + 255) / 256) * 256));
   if (ctx->dbg_on) {
@@ -292,8 +293,9 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(aux, ctx->aux_fork, 0));
     const int ic_r = max_c, is_r = max_s;
-    auto ins_c = [&]() { ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, ic_r, (const MatchState*)ctx->m_state.p, nullptr, aux); };
-    auto ins_s = [&]() { ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, is_r, (const MatchState*)ctx->m_state.p, nullptr, st); };
+    const int* step_skip = (const int*)ctx->map.flags.p + 6;
+    auto ins_c = [&]() { ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, ic_r, (const MatchState*)ctx->m_state.p, nullptr, aux, step_skip); };
+    auto ins_s = [&]() { ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, is_r, (const MatchState*)ctx->m_state.p, nullptr, st, step_skip); };
     if (use_graphs) {
       ctx->stage_graphs.run({3, (unsigned long long)S, P(ctx->m_corner_ds.p), P(d_nds), (unsigned long long)cap_c, (unsigned long long)ic_r, P(ctx->m_state.p), P(aux)}, aux, ins_c);
       CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_join, aux));
@@ -318,11 +320,19 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     int act_c = 1, act_s = 1;
     for (int s = 0; s < S; s++) { act_c = std::max(act_c, nds[s]); act_s = std::max(act_s, nds[S + s]); }
     ctx->est_c = act_c; ctx->est_s = act_s;
-    if (!localise && (flags[4] || flags[5])) {
-      // a stream had more filtered points than the insert was launched for: that class' insert did nothing; repeat it exactly
+    if (flags[6]) {
+      // a stream had more filtered points than this step's launches were sized for: the Gauss-Newton kernels and the map
+      // insertion saw the flag and did nothing.  Repeat both with exact sizes (launch by launch: this is the rare path).
       ++ctx->insert_redos;
-      if (flags[4]) ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, std::min(cap_c, act_c), (const MatchState*)ctx->m_state.p, nullptr, st);
-      if (flags[5]) ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, std::min(cap_s, act_s), (const MatchState*)ctx->m_state.p, nullptr, st);
+      CM_CUDA_CHECK(ctx, cudaMemsetAsync((int*)ctx->map.flags.p + 4, 0, sizeof(int) * 3, st));
+      m.max_queries = std::min(act_c, cap_c) + std::min(act_s, cap_s);
+      m.skip = nullptr;
+      launch_match(m, st, &ctx->prof);
+      if (!localise) {
+        ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, std::min(cap_c, act_c), (const MatchState*)ctx->m_state.p, nullptr, st);
+        ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, std::min(cap_s, act_s), (const MatchState*)ctx->m_state.p, nullptr, st);
+      }
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
       CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
       CM_CUDA_CHECK(ctx, cudaGetLastError());

@@ -100,6 +100,7 @@ struct CorrArgs {
   const int* iter_dev;                        // optional: the evaluation index lives in device memory (graph WHILE loop); hard_count is then the row base
   int iter;                                   // the evaluation index when iter_dev is NULL
   int warm;                                   // 1: warm-start the 5-NN lists from the previous iteration (COOPERMAP_NO_WARM=1: off)
+  const int* skip;                            // optional: non-zero = do nothing (MatchLaunch::skip)
   void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
   MatchParamsDev prm;
 };
@@ -246,7 +247,7 @@ template <bool kOrigIdx>
 __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kernel(CorrArgs a) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
-  if (st.done) return;
+  if (st.done || (a.skip && *a.skip)) return;
   __shared__ float sR[9], sT[3];
   __shared__ uint4 rng[8 * CM_SEARCH_THREADS];
   if (threadIdx.x < 9) sR[threadIdx.x] = st.R[threadIdx.x];
@@ -256,70 +257,71 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   const int nT = ((nC + 31) & ~31) + nS;
   const int it = a.iter_dev ? *a.iter_dev : a.iter;
   const unsigned int FULL = 0xffffffffu;
-  // the grid is sized from an ESTIMATE of the filtered feature counts (they never leave the device): a stream with more
-  // queries than the grid has threads simply loops
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; (t & ~31) < nT; t += gridDim.x * blockDim.x) {
-    unsigned long long t0 = 0;
-    if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    bool in_range, isCorner; int row;
-    float sx, sy, sz;
-    bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
-    const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
-    Top5 best;
-    top5_init(best);
-    KnnGeom c;
-    valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
-    bool need = false;
-    unsigned int ncand = 0;
-    // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
-    const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
-    if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
-    unsigned int hard = __ballot_sync(FULL, need);
-    if (a.dbg && t < (int)(gridDim.x * blockDim.x)) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      const unsigned int mx = __reduce_max_sync(FULL, ncand), sm = __reduce_add_sync(FULL, ncand);
-      if ((threadIdx.x & 31) == 0) {
-        unsigned long long* d = a.dbg + 4 * ((size_t)(s * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
-        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        d[0] = t0; d[1] = t1; d[2] = ((unsigned long long)mx << 32) | sm;
-        d[3] = ((unsigned long long)__popc(hard) << 32) | ((unsigned long long)smid << 16) | (isCorner ? 1u : 0u);
-      }
+  // (the grid may be sized from an ESTIMATE of the filtered feature counts: the caller checks on the device that no stream
+  // exceeded it and repeats the match otherwise -- a grid-stride loop here cost 25 % of the kernel in spills)
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t & ~31) >= nT) return;   // whole warp idle
+  unsigned long long t0 = 0;
+  if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  bool in_range, isCorner; int row;
+  float sx, sy, sz;
+  bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
+  const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
+  Top5 best;
+  top5_init(best);
+  KnnGeom c;
+  valid = knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0) && valid;
+  bool need = false;
+  unsigned int ncand = 0;
+  // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
+  const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
+  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
+  unsigned int hard = __ballot_sync(FULL, need);
+  if (a.dbg) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const unsigned int mx = __reduce_max_sync(FULL, ncand), sm = __reduce_add_sync(FULL, ncand);
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* d = a.dbg + 4 * ((size_t)(s * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
+      unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      d[0] = t0; d[1] = t1; d[2] = ((unsigned long long)mx << 32) | sm;
+      d[3] = ((unsigned long long)__popc(hard) << 32) | ((unsigned long long)smid << 16) | (isCorner ? 1u : 0u);
     }
-    if (a.hard) {
-      // deferred: one warp-aggregated reservation, every hard lane writes its own item
-      if (hard) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(a.iter_dev ? a.hard_count + it : a.hard_count, __popc(hard));
-        base = __shfl_sync(FULL, base, 0);
-        if (need) {
-          const int pos = base + __popc(hard & ((1u << lane) - 1));
-          if (pos < a.hard_cap) {
-            HardItem item;
-            item.s = s; item.t = t; item.pad = 0;
+  }
+  if (a.hard) {
+    // deferred: one warp-aggregated reservation, every hard lane writes its own item
+    if (hard) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(a.iter_dev ? a.hard_count + it : a.hard_count, __popc(hard));
+      base = __shfl_sync(FULL, base, 0);
+      if (need) {
+        const int pos = base + __popc(hard & ((1u << lane) - 1));
+        if (pos < a.hard_cap) {
+          HardItem item;
+          item.s = s; item.t = t; item.pad = 0;
 #pragma unroll
-            for (int k = 0; k < 5; k++) { item.d[k] = best.d(k); item.idx[k] = best.idx(k); item.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
-            reinterpret_cast<HardItem*>(a.hard)[pos] = item;
-          }
+          for (int k = 0; k < 5; k++) { item.d[k] = best.d(k); item.idx[k] = best.idx(k); item.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
+          reinterpret_cast<HardItem*>(a.hard)[pos] = item;
         }
       }
-      if (!in_range || need) continue;
-    } else {
-      while (hard) {
-        const int h = __ffs(hard) - 1;
-        hard &= hard - 1;
-        knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
-      }
-      if (!in_range) continue;
     }
-    search_store<kOrigIdx>(a, s, row, valid && best.d(4) < a.prm.knn_gate, best);
+    if (!in_range || need) return;
+  } else {
+    while (hard) {
+      const int h = __ffs(hard) - 1;
+      hard &= hard - 1;
+      knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
+    }
+    if (!in_range) return;
   }
+  search_store<kOrigIdx>(a, s, row, valid && best.d(4) < a.prm.knn_gate, best);
 }
 
 // K5a': the hard queries of one Gauss-Newton evaluation, one warp per query (grid-stride over the list).
 template <bool kOrigIdx>
 __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
+  if (a.skip && *a.skip) return;
   const int n = min(a.iter_dev ? a.hard_count[*a.iter_dev] : *a.hard_count, a.hard_cap);
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -417,6 +419,7 @@ struct SolveArgs {
   IterTrace* trace;   // optional [nstreams][max_iterations]
   int iter;
   const int* iter_dev;   // optional: overrides iter (graph WHILE loop)
+  const int* skip;       // optional: non-zero = do nothing (MatchLaunch::skip)
   MatchParamsDev prm;
 };
 
@@ -595,7 +598,7 @@ struct FusedArgs { double* partials; int* tickets; double* sums; int ptiles; /* 
 __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a, FusedArgs f) {
   const int s = blockIdx.y;
   const MatchState& st = a.state[s];
-  if (st.done) return;
+  if (st.done || (a.skip && *a.skip)) return;
   const int nC = a.n_corner[s], nS = a.n_surf[s];
   const int capQ = a.cap_corner + a.cap_surf;
   // tiles of 256 query slots.  The grid comes from an estimate of the filtered counts; a CTA takes tiles blockIdx.x,
@@ -683,6 +686,7 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
 
 // K6b for the fused path: one warp per stream (streams diverge: degenerate / first-iteration branches), lane 0 works
 __global__ void __launch_bounds__(32) solve_warp_kernel(SolveArgs a, const double* __restrict__ sums) {
+  if (a.skip && *a.skip) return;
   if (threadIdx.x == 0) solve_stream(a, blockIdx.x, sums + (size_t)blockIdx.x * 32);
 }
 
@@ -751,7 +755,7 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
   ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr; ca.iter_dev = nullptr; sa.iter_dev = nullptr;
   static const int warm = getenv("COOPERMAP_NO_WARM") ? 0 : 1;
-  ca.iter = 0; ca.warm = warm;
+  ca.iter = 0; ca.warm = warm; ca.skip = m.skip; sa.skip = m.skip;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
@@ -834,11 +838,13 @@ void launch_match(const MatchLaunch& m, cudaStream_t stream, KernelProfiler* pro
 }
 
 // Last node of the WHILE body: next evaluation index, loop again while some stream is still iterating.
-__global__ void gn_advance_kernel(cudaGraphConditionalHandle handle, int* iter, const MatchState* state, int nstreams, int max_iterations) {
+__global__ void gn_advance_kernel(cudaGraphConditionalHandle handle, int* iter, const MatchState* state, int nstreams, int max_iterations,
+                                  const int* skip) {
   const int it = *iter + 1;
   *iter = it;
   int active = 0;
   for (int s = 0; s < nstreams; s++) active |= state[s].done ? 0 : 1;
+  if (skip && *skip) active = 0;
   cudaGraphSetConditional(handle, (active && it < max_iterations) ? 1u : 0u);
 }
 
@@ -893,7 +899,7 @@ static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cuda
     if (ok) {
       const unsigned long long b0 = g_launch_count;
       launch_match_body(m, d_iter, stream);
-      CM_LAUNCH(gn_advance_kernel, 1, 1, 0, stream, handle, d_iter, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations);
+      CM_LAUNCH(gn_advance_kernel, 1, 1, 0, stream, handle, d_iter, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations, m.skip);
       *launches_per_eval = g_launch_count - b0;
       ok = cudaStreamEndCapture(stream, &tmp) == cudaSuccess;
     }
@@ -915,7 +921,7 @@ static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
   P(m.pose_in); P(m.state); P(m.rows); P(m.nn_slot); P(m.sums); P(m.trace); P(m.nn); I(m.orig_idx);
   const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
   I((maxq + 32 + 255) / 256);   // the grids depend on max_queries only through this
-  P(m.own_box); P(m.hard); P(m.hard_count); I(m.hard_cap); I(m.hard_blocks); P(m.partials); P(m.tickets); I(m.partial_blocks);
+  P(m.own_box); P(m.skip); P(m.hard); P(m.hard_count); I(m.hard_cap); I(m.hard_blocks); P(m.partials); P(m.tickets); I(m.partial_blocks);
   I(m.prm.max_iterations); F(m.prm.delta_t_abort); F(m.prm.delta_r_abort); F(m.prm.knn_gate); F(m.prm.plane_max_dist);
   I(m.prm.min_ref_corner); I(m.prm.min_ref_surf); I(m.prm.min_rows); F(m.prm.eig_threshold); I(m.prm.few_rows_continue);
   I(m.prm.own_cube_only); I(m.prm.nan_guard);

@@ -574,19 +574,18 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       if (lane == 0) p1_begin[j] = np1;
       if (ep >= 0) {
         for (int k = 0; k < prm.max_flat; k++) {
-          // arg-min on (curvature, index): the lane keeps its first smallest cell (ascending c, strict <), the warp the smaller index on ties
-          float bv = __int_as_float(0x7f800000); int bc = 0x7fffffff;
+          unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
           for (int c = sp + lane; c <= ep; c += 32) {
             const float cv = curv[c];
-            if (cv < prm.curv_thr && cv < bv && state[c] != P_SURF_PICKED_NEAR) { bv = cv; bc = c; }
+            if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) {
+              const unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned int)c;
+              best = kk < best ? kk : best;
+            }
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
-          }
-          if (bc == 0x7fffffff) break;
-          const int c = bc;
+          for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y < best ? y : best; }
+          if (best == 0xFFFFFFFFFFFFFFFFull) break;
+          const int c = (int)(best & 0xFFFFFFFFu);
           __syncwarp();   // every lane has finished reading state[] (the shuffles order execution, this orders memory)
           if (lane <= 2 * R) state[c - R + lane] = P_SURF_PICKED_NEAR;   // markAsPicked: c-R .. c+R
           if (lane == 0 && np1 < SR_MAXREG * 8) p1buf[np1] = (unsigned short)c;
