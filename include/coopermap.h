@@ -298,6 +298,9 @@ int cm_match_local_host(cm_ctx* ctx, const cm_point* ref_corner, size_t n_ref_co
  * the following cm_pipeline_step / cm_mapping_process calls (iter < 0: off).  4 words per warp: start ns, end ns,
  * (max << 32 | sum) level-0 candidates over the lanes, (hard queries << 32 | smid << 16 | is_corner). */
 int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out4);   /* {Gauss-Newton loop graphs built, insert chain captures, insert repeats, 0} */
+int cm_debug_read_slots(cm_ctx* ctx, int* out, size_t n_ints);                                      /* neighbour pool slots of the last mapping step */
+int cm_debug_read_queries(cm_ctx* ctx, int cls, float* out, size_t n_floats, int* counts);          /* its filtered query clouds */
+int cm_debug_read_map_points(cm_ctx* ctx, int stream_index, int cls, const int* slots, int n, float* out4);   /* map points by pool slot */
 int cm_debug_graph_info(cm_ctx* ctx, int* n_graphs, int* while_loop);   /* CUDA graphs cached for the Gauss-Newton loop; 1 = WHILE-node graphs */
 int cm_debug_search_trace_enable(cm_ctx* ctx, int iter);
 int cm_debug_search_trace_read(cm_ctx* ctx, unsigned long long* out, size_t cap_words, size_t* n_words);

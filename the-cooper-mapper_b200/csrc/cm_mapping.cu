@@ -843,6 +843,32 @@ int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out4) {
   out4[0] = ctx->match_graphs.builds; out4[1] = ctx->stage_graphs.captures; out4[2] = ctx->insert_redos; out4[3] = 0;
   return CM_OK;
 }
+/* development aids: the neighbour slots (5 per query row, [stream][cap_corner + cap_surf][5]) the last mapping step's final search
+ * left behind, the filtered query clouds, and map points by pool slot */
+int cm_debug_read_slots(cm_ctx* ctx, int* out, size_t n_ints) {
+  if (!ctx || !out) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  CM_CUDA_CHECK(ctx, cudaMemcpy(out, ctx->m_slots.p, std::min(n_ints * sizeof(int), ctx->m_slots.cap), cudaMemcpyDeviceToHost));
+  return CM_OK;
+}
+int cm_debug_read_queries(cm_ctx* ctx, int cls, float* out, size_t n_floats, int* counts) {
+  if (!ctx || !out || cls < 0 || cls > 1) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  cm::DeviceBuffer& b = cls == 0 ? ctx->m_corner_ds : ctx->m_surf_ds;
+  CM_CUDA_CHECK(ctx, cudaMemcpy(out, b.p, std::min(n_floats * sizeof(float), b.cap), cudaMemcpyDeviceToHost));
+  if (counts) CM_CUDA_CHECK(ctx, cudaMemcpy(counts, (const int*)ctx->m_n_ds.p + cls * ctx->map_streams, sizeof(int) * ctx->map_streams, cudaMemcpyDeviceToHost));
+  return CM_OK;
+}
+int cm_debug_read_map_points(cm_ctx* ctx, int stream_index, int cls, const int* slots, int n, float* out4) {
+  if (!ctx || !slots || !out4 || cls < 0 || cls > 1 || stream_index < 0 || stream_index >= ctx->map_streams) return CM_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  const float4* pool = (const float4*)ctx->map.pts[cls].p + (size_t)stream_index * ctx->map.pool_cap[cls];
+  for (int i = 0; i < n; i++) {
+    if (slots[i] < 0 || (unsigned int)slots[i] >= ctx->map.pool_cap[cls]) { out4[4 * i] = out4[4 * i + 1] = out4[4 * i + 2] = out4[4 * i + 3] = nanf(""); continue; }
+    CM_CUDA_CHECK(ctx, cudaMemcpy(out4 + 4 * i, pool + slots[i], sizeof(float4), cudaMemcpyDeviceToHost));
+  }
+  return CM_OK;
+}
 int cm_prof_enable(cm_ctx* ctx, int on) { if (!ctx) return CM_ERR_ARG; ctx->prof.enabled = ctx->prof_sr.enabled = on != 0; return CM_OK; }
 int cm_prof_drain_scanreg(cm_ctx* ctx, double* kernel_ms, int* launches) {
   if (!ctx || !kernel_ms) return CM_ERR_ARG;

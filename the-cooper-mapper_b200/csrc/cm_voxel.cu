@@ -28,17 +28,19 @@ namespace cm {
 #define VS_T 1024
 #define VS_WARPS (VS_T / 32)
 #define VS_PAD 0xFFFFFFFFu
+#define VS_RC 16384          // runs whose sort buffers fit in shared memory (2 x u32 keys + 2 x u16 values = 192 KB)
+#define VS_ARRAYS 7          // scratch arrays per segment: key A / B, value A / B, run start, run end, point order
 
 struct VoxClass {            // one batch of segments filtered with one leaf
   const float4* in; const int* n_in; int cap_in;
   float inv;                 // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
   float4* out; int* n_out; int cap_out;
-  unsigned int* scratch;     // [nseg][6][stride]: key A / B, value A / B, run start, run end
+  unsigned int* scratch;     // [nseg][VS_ARRAYS][stride]
 };
 struct VoxSegArgs {
   VoxClass cls[2];
   int nseg, ncls;
-  unsigned int stride;       // scratch entries per array and segment (>= the largest n_in)
+  unsigned int stride;       // scratch entries per array and segment (> the largest n_in)
   int* overflow;             // optional flag: an output exceeded cap_out (or an input the scratch stride)
   VoxBox* box_out;           // optional [ncls][nseg]: the bounding boxes (diagnostics)
 };
@@ -53,6 +55,88 @@ __device__ __forceinline__ unsigned int vox_index_of(const float4& q, const VoxB
   return (unsigned int)(ijk0 + ijk1 * b.mul1 + ijk2 * b.mul2);
 }
 
+struct VoxShared {
+  VoxBox box;
+  float red[VS_WARPS][6];
+  int redn[VS_WARPS];
+  unsigned int idx[VS_T + 2];
+  unsigned int carry;
+  int wt[2][VS_WARPS];
+  int wl[2][VS_WARPS];
+  unsigned int hist[4][256];
+  unsigned int digit[256];
+  unsigned int wsum[8];
+  unsigned short gsum[4][256];
+  unsigned char wcnt[VS_WARPS][256];
+};
+
+// Stable LSD radix sort of (key, value) pairs by the low 8 * npass key bits, ping-pong between buffers 0 and 1 (in shared or
+// global memory: generic pointers).  Pass 0 takes value r for item r (the identity), so the caller fills key[0] only.
+// Returns the buffer that holds the result.  hist[p] = digit histogram of pass p (filled by the caller).
+template <typename V>
+__device__ __forceinline__ int vox_lsd_sort(VoxShared& sh, unsigned int* key0, unsigned int* key1, V* val0, V* val1, unsigned int nruns, int npass) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
+  int cur = 0;
+  for (int p = 0; p < npass; p++) {
+    const int shift = 8 * p;
+    if (tid < 256) {   // exclusive scan of the digit histogram
+      const unsigned int v = sh.hist[p][tid];
+      unsigned int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (lane == 31) sh.wsum[warp] = x;
+      sh.digit[tid] = x - v;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      unsigned int add = 0;
+      for (int w = 0; w < warp; w++) add += sh.wsum[w];
+      sh.digit[tid] += add;
+    }
+    // (the first barrier of the tile loop orders these writes before their first use)
+    const unsigned int* sk = cur ? key1 : key0; const V* sv = cur ? val1 : val0;
+    unsigned int* dk = cur ? key0 : key1; V* dv = cur ? val0 : val1;
+    for (unsigned int t0 = 0; t0 < nruns; t0 += VS_T) {
+      const unsigned int r = t0 + tid;
+      const bool ok = r < nruns;
+      const unsigned int key = ok ? sk[r] : 0u;
+      const unsigned int val = ok ? (p == 0 ? r : (unsigned int)sv[r]) : 0u;
+      const unsigned int d = ok ? ((key >> shift) & 255u) : (256u + (unsigned int)lane);
+#pragma unroll
+      for (int q = 0; q < 2; q++) reinterpret_cast<unsigned int*>(&sh.wcnt[0][0])[tid + q * VS_T] = 0u;
+      __syncthreads();
+      const unsigned int m = __match_any_sync(0xffffffffu, d);
+      const unsigned int rank_w = __popc(m & lt);
+      if (ok && rank_w == 0) sh.wcnt[warp][d] = (unsigned char)__popc(m);   // <= 32
+      __syncthreads();
+      {   // per digit: exclusive prefix over the 32 warps, four threads per digit (8 warps each) + their group totals
+        const int d2 = tid & 255, g = tid >> 8;
+        unsigned int acc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned int c = sh.wcnt[g * 8 + w][d2]; sh.wcnt[g * 8 + w][d2] = (unsigned char)acc; acc += c; }   // acc <= 224 before the last add
+        sh.gsum[g][d2] = (unsigned short)acc;
+      }
+      __syncthreads();
+      if (ok) {
+        unsigned int pos = sh.digit[d] + sh.wcnt[warp][d] + rank_w;
+        const int g = warp >> 3;
+        if (g > 0) pos += sh.gsum[0][d];
+        if (g > 1) pos += sh.gsum[1][d];
+        if (g > 2) pos += sh.gsum[2][d];
+        dk[pos] = key; dv[pos] = (V)val;
+      }
+      __syncthreads();
+      if (tid < 256) sh.digit[tid] += (unsigned int)sh.gsum[0][tid] + sh.gsum[1][tid] + sh.gsum[2][tid] + sh.gsum[3][tid];
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
+extern __shared__ __align__(16) unsigned char vox_dyn_smem[];
+
 __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
   const int s = blockIdx.x, ci = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const VoxClass& k = a.cls[ci];
@@ -60,24 +144,15 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
   const float4* in = k.in + (size_t)s * k.cap_in;
   int n = k.n_in[s];
   if (n < 0) n = 0;
-  if ((unsigned int)n > a.stride) { n = (int)a.stride; if (tid == 0 && a.overflow) atomicExch(a.overflow, 1); }
-  unsigned int* base = k.scratch + (size_t)s * 6 * a.stride;
-  unsigned int* keyb[2] = {base, base + a.stride};
-  unsigned int* valb[2] = {base + 2 * (size_t)a.stride, base + 3 * (size_t)a.stride};
+  if ((unsigned int)n >= a.stride) { n = (int)a.stride - 1; if (tid == 0 && a.overflow) atomicExch(a.overflow, 1); }
+  unsigned int* base = k.scratch + (size_t)s * VS_ARRAYS * a.stride;
+  unsigned int* gkey0 = base; unsigned int* gkey1 = base + a.stride;
+  unsigned int* gval0 = base + 2 * (size_t)a.stride; unsigned int* gval1 = base + 3 * (size_t)a.stride;
   unsigned int* run_start = base + 4 * (size_t)a.stride;
   unsigned int* run_end = base + 5 * (size_t)a.stride;
+  unsigned int* order = base + 6 * (size_t)a.stride;
 
-  __shared__ VoxBox s_box;
-  __shared__ float s_red[VS_WARPS][6];
-  __shared__ int s_redn[VS_WARPS];
-  __shared__ unsigned int s_idx[VS_T + 2];
-  __shared__ unsigned int s_carry;
-  __shared__ int s_wt[2][VS_WARPS];
-  __shared__ unsigned int s_hist[4][256];
-  __shared__ unsigned int s_digit[256];
-  __shared__ unsigned int s_wsum[8];
-  __shared__ unsigned int s_gsum[4][256];
-  __shared__ unsigned short s_wcnt[VS_WARPS][256];
+  __shared__ VoxShared sh;
   const unsigned int lt = (1u << lane) - 1u;
 
   // ---- 1. bounding box (voxel_grid_partition.hpp:108-137) ------------------------------------------------------------
@@ -101,13 +176,13 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
       }
       nf += __shfl_xor_sync(0xffffffffu, nf, o);
     }
-    if (lane == 0) { for (int c = 0; c < 3; c++) { s_red[warp][c] = mn[c]; s_red[warp][3 + c] = mx[c]; } s_redn[warp] = nf; }
-    for (int q = tid; q < 4 * 256; q += VS_T) (&s_hist[0][0])[q] = 0u;
+    if (lane == 0) { for (int c = 0; c < 3; c++) { sh.red[warp][c] = mn[c]; sh.red[warp][3 + c] = mx[c]; } sh.redn[warp] = nf; }
+    for (int q = tid; q < 4 * 256; q += VS_T) (&sh.hist[0][0])[q] = 0u;
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < VS_WARPS; w++) {
-        for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], s_red[w][c]); mx[c] = fmaxf(mx[c], s_red[w][3 + c]); }
-        nf += s_redn[w];
+        for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], sh.red[w][c]); mx[c] = fmaxf(mx[c], sh.red[w][3 + c]); }
+        nf += sh.redn[w];
       }
       VoxBox b;
       b.nfinite = nf; b.passthrough = 0; b.cells = 1;
@@ -126,13 +201,13 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
         const long long span = (long long)d0 * d1 * (long long)(maxb[2] - b.minb[2] + 1);
         if (!b.passthrough && span > b.cells) b.cells = span;
       }
-      s_box = b;
+      sh.box = b;
       if (a.box_out) a.box_out[ci * a.nseg + s] = b;
-      s_carry = VS_PAD;
+      sh.carry = VS_PAD;
     }
     __syncthreads();
   }
-  const VoxBox box = s_box;
+  const VoxBox box = sh.box;
   int bits = 1;
   while (bits < 32 && (1LL << bits) < box.cells) bits++;
   const int npass = (bits + 7) / 8;
@@ -146,26 +221,26 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
       const int i = t0 + tid;
       unsigned int idx = VS_PAD;
       if (i < n) idx = vox_index_of(in[i], box, inv, (unsigned int)i);
-      s_idx[1 + tid] = idx;
+      sh.idx[1 + tid] = idx;
       if (tid == 0) {
-        s_idx[0] = s_carry;
+        sh.idx[0] = sh.carry;
         const int j = t0 + VS_T;
-        s_idx[1 + VS_T] = j < n ? vox_index_of(in[j], box, inv, (unsigned int)j) : VS_PAD;
+        sh.idx[1 + VS_T] = j < n ? vox_index_of(in[j], box, inv, (unsigned int)j) : VS_PAD;
       }
       __syncthreads();
       const bool valid = idx != VS_PAD;
-      const bool st = valid && s_idx[tid] != idx, en = valid && s_idx[tid + 2] != idx;
+      const bool st = valid && sh.idx[tid] != idx, en = valid && sh.idx[tid + 2] != idx;
       const unsigned int b0 = __ballot_sync(0xffffffffu, st), b1 = __ballot_sync(0xffffffffu, en);
-      if (lane == 0) s_wt[buf][warp] = __popc(b0) | (__popc(b1) << 16);
-      if (tid == VS_T - 1) s_carry = idx;
+      if (lane == 0) sh.wt[buf][warp] = __popc(b0) | (__popc(b1) << 16);
+      if (tid == VS_T - 1) sh.carry = idx;
       __syncthreads();
-      const int v = s_wt[buf][lane];
+      const int v = sh.wt[buf][lane];
       const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
       const int tot = __reduce_add_sync(0xffffffffu, v);
       const unsigned int ps = nruns + (before & 0xFFFF) + __popc(b0 & lt), pe = nends + (before >> 16) + __popc(b1 & lt);
       if (st) {
-        keyb[0][ps] = idx; valb[0][ps] = ps; run_start[ps] = (unsigned int)i;
-        for (int p = 0; p < npass; p++) atomicAdd(&s_hist[p][(idx >> (8 * p)) & 255u], 1u);
+        gkey0[ps] = idx; run_start[ps] = (unsigned int)i;
+        for (int p = 0; p < npass; p++) atomicAdd(&sh.hist[p][(idx >> (8 * p)) & 255u], 1u);
       }
       if (en) run_end[pe] = (unsigned int)i + 1u;
       nruns += (unsigned int)(tot & 0xFFFF); nends += (unsigned int)(tot >> 16);
@@ -174,106 +249,84 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
   }
   __syncthreads();
 
-  // ---- 3. stable LSD radix sort of the runs by voxel index ----------------------------------------------------------------
-  int cur = 0;
-  for (int p = 0; p < npass; p++) {
-    const int shift = 8 * p;
-    if (tid < 256) {   // exclusive scan of the digit histogram
-      const unsigned int v = s_hist[p][tid];
-      unsigned int x = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      if (lane == 31) s_wsum[warp] = x;
-      s_digit[tid] = x - v;
-    }
+  // ---- 3. stable LSD radix sort of the runs by voxel index: in shared memory when they fit, else in the global scratch -----
+  const unsigned int* sk; const void* sv; bool v16;
+  unsigned int* voff;   // start of every voxel's points in `order` (a free key buffer)
+  if (nruns <= VS_RC) {
+    unsigned int* k0 = reinterpret_cast<unsigned int*>(vox_dyn_smem); unsigned int* k1 = k0 + VS_RC;
+    unsigned short* v0 = reinterpret_cast<unsigned short*>(k1 + VS_RC); unsigned short* v1 = v0 + VS_RC;
+    for (unsigned int r = tid; r < nruns; r += VS_T) k0[r] = gkey0[r];
     __syncthreads();
-    if (tid < 256) {
-      unsigned int add = 0;
-      for (int w = 0; w < warp; w++) add += s_wsum[w];
-      s_digit[tid] += add;
-    }
-    // (the first barrier of the tile loop orders these writes before their first use)
-    const unsigned int* sk = keyb[cur]; const unsigned int* sv = valb[cur];
-    unsigned int* dk = keyb[cur ^ 1]; unsigned int* dv = valb[cur ^ 1];
-    for (unsigned int t0 = 0; t0 < nruns; t0 += VS_T) {
-      const unsigned int r = t0 + tid;
-      const bool ok = r < nruns;
-      const unsigned int key = ok ? sk[r] : 0u, val = ok ? sv[r] : 0u;
-      const unsigned int d = ok ? ((key >> shift) & 255u) : (256u + (unsigned int)lane);
-#pragma unroll
-      for (int q = 0; q < 4; q++) reinterpret_cast<unsigned int*>(&s_wcnt[0][0])[tid + q * VS_T] = 0u;
-      __syncthreads();
-      const unsigned int m = __match_any_sync(0xffffffffu, d);
-      const unsigned int rank_w = __popc(m & lt);
-      if (ok && rank_w == 0) s_wcnt[warp][d] = (unsigned short)__popc(m);
-      __syncthreads();
-      {   // per digit: exclusive prefix over the 32 warps, four threads per digit (8 warps each) + their group totals
-        const int d2 = tid & 255, g = tid >> 8;
-        unsigned int acc = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) { const unsigned int c = s_wcnt[g * 8 + w][d2]; s_wcnt[g * 8 + w][d2] = (unsigned short)acc; acc += c; }
-        s_gsum[g][d2] = acc;
-      }
-      __syncthreads();
-      if (ok) {
-        unsigned int pos = s_digit[d] + s_wcnt[warp][d] + rank_w;
-        const int g = warp >> 3;
-        if (g > 0) pos += s_gsum[0][d];
-        if (g > 1) pos += s_gsum[1][d];
-        if (g > 2) pos += s_gsum[2][d];
-        dk[pos] = key; dv[pos] = val;
-      }
-      __syncthreads();
-      if (tid < 256) s_digit[tid] += s_gsum[0][tid] + s_gsum[1][tid] + s_gsum[2][tid] + s_gsum[3][tid];
-    }
-    __syncthreads();
-    cur ^= 1;
+    const int cur = vox_lsd_sort<unsigned short>(sh, k0, k1, v0, v1, nruns, npass);
+    sk = cur ? k1 : k0; sv = cur ? (const void*)v1 : (const void*)v0; v16 = true;
+    if (npass == 0) { for (unsigned int r = tid; r < nruns; r += VS_T) v0[r] = (unsigned short)r; __syncthreads(); }
+    voff = gkey1;
+  } else {
+    const int cur = vox_lsd_sort<unsigned int>(sh, gkey0, gkey1, gval0, gval1, nruns, npass);
+    sk = cur ? gkey1 : gkey0; sv = cur ? (const void*)gval1 : (const void*)gval0; v16 = false;
+    if (npass == 0) { for (unsigned int r = tid; r < nruns; r += VS_T) gval0[r] = r; __syncthreads(); }
+    voff = cur ? gkey0 : gkey1;
   }
 
-  // ---- 4. voxel heads -> output rank -> centroid (runs in order, points of a run in order) -----------------------------------
-  const unsigned int* sk = keyb[cur]; const unsigned int* sv = valb[cur];
-  float4* out = k.out + (size_t)s * k.cap_out;
-  unsigned int nvox = 0;
+  // ---- 4. flatten: the points of every voxel, in (voxel, input) order, as one index list; voxel starts ------------------------
+  unsigned int nvox = 0, npts = 0;
   {
     int buf = 0;
     for (unsigned int t0 = 0; t0 < nruns; t0 += VS_T) {
       const unsigned int r = t0 + tid;
-      const unsigned int key = r < nruns ? sk[r] : VS_PAD;
-      const bool head = r < nruns && (r == 0 || sk[r - 1] != key);
+      const bool ok = r < nruns;
+      const unsigned int key = ok ? sk[r] : VS_PAD;
+      const bool head = ok && (r == 0 || sk[r - 1] != key);
+      unsigned int i0 = 0, len = 0;
+      if (ok) {
+        const unsigned int id = v16 ? (unsigned int)reinterpret_cast<const unsigned short*>(sv)[r] : reinterpret_cast<const unsigned int*>(sv)[r];
+        i0 = run_start[id]; len = run_end[id] - i0;
+      }
       const unsigned int b0 = __ballot_sync(0xffffffffu, head);
-      if (lane == 0) s_wt[buf][warp] = __popc(b0);
+      unsigned int x = len;   // inclusive warp scan of the run lengths
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (lane == 0) sh.wt[buf][warp] = __popc(b0);
+      if (lane == 31) sh.wl[buf][warp] = (int)x;
       __syncthreads();
-      const int v = s_wt[buf][lane];
-      const int before = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0);
-      const int tot = __reduce_add_sync(0xffffffffu, v);
-      if (head) {
-        const unsigned int pos = nvox + (unsigned int)before + __popc(b0 & lt);
-        float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
-        unsigned int cnt = 0;
-        for (unsigned int rr = r; rr < nruns && sk[rr] == key; rr++) {
-          const unsigned int id = sv[rr];
-          const unsigned int i0 = run_start[id], i1 = run_end[id];
-          // Eigen::VectorXf centroid += point, in sorted (= input) order; four loads in flight, the adds stay sequential
-          for (unsigned int i = i0; i < i1; i += 4) {
-            const unsigned int m = i1 - i;
-            const float4 q0 = in[i];
-            float4 q1, q2, q3;
-            if (m > 1) q1 = in[i + 1];
-            if (m > 2) q2 = in[i + 2];
-            if (m > 3) q3 = in[i + 3];
-            cx += q0.x; cy += q0.y; cz += q0.z; cw += q0.w;
-            if (m > 1) { cx += q1.x; cy += q1.y; cz += q1.z; cw += q1.w; }
-            if (m > 2) { cx += q2.x; cy += q2.y; cz += q2.z; cw += q2.w; }
-            if (m > 3) { cx += q3.x; cy += q3.y; cz += q3.z; cw += q3.w; }
-          }
-          cnt += i1 - i0;
+      const int vh = sh.wt[buf][lane], vl = sh.wl[buf][lane];
+      const int hbefore = __reduce_add_sync(0xffffffffu, lane < warp ? vh : 0), htot = __reduce_add_sync(0xffffffffu, vh);
+      const int lbefore = __reduce_add_sync(0xffffffffu, lane < warp ? vl : 0), ltot = __reduce_add_sync(0xffffffffu, vl);
+      const unsigned int off = npts + (unsigned int)lbefore + (x - len);
+      if (head) voff[nvox + (unsigned int)hbefore + __popc(b0 & lt)] = off;
+      for (unsigned int j = 0; j < len; j++) order[off + j] = i0 + j;
+      nvox += (unsigned int)htot; npts += (unsigned int)ltot;
+      buf ^= 1;
+    }
+    if (tid == 0) voff[nvox] = npts;
+  }
+  __syncthreads();
+
+  // ---- 5. centroids: eight lanes per voxel load its points together, the adds stay sequential in (voxel, input) order -------
+  float4* out = k.out + (size_t)s * k.cap_out;
+  {
+    const int sub = tid & 7;
+    for (unsigned int v0 = 0; v0 < nvox; v0 += VS_T / 8) {
+      const unsigned int v = v0 + (unsigned int)(tid >> 3);
+      unsigned int p0 = 0, np = 0;
+      if (v < nvox) { p0 = voff[v]; np = voff[v + 1] - p0; }
+      const unsigned int npmax = __reduce_max_sync(0xffffffffu, np);
+      float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
+      for (unsigned int b = 0; b < npmax; b += 8) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b + sub < np) q = in[order[p0 + b + sub]];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          const float x = __shfl_sync(0xffffffffu, q.x, jj, 8), y = __shfl_sync(0xffffffffu, q.y, jj, 8);
+          const float z = __shfl_sync(0xffffffffu, q.z, jj, 8), w = __shfl_sync(0xffffffffu, q.w, jj, 8);
+          if (b + jj < np) { cx += x; cy += y; cz += z; cw += w; }   // Eigen::VectorXf centroid += point, in sorted (= input) order
         }
-        const float c = (float)cnt;
-        if (pos < (unsigned int)k.cap_out) out[pos] = make_float4(cx / c, cy / c, cz / c, cw / c);
+      }
+      if (sub == 0 && v < nvox) {
+        const float c = (float)np;
+        if (v < (unsigned int)k.cap_out) out[v] = make_float4(cx / c, cy / c, cz / c, cw / c);
         else if (a.overflow) atomicExch(a.overflow, 1);
       }
-      nvox += (unsigned int)tot;
-      buf ^= 1;
     }
   }
   if (tid == 0) k.n_out[s] = nvox <= (unsigned int)k.cap_out ? (int)nvox : k.cap_out;
@@ -281,6 +334,12 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
 
 // number of key bits that index `cells` distinct voxel indices
 int vox_index_bits(long long cells) { int b = 1; while (b < 32 && (1LL << b) < cells) b++; return b; }
+
+#define VS_DYN_SMEM ((size_t)VS_RC * 12)
+static void vox_configure() {
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(vox_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_DYN_SMEM); done = true; }
+}
 
 static void fill_class(VoxClass& c, const float4* d_in, const int* d_n_in, int cap_in, float leaf, float4* d_out, int* d_n_out, int cap_out,
                        unsigned int* scratch) {
@@ -291,13 +350,14 @@ void VoxelFilter::run(int nseg, const float4* d_in, const int* d_n_in, int cap_i
                       int cap_out, int* d_overflow, cudaStream_t stream) {
   if (nseg <= 0 || cap_in <= 0) return;
   if (max_n <= 0 || max_n > cap_in) max_n = cap_in;   // host-known upper bound of n_in[s]: sizes the scratch
-  const size_t stride = ((size_t)max_n + 255) & ~(size_t)255;
-  scratch.reserve((size_t)nseg * 6 * stride * sizeof(unsigned int));
+  const size_t stride = ((size_t)max_n + 1 + 255) & ~(size_t)255;
+  scratch.reserve((size_t)nseg * VS_ARRAYS * stride * sizeof(unsigned int));
   VoxSegArgs a;
   fill_class(a.cls[0], d_in, d_n_in, cap_in, leaf, d_out, d_n_out, cap_out, (unsigned int*)scratch.p);
   a.cls[1] = a.cls[0];
   a.nseg = nseg; a.ncls = 1; a.stride = (unsigned int)stride; a.overflow = d_overflow; a.box_out = nullptr;
-  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 1), VS_T, 0, stream, a);
+  vox_configure();
+  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 1), VS_T, VS_DYN_SMEM, stream, a);
 }
 
 void VoxelFilter::run2(int nseg, const float4* d_in0, const int* d_n_in0, int cap_in0, float leaf0, float4* d_out0, int* d_n_out0, int cap_out0,
@@ -306,13 +366,14 @@ void VoxelFilter::run2(int nseg, const float4* d_in0, const int* d_n_in0, int ca
   if (nseg <= 0 || cap_in0 <= 0 || cap_in1 <= 0) return;
   const int capmax = cap_in0 > cap_in1 ? cap_in0 : cap_in1;
   if (max_n <= 0 || max_n > capmax) max_n = capmax;
-  const size_t stride = ((size_t)max_n + 255) & ~(size_t)255;
-  scratch.reserve((size_t)2 * nseg * 6 * stride * sizeof(unsigned int));
+  const size_t stride = ((size_t)max_n + 1 + 255) & ~(size_t)255;
+  scratch.reserve((size_t)2 * nseg * VS_ARRAYS * stride * sizeof(unsigned int));
   VoxSegArgs a;
   fill_class(a.cls[0], d_in0, d_n_in0, cap_in0, leaf0, d_out0, d_n_out0, cap_out0, (unsigned int*)scratch.p);
-  fill_class(a.cls[1], d_in1, d_n_in1, cap_in1, leaf1, d_out1, d_n_out1, cap_out1, (unsigned int*)scratch.p + (size_t)nseg * 6 * stride);
+  fill_class(a.cls[1], d_in1, d_n_in1, cap_in1, leaf1, d_out1, d_n_out1, cap_out1, (unsigned int*)scratch.p + (size_t)nseg * VS_ARRAYS * stride);
   a.nseg = nseg; a.ncls = 2; a.stride = (unsigned int)stride; a.overflow = d_overflow; a.box_out = nullptr;
-  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 2), VS_T, 0, stream, a);
+  vox_configure();
+  CM_LAUNCH(vox_segment_kernel, dim3(nseg, 2), VS_T, VS_DYN_SMEM, stream, a);
 }
 
 }  // namespace cm
