@@ -139,6 +139,62 @@ __device__ __forceinline__ bool cand_ok(const GridView& g, int filt, const float
   return i >= 0 && i < w.dims[0] && j >= 0 && j < w.dims[1] && k >= 0 && k < w.dims[2] && (i + j * w.dims[0] + k * w.dims[0] * w.dims[1]) == filt;
 }
 
+// ---- exact distance ties ----------------------------------------------------------------------------------------------------
+// Two map points at EXACTLY the same float distance from a query (about once per 30 sweeps and stream) must be ordered the way the
+// reference's clouds order them, or the neighbour list -- and with it the last bit of a pose -- would depend on the pool slots, i.e.
+// on the order in which atomics happened to append points.  For clouds handed in by the caller the list keys carry the original
+// index (the oracle's rule: ties by index).  For the device-resident map the rule is the order of the reference's surround cloud
+// (FeatureMap::getSurroundFeature, FeatureMap.h:256-265): cubes in (i, j, k) loop order, inside a cube pcl::VoxelGrid's output
+// order, i.e. by voxel index (z, then y, then x).  Evaluated only when a tie actually occurs.
+__device__ inline bool canon_less_map(const GridView& g, const float4 pa, int slot_a, const float4 pb, int slot_b) {
+  if (g.window) {
+    const CubeWindow& w = *g.window;
+    const int ia = (int)(roundf(pa.x / w.cube_size) + (float)w.origin[0]), ib = (int)(roundf(pb.x / w.cube_size) + (float)w.origin[0]);
+    if (ia != ib) return ia < ib;
+    const int ja = (int)(roundf(pa.y / w.cube_size) + (float)w.origin[1]), jb = (int)(roundf(pb.y / w.cube_size) + (float)w.origin[1]);
+    if (ja != jb) return ja < jb;
+    const int ka = (int)(roundf(pa.z / w.cube_size) + (float)w.origin[2]), kb = (int)(roundf(pb.z / w.cube_size) + (float)w.origin[2]);
+    if (ka != kb) return ka < kb;
+  }
+  const float za = floorf(pa.z * g.inv_leaf), zb = floorf(pb.z * g.inv_leaf);
+  if (za != zb) return za < zb;
+  const float ya = floorf(pa.y * g.inv_leaf), yb = floorf(pb.y * g.inv_leaf);
+  if (ya != yb) return ya < yb;
+  const float xa = floorf(pa.x * g.inv_leaf), xb = floorf(pb.x * g.inv_leaf);
+  if (xa != xb) return xa < xb;
+  return slot_a < slot_b;   // two points of one voxel and cube (a drifted centroid next to the resident one)
+}
+
+// Insert with canonical tie handling.  kOrigIdx lists are canonical by construction (the key's low word is the original index).
+// unique: the list may already hold this very point (warm start).
+template <bool kOrigIdx>
+__device__ __forceinline__ void top5_insert_canon(const GridView& g, Top5& t, float d, int idx, int slot, const float4& p, bool unique) {
+  const unsigned long long key = top5_key(d, idx);
+  if (kOrigIdx) {
+    if (unique) top5_insert_key_unique(t, key, slot); else top5_insert_key(t, key, slot);
+    return;
+  }
+  const unsigned int db = __float_as_uint(d);
+  const bool tie = db == (unsigned int)(t.key[0] >> 32) || db == (unsigned int)(t.key[1] >> 32) || db == (unsigned int)(t.key[2] >> 32) ||
+                   db == (unsigned int)(t.key[3] >> 32) || db == (unsigned int)(t.key[4] >> 32);
+  if (!tie) { top5_insert_key(t, key, slot); return; }
+  if (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3] || key == t.key[4]) return;   // the same point
+  bool c[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const unsigned int dk = (unsigned int)(t.key[k] >> 32);
+    c[k] = db < dk;
+    if (db == dk) { const int sk = t.idx(k); c[k] = canon_less_map(g, p, slot, __ldg(g.pts + sk), sk); }
+  }
+  if (!c[4]) return;
+  // new slot k = c_{k-1} ? old[k-1] : (c_k ? new : old[k])   (c is monotone: c_k implies c_{k+1})
+  t.key[4] = c[3] ? t.key[3] : key;
+  t.key[3] = c[2] ? t.key[2] : (c[3] ? key : t.key[3]);
+  t.key[2] = c[1] ? t.key[1] : (c[2] ? key : t.key[2]);
+  t.key[1] = c[0] ? t.key[0] : (c[1] ? key : t.key[1]);
+  t.key[0] = c[0] ? key : t.key[0];
+}
+
 // Squared distance from u (voxel units) to the slab [lo, hi) of a cell along one axis, 0 inside.
 __device__ __forceinline__ float slab_dist(float u, float lo, float hi) { float d = fmaxf(fmaxf(lo - u, u - hi), 0.f); return d; }
 
@@ -267,7 +323,8 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
 // correct start: the result is the exact top-5 of (cells scanned) U (start points), the same set either way.
 template <bool kOrigIdx>
 __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c, float qx, float qy, float qz, uint4* rng, Top5& best,
-                                            unsigned int* ncand = nullptr, const int* prev = nullptr) {
+                                            unsigned int* ncand = nullptr, const int* prev = nullptr, bool* tie_out = nullptr) {
+  bool tie = false;   // some candidate was at EXACTLY the distance of a list entry (map grids): the list order is then not canonical
   const int k = g.kdiv;
   const float kf = (float)k;
   const float leaf98 = 0.98f * (g.cell / kf);
@@ -288,7 +345,13 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
         if (cand_ok(g, c.filt, q[u])) {
           float dx = qx - q[u].x, dy = qy - q[u].y, dz = qz - q[u].z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          top5_insert_key_unique(best, top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]), sl[u]);
+          const unsigned long long kq = top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]);
+          if (!kOrigIdx) {
+            const unsigned int db = (unsigned int)(kq >> 32);
+            tie = tie || db == (unsigned int)(best.key[0] >> 32) || db == (unsigned int)(best.key[1] >> 32) || db == (unsigned int)(best.key[2] >> 32) ||
+                  db == (unsigned int)(best.key[3] >> 32) || db == (unsigned int)(best.key[4] >> 32);
+          }
+          top5_insert_key_unique(best, kq, sl[u]);
         }
       }
       warm = true;
@@ -357,6 +420,11 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
       unsigned long long kq = kk[0];
 #pragma unroll
       for (int v = 1; v < CM_KNN_UNROLL; v++) kq = (u == v) ? kk[v] : kq;
+      if (!kOrigIdx) {   // an exact distance tie with a list entry: the caller re-runs this query canonically (top5_insert_canon)
+        const unsigned int db = (unsigned int)(kq >> 32);
+        tie = tie || db == (unsigned int)(best.key[0] >> 32) || db == (unsigned int)(best.key[1] >> 32) || db == (unsigned int)(best.key[2] >> 32) ||
+              db == (unsigned int)(best.key[3] >> 32) || db == (unsigned int)(best.key[4] >> 32);
+      }
       if (warm) top5_insert_key_unique(best, kq, (int)(r.x + j0 + u));
       else top5_insert_key(best, kq, (int)(r.x + j0 + u));
     }
@@ -365,6 +433,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
     if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
   }
   if (ncand) *ncand = scanned;
+  if (tie_out) *tie_out = tie;
   if (g.max_level < 1) return false;
   const float r0 = leaf98 * c.m0;
   return !(best.d(4) < r0 * r0);
@@ -372,9 +441,11 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
 
 // Levels >= 1 of ONE query, executed by a whole warp.  The query (position, geometry, current list) lives in lane h;
 // on return lane h's list is final.
+// L0 = 0 repeats the level-0 block as well (a query whose per-thread pass met an exact distance tie starts over from an empty list:
+// this path orders ties canonically).
 template <bool kOrigIdx>
 __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const KnnGeom& c, float qx, float qy, float qz, float gate,
-                                                 Top5& best) {
+                                                 Top5& best, int L0 = 1) {
   const unsigned int FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = g.kdiv;
@@ -386,9 +457,9 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
   const int bfilter = __shfl_sync(FULL, c.filt, h);
   float bd5 = __shfl_sync(FULL, best.d(4), h);
   const float kf = (float)k;
-  for (int L = 1; L <= g.max_level; L++) {
+  for (int L = L0; L <= g.max_level; L++) {
     const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
-    if (bd5 < rr * rr) break;
+    if (L > 0 && bd5 < rr * rr) break;
     const int n = 2 + 2 * L, ncells = n * n * n;
     const float bound = fminf(bd5, gate);
     Top5 loc;
@@ -420,7 +491,7 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
           float ddx = bqx - p.x, ddy = bqy - p.y, ddz = bqz - p.z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
           const int jj = (int)(st + j);
-          top5_insert(loc, d, kOrigIdx ? __float_as_int(p.w) : jj, jj);
+          if (d <= loc.d(4)) top5_insert_canon<kOrigIdx>(g, loc, d, kOrigIdx ? __float_as_int(p.w) : jj, jj, p, false);
         }
       }
     }
@@ -430,11 +501,28 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
       const unsigned int mind = __reduce_min_sync(FULL, dbits);
       if (mind == __float_as_uint(FLT_MAX)) break;
       const unsigned int cand = (dbits == mind) ? ibits : 0xFFFFFFFFu;
-      const unsigned int mini = __reduce_min_sync(FULL, cand);
-      const int src = __ffs(__ballot_sync(FULL, dbits == mind && ibits == mini)) - 1;
-      const int wslot = __shfl_sync(FULL, loc.slot[0], src);
+      unsigned int mini = __reduce_min_sync(FULL, cand);
+      unsigned int tied = __ballot_sync(FULL, dbits == mind);
+      int src = __ffs(__ballot_sync(FULL, dbits == mind && ibits == mini)) - 1;
+      const int myslot = kOrigIdx ? loc.slot[0] : (int)ibits;
+      // the winner's point travels to the owner; on an exact distance tie between lanes the canonical order decides (map grids)
+      float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dbits == mind && myslot >= 0) hp = __ldg(g.pts + myslot);
+      if (!kOrigIdx && (tied & (tied - 1))) {
+        src = __ffs(tied) - 1; tied &= tied - 1;
+        while (tied) {
+          const int o = __ffs(tied) - 1; tied &= tied - 1;
+          const float4 pa = make_float4(__shfl_sync(FULL, hp.x, o), __shfl_sync(FULL, hp.y, o), __shfl_sync(FULL, hp.z, o), 0.f);
+          const float4 pb = make_float4(__shfl_sync(FULL, hp.x, src), __shfl_sync(FULL, hp.y, src), __shfl_sync(FULL, hp.z, src), 0.f);
+          const int sa = __shfl_sync(FULL, myslot, o), sb = __shfl_sync(FULL, myslot, src);
+          if (canon_less_map(g, pa, sa, pb, sb)) src = o;
+        }
+        mini = __shfl_sync(FULL, ibits, src);
+      }
+      const int wslot = __shfl_sync(FULL, myslot, src);
+      const float4 wp = make_float4(__shfl_sync(FULL, hp.x, src), __shfl_sync(FULL, hp.y, src), __shfl_sync(FULL, hp.z, src), __shfl_sync(FULL, hp.w, src));
       // unique: a list that was warm-started from the previous iteration's neighbours may already hold points of this shell
-      if (lane == h) top5_insert_key_unique(best, ((unsigned long long)mind << 32) | mini, wslot);
+      if (lane == h) top5_insert_canon<kOrigIdx>(g, best, __uint_as_float(mind), (int)mini, wslot, wp, true);
       if (lane == src) {
 #pragma unroll
         for (int u = 0; u < 4; u++) { loc.key[u] = loc.key[u + 1]; loc.slot[u] = loc.slot[u + 1]; }

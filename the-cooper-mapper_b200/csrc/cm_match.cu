@@ -275,7 +275,12 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   unsigned int ncand = 0;
   // iterations >= 1 start from the neighbours found one iteration ago (written by search_store for every query of the stream)
   const int* prev = (valid && it > 0 && a.warm) ? a.nn_slot + ((size_t)s * (a.cap_corner + a.cap_surf) + row) * 5 : nullptr;
-  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev);
+  bool tie = false;
+  if (valid) need = knn5_level0<kOrigIdx>(g, c, sx, sy, sz, rng, best, a.dbg ? &ncand : nullptr, prev, &tie);
+  // an exact distance tie (about one query in 10^5): the query goes to the warp-cooperative pass, which starts it over with the
+  // canonical tie order -- needs the hard queue (always there for map grids)
+  tie = tie && a.hard != nullptr;
+  need = need || tie;
   unsigned int hard = __ballot_sync(FULL, need);
   if (a.dbg) {
     unsigned long long t1;
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
         const int pos = base + __popc(hard & ((1u << lane) - 1));
         if (pos < a.hard_cap) {
           HardItem item;
-          item.s = s; item.t = t; item.pad = 0;
+          item.s = s; item.t = t; item.pad = tie ? 1 : 0;
 #pragma unroll
           for (int k = 0; k < 5; k++) { item.d[k] = best.d(k); item.idx[k] = best.idx(k); item.slot[k] = kOrigIdx ? best.slot[k] : best.idx(k); }
           reinterpret_cast<HardItem*>(a.hard)[pos] = item;
@@ -341,9 +346,10 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
     KnnGeom c;
     knn5_geom(g, sx, sy, sz, a.prm.knn_gate, c, a.prm.own_cube_only != 0);
     Top5 best;
+    const int redo = item->pad;   // 1: exact distance tie in the per-thread pass -> start over from the level-0 block, canonical ties
 #pragma unroll
-    for (int k = 0; k < 5; k++) { best.key[k] = top5_key(item->d[k], item->idx[k]); best.slot[k] = item->slot[k]; }
-    knn5_warp_finish<kOrigIdx>(g, 0, c, sx, sy, sz, a.prm.knn_gate, best);
+    for (int k = 0; k < 5; k++) { best.key[k] = redo ? CM_TOP5_EMPTY : top5_key(item->d[k], item->idx[k]); best.slot[k] = redo ? -1 : item->slot[k]; }
+    knn5_warp_finish<kOrigIdx>(g, 0, c, sx, sy, sz, a.prm.knn_gate, best, redo ? 0 : 1);
     if (lane == 0) search_store<kOrigIdx>(a, s, row, best.d(4) < a.prm.knn_gate, best);
   }
 }
