@@ -347,9 +347,8 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
           float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           const unsigned long long kq = top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]);
           if (!kOrigIdx) {
-            const unsigned int db = (unsigned int)(kq >> 32);
-            tie = tie || db == (unsigned int)(best.key[0] >> 32) || db == (unsigned int)(best.key[1] >> 32) || db == (unsigned int)(best.key[2] >> 32) ||
-                  db == (unsigned int)(best.key[3] >> 32) || db == (unsigned int)(best.key[4] >> 32);
+#pragma unroll
+            for (int e = 0; e < 5; e++) tie = tie || (((kq ^ best.key[e]) >> 32) == 0ull && kq != best.key[e]);
           }
           top5_insert_key_unique(best, kq, sl[u]);
         }
@@ -421,9 +420,9 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
 #pragma unroll
       for (int v = 1; v < CM_KNN_UNROLL; v++) kq = (u == v) ? kk[v] : kq;
       if (!kOrigIdx) {   // an exact distance tie with a list entry: the caller re-runs this query canonically (top5_insert_canon)
-        const unsigned int db = (unsigned int)(kq >> 32);
-        tie = tie || db == (unsigned int)(best.key[0] >> 32) || db == (unsigned int)(best.key[1] >> 32) || db == (unsigned int)(best.key[2] >> 32) ||
-              db == (unsigned int)(best.key[3] >> 32) || db == (unsigned int)(best.key[4] >> 32);
+        // (same distance, different point: a warm list meets its own entries again, those are not ties)
+#pragma unroll
+        for (int e = 0; e < 5; e++) tie = tie || (((kq ^ best.key[e]) >> 32) == 0ull && kq != best.key[e]);
       }
       if (warm) top5_insert_key_unique(best, kq, (int)(r.x + j0 + u));
       else top5_insert_key(best, kq, (int)(r.x + j0 + u));
