@@ -115,6 +115,20 @@ __device__ __forceinline__ void top5_insert_key_unique(Top5& t, unsigned long lo
   if (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3]) return;
   top5_insert_key(t, key, slot);
 }
+// Insert that also tracks d6, the smallest distance among the candidates that were turned away at the door or pushed out of the
+// list (only candidates at or below the current 5th distance ever get here, and only those can tie with the final 5th).
+// At the end  d6 == d(4)  or two equal neighbours in the list  <=>  the list depends on how exact distance ties were broken.
+__device__ __forceinline__ void top5_insert_track(Top5& t, unsigned long long key, int slot, bool unique, float& d6) {
+  if (unique && (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3] || key == t.key[4])) return;
+  const float d = __uint_as_float((unsigned int)(key >> 32));
+  if (!(key < t.key[4])) { d6 = fminf(d6, d); return; }
+  d6 = fminf(d6, t.d(4));
+  top5_insert_key(t, key, slot);
+}
+__device__ __forceinline__ bool top5_has_tie(const Top5& t, float d6) {
+  const float d4 = t.d(4);
+  return (d6 == d4 && d4 < FLT_MAX) || t.d(0) == t.d(1) || t.d(1) == t.d(2) || t.d(2) == t.d(3) || (t.d(3) == d4 && d4 < FLT_MAX);
+}
 
 // worldToCube (FeatureMap.h:475-487) -> index into the 7x7x7 window, -1 outside it
 __device__ __forceinline__ int window_index(const CubeWindow& w, float x, float y, float z) {
@@ -324,7 +338,7 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
 template <bool kOrigIdx>
 __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c, float qx, float qy, float qz, uint4* rng, Top5& best,
                                             unsigned int* ncand = nullptr, const int* prev = nullptr, bool* tie_out = nullptr) {
-  bool tie = false;   // some candidate was at EXACTLY the distance of a list entry (map grids): the list order is then not canonical
+  float d6 = FLT_MAX;   // smallest distance turned away from / pushed out of the list (map grids: exact-tie detection, top5_insert_track)
   const int k = g.kdiv;
   const float kf = (float)k;
   const float leaf98 = 0.98f * (g.cell / kf);
@@ -345,12 +359,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
         if (cand_ok(g, c.filt, q[u])) {
           float dx = qx - q[u].x, dy = qy - q[u].y, dz = qz - q[u].z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          const unsigned long long kq = top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]);
-          if (!kOrigIdx) {
-#pragma unroll
-            for (int e = 0; e < 5; e++) tie = tie || (((kq ^ best.key[e]) >> 32) == 0ull && kq != best.key[e]);
-          }
-          top5_insert_key_unique(best, kq, sl[u]);
+          top5_insert_key_unique(best, top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]), sl[u]);
         }
       }
       warm = true;
@@ -419,20 +428,15 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
       unsigned long long kq = kk[0];
 #pragma unroll
       for (int v = 1; v < CM_KNN_UNROLL; v++) kq = (u == v) ? kk[v] : kq;
-      if (!kOrigIdx) {   // an exact distance tie with a list entry: the caller re-runs this query canonically (top5_insert_canon)
-        // (same distance, different point: a warm list meets its own entries again, those are not ties)
-#pragma unroll
-        for (int e = 0; e < 5; e++) tie = tie || (((kq ^ best.key[e]) >> 32) == 0ull && kq != best.key[e]);
-      }
-      if (warm) top5_insert_key_unique(best, kq, (int)(r.x + j0 + u));
-      else top5_insert_key(best, kq, (int)(r.x + j0 + u));
+      if (kOrigIdx) { if (warm) top5_insert_key_unique(best, kq, (int)(r.x + j0 + u)); else top5_insert_key(best, kq, (int)(r.x + j0 + u)); }
+      else top5_insert_track(best, kq, (int)(r.x + j0 + u), warm, d6);   // map grids: remember what was turned away (exact ties)
     }
     if (ncand) scanned += left < (unsigned int)CM_KNN_UNROLL ? left : (unsigned int)CM_KNN_UNROLL;
     j0 += CM_KNN_UNROLL;
     if (j0 >= r.y) { ci++; j0 = 0; if (ci < nr) r = my[ci * stride]; }
   }
   if (ncand) *ncand = scanned;
-  if (tie_out) *tie_out = tie;
+  if (tie_out) *tie_out = !kOrigIdx && top5_has_tie(best, d6);   // the caller re-runs such a query canonically (top5_insert_canon)
   if (g.max_level < 1) return false;
   const float r0 = leaf98 * c.m0;
   return !(best.d(4) < r0 * r0);

@@ -243,6 +243,15 @@ __device__ __forceinline__ bool search_query(const CorrArgs& a, int s, int t, co
 #ifndef CM_SEARCH_MINB
 #define CM_SEARCH_MINB 6
 #endif
+// out of line on purpose: search_kernel only gets here without a hard queue (never in the mapping stage), and the shell pass
+// inlined into it costs the per-thread pass 120 bytes of spills
+template <bool kOrigIdx>
+__device__ __noinline__ void knn5_warp_finish_cold(const GridView* g, int h, const KnnGeom* c, float qx, float qy, float qz, float gate, Top5* best) {
+  Top5 b = *best;
+  knn5_warp_finish<kOrigIdx>(*g, h, *c, qx, qy, qz, gate, b);
+  *best = b;
+}
+
 template <bool kOrigIdx>
 __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kernel(CorrArgs a) {
   const int s = blockIdx.y;
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
     while (hard) {
       const int h = __ffs(hard) - 1;
       hard &= hard - 1;
-      knn5_warp_finish<kOrigIdx>(g, h, c, sx, sy, sz, a.prm.knn_gate, best);
+      knn5_warp_finish_cold<kOrigIdx>(&g, h, &c, sx, sy, sz, a.prm.knn_gate, &best);
     }
     if (!in_range) return;
   }
