@@ -264,6 +264,24 @@ int cm_shard_begin_host(cm_ctx* ctx, const cm_point* corner, size_t n_corner, co
 int cm_shard_partial_host(cm_ctx* ctx, int iter, const float* own_lo, const float* own_hi, double* sums32);
 int cm_shard_solve_host(cm_ctx* ctx, int iter, const double* sums32, cm_pose* pose, int* done, cm_match_stats* stats);
 
+/* ---- one map over several GPUs (BASELINE config 4) -------------------------------------------------------------------------------
+ * One process and one context per GPU.  Rank 0 calls cm_dist_unique_id (a 128-byte ncclUniqueId), the host program hands it to
+ * the other ranks (MPI, torch.distributed, a file), every rank calls cm_dist_init BEFORE cm_mapping_create.  From then on the
+ * context's map keeps only the 50 m cubes this rank owns (cube (i, j, k) of the FeatureMap lattice, FeatureMap.h:475-487, belongs
+ * to rank (i + 3 j + 5 k) mod nranks, so the cubes around a sensor spread over all ranks) plus the points within sqrt(5) m of them,
+ * the gate of ScanMatch.cpp:102,120 -- every accepted 5-NN of a query that falls into an owned cube is then local.  Every rank
+ * feeds the SAME sweeps and poses to the ordinary entry points (cm_map_insert_host, cm_mapping_process_host, cm_pipeline_step_*):
+ * a rank evaluates the queries whose map-frame position lies in its cubes, the per-rank partial normal equations (32 doubles per
+ * stream) are summed over the ranks once per Gauss-Newton iteration by the library's own exchange kernel -- every rank stores its
+ * vector into every peer's mailbox over NVLink (CUDA IPC peer mappings) and adds them in rank order; NCCL all-gather where IPC is
+ * not available -- and every rank solves the same 6x6 system: identical poses on all ranks, nothing is broadcast.
+ * NCCL is loaded with dlopen (libnccl.so.2); without it cm_dist_init returns CM_ERR_UNSUPPORTED. */
+int cm_dist_unique_id(void* id128);
+int cm_dist_init(cm_ctx* ctx, const void* id128, int rank, int nranks);
+int cm_dist_info(cm_ctx* ctx, int* rank, int* nranks, int* p2p);   /* p2p = 1: peer-memory mailboxes, 0: NCCL all-gather transport */
+/* the exchange as an operator: vec[0..n) (n <= 8192) summed over the ranks in rank order; repeat > 1 times it (ms per call) */
+int cm_dist_allreduce_host(cm_ctx* ctx, double* vec, int n, int repeat, float* ms_per_call);
+
 /* ---- measurement helpers (no reference counterpart; used by bench.py) ------------------------------------------------
  * cm_timer_record(ctx, 0 | 1) records a CUDA event on the context's stream; cm_timer_elapsed_ms returns event 1 - event 0.
  * cm_prof_enable brackets every launch of the dominant kernel (the fused correspondence kernel) with CUDA events on

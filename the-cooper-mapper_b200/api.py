@@ -135,6 +135,33 @@ class Context:
         self._check(self.L.cm_debug_math_host(self.h, C.c_int(op), _ptr(a), C.c_size_t(len(a)), _ptr(out)))
         return out
 
+    # ---- one map over several GPUs (cm_dist_*) -------------------------------------------------------------------------------
+    @staticmethod
+    def dist_unique_id():
+        """128-byte NCCL id (call on rank 0, hand the bytes to every rank)."""
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.cm_dist_unique_id(buf)
+        if rc != 0:
+            raise CoopermapError("cm_dist_unique_id failed (%d): libnccl.so.2 not loadable?" % rc)
+        return buf.raw
+
+    def dist_init(self, id128, rank, nranks):
+        """Join `nranks` contexts (one per process / GPU) into one sharded map; call before mapping_create."""
+        self._check(self.L.cm_dist_init(self.h, C.c_char_p(id128), C.c_int(rank), C.c_int(nranks)))
+
+    def dist_info(self):
+        r = C.c_int(0); n = C.c_int(1); p = C.c_int(0)
+        self._check(self.L.cm_dist_info(self.h, C.byref(r), C.byref(n), C.byref(p)))
+        return dict(rank=r.value, nranks=n.value, p2p=bool(p.value))
+
+    def dist_allreduce(self, vec, repeat=1):
+        """Sum a float64 vector over the ranks with the library's exchange kernel -> (total, ms per call)."""
+        v = np.ascontiguousarray(vec, np.float64).copy()
+        ms = C.c_float(0)
+        self._check(self.L.cm_dist_allreduce_host(self.h, _ptr(v), C.c_int(len(v)), C.c_int(repeat), C.byref(ms)))
+        return v, ms.value
+
     # ---- mapping stage (device-resident map) -------------------------------------------------------------------------
     def mapping_create(self, nstreams, max_corner_points=200000, max_surf_points=2000000):
         self.nstreams = int(nstreams)

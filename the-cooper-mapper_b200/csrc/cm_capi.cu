@@ -94,6 +94,7 @@ void cm_ctx_destroy(cm_ctx* ctx) {
     for (int j = 0; j < 2; j++) if (ctx->pipe[i].copied_x[j]) cudaEventDestroy(ctx->pipe[i].copied_x[j]);
     if (ctx->pipe[i].h_n5) cudaFreeHost(ctx->pipe[i].h_n5);
   }
+  cm::dist_destroy(ctx);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;

@@ -27,6 +27,25 @@ struct LocalWindow {
   int n_surround[2] = {0, 0};
 };
 
+// ---- multi-GPU state (cm_dist.cu) ------------------------------------------------------------------------------------------
+#define CM_DIST_MAX_RANKS 16
+#define CM_DIST_NMAX 8192            // doubles per exchange (256 streams x 32)
+struct DistDev {                     // what the exchange kernel sees
+  int rank, nranks, nmax, p2p;
+  double* mbox_peer[CM_DIST_MAX_RANKS];               // every rank's mailbox, mapped into this process (CUDA IPC); [rank] = mine
+  unsigned long long* flags_peer[CM_DIST_MAX_RANKS];  // their sequence numbers
+  const double* gathered;                             // all-gather transport: [nranks][n] (no IPC)
+};
+struct DistState {
+  bool on = false;
+  void* comm = nullptr;              // ncclComm_t
+  void* mailbox = nullptr;           // this rank's mailbox (cudaMalloc, exported with cudaIpcGetMemHandle)
+  void* peer_ptr[CM_DIST_MAX_RANKS] = {};
+  DistDev dev;
+  unsigned long long seq = 0;        // exchanges so far (all ranks advance together)
+  DeviceBuffer err, gathered, scratch;
+};
+
 }  // namespace cm
 
 struct cm_ctx {
@@ -70,6 +89,7 @@ struct cm_ctx {
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
   cm::LocalWindow local;               // cm_mapping_local_*
+  cm::DistState dist;                  // cm_dist_init: this context is one rank of a sharded map
   // pinned, device-accessible host staging for the per-step parameter uploads of the mapping stage (poses, cube windows): they
   // are copied by a kernel, not by the copy engine that the sweep uploads keep busy
   void* h_stage = nullptr; size_t h_stage_cap = 0;
@@ -112,6 +132,8 @@ MatchParamsDev dev_params(const cm_config& c);
 int ctx_fail(cm_ctx* ctx, int code, const std::string& msg);
 void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L);
 void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out);
+int dist_allreduce(cm_ctx* ctx, double* d_vec, int n, cudaStream_t stream);   // in-place sum over the ranks (cm_dist.cu)
+void dist_destroy(cm_ctx* ctx);
 }  // namespace cm
 
 extern "C" int cm_match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,

@@ -119,9 +119,11 @@ __device__ __forceinline__ void top5_insert_key_unique(Top5& t, unsigned long lo
 // list (only candidates at or below the current 5th distance ever get here, and only those can tie with the final 5th).
 // At the end  d6 == d(4)  or two equal neighbours in the list  <=>  the list depends on how exact distance ties were broken.
 __device__ __forceinline__ void top5_insert_track(Top5& t, unsigned long long key, int slot, bool unique, float& d6) {
-  if (unique && (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3] || key == t.key[4])) return;
-  const float d = __uint_as_float((unsigned int)(key >> 32));
-  if (!(key < t.key[4])) { d6 = fminf(d6, d); return; }
+  if (!(key < t.key[4])) {   // turned away (key == key[4]: a warm list meeting its own 5th entry again)
+    if (key != t.key[4]) d6 = fminf(d6, __uint_as_float((unsigned int)(key >> 32)));
+    return;
+  }
+  if (unique && (key == t.key[0] || key == t.key[1] || key == t.key[2] || key == t.key[3])) return;
   d6 = fminf(d6, t.d(4));
   top5_insert_key(t, key, slot);
 }
@@ -137,6 +139,12 @@ __device__ __forceinline__ int window_index(const CubeWindow& w, float x, float 
   int k = (int)(roundf(z / w.cube_size) + (float)w.origin[2]) - w.w0[2];
   if (i < 0 || i > 6 || j < 0 || j > 6 || k < 0 || k > 6) return -1;
   return (i * 7 + j) * 7 + k;
+}
+
+// Sharded map (cm_dist.cu): the rank that owns cube (i, j, k) of the FeatureMap lattice.  Neighbouring cubes go to different
+// ranks on purpose: the cubes around a sensor -- where all of a sweep's queries fall -- are spread over every rank.
+__host__ __device__ __forceinline__ int cube_owner(int i, int j, int k, int nranks) {
+  return (int)((unsigned int)(i + 3 * j + 5 * k) % (unsigned int)nranks);
 }
 
 // Candidate filter codes (KnnGeom::filt): CM_FILT_NONE: every point of the grid is searched; CM_FILT_WINDOW: only points

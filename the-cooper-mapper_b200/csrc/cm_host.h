@@ -157,6 +157,7 @@ struct MatchLaunch {
   int orig_idx;                               // grids carry original indices in pts[].w
   int max_queries = 0;                        // what the grids are sized for: n_corner[s] + n_surf[s] of the largest stream, exact or an
                                               // ESTIMATE (the kernels loop when a stream has more); 0: use the capacities
+  int dist_rank = 0, dist_nranks = 1;         // sharded map: evaluate only the queries whose map-frame cube this rank owns
   const int* skip = nullptr;                  // optional device flag: non-zero = the grids above were too small for some stream (estimate
                                               // missed): every kernel of the match returns at once and the caller repeats it with exact sizes
   int bound_queries = 0;                      // host-known UPPER BOUND of n_corner[s] + n_surf[s]: sizes the scratch (0: max_queries)
@@ -214,7 +215,9 @@ struct MatchGraphCache {
 void launch_match_groups(const MatchLaunch& m, cudaStream_t stream, int ngroups, cudaStream_t* gs, cudaEvent_t fork, cudaEvent_t* join,
                          KernelProfiler* prof = nullptr);
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream);
-void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr, bool fused = false);
+// defer_solve (fused only): stop after the per-stream sums -- the caller exchanges them between ranks and calls launch_match_solve_warp
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof = nullptr, bool fused = false, bool defer_solve = false);
+void launch_match_solve_warp(const MatchLaunch& m, int it, cudaStream_t stream);
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);
 void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream);
 
@@ -276,11 +279,15 @@ struct DeviceMap {
   DeviceBuffer windows, flags;
   DeviceBuffer n_pending[2], world[2], keys_a[2], keys_b[2], vals_a[2], vals_b[2], pending[2];   // insert scratch per class: the two classes may run on different streams
   unsigned int table_cap[2] = {0, 0}, pool_cap[2] = {0, 0};
+  int shard_rank = 0, shard_nranks = 1;   // > 1 ranks: keep only the cubes cube_owner() gives this rank, plus a sqrt(5) m halo (cm_dist.cu)
   void create(int nstreams, const MapConfig& c, cudaStream_t stream);
   // also refreshes the GridViews.  staged: h_windows is pinned, device-accessible host memory -> copied by a kernel instead of
   // a host-to-device memcpy (a small memcpy queues behind the sweep uploads that keep the copy engine busy)
   // h_windows == NULL: the windows on the device are still current (only the views are refreshed)
   void set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream, bool staged = false);
+  // sharded map: views[].npts (points of the active cubes THIS rank owns) <-> a vector of 2 * nstreams doubles for the exchange
+  void pack_npts(double* d_vec, cudaStream_t stream);
+  void unpack_npts(const double* d_vec, cudaStream_t stream);
   // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
   // max_n: what the launches are sized for (an estimate is fine: if a stream has more, the insert does nothing and sets flags[4 + cls]);
   // step_skip: optional device flag, non-zero = insert nothing (the caller is about to repeat the step)

@@ -64,11 +64,36 @@ __global__ void map_group_clear_kernel(GroupEntry* tab, unsigned int cap, const 
   if (i < cap) { tab[i].key = CM_MAP_PAD; tab[i].head = 0x7fffffff; tab[i].tail = -1; }
 }
 
+// Sharded map: does this rank hold the point?  Yes if it owns the point's cube, or a neighbouring cube whose box is within the
+// halo of the point: a query evaluated by the owner of its cube finds every map point within sqrt(5) m (the 5-NN gate) locally.
+__device__ __forceinline__ bool shard_keeps(const MapClassDev& m, float x, float y, float z, int ci, int cj, int ck, int rank, int nranks) {
+  if (cube_owner(ci, cj, ck, nranks) == rank) return true;
+  const float HALO = 2.2360680f * 1.001f + 0.01f;
+  const float half = 0.5f * m.cube_size;
+  const float c[3] = {x, y, z};
+  const int idx[3] = {ci, cj, ck};
+  int lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float centre = m.cube_size * (float)(idx[a] - m.origin[a]);
+    lo[a] = (c[a] - (centre - half)) < HALO ? -1 : 0;
+    hi[a] = ((centre + half) - c[a]) < HALO ? 1 : 0;
+  }
+  for (int di = lo[0]; di <= hi[0]; di++)
+    for (int dj = lo[1]; dj <= hi[1]; dj++)
+      for (int dk = lo[2]; dk <= hi[2]; dk++) {
+        const int ni = ci + di, nj = cj + dj, nk = ck + dk;
+        if (ni < 0 || ni >= m.dims[0] || nj < 0 || nj >= m.dims[1] || nk < 0 || nk >= m.dims[2]) continue;
+        if (cube_owner(ni, nj, nk, nranks) == rank) return true;
+      }
+  return false;
+}
+
 __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int cap, int max_n, int nstreams,
                                const MatchState* __restrict__ state, const float* __restrict__ tf_override, MapClassDev* maps,
                                float4* __restrict__ world, unsigned long long* __restrict__ keys, unsigned int* __restrict__ slot_of,
                                int* __restrict__ next, GroupEntry* __restrict__ gtab, unsigned int gmask, int* __restrict__ flags,
-                               const int* __restrict__ skip) {
+                               const int* __restrict__ skip, int shard_rank, int shard_nranks) {
   if (*skip) return;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (size_t)nstreams * max_n) return;
@@ -89,7 +114,8 @@ __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __rest
       int ci = world_to_cube_axis(w.x, m.cube_size, m.origin[0]);
       int cj = world_to_cube_axis(w.y, m.cube_size, m.origin[1]);
       int ck = world_to_cube_axis(w.z, m.cube_size, m.origin[2]);
-      if (ci >= 0 && ci < m.dims[0] && cj >= 0 && cj < m.dims[1] && ck >= 0 && ck < m.dims[2]) {   // isIndexValid, :102-108
+      if (ci >= 0 && ci < m.dims[0] && cj >= 0 && cj < m.dims[1] && ck >= 0 && ck < m.dims[2] &&   // isIndexValid, :102-108
+          (shard_nranks <= 1 || shard_keeps(m, w.x, w.y, w.z, ci, cj, ck, shard_rank, shard_nranks))) {
         float vx = floorf(w.x * m.inv_leaf), vy = floorf(w.y * m.inv_leaf), vz = floorf(w.z * m.inv_leaf);
         if (fabsf(vx) < (float)CM_VOX_BIAS && fabsf(vy) < (float)CM_VOX_BIAS && fabsf(vz) < (float)CM_VOX_BIAS) {
           unsigned long long kx = (unsigned long long)((int)vx + CM_VOX_BIAS), ky = (unsigned long long)((int)vy + CM_VOX_BIAS),
@@ -237,7 +263,8 @@ __global__ void map_clear_kernel(CellEntry* e, unsigned int* cellcap, unsigned i
 
 // searchable size of the surround map (sum of the valid cubes) -> GridView.npts, and the rest of the view.
 // One warp per stream.
-__global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, GridView* views, int nstreams, float gate) {
+__global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, GridView* views, int nstreams, float gate, int shard_rank,
+                                int shard_nranks) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nstreams) return;
   MapClassDev& m = maps[s];
@@ -246,6 +273,7 @@ __global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, Gr
   for (int a = lane; a < 343; a += 32) {
     if (!w.active[a]) continue;
     int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
+    if (shard_nranks > 1 && cube_owner(i, j, k, shard_nranks) != shard_rank) continue;   // halo copies are counted by their owner
     total += m.cube_count[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
   }
 #pragma unroll
@@ -349,7 +377,22 @@ void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_
   else cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
   for (int cls = 0; cls < 2; cls++)
     CM_LAUNCH(map_view_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
-              (GridView*)views[cls].p, nstreams, gate);
+              (GridView*)views[cls].p, nstreams, gate, shard_rank, shard_nranks);
+}
+
+__global__ void map_npts_pack_kernel(const GridView* vc, const GridView* vs, int nstreams, double* vec) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nstreams) { vec[s] = (double)vc[s].npts; vec[nstreams + s] = (double)vs[s].npts; }
+}
+__global__ void map_npts_unpack_kernel(GridView* vc, GridView* vs, int nstreams, const double* vec) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nstreams) { vc[s].npts = (int)vec[s]; vs[s].npts = (int)vec[nstreams + s]; }
+}
+void DeviceMap::pack_npts(double* d_vec, cudaStream_t stream) {
+  CM_LAUNCH(map_npts_pack_kernel, (nstreams + 63) / 64, 64, 0, stream, (const GridView*)views[0].p, (const GridView*)views[1].p, nstreams, d_vec);
+}
+void DeviceMap::unpack_npts(const double* d_vec, cudaStream_t stream) {
+  CM_LAUNCH(map_npts_unpack_kernel, (nstreams + 63) / 64, 64, 0, stream, (GridView*)views[0].p, (GridView*)views[1].p, nstreams, d_vec);
 }
 
 void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf,
@@ -368,7 +411,7 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
   CM_LAUNCH(map_insert_guard_kernel, 1, 256, 0, stream, d_n, nstreams, max_n, (int*)flags.p + 4 + cls, step_skip);
   CM_LAUNCH(map_group_clear_kernel, (gcap + 255) / 256, 256, 0, stream, (GroupEntry*)keys_b[cls].p, gcap, skip);
   CM_LAUNCH(map_key_kernel, nb, 256, 0, stream, d_pts, d_n, cap, max_n, nstreams, d_state, d_tf, (MapClassDev*)dev[cls].p, (float4*)world[cls].p,
-            (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p, skip);
+            (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p, skip, shard_rank, shard_nranks);
   CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a[cls].p, (const unsigned int*)vals_a[cls].p, (const int*)vals_b[cls].p,
             (const GroupEntry*)keys_b[cls].p, n, (const float4*)world[cls].p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending[cls].p,
             (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p, skip);

@@ -262,6 +262,26 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   m.sums = (double*)ctx->m_sums.p; m.trace = nullptr; m.nn = nullptr; m.orig_idx = 0; m.prm = prm;
   m.max_queries = max_q; m.bound_queries = bound_c + bound_s;
   m.skip = (const int*)ctx->map.flags.p + 6;   // set by launch_step_guard below when an estimate was too small
+  const bool sharded = ctx->dist.on && ctx->dist.dev.nranks > 1;
+  if (sharded) { m.dist_rank = ctx->dist.dev.rank; m.dist_nranks = ctx->dist.dev.nranks; }
+  // One map over several ranks: every rank runs the same loop on its own queries; between the per-stream sums and the 6x6 step
+  // the library's exchange kernel adds the sums of all ranks in rank order (cm_dist.cu), so every rank takes the same step.
+  // Launch by launch: every rank must issue the same max_iterations exchanges whatever its streams converge to.
+  auto run_gn_sharded = [&](const MatchLaunch& ml) -> int {
+    ctx->dist.scratch.reserve(sizeof(double) * 2 * (size_t)S);
+    ctx->map.pack_npts((double*)ctx->dist.scratch.p, st);          // the reference-size gate (ScanMatch.cpp:57-61) looks at the WHOLE map
+    int rc = dist_allreduce(ctx, (double*)ctx->dist.scratch.p, 2 * S, st);
+    if (rc < 0) return rc;
+    ctx->map.unpack_npts((const double*)ctx->dist.scratch.p, st);
+    launch_match_init(ml, st);
+    for (int it = 0; it < ml.prm.max_iterations; it++) {
+      launch_match_partial(ml, it, st, &ctx->prof, true, true);
+      rc = dist_allreduce(ctx, ml.sums, 32 * S, st);
+      if (rc < 0) return rc;
+      launch_match_solve_warp(ml, it, st);
+    }
+    return CM_OK;
+  };
   // capacities from the bound, in whole 256-query tiles: the Gauss-Newton graph key then repeats from frame to frame
   ctx->hardq.attach(m, (size_t)S * (size_t)(((m.bound_queries + 32 + 255) / 256) * 256));
   if (ctx->dbg_on) {
@@ -284,7 +304,8 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     } else {
       // replay from a CUDA graph unless per-launch events are wanted (bench.py's kernel timing, the timeline, the search trace)
       const bool want_events = ctx->prof.enabled || g_timeline.on || ctx->dbg_on || no_graph;
-      if (want_events || !ctx->match_graphs.launch(m, st)) launch_match(m, st, &ctx->prof);
+      if (sharded) { const int rc = run_gn_sharded(m); if (rc < 0) return rc; }
+      else if (want_events || !ctx->match_graphs.launch(m, st)) launch_match(m, st, &ctx->prof);
     }
   }
   issue_deferred_prefetch(ctx);   // the Gauss-Newton loop is on its way: submit the next sweep's upload + scan registration now
@@ -316,6 +337,11 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
   CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   CM_CUDA_CHECK(ctx, cudaGetLastError());
+  if (sharded) {
+    int derr = 0;
+    CM_CUDA_CHECK(ctx, cudaMemcpy(&derr, ctx->dist.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (derr) return fail(ctx, CM_ERR_CUDA, "sharded map: the exchange timed out waiting for a peer rank");
+  }
   {
     int act_c = 1, act_s = 1;
     for (int s = 0; s < S; s++) { act_c = std::max(act_c, nds[s]); act_s = std::max(act_s, nds[S + s]); }
@@ -327,7 +353,8 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
       CM_CUDA_CHECK(ctx, cudaMemsetAsync((int*)ctx->map.flags.p + 4, 0, sizeof(int) * 3, st));
       m.max_queries = std::min(act_c, cap_c) + std::min(act_s, cap_s);
       m.skip = nullptr;
-      launch_match(m, st, &ctx->prof);
+      if (sharded) { const int rc = run_gn_sharded(m); if (rc < 0) return rc; }
+      else launch_match(m, st, &ctx->prof);
       if (!localise) {
         ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, std::min(cap_c, act_c), (const MatchState*)ctx->m_state.p, nullptr, st);
         ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, std::min(cap_s, act_s), (const MatchState*)ctx->m_state.p, nullptr, st);

@@ -101,6 +101,7 @@ struct CorrArgs {
   int iter;                                   // the evaluation index when iter_dev is NULL
   int warm;                                   // 1: warm-start the 5-NN lists from the previous iteration (COOPERMAP_NO_WARM=1: off)
   const int* skip;                            // optional: non-zero = do nothing (MatchLaunch::skip)
+  int dist_rank, dist_nranks;                 // sharded map: only the queries whose map-frame cube this rank owns are evaluated
   void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
   MatchParamsDev prm;
 };
@@ -232,6 +233,13 @@ __device__ __forceinline__ bool search_query(const CorrArgs& a, int s, int t, co
     if (a.own_box) {
       const float* b = a.own_box;
       valid = *sx >= b[0] && *sx < b[3] && *sy >= b[1] && *sy < b[4] && *sz >= b[2] && *sz < b[5];
+    }
+    if (a.dist_nranks > 1) {   // worldToCube (FeatureMap.h:475-487) of the query, clamped into the grid
+      const CubeWindow& w = *a.grid_surf[s].window;
+      int ci = (int)(roundf(*sx / w.cube_size) + (float)w.origin[0]), cj = (int)(roundf(*sy / w.cube_size) + (float)w.origin[1]),
+          ck = (int)(roundf(*sz / w.cube_size) + (float)w.origin[2]);
+      ci = min(max(ci, 0), w.dims[0] - 1); cj = min(max(cj, 0), w.dims[1] - 1); ck = min(max(ck, 0), w.dims[2] - 1);
+      valid = cube_owner(ci, cj, ck, a.dist_nranks) == a.dist_rank;
     }
   }
   return valid;
@@ -771,6 +779,7 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr; ca.iter_dev = nullptr; sa.iter_dev = nullptr;
   static const int warm = getenv("COOPERMAP_NO_WARM") ? 0 : 1;
   ca.iter = 0; ca.warm = warm; ca.skip = m.skip; sa.skip = m.skip;
+  ca.dist_rank = m.dist_rank; ca.dist_nranks = m.dist_nranks;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
@@ -782,7 +791,7 @@ void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
 }
 
 // one Gauss-Newton evaluation: correspondences + rows + (partial) normal-equation sums into m.sums
-void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof, bool fused) {
+void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof, bool fused, bool defer_solve) {
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
   const int capQ = m.cap_corner + m.cap_surf;
@@ -808,7 +817,7 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (fused) {
     FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.ptiles = m.partial_blocks;
     CM_LAUNCH(fit_solve_kernel, grid, 256, 0, stream, ca, f);
-    CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
+    if (!defer_solve) CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
     return;
   }
   CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
@@ -822,6 +831,13 @@ void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream) {
   fill_args(m, ca, sa);
   sa.iter = it;
   CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+}
+
+void launch_match_solve_warp(const MatchLaunch& m, int it, cudaStream_t stream) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  sa.iter = it;
+  CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
 }
 
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream) {
@@ -936,7 +952,7 @@ static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
   P(m.pose_in); P(m.state); P(m.rows); P(m.nn_slot); P(m.sums); P(m.trace); P(m.nn); I(m.orig_idx);
   const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
   I((maxq + 32 + 255) / 256);   // the grids depend on max_queries only through this
-  P(m.own_box); P(m.skip); P(m.hard); P(m.hard_count); I(m.hard_cap); I(m.hard_blocks); P(m.partials); P(m.tickets); I(m.partial_blocks);
+  P(m.own_box); I(m.dist_rank); I(m.dist_nranks); P(m.skip); P(m.hard); P(m.hard_count); I(m.hard_cap); I(m.hard_blocks); P(m.partials); P(m.tickets); I(m.partial_blocks);
   I(m.prm.max_iterations); F(m.prm.delta_t_abort); F(m.prm.delta_r_abort); F(m.prm.knn_gate); F(m.prm.plane_max_dist);
   I(m.prm.min_ref_corner); I(m.prm.min_ref_surf); I(m.prm.min_rows); F(m.prm.eig_threshold); I(m.prm.few_rows_continue);
   I(m.prm.own_cube_only); I(m.prm.nan_guard);
