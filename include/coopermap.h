@@ -224,6 +224,16 @@ int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner,
  * cube clouds (the content FeatureMap::saveCloudToFiles writes, FeatureMap.h:378-412). */
 int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, int* cube_index, size_t cap, size_t* n_out);
 
+/* "Map cloud out".  FeatureMap::getSurroundFeature (FeatureMap.h:256-265): the clouds of the valid cubes of the last
+ * FeatureMap::update (cm_mapping_process / cm_pipeline_step), concatenated in the order computeActiveAera found them (i, j, k
+ * loops, :308-352), every cube in pcl::VoxelGrid order -- what the reference publishes as /laser_cloud_surround_{corner,surf}
+ * (LaserMatcher.cpp:357-394).  n_out2[0 / 1] return the full sizes even when they exceed the capacities.
+ * cm_map_full_host = FeatureMap::getFullMap (:267-287): every cube in index order, its corner cloud then its surf cloud, each
+ * re-filtered with `leaf` (the reference's map_filter_full, LaserMatcher.cpp:116) -- /FullMap and the ~saveMap service (:164-188). */
+int cm_map_surround_host(cm_ctx* ctx, int stream_index, cm_point* out_corner, size_t cap_corner, cm_point* out_surf, size_t cap_surf,
+                         size_t* n_out2);
+int cm_map_full_host(cm_ctx* ctx, int stream_index, float leaf, cm_point* out, size_t cap, size_t* n_out);
+
 /* FeatureMap::saveCloudToFiles / loadCloudFromFiles (FeatureMap.h:378-462): <dir>/index.txt ("count type i j k size" per
  * file, type 0 corner / 1 surf, cubes enumerated i, j, k with corner before surf) + <dir>/<count>.pcd, binary PCD files as
  * pcl::io::savePCDFileBinary writes them for pcl::PointXYZI; a cube's points are stored in VoxelGrid order.  Loading pushes

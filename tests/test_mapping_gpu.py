@@ -135,3 +135,34 @@ def test_estimate_sized_launches_change_nothing(cmb, synth, monkeypatch):
             assert st_a[s]["iterations"] == st_b[s]["iterations"] and st_a[s]["rows"] == st_b[s]["rows"]
     for a, b in zip(maps_ref, maps_und):
         assert _same(a, b)
+
+
+def test_surround_and_full_map_clouds(cmb, oracle, synth):
+    """'Map cloud out' of the boundary: FeatureMap::getSurroundFeature (valid cubes in (i, j, k) order, VoxelGrid order inside)
+    and getFullMap (every cube re-filtered at the full-map leaf), byte for byte."""
+    sc = synth.make_scene(seed=41, extent=60.0, n_boxes=16, n_poles=10)
+    ctx = cmb.Context(**MAP_CFG)
+    ctx.mapping_create(1, 100000, 600000)
+    om = oracle.Mapping(map_params=ORACLE_MAP)
+    assert all(len(c) == 0 for c in ctx.map_surround(0))            # no update yet: no valid cube
+    for k, (R, t, fr) in enumerate(_frames(synth, sc, 4, model="HDL-32", cols=1024, speed=1.5)):
+        f = oracle.scanreg_organised(fr)
+        od = (R.astype(np.float32), t.astype(np.float32))
+        ctx.mapping_process([od], [f["lessSharp"]], [f["lessFlat"]])
+        om.process(od[0], od[1], f["lessSharp"], f["lessFlat"])
+    gc, gs = ctx.map_surround(0)
+    assert len(gs) > 5000
+    assert _same(gc, om.map_surround(0)) and _same(gs, om.map_surround(1))
+    # getFullMap, restated with the oracle's VoxelGrid on the cube clouds
+    leaf = 2.0
+    parts = []
+    exp = [ctx.map_export_sorted(0, cls) for cls in (0, 1)]
+    cubes = sorted(set(exp[0][1].tolist()) | set(exp[1][1].tolist()))
+    for c in cubes:
+        for cls in (0, 1):
+            pts = exp[cls][0][exp[cls][1] == c]
+            if len(pts):
+                parts.append(oracle.voxel_filter(pts, leaf))
+    want = np.concatenate(parts)
+    assert _same(ctx.map_full(0, leaf), want)
+    ctx.close()

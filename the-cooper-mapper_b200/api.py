@@ -291,6 +291,22 @@ class Context:
         self._check(self.L.cm_map_export_host(self.h, C.c_int(stream), C.c_int(cls), _ptr(pts), _ptr(cube), C.c_size_t(len(pts)), C.byref(n)))
         return pts[:n.value].copy(), cube[:n.value].copy()
 
+    def map_surround(self, stream):
+        """FeatureMap::getSurroundFeature -> (corner, surf) clouds of the valid cubes, in the reference's order."""
+        n = (C.c_size_t * 2)()
+        self._check(self.L.cm_map_surround_host(self.h, C.c_int(stream), None, C.c_size_t(0), None, C.c_size_t(0), n))
+        c = np.empty((max(n[0], 1), 4), np.float32); s = np.empty((max(n[1], 1), 4), np.float32)
+        self._check(self.L.cm_map_surround_host(self.h, C.c_int(stream), _ptr(c), C.c_size_t(len(c)), _ptr(s), C.c_size_t(len(s)), n))
+        return c[:n[0]].copy(), s[:n[1]].copy()
+
+    def map_full(self, stream, leaf):
+        """FeatureMap::getFullMap: every cube's corner and surf cloud re-filtered with `leaf`, cubes in index order."""
+        n = C.c_size_t(0)
+        self._check(self.L.cm_map_full_host(self.h, C.c_int(stream), C.c_float(leaf), None, C.c_size_t(0), C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        self._check(self.L.cm_map_full_host(self.h, C.c_int(stream), C.c_float(leaf), _ptr(out), C.c_size_t(len(out)), C.byref(n)))
+        return out[:n.value].copy()
+
     def map_export_sorted(self, stream, cls):
         """Export ordered like the reference's cube clouds: by cube index, then by voxel (z, y, x)."""
         pts, cube = self.map_export(stream, cls)

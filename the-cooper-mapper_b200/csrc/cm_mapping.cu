@@ -799,6 +799,147 @@ int cm_map_export_host(cm_ctx* ctx, int stream_index, int cls, cm_point* out, in
   return CM_OK;
 }
 
+/* ---- "map cloud out": FeatureMap::getSurroundFeature (FeatureMap.h:256-265) and getFullMap (:267-287) ------------------------------
+ * The map lives in a hash of cells; the reference's clouds are ordered: valid cubes in (i, j, k) loop order (:308-352), inside a
+ * cube the output order of pcl::VoxelGrid (by voxel index: z, then y, then x).  The export is ordered on the host: this is the
+ * publishing path (every _mapFrameNum-th frame / a service call, LaserMatcher.cpp:164-188, 357-394), not the per-sweep path. */
+namespace {
+struct ExportedCloud { std::vector<float4> pts; std::vector<int> cube; };
+int export_class(cm_ctx* ctx, int stream_index, int cls, ExportedCloud& out) {
+  cudaStream_t st = ctx->stream;
+  ctx->m_exp_n.reserve(sizeof(unsigned int));
+  ctx->m_exp_pts.reserve(sizeof(float4)); ctx->m_exp_cube.reserve(sizeof(int));
+  unsigned int n = 0;
+  ctx->map.export_points(cls, stream_index, (float4*)ctx->m_exp_pts.p, (int*)ctx->m_exp_cube.p, (unsigned int*)ctx->m_exp_n.p, 0u, st);   // count
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(&n, ctx->m_exp_n.p, sizeof(n), cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  out.pts.resize(n); out.cube.resize(n);
+  if (!n) return CM_OK;
+  ctx->m_exp_pts.reserve((size_t)n * sizeof(float4)); ctx->m_exp_cube.reserve((size_t)n * sizeof(int));
+  ctx->map.export_points(cls, stream_index, (float4*)ctx->m_exp_pts.p, (int*)ctx->m_exp_cube.p, (unsigned int*)ctx->m_exp_n.p, n, st);
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out.pts.data(), ctx->m_exp_pts.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out.cube.data(), ctx->m_exp_cube.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  CM_CUDA_CHECK(ctx, cudaGetLastError());
+  return CM_OK;
+}
+// order of a cube's cloud after downsizeValidCloud: pcl::VoxelGrid output order = ascending voxel index (z, y, x)
+struct VoxOrder {
+  float inv;
+  bool operator()(const float4& a, const float4& b) const {
+    const float za = floorf(a.z * inv), zb = floorf(b.z * inv); if (za != zb) return za < zb;
+    const float ya = floorf(a.y * inv), yb = floorf(b.y * inv); if (ya != yb) return ya < yb;
+    return floorf(a.x * inv) < floorf(b.x * inv);
+  }
+};
+}  // namespace
+
+int cm_map_surround_host(cm_ctx* ctx, int stream_index, cm_point* out_corner, size_t cap_corner, cm_point* out_surf, size_t cap_surf, size_t* n_out2) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (stream_index < 0 || stream_index >= ctx->map_streams || !n_out2) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const size_t wb = sizeof(CubeWindow) * (size_t)ctx->map_streams;
+  n_out2[0] = n_out2[1] = 0;
+  if (ctx->wins_shadow.size() != wb) return CM_OK;   // no FeatureMap::update yet: _cubeValidInd is empty
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const CubeWindow& w = ((const CubeWindow*)ctx->wins_shadow.data())[stream_index];
+    const int W = w.dims[0], H = w.dims[1];
+    for (int cls = 0; cls < 2; cls++) {
+      ExportedCloud e;
+      const int rc = export_class(ctx, stream_index, cls, e);
+      if (rc < 0) return rc;
+      const float leaf = cls == 0 ? ctx->cfg.map_filter_corner : ctx->cfg.map_filter_surf;
+      VoxOrder vo{1.0f / leaf};
+      // valid cubes in the order computeActiveAera pushes them: i outermost, k innermost (FeatureMap.h:311-349)
+      struct Item { long long cube_rank; float4 p; };
+      std::vector<Item> items;
+      items.reserve(e.pts.size());
+      for (size_t q = 0; q < e.pts.size(); q++) {
+        const int c = e.cube[q];
+        const int i = c % W, j = (c / W) % H, k = c / (W * H);
+        const int wi = i - w.w0[0], wj = j - w.w0[1], wk = k - w.w0[2];
+        if (wi < 0 || wi > 6 || wj < 0 || wj > 6 || wk < 0 || wk > 6 || !w.active[(wi * 7 + wj) * 7 + wk]) continue;
+        items.push_back(Item{((long long)wi * 7 + wj) * 7 + wk, e.pts[q]});
+      }
+      std::stable_sort(items.begin(), items.end(), [&](const Item& a, const Item& b) {
+        if (a.cube_rank != b.cube_rank) return a.cube_rank < b.cube_rank;
+        return vo(a.p, b.p);
+      });
+      n_out2[cls] = items.size();
+      cm_point* out = cls == 0 ? out_corner : out_surf;
+      const size_t cap = cls == 0 ? cap_corner : cap_surf;
+      if (out) for (size_t q = 0; q < items.size() && q < cap; q++) out[q] = cm_point{items[q].p.x, items[q].p.y, items[q].p.z, items[q].p.w};
+    }
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
+int cm_map_full_host(cm_ctx* ctx, int stream_index, float leaf, cm_point* out, size_t cap, size_t* n_out) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (stream_index < 0 || stream_index >= ctx->map_streams || !n_out || !(leaf > 0.f)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    // getFullMap: for every cube in index order: VoxelGrid(leaf) of its corner cloud, then of its surf cloud
+    ExportedCloud e[2];
+    for (int cls = 0; cls < 2; cls++) { const int rc = export_class(ctx, stream_index, cls, e[cls]); if (rc < 0) return rc; }
+    struct Seg { int cube, cls; size_t first, count; };
+    std::vector<float4> sorted[2];
+    std::vector<Seg> segs;
+    for (int cls = 0; cls < 2; cls++) {
+      const float mleaf = cls == 0 ? ctx->cfg.map_filter_corner : ctx->cfg.map_filter_surf;
+      VoxOrder vo{1.0f / mleaf};
+      std::vector<size_t> order(e[cls].pts.size());
+      for (size_t q = 0; q < order.size(); q++) order[q] = q;
+      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        if (e[cls].cube[a] != e[cls].cube[b]) return e[cls].cube[a] < e[cls].cube[b];
+        return vo(e[cls].pts[a], e[cls].pts[b]);
+      });
+      sorted[cls].resize(order.size());
+      for (size_t q = 0; q < order.size(); q++) {
+        sorted[cls][q] = e[cls].pts[order[q]];
+        const int c = e[cls].cube[order[q]];
+        if (q == 0 || e[cls].cube[order[q - 1]] != c) segs.push_back(Seg{c, cls, q, 0});
+        segs.back().count++;
+      }
+    }
+    std::stable_sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.cube != b.cube ? a.cube < b.cube : a.cls < b.cls; });
+    *n_out = 0;
+    if (segs.empty()) return CM_OK;
+    size_t cap_in = 1;
+    for (const Seg& sg : segs) cap_in = std::max(cap_in, sg.count);
+    const int nseg = (int)segs.size();
+    std::vector<float4> packed((size_t)nseg * cap_in);
+    std::vector<int> n_in(nseg);
+    for (int q = 0; q < nseg; q++) {
+      n_in[q] = (int)segs[q].count;
+      memcpy(&packed[(size_t)q * cap_in], &sorted[segs[q].cls][segs[q].first], segs[q].count * sizeof(float4));
+    }
+    ctx->d_vin.reserve(packed.size() * sizeof(float4)); ctx->d_vout.reserve(packed.size() * sizeof(float4));
+    ctx->d_vn_in.reserve(sizeof(int) * nseg); ctx->d_vn_out.reserve(sizeof(int) * nseg); ctx->d_flag.reserve(sizeof(int));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vin.p, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_vn_in.p, n_in.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), st));
+    ctx->voxel.run(nseg, (const float4*)ctx->d_vin.p, (const int*)ctx->d_vn_in.p, (int)cap_in, (int)cap_in, leaf, (float4*)ctx->d_vout.p,
+                   (int*)ctx->d_vn_out.p, (int)cap_in, (int*)ctx->d_flag.p, st);
+    std::vector<int> n_o(nseg);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n_o.data(), ctx->d_vn_out.p, sizeof(int) * nseg, cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(packed.data(), ctx->d_vout.p, packed.size() * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+    size_t o = 0;
+    for (int q = 0; q < nseg; q++)
+      for (int r = 0; r < n_o[q]; r++, o++)
+        if (out && o < cap) { const float4 p = packed[(size_t)q * cap_in + r]; out[o] = cm_point{p.x, p.y, p.z, p.w}; }
+    *n_out = o;
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------------------------- */
 int cm_timer_record(cm_ctx* ctx, int which) {
   if (!ctx || which < 0 || which > 1) return CM_ERR_ARG;
