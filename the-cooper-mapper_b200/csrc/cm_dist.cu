@@ -209,17 +209,20 @@ int cm_dist_allreduce_host(cm_ctx* ctx, double* vec, int n, int repeat, float* m
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     if (repeat < 1) repeat = 1;
     float ms = 0.f;
-    for (int k = 0; k < repeat; k++) {
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, vec, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-      if (k == repeat - 1 || k == 0) cudaEventRecord(k == 0 ? e0 : e1, ctx->stream);
-      const int rc = dist_allreduce(ctx, (double*)b.p, n, ctx->stream);
-      if (rc < 0) return rc;
+    if (repeat > 1) {   // timing: the exchange kernel alone, back to back, on a vector of zeros (sums stay zero)
+      CM_CUDA_CHECK(ctx, cudaMemsetAsync(b.p, 0, sizeof(double) * n, ctx->stream));
+      for (int k = 0; k < 3; k++) { const int rc = dist_allreduce(ctx, (double*)b.p, n, ctx->stream); if (rc < 0) return rc; }
+      cudaEventRecord(e0, ctx->stream);
+      for (int k = 0; k < repeat; k++) { const int rc = dist_allreduce(ctx, (double*)b.p, n, ctx->stream); if (rc < 0) return rc; }
+      cudaEventRecord(e1, ctx->stream);
+      CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaEventElapsedTime(&ms, e0, e1);
     }
-    cudaEventRecord(e1, ctx->stream);
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, vec, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    { const int rc = dist_allreduce(ctx, (double*)b.p, n, ctx->stream); if (rc < 0) return rc; }
     std::vector<double> out(n);
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(out.data(), b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     memcpy(vec, out.data(), sizeof(double) * n);
     if (ms_per_call) *ms_per_call = ms / (float)repeat;
