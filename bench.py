@@ -524,7 +524,12 @@ def run_config2(args, synth, rank, world, local_rank):
         peak, peak_src = measured_peak()
         step_bytes = 16.0 * S * K * NPTS + 16.0 * cnt["feat"] + 96.0 * cnt["qi"] + 32.0 * cnt["ins"]
         step_gbs = step_bytes / (ms_total * 1e-3) / 1e9
-        big = [e for e in kernels if e["share_of_kernel_time"] and e["share_of_kernel_time"] >= 0.05]
+        # every kernel >= 5 % of the step's kernel time, then the next longest ones until the list covers >= 92 % of it
+        big, cum = [], 0.0
+        for e in kernels:   # sorted, longest first
+            sh = e["share_of_kernel_time"] or 0.0
+            if sh >= 0.05 or cum < 0.92:
+                big.append(e); cum += sh
         dom = next((e for e in kernels if e["frac"]), None)          # longest kernel with an algorithmic-bytes figure
         if kernels and kernels[0]["frac"]:
             dom = kernels[0]
