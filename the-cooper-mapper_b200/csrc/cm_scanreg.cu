@@ -28,6 +28,7 @@ enum { L_CORNER_SHARP = 1, L_SURFACE_FLAT = -1, L_ONESIDE_FLAT = 5, L_MESSY = 9,
 #define SR_THREADS 512
 #define SR_MAXR 8          // curvatureRegion upper bound
 #define SR_MAXREG 16       // nFeatureRegions upper bound
+#define SR_P1REGS 12       // pass 1 keeps regions of up to 32 * SR_P1REGS cells in registers
 #define SR_MAXCOLS 8192     // columns per ring the shared-memory layout can hold at most (scanreg_smem_bytes rejects more)
 
 // ------------------------------------------------------------------------------------------------------------
@@ -516,7 +517,9 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
   signed char* wfl = reinterpret_cast<signed char*>(lst[2]);   // window result: 1 line, 3 no line      (first half of lst[2])
   signed char* wcand = wfl + cap;                               // 1: the cell is a pass-3 candidate    (second half of lst[2])
   unsigned short* wlist = lst[3];                               // windows some candidate needs
-  unsigned short* slist = ord;                                  // windows whose eigen-solve cannot be skipped
+  // windows whose eigen-solve cannot be skipped: the tail of `key` behind wxy (KEYN * 8 >= 10 * cap bytes, wxy takes 8 * cap)
+  unsigned short* slist = reinterpret_cast<unsigned short*>(key) + 4 * cap;
+  unsigned int* ckey = reinterpret_cast<unsigned int*>(key);    // curvature bits of the candidates (rank sort, before wxy is written)
   // ---- cells above the curvature threshold, in index order (they are the pass-3 candidates, :305-314) -------------
   {
     unsigned int m = 0;
@@ -572,7 +575,36 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     for (int j = 0; j < NR; j++) {
       const int sp = reg_sp[j], ep = reg_ep[j];
       if (lane == 0) p1_begin[j] = np1;
-      if (ep >= 0) {
+      if (ep >= 0 && ep - sp + 1 <= 32 * SR_P1REGS) {
+        // the region's candidates live in registers: cell sp + lane + 32 r in kreg[r], key = curvature bits (curvatures are >= 0, so
+        // the bit pattern orders like the value), 0xFFFFFFFF = not a candidate.  One pick = a local arg-min, two warp reductions
+        // (smallest bits, then the smallest cell among equal bits: the (curvature, index) order of the stable sort) and the +-R
+        // suppression applied to the registers
+        unsigned int kreg[SR_P1REGS];
+#pragma unroll
+        for (int r = 0; r < SR_P1REGS; r++) {
+          const int c = sp + lane + 32 * r;
+          unsigned int kv = 0xFFFFFFFFu;
+          if (c <= ep) { const float cv = curv[c]; if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) kv = __float_as_uint(cv); }
+          kreg[r] = kv;
+        }
+        for (int k = 0; k < prm.max_flat; k++) {
+          unsigned int m = kreg[0]; int mr = 0;
+#pragma unroll
+          for (int r = 1; r < SR_P1REGS; r++) if (kreg[r] < m) { m = kreg[r]; mr = r; }
+          const unsigned int mb = __reduce_min_sync(0xffffffffu, m);
+          if (mb == 0xFFFFFFFFu) break;
+          const int c = (int)__reduce_min_sync(0xffffffffu, m == mb ? (unsigned int)(sp + lane + 32 * mr) : 0x7fffffffu);
+#pragma unroll
+          for (int r = 0; r < SR_P1REGS; r++) { const int d = sp + lane + 32 * r - c; if (d >= -R && d <= R) kreg[r] = 0xFFFFFFFFu; }
+          if (lane <= 2 * R) state[c - R + lane] = P_SURF_PICKED_NEAR;   // markAsPicked: c-R .. c+R
+          if (lane == 0 && np1 < SR_MAXREG * 8) p1buf[np1] = (unsigned short)c;
+          np1++;
+        }
+        __syncwarp();
+        for (int c = sp + lane; c <= ep; c += 32) snap[c] = state[c];   // what passes 2 and 3 of region j see
+        __syncwarp();
+      } else if (ep >= 0) {
         for (int k = 0; k < prm.max_flat; k++) {
           unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
           for (int c = sp + lane; c <= ep; c += 32) {
@@ -599,7 +631,23 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
     if (lane == 0) p1_begin[NR] = np1;
   } else {
     const int NT = SR_THREADS - 32, t = tid - 32;
-    // phase A: covariance of every needed window + the cheap exact test that rules most of them out (window_not_line)
+    // ---- descending (curvature, index) order inside every region: rank by counting.  The candidate list is in index order, so
+    //      an equal curvature later in the list wins the tie: two loops of 32-bit compares on the curvature bits.  Independent
+    //      of the picks and of the labels: done here, while warp 0 walks its chain ------------------------------------------------
+    for (int i = t; i < m_all; i += NT) ckey[i] = __float_as_uint(curv[nfl[i]]);   // curvatures are >= 0: bit order = value order
+    asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS - 32));
+    for (int i = t; i < m_all; i += NT) {
+      const int c = nfl[i];
+      const int rj = region_of(c);
+      const unsigned int ki = ckey[i];
+      const int b0 = nf_begin[rj], b1 = nf_begin[rj + 1];
+      int rank = 0;
+      for (int k = b0; k < i; k++) rank += (ckey[k] > ki) ? 1 : 0;
+      for (int k = i + 1; k < b1; k++) rank += (ckey[k] >= ki) ? 1 : 0;
+      ord[b0 + rank] = (unsigned short)c;
+    }
+    // phase A (writes wfl and slist only; wxy, which shares the bytes of ckey, is written after the next barrier):
+    // covariance of every needed window + the cheap exact test that rules most of them out (window_not_line)
     for (int i = t; i < n_win; i += NT) {
       const int w = wlist[i];
       float cx, cy, cz, A[6];
@@ -635,22 +683,6 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
       }
       lab[c] = (signed char)l;
     }
-  }
-  __syncthreads();
-  // ---- descending (curvature, index) order inside every region: rank by counting.  The candidate list is in index order, so
-  //      an equal curvature later in the list wins the tie: two loops of 32-bit compares on the curvature bits ---------------
-  unsigned int* ckey = reinterpret_cast<unsigned int*>(key);
-  for (int i = tid; i < m_all; i += SR_THREADS) ckey[i] = __float_as_uint(curv[nfl[i]]);   // curvatures are >= 0: bit order = value order
-  __syncthreads();
-  for (int i = tid; i < m_all; i += SR_THREADS) {
-    const int c = nfl[i];
-    const int rj = region_of(c);
-    const unsigned int ki = ckey[i];
-    const int b0 = nf_begin[rj], b1 = nf_begin[rj + 1];
-    int rank = 0;
-    for (int k = b0; k < i; k++) rank += (ckey[k] > ki) ? 1 : 0;
-    for (int k = i + 1; k < b1; k++) rank += (ckey[k] >= ki) ? 1 : 0;
-    ord[b0 + rank] = (unsigned short)c;
   }
   __syncthreads();
   // `key` is free again: carve four u16 prefix arrays out of it
