@@ -213,6 +213,17 @@ int cm_pipeline_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int col
                           cm_match_stats* stats);
 int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, const cm_iso* odom, cm_iso* mapped,
                          cm_match_stats* stats);
+/* The same for sweeps the way a nodelet holds them after pcl::fromROSMsg (util/ros_utils.h:27-35): ONE cloud per stream,
+ * clouds[s] = &cloud_s->points[0], in ordinary (pageable) host memory, points `stride` bytes apart with x, y, z as three floats at
+ * offset 0 -- stride 32 for pcl::PointXYZI, 48 for PointXYZINormal, 16 for cm_point, 12 for packed coordinates.  The library
+ * gathers the coordinates into its own pinned staging buffers with worker threads (COOPERMAP_STAGE_THREADS, default: the cores
+ * of the calling thread's affinity mask, at most 16), uploads 12 bytes per point chunk by chunk while the next chunk is being
+ * packed, and expands them on the device; the intensity is not transferred (scan registration replaces it with ring + relTime,
+ * OrganizedScanRegistration.cpp:109-110).  The clouds may be reused as soon as the call returns; the slot is keyed by clouds[0].
+ * Results are bit-identical to the packed entries. */
+int cm_pipeline_prefetch_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols);
+int cm_pipeline_step_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols, const cm_iso* odom,
+                                  cm_iso* mapped, cm_match_stats* stats);
 
 /* FeatureMap::addFeatureCloud(cornerCloud, surfCloud, tf) (FeatureMap.h:219-230): transform by tf[s], push into the
  * 50 m cubes, merge per voxel (= downsizeValidCloud, :289-306, restricted to the voxels that received points). */

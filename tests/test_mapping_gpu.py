@@ -166,3 +166,52 @@ def test_surround_and_full_map_clouds(cmb, oracle, synth):
     want = np.concatenate(parts)
     assert _same(ctx.map_full(0, leaf), want)
     ctx.close()
+
+
+def test_strided_pageable_sweeps_match_packed_entry(cmb, synth):
+    """cm_pipeline_prefetch_strided_host / cm_pipeline_step_strided_host: one pageable cloud per stream with the 32-byte point
+    stride of pcl::PointXYZI (and 48 / 12 byte strides) must give the poses and the map of the packed 16-byte entry, bit for bit,
+    prefetched or not."""
+    import ctypes as C
+    sc = synth.make_scene(seed=91, extent=40.0, n_boxes=12, n_poles=10)
+    S, rows, cols, NF = 3, 16, 900, 4
+    seqs = [_frames(synth, sc, NF, seed=500 + 40 * s, cols=cols) for s in range(S)]
+
+    def pcl_cloud(fr, stride):
+        """(rows, cols, 4) float32 -> flat array of rows*cols points `stride` bytes apart (x, y, z at offset 0, junk elsewhere)"""
+        n = fr.shape[0] * fr.shape[1]
+        buf = np.full((n, stride // 4), 7.25, np.float32)
+        buf[:, :3] = fr.reshape(n, 4)[:, :3]
+        if stride >= 32:
+            buf[:, 4] = fr.reshape(n, 4)[:, 3]        # PointXYZI: intensity behind the padded xyz
+        return buf
+
+    def run(mode):
+        ctx = cmb.Context(**MAP_CFG)
+        ctx.mapping_create(S, 100000, 600000)
+        out = []
+        mapped = np.empty((S, 12), np.float32); stats = (cmb.MatchStats * S)()
+        clouds = [[pcl_cloud(seqs[s][k][2], mode if mode else 32) for s in range(S)] for k in range(NF)]
+        for k in range(NF):
+            od = ctx._pack_isos([(seqs[s][k][0].astype(np.float32), seqs[s][k][1].astype(np.float32)) for s in range(S)])
+            if mode == 0:
+                fr = np.ascontiguousarray(np.stack([seqs[s][k][2] for s in range(S)]))
+                ctx.pipeline_step_packed(fr, od, mapped, stats)
+            else:
+                if k == 0:
+                    ctx.pipeline_prefetch_strided(clouds[0], rows, cols)
+                if k + 1 < NF and k != 2:                          # frame 3 is NOT prefetched: the synchronous strided path
+                    ctx.pipeline_prefetch_strided(clouds[k + 1], rows, cols)
+                ctx.pipeline_step_strided(clouds[k], rows, cols, od, mapped, stats)
+            out.append((mapped.copy(), [stats[s].iterations for s in range(S)]))
+        maps = [ctx.map_export_sorted(s, cls)[0] for s in range(S) for cls in (0, 1)]
+        ctx.close()
+        return out, maps
+
+    ref, maps_ref = run(0)
+    for stride in (32, 48, 12):
+        got, maps = run(stride)
+        for (ma, ia), (mb, ib) in zip(ref, got):
+            assert np.array_equal(ma, mb) and ia == ib, stride
+        for a, b in zip(maps_ref, maps):
+            assert _same(a, b), stride

@@ -277,6 +277,23 @@ class Context:
         return self._check(self.L.cm_pipeline_step_host(self.h, _ptr(fr), C.c_int(fr.shape[1]), C.c_int(fr.shape[2]),
                                                         _ptr(odoms_packed), _ptr(mapped_out), stats_out))
 
+    @staticmethod
+    def _cloud_ptrs(clouds):
+        """clouds: one array per stream whose rows are points (x, y, z first); returns (void*[S], stride in bytes)."""
+        stride = int(clouds[0].strides[-2]) if clouds[0].ndim >= 2 else int(clouds[0].strides[0])
+        arr = (C.c_void_p * len(clouds))(*[c.ctypes.data for c in clouds])
+        return arr, stride
+
+    def pipeline_prefetch_strided(self, clouds, rows, cols):
+        """cm_pipeline_prefetch_strided_host: one host cloud per stream, any point stride (pcl::PointXYZI = 32 bytes), pageable memory."""
+        arr, stride = self._cloud_ptrs(clouds)
+        return self._check(self.L.cm_pipeline_prefetch_strided_host(self.h, arr, C.c_size_t(stride), C.c_int(rows), C.c_int(cols)))
+
+    def pipeline_step_strided(self, clouds, rows, cols, odoms_packed, mapped_out, stats_out):
+        arr, stride = self._cloud_ptrs(clouds)
+        return self._check(self.L.cm_pipeline_step_strided_host(self.h, arr, C.c_size_t(stride), C.c_int(rows), C.c_int(cols),
+                                                                _ptr(odoms_packed), _ptr(mapped_out), stats_out))
+
     def map_insert(self, corners, surfs, tfs):
         """FeatureMap::addFeatureCloud per stream."""
         cb, cn, ccap = self._pack_clouds(corners); sb, sn, scap = self._pack_clouds(surfs)

@@ -93,8 +93,10 @@ void cm_ctx_destroy(cm_ctx* ctx) {
     if (ctx->pipe[i].copied2) cudaEventDestroy(ctx->pipe[i].copied2);
     for (int j = 0; j < 2; j++) if (ctx->pipe[i].copied_x[j]) cudaEventDestroy(ctx->pipe[i].copied_x[j]);
     if (ctx->pipe[i].h_n5) cudaFreeHost(ctx->pipe[i].h_n5);
+    if (ctx->pipe[i].h_xyz) cudaFreeHost(ctx->pipe[i].h_xyz);
   }
   cm::dist_destroy(ctx);
+  cm::stage_pool_destroy(ctx);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;

@@ -36,6 +36,7 @@ struct DistDev {                     // what the exchange kernel sees
   unsigned long long* flags_peer[CM_DIST_MAX_RANKS];  // their sequence numbers
   const double* gathered;                             // all-gather transport: [nranks][n] (no IPC)
 };
+struct StagePool;
 struct DistState {
   bool on = false;
   void* comm = nullptr;              // ncclComm_t
@@ -111,6 +112,8 @@ struct cm_ctx {
     const void* src = nullptr; int rows = 0, cols = 0; bool is_host = false;   // what was prefetched (NULL: free)
     cudaEvent_t done = nullptr, copied = nullptr, copied2 = nullptr, copied_x[2] = {nullptr, nullptr};
     size_t frames_valid = 0;
+    // strided / pageable sweeps (cm_stage.cu): packed xyz staging, pinned on the host and its device copy
+    cm::DeviceBuffer frames_xyz; void* h_xyz = nullptr; size_t h_xyz_cap = 0;
     // feature counts read back by the prefetch itself (side stream -> pinned host memory): the step that
     // consumes the slot starts without a host round trip
     int* h_n5 = nullptr; int h_streams = 0; bool counts_ready = false;
@@ -124,6 +127,7 @@ struct cm_ctx {
   int p_cap = 0;
   // a prefetch registered with cm_pipeline_prefetch_deferred_*: issued by the next cm_pipeline_step right after it has submitted
   // its Gauss-Newton loop, so that the host time of the submission hides behind device work
+  cm::StagePool* stage_pool = nullptr;   // worker threads that repack strided host sweeps (cm_stage.cu)
   const void* defer_frames = nullptr; int defer_rows = 0, defer_cols = 0; bool defer_is_host = false; int defer_rc = 0;
 };
 
@@ -134,6 +138,8 @@ void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L);
 void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_match_stats* out);
 int dist_allreduce(cm_ctx* ctx, double* d_vec, int n, cudaStream_t stream);   // in-place sum over the ranks (cm_dist.cu)
 void dist_destroy(cm_ctx* ctx);
+void stage_pool_destroy(cm_ctx* ctx);
+int stage_upload_strided(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const void* const* clouds, size_t stride, int rows, int cols, cudaStream_t consumer);
 }  // namespace cm
 
 extern "C" int cm_match_stateless_dev(cm_ctx* ctx, const float4* d_rc, size_t nrc, const float4* d_rs, size_t nrs, const float4* d_c, size_t nc,

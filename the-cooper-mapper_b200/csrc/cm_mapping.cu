@@ -149,7 +149,7 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
   return CM_OK;
 }
 
-static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host);
+static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host, const void* const* clouds = nullptr, size_t stride = 0);
 // the prefetch registered with cm_pipeline_prefetch_deferred_* (if any): submitted while the device works on the current step
 static void issue_deferred_prefetch(cm_ctx* ctx) {
   if (!ctx->defer_frames) return;
@@ -616,7 +616,8 @@ static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int c
                              max_s, odom, mapped, stats, false);
 }
 
-static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
+// clouds != NULL: one strided host cloud per stream (cm_pipeline_prefetch_strided_host); `frames` is then the slot key, clouds[0]
+static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host, const void* const* clouds, size_t stride) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
   if (!frames || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
   if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
@@ -634,7 +635,12 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
     if (!slot.copied2) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied2, cudaEventDisableTiming));
     // a free slot fed a step that has returned (the pipeline entries synchronise): nothing reads its buffers any more
     const float4* d_frames = (const float4*)frames;
-    if (is_host) {
+    if (clouds) {
+      const int rc = stage_upload_strided(ctx, slot, clouds, stride, rows, cols, ctx->side_stream);
+      if (rc != CM_OK) return rc;
+      slot.frames_valid = 0;
+      d_frames = (const float4*)slot.frames.p;
+    } else if (is_host) {
       const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
       slot.frames.reserve(bytes);
       // upload on its own streams: the copy of sweep k+2 runs while sweep k+1 is in scan registration
@@ -683,7 +689,7 @@ static int pipeline_prefetch(cm_ctx* ctx, const void* frames, int rows, int cols
 }
 
 static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host, const cm_iso* odom, cm_iso* mapped,
-                         cm_match_stats* stats) {
+                         cm_match_stats* stats, const void* const* clouds = nullptr, size_t stride = 0) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
   if (!frames || !odom || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
   if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "cols too large for one CTA per ring");
@@ -703,7 +709,15 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
     }
     cm_ctx::PipeSlot& slot = ctx->pipe[CM_PIPE_SLOTS];
     const float4* d_frames = (const float4*)frames;
-    if (is_host) {
+    if (clouds) {
+      if (!ctx->copy_stream) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      if (!ctx->copy_stream2) CM_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+      if (!slot.copied) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied, cudaEventDisableTiming));
+      if (!slot.copied2) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&slot.copied2, cudaEventDisableTiming));
+      const int rc = stage_upload_strided(ctx, slot, clouds, stride, rows, cols, ctx->stream);
+      if (rc != CM_OK) return rc;
+      d_frames = (const float4*)slot.frames.p;
+    } else if (is_host) {
       const size_t bytes = (size_t)ctx->map_streams * rows * cols * sizeof(cm_point);
       slot.frames.reserve(bytes);
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames.p, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -722,6 +736,22 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
 
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch(ctx, frames, rows, cols, true); }
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch(ctx, d_frames, rows, cols, false); }
+static bool strided_args_ok(cm_ctx* ctx, const void* const* clouds, size_t stride) {
+  if (!clouds || stride < 12 || (stride & 3)) return false;
+  for (int s = 0; s < ctx->map_streams; s++) if (!clouds[s] || ((uintptr_t)clouds[s] & 3)) return false;
+  return true;
+}
+int cm_pipeline_prefetch_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!strided_args_ok(ctx, clouds, stride)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  return pipeline_prefetch(ctx, clouds[0], rows, cols, true, clouds, stride);
+}
+int cm_pipeline_step_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols, const cm_iso* odom,
+                                  cm_iso* mapped, cm_match_stats* stats) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!strided_args_ok(ctx, clouds, stride)) return fail(ctx, CM_ERR_ARG, "bad argument");
+  return pipeline_step(ctx, clouds[0], rows, cols, true, odom, mapped, stats, clouds, stride);
+}
 static int pipeline_prefetch_deferred(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
   if (!frames || rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
