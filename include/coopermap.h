@@ -136,10 +136,12 @@ typedef struct cm_scanreg_out {
 int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams, int rows, int cols, cm_scanreg_out* out);
 
 /* MultiScanRegistration::process (MultiScanRegistration.cpp:95-200) + extractFeatures for ONE raw azimuth-major sweep of
- * n points of a spinning multi-beam LiDAR (lidar: 0 VLP-16, 1 HDL-32, 2 HDL-64E; ring mappers MultiScanRegistration.h:90-102).
- * The O(n) trigonometric front end (axis swap, ring from the elevation angle, azimuth unwrap, relTime) runs on the host
- * with libm exactly like the reference; feature extraction runs on the device.  rows_out / cols_out return the ring-major
- * layout (rings x longest ring) that the optional full-resolution outputs of `out` use (size them for n entries). */
+ * n points of a spinning multi-beam LiDAR (lidar: 0 VLP-16, 1 HDL-32, 2 HDL-64E -- linear ring mappers, MultiScanRegistration.h:90-102;
+ * 3 Pandar40 -- MultiScanMapperP, MultiScanRegistration.h:24-42 with lidar_type.h:78-104).  The whole front end (axis swap, ring from
+ * the elevation angle, azimuth unwrap with the half-sweep flag, relTime, stable per-ring append) runs on the device; atan / atan2
+ * are the library's correctly rounded cm_atanf / cm_atan2f (glibc's float versions differ from them by 1 ulp on ~15 % of the
+ * inputs; the oracle uses the same functions).  rows_out / cols_out return the ring-major layout (rings x longest ring); the
+ * optional full-resolution outputs of `out` come back in the concatenated _laserCloud order (size them for n entries). */
 int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out);
 
 /* pcl::VoxelGrid<pcl::PointXYZI>::filter with a cubic leaf, batched over nseg independent clouds: cloud s is

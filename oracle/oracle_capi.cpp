@@ -58,7 +58,7 @@ void cmo_iso_to_twist(const float* R, const float* t, float* pose) { Iso i; std:
 
 // same op codes as cm_debug_math_host (include/coopermap.h): the shared header compiled for the HOST
 void cmo_debug_math(int op, const float* in, size_t n, float* out) {
-  static const int ni[7] = {42, 20, 6, 36, 36, 36, 6}, no[7] = {6, 3, 12, 42, 6, 36, 15};
+  static const int ni[8] = {42, 20, 6, 36, 36, 36, 6, 2}, no[8] = {6, 3, 12, 42, 6, 36, 15, 2};
   for (size_t t = 0; t < n; t++) {
     const float* a = in + t * ni[op]; float* o = out + t * no[op];
     if (op == 0) { float A[36], b[6]; std::memcpy(A, a, 144); std::memcpy(b, a + 36, 24); cm::colpiv_qr_solve<6, 6>(A, b, o); }
@@ -67,6 +67,7 @@ void cmo_debug_math(int op, const float* in, size_t n, float* out) {
     else if (op == 3) cm::eig_sym<6>(a, o, o + 6);
     else if (op == 4) cm::eig_sym<6>(a, o, (float*)nullptr);
     else if (op == 5) { float inv[36]; bool ok = cm::inverse_lu<6>(a, inv); for (int i = 0; i < 36; i++) o[i] = ok ? inv[i] : 0.f; }
+    else if (op == 7) { o[0] = cm::cm_atan2f(a[0], a[1]); o[1] = cm::cm_atanf(a[0] / a[1]); }
     else if (op == 6) { cm::pose_to_matrix(a, o); for (int i = 0; i < 3; i++) cm::cm_sincosf(a[i], o + 9 + i, o + 12 + i); }
   }
 }

@@ -109,7 +109,7 @@ def iso_to_twist(R, t):
     return pose
 
 
-MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15)}
+MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15), 7: (2, 2)}
 
 
 def debug_math(op, inputs):

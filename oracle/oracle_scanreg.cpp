@@ -302,19 +302,33 @@ void scanreg_organised(const ScanRegParams& prm, const float* xyzi, int rows, in
   extract_features(prm, r);
 }
 
-// MultiScanRegistration.cpp:95-200
+// ring of a vertical angle in degrees for the Pandar40 (MultiScanMapperP::getRingForAngle = scanID_pandar(rad2deg(angle)),
+// MultiScanRegistration.h:37, lidar_type.h:78-104): piecewise-linear bins; angles no branch covers (exactly -15, -5.8, or >= 7.5
+// degrees; the reference also prints "ERROR" for the last) fall to ring 0
+static int scan_id_pandar(float angle) {
+  int scanID = 0;
+  if (angle < -15.0) scanID = 0;
+  else if (angle > -15.0 && angle < -5.8) scanID = (int)(angle + 16.0 + 0.5);
+  else if (angle > -5.8 && angle < 2.8) scanID = (int)((angle + 5.667) / 0.33 + 0.5) + 10;
+  else if (angle > 1.8 && angle < 7.5) scanID = (int)(angle - 2.0 + 0.5) + 34;
+  return scanID;
+}
+
+// MultiScanRegistration.cpp:95-200.  lidar: 0 VLP-16, 1 HDL-32, 2 HDL-64E (linear mappers, MultiScanRegistration.h:90-102),
+// 3 Pandar40 (MultiScanMapperP, :24-42).  atan / atan2 through cm_atanf / cm_atan2f (canonical, see cm_math.h).
 void scanreg_sweep(const ScanRegParams& prm, const float* xyzi, int n, int lidar, ScanRegResult& r) {
   r = ScanRegResult();
   float lower, upper; int nRings;
   if (lidar == 0) { lower = -15; upper = 15; nRings = 16; }
   else if (lidar == 1) { lower = -30.67f; upper = 10.67f; nRings = 32; }
+  else if (lidar == 3) { lower = -15.444f; upper = 6.96f; nRings = 40; }
   else { lower = -24.9f; upper = 2; nRings = 64; }
   float factor = (nRings - 1) / (upper - lower);   // MultiScanRegistration.h:63
   std::vector<std::vector<PointIN>> rings(nRings);
   if (n > 0) {
     const float* in = xyzi;
-    float startOri = -std::atan2(in[1], in[0]);
-    float endOri = -std::atan2(in[4 * (n - 1) + 1], in[4 * (n - 1) + 0]) + 2 * float(M_PI);
+    float startOri = -cm::cm_atan2f(in[1], in[0]);
+    float endOri = -cm::cm_atan2f(in[4 * (n - 1) + 1], in[4 * (n - 1) + 0]) + 2 * float(M_PI);
     if (endOri - startOri > 3 * M_PI) endOri -= 2 * M_PI;
     else if (endOri - startOri < M_PI) endOri += 2 * M_PI;
     bool halfPassed = false;
@@ -323,10 +337,11 @@ void scanreg_sweep(const ScanRegParams& prm, const float* xyzi, int n, int lidar
       point.x = in[4 * i + 1]; point.y = in[4 * i + 2]; point.z = in[4 * i + 0]; point.intensity = in[4 * i + 3];
       if (!std::isfinite(point.x) || !std::isfinite(point.y) || !std::isfinite(point.z)) continue;
       if (point.x * point.x + point.y * point.y + point.z * point.z < 0.0001) continue;
-      float angle = std::atan(point.y / std::sqrt(point.x * point.x + point.z * point.z));
-      int scanID = int(((angle * 180 / M_PI) - lower) * factor + 0.5);   // MultiScanRegistration.h:85-87
+      float angle = cm::cm_atanf(point.y / std::sqrt(point.x * point.x + point.z * point.z));
+      int scanID = lidar == 3 ? scan_id_pandar((float)(angle * 180.0 / M_PI))   // rad2deg(float), math_utils.h:24
+                              : int(((angle * 180 / M_PI) - lower) * factor + 0.5);   // MultiScanRegistration.h:85-87
       if (scanID >= nRings || scanID < 0) continue;
-      float ori = -std::atan2(point.x, point.z);
+      float ori = -cm::cm_atan2f(point.x, point.z);
       if (!halfPassed) {
         if (ori < startOri - M_PI / 2) ori += 2 * M_PI;
         else if (ori > startOri + M_PI * 3 / 2) ori -= 2 * M_PI;

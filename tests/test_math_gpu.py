@@ -28,10 +28,14 @@ def _inputs(op, n, rng):
         return (rng.normal(size=(n, 36)) + 2 * np.eye(6).ravel()).astype(np.float32)
     if op == 6:
         return (rng.uniform(-1, 1, (n, 6)) * np.array([3.2, 1.6, 3.2, 100, 100, 100])).astype(np.float32)
+    if op == 7:
+        x = (rng.uniform(-1, 1, (n, 2)) * rng.choice([1e-3, 1.0, 120.0], (n, 2))).astype(np.float32)
+        x[::97, 0] = 0.0; x[::89, 1] = 0.0; x[::101] = np.abs(x[::101])
+        return x
     raise ValueError(op)
 
 
-@pytest.mark.parametrize("op", range(7))
+@pytest.mark.parametrize("op", range(8))
 def test_math_device_equals_host(ctx, oracle, op):
     x = _inputs(op, 4096, np.random.default_rng(100 + op))
     dev = ctx.debug_math(op, x)

@@ -22,6 +22,23 @@ def test_sincos_correctly_rounded(oracle):
     assert np.all(np.abs(c - rc) <= 0.5000001 * np.spacing(np.abs(rc).astype(np.float32)))
 
 
+def test_atan_correctly_rounded(oracle):
+    """cm_atan2f / cm_atanf (the raw-sweep front end's canonical atan, cm_math.h) against float64 libm rounded to float."""
+    rng = np.random.default_rng(5)
+    x = (rng.uniform(-1, 1, (200000, 2)) * rng.choice([1e-4, 1e-2, 1.0, 150.0], (200000, 2))).astype(np.float32)
+    x[::97, 0] = 0.0; x[::89, 1] = 1e-30
+    got = oracle.debug_math(7, x)
+    want2 = np.arctan2(x[:, 0].astype(np.float64), x[:, 1].astype(np.float64)).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want1 = np.arctan((x[:, 0] / x[:, 1]).astype(np.float64)).astype(np.float32)
+    assert np.array_equal(got[:, 0].view(np.uint32), want2.view(np.uint32))
+    assert np.array_equal(got[:, 1].view(np.uint32), want1.view(np.uint32))
+    # quadrant conventions at the axes
+    ax = np.array([[0, 1], [0, -1], [1, 0], [-1, 0], [0, 0], [-0.0, -1]], np.float32)
+    g = oracle.debug_math(7, ax)[:, 0]
+    assert np.array_equal(g, np.arctan2(ax[:, 0].astype(np.float64), ax[:, 1].astype(np.float64)).astype(np.float32))
+
+
 def test_eig3_against_lapack(oracle):
     rng = np.random.default_rng(1)
     for t in range(500):

@@ -66,9 +66,10 @@ def test_scanreg_params(cmb, oracle, synth, scene_small):
     c2.close()
 
 
-@pytest.mark.parametrize("model,lidar", [("VLP-16", 0), ("HDL-64E", 2)])
+@pytest.mark.parametrize("model,lidar", [("VLP-16", 0), ("HDL-32", 1), ("HDL-64E", 2), ("Pandar40", 3)])
 def test_scanreg_raw_sweep_entry(ctx, oracle, synth, scene_small, model, lidar):
-    """MultiScanRegistration::process: host trig front end + device feature extraction == oracle, bit for bit."""
+    """MultiScanRegistration::process: DEVICE front end (ring binning, azimuth unwrap, relTime, stable per-ring append) + feature
+    extraction == oracle, bit for bit: the ring-major cloud with its curvature field, every ring range, every list."""
     sc, _, _ = scene_small
     R, t = synth.pose_matrix(0.4, 0.0, 0.0, (1.0, 0.5, 0.0))
     fr = synth.simulate_scan(sc, R, t, model, seed=21, cols=1024 if lidar == 2 else None)

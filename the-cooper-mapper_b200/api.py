@@ -126,7 +126,7 @@ class Context:
         return int(self.L.cm_launch_count(self.h))
 
     # ---- device self-test of the shared math ------------------------------------------------------------------
-    MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15)}
+    MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15), 7: (2, 2)}
 
     def debug_math(self, op, inputs):
         nin, nout = self.MATH_DIMS[op]
@@ -453,7 +453,7 @@ class Context:
         return res[0] if single else res
 
     def scanreg_sweep(self, sweep, lidar, debug=False):
-        """MultiScanRegistration::process for one raw azimuth-major sweep (n, 4); lidar 0 VLP-16, 1 HDL-32, 2 HDL-64E."""
+        """MultiScanRegistration::process for one raw azimuth-major sweep (n, 4); lidar 0 VLP-16, 1 HDL-32, 2 HDL-64E, 3 Pandar40."""
         sw = _f32(sweep, 4)
         n = max(len(sw), 1)
         out = ScanRegOut()
@@ -464,7 +464,7 @@ class Context:
         out.n = cnt.ctypes.data
         dbg = {}
         if debug:
-            rings = {0: 16, 1: 32, 2: 64}[lidar]
+            rings = {0: 16, 1: 32, 2: 64, 3: 40}[lidar]
             dbg = dict(cloud=np.empty((n, 4), np.float32), ccurv=np.empty(n, np.float32), ranges=np.empty((rings, 2), np.int32),
                        idx=[np.empty(n, np.int32) for _ in range(4)], picked=np.empty(n, np.int8),
                        curvature=np.empty(n, np.float32), label=np.empty(n, np.int8))

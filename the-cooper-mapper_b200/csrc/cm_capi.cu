@@ -326,8 +326,10 @@ void fill_scanreg_params(const cm_config& c, ScanRegLaunch& L) {
 extern "C" {
 
 // shared by the organised and the raw-sweep entries: frames (and optional tags) are HOST arrays [S][rows][cols]
+// (d_frames_in / d_tags_in non-NULL: the rows are already on the device -- the raw-sweep front end produced them there)
 static int scanreg_run_host(cm_ctx* ctx, const cm_point* frames, const float* tags, float blind_sq_override, int nstreams, int rows,
-                            int cols, cm_scanreg_out* out, size_t full_res_entries) {
+                            int cols, cm_scanreg_out* out, size_t full_res_entries, const float4* d_frames_in = nullptr,
+                            const float* d_tags_in = nullptr) {
   const cm_config& cfg = ctx->cfg;
   if (cols > 65535 || cfg.curvature_region < 1 || cfg.curvature_region > 8 || cfg.n_feature_regions < 1 || cfg.n_feature_regions > 16 ||
       cfg.max_surface_flat < 0 || cfg.max_surface_flat > 8 || cfg.max_corner_sharp < 0)
@@ -337,14 +339,17 @@ static int scanreg_run_host(cm_ctx* ctx, const cm_point* frames, const float* ta
     cudaSetDevice(cfg.device);
     cudaStream_t st = ctx->stream;
     const size_t npts = (size_t)nstreams * rows * cols;
-    ctx->d_frames.reserve(npts * sizeof(cm_point));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_frames.p, frames, npts * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (!d_frames_in) {
+      ctx->d_frames.reserve(npts * sizeof(cm_point));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_frames.p, frames, npts * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    }
     ScanRegLaunch L;
     memset(&L, 0, sizeof(L));
-    L.nstreams = nstreams; L.rows = rows; L.cols = cols; L.frames = (const float4*)ctx->d_frames.p;
+    L.nstreams = nstreams; L.rows = rows; L.cols = cols; L.frames = d_frames_in ? d_frames_in : (const float4*)ctx->d_frames.p;
     fill_scanreg_params(cfg, L);
     L.blind_sq_override = blind_sq_override;
-    if (tags) {
+    if (d_tags_in) L.tags = d_tags_in;
+    else if (tags) {
       ctx->d_tags.reserve(npts * sizeof(float));
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_tags.p, tags, npts * sizeof(float), cudaMemcpyHostToDevice, st));
       L.tags = (const float*)ctx->d_tags.p;
@@ -394,61 +399,31 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
   return scanreg_run_host(ctx, frames, nullptr, -1.f, nstreams, rows, cols, out, (size_t)nstreams * rows * cols);
 }
 
-// Raw-sweep front end, MultiScanRegistration::process (MultiScanRegistration.cpp:95-190): per point axis swap, validity,
-// ring from the elevation angle, azimuth unwrap with the half-sweep flag, relTime -- O(N) libm trigonometry whose
-// half-sweep flag is order dependent; it runs on the host (so it is bit-identical to the reference's libm), the rings are
-// handed to the same device kernels as ring-major rows with their precomputed curvature field.
+// Raw-sweep front end, MultiScanRegistration::process (MultiScanRegistration.cpp:95-190): per point axis swap, validity, ring from
+// the elevation angle, azimuth unwrap with the half-sweep flag, relTime, stable per-ring append -- on the device (cm_frontend.cu);
+// the rings go to the same extraction kernels as ring-major rows with their precomputed curvature field.  The sweep crosses PCIe
+// once, unsorted; the only host work is two atan2 for the sweep's start / end orientation.
 int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out) {
-  if (!ctx || (!sweep && n) || !out || !out->n || lidar < 0 || lidar > 2) return fail(ctx, CM_ERR_ARG, "bad argument");
+  float lo, up; int nr;
+  if (!ctx || (!sweep && n) || !out || !out->n || !frontend_mapper(lidar, &lo, &up, &nr) || n > 0x7fffffffu) return fail(ctx, CM_ERR_ARG, "bad argument");
   for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
-  float lower, upper; int nRings;                       // MultiScanRegistration.h:90-102
-  if (lidar == 0) { lower = -15; upper = 15; nRings = 16; }
-  else if (lidar == 1) { lower = -30.67f; upper = 10.67f; nRings = 32; }
-  else { lower = -24.9f; upper = 2; nRings = 64; }
-  const float factor = (nRings - 1) / (upper - lower);  // MultiScanRegistration.h:63
-  const float scanPeriod = ctx->cfg.scan_period;
-  std::vector<std::vector<cm_point>> ring_pts(nRings);
-  std::vector<std::vector<float>> ring_tag(nRings);
-  if (n > 0) {
-    float startOri = -atan2f(sweep[0].y, sweep[0].x);                                   // :103-110
-    float endOri = -atan2f(sweep[n - 1].y, sweep[n - 1].x) + 2 * float(M_PI);
-    if (endOri - startOri > 3 * M_PI) endOri -= 2 * M_PI;
-    else if (endOri - startOri < M_PI) endOri += 2 * M_PI;
-    bool halfPassed = false;
-    for (size_t i = 0; i < n; i++) {
-      cm_point p;
-      p.x = sweep[i].y; p.y = sweep[i].z; p.z = sweep[i].x; p.intensity = sweep[i].intensity;   // :120-123
-      if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
-      if (p.x * p.x + p.y * p.y + p.z * p.z < 0.0001) continue;
-      float angle = atanf(p.y / sqrtf(p.x * p.x + p.z * p.z));
-      int scanID = int(((angle * 180 / M_PI) - lower) * factor + 0.5);                   // MultiScanRegistration.h:85-87
-      if (scanID >= nRings || scanID < 0) continue;
-      float ori = -atan2f(p.x, p.z);
-      if (!halfPassed) {
-        if (ori < startOri - M_PI / 2) ori += 2 * M_PI;
-        else if (ori > startOri + M_PI * 3 / 2) ori -= 2 * M_PI;
-        if (ori - startOri > M_PI) halfPassed = true;
-      } else {
-        ori += 2 * M_PI;
-        if (ori < endOri - M_PI * 3 / 2) ori += 2 * M_PI;
-        else if (ori > endOri + M_PI / 2) ori -= 2 * M_PI;
-      }
-      float relTime = scanPeriod * (ori - startOri) / (endOri - startOri);
-      ring_pts[scanID].push_back(p);
-      ring_tag[scanID].push_back(scanID + relTime);                                      // point.curvature, :167-168
-    }
+  int rows = nr, cols = 1;
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    ctx->d_sweep.reserve((n ? n : 1) * sizeof(cm_point));
+    if (n) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sweep.p, sweep, n * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 first = n ? make_float4(sweep[0].x, sweep[0].y, sweep[0].z, 0.f) : zero;
+    const float4 last = n ? make_float4(sweep[n - 1].x, sweep[n - 1].y, sweep[n - 1].z, 0.f) : zero;
+    ctx->frontend.run((const float4*)ctx->d_sweep.p, (int)n, first, last, lidar, ctx->cfg.scan_period, st, &rows, &cols);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
-  size_t cols = 1;
-  for (int r = 0; r < nRings; r++) cols = std::max(cols, ring_pts[r].size());
-  const float qnan = nanf("");
-  std::vector<cm_point> frame((size_t)nRings * cols, cm_point{qnan, qnan, qnan, 0.f});
-  std::vector<float> tags((size_t)nRings * cols, 0.f);
-  for (int r = 0; r < nRings; r++)
-    for (size_t i = 0; i < ring_pts[r].size(); i++) { frame[r * cols + i] = ring_pts[r][i]; tags[r * cols + i] = ring_tag[r][i]; }
-  if (rows_out) *rows_out = nRings;
-  if (cols_out) *cols_out = (int)cols;
-  // the caller's optional full-resolution buffers must hold rows * cols entries; report the shape first when they are absent
-  return scanreg_run_host(ctx, frame.data(), tags.data(), 0.f, 1, nRings, (int)cols, out, n);
+  if (rows_out) *rows_out = rows;
+  if (cols_out) *cols_out = cols;
+  // full-resolution outputs come back in the reference's concatenated _laserCloud order: at most n entries
+  return scanreg_run_host(ctx, nullptr, nullptr, 0.f, 1, rows, cols, out, n, (const float4*)ctx->frontend.frame.p, (const float*)ctx->frontend.tags.p);
 }
 
 /* ---- sharded-map matching: one rank's part of ScanMatch::scanMatchScan when the reference map is split over ranks ---- */

@@ -9,7 +9,7 @@ namespace cm {
 
 // op 0: colpiv_qr_solve<6,6> (36 + 6 -> 6)   1: colpiv_qr_solve<5,3> (15 + 5 -> 3)   2: eig3_sym (6 -> 3 + 9)
 // op 3: eig_sym<6> (36 -> 6 + 36)   4: eig_sym<6> values only (36 -> 6)   5: inverse_lu<6> (36 -> 36)
-// op 6: pose_to_matrix + cm_sincosf (6 -> 9 + 3 + 3)
+// op 6: pose_to_matrix + cm_sincosf (6 -> 9 + 3 + 3)   7: cm_atan2f(y, x), cm_atanf(y / x) (2 -> 2)
 __device__ void debug_math_op(int op, const float* in, float* out) {
   if (op == 0) { float A[36], b[6], x[6]; for (int i = 0; i < 36; i++) A[i] = in[i]; for (int i = 0; i < 6; i++) b[i] = in[36 + i]; colpiv_qr_solve<6, 6>(A, b, x); for (int i = 0; i < 6; i++) out[i] = x[i]; }
   else if (op == 1) { float A[15], b[5], x[3]; for (int i = 0; i < 15; i++) A[i] = in[i]; for (int i = 0; i < 5; i++) b[i] = in[15 + i]; colpiv_qr_solve<5, 3>(A, b, x); for (int i = 0; i < 3; i++) out[i] = x[i]; }
@@ -17,6 +17,7 @@ __device__ void debug_math_op(int op, const float* in, float* out) {
   else if (op == 3) { float w[6], V[36]; eig_sym<6>(in, w, V); for (int i = 0; i < 6; i++) out[i] = w[i]; for (int i = 0; i < 36; i++) out[6 + i] = V[i]; }
   else if (op == 4) { float w[6]; eig_sym<6>(in, w, (float*)nullptr); for (int i = 0; i < 6; i++) out[i] = w[i]; }
   else if (op == 5) { float inv[36]; bool ok = inverse_lu<6>(in, inv); for (int i = 0; i < 36; i++) out[i] = ok ? inv[i] : 0.f; }
+  else if (op == 7) { out[0] = cm_atan2f(in[0], in[1]); out[1] = cm_atanf(in[0] / in[1]); }
   else if (op == 6) { float R[9]; pose_to_matrix(in, R); for (int i = 0; i < 9; i++) out[i] = R[i]; for (int i = 0; i < 3; i++) cm_sincosf(in[i], &out[9 + i], &out[12 + i]); }
 }
 __global__ void debug_math_kernel(int op, const float* in, int nin, float* out, int nout, int n) {
@@ -24,8 +25,8 @@ __global__ void debug_math_kernel(int op, const float* in, int nin, float* out, 
   if (i < n) debug_math_op(op, in + (size_t)i * nin, out + (size_t)i * nout);
 }
 int debug_math_dims(int op, int* nin, int* nout) {
-  static const int ni[7] = {42, 20, 6, 36, 36, 36, 6}, no[7] = {6, 3, 12, 42, 6, 36, 15};
-  if (op < 0 || op > 6) return -1;
+  static const int ni[8] = {42, 20, 6, 36, 36, 36, 6, 2}, no[8] = {6, 3, 12, 42, 6, 36, 15, 2};
+  if (op < 0 || op > 7) return -1;
   *nin = ni[op]; *nout = no[op];
   return 0;
 }

@@ -323,4 +323,12 @@ size_t scanreg_smem_bytes(int cols);
 int debug_math_dims(int op, int* nin, int* nout);
 void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream);
 
+// Raw-sweep front end on the device (cm_frontend.cu): MultiScanRegistration::process up to the per-ring clouds.
+struct SweepFrontEnd {
+  DeviceBuffer ring_of, hist, frame, tags;
+  void run(const float4* d_sweep, int n, const float4& first, const float4& last, int lidar, float scan_period, cudaStream_t st,
+           int* rows_out, int* cols_out);
+};
+bool frontend_mapper(int lidar, float* lower, float* upper, int* nrings);
+
 }  // namespace cm

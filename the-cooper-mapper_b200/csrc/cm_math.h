@@ -70,6 +70,62 @@ CM_HD void cm_sincosf(float x, float* s, float* c) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// atan / atan2 for the raw-sweep front end (MultiScanRegistration.cpp:103-156 calls libm's float atan / atan2): like
+// cm_sincosf a canonical definition shared by the GPU and the oracle -- evaluated in double with + - * / only
+// (x > 1: pi/2 - atan(1/x); t in [0, 1]: atan(t) = atan(k/8) + atan((t - k/8) / (1 + t k/8)), |argument| <= 1/16, Taylor series to
+// u^17) and rounded once to float: error < 1e-16 before the rounding, i.e. the correctly rounded float except within ~1e-8 ulp
+// of a rounding boundary; glibc's atanf / atan2f differ from it by 1 ulp on a few percent of the inputs.
+// ----------------------------------------------------------------------------------------------------------
+CM_HD double cm_atan_tab(int k) {   // atan(k / 8), correctly rounded doubles
+  switch (k) {
+    case 0: return 0.0;
+    case 1: return 1.24354994546761438e-01;
+    case 2: return 2.44978663126864143e-01;
+    case 3: return 3.58770670270572245e-01;
+    case 4: return 4.63647609000806094e-01;
+    case 5: return 5.58599315343562441e-01;
+    case 6: return 6.43501108793284371e-01;
+    case 7: return 7.18829999621624527e-01;
+    default: return 7.85398163397448279e-01;
+  }
+}
+CM_HD double cm_atan_pos_d(double x) {   // x >= 0 (or NaN) -> atan(x) in [0, pi/2]
+  if (!(x == x)) return x;
+  const double pio2_hi = 1.57079632679489656e+00, pio2_lo = 6.12323399573676604e-17;
+  const bool inv = x > 1.0;
+  const double t = inv ? 1.0 / x : x;           // [0, 1]; 1 / inf = 0
+  const int k = (int)(t * 8.0 + 0.5);
+  const double c = (double)k * 0.125;
+  const double u = (t - c) / (1.0 + t * c);
+  const double u2 = u * u;
+  double p = 1.0 / 17.0;
+  p = p * u2 - 1.0 / 15.0;
+  p = p * u2 + 1.0 / 13.0;
+  p = p * u2 - 1.0 / 11.0;
+  p = p * u2 + 1.0 / 9.0;
+  p = p * u2 - 1.0 / 7.0;
+  p = p * u2 + 1.0 / 5.0;
+  p = p * u2 - 1.0 / 3.0;
+  const double a = cm_atan_tab(k) + (u + u * (u2 * p));
+  return inv ? (pio2_hi - a) + pio2_lo : a;
+}
+CM_HD float cm_atanf(float x) {
+  const double a = cm_atan_pos_d(fabs((double)x));
+  return (float)copysign(a, (double)x);
+}
+CM_HD float cm_atan2f(float y, float x) {   // finite arguments or NaN (the front end drops non-finite points before it gets here)
+  const double pi_hi = 3.14159265358979312e+00, pi_lo = 1.22464679914735321e-16;
+  const double pio2_hi = 1.57079632679489656e+00, pio2_lo = 6.12323399573676604e-17;
+  const double ax = fabs((double)x), ay = fabs((double)y);
+  double a;
+  if (ax == 0.0 && ay == 0.0) a = 0.0;
+  else if (ay <= ax) a = cm_atan_pos_d(ay / ax);
+  else a = (pio2_hi - cm_atan_pos_d(ax / ay)) + pio2_lo;
+  if (x < 0.f || (x == 0.f && signbit(x) && ay == 0.0)) a = (pi_hi - a) + pi_lo;   // second / third quadrant, atan2(+-0, -0) = +-pi
+  return (float)((y < 0.f || (y == 0.f && signbit(y))) ? -a : a);
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // Givens rotation, Eigen JacobiRotation<float>::makeGivens (real case).
 // ----------------------------------------------------------------------------------------------------------
 CM_HD void make_givens(float p, float q, float* c, float* s) {

@@ -12,6 +12,13 @@ LIDARS = {
     "VLP-16": (16, 1800, -15.0, 15.0, 100.0),
     "HDL-32": (32, 2048, -30.67, 10.67, 100.0),
     "HDL-64E": (64, 2048, -24.9, 2.0, 120.0),
+    "Pandar40": (40, 1800, -15.444, 6.96, 100.0),   # MultiScanMapperP::Pandar40, MultiScanRegistration.h:39-41
+}
+# beams that are not equally spaced: elevation per ring in degrees, lowest first (Pandar40 data sheet, lidar_type.h:11-52)
+ELEVATIONS = {
+    "Pandar40": [-15.444, -14.543, -13.63, -12.705, -11.772, -10.826, -9.871, -8.908, -7.934, -6.957, -5.974, -5.647, -5.311, -4.986,
+                 -4.657, -4.321, -3.996, -3.663, -3.327, -3.0, -2.667, -2.331, -2.001, -1.667, -1.334, -1.001, -0.667, -0.334, 0.0,
+                 0.333, 0.667, 1.001, 1.333, 1.667, 2.001, 2.999, 3.996, 4.988, 5.976, 6.96],
 }
 
 
@@ -60,6 +67,8 @@ def ray_dirs(model, rows=None, cols=None, tilt_deg=None):
         R, Cn, lo, up, _ = LIDARS[model]
         rows = rows or R; cols = cols or Cn
         el = np.deg2rad(np.linspace(lo, up, rows))
+        if model in ELEVATIONS and rows == len(ELEVATIONS[model]):
+            el = np.deg2rad(np.asarray(ELEVATIONS[model], np.float64))
         az = -2.0 * np.pi * (np.arange(cols) + 0.25) / cols
         ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
         d = np.stack([ce * np.cos(az)[None, :], ce * np.sin(az)[None, :], np.broadcast_to(se, (rows, cols))], -1)
