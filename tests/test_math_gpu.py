@@ -31,6 +31,7 @@ def _inputs(op, n, rng):
     if op == 7:
         x = (rng.uniform(-1, 1, (n, 2)) * rng.choice([1e-3, 1.0, 120.0], (n, 2))).astype(np.float32)
         x[::97, 0] = 0.0; x[::89, 1] = 0.0; x[::101] = np.abs(x[::101])
+        x[(x[:, 0] == 0) & (x[:, 1] == 0), 1] = 1.0        # 0 / 0: the NaN's sign bit is platform-defined
         return x
     raise ValueError(op)
 

@@ -791,6 +791,13 @@ void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
 }
 
 // one Gauss-Newton evaluation: correspondences + rows + (partial) normal-equation sums into m.sums
+// CTAs of search_hard_kernel (grid-strided, one warp per hard query): latency-bound shell scans, so as many warps as the register
+// file holds -- 3 CTAs of 256 threads per SM at 80 registers
+static int hard_blocks_default() {
+  static const int n = []() { const char* e = getenv("COOPERMAP_HARD_BLOCKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 444; }();
+  return n;
+}
+
 void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof, bool fused, bool defer_solve) {
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
@@ -808,7 +815,7 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   if (ca.hard) {
-    const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
+    const int hb = m.hard_blocks > 0 ? m.hard_blocks : hard_blocks_default();
     if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
     else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
   }
@@ -891,7 +898,7 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   dim3 sgrid((bx * 256 + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, m.nstreams);
   if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
-  const int hb = m.hard_blocks > 0 ? m.hard_blocks : 296;
+  const int hb = m.hard_blocks > 0 ? m.hard_blocks : hard_blocks_default();
   if (m.orig_idx) CM_LAUNCH(search_hard_kernel<true>, hb, 256, 0, stream, ca);
   else CM_LAUNCH(search_hard_kernel<false>, hb, 256, 0, stream, ca);
   FusedArgs f; f.partials = m.partials; f.tickets = m.tickets; f.sums = m.sums; f.ptiles = m.partial_blocks;
