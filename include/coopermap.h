@@ -163,8 +163,8 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
  * corner / surf: /laser_cloud_corner_last and /laser_cloud_surf_last as [nstreams][cap_*] with counts n_*[s];
  * mapped[s]: /aft_mapped_to_init pose.  Steps: transformMerge (LaserMatcher.cpp:333-340), voxel-filter the frame
  * (:288-301), FeatureMap::update + surround selection (:303-325), ScanMatch::scanMatchScan on the map (:327-331),
- * transformUpdate (:342-347), FeatureMap::addFeatureCloud (:349-355).  Returns CM_ERR_UNSUPPORTED where the
- * reference would shift() its cube grid (sensor within 3 cubes of the grid border). */
+ * transformUpdate (:342-347), FeatureMap::addFeatureCloud (:349-355).  FeatureMap::shift (sensor within 3 cubes of the grid border,
+ * FeatureMap.h:232-245, 354-376) is reproduced literally, including the cubes its in-place pointer swaps move the wrong way. */
 int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
                             const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
 

@@ -291,6 +291,10 @@ size_t cmo_mapping_cloud(void* hh, int which, float* out, size_t cap) {
   if (out) std::memcpy(out, v->data(), std::min(cap, v->size()) * sizeof(PointI));
   return v->size();
 }
+void cmo_mapping_origin(void* hh, int* out3) {   // _cubeOriginWidth / Height / Depth (moved by FeatureMap::update's shift)
+  LaserMapping* m = ((MappingHandle*)hh)->m;
+  out3[0] = m->map.originW; out3[1] = m->map.originH; out3[2] = m->map.originD;
+}
 // direct map access for tests: update + surround, add
 void cmo_mapping_map_update(void* hh, const float* sensor) { ((MappingHandle*)hh)->m->map.update(sensor); }
 void cmo_mapping_map_add(void* hh, const float* corner, size_t nc, const float* surf, size_t ns, const float* R, const float* t) {

@@ -349,6 +349,11 @@ class Mapping:
         self.L.cmo_mapping_cloud(C.c_void_p(self.h), C.c_int(which), _p(out), C.c_size_t(len(out)))
         return out[:n].copy()
 
+    def origin(self):
+        o = np.zeros(3, np.int32)
+        self.L.cmo_mapping_origin(C.c_void_p(self.h), _p(o))
+        return o.tolist()
+
     def map_update(self, sensor):
         s = _f32(sensor)
         self.L.cmo_mapping_map_update(C.c_void_p(self.h), _p(s))

@@ -85,15 +85,52 @@ def test_pipeline_step_equals_scanreg_plus_mapping(cmb, oracle, synth):
             assert stats[s]["iterations"] == ost["iterations"]
 
 
-def test_lasermapping_mirror_and_shift_unsupported(cmb, oracle, synth):
+def test_lasermapping_mirror(cmb, oracle, synth):
     sc = synth.make_scene(seed=41, extent=40.0, n_boxes=12, n_poles=10)
     lm = cmb.LaserMapping(max_corner_points=50000, max_surf_points=300000, **MAP_CFG)
     R, t, fr = _frames(synth, sc, 1)[0]
     f = oracle.scanreg_organised(fr)
     gR, gt = lm.process(R.astype(np.float32), t.astype(np.float32), f["lessSharp"], f["lessFlat"])
     assert lm.last_stats["status"] == 1                      # empty map: "reference cloud points too few"
-    with pytest.raises(cmb.CoopermapError):                  # 200 m up: the reference would shift() its cube grid
-        lm.process(R.astype(np.float32), np.array([0, 0, 200], np.float32), f["lessSharp"], f["lessFlat"])
+    # 200 m up: the reference shift()s its cube grid (FeatureMap.h:232-245) -- so does the device map
+    lm.process(R.astype(np.float32), np.array([0, 0, 200], np.float32), f["lessSharp"], f["lessFlat"])
+
+
+@pytest.mark.parametrize("heading", [(1.0, 0.0), (-1.0, 0.0), (-0.8, 0.6), (0.7, -0.7)])
+def test_feature_map_shift_matches_literal_reference(cmb, oracle, synth, heading):
+    """FeatureMap::shift (FeatureMap.h:354-376) when the sensor walks out of the central cubes of a small grid: towards +x the
+    reference's in-place pointer swaps are a proper shift, towards -x (or -x / +y ...) they move every cube the WRONG way (the
+    stored clouds end up two cubes from where their coordinates say and partly drop out of the surround window).  The device map
+    reproduces both: poses, iterations, row counts, surround clouds and the stored cubes are those of the literal oracle."""
+    sc = synth.make_scene(seed=77, extent=220.0, n_boxes=90, n_poles=60)
+    grid = dict(cube_w=9, cube_h=9, cube_d=7, cube_size=40.0, valid_distance=120.0)
+    ctx = cmb.Context(**MAP_CFG, **grid)
+    ctx.mapping_create(1, 200000, 900000)
+    om = oracle.Mapping(map_params=dict(ORACLE_MAP, cubeW=9, cubeH=9, cubeD=7, cubeSize=40.0, validDistance=120.0))
+    hx, hy = heading
+    n_shift_frames = 0
+    for k in range(13):
+        pos = np.array([hx * 13.0 * k, hy * 13.0 * k, 0.0])
+        R, t = synth.pose_matrix(0.05 * np.sin(0.7 * k), 0.0, 0.0, pos)
+        fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=900 + k, cols=900)
+        rng_ = np.linalg.norm(fr[..., :3], axis=-1)
+        fr[rng_ > 80.0] = np.nan        # every return lands in a VALID cube (80 m + half a cube diagonal < 120 m): see cm_map.cu (1)
+        f = oracle.scanreg_organised(fr)
+        od = (R.astype(np.float32), (t + np.array([0.03, -0.02, 0.01])).astype(np.float32))
+        before = tuple(om.origin())
+        isos, stats = ctx.mapping_process([od], [f["lessSharp"]], [f["lessFlat"]])
+        oR, ot, ost = om.process(od[0], od[1], f["lessSharp"], f["lessFlat"])
+        n_shift_frames += tuple(om.origin()) != before
+        assert stats[0]["iterations"] == ost["iterations"] and stats[0]["rows"] == ost["rows"], (k, stats[0], ost)
+        assert (stats[0]["status"] == 1) == bool(ost["tooFewRef"]), (k, stats[0], ost)
+        assert np.array_equal(isos[0][0], oR) and np.array_equal(isos[0][1], ot), (k, isos[0], oR, ot)
+        gc, gs = ctx.map_surround(0)
+        assert _same(gc, om.map_surround(0)) and _same(gs, om.map_surround(1)), k
+    assert n_shift_frames >= 2
+    for cls, which in ((0, 4), (1, 5)):
+        g, cubes = ctx.map_export_sorted(0, cls)
+        assert _same(g, om.cloud(which))
+    ctx.close()
 
 
 def test_estimate_sized_launches_change_nothing(cmb, synth, monkeypatch):

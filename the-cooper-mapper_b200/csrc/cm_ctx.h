@@ -100,6 +100,7 @@ struct cm_ctx {
   cudaEvent_t timer[2] = {nullptr, nullptr};
   unsigned long long dbg_graph_builds = 0, dbg_stage_captures = 0;
   int est_c = 0, est_s = 0;                 // largest filtered corner / surf cloud of the previous mapping step (sizes the next step's launches)
+  unsigned long long n_shifts = 0;          // FeatureMap::shift calls that moved cubes so far
   unsigned long long insert_redos = 0;      // steps whose map insertion had to be repeated with exact sizes
   // per-step counters of the last cm_mapping_process / cm_pipeline_step (for the roofline arithmetic)
   unsigned long long last_query_iters = 0, last_queries = 0, last_inserted = 0, last_features = 0;

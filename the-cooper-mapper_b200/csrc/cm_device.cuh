@@ -48,6 +48,10 @@ struct GridView {
   int max_level;              // last shell to visit so that (max_level + 0.48) * cell >= sqrt(gate)
   const CubeWindow* window;   // NULL: no cube filtering
   const int* cube_count;      // points per 50 m cube [W*H*D] (map grids; NULL for stateless clouds)
+  // FeatureMap::shift (FeatureMap.h:354-376) moves the cube POINTERS; when it moves them the wrong way (see cm_map.cu) a point is
+  // stored in another cube than its coordinates say.  epoch[slot] names the shift history of a pool slot, eoff[3 * epoch] the
+  // displacement (in cubes) of its storage cube from its coordinate cube; displaced == 0: no such point exists (the common case)
+  const unsigned char* epoch; const int* eoff; int displaced;
 };
 
 __host__ __device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
@@ -132,11 +136,18 @@ __device__ __forceinline__ bool top5_has_tie(const Top5& t, float d6) {
   return (d6 == d4 && d4 < FLT_MAX) || t.d(0) == t.d(1) || t.d(1) == t.d(2) || t.d(2) == t.d(3) || (t.d(3) == d4 && d4 < FLT_MAX);
 }
 
-// worldToCube (FeatureMap.h:475-487) -> index into the 7x7x7 window, -1 outside it
-__device__ __forceinline__ int window_index(const CubeWindow& w, float x, float y, float z) {
-  int i = (int)(roundf(x / w.cube_size) + (float)w.origin[0]) - w.w0[0];
-  int j = (int)(roundf(y / w.cube_size) + (float)w.origin[1]) - w.w0[1];
-  int k = (int)(roundf(z / w.cube_size) + (float)w.origin[2]) - w.w0[2];
+// worldToCube (FeatureMap.h:475-487) of a map point: the cube its coordinates name plus the displacement of its epoch (see GridView)
+__device__ __forceinline__ void label_cube(const GridView& g, const CubeWindow& w, const float4& p, int slot, int* i, int* j, int* k) {
+  *i = (int)(roundf(p.x / w.cube_size) + (float)w.origin[0]);
+  *j = (int)(roundf(p.y / w.cube_size) + (float)w.origin[1]);
+  *k = (int)(roundf(p.z / w.cube_size) + (float)w.origin[2]);
+  if (g.displaced) { const int* o = g.eoff + 3 * (int)g.epoch[slot]; *i += o[0]; *j += o[1]; *k += o[2]; }
+}
+// -> index into the 7x7x7 window, -1 outside it
+__device__ __forceinline__ int window_index(const GridView& g, const CubeWindow& w, const float4& p, int slot) {
+  int i, j, k;
+  label_cube(g, w, p, slot, &i, &j, &k);
+  i -= w.w0[0]; j -= w.w0[1]; k -= w.w0[2];
   if (i < 0 || i > 6 || j < 0 || j > 6 || k < 0 || k > 6) return -1;
   return (i * 7 + j) * 7 + k;
 }
@@ -150,14 +161,15 @@ __host__ __device__ __forceinline__ int cube_owner(int i, int j, int k, int nran
 // Candidate filter codes (KnnGeom::filt): CM_FILT_NONE: every point of the grid is searched; CM_FILT_WINDOW: only points
 // whose cube is in the active window (FeatureMap::getSurroundFeature, FeatureMap.h:256-265); >= 0: only points of the
 // cube with that linear index -- the localisation matcher searches the query's own cube (FeatureMap.h:521-527).
+// slot: the candidate's pool slot (its epoch decides which cube STORES it).
 #define CM_FILT_NONE (-1)
 #define CM_FILT_WINDOW (-2)
-__device__ __forceinline__ bool cand_ok(const GridView& g, int filt, const float4& p) {
+__device__ __forceinline__ bool cand_ok(const GridView& g, int filt, const float4& p, int slot) {
   if (filt == CM_FILT_NONE) return true;
   const CubeWindow& w = *g.window;
-  if (filt == CM_FILT_WINDOW) { const int wi = window_index(w, p.x, p.y, p.z); return wi >= 0 && w.active[wi]; }
-  const int i = (int)(roundf(p.x / w.cube_size) + (float)w.origin[0]), j = (int)(roundf(p.y / w.cube_size) + (float)w.origin[1]),
-            k = (int)(roundf(p.z / w.cube_size) + (float)w.origin[2]);
+  if (filt == CM_FILT_WINDOW) { const int wi = window_index(g, w, p, slot); return wi >= 0 && w.active[wi]; }
+  int i, j, k;
+  label_cube(g, w, p, slot, &i, &j, &k);
   return i >= 0 && i < w.dims[0] && j >= 0 && j < w.dims[1] && k >= 0 && k < w.dims[2] && (i + j * w.dims[0] + k * w.dims[0] * w.dims[1]) == filt;
 }
 
@@ -171,11 +183,11 @@ __device__ __forceinline__ bool cand_ok(const GridView& g, int filt, const float
 __device__ inline bool canon_less_map(const GridView& g, const float4 pa, int slot_a, const float4 pb, int slot_b) {
   if (g.window) {
     const CubeWindow& w = *g.window;
-    const int ia = (int)(roundf(pa.x / w.cube_size) + (float)w.origin[0]), ib = (int)(roundf(pb.x / w.cube_size) + (float)w.origin[0]);
+    int ia, ja, ka, ib, jb, kb;
+    label_cube(g, w, pa, slot_a, &ia, &ja, &ka);
+    label_cube(g, w, pb, slot_b, &ib, &jb, &kb);
     if (ia != ib) return ia < ib;
-    const int ja = (int)(roundf(pa.y / w.cube_size) + (float)w.origin[1]), jb = (int)(roundf(pb.y / w.cube_size) + (float)w.origin[1]);
     if (ja != jb) return ja < jb;
-    const int ka = (int)(roundf(pa.z / w.cube_size) + (float)w.origin[2]), kb = (int)(roundf(pb.z / w.cube_size) + (float)w.origin[2]);
     if (ka != kb) return ka < kb;
   }
   const float za = floorf(pa.z * g.inv_leaf), zb = floorf(pb.z * g.inv_leaf);
@@ -236,7 +248,7 @@ __device__ __forceinline__ void scan_points(const GridView& g, unsigned int star
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       if (j0 + u < count) {
-        if (!cand_ok(g, filt, p[u])) continue;
+        if (!cand_ok(g, filt, p[u], (int)(start + j0 + u))) continue;
         float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
         float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         const int j = (int)(start + j0 + u);
@@ -320,7 +332,7 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
         for (int j = j0; j <= j1; j++)
           for (int kk = k0; kk <= k1; kk++) f = f || !w.active[(i * 7 + j) * 7 + kk];
     }
-    if (f) c.filt = CM_FILT_WINDOW;
+    if (f || g.displaced) c.filt = CM_FILT_WINDOW;   // displaced content: a nearby point may be stored in an inactive cube
   }
   // distance (voxel units) from the query to the nearest face of the level-0 block
   const float lox = (float)(c.lx * k), loy = (float)(c.ly * k), loz = (float)(c.lz * k);
@@ -364,7 +376,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
       for (int u = 0; u < 5; u++) q[u] = __ldg(g.pts + sl[u]);
 #pragma unroll
       for (int u = 0; u < 5; u++) {
-        if (cand_ok(g, c.filt, q[u])) {
+        if (cand_ok(g, c.filt, q[u], sl[u])) {
           float dx = qx - q[u].x, dy = qy - q[u].y, dz = qz - q[u].z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           top5_insert_key_unique(best, top5_key(d, kOrigIdx ? __float_as_int(q[u].w) : sl[u]), sl[u]);
@@ -423,7 +435,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
 #pragma unroll
     for (int u = 0; u < CM_KNN_UNROLL; u++) {
       kk[u] = CM_TOP5_EMPTY;
-      if ((unsigned int)u < left && (nofilt || cand_ok(g, c.filt, p[u]))) {
+      if ((unsigned int)u < left && (nofilt || cand_ok(g, c.filt, p[u], (int)(r.x + j0 + u)))) {
         float dx = qx - p[u].x, dy = qy - p[u].y, dz = qz - p[u].z;
         float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         kk[u] = top5_key(d, kOrigIdx ? __float_as_int(p[u].w) : (int)(r.x + j0 + u));
@@ -498,7 +510,7 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
         const unsigned int st = __shfl_sync(FULL, start, src), ct = __shfl_sync(FULL, count, src);
         for (unsigned int j = lane; j < ct; j += 32) {
           const float4 p = __ldg(g.pts + st + j);
-          if (!cand_ok(g, bfilter, p)) continue;
+          if (!cand_ok(g, bfilter, p, (int)(st + j))) continue;
           float ddx = bqx - p.x, ddy = bqy - p.y, ddz = bqz - p.z;
           float d = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
           const int jj = (int)(st + j);

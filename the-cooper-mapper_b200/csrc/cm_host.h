@@ -265,6 +265,8 @@ struct MapClassDev {            // one class (corner / surf) of one stream, live
   int* cube_count;              // points per 50 m cube [W*H*D]
   float leaf, inv_leaf; int kdiv;
   float cube_size; int dims[3]; int origin[3];
+  // FeatureMap::shift bookkeeping (cm_map.cu): epoch per pool slot, displacement of every epoch [256][3], the epoch new points get
+  unsigned char* epoch; int* eoff; int cur_epoch;
 };
 struct MapConfig {
   size_t max_corner, max_surf;  // capacity in points per stream
@@ -277,6 +279,10 @@ struct DeviceMap {
   MapConfig cfg;
   DeviceBuffer entries[2], cellcap[2], pending_cnt[2], pts[2], cube_count[2], cursor[2], dev[2], views[2];
   DeviceBuffer windows, flags;
+  DeviceBuffer epoch[2], eoff;                    // see MapClassDev
+  std::vector<MapClassDev> hdev[2];               // host mirror of dev[] (pointers and constants; origin / cur_epoch as of the last shift)
+  std::vector<int> h_eoff;                        // [nstreams][256][3]
+  std::vector<int> cur_epoch;                     // per stream
   DeviceBuffer n_pending[2], world[2], keys_a[2], keys_b[2], vals_a[2], vals_b[2], pending[2];   // insert scratch per class: the two classes may run on different streams
   unsigned int table_cap[2] = {0, 0}, pool_cap[2] = {0, 0};
   int shard_rank = 0, shard_nranks = 1;   // > 1 ranks: keep only the cubes cube_owner() gives this rank, plus a sqrt(5) m halo (cm_dist.cu)
@@ -294,6 +300,10 @@ struct DeviceMap {
   void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream,
               const int* step_skip = nullptr);
   size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);
+  // FeatureMap::shift(d) of stream s followed by `origin += d` (FeatureMap.h:232-245, 354-376): relabels the stored points, drops
+  // the cubes that leave the grid, recounts cube_count.  new_origin = the stream's origin after the shift.  False: more than 255
+  // wrong-way shifts (the epoch counter is a byte)
+  bool shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream);
 };
 
 // K1/K2: scan registration for organised sweeps (cm_scanreg.cu)

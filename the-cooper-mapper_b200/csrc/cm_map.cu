@@ -15,8 +15,13 @@
 //
 // Known deviations (documented in DESIGN.md): (1) points landing in a cube that is outside the valid window are
 // merged immediately, the reference leaves them unmerged until the cube becomes valid (needs ranges > ~106 m);
-// (2) FeatureMap::shift (the grid re-centring when the sensor comes within 3 cubes of the grid border, i.e. after
-// ~3 km / +-125 m vertically) is not implemented: cm_map_update reports CM_ERR_UNSUPPORTED.
+// FeatureMap::shift (the grid re-centring when the sensor comes within 3 cubes of the grid border, :232-245, 354-376) swaps cube
+// POINTERS in place while it iterates upwards.  Worked out (and checked against the literal loop for every |d| <= 2): the contents
+// move by T = -sigma * d, sigma = sign of the first non-zero component of d in (i, j, k) order, contents that leave the grid are
+// cleared.  The origin moves by +d, so for sigma < 0 this is the proper shift and for sigma > 0 every cube ends up 2 d away from
+// where the coordinates of its points say.  The map here is keyed by coordinates; a byte per pool slot (`epoch`) and a displacement
+// per epoch (`eoff`) record which cube STORES a point, which is what the surround selection, the per-cube voxel merge, the cube
+// counts and the exported clouds go by.  Without a wrong-way shift every displacement is zero and none of this is looked at.
 #include "cm_host.h"
 #include "cm_math.h"
 #include <algorithm>
@@ -182,9 +187,11 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
   const unsigned int start = m.entries[e].start, count = m.entries[e].count;
   for (unsigned int j = 0; j < count; j++) {
     float4 q = m.pts[start + j];
+    int o0 = 0, o1 = 0, o2 = 0;   // the resident point is merged only if the same CUBE stores it (a displaced epoch is another cube)
+    if (m.cur_epoch) { const int* o = m.eoff + 3 * (int)m.epoch[start + j]; o0 = o[0]; o1 = o[1]; o2 = o[2]; }
     if ((int)floorf(q.x * m.inv_leaf) == vx && (int)floorf(q.y * m.inv_leaf) == vy && (int)floorf(q.z * m.inv_leaf) == vz &&
-        world_to_cube_axis(q.x, m.cube_size, m.origin[0]) == ci && world_to_cube_axis(q.y, m.cube_size, m.origin[1]) == cj &&
-        world_to_cube_axis(q.z, m.cube_size, m.origin[2]) == ck) {
+        world_to_cube_axis(q.x, m.cube_size, m.origin[0]) + o0 == ci && world_to_cube_axis(q.y, m.cube_size, m.origin[1]) + o1 == cj &&
+        world_to_cube_axis(q.z, m.cube_size, m.origin[2]) + o2 == ck) {
       sx += q.x; sy += q.y; sz += q.z; si += q.w; cnt++;
       if (keep < 0) keep = (int)j;
       else atomicExch(flags + 1, 1);   // two resident points in one voxel (rounding drift): not merged here, only reported
@@ -231,7 +238,7 @@ __global__ void map_grow_kernel(const PendingAdd* __restrict__ pending, const un
   const unsigned int nstart = atomicAdd(m.cursor, ncap);
   if (nstart + ncap > m.pool_cap) { atomicExch(flags + 3, 1); return; }   // pool exhausted: the appends are dropped
   const unsigned int ostart = m.entries[e].start;
-  for (unsigned int j = 0; j < count; j++) m.pts[nstart + j] = m.pts[ostart + j];
+  for (unsigned int j = 0; j < count; j++) { m.pts[nstart + j] = m.pts[ostart + j]; m.epoch[nstart + j] = m.epoch[ostart + j]; }
   m.entries[e].start = nstart;
   m.cellcap[e] = ncap;
 }
@@ -249,6 +256,7 @@ __global__ void map_append_kernel(const PendingAdd* __restrict__ pending, const 
   const unsigned int j = atomicAdd(&m.entries[e].count, 1u);
   if (j < m.cellcap[e]) {
     m.pts[m.entries[e].start + j] = pa.p;
+    m.epoch[m.entries[e].start + j] = (unsigned char)m.cur_epoch;
     atomicAdd(&m.cube_count[pa.cube], 1);
     atomicAdd(m.total, 1);
   } else {
@@ -286,6 +294,7 @@ __global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, Gr
   int L = (int)ceilf(sqrtf(gate) / (0.98f * v.cell) - 0.5f);
   v.max_level = L < 0 ? 0 : L;
   v.window = windows + s; v.cube_count = m.cube_count;
+  v.epoch = m.epoch; v.eoff = m.eoff; v.displaced = m.cur_epoch > 0 ? 1 : 0;
   views[s] = v;
 }
 
@@ -303,6 +312,7 @@ __global__ void map_export_kernel(const MapClassDev* maps, int s, float4* out, i
       out[o] = p;
       int ci = world_to_cube_axis(p.x, m.cube_size, m.origin[0]), cj = world_to_cube_axis(p.y, m.cube_size, m.origin[1]),
           ck = world_to_cube_axis(p.z, m.cube_size, m.origin[2]);
+      if (m.cur_epoch) { const int* eo = m.eoff + 3 * (int)m.epoch[start + j]; ci += eo[0]; cj += eo[1]; ck += eo[2]; }
       cube_out[o] = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
     }
   }
@@ -316,6 +326,10 @@ static unsigned int pow2_at_least(size_t v) { unsigned int p = 1024; while (p < 
 void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
   nstreams = nstreams_; cfg = c;
   const int ncubes = c.dims[0] * c.dims[1] * c.dims[2];
+  h_eoff.assign((size_t)nstreams * 256 * 3, 0);
+  cur_epoch.assign(nstreams, 0);
+  eoff.reserve(h_eoff.size() * sizeof(int));
+  cudaMemsetAsync(eoff.p, 0, h_eoff.size() * sizeof(int), stream);
   for (int cls = 0; cls < 2; cls++) {
     const size_t maxpts = cls == 0 ? c.max_corner : c.max_surf;
     const unsigned int tcap = pow2_at_least(maxpts);            // cells <= points; load factor <= 0.5 when cells hold >= 2 points
@@ -326,6 +340,8 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
     pending_cnt[cls].reserve((size_t)nstreams * tcap * sizeof(unsigned int));
     pts[cls].reserve((size_t)nstreams * pool * sizeof(float4));
     cube_count[cls].reserve((size_t)nstreams * ncubes * sizeof(int));
+    epoch[cls].reserve((size_t)nstreams * pool);
+    cudaMemsetAsync(epoch[cls].p, 0, (size_t)nstreams * pool, stream);
     cursor[cls].reserve((size_t)nstreams * 2 * sizeof(unsigned int));
     dev[cls].reserve((size_t)nstreams * sizeof(MapClassDev));
     views[cls].reserve((size_t)nstreams * sizeof(GridView));
@@ -351,8 +367,12 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
       m.kdiv = cls == 0 ? c.kdiv_corner : c.kdiv_surf;
       m.cube_size = c.cube_size;
       for (int k = 0; k < 3; k++) { m.dims[k] = c.dims[k]; m.origin[k] = c.origin[k]; }
+      m.epoch = (unsigned char*)epoch[cls].p + (size_t)s * pool;
+      m.eoff = (int*)eoff.p + (size_t)s * 256 * 3;
+      m.cur_epoch = 0;
     }
     cudaMemcpyAsync(dev[cls].p, h.data(), sizeof(MapClassDev) * nstreams, cudaMemcpyHostToDevice, stream);
+    hdev[cls] = h;
   }
   windows.reserve(sizeof(CubeWindow) * nstreams);
   flags.reserve(sizeof(int) * 8);
@@ -419,6 +439,55 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
             (MapClassDev*)dev[cls].p, (int*)flags.p);
   CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
             (MapClassDev*)dev[cls].p);
+}
+
+// ---- FeatureMap::shift ----------------------------------------------------------------------------------------------------------
+// One thread per cell: keeps the points whose storage cube (coordinates under the NEW origin + displacement of the epoch) is still
+// inside the grid, in their order, and counts them into cube_count (zeroed by the caller).  m->origin / eoff already hold the
+// state after the shift.
+__global__ void map_shift_kernel(MapClassDev* mp) {
+  MapClassDev& m = *mp;
+  const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > m.mask || m.entries[e].key == CM_EMPTY_KEY) return;
+  const unsigned int start = m.entries[e].start, count = m.entries[e].count;
+  unsigned int kept = 0;
+  for (unsigned int j = 0; j < count; j++) {
+    const float4 q = m.pts[start + j];
+    const unsigned char ep = m.epoch[start + j];
+    const int* o = m.eoff + 3 * (int)ep;
+    const int ci = world_to_cube_axis(q.x, m.cube_size, m.origin[0]) + o[0], cj = world_to_cube_axis(q.y, m.cube_size, m.origin[1]) + o[1],
+              ck = world_to_cube_axis(q.z, m.cube_size, m.origin[2]) + o[2];
+    if (ci < 0 || ci >= m.dims[0] || cj < 0 || cj >= m.dims[1] || ck < 0 || ck >= m.dims[2]) continue;
+    if (kept != j) { m.pts[start + kept] = q; m.epoch[start + kept] = ep; }
+    kept++;
+    atomicAdd(&m.cube_count[ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1]], 1);
+  }
+  if (kept != count) { m.entries[e].count = kept; atomicSub(m.total, (int)(count - kept)); }
+}
+
+bool DeviceMap::shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream) {
+  // contents move by T = -sigma d (see the header); the displacement of a stored point changes by T - d
+  int sigma = 0;
+  for (int k = 0; k < 3 && !sigma; k++) sigma = d[k] > 0 ? 1 : (d[k] < 0 ? -1 : 0);
+  int* row = h_eoff.data() + (size_t)s * 256 * 3;
+  if (sigma > 0) {
+    if (cur_epoch[s] >= 255) return false;
+    for (int e = 0; e <= cur_epoch[s]; e++) for (int k = 0; k < 3; k++) row[3 * e + k] -= 2 * d[k];
+    cur_epoch[s]++;                                   // points inserted from now on are stored where their coordinates say
+    for (int k = 0; k < 3; k++) row[3 * cur_epoch[s] + k] = 0;
+    cudaMemcpyAsync((int*)eoff.p + (size_t)s * 256 * 3, row, sizeof(int) * 3 * (cur_epoch[s] + 1), cudaMemcpyHostToDevice, stream);
+  }
+  const int ncubes = cfg.dims[0] * cfg.dims[1] * cfg.dims[2];
+  for (int cls = 0; cls < 2; cls++) {
+    MapClassDev& h = hdev[cls][s];
+    for (int k = 0; k < 3; k++) h.origin[k] = new_origin[k];
+    h.cur_epoch = cur_epoch[s];
+    MapClassDev* dm = (MapClassDev*)dev[cls].p + s;
+    cudaMemcpyAsync(dm, &h, sizeof(MapClassDev), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(h.cube_count, 0, sizeof(int) * ncubes, stream);
+    CM_LAUNCH(map_shift_kernel, (table_cap[cls] + 255) / 256, 256, 0, stream, dm);
+  }
+  return true;
 }
 
 size_t DeviceMap::export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream) {

@@ -40,16 +40,17 @@ static void iso_to_twist(const HostIso& it, float pose[6]) {
 }
 static void twist_to_iso(const float pose[6], HostIso& it) { pose_to_matrix(pose, it.R); it.t[0] = pose[3]; it.t[1] = pose[4]; it.t[2] = pose[5]; }
 
-// FeatureMap::update + computeActiveAera (FeatureMap.h:232-254, 308-352).  Returns false when the reference would
-// shift() the cube grid (not implemented).
-static bool update_window(const cm_config& cfg, MappingStream& st, const float sensor[3], CubeWindow& w) {
+// FeatureMap::update + computeActiveAera (FeatureMap.h:232-254, 308-352).  shift_d returns the argument of the reference's
+// shift(newGrid - grid) (all zero: the cubes stay); the origin in `st` is already moved by it.
+static void update_window(const cm_config& cfg, MappingStream& st, const float sensor[3], CubeWindow& w, int shift_d[3]) {
   const int dims[3] = {cfg.cube_w, cfg.cube_h, cfg.cube_d};
   int g[3];
   for (int k = 0; k < 3; k++) g[k] = (int)(roundf(sensor[k] / cfg.cube_size) + (float)st.origin[k]);   // worldToCube :479-481
   const int PAD = 3;
   for (int k = 0; k < 3; k++) {
     int ng = std::min(std::max(g[k], PAD), dims[k] - PAD - 1);
-    if (ng != g[k]) return false;   // shift(newGrid - grid) would move the cubes
+    shift_d[k] = ng - g[k];         // shift(newGrid - grid), then _cubeOrigin += newGrid - grid (:243-249)
+    st.origin[k] += shift_d[k];
     st.cur[k] = ng;
   }
   memset(&w, 0, sizeof(w));
@@ -88,7 +89,6 @@ static bool update_window(const cm_config& cfg, MappingStream& st, const float s
         }
     w.interior[a] = all ? 1 : 0;
   }
-  return true;
 }
 
 __global__ void gather_counts_kernel(const int* __restrict__ n5, int* __restrict__ n2, int S) {
@@ -190,16 +190,28 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
   {
     // every stream's window is validated on a copy first: a failure leaves no stream half-updated
     std::vector<MappingStream> next(ctx->mstreams.begin(), ctx->mstreams.end());
+    std::vector<int> shifts;   // (stream, d[3]) of the streams whose cube grid is re-centred this frame
     for (int s = 0; s < S; s++) {
       MappingStream& ms = next[s];
       HostIso odomNew; memcpy(odomNew.R, h_odom[s].R, 36); memcpy(odomNew.t, h_odom[s].t, 12);
       HostIso L2W = iso_mul(ms.mappedLast, iso_inverse(ms.odomLast));   // transformAssociate, transform_utils.h:502-507
       ms.mappedNew = iso_mul(L2W, odomNew);
-      if (!update_window(cfg, ms, ms.mappedNew.t, wins[s]))
-        return fail(ctx, CM_ERR_UNSUPPORTED, "sensor left the supported part of the cube grid (FeatureMap::shift not implemented)");
+      int d[3];
+      update_window(cfg, ms, ms.mappedNew.t, wins[s], d);
+      if (d[0] || d[1] || d[2]) {
+        if (ctx->dist.on) return fail(ctx, CM_ERR_UNSUPPORTED, "FeatureMap::shift on a sharded map");
+        const bool wrong_way = d[0] > 0 || (d[0] == 0 && (d[1] > 0 || (d[1] == 0 && d[2] > 0)));
+        if (wrong_way && ctx->map.cur_epoch[s] >= 255) return fail(ctx, CM_ERR_UNSUPPORTED, "more than 255 wrong-way FeatureMap::shift calls");
+        shifts.push_back(s); shifts.push_back(d[0]); shifts.push_back(d[1]); shifts.push_back(d[2]);
+      }
       iso_to_twist(ms.mappedNew, &pose_in[6 * s]);
     }
     ctx->mstreams.swap(next);
+    for (size_t q = 0; q < shifts.size(); q += 4) {   // FeatureMap::shift: relabel / drop the stored points of that stream
+      const int s = shifts[q];
+      ctx->map.shift(s, &shifts[q + 1], ctx->mstreams[s].origin, st);
+      ctx->n_shifts++;
+    }
   }
   // prepareFeatureFrame: voxel filters
   ctx->m_corner_ds.reserve((size_t)S * cap_c * sizeof(float4));

@@ -765,6 +765,7 @@ void GridStorage::build(const float4* d_pts, int n, float cell_size, float gate,
   view.inv_leaf = inv; view.kdiv = 1; view.cell = cell_size;
   view.npts = n;
   view.window = nullptr; view.cube_count = nullptr;
+  view.epoch = nullptr; view.eoff = nullptr; view.displaced = 0;
   view.max_level = grid_max_level(cell_size, gate);
 }
 
