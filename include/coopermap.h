@@ -256,6 +256,18 @@ int cm_map_full_host(cm_ctx* ctx, int stream_index, float leaf, cm_point* out, s
 int cm_map_save_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files);
 int cm_map_load_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files, size_t* n_points, size_t* n_misplaced);
 
+/* DynamicFeatureMap paging (util/DynamicFeatureMap.h:129-161, 504-677) for a prebuilt map that does not fit (or need not sit) in
+ * memory as a whole.  cm_map_page_open_host reads <dir>/index2.txt ("count type i j k size" per <count>.pcd file, type 0 corner /
+ * 1 surf, GLOBAL cube indices i = round(x / cube_size) as the reference's indexConvert writes them) and fixes the resident window
+ * (the reference's DynamicFeatureMap(21, 11, 21); sizes are odd, the sensor's cube is the centre).  cm_map_page_update_host is
+ * DynamicFeatureMap::update: on the first call every catalogued cube of the window around the sensor is read, every file through
+ * the map voxel filter; afterwards, whenever the sensor enters another cube, the cubes that entered the window are read and the
+ * cubes that left it are dropped.  The localisation / mapping entries then work on the resident cubes.  The device lattice
+ * (cm_config cube_w x cube_h x cube_d) is re-centred on the sensor when the window would leave it, so travel is unbounded. */
+int cm_map_page_open_host(cm_ctx* ctx, int stream_index, const char* dir, int window_w, int window_h, int window_d, int* n_entries);
+int cm_map_page_update_host(cm_ctx* ctx, int stream_index, const float* sensor_xyz, int* n_files_loaded, int* n_cubes_evicted,
+                            size_t* n_points_loaded);
+
 /* ---- scan-to-scan odometry ------------------------------------------------------------------------------------------ */
 typedef struct cm_odom_stats {
   int initialising;   /* first frame: clouds stored, no motion estimated (LaserOdometry.cpp:295-303) */

@@ -104,3 +104,68 @@ def test_map_files_round_trip(cmb, oracle, synth, tmp_path):
         assert _same(ctx3.map_export_sorted(0, cls)[0], om.cloud(which))
     for c in (ctx, ctx2, ctx3):
         c.close()
+
+
+def test_dynamic_map_paging(cmb, oracle, synth, tmp_path):
+    """DynamicFeatureMap paging (DynamicFeatureMap.h:129-161, 504-677): index2.txt with GLOBAL cube indices, a window of cubes
+    around the sensor resident, cubes read when they enter the window and dropped when they leave it, the lattice re-centred when
+    the window would leave it.  The resident map must always be the union of the catalogued cubes of the current window, and the
+    localisation matcher on the paged map must give the pose it gives on the fully loaded map."""
+    cube = 20.0
+    sc = synth.make_scene(seed=91, extent=260.0, n_boxes=120, n_poles=80)
+    mc, ms = synth.sample_map(sc, 0.5, seed=92, region=(-130, 130, -25, 25))
+    # the catalogue: one filtered cloud per (cube, class), as FeatureMap::saveCloudToFiles + indexConvert leave them
+    files = {}
+    lines = []
+    count = 0
+    for cls, pts in ((0, mc), (1, ms)):
+        g = np.round(pts[:, :3] / np.float32(cube)).astype(np.int64)
+        for key in sorted(set(map(tuple, g.tolist()))):
+            sel = pts[(g == np.array(key)).all(axis=1)]
+            fl = oracle.voxel_filter(sel, 0.4)
+            oracle.write_pcd_binary(str(tmp_path / ("%d.pcd" % count)), fl)
+            files[(cls,) + key] = fl
+            lines.append("%d %d %d %d %d %d" % (count, cls, key[0], key[1], key[2], len(fl)))
+            count += 1
+    (tmp_path / "index2.txt").write_text("\n".join(lines) + "\n")
+    grid = dict(cube_w=9, cube_h=9, cube_d=7, cube_size=cube, valid_distance=60.0)
+    win = (5, 3, 3)
+    ctx = cmb.Context(**MAP_CFG, **grid)
+    ctx.mapping_create(1, 100000, 1500000)
+    assert ctx.map_page_open(0, tmp_path, win) == count
+
+    def expect(centre, cls):
+        parts = []
+        for key, fl in files.items():
+            if key[0] == cls and all(abs(key[1 + a] - centre[a]) <= win[a] // 2 for a in range(3)):
+                parts.append((key[1:], fl))
+        parts.sort(key=lambda kv: (kv[0][2], kv[0][1], kv[0][0]))        # lattice index order: k, then j, then i
+        return np.concatenate([p for _, p in parts]) if parts else np.zeros((0, 4), np.float32)
+
+    full = cmb.Context(**MAP_CFG, cube_w=21, cube_h=9, cube_d=7, cube_size=cube, valid_distance=60.0)
+    full.mapping_create(1, 100000, 1500000)
+    eye = (np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+    full.map_insert([np.concatenate([f for k, f in files.items() if k[0] == 0])], [np.concatenate([f for k, f in files.items() if k[0] == 1])], [eye])
+    total_loaded = total_evicted = 0
+    for k, x in enumerate(np.linspace(-100.0, 100.0, 21)):                 # 10 m per step: a new cube every other step
+        sensor = np.array([x, 2.0, 0.0], np.float32)
+        nf, ne, npts = ctx.map_page_update(0, sensor)
+        total_loaded += nf; total_evicted += ne
+        q = sensor / np.float32(cube)
+        centre = (np.sign(q) * np.floor(np.abs(q) + 0.5)).astype(int)      # roundf: halves away from zero (x = -90 -> cube -5)
+        for cls in (0, 1):
+            got, _ = ctx.map_export_sorted(0, cls)
+            assert _same(got, expect(centre, cls)), (k, x, cls, len(got))
+        if k % 5 == 2:
+            R, t = synth.pose_matrix(0.0, 0.0, 0.0, (float(x), 2.0, 0.0))
+            fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=500 + k, cols=900)
+            rng_ = np.linalg.norm(fr[..., :3], axis=-1)
+            fr[rng_ > 15.0] = np.nan                                         # queries stay inside the resident window (+-1 cube in y and z)
+            f = oracle.scanreg_organised(fr)
+            od = (R.astype(np.float32), (t + np.array([0.04, -0.03, 0.01])).astype(np.float32))
+            a, sa = ctx.localization_process([od], [f["lessSharp"]], [f["lessFlat"]])
+            b, sb = full.localization_process([od], [f["lessSharp"]], [f["lessFlat"]])
+            assert sa[0]["rows"] == sb[0]["rows"] > 50 and sa[0]["iterations"] == sb[0]["iterations"]
+            assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1])
+    assert total_loaded > 30 and total_evicted > 30
+    ctx.close(); full.close()

@@ -247,6 +247,20 @@ class Context:
         self._check(self.L.cm_map_load_host(self.h, C.c_int(stream), str(directory).encode(), C.byref(n), C.byref(npts), C.byref(bad)))
         return n.value, npts.value, bad.value
 
+    def map_page_open(self, stream, directory, window=(21, 11, 21)):
+        """DynamicFeatureMap::setupFilesDirectory: read <dir>/index2.txt (global cube indices) -> number of catalogue lines."""
+        n = C.c_int(0)
+        self._check(self.L.cm_map_page_open_host(self.h, C.c_int(stream), str(directory).encode(), C.c_int(window[0]), C.c_int(window[1]),
+                                                 C.c_int(window[2]), C.byref(n)))
+        return n.value
+
+    def map_page_update(self, stream, sensor):
+        """DynamicFeatureMap::update -> (files read, cubes dropped, points read)."""
+        sx = _f32(sensor)
+        nf = C.c_int(0); ne = C.c_int(0); npts = C.c_size_t(0)
+        self._check(self.L.cm_map_page_update_host(self.h, C.c_int(stream), _ptr(sx), C.byref(nf), C.byref(ne), C.byref(npts)))
+        return nf.value, ne.value, npts.value
+
     def pipeline_step(self, frames, odoms):
         """Scan registration + mapping for one organised sweep per stream: frames (S, rows, cols, 4)."""
         fr = _f32(frames)

@@ -2,7 +2,9 @@
 #pragma once
 #include "../../include/coopermap.h"
 #include "cm_host.h"
+#include <array>
 #include <deque>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -25,6 +27,15 @@ struct LocalWindow {
   double accum = 0.0; bool first = true; double prevR[9], prevT[3];   // FrameUpdater: accum_distance, is_first, prev_keypose
   HostIso mappedLast, mappedNew, odomLast;
   int n_surround[2] = {0, 0};
+};
+
+// DynamicFeatureMap paging (cm_mapio.cu): the index2.txt catalogue of one stream and the window that is resident
+struct PageState {
+  bool open = false, first = true;
+  std::string dir;
+  std::map<std::array<int, 3>, int> files[2];   // global cube index -> file number, [0] corner / [1] surf
+  int win[3] = {21, 11, 21};                    // DynamicFeatureMap(cubeWidth_, cubeHeight_, cubeDepth_)
+  int sensor[3] = {0, 0, 0};                    // _sensorGloId
 };
 
 // ---- multi-GPU state (cm_dist.cu) ------------------------------------------------------------------------------------------
@@ -91,6 +102,8 @@ struct cm_ctx {
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
   cm::LocalWindow local;               // cm_mapping_local_*
+  std::vector<cm::PageState> pages;    // cm_map_page_* (one per stream)
+  cm::DeviceBuffer d_drop;
   cm::DistState dist;                  // cm_dist_init: this context is one rank of a sharded map
   // pinned, device-accessible host staging for the per-step parameter uploads of the mapping stage (poses, cube windows): they
   // are copied by a kernel, not by the copy engine that the sweep uploads keep busy

@@ -303,7 +303,7 @@ struct DeviceMap {
   // FeatureMap::shift(d) of stream s followed by `origin += d` (FeatureMap.h:232-245, 354-376): relabels the stored points, drops
   // the cubes that leave the grid, recounts cube_count.  new_origin = the stream's origin after the shift.  False: more than 255
   // wrong-way shifts (the epoch counter is a byte)
-  bool shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream);
+  bool shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream, bool literal = true, const unsigned char* d_drop = nullptr);
 };
 
 // K1/K2: scan registration for organised sweeps (cm_scanreg.cu)

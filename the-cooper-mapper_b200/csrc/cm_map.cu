@@ -445,7 +445,8 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
 // One thread per cell: keeps the points whose storage cube (coordinates under the NEW origin + displacement of the epoch) is still
 // inside the grid, in their order, and counts them into cube_count (zeroed by the caller).  m->origin / eoff already hold the
 // state after the shift.
-__global__ void map_shift_kernel(MapClassDev* mp) {
+// drop (optional): [W*H*D] bytes, non-zero = the cube is evicted (DynamicFeatureMap paging, cm_mapio.cu)
+__global__ void map_shift_kernel(MapClassDev* mp, const unsigned char* __restrict__ drop) {
   MapClassDev& m = *mp;
   const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e > m.mask || m.entries[e].key == CM_EMPTY_KEY) return;
@@ -458,6 +459,7 @@ __global__ void map_shift_kernel(MapClassDev* mp) {
     const int ci = world_to_cube_axis(q.x, m.cube_size, m.origin[0]) + o[0], cj = world_to_cube_axis(q.y, m.cube_size, m.origin[1]) + o[1],
               ck = world_to_cube_axis(q.z, m.cube_size, m.origin[2]) + o[2];
     if (ci < 0 || ci >= m.dims[0] || cj < 0 || cj >= m.dims[1] || ck < 0 || ck >= m.dims[2]) continue;
+    if (drop && drop[ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1]]) continue;
     if (kept != j) { m.pts[start + kept] = q; m.epoch[start + kept] = ep; }
     kept++;
     atomicAdd(&m.cube_count[ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1]], 1);
@@ -465,10 +467,11 @@ __global__ void map_shift_kernel(MapClassDev* mp) {
   if (kept != count) { m.entries[e].count = kept; atomicSub(m.total, (int)(count - kept)); }
 }
 
-bool DeviceMap::shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream) {
+bool DeviceMap::shift(int s, const int d[3], const int new_origin[3], cudaStream_t stream, bool literal, const unsigned char* d_drop) {
   // contents move by T = -sigma d (see the header); the displacement of a stored point changes by T - d
+  // literal == false: a plain re-centring (every cube follows the origin), d_drop: cubes to evict on the way
   int sigma = 0;
-  for (int k = 0; k < 3 && !sigma; k++) sigma = d[k] > 0 ? 1 : (d[k] < 0 ? -1 : 0);
+  for (int k = 0; k < 3 && !sigma && literal; k++) sigma = d[k] > 0 ? 1 : (d[k] < 0 ? -1 : 0);
   int* row = h_eoff.data() + (size_t)s * 256 * 3;
   if (sigma > 0) {
     if (cur_epoch[s] >= 255) return false;
@@ -485,7 +488,7 @@ bool DeviceMap::shift(int s, const int d[3], const int new_origin[3], cudaStream
     MapClassDev* dm = (MapClassDev*)dev[cls].p + s;
     cudaMemcpyAsync(dm, &h, sizeof(MapClassDev), cudaMemcpyHostToDevice, stream);
     cudaMemsetAsync(h.cube_count, 0, sizeof(int) * ncubes, stream);
-    CM_LAUNCH(map_shift_kernel, (table_cap[cls] + 255) / 256, 256, 0, stream, dm);
+    CM_LAUNCH(map_shift_kernel, (table_cap[cls] + 255) / 256, 256, 0, stream, dm, d_drop);
   }
   return true;
 }

@@ -158,30 +158,9 @@ int cm_map_save_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_file
   return CM_OK;
 }
 
-int cm_map_load_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files, size_t* n_points, size_t* n_misplaced) {
-  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
-  if (!dir || stream_index < 0 || stream_index >= ctx->map_streams) return fail(ctx, CM_ERR_ARG, "bad argument");
+// pushes two host clouds (corner, surf; world coordinates) of ONE stream through the map's insert kernels (= the map voxel filter)
+static int insert_clouds(cm_ctx* ctx, int stream_index, const std::vector<cm_point> cloud[2]) {
   const cm_config& cfg = ctx->cfg;
-  const std::string d(dir);
-  std::ifstream fin((d + "/index.txt").c_str());
-  if (!fin) return fail(ctx, CM_ERR_ARG, "cannot open " + d + "/index.txt");
-  std::vector<cm_point> cloud[2], tmp;
-  int count, type, i, j, k, files = 0;
-  long long size;
-  size_t misplaced = 0;
-  const MappingStream& ms = ctx->mstreams[stream_index];
-  while (fin >> count >> type >> i >> j >> k >> size) {
-    if (type != 0 && type != 1) continue;
-    std::string why;
-    if (!read_pcd(file_name(d, count), tmp, why)) return fail(ctx, CM_ERR_ARG, file_name(d, count) + ": " + why);
-    for (const cm_point& p : tmp) {   // the reference puts the file into cube (i, j, k); here a point's cube follows from its coordinates
-      const int ci = (int)(roundf(p.x / cfg.cube_size) + (float)ms.origin[0]), cj = (int)(roundf(p.y / cfg.cube_size) + (float)ms.origin[1]),
-                ck = (int)(roundf(p.z / cfg.cube_size) + (float)ms.origin[2]);
-      if (ci != i || cj != j || ck != k) misplaced++;
-    }
-    cloud[type].insert(cloud[type].end(), tmp.begin(), tmp.end());
-    files++;
-  }
   try {
     cudaSetDevice(cfg.device);
     cudaStream_t st = ctx->stream;
@@ -211,9 +190,157 @@ int cm_map_load_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_file
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
+  return CM_OK;
+}
+
+int cm_map_load_host(cm_ctx* ctx, int stream_index, const char* dir, int* n_files, size_t* n_points, size_t* n_misplaced) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!dir || stream_index < 0 || stream_index >= ctx->map_streams) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const cm_config& cfg = ctx->cfg;
+  const std::string d(dir);
+  std::ifstream fin((d + "/index.txt").c_str());
+  if (!fin) return fail(ctx, CM_ERR_ARG, "cannot open " + d + "/index.txt");
+  std::vector<cm_point> cloud[2], tmp;
+  int count, type, i, j, k, files = 0;
+  long long size;
+  size_t misplaced = 0;
+  const MappingStream& ms = ctx->mstreams[stream_index];
+  while (fin >> count >> type >> i >> j >> k >> size) {
+    if (type != 0 && type != 1) continue;
+    std::string why;
+    if (!read_pcd(file_name(d, count), tmp, why)) return fail(ctx, CM_ERR_ARG, file_name(d, count) + ": " + why);
+    for (const cm_point& p : tmp) {   // the reference puts the file into cube (i, j, k); here a point's cube follows from its coordinates
+      const int ci = (int)(roundf(p.x / cfg.cube_size) + (float)ms.origin[0]), cj = (int)(roundf(p.y / cfg.cube_size) + (float)ms.origin[1]),
+                ck = (int)(roundf(p.z / cfg.cube_size) + (float)ms.origin[2]);
+      if (ci != i || cj != j || ck != k) misplaced++;
+    }
+    cloud[type].insert(cloud[type].end(), tmp.begin(), tmp.end());
+    files++;
+  }
+  { const int rc = insert_clouds(ctx, stream_index, cloud); if (rc != CM_OK) return rc; }
   if (n_files) *n_files = files;
   if (n_points) *n_points = cloud[0].size() + cloud[1].size();
   if (n_misplaced) *n_misplaced = misplaced;
+  return CM_OK;
+}
+
+// ---- DynamicFeatureMap paging ---------------------------------------------------------------------------------------------------
+// util/DynamicFeatureMap.h:129-161 (setupPCDFileName: <dir>/index2.txt, "count type i j k size" with GLOBAL cube indices
+// i = round(x / cubeSize), ...), :504-677 (update: the cubes of a window around the sensor's cube are resident; when the sensor
+// changes cube, the cubes that enter the window are read -- every file through the map voxel filter -- and the cubes that leave it
+// are dropped, their slots reused).  The resident window lives in the device map; cube (i, j, k) of the catalogue is cube
+// (i, j, k) + origin of the device lattice (FeatureMap::worldToCube uses the same round()).  When the window would leave the
+// device lattice, the lattice is re-centred on the sensor (a plain re-labelling: the map is keyed by coordinates).
+int cm_map_page_open_host(cm_ctx* ctx, int stream_index, const char* dir, int window_w, int window_h, int window_d, int* n_entries) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!dir || stream_index < 0 || stream_index >= ctx->map_streams || window_w < 1 || window_h < 1 || window_d < 1 || !(window_w & 1) ||
+      !(window_h & 1) || !(window_d & 1))
+    return fail(ctx, CM_ERR_ARG, "bad argument (window sizes are odd: the sensor's cube is the centre)");
+  if (window_w > ctx->cfg.cube_w || window_h > ctx->cfg.cube_h || window_d > ctx->cfg.cube_d)
+    return fail(ctx, CM_ERR_ARG, "paging window larger than the cube lattice of cm_config");
+  if (ctx->dist.on) return fail(ctx, CM_ERR_UNSUPPORTED, "paging on a sharded map");
+  const std::string d(dir);
+  std::ifstream fin((d + "/index2.txt").c_str());
+  if (!fin) return fail(ctx, CM_ERR_ARG, "cannot open " + d + "/index2.txt");
+  if (ctx->pages.size() != (size_t)ctx->map_streams) ctx->pages.assign(ctx->map_streams, PageState());
+  PageState& pg = ctx->pages[stream_index];
+  pg = PageState();
+  pg.dir = d; pg.win[0] = window_w; pg.win[1] = window_h; pg.win[2] = window_d;
+  int count, type, i, j, k; long long size; int n = 0;
+  while (fin >> count >> type >> i >> j >> k >> size) {   // :141-155 (a later line for the same cube replaces the earlier one)
+    if (type != 0 && type != 1) type = 1;                // `if (!type) corner else surf`
+    pg.files[type][{i, j, k}] = count;
+    n++;
+  }
+  pg.open = true;
+  if (n_entries) *n_entries = n;
+  return CM_OK;
+}
+
+int cm_map_page_update_host(cm_ctx* ctx, int stream_index, const float* sensor, int* n_files_loaded, int* n_cubes_evicted, size_t* n_points_loaded) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!sensor || stream_index < 0 || stream_index >= ctx->map_streams || ctx->pages.size() != (size_t)ctx->map_streams ||
+      !ctx->pages[stream_index].open)
+    return fail(ctx, CM_ERR_ARG, "bad argument / cm_map_page_open_host has not been called for this stream");
+  PageState& pg = ctx->pages[stream_index];
+  const cm_config& cfg = ctx->cfg;
+  MappingStream& ms = ctx->mstreams[stream_index];
+  const int dims[3] = {cfg.cube_w, cfg.cube_h, cfg.cube_d};
+  int g[3];
+  for (int a = 0; a < 3; a++) g[a] = (int)roundf(sensor[a] / cfg.cube_size);   // Glo2GloIdx, :318-323
+  int files = 0, evicted = 0; size_t points = 0;
+  if (n_files_loaded) *n_files_loaded = 0;
+  if (n_cubes_evicted) *n_cubes_evicted = 0;
+  if (n_points_loaded) *n_points_loaded = 0;
+  if (!pg.first && g[0] == pg.sensor[0] && g[1] == pg.sensor[1] && g[2] == pg.sensor[2]) return CM_OK;   // same cube: nothing moves (:556-558)
+  const int half[3] = {pg.win[0] / 2, pg.win[1] / 2, pg.win[2] / 2};
+  auto in_window = [&](const int c[3], const int centre[3]) {   // !OutRange, :265-273
+    for (int a = 0; a < 3; a++) if (c[a] < centre[a] - half[a] || c[a] > centre[a] + half[a]) return false;
+    return true;
+  };
+  try {
+    cudaSetDevice(cfg.device);
+    cudaStream_t st = ctx->stream;
+    // does the new window fit the device lattice with the current origin?  if not, re-centre the lattice on the sensor's cube
+    // (and keep the sensor inside the central cubes FeatureMap::update wants, so that the stage entries never shift a paged map)
+    bool fits = true;
+    for (int a = 0; a < 3; a++)
+      if (g[a] - half[a] + ms.origin[a] < 0 || g[a] + half[a] + ms.origin[a] >= dims[a] || g[a] + ms.origin[a] < 3 || g[a] + ms.origin[a] > dims[a] - 4)
+        fits = false;
+    int new_origin[3] = {ms.origin[0], ms.origin[1], ms.origin[2]}, d[3] = {0, 0, 0};
+    if (!fits) for (int a = 0; a < 3; a++) { new_origin[a] = dims[a] / 2 - g[a]; d[a] = new_origin[a] - ms.origin[a]; }
+    // cubes of the old window that are outside the new one are dropped (:592-611); on the first call the map keeps what it holds
+    const size_t ncubes = (size_t)dims[0] * dims[1] * dims[2];
+    std::vector<unsigned char> drop;
+    if (!pg.first) {
+      drop.assign(ncubes, 0);
+      for (int i = pg.sensor[0] - half[0]; i <= pg.sensor[0] + half[0]; i++)
+        for (int j = pg.sensor[1] - half[1]; j <= pg.sensor[1] + half[1]; j++)
+          for (int k = pg.sensor[2] - half[2]; k <= pg.sensor[2] + half[2]; k++) {
+            const int c[3] = {i, j, k};
+            if (in_window(c, g)) continue;
+            const int li = i + new_origin[0], lj = j + new_origin[1], lk = k + new_origin[2];   // lattice index AFTER the re-centring
+            if (li < 0 || li >= dims[0] || lj < 0 || lj >= dims[1] || lk < 0 || lk >= dims[2]) { evicted++; continue; }   // falls off the lattice anyway
+            drop[li + lj * dims[0] + lk * dims[0] * dims[1]] = 1;
+            evicted++;
+          }
+    }
+    if (!fits || evicted) {
+      const unsigned char* d_drop = nullptr;
+      if (!drop.empty()) {
+        ctx->d_drop.reserve(ncubes);
+        CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_drop.p, drop.data(), ncubes, cudaMemcpyHostToDevice, st));
+        d_drop = (const unsigned char*)ctx->d_drop.p;
+      }
+      ctx->map.shift(stream_index, d, new_origin, st, false, d_drop);
+      CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));   // `drop` goes out of scope
+      for (int a = 0; a < 3; a++) ms.origin[a] = new_origin[a];
+    }
+    // cubes that enter the window are read (:524-553 first call, :559-590 + 636-672 afterwards), in the reference's loop order
+    std::vector<cm_point> cloud[2], tmp;
+    for (int i = g[0] - half[0]; i <= g[0] + half[0]; i++)
+      for (int j = g[1] - half[1]; j <= g[1] + half[1]; j++)
+        for (int k = g[2] - half[2]; k <= g[2] + half[2]; k++) {
+          const int c[3] = {i, j, k};
+          if (!pg.first && in_window(c, pg.sensor)) continue;
+          for (int type = 0; type < 2; type++) {
+            auto it = pg.files[type].find({i, j, k});
+            if (it == pg.files[type].end()) continue;
+            std::string why;
+            if (!read_pcd(file_name(pg.dir, it->second), tmp, why)) continue;   // `if(!file) continue;`
+            cloud[type].insert(cloud[type].end(), tmp.begin(), tmp.end());
+            files++; points += tmp.size();
+          }
+        }
+    if (files) { const int rc = insert_clouds(ctx, stream_index, cloud); if (rc != CM_OK) return rc; }
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  pg.first = false;
+  for (int a = 0; a < 3; a++) pg.sensor[a] = g[a];
+  if (n_files_loaded) *n_files_loaded = files;
+  if (n_cubes_evicted) *n_cubes_evicted = evicted;
+  if (n_points_loaded) *n_points_loaded = points;
   return CM_OK;
 }
 
