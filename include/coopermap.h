@@ -286,6 +286,17 @@ int cm_odometry_process_host(cm_ctx* ctx, const cm_point* sharp, int n_sharp, co
                              cm_iter_trace* trace);
 int cm_odometry_reset(cm_ctx* ctx);
 
+/* The odometry stage for EVERY stream of a context in one set of launches (the batch form of cm_odometry_process_host, like
+ * cm_mapping_process_host is of the mapping stage): clouds are [nstreams][cap_*] arrays with per-stream counts, each stream keeps
+ * its own _transform / _Tsum / last clouds; streams on their first frame only store their clouds, streams whose last clouds are
+ * too small skip scanMatch (LaserOdometry.cpp:338), the others iterate together.  corner_last / surf_last (optional) return
+ * [nstreams][cap_less_sharp] / [nstreams][cap_less_flat]. */
+int cm_odometry_batch_create(cm_ctx* ctx, int nstreams, int cap_sharp, int cap_less_sharp, int cap_flat, int cap_less_flat);
+int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int* n_sharp, const cm_point* less_sharp, const int* n_less_sharp,
+                                   const cm_point* flat, const int* n_flat, const cm_point* less_flat, const int* n_less_flat, cm_iso* odom,
+                                   cm_pose* transform, cm_point* corner_last, cm_point* surf_last, cm_odom_stats* stats);
+
+
 /* ---- sharded-map matching (BASELINE config 4: one map split over ranks) ---------------------------------------------------
  * ScanMatch::scanMatchScan with the reference clouds partitioned in space: rank r holds the map points of its region plus a
  * sqrt(5) m halo (cm_shard_set_map_host), evaluates per iteration only the queries whose map-frame position lies in its

@@ -49,3 +49,40 @@ def test_odometry_degenerate_inputs(cmb, oracle):
     g = ctx.odometry_process(e, e, e, e)
     assert g["iterations"] == 0
     ctx.close()
+
+
+def test_odometry_batch_equals_per_stream_oracle(cmb, oracle, synth):
+    """cm_odometry_batch_process_host: every stream of the batch follows its own LaserOdometry chain bit for bit -- different
+    LiDAR motion per stream, a stream whose clouds are too small for scanMatch (LaserOdometry.cpp:338) in the middle of the
+    sequence, ragged cloud sizes."""
+    sc = synth.make_scene(seed=43, extent=40.0, n_boxes=12, n_poles=10)
+    S, NF = 4, 5
+    ctx = cmb.Context()
+    ctx.odometry_batch_create(S, 4000, 30000, 8000, 30000)
+    oos = [oracle.Odometry() for _ in range(S)]
+    trajs = [synth.trajectory(NF, seed=s, speed=0.2 + 0.15 * s) for s in range(S)]
+    moved = 0.0
+    for k in range(NF):
+        feats = []
+        for s in range(S):
+            R, t = trajs[s][k]
+            f = oracle.scanreg_organised(synth.simulate_scan(sc, R, t, "VLP-16", seed=200 + 10 * s + k, cols=900 if s % 2 else 1200))
+            if s == 2 and k == 2:          # a sweep with almost no features: the NEXT frame of this stream skips scanMatch
+                f = {n: f[n][:6] for n in ("sharp", "lessSharp", "flat", "lessFlat")}
+            feats.append(f)
+        got = ctx.odometry_batch_process([f["sharp"] for f in feats], [f["lessSharp"] for f in feats], [f["flat"] for f in feats],
+                                         [f["lessFlat"] for f in feats])
+        for s in range(S):
+            f = feats[s]
+            o = oos[s].process(f["sharp"], f["lessSharp"], f["flat"], f["lessFlat"])
+            g = got[s]
+            assert g["initialising"] == (k == 0)
+            assert g["iterations"] == o["iterations"], (k, s)
+            assert np.array_equal(g["transform"], o["transform"]), (k, s)
+            assert np.array_equal(g["R"], o["R"]) and np.array_equal(g["t"], o["t"]), (k, s)
+            assert _same(g["corner_last"], o["corner_last"]) and _same(g["surf_last"], o["surf_last"]), (k, s)
+            if s == 2 and k == 3:
+                assert not g["matched"]
+            moved = max(moved, float(np.linalg.norm(g["t"])))
+    assert moved > 0.5
+    ctx.close()

@@ -369,6 +369,33 @@ class Context:
                     surf_last=sl[:len(a[3])].copy(), iterations=st.iterations, rows=st.rows, matched=bool(st.matched),
                     initialising=bool(st.initialising), converged=bool(st.converged), log=log)
 
+    def odometry_batch_create(self, nstreams, cap_sharp, cap_less_sharp, cap_flat, cap_less_flat):
+        self._ob = (nstreams, cap_sharp, cap_less_sharp, cap_flat, cap_less_flat)
+        self._check(self.L.cm_odometry_batch_create(self.h, *[C.c_int(v) for v in self._ob]))
+
+    def odometry_batch_process(self, sharps, less_sharps, flats, less_flats, want_clouds=True):
+        """LaserOdometry::process for one frame of EVERY stream (lists of (n, 4) clouds) -> list of dicts like odometry_process."""
+        S, caps = self._ob[0], self._ob[1:]
+        bufs, cnts = [], []
+        for clouds, cap in zip((sharps, less_sharps, flats, less_flats), caps):
+            b = np.zeros((S, cap, 4), np.float32); n = np.zeros(S, np.int32)
+            for s, c in enumerate(clouds):
+                c = _f32(c, 4); n[s] = len(c); b[s, :len(c)] = c
+            bufs.append(b); cnts.append(n)
+        iso = np.empty((S, 12), np.float32); tf = np.empty((S, 6), np.float32); st = (OdomStats * S)()
+        cl = np.empty((S, caps[1], 4), np.float32) if want_clouds else None
+        sl = np.empty((S, caps[3], 4), np.float32) if want_clouds else None
+        self._check(self.L.cm_odometry_batch_process_host(self.h, _ptr(bufs[0]), _ptr(cnts[0]), _ptr(bufs[1]), _ptr(cnts[1]), _ptr(bufs[2]),
+                                                          _ptr(cnts[2]), _ptr(bufs[3]), _ptr(cnts[3]), _ptr(iso), _ptr(tf),
+                                                          _ptr(cl) if want_clouds else None, _ptr(sl) if want_clouds else None, st))
+        out = []
+        for s in range(S):
+            out.append(dict(R=iso[s, :9].reshape(3, 3).copy(), t=iso[s, 9:].copy(), transform=tf[s].copy(),
+                            corner_last=cl[s, :cnts[1][s]].copy() if want_clouds else None,
+                            surf_last=sl[s, :cnts[3][s]].copy() if want_clouds else None, iterations=st[s].iterations, rows=st[s].rows,
+                            matched=bool(st[s].matched), initialising=bool(st[s].initialising), converged=bool(st[s].converged)))
+        return out
+
     # ---- measurement helpers -------------------------------------------------------------------------------------
     def timer_record(self, which):
         self._check(self.L.cm_timer_record(self.h, C.c_int(which)))

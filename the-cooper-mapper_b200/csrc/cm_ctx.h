@@ -29,6 +29,16 @@ struct LocalWindow {
   int n_surround[2] = {0, 0};
 };
 
+// batched scan-to-scan odometry (cm_odometry.cu): LaserOdometry's members for every stream of the context
+struct OdomBatch {
+  int S = 0, cap_sharp = 0, cap_less_sharp = 0, cap_flat = 0, cap_less_flat = 0;
+  std::vector<int> inited, n_last_c, n_last_s;
+  std::vector<float> tf;            // [S][6] _transform
+  std::vector<HostIso> Tsum;        // _Tsum
+  DeviceBuffer sharp, flat, last_c, last_s, ints, ind, rows, state, sums, pose, tfinv;
+  GridBatch grid_c, grid_s;
+};
+
 // DynamicFeatureMap paging (cm_mapio.cu): the index2.txt catalogue of one stream and the window that is resident
 struct PageState {
   bool open = false, first = true;
@@ -101,6 +111,7 @@ struct cm_ctx {
   // sharded-map matching (cm_shard_*): persistent grids in grid_a / grid_b
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
+  cm::OdomBatch obatch;                // cm_odometry_batch_*
   cm::LocalWindow local;               // cm_mapping_local_*
   std::vector<cm::PageState> pages;    // cm_map_page_* (one per stream)
   cm::DeviceBuffer d_drop;

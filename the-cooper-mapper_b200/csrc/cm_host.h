@@ -229,6 +229,24 @@ struct OdomLaunch {
   const MatchState* state; int* ind; RowOut* rows;
 };
 void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream);
+// batched odometry (one launch set for all streams of a context)
+struct GridBatch {            // nstreams voxel-cell grids of equal capacity, rebuilt together (streams with on[s] == 0 keep theirs)
+  DeviceBuffer entries, pts, cell_of, cursor, views;
+  int nstreams = 0, cap = 0; unsigned int tcap = 0;
+  void create(int nstreams, int cap, cudaStream_t stream);
+  void build(const float4* d_pts, const int* d_n, int max_n, const int* d_on, float cell_size, float gate, cudaStream_t stream);
+};
+struct OdomBatchLaunch {
+  int nstreams;
+  const float4* sharp; const float4* flat; int cap_sharp, cap_flat; const int* n_sharp; const int* n_flat; int max_sharp, max_flat;
+  const float4* last_corner; const float4* last_surf; int cap_last_corner, cap_last_surf; const int* bound_corner; const int* bound_surf;
+  const GridView* grid_corner; const GridView* grid_surf;
+  const MatchState* state; int* ind; RowOut* rows;
+};
+void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream);
+void launch_odom_gate(MatchState* d_state, const int* d_active, int nstreams, cudaStream_t stream);
+void launch_odom_to_end_batch(float4* d_cloud, int cap, const int* d_n, int max_n, int nstreams, const float* d_tf6, const float* d_inv12,
+                              const int* d_on, cudaStream_t stream);
 void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float* d_inv12, cudaStream_t stream);
 
 // K3: batched pcl::VoxelGrid-equivalent filter (cm_voxel.cu).  Segment s reads in[s*cap_in .. +n_in[s]) and writes

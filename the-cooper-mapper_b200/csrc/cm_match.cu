@@ -61,6 +61,70 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ pts, int n, CellE
   out[entries[h].start + j] = p;
 }
 
+// ---- the same for a batch of independent clouds (blockIdx.y = stream; on[s] == 0: that stream keeps its old grid) -----------------
+__global__ void gridb_clear_kernel(CellEntry* e, unsigned int tcap, unsigned int* cursor, const int* __restrict__ on) {
+  const int s = blockIdx.y;
+  if (!on[s]) return;
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tcap) { CellEntry& c = e[(size_t)s * tcap + i]; c.key = CM_EMPTY_KEY; c.start = 0; c.count = 0; }
+  if (i == 0) cursor[s] = 0u;
+}
+__global__ void gridb_count_kernel(const float4* __restrict__ pts, const int* __restrict__ n, int cap, CellEntry* entries, unsigned int tcap,
+                                   float inv, int* __restrict__ cell_of, const int* __restrict__ on) {
+  const int s = blockIdx.y;
+  if (!on[s]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[s]) return;
+  CellEntry* ent = entries + (size_t)s * tcap;
+  const unsigned int mask = tcap - 1;
+  int* co = cell_of + (size_t)s * cap;
+  float4 p = pts[(size_t)s * cap + i];
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { co[i] = -1; return; }
+  float fx = floorf(p.x * inv), fy = floorf(p.y * inv), fz = floorf(p.z * inv);
+  if (!(fabsf(fx) < 1.0e6f && fabsf(fy) < 1.0e6f && fabsf(fz) < 1.0e6f)) { co[i] = -1; return; }
+  unsigned long long key = pack_cell((int)fx, (int)fy, (int)fz);
+  unsigned int h = hash_cell(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&ent[h].key, CM_EMPTY_KEY, key);
+    if (prev == CM_EMPTY_KEY || prev == key) break;
+    h = (h + 1) & mask;
+  }
+  atomicAdd(&ent[h].count, 1u);
+  co[i] = (int)h;
+}
+__global__ void gridb_offsets_kernel(CellEntry* entries, unsigned int tcap, unsigned int* cursor, const int* __restrict__ on) {
+  const int s = blockIdx.y;
+  if (!on[s]) return;
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tcap) return;
+  CellEntry& c = entries[(size_t)s * tcap + i];
+  const unsigned int cnt = c.count;
+  if (cnt) { c.start = atomicAdd(&cursor[s], cnt); c.count = 0; }
+}
+__global__ void gridb_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n, int cap, CellEntry* entries, unsigned int tcap,
+                                     const int* __restrict__ cell_of, float4* __restrict__ out, const int* __restrict__ on) {
+  const int s = blockIdx.y;
+  if (!on[s]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[s]) return;
+  const int h = cell_of[(size_t)s * cap + i];
+  if (h < 0) return;
+  CellEntry& c = entries[(size_t)s * tcap + h];
+  float4 p = pts[(size_t)s * cap + i];
+  const unsigned int j = atomicAdd(&c.count, 1u);
+  p.w = __int_as_float(i);           // original index: tie-break + reported neighbour
+  out[(size_t)s * cap + c.start + j] = p;
+}
+__global__ void gridb_view_kernel(GridView* views, const CellEntry* entries, unsigned int tcap, const float4* pts, int cap, const int* __restrict__ n,
+                                  float inv, float cell, int max_level, const int* __restrict__ on, int nstreams) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams || !on[s]) return;
+  GridView v;
+  v.entries = entries + (size_t)s * tcap; v.pts = pts + (size_t)s * cap; v.mask = tcap - 1; v.inv_leaf = inv; v.kdiv = 1; v.cell = cell;
+  v.npts = n[s]; v.max_level = max_level; v.window = nullptr; v.cube_count = nullptr; v.epoch = nullptr; v.eoff = nullptr; v.displaced = 0;
+  views[s] = v;
+}
+
 // ============================================================================================================
 // Pose bookkeeping (Twist + Angle caches + Isometry3f rotation)
 // ============================================================================================================
@@ -862,6 +926,42 @@ void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
   a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter;
   const int nT = ((o.n_sharp + 31) & ~31) + o.n_flat;
   CM_LAUNCH(odom_corr_kernel, (nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, 128, 0, stream, a);
+}
+void GridBatch::create(int nstreams_, int cap_, cudaStream_t stream) {
+  nstreams = nstreams_; cap = cap_ > 0 ? cap_ : 1;
+  tcap = next_pow2((unsigned int)(2 * cap));
+  entries.reserve((size_t)nstreams * tcap * sizeof(CellEntry)); pts.reserve((size_t)nstreams * cap * sizeof(float4));
+  cell_of.reserve((size_t)nstreams * cap * sizeof(int)); cursor.reserve((size_t)nstreams * sizeof(unsigned int));
+  views.reserve((size_t)nstreams * sizeof(GridView));
+  cudaMemsetAsync(views.p, 0, (size_t)nstreams * sizeof(GridView), stream);   // npts = 0 until a stream's first build
+}
+void GridBatch::build(const float4* d_pts, const int* d_n, int max_n, const int* d_on, float cell_size, float gate, cudaStream_t stream) {
+  const float inv = 1.0f / cell_size;
+  if (max_n > cap) max_n = cap;
+  const dim3 gt((tcap + 255) / 256, nstreams), gp((max_n + 255) / 256 > 0 ? (max_n + 255) / 256 : 1, nstreams);
+  CM_LAUNCH(gridb_clear_kernel, gt, 256, 0, stream, (CellEntry*)entries.p, tcap, (unsigned int*)cursor.p, d_on);
+  CM_LAUNCH(gridb_count_kernel, gp, 256, 0, stream, d_pts, d_n, cap, (CellEntry*)entries.p, tcap, inv, (int*)cell_of.p, d_on);
+  CM_LAUNCH(gridb_offsets_kernel, gt, 256, 0, stream, (CellEntry*)entries.p, tcap, (unsigned int*)cursor.p, d_on);
+  CM_LAUNCH(gridb_scatter_kernel, gp, 256, 0, stream, d_pts, d_n, cap, (CellEntry*)entries.p, tcap, (const int*)cell_of.p, (float4*)pts.p, d_on);
+  CM_LAUNCH(gridb_view_kernel, (nstreams + 63) / 64, 64, 0, stream, (GridView*)views.p, (const CellEntry*)entries.p, tcap, (const float4*)pts.p, cap,
+            d_n, inv, cell_size, grid_max_level(cell_size, gate), d_on, nstreams);
+}
+
+void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream) {
+  OdomBatchArgs b;
+  b.sharp = o.sharp; b.flat = o.flat; b.cap_sharp = o.cap_sharp; b.cap_flat = o.cap_flat; b.n_sharp = o.n_sharp; b.n_flat = o.n_flat;
+  b.last_corner = o.last_corner; b.last_surf = o.last_surf; b.cap_last_corner = o.cap_last_corner; b.cap_last_surf = o.cap_last_surf;
+  b.bound_corner = o.bound_corner; b.bound_surf = o.bound_surf; b.grid_corner = o.grid_corner; b.grid_surf = o.grid_surf;
+  b.state = o.state; b.ind = o.ind; b.rows = o.rows; b.iter = iter;
+  const int nT = ((o.max_sharp + 31) & ~31) + o.max_flat;
+  CM_LAUNCH(odom_corr_batch_kernel, dim3((nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, o.nstreams), 128, 0, stream, b);
+}
+void launch_odom_gate(MatchState* d_state, const int* d_active, int nstreams, cudaStream_t stream) {
+  CM_LAUNCH(odom_gate_kernel, (nstreams + 63) / 64, 64, 0, stream, d_state, d_active, nstreams);
+}
+void launch_odom_to_end_batch(float4* d_cloud, int cap, const int* d_n, int max_n, int nstreams, const float* d_tf6, const float* d_inv12,
+                              const int* d_on, cudaStream_t stream) {
+  if (max_n > 0) CM_LAUNCH(odom_to_end_batch_kernel, dim3((max_n + 255) / 256, nstreams), 256, 0, stream, d_cloud, cap, d_n, d_tf6, d_inv12, d_on);
 }
 void launch_odom_to_end(float4* d_cloud, int n, const float* d_tf6, const float* d_inv12, cudaStream_t stream) {
   if (n > 0) CM_LAUNCH(odom_to_end_kernel, (n + 255) / 256, 256, 0, stream, d_cloud, n, d_tf6, d_inv12);

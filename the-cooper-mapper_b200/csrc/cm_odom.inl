@@ -31,10 +31,8 @@ __device__ __forceinline__ float odom_sqdiff(const float4& a, float bx, float by
   return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
-  __shared__ uint4 rng[8 * 128];
-  __shared__ PoseCoef kc;
-  __shared__ float tf[6];
+// one stream's correspondences and rows for one Gauss-Newton iteration (every thread of the CTA calls; uniform early exits only)
+__device__ __forceinline__ void odom_corr_body(const OdomArgs& a, uint4* rng, PoseCoef& kc, float* tf) {
   const MatchState& st = *a.state;
   if (st.done) return;
   if (threadIdx.x == 0) make_pose_coef(st, kc);
@@ -151,6 +149,62 @@ __global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
   float4* dst = reinterpret_cast<float4*>(a.rows + row);
   dst[0] = make_float4(rowv.a[0], rowv.a[1], rowv.a[2], rowv.a[3]);
   dst[1] = make_float4(rowv.a[4], rowv.a[5], rowv.b, __int_as_float(rowv.flag));
+}
+
+__global__ void __launch_bounds__(128) odom_corr_kernel(OdomArgs a) {
+  __shared__ uint4 rng[8 * 128];
+  __shared__ PoseCoef kc;
+  __shared__ float tf[6];
+  odom_corr_body(a, rng, kc, tf);
+}
+
+// the same for a batch of independent streams (blockIdx.y): clouds [S][cap], per-stream counts, grids and states
+struct OdomBatchArgs {
+  const float4* sharp; const float4* flat; int cap_sharp, cap_flat; const int* n_sharp; const int* n_flat;
+  const float4* last_corner; const float4* last_surf; int cap_last_corner, cap_last_surf; const int* bound_corner; const int* bound_surf;
+  const GridView* grid_corner; const GridView* grid_surf;
+  const MatchState* state; int* ind; RowOut* rows; int iter;
+};
+__global__ void __launch_bounds__(128) odom_corr_batch_kernel(OdomBatchArgs b) {
+  __shared__ uint4 rng[8 * 128];
+  __shared__ PoseCoef kc;
+  __shared__ float tf[6];
+  const int s = blockIdx.y;
+  OdomArgs a;
+  a.sharp = b.sharp + (size_t)s * b.cap_sharp; a.flat = b.flat + (size_t)s * b.cap_flat;
+  a.n_sharp = b.n_sharp[s]; a.n_flat = b.n_flat[s];
+  a.last_corner = b.last_corner + (size_t)s * b.cap_last_corner; a.last_surf = b.last_surf + (size_t)s * b.cap_last_surf;
+  a.bound_corner = b.bound_corner[s]; a.bound_surf = b.bound_surf[s];
+  a.grid_corner = b.grid_corner[s]; a.grid_surf = b.grid_surf[s];
+  a.state = b.state + s;
+  a.ind = b.ind + (size_t)s * (2 * b.cap_sharp + 3 * b.cap_flat);
+  a.rows = b.rows + (size_t)s * (b.cap_sharp + b.cap_flat);
+  a.iter = b.iter;
+  odom_corr_body(a, rng, kc, tf);
+}
+
+// transformToEnd for a batch: cloud [S][cap], tf6 [S][6], inv12 [S][12]; streams with on[s] == 0 keep their cloud as it is
+__global__ void odom_to_end_batch_kernel(float4* __restrict__ cloud, int cap, const int* __restrict__ n, const float* __restrict__ tf6,
+                                         const float* __restrict__ inv12, const int* __restrict__ on) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!on[s] || i >= n[s]) return;
+  float tf[6], R[9], t[3];
+#pragma unroll
+  for (int k = 0; k < 6; k++) tf[k] = tf6[6 * s + k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = inv12[12 * s + k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) t[k] = inv12[12 * s + 9 + k];
+  float4 p = cloud[(size_t)s * cap + i];
+  float sx, sy, sz, x, y, z;
+  odom_to_start(tf, p, &sx, &sy, &sz);
+  transform_point(R, t, sx, sy, sz, &x, &y, &z);
+  cloud[(size_t)s * cap + i] = make_float4(x, y, z, p.w);
+}
+// streams that do not run scanMatch this frame (first frame, or too few points in the last clouds, LaserOdometry.cpp:338)
+__global__ void odom_gate_kernel(MatchState* state, const int* __restrict__ active, int nstreams) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nstreams && !active[s]) state[s].done = 1;
 }
 
 // transformToEnd (LaserOdometry.cpp:156-168): every point to the sweep start, then through the inverse of the full transform
