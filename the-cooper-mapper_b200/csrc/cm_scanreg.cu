@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(SR_THREADS) sr_ring_kernel(ScanRegArgs a) {
           if (c <= ep) { const float cv = curv[c]; if (state[c] != P_SURF_PICKED_NEAR && cv < prm.curv_thr) kv = __float_as_uint(cv); }
           kreg[r] = kv;
         }
+        __syncwarp();   // every lane has read state[] before any lane marks a pick (the reductions order execution, this orders memory)
         for (int k = 0; k < prm.max_flat; k++) {
           unsigned int m = kreg[0]; int mr = 0;
 #pragma unroll
