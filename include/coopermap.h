@@ -144,6 +144,19 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
  * optional full-resolution outputs of `out` come back in the concatenated _laserCloud order (size them for n entries). */
 int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out);
 
+/* The IMU branch of scan registration (`hasIMUData()`, ScanRegistration.cpp:89-188).  cm_imu_push_host is handleIMUMessage: one
+ * call per sensor_msgs/Imu with the stamp in seconds, roll / pitch / yaw as tf's getRPY gives them and the raw linear acceleration;
+ * the context keeps the last 200 states (imuHistorySize) with gravity removed and position / velocity integrated.
+ * cm_scanreg_sweep_imu_host is cm_scanreg_sweep_host for a sweep stamped scan_time: every accepted point is projected to the sweep
+ * start with the IMU state interpolated at its relTime (setIMUTransformFor + transformToStartIMU, :145-166) on the device -- the
+ * forward-only `_imuIdx` of the reference is a prefix maximum over relTime -- and imu_trans (12 floats, optional) returns the four
+ * /imu_trans points of publishResult (:681-708).  With an empty history it equals cm_scanreg_sweep_host. */
+typedef struct cm_imu_sample { double stamp, roll, pitch, yaw, ax, ay, az; } cm_imu_sample;
+int cm_imu_push_host(cm_ctx* ctx, const cm_imu_sample* m);
+int cm_imu_clear(cm_ctx* ctx);
+int cm_scanreg_sweep_imu_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, double scan_time, cm_scanreg_out* out, int* rows_out,
+                              int* cols_out, float* imu_trans);
+
 /* pcl::VoxelGrid<pcl::PointXYZI>::filter with a cubic leaf, batched over nseg independent clouds: cloud s is
  * in[s*cap_in .. s*cap_in + n_in[s]) and its result out[s*cap_out .. s*cap_out + n_out[s]), ordered by voxel index,
  * every field (x, y, z, intensity) averaged.  Replaces the filter calls at ScanRegistration.cpp:390-399,

@@ -59,6 +59,23 @@ void extract_features(const ScanRegParams& prm, ScanRegResult& r);   // ScanRegi
 void scanreg_organised(const ScanRegParams& prm, const float* xyzi, int rows, int cols, ScanRegResult& r);
 // lidar: 0 VLP-16, 1 HDL-32, 2 HDL-64E  (MultiScanRegistration.h:85-102)
 void scanreg_sweep(const ScanRegParams& prm, const float* xyzi, int n, int lidar, ScanRegResult& r);
+
+// IMUState (ScanRegistration.h:122-170) and the IMU history of ScanRegistration (a CircularBuffer of imuHistorySize = 200 states)
+struct ImuState {
+  double stamp = 0.0;                       // seconds
+  float roll = 0.f, pitch = 0.f, yaw = 0.f;   // Angle::rad()
+  float pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
+};
+struct ImuHistory {
+  std::vector<ImuState> h;                  // oldest first
+  size_t capacity = 200;
+  // ScanRegistration::handleIMUMessage (ScanRegistration.cpp:89-121): roll / pitch / yaw as tf's getRPY gives them, raw acceleration
+  void push(double stamp, double roll, double pitch, double yaw, double ax, double ay, double az);
+};
+// MultiScanRegistration::process with hasIMUData() (MultiScanRegistration.cpp:95-200 + ScanRegistration.cpp:123-188): every point is
+// projected to the sweep start with the interpolated IMU state.  imuTrans: the four /imu_trans points (ScanRegistration.cpp:681-708)
+void scanreg_sweep_imu(const ScanRegParams& prm, const float* xyzi, int n, int lidar, double scanTime, const ImuHistory& imu,
+                       ScanRegResult& r, float imuTrans[12]);
 int point_classify(const std::vector<PointIN>& cloud, size_t idx, int curvatureRegion);
 
 // pcl::VoxelGrid<PointXYZI>::filter (leaf = cubic)

@@ -92,6 +92,15 @@ void* cmo_scanreg_sweep(const float* fparams, const int* iparams, const float* x
   scanreg_sweep(make_prm(fparams, iparams), xyzi, n, lidar, h->r);
   return h;
 }
+// imu: [nimu][7] doubles (stamp, roll, pitch, yaw, ax, ay, az) pushed in order through ImuHistory::push; imuTrans: 12 floats out
+void* cmo_scanreg_sweep_imu(const float* fparams, const int* iparams, const float* xyzi, int n, int lidar, double scanTime, const double* imu,
+                            int nimu, float* imuTrans) {
+  ScanRegHandle* h = new ScanRegHandle();
+  ImuHistory hist;
+  for (int k = 0; k < nimu; k++) hist.push(imu[7 * k], imu[7 * k + 1], imu[7 * k + 2], imu[7 * k + 3], imu[7 * k + 4], imu[7 * k + 5], imu[7 * k + 6]);
+  scanreg_sweep_imu(make_prm(fparams, iparams), xyzi, n, lidar, scanTime, hist, h->r, imuTrans);
+  return h;
+}
 void cmo_scanreg_free(void* h) { delete (ScanRegHandle*)h; }
 // field ids: 0 cloud(5f) 1 scanStart 2 scanEnd 3 sharp(4f) 4 lessSharp 5 flat 6 lessFlat 7 sharpIdx 8 lessSharpIdx
 // 9 flatIdx 10 lessFlatRawIdx 11 lessFlatRawRing 12 picked 13 curvature 14 classLabel 15..18 dbg blind/block/slop/curv

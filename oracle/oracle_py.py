@@ -170,6 +170,20 @@ def scanreg_sweep(xyzi, lidar, params=None, fast=False):
     return _sr_collect(L, h)
 
 
+def scanreg_sweep_imu(xyzi, lidar, scan_time, imu, params=None):
+    """MultiScanRegistration::process with IMU data: imu = (k, 7) float64 rows (stamp, roll, pitch, yaw, ax, ay, az) in arrival order.
+    Returns (outputs, imu_trans (4, 3))."""
+    L = lib()
+    L.cmo_scanreg_sweep_imu.restype = C.c_void_p
+    xyzi = _f32(xyzi)
+    imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+    f, i = _sr_params(params)
+    tr = np.zeros(12, np.float32)
+    h = L.cmo_scanreg_sweep_imu(_p(f), _p(i), _p(xyzi), C.c_int(xyzi.shape[0]), C.c_int(lidar), C.c_double(scan_time), _p(imu),
+                                C.c_int(len(imu)), _p(tr))
+    return _sr_collect(L, h), tr.reshape(4, 3)
+
+
 # ---- voxel filter -----------------------------------------------------------------------------------------
 def voxel_filter(xyzi, leaf, fast=False):
     L = lib(fast)

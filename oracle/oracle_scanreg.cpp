@@ -360,4 +360,126 @@ void scanreg_sweep(const ScanRegParams& prm, const float* xyzi, int n, int lidar
   extract_features(prm, r);
 }
 
+// ---- IMU de-skew ------------------------------------------------------------------------------------------------------------
+namespace {
+struct Ang { float rad, c, s; };                                  // Angle.h: radian + buffered cos / sin (cm_sincosf, see cm_math.h)
+inline Ang ang(float r) { Ang a; a.rad = r; cm::cm_sincosf(r, &a.s, &a.c); return a; }
+inline Ang neg(const Ang& a) { Ang o; o.rad = -a.rad; o.c = a.c; o.s = -a.s; return o; }   // Angle::operator-()
+inline void rotX(float v[3], const Ang& a) { float y = v[1]; v[1] = a.c * y - a.s * v[2]; v[2] = a.s * y + a.c * v[2]; }   // math_utils.h:115-145
+inline void rotY(float v[3], const Ang& a) { float x = v[0]; v[0] = a.c * x + a.s * v[2]; v[2] = a.c * v[2] - a.s * x; }
+inline void rotZ(float v[3], const Ang& a) { float x = v[0]; v[0] = a.c * x - a.s * v[1]; v[1] = a.s * x + a.c * v[1]; }
+inline void rotateZXY(float v[3], const Ang& z, const Ang& x, const Ang& y) { rotZ(v, z); rotX(v, x); rotY(v, y); }   // :184-205
+inline void rotateYXZ(float v[3], const Ang& y, const Ang& x, const Ang& z) { rotY(v, y); rotX(v, x); rotZ(v, z); }   // :215-236
+// IMUState::interpolate(start, end, ratio, result), ScanRegistration.h:151-169
+ImuState imu_interpolate(const ImuState& start, const ImuState& end, float ratio) {
+  ImuState r;
+  float invRatio = 1 - ratio;
+  r.roll = start.roll * invRatio + end.roll * ratio;
+  r.pitch = start.pitch * invRatio + end.pitch * ratio;
+  if (start.yaw - end.yaw > M_PI) r.yaw = (float)(start.yaw * invRatio + (end.yaw + 2 * M_PI) * ratio);
+  else if (start.yaw - end.yaw < -M_PI) r.yaw = (float)(start.yaw * invRatio + (end.yaw - 2 * M_PI) * ratio);
+  else r.yaw = start.yaw * invRatio + end.yaw * ratio;
+  for (int k = 0; k < 3; k++) { r.vel[k] = start.vel[k] * invRatio + end.vel[k] * ratio; r.pos[k] = start.pos[k] * invRatio + end.pos[k] * ratio; }
+  return r;
+}
+// ScanRegistration::interpolateIMUStateFor (ScanRegistration.cpp:168-186); imuIdx is the member that only moves forward
+ImuState imu_state_for(const ImuHistory& imu, double scanTime, float relTime, size_t& imuIdx) {
+  double timeDiff = (scanTime - imu.h[imuIdx].stamp) + relTime;
+  while (imuIdx < imu.h.size() - 1 && timeDiff > 0) { imuIdx++; timeDiff = (scanTime - imu.h[imuIdx].stamp) + relTime; }
+  if (imuIdx == 0 || timeDiff > 0) return imu.h[imuIdx];
+  float ratio = (float)(-timeDiff / (imu.h[imuIdx].stamp - imu.h[imuIdx - 1].stamp));
+  return imu_interpolate(imu.h[imuIdx], imu.h[imuIdx - 1], ratio);
+}
+}  // namespace
+
+void ImuHistory::push(double stamp, double roll, double pitch, double yaw, double ax, double ay, double az) {
+  ImuState n;
+  n.acc[0] = float(ay - std::sin(roll) * std::cos(pitch) * 9.81);     // ScanRegistration.cpp:96-99
+  n.acc[1] = float(az - std::cos(roll) * std::cos(pitch) * 9.81);
+  n.acc[2] = float(ax + std::sin(pitch) * 9.81);
+  n.stamp = stamp; n.roll = (float)roll; n.pitch = (float)pitch; n.yaw = (float)yaw;
+  if (!h.empty()) {                                                   // :108-118
+    float acc[3] = {n.acc[0], n.acc[1], n.acc[2]};
+    rotateZXY(acc, ang(n.roll), ang(n.pitch), ang(n.yaw));
+    const ImuState& prev = h.back();
+    float timeDiff = float(n.stamp - prev.stamp);
+    for (int k = 0; k < 3; k++) {
+      n.pos[k] = (prev.pos[k] + (prev.vel[k] * timeDiff)) + (((0.5f * acc[k]) * timeDiff) * timeDiff);
+      n.vel[k] = prev.vel[k] + acc[k] * timeDiff;
+    }
+  }
+  if (h.size() < capacity) h.push_back(n);
+  else { h.erase(h.begin()); h.push_back(n); }                        // CircularBuffer::push: the oldest state goes
+}
+
+void scanreg_sweep_imu(const ScanRegParams& prm, const float* xyzi, int n, int lidar, double scanTime, const ImuHistory& imu,
+                       ScanRegResult& r, float imuTrans[12]) {
+  r = ScanRegResult();
+  for (int k = 0; k < 12; k++) imuTrans[k] = 0.f;
+  float lower, upper; int nRings;
+  if (lidar == 0) { lower = -15; upper = 15; nRings = 16; }
+  else if (lidar == 1) { lower = -30.67f; upper = 10.67f; nRings = 32; }
+  else if (lidar == 3) { lower = -15.444f; upper = 6.96f; nRings = 40; }
+  else { lower = -24.9f; upper = 2; nRings = 64; }
+  float factor = (nRings - 1) / (upper - lower);
+  std::vector<std::vector<PointIN>> rings(nRings);
+  const bool hasImu = !imu.h.empty();
+  size_t imuIdx = 0;                                                  // reset(scanTime): _imuIdx = 0, _imuStart = state at relTime 0
+  ImuState imuStart, imuCur;
+  float shift[3] = {0, 0, 0};
+  if (hasImu) imuStart = imu_state_for(imu, scanTime, 0.f, imuIdx);
+  if (n > 0) {
+    const float* in = xyzi;
+    float startOri = -cm::cm_atan2f(in[1], in[0]);
+    float endOri = -cm::cm_atan2f(in[4 * (n - 1) + 1], in[4 * (n - 1) + 0]) + 2 * float(M_PI);
+    if (endOri - startOri > 3 * M_PI) endOri -= 2 * M_PI;
+    else if (endOri - startOri < M_PI) endOri += 2 * M_PI;
+    bool halfPassed = false;
+    for (int i = 0; i < n; i++) {
+      PointIN point;
+      point.x = in[4 * i + 1]; point.y = in[4 * i + 2]; point.z = in[4 * i + 0]; point.intensity = in[4 * i + 3];
+      if (!std::isfinite(point.x) || !std::isfinite(point.y) || !std::isfinite(point.z)) continue;
+      if (point.x * point.x + point.y * point.y + point.z * point.z < 0.0001) continue;
+      float angle = cm::cm_atanf(point.y / std::sqrt(point.x * point.x + point.z * point.z));
+      int scanID = lidar == 3 ? scan_id_pandar((float)(angle * 180.0 / M_PI)) : int(((angle * 180 / M_PI) - lower) * factor + 0.5);
+      if (scanID >= nRings || scanID < 0) continue;
+      float ori = -cm::cm_atan2f(point.x, point.z);
+      if (!halfPassed) {
+        if (ori < startOri - M_PI / 2) ori += 2 * M_PI;
+        else if (ori > startOri + M_PI * 3 / 2) ori -= 2 * M_PI;
+        if (ori - startOri > M_PI) halfPassed = true;
+      } else {
+        ori += 2 * M_PI;
+        if (ori < endOri - M_PI * 3 / 2) ori += 2 * M_PI;
+        else if (ori > endOri + M_PI / 2) ori -= 2 * M_PI;
+      }
+      float relTime = prm.scanPeriod * (ori - startOri) / (endOri - startOri);
+      point.curvature = scanID + relTime;
+      if (hasImu) {                                                   // setIMUTransformFor + transformToStartIMU, :145-166
+        imuCur = imu_state_for(imu, scanTime, relTime, imuIdx);
+        float relSweepTime = (float)(0.0 + relTime);                  // (_scanTime - _sweepStart).toSec() + relTime, a new sweep
+        for (int k = 0; k < 3; k++) shift[k] = (imuCur.pos[k] - imuStart.pos[k]) - imuStart.vel[k] * relSweepTime;
+        float v[3] = {point.x, point.y, point.z};
+        rotateZXY(v, ang(imuCur.roll), ang(imuCur.pitch), ang(imuCur.yaw));
+        v[0] += shift[0]; v[1] += shift[1]; v[2] += shift[2];
+        rotateYXZ(v, neg(ang(imuStart.yaw)), neg(ang(imuStart.pitch)), neg(ang(imuStart.roll)));
+        point.x = v[0]; point.y = v[1]; point.z = v[2];
+      }
+      rings[scanID].push_back(point);
+    }
+  }
+  if (hasImu) {                                                       // publishResult, :681-708
+    imuTrans[0] = imuStart.pitch; imuTrans[1] = imuStart.yaw; imuTrans[2] = imuStart.roll;
+    imuTrans[3] = imuCur.pitch; imuTrans[4] = imuCur.yaw; imuTrans[5] = imuCur.roll;
+    float s3[3] = {shift[0], shift[1], shift[2]};
+    rotateYXZ(s3, neg(ang(imuStart.yaw)), neg(ang(imuStart.pitch)), neg(ang(imuStart.roll)));
+    imuTrans[6] = s3[0]; imuTrans[7] = s3[1]; imuTrans[8] = s3[2];
+    float v3[3] = {imuCur.vel[0] - imuStart.vel[0], imuCur.vel[1] - imuStart.vel[1], imuCur.vel[2] - imuStart.vel[2]};
+    rotateYXZ(v3, neg(ang(imuStart.yaw)), neg(ang(imuStart.pitch)), neg(ang(imuStart.roll)));
+    imuTrans[9] = v3[0]; imuTrans[10] = v3[1]; imuTrans[11] = v3[2];
+  }
+  finish_rings(rings, r);
+  extract_features(prm, r);
+}
+
 }  // namespace cmo

@@ -77,3 +77,37 @@ def test_scanreg_raw_sweep_entry(ctx, oracle, synth, scene_small, model, lidar):
     ok = np.where(np.isfinite(sweep[:, 0]))[0]
     sweep = sweep[ok[0]:ok[-1] + 1]      # a driver never starts / ends a sweep on a missing return (startOri / endOri would be NaN)
     _check(ctx.scanreg_sweep(sweep, lidar, debug=True), oracle.scanreg_sweep(sweep, lidar))
+
+
+def test_scanreg_raw_sweep_with_imu_deskew(cmb, oracle, synth, scene_small):
+    """The hasIMUData() branch (ScanRegistration.cpp:89-188): IMU messages integrated by cm_imu_push_host, every point of the sweep
+    projected to the sweep start with the state interpolated at its relTime -- on the device, where the reference's forward-only
+    _imuIdx becomes a prefix maximum -- and the /imu_trans points; all bit-identical to the oracle."""
+    sc, _, _ = scene_small
+    R, t = synth.pose_matrix(0.2, 0.0, 0.0, (0.5, 0.3, 0.0))
+    fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=33, cols=1200)
+    sweep = synth.organised_to_sweep(fr)
+    ok = np.where(np.isfinite(sweep[:, 0]))[0]
+    sweep = sweep[ok[0]:ok[-1] + 1]
+    rng = np.random.default_rng(9)
+    scan_time = 100.05
+    # 100 Hz IMU from before the sweep to after its end (0.1 s): a gentle turn with accelerations; two messages share a gap of 30 ms
+    stamps = np.concatenate([np.arange(99.90, 100.04, 0.01), np.arange(100.07, 100.22, 0.01)])
+    imu = np.zeros((len(stamps), 7))
+    imu[:, 0] = stamps
+    imu[:, 1] = 0.01 * np.sin(3 * stamps); imu[:, 2] = 0.02 * np.cos(2 * stamps); imu[:, 3] = 3.1 + 0.4 * (stamps - 100.0)   # yaw crosses pi
+    imu[imu[:, 3] > np.pi, 3] -= 2 * np.pi
+    imu[:, 4:] = rng.normal(0, 0.5, (len(stamps), 3)) + np.array([0.0, 0.0, 9.81])
+    ctx = cmb.Context()
+    for m in imu:
+        ctx.imu_push(*m)
+    g = ctx.scanreg_sweep(sweep, 0, debug=True, imu_scan_time=scan_time)
+    o, tr = oracle.scanreg_sweep_imu(sweep, 0, scan_time, imu)
+    _check(g, o)
+    assert np.array_equal(g["imu_trans"].view(np.uint32), tr.view(np.uint32))
+    plain = oracle.scanreg_sweep(sweep, 0)
+    assert np.abs(o["cloud"][:, :3] - plain["cloud"][:, :3]).max() > 1e-3         # the de-skew did move the points
+    # an empty history is the plain entry
+    ctx.imu_clear()
+    _check(ctx.scanreg_sweep(sweep, 0, debug=True, imu_scan_time=scan_time), plain)
+    ctx.close()

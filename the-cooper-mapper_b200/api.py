@@ -493,7 +493,15 @@ class Context:
             res.append(d)
         return res[0] if single else res
 
-    def scanreg_sweep(self, sweep, lidar, debug=False):
+    def imu_push(self, stamp, roll, pitch, yaw, ax, ay, az):
+        """ScanRegistration::handleIMUMessage."""
+        m = (C.c_double * 7)(stamp, roll, pitch, yaw, ax, ay, az)
+        self._check(self.L.cm_imu_push_host(self.h, m))
+
+    def imu_clear(self):
+        self._check(self.L.cm_imu_clear(self.h))
+
+    def scanreg_sweep(self, sweep, lidar, debug=False, imu_scan_time=None):
         """MultiScanRegistration::process for one raw azimuth-major sweep (n, 4); lidar 0 VLP-16, 1 HDL-32, 2 HDL-64E, 3 Pandar40."""
         sw = _f32(sweep, 4)
         n = max(len(sw), 1)
@@ -515,7 +523,12 @@ class Context:
                 out.idx[k] = dbg["idx"][k].ctypes.data
             out.picked = dbg["picked"].ctypes.data; out.curvature = dbg["curvature"].ctypes.data; out.label = dbg["label"].ctypes.data
         rows = C.c_int(0); cols = C.c_int(0)
-        self._check(self.L.cm_scanreg_sweep_host(self.h, _ptr(sw), C.c_size_t(len(sw)), C.c_int(lidar), C.byref(out), C.byref(rows), C.byref(cols)))
+        imu_trans = np.zeros(12, np.float32)
+        if imu_scan_time is None:
+            self._check(self.L.cm_scanreg_sweep_host(self.h, _ptr(sw), C.c_size_t(len(sw)), C.c_int(lidar), C.byref(out), C.byref(rows), C.byref(cols)))
+        else:   # de-skew with the IMU states pushed so far (cm_imu_push_host)
+            self._check(self.L.cm_scanreg_sweep_imu_host(self.h, _ptr(sw), C.c_size_t(len(sw)), C.c_int(lidar), C.c_double(imu_scan_time),
+                                                         C.byref(out), C.byref(rows), C.byref(cols), _ptr(imu_trans)))
         names = ["sharp", "lessSharp", "flat", "lessFlat"]
         d = {names[k]: bufs[k][:cnt[k]].copy() for k in range(4)}
         if debug:
@@ -525,6 +538,8 @@ class Context:
             d["flatIdx"] = dbg["idx"][2][:cnt[2]].copy(); d["lessFlatRawIdx"] = dbg["idx"][3][:cnt[4]].copy()
             d["picked"] = dbg["picked"].astype(np.int32); d["curvature"] = dbg["curvature"].copy()
             d["classLabel"] = dbg["label"].astype(np.int32)
+        if imu_scan_time is not None:
+            d["imu_trans"] = imu_trans.reshape(4, 3).copy()
         return d
 
     # ---- voxel filter --------------------------------------------------------------------------------------------

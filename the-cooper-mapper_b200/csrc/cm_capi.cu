@@ -403,7 +403,27 @@ int cm_scanreg_organised_host(cm_ctx* ctx, const cm_point* frames, int nstreams,
 // the elevation angle, azimuth unwrap with the half-sweep flag, relTime, stable per-ring append -- on the device (cm_frontend.cu);
 // the rings go to the same extraction kernels as ring-major rows with their precomputed curvature field.  The sweep crosses PCIe
 // once, unsorted; the only host work is two atan2 for the sweep's start / end orientation.
+int cm_imu_push_host(cm_ctx* ctx, const cm_imu_sample* m) {
+  if (!ctx || !m) return fail(ctx, CM_ERR_ARG, "bad argument");
+  ctx->imu.push(m->stamp, m->roll, m->pitch, m->yaw, m->ax, m->ay, m->az);
+  return CM_OK;
+}
+int cm_imu_clear(cm_ctx* ctx) {
+  if (!ctx) return CM_ERR_ARG;
+  ctx->imu.clear();
+  return CM_OK;
+}
+static int scanreg_sweep_common(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out,
+                                bool use_imu, double scan_time, float* imu_trans);
 int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out) {
+  return scanreg_sweep_common(ctx, sweep, n, lidar, out, rows_out, cols_out, false, 0.0, nullptr);
+}
+int cm_scanreg_sweep_imu_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, double scan_time, cm_scanreg_out* out, int* rows_out,
+                              int* cols_out, float* imu_trans) {
+  return scanreg_sweep_common(ctx, sweep, n, lidar, out, rows_out, cols_out, true, scan_time, imu_trans);
+}
+static int scanreg_sweep_common(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, cm_scanreg_out* out, int* rows_out, int* cols_out,
+                                bool use_imu, double scan_time, float* imu_trans) {
   float lo, up; int nr;
   if (!ctx || (!sweep && n) || !out || !out->n || !frontend_mapper(lidar, &lo, &up, &nr) || n > 0x7fffffffu) return fail(ctx, CM_ERR_ARG, "bad argument");
   for (int k = 0; k < 4; k++) if (!out->pts[k] || out->cap[k] <= 0) return fail(ctx, CM_ERR_ARG, "bad output buffers");
@@ -416,7 +436,8 @@ int cm_scanreg_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lida
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 first = n ? make_float4(sweep[0].x, sweep[0].y, sweep[0].z, 0.f) : zero;
     const float4 last = n ? make_float4(sweep[n - 1].x, sweep[n - 1].y, sweep[n - 1].z, 0.f) : zero;
-    ctx->frontend.run((const float4*)ctx->d_sweep.p, (int)n, first, last, lidar, ctx->cfg.scan_period, st, &rows, &cols);
+    ctx->frontend.run((const float4*)ctx->d_sweep.p, (int)n, first, last, lidar, ctx->cfg.scan_period, st, &rows, &cols,
+                      (use_imu && !ctx->imu.stamp.empty()) ? &ctx->imu : nullptr, scan_time, imu_trans);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }

@@ -86,6 +86,7 @@ struct cm_ctx {
   cm::ScanRegistrationGpu scanreg;
   cm::DeviceBuffer d_tags, d_l_ds[4], d_sweep;
   cm::SweepFrontEnd frontend;          // raw-sweep front end (cm_scanreg_sweep_host)
+  cm::ImuHistoryHost imu;              // cm_imu_push_host
   cm::DeviceBuffer d_frames, d_sr_pts[4], d_sr_idx[4], d_sr_n, d_sr_cloud, d_sr_ccurv, d_sr_picked, d_sr_curv, d_sr_label, d_sr_range;
   cm::DeviceBuffer d_vin, d_vout, d_vn_in, d_vn_out, d_flag;
   // mapping stage (cm_mapping.cu)

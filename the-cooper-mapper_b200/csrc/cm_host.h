@@ -352,10 +352,19 @@ int debug_math_dims(int op, int* nin, int* nout);
 void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream);
 
 // Raw-sweep front end on the device (cm_frontend.cu): MultiScanRegistration::process up to the per-ring clouds.
+// ScanRegistration's IMU history (a CircularBuffer of imuHistorySize states, ScanRegistration.cpp:53,89-121), oldest first
+struct ImuHistoryHost {
+  std::vector<double> stamp;      // seconds
+  std::vector<float> state;       // [n][9]: roll, pitch, yaw, position, velocity
+  size_t capacity = 200;
+  void push(double stamp, double roll, double pitch, double yaw, double ax, double ay, double az);   // handleIMUMessage
+  void clear() { stamp.clear(); state.clear(); }
+};
 struct SweepFrontEnd {
-  DeviceBuffer ring_of, hist, frame, tags;
+  DeviceBuffer ring_of, hist, frame, tags, rel, imu_buf;
+  // imu (optional, non-empty): de-skew every point to the sweep start (hasIMUData() branch); imu_trans12: the /imu_trans points
   void run(const float4* d_sweep, int n, const float4& first, const float4& last, int lidar, float scan_period, cudaStream_t st,
-           int* rows_out, int* cols_out);
+           int* rows_out, int* cols_out, const ImuHistoryHost* imu = nullptr, double scan_time = 0.0, float* imu_trans12 = nullptr);
 };
 bool frontend_mapper(int lidar, float* lower, float* upper, int* nrings);
 
