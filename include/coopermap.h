@@ -240,8 +240,15 @@ int cm_pipeline_prefetch_strided_host(cm_ctx* ctx, const void* const* clouds, si
 int cm_pipeline_step_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols, const cm_iso* odom,
                                   cm_iso* mapped, cm_match_stats* stats);
 
-/* FeatureMap::addFeatureCloud(cornerCloud, surfCloud, tf) (FeatureMap.h:219-230): transform by tf[s], push into the
- * 50 m cubes, merge per voxel (= downsizeValidCloud, :289-306, restricted to the voxels that received points). */
+/* FeatureMap::update(sensorPose) (FeatureMap.h:232-254) of one stream outside a stage step (the stage entries do it themselves):
+ * shift() if the sensor nears the border of the cube grid, then the valid-cube window of computeActiveAera around `sensor_xyz`. */
+int cm_map_update_host(cm_ctx* ctx, int stream_index, const float* sensor_xyz);
+
+/* FeatureMap::addFeatureCloud(cornerCloud, surfCloud, tf) (FeatureMap.h:219-230): transform by tf[s], push into the 50 m cubes,
+ * downsizeValidCloud (:289-306): the VALID cubes (the window of the last update: cm_map_update_host or a stage step) are voxel-
+ * filtered -- incrementally: only the voxels that received points change --, points pushed into other cubes stay unfiltered until
+ * their cube is valid during a later insert, exactly like the reference's cube clouds.  Before any update every cube counts as
+ * valid (a map that is only being built, like FeatureMap::loadCloudFromFiles filtering every file). */
 int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner, int cap_corner, const cm_point* surf,
                        const int* n_surf, int cap_surf, const cm_iso* tf);
 

@@ -96,6 +96,46 @@ def test_lasermapping_mirror(cmb, oracle, synth):
     lm.process(R.astype(np.float32), np.array([0, 0, 200], np.float32), f["lessSharp"], f["lessFlat"])
 
 
+@pytest.mark.parametrize("step", [4.0, 11.0])
+def test_far_cubes_stay_unfiltered_until_valid(cmb, oracle, synth, step):
+    """FeatureMap::downsizeValidCloud (FeatureMap.h:289-306) only filters VALID cubes: returns that land in a cube outside the window
+    stay raw (several points per voxel, all of them searchable once the cube is valid) until an insert finds the cube valid and
+    filters its whole cloud at once.  20 m cubes with a 60 m validity radius and 100 m LiDAR range put a third of every sweep into
+    invalid cubes; the sensor then walks into them.  Poses, surround clouds and every stored cube equal the oracle's, frame by frame
+    (the larger step also re-centres the grid: FeatureMap::shift on cubes that hold raw points)."""
+    sc = synth.make_scene(seed=79, extent=150.0, n_boxes=70, n_poles=40)
+    grid = dict(cube_w=13, cube_h=13, cube_d=7, cube_size=20.0, valid_distance=60.0)
+    ctx = cmb.Context(**MAP_CFG, **grid)
+    ctx.mapping_create(1, 200000, 1200000)
+    om = oracle.Mapping(map_params=dict(ORACLE_MAP, cubeW=13, cubeH=13, cubeD=7, cubeSize=20.0, validDistance=60.0))
+    raw_seen = 0
+    for k in range(9):
+        pos = np.array([step * k, 0.6 * step * k, 0.0])
+        R, t = synth.pose_matrix(0.04 * np.sin(0.9 * k), 0.0, 0.0, pos)
+        fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=700 + k, cols=900)
+        f = oracle.scanreg_organised(fr)
+        od = (R.astype(np.float32), (t + np.array([0.02, -0.03, 0.01])).astype(np.float32))
+        isos, stats = ctx.mapping_process([od], [f["lessSharp"]], [f["lessFlat"]])
+        oR, ot, ost = om.process(od[0], od[1], f["lessSharp"], f["lessFlat"])
+        assert stats[0]["iterations"] == ost["iterations"] and stats[0]["rows"] == ost["rows"], (k, stats[0], ost)
+        assert np.array_equal(isos[0][0], oR) and np.array_equal(isos[0][1], ot), (k, isos[0], oR, ot)
+        gc, gs = ctx.map_surround(0)
+        assert _same(gs, om.map_surround(1)) and _same(gc, om.map_surround(0)), k
+        # every stored cube, raw ones included: same points (the order inside an unfiltered cube is the push order in the reference
+        # and the cell order here, so compare as sorted multisets per cube)
+        for cls, which in ((0, 4), (1, 5)):
+            g, cubes = ctx.map_export_sorted(0, cls)
+            o = om.cloud(which)
+            assert len(g) == len(o), (k, cls, len(g), len(o))
+            key = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+            assert _same(key(g), key(o)), (k, cls)
+            v = np.floor(g[:, :3] * np.float32(1.0 / 0.4)).astype(np.int64)
+            cb = np.round(g[:, :3] / np.float32(20.0)).astype(np.int64)
+            raw_seen += len(g) - len(np.unique(np.concatenate([v, cb], 1), axis=0))
+    assert raw_seen > 100           # there were unfiltered cubes (several points per voxel) along the way
+    ctx.close()
+
+
 @pytest.mark.parametrize("heading", [(1.0, 0.0), (-1.0, 0.0), (-0.8, 0.6), (0.7, -0.7)])
 def test_feature_map_shift_matches_literal_reference(cmb, oracle, synth, heading):
     """FeatureMap::shift (FeatureMap.h:354-376) when the sensor walks out of the central cubes of a small grid: towards +x the

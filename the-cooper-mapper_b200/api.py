@@ -308,6 +308,11 @@ class Context:
         return self._check(self.L.cm_pipeline_step_strided_host(self.h, arr, C.c_size_t(stride), C.c_int(rows), C.c_int(cols),
                                                                 _ptr(odoms_packed), _ptr(mapped_out), stats_out))
 
+    def map_update(self, stream, sensor):
+        """FeatureMap::update(sensorPose) for one stream: shift if needed + the valid-cube window."""
+        sx = _f32(sensor)
+        self._check(self.L.cm_map_update_host(self.h, C.c_int(stream), _ptr(sx)))
+
     def map_insert(self, corners, surfs, tfs):
         """FeatureMap::addFeatureCloud per stream."""
         cb, cn, ccap = self._pack_clouds(corners); sb, sn, scap = self._pack_clouds(surfs)

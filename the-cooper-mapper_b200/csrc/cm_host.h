@@ -285,6 +285,9 @@ struct MapClassDev {            // one class (corner / surf) of one stream, live
   float cube_size; int dims[3]; int origin[3];
   // FeatureMap::shift bookkeeping (cm_map.cu): epoch per pool slot, displacement of every epoch [256][3], the epoch new points get
   unsigned char* epoch; int* eoff; int cur_epoch;
+  // cubes that received points while they were outside the valid window: their clouds are unfiltered until they become valid again
+  // (FeatureMap::downsizeValidCloud only visits valid cubes, FeatureMap.h:289-306)
+  unsigned char* dirty;         // [W*H*D]
 };
 struct MapConfig {
   size_t max_corner, max_surf;  // capacity in points per stream
@@ -298,6 +301,8 @@ struct DeviceMap {
   DeviceBuffer entries[2], cellcap[2], pending_cnt[2], pts[2], cube_count[2], cursor[2], dev[2], views[2];
   DeviceBuffer windows, flags;
   DeviceBuffer epoch[2], eoff;                    // see MapClassDev
+  DeviceBuffer cube_dirty[2], need[2];            // unfiltered cubes per stream; per-stream "a dirty cube is valid now" flags of an insert
+  bool windows_valid = false;                     // set_windows has run at least once (before that every cube counts as valid)
   std::vector<MapClassDev> hdev[2];               // host mirror of dev[] (pointers and constants; origin / cur_epoch as of the last shift)
   std::vector<int> h_eoff;                        // [nstreams][256][3]
   std::vector<int> cur_epoch;                     // per stream
@@ -315,8 +320,10 @@ struct DeviceMap {
   // transform by the per-stream pose in d_state (or by d_tf: [S][12] = R row-major + t) and merge into the map
   // max_n: what the launches are sized for (an estimate is fine: if a stream has more, the insert does nothing and sets flags[4 + cls]);
   // step_skip: optional device flag, non-zero = insert nothing (the caller is about to repeat the step)
+  // filter_all: every cube is filtered (FeatureMap::loadCloudFromFiles filters each file, :428-456); otherwise the reference's
+  // addFeatureCloud: points pushed into a cube outside the valid window stay unfiltered until the cube is valid during an insert
   void insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf, cudaStream_t stream,
-              const int* step_skip = nullptr);
+              const int* step_skip = nullptr, bool filter_all = false);
   size_t export_points(int cls, int s, float4* d_out, int* d_cube, unsigned int* d_n, unsigned int cap, cudaStream_t stream);
   // FeatureMap::shift(d) of stream s followed by `origin += d` (FeatureMap.h:232-245, 354-376): relabels the stored points, drops
   // the cubes that leave the grid, recounts cube_count.  new_origin = the stream's origin after the shift.  False: more than 255

@@ -13,8 +13,14 @@
 // overflows (the old block is abandoned; compaction is left to a rebuild).  The same table is what the matcher's
 // 5-NN search reads (cm_device.cuh), so an insert is immediately searchable.
 //
-// Known deviations (documented in DESIGN.md): (1) points landing in a cube that is outside the valid window are
-// merged immediately, the reference leaves them unmerged until the cube becomes valid (needs ranges > ~106 m);
+// Cubes outside the valid window (needs returns beyond ~106 m: range + half a cube diagonal > 150 m): the reference pushes points
+// into them but downsizeValidCloud (:289-306) only filters VALID cubes, so such a cube holds raw points -- several per voxel --
+// until it is valid during a later insert, when its whole cloud is filtered at once: per voxel the centroid of [the point left by
+// the last filter, then the raw points in push order].  Here: a group that lands in a cube that is invalid (or still holds raw
+// points) is appended RAW, members in push order in consecutive slots, and the cube is marked dirty; a cell block keeps its
+// append order, so at the end of an insert the dirty cubes that are valid now are re-filtered cell by cell IN BLOCK ORDER, which
+// is the reference's summation order.  Raw points are ordinary pool points: the search sees them like the reference's surround
+// cloud does.
 // FeatureMap::shift (the grid re-centring when the sensor comes within 3 cubes of the grid border, :232-245, 354-376) swaps cube
 // POINTERS in place while it iterates upwards.  Worked out (and checked against the literal loop for every |d| <= 2): the contents
 // move by T = -sigma * d, sigma = sign of the first non-zero component of d in (i, j, k) order, contents that leave the grid are
@@ -148,7 +154,7 @@ __global__ void map_key_kernel(const float4* __restrict__ pts, const int* __rest
 }
 
 // ---- 2. one thread per (stream, cube, voxel) group: merge with the resident point or queue an append ---------------
-struct PendingAdd { float4 p; unsigned int entry; int stream; int cube; };
+struct PendingAdd { float4 p; unsigned int entry; int stream; int cube; int raw_tail; int raw_n; int pad[3]; };   // raw_n > 0: append the group's members unmerged
 
 __device__ __forceinline__ unsigned int map_find_or_create_cell(MapClassDev& m, int cx, int cy, int cz) {
   unsigned long long key = pack_cell(cx, cy, cz);
@@ -165,7 +171,7 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
                                  const int* __restrict__ next, const GroupEntry* __restrict__ gtab, size_t n,
                                  const float4* __restrict__ world, MapClassDev* maps, PendingAdd* __restrict__ pending,
                                  unsigned int* __restrict__ n_pending, unsigned int pending_cap, int* __restrict__ flags,
-                                 const int* __restrict__ skip) {
+                                 const int* __restrict__ skip, const CubeWindow* __restrict__ windows) {
   if (*skip) return;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
@@ -181,6 +187,24 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
             ck = world_to_cube_axis(first.z, m.cube_size, m.origin[2]);
   const unsigned int e = map_find_or_create_cell(m, floor_div(vx, m.kdiv), floor_div(vy, m.kdiv), floor_div(vz, m.kdiv));
   if (e == 0xFFFFFFFFu) { atomicExch(flags + 2, 1); return; }   // cell table full: reported as CM_ERR_CAPACITY
+  const int cube_lin = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
+  if (windows) {   // is the cube in _cubeValidInd, and free of raw points?  (windows == NULL: filter everywhere)
+    const CubeWindow& w = windows[s];
+    const int wi = ci - w.w0[0], wj = cj - w.w0[1], wk = ck - w.w0[2];
+    const bool valid = wi >= 0 && wi < 7 && wj >= 0 && wj < 7 && wk >= 0 && wk < 7 && w.active[(wi * 7 + wj) * 7 + wk];
+    if (!valid || m.dirty[cube_lin]) {
+      int nmem = 0;
+      for (int j = ge.tail; j >= 0; j = next[j]) nmem++;
+      m.dirty[cube_lin] = 1;
+      unsigned int slot = atomicAdd(n_pending, 1u);
+      if (slot < pending_cap) {
+        PendingAdd pa; pa.p = first; pa.entry = e; pa.stream = s; pa.cube = cube_lin; pa.raw_tail = ge.tail; pa.raw_n = nmem;
+        pending[slot] = pa;
+        atomicAdd(&m.pending[e], (unsigned int)nmem);
+      } else atomicExch(flags + 2, 1);
+      return;
+    }
+  }
   // resident point(s) of this voxel in this cube come first in the sum (they precede the pushed points in the cube cloud)
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
   int cnt = 0, keep = -1;
@@ -213,7 +237,7 @@ __global__ void map_merge_kernel(const unsigned long long* __restrict__ keys, co
   } else {
     unsigned int slot = atomicAdd(n_pending, 1u);
     if (slot < pending_cap) {
-      PendingAdd pa; pa.p = cen; pa.entry = e; pa.stream = s; pa.cube = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
+      PendingAdd pa; pa.p = cen; pa.entry = e; pa.stream = s; pa.cube = cube_lin; pa.raw_tail = -1; pa.raw_n = 0;
       pending[slot] = pa;
       atomicAdd(&m.pending[e], 1u);
     } else atomicExch(flags + 2, 1);
@@ -245,13 +269,28 @@ __global__ void map_grow_kernel(const PendingAdd* __restrict__ pending, const un
 
 // ---- 4. append ---------------------------------------------------------------------------------------------------------
 __global__ void map_append_kernel(const PendingAdd* __restrict__ pending, const unsigned int* __restrict__ n_pending,
-                                  unsigned int pending_cap, MapClassDev* maps) {
+                                  unsigned int pending_cap, MapClassDev* maps, const int* __restrict__ next, const float4* __restrict__ world) {
   unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int np = *n_pending; if (np > pending_cap) np = pending_cap;
   if (i >= np) return;
   const PendingAdd pa = pending[i];
   MapClassDev& m = maps[pa.stream];
   const unsigned int e = pa.entry;
+  if (pa.raw_n > 0) {   // a group for an invalid / unfiltered cube: its members, unmerged, in push order, in consecutive slots
+    const unsigned int j0 = atomicAdd(&m.entries[e].count, (unsigned int)pa.raw_n);
+    if (j0 + (unsigned int)pa.raw_n > m.cellcap[e]) { atomicSub(&m.entries[e].count, (unsigned int)pa.raw_n); return; }   // growth failed (flagged)
+    unsigned int w = m.entries[e].start + j0;
+    for (int last = -1;;) {
+      int best = 0x7fffffff;
+      for (int j = pa.raw_tail; j >= 0; j = next[j]) if (j > last && j < best) best = j;
+      if (best == 0x7fffffff) break;
+      m.pts[w] = world[best]; m.epoch[w] = (unsigned char)m.cur_epoch; w++;
+      last = best;
+    }
+    atomicAdd(&m.cube_count[pa.cube], pa.raw_n);
+    atomicAdd(m.total, pa.raw_n);
+    return;
+  }
   if (m.entries[e].count >= m.cellcap[e]) return;   // growth failed (pool exhausted, already flagged)
   const unsigned int j = atomicAdd(&m.entries[e].count, 1u);
   if (j < m.cellcap[e]) {
@@ -261,6 +300,94 @@ __global__ void map_append_kernel(const PendingAdd* __restrict__ pending, const 
     atomicAdd(m.total, 1);
   } else {
     atomicSub(&m.entries[e].count, 1u);
+  }
+}
+
+// ---- 5. downsizeValidCloud for the cubes that hold raw points and are valid now --------------------------------------------------
+__device__ __forceinline__ bool cube_valid_now(const CubeWindow& w, int ci, int cj, int ck) {
+  const int wi = ci - w.w0[0], wj = cj - w.w0[1], wk = ck - w.w0[2];
+  return wi >= 0 && wi < 7 && wj >= 0 && wj < 7 && wk >= 0 && wk < 7 && w.active[(wi * 7 + wj) * 7 + wk];
+}
+// need[s] = some cube of stream s is dirty and valid (one warp per stream)
+__global__ void map_need_kernel(const MapClassDev* maps, const CubeWindow* __restrict__ windows, int nstreams, int* __restrict__ need,
+                                const int* __restrict__ skip) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nstreams) return;
+  int any = 0;
+  if (!*skip) {
+    const MapClassDev& m = maps[s];
+    const CubeWindow& w = windows[s];
+    for (int a = lane; a < 343; a += 32) {
+      if (!w.active[a]) continue;
+      const int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
+      if (i < 0 || i >= m.dims[0] || j < 0 || j >= m.dims[1] || k < 0 || k >= m.dims[2]) continue;
+      any |= m.dirty[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
+    }
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) need[s] = any ? 1 : 0;
+}
+// one thread per cell of a stream that needs it: the points of dirty valid cubes, voxel by voxel in block order (= push order),
+// become one centroid at the voxel's first slot; the block is compacted in place
+__global__ void map_refilter_kernel(MapClassDev* maps, const CubeWindow* __restrict__ windows, int nstreams, const int* __restrict__ need) {
+  for (int s = 0; s < nstreams; s++) {
+    if (!need[s]) continue;
+    MapClassDev& m = maps[s];
+    const CubeWindow& w = windows[s];
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e <= m.mask; e += gridDim.x * blockDim.x) {
+      if (m.entries[e].key == CM_EMPTY_KEY) continue;
+      const unsigned int start = m.entries[e].start, count = m.entries[e].count;
+      unsigned int kept = 0;
+      for (unsigned int j = 0; j < count; j++) {
+        float4 q = m.pts[start + j];
+        if (isnan(q.x)) continue;   // consumed by an earlier voxel of this pass (a stored point is never NaN: the insert drops those)
+        const unsigned char ep = m.epoch[start + j];
+        const int* o = m.eoff + 3 * (int)ep;
+        const int ci = world_to_cube_axis(q.x, m.cube_size, m.origin[0]) + o[0], cj = world_to_cube_axis(q.y, m.cube_size, m.origin[1]) + o[1],
+                  ck = world_to_cube_axis(q.z, m.cube_size, m.origin[2]) + o[2];
+        const int lin = ci + cj * m.dims[0] + ck * m.dims[0] * m.dims[1];
+        const bool inside = ci >= 0 && ci < m.dims[0] && cj >= 0 && cj < m.dims[1] && ck >= 0 && ck < m.dims[2];
+        if (inside && m.dirty[lin] && cube_valid_now(w, ci, cj, ck)) {
+          const int vx = (int)floorf(q.x * m.inv_leaf), vy = (int)floorf(q.y * m.inv_leaf), vz = (int)floorf(q.z * m.inv_leaf);
+          float sx = q.x, sy = q.y, sz = q.z, si = q.w;
+          int cnt = 1;
+          for (unsigned int t = j + 1; t < count; t++) {
+            const float4 r = m.pts[start + t];
+            if (isnan(r.x)) continue;
+            if ((int)floorf(r.x * m.inv_leaf) != vx || (int)floorf(r.y * m.inv_leaf) != vy || (int)floorf(r.z * m.inv_leaf) != vz) continue;
+            const int* o2 = m.eoff + 3 * (int)m.epoch[start + t];
+            if (world_to_cube_axis(r.x, m.cube_size, m.origin[0]) + o2[0] != ci || world_to_cube_axis(r.y, m.cube_size, m.origin[1]) + o2[1] != cj ||
+                world_to_cube_axis(r.z, m.cube_size, m.origin[2]) + o2[2] != ck)
+              continue;
+            sx += r.x; sy += r.y; sz += r.z; si += r.w; cnt++;
+            const float qn = __int_as_float(0x7fc00000);
+            m.pts[start + t] = make_float4(qn, qn, qn, qn);   // consumed
+          }
+          if (cnt > 1) {
+            const float c = (float)cnt;
+            q = make_float4(sx / c, sy / c, sz / c, si / c);
+            atomicSub(&m.cube_count[lin], cnt - 1);
+            atomicSub(m.total, cnt - 1);
+          }
+        }
+        m.pts[start + kept] = q; m.epoch[start + kept] = ep;
+        kept++;
+      }
+      if (kept != count) m.entries[e].count = kept;
+    }
+  }
+}
+// the valid cubes of the streams that were re-filtered are clean again
+__global__ void map_dirty_clear_kernel(MapClassDev* maps, const CubeWindow* __restrict__ windows, int nstreams, const int* __restrict__ need) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nstreams || !need[s]) return;
+  MapClassDev& m = maps[s];
+  const CubeWindow& w = windows[s];
+  for (int a = lane; a < 343; a += 32) {
+    if (!w.active[a]) continue;
+    const int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
+    if (i < 0 || i >= m.dims[0] || j < 0 || j >= m.dims[1] || k < 0 || k >= m.dims[2]) continue;
+    m.dirty[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]] = 0;
   }
 }
 
@@ -342,6 +469,9 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
     cube_count[cls].reserve((size_t)nstreams * ncubes * sizeof(int));
     epoch[cls].reserve((size_t)nstreams * pool);
     cudaMemsetAsync(epoch[cls].p, 0, (size_t)nstreams * pool, stream);
+    cube_dirty[cls].reserve((size_t)nstreams * ncubes);
+    cudaMemsetAsync(cube_dirty[cls].p, 0, (size_t)nstreams * ncubes, stream);
+    need[cls].reserve((size_t)nstreams * sizeof(int));
     cursor[cls].reserve((size_t)nstreams * 2 * sizeof(unsigned int));
     dev[cls].reserve((size_t)nstreams * sizeof(MapClassDev));
     views[cls].reserve((size_t)nstreams * sizeof(GridView));
@@ -370,6 +500,7 @@ void DeviceMap::create(int nstreams_, const MapConfig& c, cudaStream_t stream) {
       m.epoch = (unsigned char*)epoch[cls].p + (size_t)s * pool;
       m.eoff = (int*)eoff.p + (size_t)s * 256 * 3;
       m.cur_epoch = 0;
+      m.dirty = (unsigned char*)cube_dirty[cls].p + (size_t)s * ncubes;
     }
     cudaMemcpyAsync(dev[cls].p, h.data(), sizeof(MapClassDev) * nstreams, cudaMemcpyHostToDevice, stream);
     hdev[cls] = h;
@@ -392,6 +523,7 @@ void staged_upload(void* d_dst, const void* pinned, size_t bytes, cudaStream_t s
 }
 
 void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_t stream, bool staged) {
+  windows_valid = true;
   if (!h_windows) {}
   else if (staged) staged_upload(windows.p, h_windows, sizeof(CubeWindow) * nstreams, stream);
   else cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
@@ -416,7 +548,8 @@ void DeviceMap::unpack_npts(const double* d_vec, cudaStream_t stream) {
 }
 
 void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, int max_n, const MatchState* d_state, const float* d_tf,
-                       cudaStream_t stream, const int* step_skip) {
+                       cudaStream_t stream, const int* step_skip, bool filter_all) {
+  const CubeWindow* wins = (filter_all || !windows_valid) ? nullptr : (const CubeWindow*)windows.p;   // no update() yet: every cube counts as valid
   if (cap <= 0) return;
   if (max_n <= 0 || max_n > cap) max_n = cap;   // host-known upper bound of d_n[s]
   const size_t n = (size_t)nstreams * max_n;
@@ -434,11 +567,16 @@ void DeviceMap::insert(int cls, const float4* d_pts, const int* d_n, int cap, in
             (unsigned long long*)keys_a[cls].p, (unsigned int*)vals_a[cls].p, (int*)vals_b[cls].p, (GroupEntry*)keys_b[cls].p, gcap - 1, (int*)flags.p, skip, shard_rank, shard_nranks);
   CM_LAUNCH(map_merge_kernel, nb, 256, 0, stream, (const unsigned long long*)keys_a[cls].p, (const unsigned int*)vals_a[cls].p, (const int*)vals_b[cls].p,
             (const GroupEntry*)keys_b[cls].p, n, (const float4*)world[cls].p, (MapClassDev*)dev[cls].p, (PendingAdd*)pending[cls].p,
-            (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p, skip);
+            (unsigned int*)n_pending[cls].p, (unsigned int)n, (int*)flags.p, skip, wins);
   CM_LAUNCH(map_grow_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
             (MapClassDev*)dev[cls].p, (int*)flags.p);
   CM_LAUNCH(map_append_kernel, nb, 256, 0, stream, (const PendingAdd*)pending[cls].p, (const unsigned int*)n_pending[cls].p, (unsigned int)n,
-            (MapClassDev*)dev[cls].p);
+            (MapClassDev*)dev[cls].p, (const int*)vals_b[cls].p, (const float4*)world[cls].p);
+  if (wins) {   // downsizeValidCloud for cubes that hold raw points and are valid now (normally none: two tiny launches and an empty one)
+    CM_LAUNCH(map_need_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (const MapClassDev*)dev[cls].p, wins, nstreams, (int*)need[cls].p, skip);
+    CM_LAUNCH(map_refilter_kernel, 296, 256, 0, stream, (MapClassDev*)dev[cls].p, wins, nstreams, (const int*)need[cls].p);
+    CM_LAUNCH(map_dirty_clear_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (MapClassDev*)dev[cls].p, wins, nstreams, (const int*)need[cls].p);
+  }
 }
 
 // ---- FeatureMap::shift ----------------------------------------------------------------------------------------------------------

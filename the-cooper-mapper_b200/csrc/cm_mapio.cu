@@ -179,8 +179,8 @@ static int insert_clouds(cm_ctx* ctx, int stream_index, const std::vector<cm_poi
     // only stream_index has points: bias the base pointers so that [stream_index][0] is the start of the upload
     const float4* pc = (const float4*)ctx->m_corner_in.p - (size_t)stream_index * cap_c;
     const float4* ps = (const float4*)ctx->m_surf_in.p - (size_t)stream_index * cap_s;
-    ctx->map.insert(0, pc, (const int*)ctx->m_n_in.p, cap_c, cap_c, nullptr, (const float*)ctx->m_tf.p, st);
-    ctx->map.insert(1, ps, (const int*)ctx->m_n_in.p + S, cap_s, cap_s, nullptr, (const float*)ctx->m_tf.p, st);
+    ctx->map.insert(0, pc, (const int*)ctx->m_n_in.p, cap_c, cap_c, nullptr, (const float*)ctx->m_tf.p, st, nullptr, true);   // every file is filtered (:428-456)
+    ctx->map.insert(1, ps, (const int*)ctx->m_n_in.p + S, cap_s, cap_s, nullptr, (const float*)ctx->m_tf.p, st, nullptr, true);
     int flags[8];
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));

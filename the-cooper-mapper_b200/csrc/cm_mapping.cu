@@ -782,6 +782,46 @@ int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, 
   return pipeline_step(ctx, d_frames, rows, cols, false, odom, mapped, stats);
 }
 
+// FeatureMap::update(sensorPose) (FeatureMap.h:232-254) of one stream outside a stage step: shift if needed, new valid-cube window
+int cm_map_update_host(cm_ctx* ctx, int stream_index, const float* sensor) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (!sensor || stream_index < 0 || stream_index >= ctx->map_streams) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const int S = ctx->map_streams;
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const size_t wb = sizeof(CubeWindow) * (size_t)S;
+    std::vector<CubeWindow> wins(S);
+    if (ctx->wins_shadow.size() == wb) memcpy(wins.data(), ctx->wins_shadow.data(), wb);
+    else {   // no stream has a window yet: the others get an empty one around their current cube
+      memset(wins.data(), 0, wb);
+      for (int s = 0; s < S; s++) {
+        const MappingStream& o = ctx->mstreams[s];
+        for (int k = 0; k < 3; k++) { wins[s].origin[k] = o.origin[k]; wins[s].w0[k] = o.cur[k] - 3; }
+        wins[s].dims[0] = ctx->cfg.cube_w; wins[s].dims[1] = ctx->cfg.cube_h; wins[s].dims[2] = ctx->cfg.cube_d; wins[s].cube_size = ctx->cfg.cube_size;
+      }
+    }
+    MappingStream ms = ctx->mstreams[stream_index];
+    int d[3];
+    update_window(ctx->cfg, ms, sensor, wins[stream_index], d);
+    if (d[0] || d[1] || d[2]) {
+      if (ctx->dist.on) return fail(ctx, CM_ERR_UNSUPPORTED, "FeatureMap::shift on a sharded map");
+      const bool wrong_way = d[0] > 0 || (d[0] == 0 && (d[1] > 0 || (d[1] == 0 && d[2] > 0)));
+      if (wrong_way && ctx->map.cur_epoch[stream_index] >= 255) return fail(ctx, CM_ERR_UNSUPPORTED, "more than 255 wrong-way FeatureMap::shift calls");
+      ctx->map.shift(stream_index, d, ms.origin, st);
+      ctx->n_shifts++;
+    }
+    ctx->mstreams[stream_index] = ms;
+    ctx->wins_shadow.assign((const unsigned char*)wins.data(), (const unsigned char*)wins.data() + wb);
+    ctx->map.set_windows(wins.data(), dev_params(ctx->cfg).knn_gate, st, false);
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));   // `wins` goes out of scope
+    CM_CUDA_CHECK(ctx, cudaGetLastError());
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
+
 int cm_map_insert_host(cm_ctx* ctx, const cm_point* corner, const int* n_corner, int cap_corner, const cm_point* surf,
                        const int* n_surf, int cap_surf, const cm_iso* tf) {
   if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
