@@ -618,7 +618,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs (1-based); 2 = the headline")
-    ap.add_argument("--streams", type=int, default=64, help="LiDAR streams per GPU (config 2)")
+    ap.add_argument("--streams", type=int, default=128, help="LiDAR streams per GPU (config 2); r01 and the first half of r02 used 64")
     ap.add_argument("--pool", type=int, default=0, help="distinct synthetic sweeps generated on the host (0: one per stream-step)")
     ap.add_argument("--ahead", type=int, default=2, help="end-to-end arm: sweeps uploaded ahead of the one being registered (1..3)")
     ap.add_argument("--pinned-gb", type=float, default=6.0, help="end-to-end arm: pinned host memory for sweep buffers per rank")

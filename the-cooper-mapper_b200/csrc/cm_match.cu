@@ -410,8 +410,14 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
   if (a.skip && *a.skip) return;
   const int n = min(a.iter_dev ? a.hard_count[*a.iter_dev] : *a.hard_count, a.hard_cap);
   const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+  // the warps take the queries one at a time off a shared cursor (the cost of a hard query varies by an order of magnitude with
+  // the number of shells it needs: a static split leaves most warps idle behind the few long ones)
+  int* cursor = (a.iter_dev ? a.hard_count + *a.iter_dev : a.hard_count) + CM_MAX_EVALS * 8;
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(cursor, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n) break;
     const HardItem* item = reinterpret_cast<const HardItem*>(a.hard) + i;
     const int s = item->s, t = item->t;
     const MatchState& st = a.state[s];
@@ -850,7 +856,7 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
 }
 
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
-  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS * 8, stream);
+  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS * 8 * 2, stream);   // counters + cursors
   if (m.tickets) cudaMemsetAsync(m.tickets, 0, sizeof(int) * m.nstreams, stream);
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
 }
