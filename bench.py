@@ -423,11 +423,49 @@ def run_config2(args, synth, rank, world, local_rank):
     e2e_ms = ctx.timer_elapsed_ms()
     barrier()
     sampler.mark_end()
-    sampler.stop()
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * K * NPTS / (float(t.item()) * 1e-3)
+
+    # ---- end-to-end with the xyz-only entry: pinned packed coordinates, 12 B per point over PCIe (the pipeline never reads the
+    #      intensity of a raw point: scan registration replaces it with ring + relTime, OrganizedScanRegistration.cpp:109-110) ---------
+    e2e16_value = e2e_value
+    e2e_bytes = int(S * NPTS * 16 + S * 48)
+    e2e_input = "pinned packed cm_point sweeps (x, y, z, intensity: 16 B per point)"
+    if not args.no_xyz12_arm:
+        x_t = [torch.empty((S, NPTS, 3), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+        x_np = [h.numpy() for h in x_t]
+        for b in range(min(nbuf, n_steps)):
+            np.copyto(x_np[b], frames[idx[n_steps + b]].reshape(S, NPTS, 4)[:, :, :3])
+        x_ptr = [ctx.cloud_ptrs([x_np[b][si] for si in range(S)]) for b in range(nbuf)]
+
+        def xyz_steps(first, count):
+            for j in range(first, min(first + A, first + count)):
+                ctx.pipeline_prefetch_strided_ptrs(x_ptr[j % nbuf][0], 12, ROWS, COLS)
+            for k in range(first, first + count):
+                if k + A < first + count:
+                    ctx.pipeline_prefetch_strided_ptrs(x_ptr[(k + A) % nbuf][0], 12, ROWS, COLS)
+                ctx.pipeline_step_strided_ptrs(x_ptr[k % nbuf][0], 12, ROWS, COLS, odom[ge(k)], mapped, stats)
+
+        xyz_steps(0, W)
+        barrier()
+        sampler.mark_begin()
+        ctx.timer_record(0)
+        xyz_steps(W, K)
+        ctx.timer_record(1)
+        x_ms = ctx.timer_elapsed_ms()
+        barrier()
+        sampler.mark_end()
+        t = torch.tensor([x_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * S * K * NPTS / (float(t.item()) * 1e-3)
+        e2e_bytes = int(S * NPTS * 12 + S * 48)
+        e2e_input = "pinned packed coordinates through the xyz-only entry (cm_pipeline_*_strided_host, stride 12: 12 B per point)"
+        del x_t, x_np, x_ptr
+
+    sampler.stop()
 
     # ---- end-to-end from the layout a nodelet holds: one PAGEABLE pcl::PointXYZI cloud (32-byte stride) per stream ------------------
     # cm_pipeline_prefetch_strided_host packs x, y, z into library-owned pinned staging with worker threads and uploads 12 B / point;
@@ -597,8 +635,10 @@ def run_config2(args, synth, rank, world, local_rank):
                        "numa_bind": numa, "parallelism": "streams sharded over ranks, no collective"},
             "roofline": roof,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(S * NPTS * 16 + S * 48),
-                    "d2h_bytes_per_step": int(S * 48 + S * C.sizeof(cmb.MatchStats))},
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": e2e_bytes,
+                    "d2h_bytes_per_step": int(S * 48 + S * C.sizeof(cmb.MatchStats)), "input": e2e_input},
+            "e2e_xyzi16": {"value": e2e16_value, "unit": "points/s", "h2d_bytes_per_step": int(S * NPTS * 16 + S * 48),
+                           "input": "pinned packed cm_point sweeps (16 B per point) through cm_pipeline_prefetch_host / cm_pipeline_step_host"},
             "e2e_pcl_layout": e2e_pcl,
             "stage_alone": stage,
             "p50_latency_ms": lat.get("end_to_end"), "p50_latency_ms_by_stage": lat,
@@ -625,6 +665,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--no-xyz12-arm", action="store_true", help="report the 16-byte end-to-end arm as e2e instead of the xyz-only 12-byte entry")
     ap.add_argument("--no-pcl-arm", action="store_true", help="skip the end-to-end arm that starts from pageable 32-byte-stride clouds")
     ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()

@@ -235,7 +235,9 @@ int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, 
  * of the calling thread's affinity mask, at most 16), uploads 12 bytes per point chunk by chunk while the next chunk is being
  * packed, and expands them on the device; the intensity is not transferred (scan registration replaces it with ring + relTime,
  * OrganizedScanRegistration.cpp:109-110).  The clouds may be reused as soon as the call returns; the slot is keyed by clouds[0].
- * Results are bit-identical to the packed entries. */
+ * Special case, the xyz-only entry: stride 12 with the clouds of all streams back to back in ONE buffer needs no packing -- the
+ * buffer is uploaded as it is (asynchronously if it is pinned; it must then stay untouched until its step has run, like the
+ * packed 16-byte entries) and a quarter fewer bytes cross PCIe.  Results are bit-identical to the packed entries. */
 int cm_pipeline_prefetch_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols);
 int cm_pipeline_step_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols, const cm_iso* odom,
                                   cm_iso* mapped, cm_match_stats* stats);

@@ -298,6 +298,17 @@ class Context:
         arr = (C.c_void_p * len(clouds))(*[c.ctypes.data for c in clouds])
         return arr, stride
 
+    def cloud_ptrs(self, clouds):
+        """(void*[S], stride) of a list of per-stream clouds, for the *_ptrs variants below (built once, used every step)."""
+        return self._cloud_ptrs(clouds)
+
+    def pipeline_prefetch_strided_ptrs(self, arr, stride, rows, cols):
+        return self._check(self.L.cm_pipeline_prefetch_strided_host(self.h, arr, C.c_size_t(stride), C.c_int(rows), C.c_int(cols)))
+
+    def pipeline_step_strided_ptrs(self, arr, stride, rows, cols, odoms_packed, mapped_out, stats_out):
+        return self._check(self.L.cm_pipeline_step_strided_host(self.h, arr, C.c_size_t(stride), C.c_int(rows), C.c_int(cols),
+                                                                _ptr(odoms_packed), _ptr(mapped_out), stats_out))
+
     def pipeline_prefetch_strided(self, clouds, rows, cols):
         """cm_pipeline_prefetch_strided_host: one host cloud per stream, any point stride (pcl::PointXYZI = 32 bytes), pageable memory."""
         arr, stride = self._cloud_ptrs(clouds)

@@ -123,7 +123,9 @@ int stage_upload_strided(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const void* const*
   const size_t total = npts * S;
   if (total % 4) return ctx_fail(ctx, CM_ERR_ARG, "rows * cols * streams must be a multiple of 4");
   const size_t bytes = total * 12;
-  if (slot.h_xyz_cap < bytes) {
+  bool packed_in_place = stride == 12;
+  for (int s = 1; s < S && packed_in_place; s++) packed_in_place = (const char*)clouds[s] == (const char*)clouds[0] + (size_t)s * npts * 12;
+  if (!packed_in_place && slot.h_xyz_cap < bytes) {
     if (slot.h_xyz) cudaFreeHost(slot.h_xyz);
     slot.h_xyz = nullptr; slot.h_xyz_cap = 0;
     static const bool wc = getenv("COOPERMAP_STAGE_WC") != nullptr;   // write-combined staging: faster for the copy engine, slower to fill
@@ -132,6 +134,24 @@ int stage_upload_strided(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const void* const*
   }
   slot.frames_xyz.reserve(bytes);
   slot.frames.reserve(total * sizeof(float4));
+  cudaStream_t cs2[2] = {ctx->copy_stream, ctx->copy_stream2};
+  // packed coordinates of all streams in ONE buffer (stride 12, cloud s right behind cloud s - 1): nothing to pack -- the caller's
+  // buffer goes to the device as it is (asynchronously when it is pinned), 12 bytes per point, in two halves on the two copy streams
+  bool contiguous = stride == 12;
+  for (int s = 1; s < S && contiguous; s++) contiguous = (const char*)clouds[s] == (const char*)clouds[0] + (size_t)s * npts * 12;
+  if (contiguous) {
+    const size_t half = (bytes / 2) & ~(size_t)255;
+    CM_TIMED("h2d_upload(xyz half)", cs2[0], CM_CUDA_CHECK(ctx, cudaMemcpyAsync(slot.frames_xyz.p, clouds[0], half, cudaMemcpyHostToDevice, cs2[0])));
+    CM_TIMED("h2d_upload(xyz half)", cs2[1], CM_CUDA_CHECK(ctx, cudaMemcpyAsync((char*)slot.frames_xyz.p + half, (const char*)clouds[0] + half, bytes - half,
+                                                                                  cudaMemcpyHostToDevice, cs2[1])));
+    CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied, cs2[0]));
+    CM_CUDA_CHECK(ctx, cudaEventRecord(slot.copied2, cs2[1]));
+    CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(consumer, slot.copied, 0));
+    CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(consumer, slot.copied2, 0));
+    const size_t nq = total / 4;
+    CM_LAUNCH(unpack_xyz_kernel, (int)std::min<size_t>((nq + 255) / 256, 148 * 8), 256, 0, consumer, (const float4*)slot.frames_xyz.p, (float4*)slot.frames.p, nq);
+    return CM_OK;
+  }
   StagePool* pool = stage_pool(ctx);
   // chunks of whole tasks; a task = `tpts` consecutive points of one stream
   const int NCH = 4;
