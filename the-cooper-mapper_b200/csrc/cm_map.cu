@@ -317,12 +317,20 @@ __global__ void map_need_kernel(const MapClassDev* maps, const CubeWindow* __res
   if (!*skip) {
     const MapClassDev& m = maps[s];
     const CubeWindow& w = windows[s];
-    for (int a = lane; a < 343; a += 32) {
-      if (!w.active[a]) continue;
+    // 11 cubes of the 7x7x7 window per lane: all `active` bytes first, then all `dirty` bytes (two load latencies, not twenty-two)
+    unsigned char act[11];
+#pragma unroll
+    for (int q = 0; q < 11; q++) { const int a = lane + 32 * q; act[q] = a < 343 ? w.active[a] : (unsigned char)0; }
+    unsigned char dr[11];
+#pragma unroll
+    for (int q = 0; q < 11; q++) {
+      const int a = lane + 32 * q;
       const int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
-      if (i < 0 || i >= m.dims[0] || j < 0 || j >= m.dims[1] || k < 0 || k >= m.dims[2]) continue;
-      any |= m.dirty[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
+      const bool ok = act[q] && i >= 0 && i < m.dims[0] && j >= 0 && j < m.dims[1] && k >= 0 && k < m.dims[2];
+      dr[q] = ok ? m.dirty[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]] : (unsigned char)0;
     }
+#pragma unroll
+    for (int q = 0; q < 11; q++) any |= dr[q];
   }
   any = __any_sync(0xffffffffu, any);
   if (lane == 0) need[s] = any ? 1 : 0;
@@ -330,8 +338,12 @@ __global__ void map_need_kernel(const MapClassDev* maps, const CubeWindow* __res
 // one thread per cell of a stream that needs it: the points of dirty valid cubes, voxel by voxel in block order (= push order),
 // become one centroid at the voxel's first slot; the block is compacted in place
 __global__ void map_refilter_kernel(MapClassDev* maps, const CubeWindow* __restrict__ windows, int nstreams, const int* __restrict__ need) {
-  for (int s = 0; s < nstreams; s++) {
-    if (!need[s]) continue;
+  for (int s0 = 0; s0 < nstreams; s0 += 32) {   // 32 streams' flags per load: the usual case (nothing to do) costs nstreams / 32 loads
+   const int lane_ = threadIdx.x & 31;
+   unsigned int todo = __ballot_sync(0xffffffffu, s0 + lane_ < nstreams && need[s0 + lane_] != 0);
+   while (todo) {
+    const int s = s0 + __ffs(todo) - 1;
+    todo &= todo - 1;
     MapClassDev& m = maps[s];
     const CubeWindow& w = windows[s];
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e <= m.mask; e += gridDim.x * blockDim.x) {
@@ -375,6 +387,7 @@ __global__ void map_refilter_kernel(MapClassDev* maps, const CubeWindow* __restr
       }
       if (kept != count) m.entries[e].count = kept;
     }
+   }
   }
 }
 // the valid cubes of the streams that were re-filtered are clean again

@@ -18,7 +18,7 @@ for r in rows:
     except Exception: continue
     per[(fpath.split('/')[-1], int(ln))]+=ins; smp[(fpath.split('/')[-1], int(ln))]+=s
 tot=sum(per.values()); tots=sum(smp.values())
-b=[(36,39,'point_valid'),(71,93,'FlagScan (ballot prefix sums)'),(120,133,'window_cov (pointClassify mean + covariance)'),(140,144,'window_not_line (eigen-solve early-out)'),(147,164,'window_line (eigen-solve + 0.08 m test)'),(166,174,'cos_angle / sq_diff'),(179,269,'bitonic sort of the voxel runs'),(317,342,'ring row bulk copy + wait'),(343,363,'ordered compaction'),(364,392,'init / tag'),(395,463,'mask: events + replay'),(465,478,'curvature'),(480,512,'region bounds / region of a cell'),(520,566,'candidate list + window list'),(569,599,'pass 1 (warp 0, chained arg-min picks)'),(600,638,'pointClassify driver (warps 1-15) incl. barrier waits'),(642,655,'curvature rank by counting'),(656,683,'pass 2 flags + prefixes'),(684,744,'pass 3 prefixes + list bases'),(745,781,'placement'),(783,802,'outputs'),(804,845,'voxel filter: bounding box'),(846,889,'voxel filter: indices + runs'),(890,923,'voxel filter: keys + expand'),(924,960,'voxel filter: heads + centroids')]
+b=[(37,40,'point_valid'),(72,94,'FlagScan (ballot prefix sums)'),(121,134,'window_cov (pointClassify mean + covariance)'),(141,145,'window_not_line (eigen-solve early-out)'),(148,165,'window_line (eigen-solve + 0.08 m test)'),(167,175,'cos_angle / sq_diff'),(180,270,'bitonic sort of the voxel runs'),(318,343,'ring row bulk copy + wait'),(344,364,'ordered compaction'),(365,393,'init / tag'),(396,464,'mask: events + replay'),(466,479,'curvature'),(481,515,'region bounds / region of a cell'),(523,568,'candidate list + window list'),(570,631,'pass 1 (warp 0, register-resident arg-min picks)'),(632,649,'curvature rank by counting (warps 1-15)'),(650,688,'pointClassify driver (warps 1-15) incl. barrier waits'),(689,716,'pass 2 flags + prefixes'),(717,777,'pass 3 prefixes + list bases'),(778,815,'placement'),(816,836,'outputs'),(837,878,'voxel filter: bounding box'),(879,922,'voxel filter: indices + runs'),(923,956,'voxel filter: keys + expand'),(957,994,'voxel filter: heads + centroids')]
 acc=collections.Counter(); accs=collections.Counter()
 for (f,l),v in per.items():
     if f=='cm_scanreg.cu':
