@@ -90,7 +90,7 @@ class OrganisedScanRegistration : public ScanRegistration {
 // MultiScanRegistration::process (MultiScanRegistration.cpp:95-200): raw azimuth-major sweep of a spinning multi-beam LiDAR.
 class MultiScanRegistration : public ScanRegistration {
  public:
-  enum Lidar { VLP16 = 0, HDL32 = 1, HDL64E = 2 };   // MultiScanRegistration.h:90-102
+  enum Lidar { VLP16 = 0, HDL32 = 1, HDL64E = 2, Pandar40 = 3 };   // MultiScanRegistration.h:24-42, 90-102
   using ScanRegistration::ScanRegistration;
   void process(const PointCloud& sweep, Lidar lidar) {
     cm_scanreg_out out = cm_scanreg_out();
@@ -99,6 +99,23 @@ class MultiScanRegistration : public ScanRegistration {
     ctx_.check(cm_scanreg_sweep_host(ctx_.get(), sweep.data(), sweep.size(), (int)lidar, &out, &rows, &cols));
     finish((int)sweep.size());
   }
+  // ScanRegistration::handleIMUMessage (ScanRegistration.cpp:89-121): stamp in seconds, roll / pitch / yaw from tf's getRPY, raw acceleration
+  void handleIMUMessage(double stamp, double roll, double pitch, double yaw, double ax, double ay, double az) {
+    const cm_imu_sample m = {stamp, roll, pitch, yaw, ax, ay, az};
+    ctx_.check(cm_imu_push_host(ctx_.get(), &m));
+  }
+  // process(in, scanTime) with hasIMUData(): every point projected to the sweep start (ScanRegistration.cpp:123-188)
+  void process(const PointCloud& sweep, Lidar lidar, double scanTime) {
+    cm_scanreg_out out = cm_scanreg_out();
+    prepare(sweep.size(), out);
+    int rows = 0, cols = 0;
+    ctx_.check(cm_scanreg_sweep_imu_host(ctx_.get(), sweep.data(), sweep.size(), (int)lidar, scanTime, &out, &rows, &cols, imuTrans_));
+    finish((int)sweep.size());
+  }
+  const float* imuTrans() const { return imuTrans_; }   // the four /imu_trans points (x, y, z each), ScanRegistration.cpp:681-708
+
+ private:
+  float imuTrans_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // ---- stage 2 ---------------------------------------------------------------------------------------------------------------
@@ -145,7 +162,24 @@ class LaserMapping {
   const cm_match_stats& stats() const { return stats_; }
   // saveMap service (LaserMatcher.cpp:357-394 -> FeatureMap::saveCloudToFiles)
   int saveMap(const std::string& dir) { int n = 0; ctx_.check(cm_map_save_host(ctx_.get(), 0, dir.c_str(), &n)); return n; }
-  // /laser_cloud_surround_* style export: all resident points of a class (0 corner, 1 surf)
+  // /laser_cloud_surround_corner, _surf: FeatureMap::getSurroundFeature (FeatureMap.h:256-265), published at LaserMatcher.cpp:357-394
+  void surroundClouds(PointCloud& corner, PointCloud& surf) {
+    size_t n2[2] = {0, 0};
+    ctx_.check(cm_map_surround_host(ctx_.get(), 0, nullptr, 0, nullptr, 0, n2));
+    corner.resize(n2[0] ? n2[0] : 1); surf.resize(n2[1] ? n2[1] : 1);
+    ctx_.check(cm_map_surround_host(ctx_.get(), 0, corner.data(), corner.size(), surf.data(), surf.size(), n2));
+    corner.resize(n2[0]); surf.resize(n2[1]);
+  }
+  // /FullMap and the ~pubFullMap service: FeatureMap::getFullMap (FeatureMap.h:267-287) at the full-map leaf (map_filter_full)
+  PointCloud fullMap(float leaf) {
+    size_t n = 0;
+    ctx_.check(cm_map_full_host(ctx_.get(), 0, leaf, nullptr, 0, &n));
+    PointCloud out(n ? n : 1);
+    ctx_.check(cm_map_full_host(ctx_.get(), 0, leaf, out.data(), out.size(), &n));
+    out.resize(n);
+    return out;
+  }
+  // every resident point of a class (0 corner, 1 surf), storage order
   PointCloud mapCloud(int cls) {
     size_t n = 0;
     ctx_.check(cm_map_export_host(ctx_.get(), 0, cls, nullptr, nullptr, 0, &n));
@@ -170,6 +204,16 @@ class LaserLocalization : public LaserMapping {
     int n = 0; size_t pts = 0, bad = 0;
     ctx_.check(cm_map_load_host(ctx_.get(), 0, dir.c_str(), &n, &pts, &bad));
     return n;
+  }
+  // dynamic mode (DynamicFeatureMap, DynamicFeatureMap.h:129-161, 504-677): <dir>/index2.txt, a window of cubes around the sensor resident
+  int openPagedMap(const std::string& dir, int windowW = 21, int windowH = 11, int windowD = 21) {
+    int n = 0;
+    ctx_.check(cm_map_page_open_host(ctx_.get(), 0, dir.c_str(), windowW, windowH, windowD, &n));
+    return n;
+  }
+  void updatePagedMap(float x, float y, float z) {
+    const float s[3] = {x, y, z};
+    ctx_.check(cm_map_page_update_host(ctx_.get(), 0, s, nullptr, nullptr, nullptr));
   }
   cm_iso process(const cm_iso& odom, const PointCloud& cornerLast, const PointCloud& surfLast) {
     cm_iso mapped; int nc = (int)cornerLast.size(), ns = (int)surfLast.size();
