@@ -29,6 +29,7 @@ namespace cm {
 #define VS_WARPS (VS_T / 32)
 #define VS_PAD 0xFFFFFFFFu
 #define VS_RC 16384          // runs whose sort buffers fit in shared memory (2 x u32 keys + 2 x u16 values = 192 KB)
+#define VS_DYN_SMEM ((size_t)VS_RC * 12)   // dynamic shared memory: the sort buffers, later the point stage of the centroid phase
 #define VS_ARRAYS 7          // scratch arrays per segment: key A / B, value A / B, run start, run end, point order
 
 struct VoxClass {            // one batch of segments filtered with one leaf
@@ -302,31 +303,43 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
   }
   __syncthreads();
 
-  // ---- 5. centroids: eight lanes per voxel load its points together, the adds stay sequential in (voxel, input) order -------
+  // ---- 5. centroids.  The points of up to 1024 consecutive voxels (contiguous in `order`) are gathered into shared memory by the
+  //      whole CTA -- independent loads, coalesced over `order` -- then ONE thread per voxel adds its points up sequentially out of
+  //      shared memory: Eigen::VectorXf centroid += point in sorted (= input) order.  (The sort buffers are free by now.) ------------
   float4* out = k.out + (size_t)s * k.cap_out;
   {
-    const int sub = tid & 7;
-    for (unsigned int v0 = 0; v0 < nvox; v0 += VS_T / 8) {
-      const unsigned int v = v0 + (unsigned int)(tid >> 3);
-      unsigned int p0 = 0, np = 0;
-      if (v < nvox) { p0 = voff[v]; np = voff[v + 1] - p0; }
-      const unsigned int npmax = __reduce_max_sync(0xffffffffu, np);
-      float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
-      for (unsigned int b = 0; b < npmax; b += 8) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b + sub < np) q = in[order[p0 + b + sub]];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-          const float x = __shfl_sync(0xffffffffu, q.x, jj, 8), y = __shfl_sync(0xffffffffu, q.y, jj, 8);
-          const float z = __shfl_sync(0xffffffffu, q.z, jj, 8), w = __shfl_sync(0xffffffffu, q.w, jj, 8);
-          if (b + jj < np) { cx += x; cy += y; cz += z; cw += w; }   // Eigen::VectorXf centroid += point, in sorted (= input) order
+    float4* stage = reinterpret_cast<float4*>(vox_dyn_smem);
+    const unsigned int PB = (unsigned int)(VS_DYN_SMEM / sizeof(float4));   // points per round
+    for (unsigned int v0 = 0; v0 < nvox;) {
+      const unsigned int pbase = voff[v0];
+      const unsigned int v = v0 + (unsigned int)tid;
+      const bool fits = v < nvox && voff[v + 1] - pbase <= PB;              // monotone in tid: the voxels of this round are a prefix
+      const unsigned int nv = (unsigned int)__syncthreads_count(fits ? 1 : 0);
+      if (nv == 0) {   // one voxel with more points than the stage holds: its sum straight from global memory
+        if (tid == 0) {
+          const unsigned int pe = voff[v0 + 1];
+          float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
+          for (unsigned int p = pbase; p < pe; p++) { const float4 q = in[order[p]]; cx += q.x; cy += q.y; cz += q.z; cw += q.w; }
+          const float c = (float)(pe - pbase);
+          if (v0 < (unsigned int)k.cap_out) out[v0] = make_float4(cx / c, cy / c, cz / c, cw / c);
+          else if (a.overflow) atomicExch(a.overflow, 1);
         }
+        v0 += 1;
+        continue;
       }
-      if (sub == 0 && v < nvox) {
-        const float c = (float)np;
+      const unsigned int npnt = voff[v0 + nv] - pbase;
+      for (unsigned int p = tid; p < npnt; p += VS_T) stage[p] = in[order[pbase + p]];
+      __syncthreads();
+      if ((unsigned int)tid < nv) {
+        const unsigned int pa = voff[v] - pbase, pe = voff[v + 1] - pbase;
+        float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
+        for (unsigned int p = pa; p < pe; p++) { const float4 q = stage[p]; cx += q.x; cy += q.y; cz += q.z; cw += q.w; }
+        const float c = (float)(pe - pa);
         if (v < (unsigned int)k.cap_out) out[v] = make_float4(cx / c, cy / c, cz / c, cw / c);
         else if (a.overflow) atomicExch(a.overflow, 1);
       }
+      __syncthreads();   // the next round overwrites the stage
+      v0 += nv;
     }
   }
   if (tid == 0) k.n_out[s] = nvox <= (unsigned int)k.cap_out ? (int)nvox : k.cap_out;
@@ -335,7 +348,6 @@ __global__ void __launch_bounds__(VS_T, 1) vox_segment_kernel(VoxSegArgs a) {
 // number of key bits that index `cells` distinct voxel indices
 int vox_index_bits(long long cells) { int b = 1; while (b < 32 && (1LL << b) < cells) b++; return b; }
 
-#define VS_DYN_SMEM ((size_t)VS_RC * 12)
 static void vox_configure() {
   static bool done = false;
   if (!done) { cudaFuncSetAttribute(vox_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_DYN_SMEM); done = true; }
