@@ -180,6 +180,11 @@ int cm_mapping_create(cm_ctx* ctx, int nstreams, size_t max_corner_points, size_
  * FeatureMap.h:232-245, 354-376) is reproduced literally, including the cubes its in-place pointer swaps move the wrong way. */
 int cm_mapping_process_host(cm_ctx* ctx, const cm_iso* odom, const cm_point* corner, const int* n_corner, int cap_corner,
                             const cm_point* surf, const int* n_surf, int cap_surf, cm_iso* mapped, cm_match_stats* stats);
+/* cm_mapping_process_host and cm_pipeline_step_* return as soon as the poses are on the host: FeatureMap::addFeatureCloud of that
+ * frame (the map insertion) is enqueued behind them on the context's stream and finishes on its own, while the caller publishes
+ * the pose and fetches the next sweep.  Everything that reads or changes the map afterwards is ordered behind it.  What the
+ * insertion hit (CM_ERR_CAPACITY, voxel range) is reported by the NEXT step -- or by cm_mapping_sync, which waits for it. */
+int cm_mapping_sync(cm_ctx* ctx);
 
 /* LaserLocalization::process (LaserLocalization.cpp:163-188) for one frame per stream against the map held by the context
  * (built with cm_map_insert_host / cm_map_load_host): same frame preparation as cm_mapping_process_host, but the pose is

@@ -20,6 +20,28 @@ def test_map_capacity_is_reported_not_silently_dropped(cmb, synth):
     ctx.close()
 
 
+def test_step_returns_with_the_pose_and_the_insertion_reports_later(cmb, synth):
+    """cm_pipeline_step_* returns when the poses are in; the map insertion it enqueued overflows a deliberately small map: the error
+    is not lost -- cm_mapping_sync (or the next step) reports it."""
+    sc = synth.make_scene(seed=61, extent=40.0, n_boxes=12, n_poles=10)
+    R, t = synth.trajectory(1, speed=0.5)[0]
+    fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=5, cols=720)[None]
+    od = [(R.astype(np.float32), t.astype(np.float32))]
+    for how in ("sync", "next_step"):
+        ctx = cmb.Context(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+        ctx.mapping_create(1, 50, 200)                      # the first sweep's features do not fit
+        isos, stats = ctx.pipeline_step(fr, od)             # empty map: pose = odometry, the insertion runs behind the return
+        assert np.array_equal(isos[0][1], od[0][1])
+        with pytest.raises(cmb.CoopermapError) as e:
+            if how == "sync":
+                ctx.mapping_sync()
+            else:
+                ctx.pipeline_step(fr, od)
+        assert "capacity" in str(e.value)
+        ctx.mapping_sync()                                  # reported once
+        ctx.close()
+
+
 def test_bad_arguments_return_error_codes(cmb):
     ctx = cmb.Context()
     L = ctx.L

@@ -419,6 +419,10 @@ class Context:
     def timer_record_side(self, which):
         self._check(self.L.cm_timer_record_side(self.h, C.c_int(which)))
 
+    def mapping_sync(self):
+        """wait for the map insertion of the last mapping / pipeline step and report what it hit"""
+        self._check(self.L.cm_mapping_sync(self.h))
+
     def pipeline_wait(self):
         self._check(self.L.cm_pipeline_wait(self.h))
 

@@ -99,6 +99,8 @@ void cm_ctx_destroy(cm_ctx* ctx) {
   cm::stage_pool_destroy(ctx);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->result_ready) cudaEventDestroy(ctx->result_ready);
   delete ctx;
 }
 

@@ -120,6 +120,9 @@ struct cm_ctx {
   // pinned, device-accessible host staging for the per-step parameter uploads of the mapping stage (poses, cube windows): they
   // are copied by a kernel, not by the copy engine that the sweep uploads keep busy
   void* h_stage = nullptr; size_t h_stage_cap = 0;
+  // pinned landing area of a mapping step's results (states, filtered counts, flags) + the event behind their copy: the step
+  // returns when the poses are in, the map insertion enqueued behind them finishes on its own
+  void* h_result = nullptr; size_t h_result_cap = 0; cudaEvent_t result_ready = nullptr;
   std::vector<unsigned char> wins_shadow;   // the cube windows last sent to the device (they rarely change from sweep to sweep)
   cm::KernelProfiler prof, prof_sr;   // search_kernel + search_hard_kernel / sr_ring_kernel launches of the pipeline
   cudaEvent_t timer[2] = {nullptr, nullptr};

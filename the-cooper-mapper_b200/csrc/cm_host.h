@@ -186,7 +186,7 @@ struct KernelProfiler {
 };
 inline void HardQueue::attach(MatchLaunch& m, size_t capacity) {
   if (capacity < 1) capacity = 1;
-  items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS * 8 * 2);   // x8: one counter row per stream group; x2: the work cursors of search_hard_kernel behind the counters
+  items.reserve(capacity * CM_HARD_ITEM_BYTES); count.reserve(sizeof(int) * CM_MAX_EVALS * 8);   // x8: one counter row per stream group
   m.hard = items.p; m.hard_count = (int*)count.p; m.hard_cap = (int)capacity;
   const int maxq = m.bound_queries > 0 ? m.bound_queries : (m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf);
   m.partial_blocks = (maxq + 32 + 255) / 256;

@@ -321,6 +321,26 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     }
   }
   issue_deferred_prefetch(ctx);   // the Gauss-Newton loop is on its way: submit the next sweep's upload + scan registration now
+  // results: states, filtered counts and flags come back together, into pinned memory, with an event behind them -- the step's
+  // only host synchronisation.  The map insertion is enqueued BEHIND that event: the caller has its poses while the insertion
+  // still runs (a synchronous caller's next sweep is uploaded and scan-registered on the side stream meanwhile).  What the
+  // insertion reports (capacity, voxel range) stays in the device flags and comes back with the next step's results, or with
+  // cm_mapping_sync / the map read-outs.
+  const size_t res_bytes = sizeof(MatchState) * S + sizeof(int) * 2 * S + sizeof(int) * 8;
+  if (ctx->h_result_cap < res_bytes) {
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    ctx->h_result = nullptr; ctx->h_result_cap = 0;
+    CM_CUDA_CHECK(ctx, cudaHostAlloc(&ctx->h_result, res_bytes, cudaHostAllocDefault));
+    ctx->h_result_cap = res_bytes;
+  }
+  if (!ctx->result_ready) CM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->result_ready, cudaEventDisableTiming));
+  MatchState* hs = (MatchState*)ctx->h_result;
+  int* nds = (int*)(hs + S);
+  int* flags = nds + 2 * S;
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds, d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+  CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->result_ready, st));
   // featureMapUpdate (commented out in LaserLocalization::process, LaserLocalization.cpp:186)
   if (!localise) {
     CM_CUDA_CHECK(ctx, cudaEventRecord(ctx->aux_fork, st));
@@ -340,14 +360,7 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
     }
     CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
   }
-  // results: states, filtered counts and flags come back together -- the step's only host synchronisation
-  std::vector<MatchState> hs(S);
-  std::vector<int> nds(2 * S);
-  int flags[8];
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(nds.data(), d_nds, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
-  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->result_ready));
   CM_CUDA_CHECK(ctx, cudaGetLastError());
   if (sharded) {
     int derr = 0;
@@ -371,8 +384,8 @@ static int mapping_process_dev(cm_ctx* ctx, const float4* d_corner, int cap_c, c
         ctx->map.insert(0, (const float4*)ctx->m_corner_ds.p, d_nds, cap_c, std::min(cap_c, act_c), (const MatchState*)ctx->m_state.p, nullptr, st);
         ctx->map.insert(1, (const float4*)ctx->m_surf_ds.p, d_nds + S, cap_s, std::min(cap_s, act_s), (const MatchState*)ctx->m_state.p, nullptr, st);
       }
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, ctx->m_state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
+      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
       CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
       CM_CUDA_CHECK(ctx, cudaGetLastError());
     }
@@ -719,6 +732,21 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
         return (rc >= 0 && ctx->defer_rc < 0) ? ctx->defer_rc : rc;
       }
     }
+    // not prefetched: when a slot is free, the sweep takes the prefetch route all the same -- its upload and scan registration go
+    // to the copy / side streams, where they do not queue behind the previous step's map insertion (still running on
+    // ctx->stream when a synchronous caller comes back with the next sweep)
+    for (int i = 0; i < CM_PIPE_SLOTS; i++)
+      if (!ctx->pipe[i].src) {
+        const int prc = pipeline_prefetch(ctx, frames, rows, cols, is_host, clouds, stride);
+        if (prc != CM_OK) return prc;
+        cm_ctx::PipeSlot& ps = ctx->pipe[i];
+        CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ps.done, 0));
+        ctx->defer_rc = 0;
+        const int rc = pipeline_mapping(ctx, ps, rows, cols, odom, mapped, stats);
+        ps.src = nullptr;
+        issue_deferred_prefetch(ctx);
+        return (rc >= 0 && ctx->defer_rc < 0) ? ctx->defer_rc : rc;
+      }
     cm_ctx::PipeSlot& slot = ctx->pipe[CM_PIPE_SLOTS];
     const float4* d_frames = (const float4*)frames;
     if (clouds) {
@@ -1047,6 +1075,26 @@ int cm_pipeline_wait(cm_ctx* ctx) {
     if (ctx->pipe[i].src && ctx->pipe[i].done) CM_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->pipe[i].done));
   return CM_OK;
 }
+/* cm_mapping_process_* / cm_pipeline_step_* return when the poses are on the host; the map insertion they enqueued may still be
+ * running.  This waits for it and reports what it hit (capacity, voxel range) -- otherwise the next step reports it. */
+int cm_mapping_sync(cm_ctx* ctx) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    int flags[8];
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(flags, ctx->map.flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags[0] || flags[2] || flags[3]) {
+      cudaMemsetAsync(ctx->map.flags.p, 0, sizeof(int) * 8, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      if (flags[0]) return fail(ctx, CM_ERR_UNSUPPORTED, "map point outside the supported voxel range (+-65536 voxels)");
+      return fail(ctx, CM_ERR_CAPACITY, "map capacity exhausted (raise max_*_points in cm_mapping_create)");
+    }
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+  return CM_OK;
+}
 int cm_pipeline_discard(cm_ctx* ctx, const void* frames) {
   if (!ctx || !frames) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
@@ -1098,6 +1146,7 @@ int cm_debug_graph_builds(cm_ctx* ctx, unsigned long long* out4) {
 int cm_debug_read_slots(cm_ctx* ctx, int* out, size_t n_ints) {
   if (!ctx || !out) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   CM_CUDA_CHECK(ctx, cudaMemcpy(out, ctx->m_slots.p, std::min(n_ints * sizeof(int), ctx->m_slots.cap), cudaMemcpyDeviceToHost));
   return CM_OK;
 }
@@ -1105,6 +1154,7 @@ int cm_debug_read_queries(cm_ctx* ctx, int cls, float* out, size_t n_floats, int
   if (!ctx || !out || cls < 0 || cls > 1) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
   cm::DeviceBuffer& b = cls == 0 ? ctx->m_corner_ds : ctx->m_surf_ds;
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   CM_CUDA_CHECK(ctx, cudaMemcpy(out, b.p, std::min(n_floats * sizeof(float), b.cap), cudaMemcpyDeviceToHost));
   if (counts) CM_CUDA_CHECK(ctx, cudaMemcpy(counts, (const int*)ctx->m_n_ds.p + cls * ctx->map_streams, sizeof(int) * ctx->map_streams, cudaMemcpyDeviceToHost));
   return CM_OK;
@@ -1113,6 +1163,7 @@ int cm_debug_read_map_points(cm_ctx* ctx, int stream_index, int cls, const int* 
   if (!ctx || !slots || !out4 || cls < 0 || cls > 1 || stream_index < 0 || stream_index >= ctx->map_streams) return CM_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
   const float4* pool = (const float4*)ctx->map.pts[cls].p + (size_t)stream_index * ctx->map.pool_cap[cls];
+  CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; i++) {
     if (slots[i] < 0 || (unsigned int)slots[i] >= ctx->map.pool_cap[cls]) { out4[4 * i] = out4[4 * i + 1] = out4[4 * i + 2] = out4[4 * i + 3] = nanf(""); continue; }
     CM_CUDA_CHECK(ctx, cudaMemcpy(out4 + 4 * i, pool + slots[i], sizeof(float4), cudaMemcpyDeviceToHost));

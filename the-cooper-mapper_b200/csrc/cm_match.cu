@@ -164,6 +164,7 @@ struct CorrArgs {
   const int* iter_dev;                        // optional: the evaluation index lives in device memory (graph WHILE loop); hard_count is then the row base
   int iter;                                   // the evaluation index when iter_dev is NULL
   int warm;                                   // 1: warm-start the 5-NN lists from the previous iteration (COOPERMAP_NO_WARM=1: off)
+  int spread;                                 // search_kernel: a warp takes 32 >> spread queries (its first lanes), see search_spread()
   const int* skip;                            // optional: non-zero = do nothing (MatchLaunch::skip)
   int dist_rank, dist_nranks;                 // sharded map: only the queries whose map-frame cube this rank owns are evaluated
   void* hard; int* hard_count; int hard_cap;  // optional device-wide list of the queries that need levels >= 1 (this evaluation's counter)
@@ -340,13 +341,20 @@ __global__ void __launch_bounds__(CM_SEARCH_THREADS, CM_SEARCH_MINB) search_kern
   const unsigned int FULL = 0xffffffffu;
   // (the grid may be sized from an ESTIMATE of the filtered feature counts: the caller checks on the device that no stream
   // exceeded it and repeats the match otherwise -- a grid-stride loop here cost 25 % of the kernel in spills)
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((t & ~31) >= nT) return;   // whole warp idle
+  // a.spread > 0 (few queries in the whole launch): a warp takes only 32 >> spread consecutive query slots, in its first lanes --
+  // the per-thread pass is divergent (every lane walks its own cells), so a warp's instruction count grows with its active lanes;
+  // with most SMs idle anyway, thinner warps on more SMs finish sooner
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 32 >> a.spread;
+  const int t = (gt >> 5) * per + (gt & 31);
+  if ((gt >> 5) * per >= nT) return;   // whole warp idle
+  const bool lane_on = (gt & 31) < per;
   unsigned long long t0 = 0;
   if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   bool in_range, isCorner; int row;
   float sx, sy, sz;
-  bool valid = search_query(a, s, t, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
+  bool valid = search_query(a, s, lane_on ? t : nT + 32, sR, sT, &in_range, &isCorner, &row, &sx, &sy, &sz);
+  if (!lane_on) isCorner = (gt >> 5) * per < ((nC + 31) & ~31);   // (only picks the grid the idle lane's dummy geometry reads)
   const GridView& g = isCorner ? a.grid_corner[s] : a.grid_surf[s];
   Top5 best;
   top5_init(best);
@@ -410,14 +418,9 @@ __global__ void __launch_bounds__(256) search_hard_kernel(CorrArgs a) {
   if (a.skip && *a.skip) return;
   const int n = min(a.iter_dev ? a.hard_count[*a.iter_dev] : *a.hard_count, a.hard_cap);
   const int lane = threadIdx.x & 31;
-  // the warps take the queries one at a time off a shared cursor (the cost of a hard query varies by an order of magnitude with
-  // the number of shells it needs: a static split leaves most warps idle behind the few long ones)
-  int* cursor = (a.iter_dev ? a.hard_count + *a.iter_dev : a.hard_count) + CM_MAX_EVALS * 8;
-  for (;;) {
-    int i = 0;
-    if (lane == 0) i = atomicAdd(cursor, 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= n) break;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // (taking the queries off a shared cursor instead of this static split was measured: same kernel time, 9 % of the samples on the atomic)
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
     const HardItem* item = reinterpret_cast<const HardItem*>(a.hard) + i;
     const int s = item->s, t = item->t;
     const MatchState& st = a.state[s];
@@ -565,13 +568,6 @@ __global__ void __launch_bounds__(512) reduce_rows_kernel(SolveArgs a, double* _
 
 // The 6x6 routines are kept out of line on purpose: each gets its own small stack frame.  Inlined into one large
 // kernel body, nvcc 12.9 (sm_100a) produced a wrong 6x6 solve (see the note in cm_math.h::colpiv_qr_solve).
-__device__ __noinline__ void dev_qr_solve6(const float* A, const float* b, float* x) {
-  float Aw[36], bw[6], xw[6];
-  for (int k = 0; k < 36; k++) Aw[k] = A[k];
-  for (int k = 0; k < 6; k++) bw[k] = b[k];
-  colpiv_qr_solve<6, 6>(Aw, bw, xw);
-  for (int k = 0; k < 6; k++) x[k] = xw[k];
-}
 __device__ __noinline__ void dev_eig6_values(const float* A, float* w) {
   float Aw[36], ww[6];
   for (int k = 0; k < 36; k++) Aw[k] = A[k];
@@ -593,36 +589,174 @@ __device__ __noinline__ bool dev_inverse6(const float* A, float* inv) {
   return ok;
 }
 
-// K6b: solve, degeneracy projection, pose update, convergence (ScanMatch.cpp:134-260).  One thread per stream; the
-// 6x6 work goes through cm_math.h, i.e. the same instruction sequence as the oracle's.
+// Column-parallel form of cm_math.h::colpiv_qr_solve<6, 6> for one warp: the SAME float operations on the same operands in the same
+// order as the sequential routine the oracle runs (every dot product and norm is still summed row by row inside one lane; -fmad=false),
+// only spread over the lanes: lane c < 6 holds column c of A in a[0..5], lane 6 holds b (the reflectors are applied to it as to a
+// seventh trailing column, step by step, instead of in a second sweep), the other lanes carry zeros.  The pivot scan, the reflector
+// of column k and the back substitution are evaluated redundantly by every lane from shuffled values, so the control flow is
+// uniform.  One lane running the unrolled sequential routine took 35 us per Gauss-Newton iteration (~5,000 dependent instructions,
+// 80 KB of straight-line code fetched once); this form is ~7x shorter.  Every lane returns the whole solution X.
+__device__ __forceinline__ void warp_qr_solve6(float (&a)[6], const int lane, float (&X)[6]) {
+  const unsigned int FULL = 0xffffffffu;
+  float nu, nd;
+  int perm = lane;
+  {
+    float sq = 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) sq += a[r] * a[r];
+    nd = sqrtf(sq); nu = nd;
+  }
+  float maxnorm = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const float v = __shfl_sync(FULL, nu, k); if (v > maxnorm) maxnorm = v; }
+  const float te = maxnorm * FLT_EPSILON;
+  const float threshold_helper = (te * te) / 6.0f;
+  const float norm_downdate_threshold = sqrtf(FLT_EPSILON);
+  int nzp = 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    int big = k;
+    float bigv = __shfl_sync(FULL, nu, k);
+#pragma unroll
+    for (int j = k + 1; j < 6; ++j) { const float v = __shfl_sync(FULL, nu, j); if (v > bigv) { bigv = v; big = j; } }
+    const float big_sq = bigv * bigv;
+    if (nzp == 6 && big_sq < threshold_helper * (float)(6 - k)) nzp = k;
+    {   // column swap k <-> big (whole columns, with their norms and permutation entry)
+      const int src = lane == k ? big : (lane == big ? k : lane);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) a[r] = __shfl_sync(FULL, a[r], src);
+      nu = __shfl_sync(FULL, nu, src); nd = __shfl_sync(FULL, nd, src); perm = __shfl_sync(FULL, perm, src);
+    }
+    // Householder reflector of column k, rows k..5
+    float ck[6], v[6];
+#pragma unroll
+    for (int r = k; r < 6; ++r) ck[r] = __shfl_sync(FULL, a[r], k);
+    float tailSqNorm = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < 6; ++r) tailSqNorm += ck[r] * ck[r];
+    const float c0 = ck[k];
+    float tau, beta;
+    if (k == 5 || tailSqNorm <= FLT_MIN) {
+      tau = 0.f; beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) v[r] = 0.f;
+    } else {
+      float bb = sqrtf(c0 * c0 + tailSqNorm);
+      if (c0 >= 0.f) bb = -bb;
+      const float d = c0 - bb;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) v[r] = ck[r] / d;
+      tau = (bb - c0) / bb;
+      beta = bb;
+    }
+    if (lane == k) {
+      a[k] = beta;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) a[r] = v[r];
+    }
+    // H_k on the trailing columns and on b (b only while k < nonzero_pivots: colpiv_qr_solve's second sweep stops there)
+    if ((lane > k && lane < 6) || (lane == 6 && k < nzp)) {
+      float tmp = a[k];
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) tmp += v[r] * a[r];
+      a[k] -= tau * tmp;
+#pragma unroll
+      for (int r = k + 1; r < 6; ++r) a[r] -= tau * v[r] * tmp;
+    }
+    if (lane > k && lane < 6 && nu != 0.f) {   // LAPACK-style norm downdate
+      float temp = fabsf(a[k]) / nu;
+      temp = (1.f + temp) * (1.f - temp);
+      temp = temp < 0.f ? 0.f : temp;
+      const float ratio = nu / nd;
+      const float temp2 = temp * (ratio * ratio);
+      if (temp2 <= norm_downdate_threshold) {
+        float sq = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) sq += a[r] * a[r];
+        nd = sqrtf(sq); nu = nd;
+      } else {
+        nu *= sqrtf(temp);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) X[i] = 0.f;
+  if (nzp == 0) return;
+  float bq[6], Rm[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    bq[i] = __shfl_sync(FULL, a[i], 6);
+#pragma unroll
+    for (int j = i; j < 6; ++j) Rm[i][j] = __shfl_sync(FULL, a[i], j);
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (i < nzp) {
+      float sb = bq[i];
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j)
+        if (j < nzp) sb -= Rm[i][j] * bq[j];
+      bq[i] = sb / Rm[i][i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int pi = __shfl_sync(FULL, perm, i);
+    if (i < nzp) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (pi == c) X[c] = bq[i];
+    }
+  }
+}
+
+// K6b: solve, degeneracy projection, pose update, convergence (ScanMatch.cpp:134-260).  One WARP per stream: the 6x6 solve is
+// column-parallel (warp_qr_solve6), the rest is lane 0's; the 6x6 eigen work goes through cm_math.h, i.e. the same instruction
+// sequence as the oracle's.
 __device__ __noinline__ void solve_stream(const SolveArgs& a_in, int s, const double* tot) {
+  const unsigned int FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   SolveArgs a = a_in;
   if (a.iter_dev) a.iter = *a.iter_dev;
   MatchState& st = a.state[s];
-  if (st.done) return;
-  const int nrows = (int)tot[27];
-  const int nline = (int)tot[28], nplane = (int)tot[29];
-  st.rows = nrows; st.line = nline; st.plane = nplane; st.score = tot[30];
   IterTrace* tr = a.trace ? a.trace + (size_t)s * a.prm.max_iterations + a.iter : nullptr;
-  if (tr) {
-    for (int k = 0; k < 6; k++) tr->pose_in[k] = st.pose[k];
-    tr->rows = nrows; tr->line = nline; tr->plane = nplane; tr->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
-    for (int k = 0; k < 36; k++) tr->AtA[k] = 0.f;
-    for (int k = 0; k < 6; k++) { tr->AtB[k] = 0.f; tr->x[k] = 0.f; }
+  int go = 0;
+  if (lane == 0 && !st.done) {
+    const int nrows = (int)tot[27];
+    const int nline = (int)tot[28], nplane = (int)tot[29];
+    st.rows = nrows; st.line = nline; st.plane = nplane; st.score = tot[30];
+    if (tr) {
+      for (int k = 0; k < 6; k++) tr->pose_in[k] = st.pose[k];
+      tr->rows = nrows; tr->line = nline; tr->plane = nplane; tr->degenerate = (st.flags & CM_F_DEGENERATE) ? 1 : 0;
+      for (int k = 0; k < 36; k++) tr->AtA[k] = 0.f;
+      for (int k = 0; k < 6; k++) { tr->AtB[k] = 0.f; tr->x[k] = 0.f; }
+    }
+    if (nrows >= a.prm.min_rows) go = 1;
+    else if (!a.prm.few_rows_continue) { st.flags |= CM_F_TOO_FEW_MATCHES; st.done = 1; }   // ScanMatch.cpp:141-145: leave the loop
+    // (few_rows_continue, LaserOdometry.cpp:501-503: skip this iteration)
   }
-  if (nrows < a.prm.min_rows) {
-    if (a.prm.few_rows_continue) return;                 // LaserOdometry.cpp:501-503: skip this iteration
-    st.flags |= CM_F_TOO_FEW_MATCHES; st.done = 1;       // ScanMatch.cpp:141-145: leave the loop
-    return;
-  }
-  float AtA[36], AtB[6], X[6];
+  go = __shfl_sync(FULL, go, 0);
+  if (!go) return;
+  float X[6];
   {
+    // lane c < 6: column c of A^T A (symmetric: element (r, c) is entry (min, max) of the upper triangle in tot[0..21)); lane 6: A^T b
+    float col[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const int lo = r < lane ? r : lane, hi = r < lane ? lane : r;
+      const int t = lane < 6 ? lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo) : 21 + r;
+      col[r] = lane < 7 ? (float)tot[t] : 0.f;
+    }
+    warp_qr_solve6(col, lane, X);   // ScanMatch.cpp:209
+  }
+  if (lane != 0) return;
+  float AtA[36], AtB[6];
+  if (a.iter == 0 || tr) {
     int t = 0;
     for (int r = 0; r < 6; r++)
       for (int c = r; c < 6; c++) { float v = (float)tot[t++]; AtA[r * 6 + c] = v; AtA[c * 6 + r] = v; }
     for (int r = 0; r < 6; r++) AtB[r] = (float)tot[21 + r];
   }
-  dev_qr_solve6(AtA, AtB, X);   // ScanMatch.cpp:209
   if (a.iter == 0) {   // ScanMatch.cpp:211-235
     float E[6];
     dev_eig6_values(AtA, E);
@@ -671,12 +805,6 @@ __device__ __noinline__ void solve_stream(const SolveArgs& a_in, int s, const do
   double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
   float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
   if (deltaR < a.prm.delta_r_abort && deltaT < a.prm.delta_t_abort) { st.flags |= CM_F_CONVERGED; st.done = 1; }
-}
-
-__global__ void solve_kernel(SolveArgs a, const double* __restrict__ sums, int nstreams) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nstreams) return;
-  solve_stream(a, s, sums + (size_t)s * 32);
 }
 
 // K5b + K6 in one launch: fit_kernel's rows are reduced inside the CTA (double, fixed order), the per-CTA partial sums
@@ -777,10 +905,10 @@ __global__ void __launch_bounds__(256, CM_FIT_MINB) fit_solve_kernel(CorrArgs a,
   }
 }
 
-// K6b for the fused path: one warp per stream (streams diverge: degenerate / first-iteration branches), lane 0 works
+// K6b: one warp per stream
 __global__ void __launch_bounds__(32) solve_warp_kernel(SolveArgs a, const double* __restrict__ sums) {
   if (a.skip && *a.skip) return;
-  if (threadIdx.x == 0) solve_stream(a, blockIdx.x, sums + (size_t)blockIdx.x * 32);
+  solve_stream(a, blockIdx.x, sums + (size_t)blockIdx.x * 32);
 }
 
 #include "cm_odom.inl"
@@ -849,14 +977,14 @@ static void fill_args(const MatchLaunch& m, CorrArgs& ca, SolveArgs& sa) {
   ca.state = m.state; ca.rows = m.rows; ca.nn_slot = m.nn_slot; ca.nn = nullptr; ca.own_box = m.own_box; ca.prm = m.prm;
   ca.hard = m.hard; ca.hard_count = m.hard_count; ca.hard_cap = m.hard_cap; ca.dbg = nullptr; ca.iter_dev = nullptr; sa.iter_dev = nullptr;
   static const int warm = getenv("COOPERMAP_NO_WARM") ? 0 : 1;
-  ca.iter = 0; ca.warm = warm; ca.skip = m.skip; sa.skip = m.skip;
+  ca.iter = 0; ca.warm = warm; ca.spread = 0; ca.skip = m.skip; sa.skip = m.skip;
   ca.dist_rank = m.dist_rank; ca.dist_nranks = m.dist_nranks;
   sa.rows = m.rows; sa.n_corner = m.n_corner; sa.n_surf = m.n_surf; sa.cap_corner = m.cap_corner; sa.cap_surf = m.cap_surf;
   sa.state = m.state; sa.trace = m.trace; sa.prm = m.prm; sa.iter = 0;
 }
 
 void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
-  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS * 8 * 2, stream);   // counters + cursors
+  if (m.hard) cudaMemsetAsync(m.hard_count, 0, sizeof(int) * CM_MAX_EVALS * 8, stream);
   if (m.tickets) cudaMemsetAsync(m.tickets, 0, sizeof(int) * m.nstreams, stream);
   CM_LAUNCH(match_init_kernel, (m.nstreams + 63) / 64, 64, 0, stream, m.state, m.pose_in, m.grid_corner, m.grid_surf, m.prm, m.nstreams);
 }
@@ -867,6 +995,20 @@ void launch_match_init(const MatchLaunch& m, cudaStream_t stream) {
 static int hard_blocks_default() {
   static const int n = []() { const char* e = getenv("COOPERMAP_HARD_BLOCKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 444; }();
   return n;
+}
+
+// search_kernel's spread for a launch of `threads` query slots in all: thin the warps out while the launch leaves SM sub-partitions
+// without a warp of their own (B200: 148 SMs x 4)
+static int search_spread(long long threads) {
+  static const int forced = getenv("COOPERMAP_SEARCH_SPREAD") ? atoi(getenv("COOPERMAP_SEARCH_SPREAD")) : -1;
+  if (forced >= 0) return forced > 3 ? 3 : forced;
+  const long long warps = threads / 32;
+  if (warps * 4 <= 148 * 4 * 2) return 2;
+  if (warps * 2 <= 148 * 4 * 2) return 1;
+  return 0;
+}
+static dim3 search_grid(int bx, int nstreams, int spread) {
+  return dim3((unsigned int)((((long long)bx * 256) << spread) + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, nstreams);
 }
 
 void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, KernelProfiler* prof, bool fused, bool defer_solve) {
@@ -882,7 +1024,8 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
   if (m.dbg && it == m.dbg_iter) { ca.dbg = m.dbg; cudaMemsetAsync(m.dbg, 0, (size_t)bx * m.nstreams * 8 * 4 * sizeof(unsigned long long), stream);   /* bx * 8 warps per stream */ }
   if (it >= CM_MAX_EVALS) ca.hard = nullptr;       // no counter left: finish hard queries inside their own warp
   if (ca.hard) ca.hard_count = m.hard_count + it;  // one counter per evaluation, zeroed by launch_match_init
-  dim3 sgrid((bx * 256 + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, m.nstreams);
+  ca.spread = m.dbg ? 0 : search_spread((long long)bx * 256 * m.nstreams);   // (the search trace is laid out for whole warps)
+  const dim3 sgrid = search_grid(bx, m.nstreams, ca.spread);
   if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   if (ca.hard) {
@@ -922,7 +1065,7 @@ void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaSt
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
   sa.iter = it;
-  CM_LAUNCH(solve_kernel, (m.nstreams + 31) / 32, 32, 0, stream, sa, sums, m.nstreams);
+  CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, sums);
 }
 
 void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
@@ -1002,7 +1145,8 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   int bx = ((m.max_queries > 0 ? m.max_queries : capQ) + 32 + 255) / 256;
   if (bx < 1) bx = 1;
   dim3 grid(bx, m.nstreams);
-  dim3 sgrid((bx * 256 + CM_SEARCH_THREADS - 1) / CM_SEARCH_THREADS, m.nstreams);
+  ca.spread = search_spread((long long)bx * 256 * m.nstreams);
+  const dim3 sgrid = search_grid(bx, m.nstreams, ca.spread);
   if (m.orig_idx) CM_LAUNCH(search_kernel<true>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   else CM_LAUNCH(search_kernel<false>, sgrid, CM_SEARCH_THREADS, 0, stream, ca);
   const int hb = m.hard_blocks > 0 ? m.hard_blocks : hard_blocks_default();
