@@ -411,15 +411,21 @@ __global__ void map_clear_kernel(CellEntry* e, unsigned int* cellcap, unsigned i
 
 // searchable size of the surround map (sum of the valid cubes) -> GridView.npts, and the rest of the view.
 // One warp per stream.
-__global__ void map_view_kernel(MapClassDev* maps, const CubeWindow* windows, GridView* views, int nstreams, float gate, int shard_rank,
-                                int shard_nranks) {
+__global__ void map_view_kernel(MapClassDev* maps, MapClassDev* maps1, const CubeWindow* windows, GridView* views, GridView* views1, int nstreams,
+                                float gate, int shard_rank, int shard_nranks) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nstreams) return;
+  if (blockIdx.y) { maps = maps1; views = views1; }   // both classes in one launch
   MapClassDev& m = maps[s];
   const CubeWindow& w = windows[s];
   int total = 0;
-  for (int a = lane; a < 343; a += 32) {
-    if (!w.active[a]) continue;
+  unsigned char act[11];
+#pragma unroll
+  for (int u = 0; u < 11; u++) { const int a = lane + 32 * u; act[u] = a < 343 ? w.active[a] : 0; }   // independent loads, then the counts
+#pragma unroll
+  for (int u = 0; u < 11; u++) {
+    const int a = lane + 32 * u;
+    if (!act[u]) continue;
     int i = a / 49 + w.w0[0], j = (a / 7) % 7 + w.w0[1], k = a % 7 + w.w0[2];
     if (shard_nranks > 1 && cube_owner(i, j, k, shard_nranks) != shard_rank) continue;   // halo copies are counted by their owner
     total += m.cube_count[i + j * m.dims[0] + k * m.dims[0] * m.dims[1]];
@@ -540,9 +546,8 @@ void DeviceMap::set_windows(const CubeWindow* h_windows, float gate, cudaStream_
   if (!h_windows) {}
   else if (staged) staged_upload(windows.p, h_windows, sizeof(CubeWindow) * nstreams, stream);
   else cudaMemcpyAsync(windows.p, h_windows, sizeof(CubeWindow) * nstreams, cudaMemcpyHostToDevice, stream);
-  for (int cls = 0; cls < 2; cls++)
-    CM_LAUNCH(map_view_kernel, (nstreams * 32 + 127) / 128, 128, 0, stream, (MapClassDev*)dev[cls].p, (const CubeWindow*)windows.p,
-              (GridView*)views[cls].p, nstreams, gate, shard_rank, shard_nranks);
+  CM_LAUNCH(map_view_kernel, dim3((nstreams * 32 + 127) / 128, 2), 128, 0, stream, (MapClassDev*)dev[0].p, (MapClassDev*)dev[1].p,
+            (const CubeWindow*)windows.p, (GridView*)views[0].p, (GridView*)views[1].p, nstreams, gate, shard_rank, shard_nranks);
 }
 
 __global__ void map_npts_pack_kernel(const GridView* vc, const GridView* vs, int nstreams, double* vec) {

@@ -620,6 +620,19 @@ static int pipeline_mapping(cm_ctx* ctx, cm_ctx::PipeSlot& slot, int rows, int c
   // feature-cloud sizes: upper bounds for the scratch of the frame voxel filters (and the byte accounting)
   std::vector<int> n5v;
   const int* n5;
+  if (slot.counts_ready && (size_t)S * cap <= ((size_t)4 << 20) && cudaEventQuery(slot.done) != cudaSuccess) {
+    // A synchronous caller with a small batch (the latency case): scan registration is still running.  The feature counts only
+    // size scratch memory and bound the launch estimates, so the step is enqueued behind it with the capacity as the bound instead
+    // of waiting for the counts on the host (~15 us of idle GPU per sweep); the counters are filled in once the step is through.
+    slot.counts_ready = false;
+    const int rc = mapping_process_dev(ctx, (const float4*)slot.pts[1].p, cap, (const float4*)slot.pts[3].p, cap, (const int*)slot.n.p, cap,
+                                       cap, odom, mapped, stats, false);
+    CM_CUDA_CHECK(ctx, cudaEventSynchronize(slot.done));   // (complete: the step waited for it on the device)
+    ctx->last_features = 0;
+    for (int s = 0; s < S; s++)
+      for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)slot.h_n5[s * 5 + k];
+    return rc;
+  }
   if (slot.counts_ready) {
     // read back by the prefetch on the side stream: normally complete long before the step starts
     CM_CUDA_CHECK(ctx, cudaEventSynchronize(slot.done));
