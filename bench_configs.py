@@ -252,6 +252,26 @@ def run_config1(args, synth, rank, world, local_rank):
         tg.append(time.perf_counter() - t0)
     launches = c_sr.launch_count() - l0
     warm = max(3, args.warmup)
+    rate3 = 28800 / float(np.mean(tg[warm:]))
+    three_calls = {"value": rate3, "unit": "points/s", "p50_ms": 1e3 * float(np.median(tg[warm:])),
+                   "note": "cm_scanreg_organised_host + cm_odometry_process_host + cm_mapping_process_host: every feature cloud crosses PCIe twice"}
+    # the call a user makes: the three stages in one (cm_pipeline_chain_step_host), the clouds stay on the device
+    import torch
+    c1 = cmb.Context(device=local_rank, **cfg)
+    c1.mapping_create(1, 100000, 800000)
+    c1.pipeline_chain_create(16, 1800)
+    od1 = np.empty((1, 12), np.float32); mp1 = np.empty((1, 12), np.float32)
+    ost1 = (cmb.OdomStats * 1)(); mst1 = (cmb.MatchStats * 1)()
+    pin1 = [torch.from_numpy(np.ascontiguousarray(frames[k][None].astype(np.float32))).pin_memory().numpy() for k in range(NF)]
+    tg = []
+    l0 = c1.launch_count()
+    for k in range(NF):
+        t0 = time.perf_counter()
+        c1.pipeline_chain_step_packed(pin1[k], od1, mp1, ost1, mst1)
+        tg.append(time.perf_counter() - t0)
+    c1.mapping_sync()
+    launches = c1.launch_count() - l0
+    c1.close()
     rate = 28800 / float(np.mean(tg[warm:]))
     # the same three-stage chain BATCHED over S independent streams (stream s starts s frames into the sequence): one launch set
     # per stage for all streams (cm_scanreg_organised_host, cm_odometry_batch_process_host, cm_mapping_process_host)
@@ -274,9 +294,27 @@ def run_config1(args, synth, rank, world, local_rank):
                "note": "scan registration -> batched odometry -> mapping for all streams per call, through host buffers and the ctypes layer "
                        "(feature clouds cross PCIe between the stages; the Python marshalling of the clouds is inside the time)"}
     cb.close()
+    # the same batch through cm_pipeline_chain_step_host: ONE call per sweep set, the clouds stay on the device between the stages
+    import torch
+    cc = cmb.Context(device=local_rank, **cfg)
+    cc.mapping_create(SB, 100000, 800000)
+    cc.pipeline_chain_create(16, 1800)
+    od_o = np.empty((SB, 12), np.float32); mp_o = np.empty((SB, 12), np.float32)
+    ost = (cmb.OdomStats * SB)(); mst = (cmb.MatchStats * SB)()
+    pinned = [torch.from_numpy(np.ascontiguousarray(fstack[[(k + s) % NF if (k + s) < NF else NF - 1 for s in range(SB)]])).pin_memory().numpy()
+              for k in range(NB)]
+    tcn = []
+    for k in range(NB):
+        t0 = time.perf_counter()
+        cc.pipeline_chain_step_packed(pinned[k], od_o, mp_o, ost, mst)
+        tcn.append(time.perf_counter() - t0)
+    cc.mapping_sync()
+    batched["device_chain"] = {"value": SB * 28800 / float(np.mean(tcn[warm:])), "unit": "points/s", "ms_per_step": 1e3 * float(np.mean(tcn[warm:])),
+                               "note": "cm_pipeline_chain_step_host: pinned sweeps in, two poses per stream out, feature clouds never leave the device"}
+    cc.close()
     line = _line(args, 1, rate, 1e3 * float(np.mean(tg[warm:])), "weak",
-                 "config 1: VLP-16 16x1800 sequence, ONE stream, scan registration -> laserOdometry -> laserMapping through the host-buffer C ABI (every sweep crosses PCIe)",
-                 dict(frames=NF, points_per_sweep=28800, p50_ms=1e3 * float(np.median(tg[warm:])), streams=1, batched=batched,
+                 "config 1: VLP-16 16x1800 sequence, ONE stream, scan registration -> laserOdometry -> laserMapping in one call per sweep (cm_pipeline_chain_step_host: host sweep in, two poses out)",
+                 dict(frames=NF, points_per_sweep=28800, p50_ms=1e3 * float(np.median(tg[warm:])), streams=1, three_calls=three_calls, batched=batched,
                       note="single stream: latency-bound by construction (three stages, ~35 dependent kernel rounds per sweep); throughput configs are 2 and 3"),
                  gpu_launches=int(launches))
     line["steps"] = NF - warm; line["warmup"] = warm

@@ -323,6 +323,20 @@ int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int
                                    const cm_point* flat, const int* n_flat, const cm_point* less_flat, const int* n_less_flat, cm_iso* odom,
                                    cm_pose* transform, cm_point* corner_last, cm_point* surf_last, cm_odom_stats* stats);
 
+/* The whole LOAM chain for one organised sweep per stream in ONE call: scan registration (MultiScanRegistration /
+ * OrganizedScanRegistration) -> LaserOdometry::process (LaserOdometry.cpp:288-326) -> LaserMapping::process (LaserMapping.cpp:39-59).
+ * What the three nodelets pass over ROS topics -- /laser_cloud_sharp, /laser_cloud_less_sharp, /laser_cloud_flat,
+ * /laser_cloud_less_flat into the odometry; /laser_cloud_corner_last, /laser_cloud_surf_last and /laser_odom_to_init into the
+ * mapping -- stays in device memory; the host gets /laser_odom_to_init (odom[s]) and /aft_mapped_to_init (mapped[s]).  Results are
+ * those of cm_scanreg_organised_host + cm_odometry_batch_process_host + cm_mapping_process_host called one after the other.
+ * cm_pipeline_chain_create (after cm_mapping_create) sizes the odometry stage for rows x cols sweeps; a sweep announced with
+ * cm_pipeline_prefetch_host is taken from there. */
+int cm_pipeline_chain_create(cm_ctx* ctx, int rows, int cols);
+int cm_pipeline_chain_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, cm_iso* odom, cm_iso* mapped, cm_odom_stats* ostats,
+                                cm_match_stats* mstats);
+int cm_pipeline_chain_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, cm_iso* odom, cm_iso* mapped, cm_odom_stats* ostats,
+                               cm_match_stats* mstats);
+
 
 /* ---- sharded-map matching (BASELINE config 4: one map split over ranks) ---------------------------------------------------
  * ScanMatch::scanMatchScan with the reference clouds partitioned in space: rank r holds the map points of its region plus a

@@ -176,6 +176,35 @@ def test_config1_vlp16_full_chain(cmb, oracle, synth):
         c.close()
 
 
+def test_chain_step_equals_the_three_stages(cmb, oracle, synth):
+    """cm_pipeline_chain_step_host: the three stages in one call, feature clouds and projected clouds staying on the device, for two
+    streams at once -- the poses of every sweep and the final maps are those of the oracle's chain (scan registration -> odometry ->
+    mapping), stream by stream."""
+    sc = synth.make_scene(seed=0x5EED0001 & 0xFFFF, extent=60.0, n_boxes=24, n_poles=20)
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    S, NF = 2, 12
+    ctx = cmb.Context(**cfg)
+    ctx.mapping_create(S, 100000, 800000)
+    ctx.pipeline_chain_create(16, 1800)
+    oos = [oracle.Odometry() for _ in range(S)]
+    oms = [oracle.Mapping(map_params=dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4)) for _ in range(S)]
+    trajs = [synth.trajectory(NF, speed=0.1, yaw_amp=0.02), synth.trajectory(NF, speed=0.07, yaw_amp=-0.03)]
+    for k in range(NF):
+        fr = np.stack([synth.simulate_scan(sc, trajs[s][k][0], trajs[s][k][1], "VLP-16", seed=0x2000 + 50 * s + k) for s in range(S)])
+        odoms, isos, ostats, stats = ctx.pipeline_chain_step(fr)
+        for s in range(S):
+            o = oracle.scanreg_organised(fr[s])
+            oo_ = oos[s].process(o["sharp"], o["lessSharp"], o["flat"], o["lessFlat"])
+            assert np.array_equal(odoms[s][0], oo_["R"]) and np.array_equal(odoms[s][1], oo_["t"]), (k, s)
+            oR, ot, ost = oms[s].process(oo_["R"], oo_["t"], oo_["corner_last"], oo_["surf_last"])
+            assert stats[s]["iterations"] == ost["iterations"], (k, s)
+            assert np.array_equal(isos[s][0], oR) and np.array_equal(isos[s][1], ot), (k, s)
+    for s in range(S):
+        for cls, which in ((0, 4), (1, 5)):
+            assert _same(ctx.map_export_sorted(s, cls)[0], oms[s].cloud(which))
+    ctx.close()
+
+
 def test_knn5_full_size_vs_nanoflann(cmb, oracle, synth):
     """Exact 5-NN at the headline size: the ~1M-point surf map of the bench workload, 20,000 queries, against the reference's
     own KD-tree (nanoflann) -- neighbour sets and float distances identical, both map cell sizes (surf and corner default)."""

@@ -8,4 +8,4 @@ Import with importlib (the directory name carries a hyphen):
     cmb = importlib.import_module("the-cooper-mapper_b200")
 """
 from .api import (CM_OK, CM_TOO_FEW_REF, CM_TOO_FEW_MATCHES, CM_NOT_CONVERGED, CM_LOW_SCORE, Config, Context,  # noqa: F401
-                  CoopermapError, LaserLocalization, LaserMapping, LaserMappingLocal, LaserOdometry, MatchStats, ScanMatch, lib_path, load_library)
+                  CoopermapError, LaserLocalization, LaserMapping, LaserMappingLocal, LaserOdometry, MatchStats, OdomStats, ScanMatch, lib_path, load_library)

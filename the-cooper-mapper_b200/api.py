@@ -412,6 +412,29 @@ class Context:
                             matched=bool(st[s].matched), initialising=bool(st[s].initialising), converged=bool(st[s].converged)))
         return out
 
+    def pipeline_chain_create(self, rows, cols):
+        """size the odometry stage of the three-stage chain for rows x cols sweeps (after mapping_create)"""
+        self._check(self.L.cm_pipeline_chain_create(self.h, C.c_int(rows), C.c_int(cols)))
+
+    def pipeline_chain_step(self, frames):
+        """scan registration -> laserOdometry -> laserMapping for one organised sweep per stream, frames (S, rows, cols, 4);
+        returns (odometry poses, mapped poses, odometry stats, mapping stats)"""
+        fr = _f32(frames)
+        S, rows, cols = fr.shape[:3]
+        od = np.empty((S, 12), np.float32); mapped = np.empty((S, 12), np.float32)
+        ost = (OdomStats * S)(); mst = (MatchStats * S)()
+        self._check(self.L.cm_pipeline_chain_step_host(self.h, _ptr(fr), C.c_int(rows), C.c_int(cols), _ptr(od), _ptr(mapped), ost, mst))
+        isos, stats = self._unpack_results(mapped, mst)
+        odoms = [(od[s, :9].reshape(3, 3).copy(), od[s, 9:].copy()) for s in range(S)]
+        ostats = [dict(iterations=ost[s].iterations, rows=ost[s].rows, matched=bool(ost[s].matched), initialising=bool(ost[s].initialising),
+                       converged=bool(ost[s].converged)) for s in range(S)]
+        return odoms, isos, ostats, stats
+
+    def pipeline_chain_step_packed(self, frames, odom_out, mapped_out, ostats_out, mstats_out):
+        fr = frames
+        return self._check(self.L.cm_pipeline_chain_step_host(self.h, _ptr(fr), C.c_int(fr.shape[1]), C.c_int(fr.shape[2]), _ptr(odom_out),
+                                                              _ptr(mapped_out), ostats_out, mstats_out))
+
     # ---- measurement helpers -------------------------------------------------------------------------------------
     def timer_record(self, which):
         self._check(self.L.cm_timer_record(self.h, C.c_int(which)))

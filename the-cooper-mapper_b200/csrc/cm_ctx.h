@@ -113,6 +113,7 @@ struct cm_ctx {
   cm::MatchLaunch shard; size_t shard_nq = 0; bool shard_ready = false;
   cm::DeviceBuffer d_box;
   cm::OdomBatch obatch;                // cm_odometry_batch_*
+  int chain_rows = 0, chain_cols = 0;  // cm_pipeline_chain_create: the sweep shape the odometry batch was sized for
   cm::LocalWindow local;               // cm_mapping_local_*
   std::vector<cm::PageState> pages;    // cm_map_page_* (one per stream)
   cm::DeviceBuffer d_drop;
@@ -169,6 +170,10 @@ void fill_match_stats(const cm_config& cfg, const MatchState& st, size_t nq, cm_
 int dist_allreduce(cm_ctx* ctx, double* d_vec, int n, cudaStream_t stream);   // in-place sum over the ranks (cm_dist.cu)
 void dist_destroy(cm_ctx* ctx);
 void stage_pool_destroy(cm_ctx* ctx);
+int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, const int* n_sharp, const void* less_sharp, size_t pitch_less_sharp,
+                        const int* n_less_sharp, const void* flat, size_t pitch_flat, const int* n_flat, const void* less_flat,
+                        size_t pitch_less_flat, const int* n_less_flat, cm_iso* odom, cm_pose* transform, cm_point* corner_last,
+                        cm_point* surf_last, cm_odom_stats* stats);   // cm_odometry.cu
 int stage_upload_strided(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const void* const* clouds, size_t stride, int rows, int cols, cudaStream_t consumer);
 }  // namespace cm
 

@@ -787,6 +787,80 @@ static int pipeline_step(cm_ctx* ctx, const void* frames, int rows, int cols, bo
   }
 }
 
+// ---- the whole LOAM chain for one sweep per stream: scan registration -> laserOdometry -> laserMapping, clouds never leave the device --
+// What the three nodelets exchange over ROS topics in the reference (/laser_cloud_sharp, _less_sharp, _flat, _less_flat into
+// LaserOdometry; /laser_cloud_corner_last, /laser_cloud_surf_last and /laser_odom_to_init into LaserMapping) stays in device memory:
+// the odometry batch reads the four clouds scan registration left in the slot, the mapping stage reads the clouds the odometry
+// projected to the sweep end.  The host sees the feature counts (they size the launches) and the two poses per stream.
+static int pipeline_chain_step(cm_ctx* ctx, const void* frames, int rows, int cols, bool is_host, cm_iso* odom, cm_iso* mapped,
+                               cm_odom_stats* ostats, cm_match_stats* mstats) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  OdomBatch& b = ctx->obatch;
+  if (b.S != ctx->map_streams || ctx->chain_rows != rows || ctx->chain_cols != cols)
+    return fail(ctx, CM_ERR_ARG, "cm_pipeline_chain_create has not been called for this sweep shape");
+  if (!frames || rows <= 0 || cols <= 0) return fail(ctx, CM_ERR_ARG, "bad argument");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    const int S = ctx->map_streams, cap = rows * cols;
+    int si = -1;
+    for (int i = 0; i < CM_PIPE_SLOTS; i++) {
+      const cm_ctx::PipeSlot& ps = ctx->pipe[i];
+      if (ps.src == frames && ps.rows == rows && ps.cols == cols && ps.is_host == is_host) { si = i; break; }
+    }
+    if (si < 0) {
+      const int prc = pipeline_prefetch(ctx, frames, rows, cols, is_host, nullptr, 0);
+      if (prc != CM_OK) return prc;
+      for (int i = 0; i < CM_PIPE_SLOTS; i++) if (ctx->pipe[i].src == frames) { si = i; break; }
+    }
+    cm_ctx::PipeSlot& slot = ctx->pipe[si];
+    CM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, slot.done, 0));
+    CM_CUDA_CHECK(ctx, cudaEventSynchronize(slot.done));   // the feature counts (read back by the prefetch)
+    slot.counts_ready = false;
+    std::vector<int> n4((size_t)4 * S);
+    ctx->last_features = 0;
+    for (int s = 0; s < S; s++)
+      for (int k = 0; k < 4; k++) { n4[(size_t)k * S + s] = slot.h_n5[s * 5 + k]; ctx->last_features += (unsigned long long)slot.h_n5[s * 5 + k]; }
+    for (int s = 0; s < S; s++)
+      if (n4[s] > b.cap_sharp || n4[S + s] > b.cap_less_sharp || n4[2 * S + s] > b.cap_flat || n4[3 * S + s] > b.cap_less_flat)
+        return fail(ctx, CM_ERR_CAPACITY, "a feature cloud exceeds the chain's capacity");
+    const size_t pitch = (size_t)cap * sizeof(cm_point);
+    std::vector<cm_iso> od(S);
+    int rc = odometry_batch_core(ctx, slot.pts[0].p, pitch, &n4[0], slot.pts[1].p, pitch, &n4[S], slot.pts[2].p, pitch, &n4[2 * S], slot.pts[3].p,
+                                 pitch, &n4[3 * S], od.data(), nullptr, nullptr, nullptr, ostats);
+    slot.src = nullptr;   // the odometry stage has copied what it keeps: the slot is free for the next sweep
+    if (rc != CM_OK) return rc;
+    if (odom) memcpy(odom, od.data(), sizeof(cm_iso) * S);
+    int max_ls = 1, max_lf = 1;
+    for (int s = 0; s < S; s++) { max_ls = std::max(max_ls, n4[S + s]); max_lf = std::max(max_lf, n4[3 * S + s]); }
+    // the counts of the projected clouds sit in the odometry batch's integer block: rows 5 and 6 = [2][S], the layout the mapping stage reads
+    return mapping_process_dev(ctx, (const float4*)b.last_c.p, b.cap_less_sharp, (const float4*)b.last_s.p, b.cap_less_flat,
+                               (const int*)b.ints.p + 5 * S, max_ls, max_lf, od.data(), mapped, mstats, false);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+int cm_pipeline_chain_create(cm_ctx* ctx, int rows, int cols) {
+  if (!ctx || ctx->map_streams <= 0) return fail(ctx, CM_ERR_ARG, "cm_mapping_create has not been called");
+  if (rows <= 0 || cols <= 0 || cols > 65535) return fail(ctx, CM_ERR_ARG, "bad argument");
+  // every feature class can take most of a sweep (EDGE_BROKEN points all join sharp / less-sharp, every point below the curvature
+  // threshold is flat, ScanRegistration.cpp:286-303): the odometry stage is sized for whole sweeps
+  const long long cap = (long long)rows * cols;
+  const int cs = (int)cap, cls = (int)cap, cf = (int)cap;
+  const int rc = cm_odometry_batch_create(ctx, ctx->map_streams, std::max(cs, 1), std::max(cls, 1), std::max(cf, 1), (int)cap);
+  if (rc != CM_OK) return rc;
+  ctx->chain_rows = rows; ctx->chain_cols = cols;
+  return CM_OK;
+}
+int cm_pipeline_chain_step_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols, cm_iso* odom, cm_iso* mapped, cm_odom_stats* ostats,
+                                cm_match_stats* mstats) {
+  return pipeline_chain_step(ctx, frames, rows, cols, true, odom, mapped, ostats, mstats);
+}
+int cm_pipeline_chain_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, cm_iso* odom, cm_iso* mapped, cm_odom_stats* ostats,
+                               cm_match_stats* mstats) {
+  return pipeline_chain_step(ctx, d_frames, rows, cols, false, odom, mapped, ostats, mstats);
+}
+
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch(ctx, frames, rows, cols, true); }
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch(ctx, d_frames, rows, cols, false); }
 static bool strided_args_ok(cm_ctx* ctx, const void* const* clouds, size_t stride) {

@@ -172,9 +172,16 @@ int cm_odometry_batch_create(cm_ctx* ctx, int nstreams, int cap_sharp, int cap_l
   return CM_OK;
 }
 
-int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int* n_sharp, const cm_point* less_sharp, const int* n_less_sharp,
-                                   const cm_point* flat, const int* n_flat, const cm_point* less_flat, const int* n_less_flat, cm_iso* odom,
-                                   cm_pose* transform, cm_point* corner_last, cm_point* surf_last, cm_odom_stats* stats) {
+}  // extern "C"
+
+namespace cm {
+// The batch stage with its four input clouds anywhere (host or device: the copies are cudaMemcpyDefault), stream s of a cloud
+// starting at src + s * pitch bytes.  cm_odometry_batch_process_host passes its packed host arrays; the pipeline chain
+// (cm_pipeline_chain_step_host, cm_mapping.cu) passes the device clouds scan registration left behind.
+int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, const int* n_sharp, const void* less_sharp, size_t pitch_less_sharp,
+                        const int* n_less_sharp, const void* flat, size_t pitch_flat, const int* n_flat, const void* less_flat,
+                        size_t pitch_less_flat, const int* n_less_flat, cm_iso* odom, cm_pose* transform, cm_point* corner_last,
+                        cm_point* surf_last, cm_odom_stats* stats) {
   if (!ctx || ctx->obatch.S <= 0) return fail(ctx, CM_ERR_ARG, "cm_odometry_batch_create has not been called");
   if (!sharp || !less_sharp || !flat || !less_flat || !n_sharp || !n_less_sharp || !n_flat || !n_less_flat) return fail(ctx, CM_ERR_ARG, "bad argument");
   OdomBatch& b = ctx->obatch;
@@ -208,8 +215,8 @@ int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int
     memset(local.data(), 0, sizeof(cm_odom_stats) * S);
     std::vector<MatchState> hs(S);
     if (any_active) {
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.sharp.p, sharp, (size_t)S * b.cap_sharp * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-      CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.flat.p, flat, (size_t)S * b.cap_flat * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+      CM_CUDA_CHECK(ctx, cudaMemcpy2DAsync(b.sharp.p, b.cap_sharp * sizeof(cm_point), sharp, pitch_sharp, (size_t)max_sharp * sizeof(cm_point), S, cudaMemcpyDefault, st));
+      CM_CUDA_CHECK(ctx, cudaMemcpy2DAsync(b.flat.p, b.cap_flat * sizeof(cm_point), flat, pitch_flat, (size_t)max_flat * sizeof(cm_point), S, cudaMemcpyDefault, st));
       CM_CUDA_CHECK(ctx, cudaMemsetAsync(b.ind.p, 0xFF, (size_t)S * (2 * (size_t)b.cap_sharp + 3 * (size_t)b.cap_flat) * sizeof(int), st));
       CM_CUDA_CHECK(ctx, cudaMemsetAsync(b.rows.p, 0, (size_t)S * capQ * sizeof(RowOut), st));
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.pose.p, b.tf.data(), (size_t)6 * S * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -258,8 +265,8 @@ int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int
       memcpy(&tfinv[(size_t)6 * S + 12 * s], inv.R, 36); memcpy(&tfinv[(size_t)6 * S + 12 * s + 9], inv.t, 12);
     }
     CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.tfinv.p, tfinv.data(), tfinv.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.last_c.p, less_sharp, (size_t)S * b.cap_less_sharp * sizeof(cm_point), cudaMemcpyHostToDevice, st));
-    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(b.last_s.p, less_flat, (size_t)S * b.cap_less_flat * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    if (max_ls) CM_CUDA_CHECK(ctx, cudaMemcpy2DAsync(b.last_c.p, b.cap_less_sharp * sizeof(cm_point), less_sharp, pitch_less_sharp, (size_t)max_ls * sizeof(cm_point), S, cudaMemcpyDefault, st));
+    if (max_lf) CM_CUDA_CHECK(ctx, cudaMemcpy2DAsync(b.last_s.p, b.cap_less_flat * sizeof(cm_point), less_flat, pitch_less_flat, (size_t)max_lf * sizeof(cm_point), S, cudaMemcpyDefault, st));
     const float* d_tf6 = (const float*)b.tfinv.p; const float* d_inv = d_tf6 + (size_t)6 * S;
     launch_odom_to_end_batch((float4*)b.last_c.p, b.cap_less_sharp, d_i + 5 * S, max_ls, S, d_tf6, d_inv, d_i + 7 * S, st);
     launch_odom_to_end_batch((float4*)b.last_s.p, b.cap_less_flat, d_i + 6 * S, max_lf, S, d_tf6, d_inv, d_i + 7 * S, st);
@@ -283,5 +290,16 @@ int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
 }
+}  // namespace cm
 
+extern "C" {
+int cm_odometry_batch_process_host(cm_ctx* ctx, const cm_point* sharp, const int* n_sharp, const cm_point* less_sharp, const int* n_less_sharp,
+                                   const cm_point* flat, const int* n_flat, const cm_point* less_flat, const int* n_less_flat, cm_iso* odom,
+                                   cm_pose* transform, cm_point* corner_last, cm_point* surf_last, cm_odom_stats* stats) {
+  if (!ctx || ctx->obatch.S <= 0) return fail(ctx, CM_ERR_ARG, "cm_odometry_batch_create has not been called");
+  const OdomBatch& b = ctx->obatch;
+  return odometry_batch_core(ctx, sharp, b.cap_sharp * sizeof(cm_point), n_sharp, less_sharp, b.cap_less_sharp * sizeof(cm_point), n_less_sharp, flat,
+                             b.cap_flat * sizeof(cm_point), n_flat, less_flat, b.cap_less_flat * sizeof(cm_point), n_less_flat, odom, transform,
+                             corner_last, surf_last, stats);
+}
 }  // extern "C"
