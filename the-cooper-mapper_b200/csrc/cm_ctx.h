@@ -37,6 +37,7 @@ struct OdomBatch {
   std::vector<HostIso> Tsum;        // _Tsum
   DeviceBuffer sharp, flat, last_c, last_s, ints, ind, rows, state, sums, pose, tfinv;
   GridBatch grid_c, grid_s;
+  OdomGraphCache graphs;
 };
 
 // DynamicFeatureMap paging (cm_mapio.cu): the index2.txt catalogue of one stream and the window that is resident

@@ -355,7 +355,10 @@ __device__ __forceinline__ bool knn5_geom(const GridView& g, float qx, float qy,
 // cell is opened: most cells are pruned by their lower bound and almost no candidate passes the insert test, which is where
 // the search spent a third of its instructions at 5 of 32 lanes (the divergent sorted insert).  Any five valid points are a
 // correct start: the result is the exact top-5 of (cells scanned) U (start points), the same set either way.
-template <bool kOrigIdx>
+// KTH: the list entry whose distance the search has to prove final -- 4 for the 5 nearest neighbours, 0 when the caller only uses the
+// nearest one (the odometry's correspondences): cells and shells beyond the current KTH-th distance are skipped, the entries behind
+// KTH are then not the true runners-up.
+template <bool kOrigIdx, int KTH = 4>
 __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c, float qx, float qy, float qz, uint4* rng, Top5& best,
                                             unsigned int* ncand = nullptr, const int* prev = nullptr, bool* tie_out = nullptr) {
   float d6 = FLT_MAX;   // smallest distance turned away from / pushed out of the list (map grids: exact-tie detection, top5_insert_track)
@@ -418,7 +421,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
   uint4 r = nr ? my[0] : make_uint4(0u, 0u, 0u, 0u);
   const bool nofilt = c.filt == CM_FILT_NONE;
   while (ci < nr) {
-    if (j0 == 0 && __uint_as_float(r.z) > best.d(4)) {   // the whole cell is farther than the current 5th neighbour
+    if (j0 == 0 && __uint_as_float(r.z) > best.d(KTH)) {   // the whole cell is farther than the current 5th neighbour
       ci++; if (ci < nr) r = my[ci * stride];
       continue;
     }
@@ -431,7 +434,7 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
     // position first: the warp iterates max-over-lanes of the number of passing candidates instead of once per position
     unsigned long long kk[CM_KNN_UNROLL];
     unsigned int pass = 0;
-    const float d5 = best.d(4);   // candidates at or below the 5th distance go to the exact (d2, index) test of the insert
+    const float d5 = best.d(KTH);   // candidates at or below the 5th distance go to the exact (d2, index) test of the insert
 #pragma unroll
     for (int u = 0; u < CM_KNN_UNROLL; u++) {
       kk[u] = CM_TOP5_EMPTY;
@@ -459,14 +462,14 @@ __device__ __forceinline__ bool knn5_level0(const GridView& g, const KnnGeom& c,
   if (tie_out) *tie_out = !kOrigIdx && top5_has_tie(best, d6);   // the caller re-runs such a query canonically (top5_insert_canon)
   if (g.max_level < 1) return false;
   const float r0 = leaf98 * c.m0;
-  return !(best.d(4) < r0 * r0);
+  return !(best.d(KTH) < r0 * r0);
 }
 
 // Levels >= 1 of ONE query, executed by a whole warp.  The query (position, geometry, current list) lives in lane h;
 // on return lane h's list is final.
 // L0 = 0 repeats the level-0 block as well (a query whose per-thread pass met an exact distance tie starts over from an empty list:
 // this path orders ties canonically).
-template <bool kOrigIdx>
+template <bool kOrigIdx, int KTH = 4>
 __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const KnnGeom& c, float qx, float qy, float qz, float gate,
                                                  Top5& best, int L0 = 1) {
   const unsigned int FULL = 0xffffffffu;
@@ -478,7 +481,7 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
   const int blx = __shfl_sync(FULL, c.lx, h), bly = __shfl_sync(FULL, c.ly, h), blz = __shfl_sync(FULL, c.lz, h);
   const float bm0 = __shfl_sync(FULL, c.m0, h);
   const int bfilter = __shfl_sync(FULL, c.filt, h);
-  float bd5 = __shfl_sync(FULL, best.d(4), h);
+  float bd5 = __shfl_sync(FULL, best.d(KTH), h);
   const float kf = (float)k;
   for (int L = L0; L <= g.max_level; L++) {
     const float rr = 0.98f * leaf * (bm0 + (float)((L - 1) * k));   // radius guaranteed by the previous level
@@ -552,24 +555,24 @@ __device__ __forceinline__ void knn5_warp_finish(const GridView& g, int h, const
         loc.key[4] = CM_TOP5_EMPTY; loc.slot[4] = -1;
       }
     }
-    bd5 = __shfl_sync(FULL, best.d(4), h);
+    bd5 = __shfl_sync(FULL, best.d(KTH), h);
   }
 }
 
 // Level 0 per thread, then the warp finishes its unresolved queries one at a time (callers without a deferred pass).
-template <bool kOrigIdx>
+template <bool kOrigIdx, int KTH = 4>
 __device__ __forceinline__ void knn5_search(const GridView& g, bool valid, float qx, float qy, float qz, float gate, uint4* rng,
                                             Top5& best) {
   top5_init(best);
   KnnGeom c;
   valid = knn5_geom(g, qx, qy, qz, gate, c, false) && valid;
   bool need = false;
-  if (valid) need = knn5_level0<kOrigIdx>(g, c, qx, qy, qz, rng, best);
+  if (valid) need = knn5_level0<kOrigIdx, KTH>(g, c, qx, qy, qz, rng, best);
   unsigned int hard = __ballot_sync(0xffffffffu, need);
   while (hard) {
     const int h = __ffs(hard) - 1;
     hard &= hard - 1;
-    knn5_warp_finish<kOrigIdx>(g, h, c, qx, qy, qz, gate, best);
+    knn5_warp_finish<kOrigIdx, KTH>(g, h, c, qx, qy, qz, gate, best);
   }
 }
 

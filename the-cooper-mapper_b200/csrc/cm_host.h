@@ -243,7 +243,18 @@ struct OdomBatchLaunch {
   const GridView* grid_corner; const GridView* grid_surf;
   const MatchState* state; int* ind; RowOut* rows;
 };
-void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream);
+void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream, const int* d_iter = nullptr);
+// The batch odometry's Gauss-Newton loop as ONE submission: init -> WHILE { correspondences + rows, reduction, 6x6 step, advance },
+// as many evaluations as the slowest stream needs (25 x 3 launches otherwise, most of them empty once the streams have converged).
+struct OdomGraphCache {
+  struct Entry { std::vector<unsigned long long> key; cudaGraphExec_t exec; unsigned long long launches; unsigned long long gen; };
+  std::vector<Entry> entries;
+  bool usable = true;
+  int* d_iter = nullptr;
+  bool launch(const MatchLaunch& m, const OdomBatchLaunch& o, const int* d_active, cudaStream_t stream);   // false: nothing was launched
+  void clear();
+  ~OdomGraphCache();
+};
 void launch_odom_gate(MatchState* d_state, const int* d_active, int nstreams, cudaStream_t stream);
 void launch_odom_to_end_batch(float4* d_cloud, int cap, const int* d_n, int max_n, int nstreams, const float* d_tf6, const float* d_inv12,
                               const int* d_on, cudaStream_t stream);

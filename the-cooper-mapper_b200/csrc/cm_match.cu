@@ -1072,7 +1072,7 @@ void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
   OdomArgs a;
   a.sharp = o.sharp; a.flat = o.flat; a.n_sharp = o.n_sharp; a.n_flat = o.n_flat;
   a.last_corner = o.last_corner; a.last_surf = o.last_surf; a.bound_corner = o.bound_corner; a.bound_surf = o.bound_surf;
-  a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter;
+  a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter; a.spread = 0;
   const int nT = ((o.n_sharp + 31) & ~31) + o.n_flat;
   CM_LAUNCH(odom_corr_kernel, (nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, 128, 0, stream, a);
 }
@@ -1096,14 +1096,23 @@ void GridBatch::build(const float4* d_pts, const int* d_n, int max_n, const int*
             d_n, inv, cell_size, grid_max_level(cell_size, gate), d_on, nstreams);
 }
 
-void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream) {
+void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream, const int* d_iter) {
   OdomBatchArgs b;
+  b.iter_dev = d_iter;
   b.sharp = o.sharp; b.flat = o.flat; b.cap_sharp = o.cap_sharp; b.cap_flat = o.cap_flat; b.n_sharp = o.n_sharp; b.n_flat = o.n_flat;
   b.last_corner = o.last_corner; b.last_surf = o.last_surf; b.cap_last_corner = o.cap_last_corner; b.cap_last_surf = o.cap_last_surf;
   b.bound_corner = o.bound_corner; b.bound_surf = o.bound_surf; b.grid_corner = o.grid_corner; b.grid_surf = o.grid_surf;
   b.state = o.state; b.ind = o.ind; b.rows = o.rows; b.iter = iter;
   const int nT = ((o.max_sharp + 31) & ~31) + o.max_flat;
-  CM_LAUNCH(odom_corr_batch_kernel, dim3((nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, o.nstreams), 128, 0, stream, b);
+  // Every fifth evaluation a query walks several rings of the last cloud (thousands of points, its warp working on one query at a
+  // time): with 32 queries per warp a single sweep keeps 10 SMs busy for 440 us.  Thin the warps out -- down to one query per warp --
+  // while the launch stays below a few warps per SM sub-partition.
+  int spread = 0;
+  while (spread < 5 && (((long long)nT * o.nstreams) << (spread + 1)) / 32 <= 148 * 4 * 8) spread++;
+  if (const char* e = getenv("COOPERMAP_ODOM_SPREAD")) spread = atoi(e);
+  b.spread = spread;
+  const long long nthreads = (long long)((nT + 31) / 32) * 32 << spread;
+  CM_LAUNCH(odom_corr_batch_kernel, dim3((unsigned int)((nthreads + 127) / 128 > 0 ? (nthreads + 127) / 128 : 1), o.nstreams), 128, 0, stream, b);
 }
 void launch_odom_gate(MatchState* d_state, const int* d_active, int nstreams, cudaStream_t stream) {
   CM_LAUNCH(odom_gate_kernel, (nstreams + 63) / 64, 64, 0, stream, d_state, d_active, nstreams);
@@ -1157,11 +1166,11 @@ static void launch_match_body(const MatchLaunch& m, const int* d_iter, cudaStrea
   CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
 }
 
-// init -> WHILE { search, hard search, fit + solve, advance }: as many evaluations as the slowest stream needs, one submission
-static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cudaStream_t stream, unsigned long long* launches_per_eval) {
-  if (!(m.partials && m.tickets && m.hard) || m.prm.max_iterations > CM_MAX_EVALS) return nullptr;
-  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
-  if ((maxq + 32 + 255) / 256 > m.partial_blocks) return nullptr;
+// init -> WHILE { body, advance }: as many evaluations as the slowest stream needs, one submission.  init / body enqueue their
+// launches on `stream` (captured); the body reads the evaluation index from d_iter.
+template <typename InitFn, typename BodyFn>
+static cudaGraphExec_t build_while_graph_fn(cudaStream_t stream, int* d_iter, const MatchState* state, int nstreams, int max_iterations,
+                                            const int* skip, InitFn init, BodyFn body, unsigned long long* launches_per_eval) {
   cudaGraph_t g = nullptr, gi = nullptr, tmp = nullptr;
   cudaGraphExec_t exec = nullptr;
   const unsigned long long before = g_launch_count;
@@ -1169,7 +1178,7 @@ static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cuda
   // init part as a child graph
   if (ok) ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
   if (ok) {
-    launch_match_init(m, stream);
+    init();
     cudaMemsetAsync(d_iter, 0, sizeof(int), stream);
     ok = cudaStreamEndCapture(stream, &gi) == cudaSuccess && gi;
   }
@@ -1183,12 +1192,12 @@ static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cuda
     ok = cudaGraphAddNode(&n_cond, g, &n_init, 1, &prm) == cudaSuccess && prm.conditional.phGraph_out;
   }
   if (ok) {
-    cudaGraph_t body = prm.conditional.phGraph_out[0];
-    ok = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    cudaGraph_t bodyg = prm.conditional.phGraph_out[0];
+    ok = cudaStreamBeginCaptureToGraph(stream, bodyg, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       const unsigned long long b0 = g_launch_count;
-      launch_match_body(m, d_iter, stream);
-      CM_LAUNCH(gn_advance_kernel, 1, 1, 0, stream, handle, d_iter, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations, m.skip);
+      body();
+      CM_LAUNCH(gn_advance_kernel, 1, 1, 0, stream, handle, d_iter, state, nstreams, max_iterations, skip);
       *launches_per_eval = g_launch_count - b0;
       ok = cudaStreamEndCapture(stream, &tmp) == cudaSuccess;
     }
@@ -1200,6 +1209,62 @@ static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cuda
   if (!ok) { cudaGetLastError(); if (exec) cudaGraphExecDestroy(exec); return nullptr; }
   return exec;
 }
+
+// the mapping stage's loop: init -> WHILE { search, hard search, fit + solve, advance }
+static cudaGraphExec_t build_while_graph(const MatchLaunch& m, int* d_iter, cudaStream_t stream, unsigned long long* launches_per_eval) {
+  if (!(m.partials && m.tickets && m.hard) || m.prm.max_iterations > CM_MAX_EVALS) return nullptr;
+  const int maxq = m.max_queries > 0 ? m.max_queries : m.cap_corner + m.cap_surf;
+  if ((maxq + 32 + 255) / 256 > m.partial_blocks) return nullptr;
+  return build_while_graph_fn(stream, d_iter, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations, m.skip,
+                              [&]() { launch_match_init(m, stream); }, [&]() { launch_match_body(m, d_iter, stream); }, launches_per_eval);
+}
+
+// the batch odometry's loop: init (+ the gate that parks the streams without a usable last frame) -> WHILE { correspondences + rows,
+// row reduction, 6x6 step, advance }
+bool OdomGraphCache::launch(const MatchLaunch& m, const OdomBatchLaunch& o, const int* d_active, cudaStream_t stream) {
+  if (!usable || g_timeline.on) return false;
+  std::vector<unsigned long long> key;
+  auto P = [&](const void* p) { key.push_back((unsigned long long)(uintptr_t)p); };
+  auto I = [&](long long v) { key.push_back((unsigned long long)v); };
+  I(m.nstreams); P(m.corner); P(m.surf); P(m.n_corner); P(m.n_surf); I(m.cap_corner); I(m.cap_surf); P(m.grid_corner); P(m.grid_surf);
+  P(m.pose_in); P(m.state); P(m.rows); P(m.sums); I(m.prm.max_iterations); P(d_active);
+  P(o.last_corner); P(o.last_surf); I(o.cap_last_corner); I(o.cap_last_surf); P(o.bound_corner); P(o.bound_surf); P(o.ind);
+  I(o.max_sharp); I(o.max_flat);
+  for (size_t i = 0; i < entries.size(); i++) {
+    Entry& e = entries[i];
+    if (e.key == key) {
+      if (e.gen != g_alloc_generation) { cudaGraphExecDestroy(e.exec); entries.erase(entries.begin() + i); break; }
+      if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) { cudaGetLastError(); return false; }
+      g_launch_count += e.launches;
+      return true;
+    }
+  }
+  if (entries.size() >= 16) clear();
+  if (!d_iter && cudaMalloc(&d_iter, sizeof(int)) != cudaSuccess) { cudaGetLastError(); d_iter = nullptr; usable = false; return false; }
+  Entry e; e.key = key; e.gen = g_alloc_generation; unsigned long long per_eval = 4;
+  int* di = d_iter;
+  e.exec = build_while_graph_fn(stream, di, (const MatchState*)m.state, m.nstreams, m.prm.max_iterations, nullptr,
+                                [&]() { launch_match_init(m, stream); launch_odom_gate(m.state, d_active, m.nstreams, stream); },
+                                [&]() {
+                                  launch_odom_corr_batch(o, 0, stream, di);
+                                  launch_match_reduce(m, 0, stream);
+                                  CorrArgs ca; SolveArgs sa;
+                                  fill_args(m, ca, sa);
+                                  sa.iter_dev = di;
+                                  CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
+                                }, &per_eval);
+  if (!e.exec) { usable = false; return false; }
+  e.launches = 2 + per_eval;
+  entries.push_back(e);
+  if (cudaGraphLaunch(e.exec, stream) != cudaSuccess) { cudaGetLastError(); return false; }
+  g_launch_count += e.launches;
+  return true;
+}
+void OdomGraphCache::clear() {
+  for (Entry& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec);
+  entries.clear();
+}
+OdomGraphCache::~OdomGraphCache() { clear(); if (d_iter) cudaFree(d_iter); }
 
 static std::vector<unsigned long long> match_graph_key(const MatchLaunch& m) {
   std::vector<unsigned long long> k;

@@ -13,6 +13,7 @@ struct OdomArgs {
   int* ind;                             // [2 * n_sharp + 3 * n_flat]: corner {closest, second}, surf {closest, second, third}
   RowOut* rows;                         // [n_sharp + n_flat]
   int iter;
+  int spread;                           // a warp takes 32 >> spread query slots (its first lanes): see launch_odom_corr_batch
 };
 
 // transformToStart (LaserOdometry.cpp:135-142): s = 10 * frac(intensity); po = T(_transform * s) * pi
@@ -38,58 +39,90 @@ __device__ __forceinline__ void odom_corr_body(const OdomArgs& a, uint4* rng, Po
   if (threadIdx.x == 0) make_pose_coef(st, kc);
   if (threadIdx.x < 6) tf[threadIdx.x] = st.pose[threadIdx.x];
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int nT = ((a.n_sharp + 31) & ~31) + a.n_flat;
-  if ((t & ~31) >= nT) return;
+  const int per = 32 >> a.spread;
+  if ((gt >> 5) * per >= nT) return;
+  const int t = (gt & 31) < per ? (gt >> 5) * per + (gt & 31) : nT + 32;   // idle lanes of a thinned warp: an invalid slot
   bool isCorner; int src, row;
   const bool valid = decode_query(t, a.n_sharp, a.n_flat, &isCorner, &src, &row);
+  if ((gt & 31) >= per) isCorner = (gt >> 5) * per < ((a.n_sharp + 31) & ~31);   // (the class of the warp's real slots)
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   float sx = 0.f, sy = 0.f, sz = 0.f;
   if (valid) { p = isCorner ? a.sharp[src] : a.flat[src]; odom_to_start(tf, p, &sx, &sy, &sz); }
   int* ind = isCorner ? a.ind + 2 * src : a.ind + 2 * a.n_sharp + 3 * src;
   if (a.iter % 5 == 0) {   // LaserOdometry.cpp:358,424: correspondences are refreshed every 5th iteration
     Top5 best;
-    knn5_search<true>(isCorner ? a.grid_corner : a.grid_surf, valid, sx, sy, sz, 25.0f, rng, best);
-    if (valid) {
-      int closest = -1, min2 = -1, min3 = -1;
-      if (best.d(0) < 25.f && best.slot[0] >= 0) {
-        closest = best.idx(0);
-        if (isCorner) {   // :363-398
-          const float4* lc = a.last_corner;
-          const int scan = (int)lc[closest].w;
-          float minD2 = 25.f;
-          for (int j = closest + 1; j < a.bound_corner; j++) {
-            const float4 q = lc[j];
-            if ((double)(int)q.w > (double)scan + 2.5) break;
-            const float d = odom_sqdiff(q, sx, sy, sz);
-            if ((int)q.w > scan && d < minD2) { minD2 = d; min2 = j; }
-          }
-          for (int j = closest - 1; j >= 0; j--) {
-            const float4 q = lc[j];
-            if ((double)(int)q.w < (double)scan - 2.5) break;
-            const float d = odom_sqdiff(q, sx, sy, sz);
-            if ((int)q.w < scan && d < minD2) { minD2 = d; min2 = j; }
-          }
-        } else {          // :427-476
-          const float4* ls = a.last_surf;
-          const int scan = (int)ls[closest].w;
-          float minD2 = 25.f, minD3 = 25.f;
-          for (int j = closest + 1; j < a.bound_surf; j++) {
-            const float4 q = ls[j];
-            if ((double)(int)q.w > (double)scan + 2.5) break;
-            const float d = odom_sqdiff(q, sx, sy, sz);
-            if ((int)q.w <= scan) { if (d < minD2) { minD2 = d; min2 = j; } }
-            else { if (d < minD3) { minD3 = d; min3 = j; } }
-          }
-          for (int j = closest - 1; j >= 0; j--) {
-            const float4 q = ls[j];
-            if ((double)(int)q.w < (double)scan - 2.5) break;
-            const float d = odom_sqdiff(q, sx, sy, sz);
-            if ((int)q.w >= scan) { if (d < minD2) { minD2 = d; min2 = j; } }
-            else { if (d < minD3) { minD3 = d; min3 = j; } }
-          }
+    knn5_search<true, 0>(isCorner ? a.grid_corner : a.grid_surf, valid, sx, sy, sz, 25.0f, rng, best);   // only the nearest point is used
+    // The second (and third) correspondent: the reference walks the last cloud from the closest point forwards, then backwards, until
+    // the ring index leaves +-2.5 rings (LaserOdometry.cpp:363-398, 427-476) -- hundreds to thousands of points per query, one after
+    // the other.  Here the WARP walks them for one query at a time, 32 consecutive points per round (one coalesced load): a ballot
+    // finds the first point past the ring limit, every lane keeps the first minimum of the points it saw (strict <, in visit order),
+    // and the lanes are merged by (distance, visit order) -- the point the sequential walk would have kept.
+    int closest = -1, min2 = -1, min3 = -1;
+    if (valid && best.d(0) < 25.f && best.slot[0] >= 0) closest = best.idx(0);
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned int work = __ballot_sync(FULL, closest >= 0);
+    while (work) {
+      const int h = __ffs(work) - 1;
+      work &= work - 1;
+      const int c0 = __shfl_sync(FULL, closest, h);
+      const float bx = __shfl_sync(FULL, sx, h), by = __shfl_sync(FULL, sy, h), bz = __shfl_sync(FULL, sz, h);
+      const float4* cloud = isCorner ? a.last_corner : a.last_surf;        // (a warp never mixes the two classes: decode_query)
+      const int bound = isCorner ? a.bound_corner : a.bound_surf;
+      const int scan = (int)cloud[c0].w;
+      float d2 = 25.f, d3 = 25.f;
+      unsigned int v2 = 0xFFFFFFFFu, v3 = 0xFFFFFFFFu;   // visit rank of the lane's candidate: forward 1, 2, ..; backward 0x40000000 + 1, 2, ..
+      for (int j0 = c0 + 1; j0 < bound; j0 += 32) {
+        const int j = j0 + lane;
+        const bool in = j < bound;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) q = cloud[j];
+        const int ring = (int)q.w;
+        const unsigned int brk = __ballot_sync(FULL, in && (double)ring > (double)scan + 2.5);
+        if (in && (brk == 0 || lane < __ffs(brk) - 1)) {
+          const float d = odom_sqdiff(q, bx, by, bz);
+          const unsigned int v = (unsigned int)(j - c0);
+          if (isCorner) { if (ring > scan && d < d2) { d2 = d; v2 = v; } }
+          else if (ring <= scan) { if (d < d2) { d2 = d; v2 = v; } }
+          else { if (d < d3) { d3 = d; v3 = v; } }
         }
+        if (brk) break;
       }
+      for (int j0 = c0 - 1; j0 >= 0; j0 -= 32) {
+        const int j = j0 - lane;
+        const bool in = j >= 0;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) q = cloud[j];
+        const int ring = (int)q.w;
+        const unsigned int brk = __ballot_sync(FULL, in && (double)ring < (double)scan - 2.5);
+        if (in && (brk == 0 || lane < __ffs(brk) - 1)) {
+          const float d = odom_sqdiff(q, bx, by, bz);
+          const unsigned int v = 0x40000000u + (unsigned int)(c0 - j);
+          if (isCorner) { if (ring < scan && d < d2) { d2 = d; v2 = v; } }
+          else if (ring >= scan) { if (d < d2) { d2 = d; v2 = v; } }
+          else { if (d < d3) { d3 = d; v3 = v; } }
+        }
+        if (brk) break;
+      }
+      // merge: smallest distance, earliest visit among equals (squared distances are >= 0: bit order = value order)
+      int w2 = -1, w3 = -1;
+      {
+        const unsigned int db = v2 != 0xFFFFFFFFu ? __float_as_uint(d2) : 0xFFFFFFFFu;
+        const unsigned int mind = __reduce_min_sync(FULL, db);
+        const unsigned int minv = __reduce_min_sync(FULL, (db == mind) ? v2 : 0xFFFFFFFFu);
+        if (mind != 0xFFFFFFFFu && minv != 0xFFFFFFFFu) w2 = minv >= 0x40000000u ? c0 - (int)(minv - 0x40000000u) : c0 + (int)minv;
+      }
+      if (!isCorner) {
+        const unsigned int db = v3 != 0xFFFFFFFFu ? __float_as_uint(d3) : 0xFFFFFFFFu;
+        const unsigned int mind = __reduce_min_sync(FULL, db);
+        const unsigned int minv = __reduce_min_sync(FULL, (db == mind) ? v3 : 0xFFFFFFFFu);
+        if (mind != 0xFFFFFFFFu && minv != 0xFFFFFFFFu) w3 = minv >= 0x40000000u ? c0 - (int)(minv - 0x40000000u) : c0 + (int)minv;
+      }
+      if (lane == h) { min2 = w2; min3 = w3; }
+    }
+    if (valid) {
       ind[0] = closest; ind[1] = min2;
       if (!isCorner) ind[2] = min3;
     }
@@ -164,6 +197,8 @@ struct OdomBatchArgs {
   const float4* last_corner; const float4* last_surf; int cap_last_corner, cap_last_surf; const int* bound_corner; const int* bound_surf;
   const GridView* grid_corner; const GridView* grid_surf;
   const MatchState* state; int* ind; RowOut* rows; int iter;
+  const int* iter_dev;   // optional: overrides iter (graph WHILE loop)
+  int spread;
 };
 __global__ void __launch_bounds__(128) odom_corr_batch_kernel(OdomBatchArgs b) {
   __shared__ uint4 rng[8 * 128];
@@ -179,7 +214,8 @@ __global__ void __launch_bounds__(128) odom_corr_batch_kernel(OdomBatchArgs b) {
   a.state = b.state + s;
   a.ind = b.ind + (size_t)s * (2 * b.cap_sharp + 3 * b.cap_flat);
   a.rows = b.rows + (size_t)s * (b.cap_sharp + b.cap_flat);
-  a.iter = b.iter;
+  a.iter = b.iter_dev ? *b.iter_dev : b.iter;
+  a.spread = b.spread;
   odom_corr_body(a, rng, kc, tf);
 }
 

@@ -7,6 +7,13 @@
 #include <algorithm>
 
 using namespace cm;
+
+// cell size of the voxel-cell hash over the last clouds (the odometry's 1-NN search with a 5 m gate): development override
+static float odom_cell(bool corner) {
+  static const float c = getenv("COOPERMAP_ODOM_CELL_C") ? (float)atof(getenv("COOPERMAP_ODOM_CELL_C")) : 2.5f;
+  static const float f = getenv("COOPERMAP_ODOM_CELL_S") ? (float)atof(getenv("COOPERMAP_ODOM_CELL_S")) : 2.5f;
+  return corner ? c : f;
+}
 static int fail(cm_ctx* ctx, int code, const std::string& msg) { return ctx_fail(ctx, code, msg); }
 
 static HostIso h_identity() { HostIso i; for (int k = 0; k < 9; k++) i.R[k] = (k % 4 == 0) ? 1.f : 0.f; i.t[0] = i.t[1] = i.t[2] = 0.f; return i; }
@@ -124,8 +131,8 @@ int cm_odometry_process_host(cm_ctx* ctx, const cm_point* sharp, int n_sharp, co
     }
     ctx->o_n_last_c = n_less_sharp; ctx->o_n_last_s = n_less_flat;
     if (first || (n_less_sharp > 10 && n_less_flat > 100)) {   // KD-trees rebuilt, :299-300, 320-323
-      ctx->o_grid_c.build((const float4*)ctx->o_last_c.p, n_less_sharp, 2.5f, 25.f, 0, st);
-      ctx->o_grid_s.build((const float4*)ctx->o_last_s.p, n_less_flat, 2.5f, 25.f, 0, st);
+      ctx->o_grid_c.build((const float4*)ctx->o_last_c.p, n_less_sharp, odom_cell(true), 25.f, 0, st);
+      ctx->o_grid_s.build((const float4*)ctx->o_last_s.p, n_less_flat, odom_cell(false), 25.f, 0, st);
     }
     if (corner_last && n_less_sharp) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(corner_last, ctx->o_last_c.p, n_less_sharp * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     if (surf_last && n_less_flat) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(surf_last, ctx->o_last_s.p, n_less_flat * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
@@ -231,18 +238,23 @@ int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, cons
       m.pose_in = (const float*)b.pose.p; m.state = (MatchState*)b.state.p; m.rows = (RowOut*)b.rows.p;
       m.nn_slot = nullptr; m.sums = (double*)b.sums.p; m.trace = nullptr; m.nn = nullptr;
       m.orig_idx = 1; m.max_queries = max_sharp + max_flat; m.prm = prm;
-      launch_match_init(m, st);
-      launch_odom_gate(m.state, d_i + 4 * S, S, st);
       OdomBatchLaunch o;
       o.nstreams = S; o.sharp = m.corner; o.flat = m.surf; o.cap_sharp = b.cap_sharp; o.cap_flat = b.cap_flat; o.n_sharp = d_i; o.n_flat = d_i + S;
       o.max_sharp = max_sharp; o.max_flat = max_flat;
       o.last_corner = (const float4*)b.last_c.p; o.last_surf = (const float4*)b.last_s.p; o.cap_last_corner = b.cap_less_sharp; o.cap_last_surf = b.cap_less_flat;
       o.bound_corner = d_i + 2 * S; o.bound_surf = d_i + 3 * S;
       o.grid_corner = m.grid_corner; o.grid_surf = m.grid_surf; o.state = m.state; o.ind = (int*)b.ind.p; o.rows = m.rows;
-      for (int it = 0; it < MAXIT; it++) {
-        launch_odom_corr_batch(o, it, st);
-        launch_match_reduce(m, it, st);
-        launch_match_solve(m, it, (const double*)m.sums, st);
+      // launch sizes in whole tiles: the loop's graph is keyed by them and then repeats from frame to frame
+      o.max_sharp = (max_sharp + 1023) & ~1023; o.max_flat = (max_flat + 1023) & ~1023;
+      static const bool no_graph = getenv("COOPERMAP_NO_GRAPH") != nullptr;
+      if (no_graph || !b.graphs.launch(m, o, d_i + 4 * S, st)) {
+        launch_match_init(m, st);
+        launch_odom_gate(m.state, d_i + 4 * S, S, st);
+        for (int it = 0; it < MAXIT; it++) {
+          launch_odom_corr_batch(o, it, st);
+          launch_match_reduce(m, it, st);
+          launch_match_solve(m, it, (const double*)m.sums, st);
+        }
       }
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), b.state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
       CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
@@ -270,8 +282,8 @@ int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, cons
     const float* d_tf6 = (const float*)b.tfinv.p; const float* d_inv = d_tf6 + (size_t)6 * S;
     launch_odom_to_end_batch((float4*)b.last_c.p, b.cap_less_sharp, d_i + 5 * S, max_ls, S, d_tf6, d_inv, d_i + 7 * S, st);
     launch_odom_to_end_batch((float4*)b.last_s.p, b.cap_less_flat, d_i + 6 * S, max_lf, S, d_tf6, d_inv, d_i + 7 * S, st);
-    b.grid_c.build((const float4*)b.last_c.p, d_i + 5 * S, std::max(max_ls, 1), d_i + 8 * S, 2.5f, 25.f, st);
-    b.grid_s.build((const float4*)b.last_s.p, d_i + 6 * S, std::max(max_lf, 1), d_i + 8 * S, 2.5f, 25.f, st);
+    b.grid_c.build((const float4*)b.last_c.p, d_i + 5 * S, std::max(max_ls, 1), d_i + 8 * S, odom_cell(true), 25.f, st);
+    b.grid_s.build((const float4*)b.last_s.p, d_i + 6 * S, std::max(max_lf, 1), d_i + 8 * S, odom_cell(false), 25.f, st);
     if (corner_last) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(corner_last, b.last_c.p, (size_t)S * b.cap_less_sharp * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     if (surf_last) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(surf_last, b.last_s.p, (size_t)S * b.cap_less_flat * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
