@@ -1,6 +1,7 @@
 // coopermap.hpp -- header-only C++ facade over the C ABI (coopermap.h): the reference's stage classes with the same names and
 // the same setup / process split, so that a nodelet written against lidar_slam::{OrganisedScanRegistration,
-// MultiScanRegistration, LaserOdometry, LaserMapping, LaserMappingLocal, LaserLocalization, ScanMatch} keeps its shape
+// MultiScanRegistration, LaserOdometry, LaserMapping, LaserMappingLocal, LaserLocalization, ScanMatch} keeps its shape; LoamPipeline
+// is the three stages of the launch file in one object
 // (L_SLAM/src/odometry/*.h, scan_to_scan_match/ScanMatch.h, nodelet/*.cpp).  Clouds are std::vector<cm_point> (the payload
 // of pcl::PointCloud<pcl::PointXYZI>), poses are cm_iso (Eigen::Isometry3f, row-major rotation + translation) or cm_pose
 // (lidar_slam::Twist).  No PCL / Eigen / ROS types: the conversion helpers a nodelet needs are in INTEGRATION.md section 2.
@@ -193,6 +194,32 @@ class LaserMapping {
  protected:
   Context ctx_;
   cm_match_stats stats_ = cm_match_stats();
+};
+
+// The three nodelets of the reference's launch file as ONE object: a sweep in, /laser_odom_to_init and /aft_mapped_to_init out
+// (cm_pipeline_chain_step_host).  The feature clouds and the projected clouds the nodelets pass over topics stay in device memory.
+// The map insertion of a sweep finishes behind process(); sync() waits for it (the map read-outs below are ordered behind it anyway).
+class LoamPipeline : public LaserMapping {
+ public:
+  LoamPipeline(int rows, int cols, const cm_config& cfg = Context::defaults(), size_t maxCornerPoints = 400000, size_t maxSurfPoints = 4000000)
+      : LaserMapping(cfg, maxCornerPoints, maxSurfPoints), rows_(rows), cols_(cols) {
+    ctx_.check(cm_pipeline_chain_create(ctx_.get(), rows, cols));
+  }
+  // organised sweep (rows x cols, ring-major, NaN = no return) -> /aft_mapped_to_init; odometry(): /laser_odom_to_init of the same sweep
+  cm_iso process(const PointCloud& organised) {
+    if (organised.size() != (size_t)rows_ * cols_) throw Error(CM_ERR_ARG, "sweep size does not match rows x cols");
+    cm_iso mapped;
+    ctx_.check(cm_pipeline_chain_step_host(ctx_.get(), organised.data(), rows_, cols_, &odom_, &mapped, &ostats_, &stats_));
+    return mapped;
+  }
+  const cm_iso& odometry() const { return odom_; }
+  const cm_odom_stats& odometryStats() const { return ostats_; }
+  void sync() { ctx_.check(cm_mapping_sync(ctx_.get())); }
+
+ private:
+  int rows_, cols_;
+  cm_iso odom_ = cm_iso();
+  cm_odom_stats ostats_ = cm_odom_stats();
 };
 
 // LaserLocalization::process (LaserLocalization.cpp:163-188): FeatureMap::scanMatchScan against a prebuilt map, no map update.

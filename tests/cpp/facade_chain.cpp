@@ -21,13 +21,19 @@ int main(int argc, char** argv) {
     coopermap::OrganisedScanRegistration scanReg(cfg);
     coopermap::LaserOdometry odometry(cfg);
     coopermap::LaserMapping mapping(cfg, 100000, 800000);
+    coopermap::LoamPipeline pipeline(rows, cols, cfg, 100000, 800000);   // the same chain in one object, clouds staying on the device
     coopermap::PointCloud sweep((size_t)rows * cols);
     std::vector<float> out;
+    int chain_mismatch = 0;
     for (int k = 0; k < nframes; k++) {
       if (fread(sweep.data(), sizeof(cm_point), sweep.size(), f) != sweep.size()) return 5;
       scanReg.process(sweep, rows, cols);
       odometry.process(scanReg.cornerPointsSharp(), scanReg.cornerPointsLessSharp(), scanReg.surfacePointsFlat(), scanReg.surfacePointsLessFlat());
       const cm_iso mapped = mapping.process(odometry.transformSum(), odometry.lastCornerCloud(), odometry.lastSurfaceCloud());
+      const cm_iso mapped1 = pipeline.process(sweep);
+      for (int i = 0; i < 9; i++) chain_mismatch += mapped1.R[i] != mapped.R[i];
+      for (int i = 0; i < 3; i++) chain_mismatch += mapped1.t[i] != mapped.t[i];
+      for (int i = 0; i < 3; i++) chain_mismatch += pipeline.odometry().t[i] != odometry.transformSum().t[i];
       for (int i = 0; i < 9; i++) out.push_back(mapped.R[i]);
       for (int i = 0; i < 3; i++) out.push_back(mapped.t[i]);
       out.push_back((float)scanReg.laserCloud().size());
@@ -38,7 +44,12 @@ int main(int argc, char** argv) {
     if (!g) return 6;
     fwrite(out.data(), 4, out.size(), g);
     fclose(g);
+    pipeline.sync();
     printf("facade_chain: %d frames, map %zu corner + %zu surf points\n", nframes, mapping.mapCloud(0).size(), mapping.mapCloud(1).size());
+    if (chain_mismatch || pipeline.mapCloud(1).size() != mapping.mapCloud(1).size()) {
+      fprintf(stderr, "LoamPipeline differs from the three stage objects (%d pose entries)\n", chain_mismatch);
+      return 7;
+    }
   } catch (const coopermap::Error& e) {
     fprintf(stderr, "coopermap error %d: %s\n", e.code, e.what());
     return 1;

@@ -1068,13 +1068,24 @@ void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaSt
   CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, sums);
 }
 
+// odometry correspondence kernels: a warp takes 32 >> spread query slots; thinned out, down to one query per warp, while the launch
+// stays below a few warps per SM sub-partition (see launch_odom_corr_batch)
+static int odom_spread(long long slots) {
+  static const int forced = getenv("COOPERMAP_ODOM_SPREAD") ? atoi(getenv("COOPERMAP_ODOM_SPREAD")) : -1;
+  if (forced >= 0) return forced > 5 ? 5 : forced;
+  int spread = 0;
+  while (spread < 5 && (slots << (spread + 1)) / 32 <= 148 * 4 * 8) spread++;
+  return spread;
+}
 void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
   OdomArgs a;
   a.sharp = o.sharp; a.flat = o.flat; a.n_sharp = o.n_sharp; a.n_flat = o.n_flat;
   a.last_corner = o.last_corner; a.last_surf = o.last_surf; a.bound_corner = o.bound_corner; a.bound_surf = o.bound_surf;
-  a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter; a.spread = 0;
+  a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter;
   const int nT = ((o.n_sharp + 31) & ~31) + o.n_flat;
-  CM_LAUNCH(odom_corr_kernel, (nT + 127) / 128 > 0 ? (nT + 127) / 128 : 1, 128, 0, stream, a);
+  a.spread = odom_spread((long long)nT);
+  const long long nthreads = (long long)((nT + 31) / 32) * 32 << a.spread;
+  CM_LAUNCH(odom_corr_kernel, (unsigned int)((nthreads + 127) / 128 > 0 ? (nthreads + 127) / 128 : 1), 128, 0, stream, a);
 }
 void GridBatch::create(int nstreams_, int cap_, cudaStream_t stream) {
   nstreams = nstreams_; cap = cap_ > 0 ? cap_ : 1;
@@ -1107,9 +1118,7 @@ void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t str
   // Every fifth evaluation a query walks several rings of the last cloud (thousands of points, its warp working on one query at a
   // time): with 32 queries per warp a single sweep keeps 10 SMs busy for 440 us.  Thin the warps out -- down to one query per warp --
   // while the launch stays below a few warps per SM sub-partition.
-  int spread = 0;
-  while (spread < 5 && (((long long)nT * o.nstreams) << (spread + 1)) / 32 <= 148 * 4 * 8) spread++;
-  if (const char* e = getenv("COOPERMAP_ODOM_SPREAD")) spread = atoi(e);
+  const int spread = odom_spread((long long)nT * o.nstreams);
   b.spread = spread;
   const long long nthreads = (long long)((nT + 31) / 32) * 32 << spread;
   CM_LAUNCH(odom_corr_batch_kernel, dim3((unsigned int)((nthreads + 127) / 128 > 0 ? (nthreads + 127) / 128 : 1), o.nstreams), 128, 0, stream, b);
