@@ -54,3 +54,26 @@ def test_voxel_full_frame_features(ctx, oracle, synth, scene_small):
     for cloud, leaf in ((f["lessFlat"], 0.8), (f["lessSharp"], 0.4), (f["lessFlat"], 1.0)):
         a = ctx.voxel_filter(cloud, leaf); b = oracle.voxel_filter(cloud, leaf)
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 1025, 8191, 8192, 70000])
+def test_voxel_cluster_kernel_equals_single_cta_kernel(ctx, oracle, monkeypatch, n):
+    """The same clouds through vox_cluster_kernel (8 CTAs of a thread-block cluster per cloud, the path for a few clouds) and through
+    vox_segment_kernel (one CTA per cloud, the path for many): byte-identical, and equal to the oracle; sizes around the slice and
+    tile boundaries of the cluster kernel (1024-point tiles, 8 slices), with non-finite points and long runs of one voxel."""
+    rng = np.random.default_rng(100 + n)
+    p = _cloud(rng, n, 30.0)
+    if n > 40:
+        p[5, 0] = np.nan; p[n // 2, 2] = np.inf; p[n - 1, 1] = -np.inf
+        p[n // 3:n // 3 + 20] = p[n // 3]                       # a run of identical points across lanes
+        p[1023:1027, :3] = p[1023, :3]                          # a run that spans a tile boundary (n > 1027 only)
+    outs = {}
+    for force in ("1", "0"):
+        monkeypatch.setenv("COOPERMAP_VOX_CLUSTER", force)
+        outs[force] = [ctx.voxel_filter(p, leaf) for leaf in (0.3, 2.0)] + ctx.voxel_filter_batch([p, p[: n // 2], p[n // 3:]], 0.5)
+    monkeypatch.delenv("COOPERMAP_VOX_CLUSTER")
+    refs = [oracle.voxel_filter(p, 0.3), oracle.voxel_filter(p, 2.0), oracle.voxel_filter(p, 0.5), oracle.voxel_filter(p[: n // 2], 0.5),
+            oracle.voxel_filter(p[n // 3:], 0.5)]
+    for a, b, r in zip(outs["1"], outs["0"], refs):
+        assert a.shape == b.shape == r.shape
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(a.view(np.uint32), r.view(np.uint32))

@@ -673,8 +673,7 @@ static void vox_configure() {
 // a few clouds only (the latency case): a cluster of CTAs per cloud while the clusters fit in two waves (measured on one HDL-64E
 // sweep: 65 us against 185 us for the single CTA); COOPERMAP_VOX_CLUSTER=0 / 1 forces the choice
 static bool vox_use_cluster(int nclouds) {
-  static const int forced = getenv("COOPERMAP_VOX_CLUSTER") ? atoi(getenv("COOPERMAP_VOX_CLUSTER")) : -1;
-  if (forced >= 0) return forced != 0;
+  if (const char* e = getenv("COOPERMAP_VOX_CLUSTER")) return atoi(e) != 0;   // read per call: the tests run both kernels in one process
   return nclouds * VC <= 2 * 148;
 }
 
