@@ -44,6 +44,22 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints its version
+# when torch.distributed creates the communicator) are sent to stderr for the whole run, the result goes to the saved descriptor
+def claim_stdout():
+    # (kept on the sys module: bench_configs.py imports this file a second time under the name `bench`)
+    if getattr(sys, "_coopermap_result_out", None) is None:
+        sys.stdout.flush()
+        sys._coopermap_result_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = getattr(sys, "_coopermap_result_out", None) or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------------------------------------------
@@ -283,7 +299,7 @@ def run_reference(args, synth, rank):
             "p50_latency_ms": 1e3 * float(np.median(per_frame[:, 0])),
             "stage1_alone_p50_ms": 1e3 * float(np.median(per_frame[:, 1])), "stage3_alone_p50_ms": 1e3 * float(np.median(per_frame[:, 2])),
             "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_config2(args, synth, rank, world, local_rank):
@@ -645,13 +661,14 @@ def run_config2(args, synth, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -112,7 +112,7 @@ def run_config3(args, synth, rank, world, local_rank):
                      dict(streams_total=TOTAL, streams_per_gpu=S, points_per_sweep=NP, converged_frac=conv, parallelism="streams sharded over ranks, no collective"),
                      e2e={"value": TOTAL * K * NP / (ms_e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": int(S * NP * 16 + S * 48),
                           "d2h_bytes_per_step": int(S * 48 + S * C.sizeof(cmb.MatchStats))}, gpu_launches=int(launches))
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -210,7 +210,7 @@ def run_config4(args, synth, rank, world, local_rank):
                           parallelism="one map over all ranks; every rank evaluates the queries in its cubes"),
                      e2e={"value": K * NP / (ms_e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": int(NP * 16 + 48) * world,
                           "d2h_bytes_per_step": int(48 + C.sizeof(cmb.MatchStats)) * world}, gpu_launches=int(launches))
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -322,7 +322,7 @@ def run_config1(args, synth, rank, world, local_rank):
                             "sample": "%d sweeps through the oracle chain (scan registration, odometry, mapping; -O3, reference nanoflann) on one core, p50 %.1f ms"
                                       % (ncpu, 1e3 * float(np.median(tc[2:])))}
     line["p50_latency_ms"] = 1e3 * float(np.median(tg[warm:]))
-    print(json.dumps(line), flush=True)
+    B.emit(line)
     for c in (c_sr, c_od, c_mp):
         c.close()
 
@@ -360,7 +360,7 @@ def run_config5(args, synth, rank, world, local_rank):
     line = _line(args, 1, rate, 1e3 * float(np.mean(tg[warm:])), "weak",
                  "config 5: tilted RPLidar-A2-like sweeps (12 revolutions x 800 points, +-30 deg nod), sparse scenes (corridor, single wall, open field), scan registration + scan-to-map through the host-buffer C ABI",
                  dict(streams=S, points_per_sweep=12 * 800, outcomes=seen, p50_ms=1e3 * float(np.median(tg[warm:]))), gpu_launches=int(ctx.launch_count() - l0))
-    print(json.dumps(line), flush=True)
+    B.emit(line)
     ctx.close()
 
 
