@@ -35,7 +35,7 @@ struct OdomBatch {
   std::vector<int> inited, n_last_c, n_last_s;
   std::vector<float> tf;            // [S][6] _transform
   std::vector<HostIso> Tsum;        // _Tsum
-  DeviceBuffer sharp, flat, last_c, last_s, ints, ind, rows, state, sums, pose, tfinv;
+  DeviceBuffer sharp, flat, last_c, last_s, ints, ind, rows, state, sums, pose, tfinv, box_c, box_s;   // box_*: chunk boxes of the last clouds
   GridBatch grid_c, grid_s;
   OdomGraphCache graphs;
 };

@@ -242,7 +242,9 @@ struct OdomBatchLaunch {
   const float4* last_corner; const float4* last_surf; int cap_last_corner, cap_last_surf; const int* bound_corner; const int* bound_surf;
   const GridView* grid_corner; const GridView* grid_surf;
   const MatchState* state; int* ind; RowOut* rows;
+  const void* box_corner = nullptr; const void* box_surf = nullptr; int box_cap_corner = 0, box_cap_surf = 0;   // chunk boxes (cm_odom.inl), optional
 };
+void launch_odom_boxes_batch(const float4* d_cloud, int cap, const int* d_n, int max_n, int nstreams, void* d_boxes, int box_cap, cudaStream_t stream);
 void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t stream, const int* d_iter = nullptr);
 // The batch odometry's Gauss-Newton loop as ONE submission: init -> WHILE { correspondences + rows, reduction, 6x6 step, advance },
 // as many evaluations as the slowest stream needs (25 x 3 launches otherwise, most of them empty once the streams have converged).

@@ -1073,8 +1073,12 @@ void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaSt
 static int odom_spread(long long slots) {
   static const int forced = getenv("COOPERMAP_ODOM_SPREAD") ? atoi(getenv("COOPERMAP_ODOM_SPREAD")) : -1;
   if (forced >= 0) return forced > 5 ? 5 : forced;
+  // (slots are padded launch sizes, about three per real query; measured on VLP-16 chains, correspondence kernels per step at 1 / 2 /
+  // 4 / 8 / 16 / 32 queries per warp: 32 streams 1722 / 1124 / 863 / 820 / 978 us from 32 down to 2, 8 streams 638 / 532 at 8 / 4 and 594 at 1)
+  const long long warps = slots / 32;
+  if ((warps << 5) <= 4096) return 5;   // one sweep: one query per warp (235 us per sweep against 259 / 304 at 2 / 4 queries per warp)
   int spread = 0;
-  while (spread < 5 && (slots << (spread + 1)) / 32 <= 148 * 4 * 8) spread++;
+  while (spread < 3 && (warps << (spread + 1)) <= 148 * 4 * 64 + 4096) spread++;   // batches: 4 queries per warp while the launch stays below ~64 warps per sub-partition
   return spread;
 }
 void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
@@ -1082,6 +1086,7 @@ void launch_odom_corr(const OdomLaunch& o, int iter, cudaStream_t stream) {
   a.sharp = o.sharp; a.flat = o.flat; a.n_sharp = o.n_sharp; a.n_flat = o.n_flat;
   a.last_corner = o.last_corner; a.last_surf = o.last_surf; a.bound_corner = o.bound_corner; a.bound_surf = o.bound_surf;
   a.grid_corner = o.grid_corner; a.grid_surf = o.grid_surf; a.state = o.state; a.ind = o.ind; a.rows = o.rows; a.iter = iter;
+  a.box_corner = nullptr; a.box_surf = nullptr;
   const int nT = ((o.n_sharp + 31) & ~31) + o.n_flat;
   a.spread = odom_spread((long long)nT);
   const long long nthreads = (long long)((nT + 31) / 32) * 32 << a.spread;
@@ -1114,6 +1119,7 @@ void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t str
   b.last_corner = o.last_corner; b.last_surf = o.last_surf; b.cap_last_corner = o.cap_last_corner; b.cap_last_surf = o.cap_last_surf;
   b.bound_corner = o.bound_corner; b.bound_surf = o.bound_surf; b.grid_corner = o.grid_corner; b.grid_surf = o.grid_surf;
   b.state = o.state; b.ind = o.ind; b.rows = o.rows; b.iter = iter;
+  b.box_corner = (const ChunkBox*)o.box_corner; b.box_surf = (const ChunkBox*)o.box_surf; b.box_cap_corner = o.box_cap_corner; b.box_cap_surf = o.box_cap_surf;
   const int nT = ((o.max_sharp + 31) & ~31) + o.max_flat;
   // Every fifth evaluation a query walks several rings of the last cloud (thousands of points, its warp working on one query at a
   // time): with 32 queries per warp a single sweep keeps 10 SMs busy for 440 us.  Thin the warps out -- down to one query per warp --
@@ -1122,6 +1128,10 @@ void launch_odom_corr_batch(const OdomBatchLaunch& o, int iter, cudaStream_t str
   b.spread = spread;
   const long long nthreads = (long long)((nT + 31) / 32) * 32 << spread;
   CM_LAUNCH(odom_corr_batch_kernel, dim3((unsigned int)((nthreads + 127) / 128 > 0 ? (nthreads + 127) / 128 : 1), o.nstreams), 128, 0, stream, b);
+}
+void launch_odom_boxes_batch(const float4* d_cloud, int cap, const int* d_n, int max_n, int nstreams, void* d_boxes, int box_cap, cudaStream_t stream) {
+  const int nb = (max_n + 31) / 32;   // chunks that can hold points (the others are never looked at: the walks stop at n)
+  if (nb > 0) CM_LAUNCH(odom_boxes_batch_kernel, dim3((nb * 32 + 127) / 128, nstreams), 128, 0, stream, d_cloud, cap, d_n, (ChunkBox*)d_boxes, box_cap);
 }
 void launch_odom_gate(MatchState* d_state, const int* d_active, int nstreams, cudaStream_t stream) {
   CM_LAUNCH(odom_gate_kernel, (nstreams + 63) / 64, 64, 0, stream, d_state, d_active, nstreams);
@@ -1238,7 +1248,7 @@ bool OdomGraphCache::launch(const MatchLaunch& m, const OdomBatchLaunch& o, cons
   I(m.nstreams); P(m.corner); P(m.surf); P(m.n_corner); P(m.n_surf); I(m.cap_corner); I(m.cap_surf); P(m.grid_corner); P(m.grid_surf);
   P(m.pose_in); P(m.state); P(m.rows); P(m.sums); I(m.prm.max_iterations); P(d_active);
   P(o.last_corner); P(o.last_surf); I(o.cap_last_corner); I(o.cap_last_surf); P(o.bound_corner); P(o.bound_surf); P(o.ind);
-  I(o.max_sharp); I(o.max_flat);
+  I(o.max_sharp); I(o.max_flat); P(o.box_corner); P(o.box_surf); I(o.box_cap_corner); I(o.box_cap_surf);
   for (size_t i = 0; i < entries.size(); i++) {
     Entry& e = entries[i];
     if (e.key == key) {

@@ -5,7 +5,12 @@
 // (util/feature_utils.h:28-61, 77-95).  The reduction and the 6x6 step are the mapping solver's kernels with the
 // odometry's constants (b = -0.05 d, eigenvalue threshold 10, "< 10 rows -> skip the iteration", NaN guards).
 
+// bounding box + ring range of 32 consecutive points of a last cloud (points [32 b, 32 b + 32)): lets the ring walks below skip the
+// chunks that cannot hold a correspondent (all farther than the 5 m gate) without changing what the walk finds
+struct ChunkBox { float mnx, mny, mnz; int ring_min; float mxx, mxy, mxz; int ring_max; };
+
 struct OdomArgs {
+  const ChunkBox* box_corner; const ChunkBox* box_surf;   // optional (NULL: every point of the walk is visited)
   const float4* sharp; const float4* flat; int n_sharp, n_flat;
   const float4* last_corner; const float4* last_surf; int bound_corner, bound_surf;   // scan bounds (clamped)
   GridView grid_corner, grid_surf;      // over the last clouds, pts[].w = original index
@@ -74,37 +79,64 @@ __device__ __forceinline__ void odom_corr_body(const OdomArgs& a, uint4* rng, Po
       const int scan = (int)cloud[c0].w;
       float d2 = 25.f, d3 = 25.f;
       unsigned int v2 = 0xFFFFFFFFu, v3 = 0xFFFFFFFFu;   // visit rank of the lane's candidate: forward 1, 2, ..; backward 0x40000000 + 1, 2, ..
-      for (int j0 = c0 + 1; j0 < bound; j0 += 32) {
-        const int j = j0 + lane;
-        const bool in = j < bound;
+      const ChunkBox* boxes = isCorner ? a.box_corner : a.box_surf;
+      // one chunk of 32 consecutive points, lane order = visit order; returns the ballot of the points past the ring limit (the walk
+      // ends at the first of them), the points before it are candidates
+      auto visit = [&](int jbase, bool forward) -> unsigned int {
+        const int j = forward ? jbase + lane : jbase - lane;
+        const bool in = forward ? (j > c0 && j < bound) : (j >= 0 && j < c0);
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in) q = cloud[j];
         const int ring = (int)q.w;
-        const unsigned int brk = __ballot_sync(FULL, in && (double)ring > (double)scan + 2.5);
+        const unsigned int brk = __ballot_sync(FULL, in && (forward ? (double)ring > (double)scan + 2.5 : (double)ring < (double)scan - 2.5));
         if (in && (brk == 0 || lane < __ffs(brk) - 1)) {
           const float d = odom_sqdiff(q, bx, by, bz);
-          const unsigned int v = (unsigned int)(j - c0);
-          if (isCorner) { if (ring > scan && d < d2) { d2 = d; v2 = v; } }
-          else if (ring <= scan) { if (d < d2) { d2 = d; v2 = v; } }
+          const unsigned int v = forward ? (unsigned int)(j - c0) : 0x40000000u + (unsigned int)(c0 - j);
+          const bool same_side = forward ? ring <= scan : ring >= scan;   // surf: the second point, else the third (LaserOdometry.cpp:441-474)
+          if (isCorner) { if ((forward ? ring > scan : ring < scan) && d < d2) { d2 = d; v2 = v; } }
+          else if (same_side) { if (d < d2) { d2 = d; v2 = v; } }
           else { if (d < d3) { d3 = d; v3 = v; } }
         }
-        if (brk) break;
-      }
-      for (int j0 = c0 - 1; j0 >= 0; j0 -= 32) {
-        const int j = j0 - lane;
-        const bool in = j >= 0;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) q = cloud[j];
-        const int ring = (int)q.w;
-        const unsigned int brk = __ballot_sync(FULL, in && (double)ring < (double)scan - 2.5);
-        if (in && (brk == 0 || lane < __ffs(brk) - 1)) {
-          const float d = odom_sqdiff(q, bx, by, bz);
-          const unsigned int v = 0x40000000u + (unsigned int)(c0 - j);
-          if (isCorner) { if (ring < scan && d < d2) { d2 = d; v2 = v; } }
-          else if (ring >= scan) { if (d < d2) { d2 = d; v2 = v; } }
-          else { if (d < d3) { d3 = d; v3 = v; } }
+        return brk;
+      };
+      if (!boxes) {
+        for (int j0 = c0 + 1; j0 < bound; j0 += 32) if (visit(j0, true)) break;
+        for (int j0 = c0 - 1; j0 >= 0; j0 -= 32) if (visit(j0, false)) break;
+      } else {
+        // 32 chunk boxes per round: a chunk is visited when it is within the gate OR holds a point past the ring limit (the walk may
+        // end inside it); a far chunk without such a point contributes nothing and is skipped.  (0.9999: the box distance is a float
+        // lower bound of the point distances it stands for.)
+        auto wanted = [&](int cb, bool have, bool forward) -> bool {
+          if (!have) return false;
+          const ChunkBox b = boxes[cb];
+          const float ex = fmaxf(fmaxf(b.mnx - bx, bx - b.mxx), 0.f), ey = fmaxf(fmaxf(b.mny - by, by - b.mxy), 0.f), ez = fmaxf(fmaxf(b.mnz - bz, bz - b.mxz), 0.f);
+          const bool near = (ex * ex + ey * ey + ez * ez) * 0.9999f < 25.f;
+          const bool limit = forward ? b.ring_max > scan + 2 : b.ring_min < scan - 2;
+          return near || limit;
+        };
+        bool stop = false;
+        if (c0 + 1 < bound) {
+          const int cbl = (bound - 1) >> 5;
+          for (int cb0 = (c0 + 1) >> 5; cb0 <= cbl && !stop; cb0 += 32) {
+            unsigned int todo = __ballot_sync(FULL, wanted(cb0 + lane, cb0 + lane <= cbl, true));
+            while (todo) {
+              const int kq = __ffs(todo) - 1;
+              todo &= todo - 1;
+              if (visit((cb0 + kq) << 5, true)) { stop = true; break; }
+            }
+          }
         }
-        if (brk) break;
+        stop = false;
+        if (c0 > 0) {
+          for (int cb0 = (c0 - 1) >> 5; cb0 >= 0 && !stop; cb0 -= 32) {
+            unsigned int todo = __ballot_sync(FULL, wanted(cb0 - lane, cb0 - lane >= 0, false));
+            while (todo) {
+              const int kq = __ffs(todo) - 1;
+              todo &= todo - 1;
+              if (visit(((cb0 - kq) << 5) + 31, false)) { stop = true; break; }
+            }
+          }
+        }
       }
       // merge: smallest distance, earliest visit among equals (squared distances are >= 0: bit order = value order)
       int w2 = -1, w3 = -1;
@@ -199,6 +231,7 @@ struct OdomBatchArgs {
   const MatchState* state; int* ind; RowOut* rows; int iter;
   const int* iter_dev;   // optional: overrides iter (graph WHILE loop)
   int spread;
+  const ChunkBox* box_corner; const ChunkBox* box_surf; int box_cap_corner, box_cap_surf;   // [S][box_cap_*] (optional)
 };
 __global__ void __launch_bounds__(128) odom_corr_batch_kernel(OdomBatchArgs b) {
   __shared__ uint4 rng[8 * 128];
@@ -216,7 +249,40 @@ __global__ void __launch_bounds__(128) odom_corr_batch_kernel(OdomBatchArgs b) {
   a.rows = b.rows + (size_t)s * (b.cap_sharp + b.cap_flat);
   a.iter = b.iter_dev ? *b.iter_dev : b.iter;
   a.spread = b.spread;
+  a.box_corner = b.box_corner ? b.box_corner + (size_t)s * b.box_cap_corner : nullptr;
+  a.box_surf = b.box_surf ? b.box_surf + (size_t)s * b.box_cap_surf : nullptr;
   odom_corr_body(a, rng, kc, tf);
+}
+
+// chunk boxes of a batch of last clouds: one warp per chunk of 32 points
+__global__ void __launch_bounds__(128) odom_boxes_batch_kernel(const float4* __restrict__ cloud, int cap, const int* __restrict__ n, ChunkBox* __restrict__ boxes,
+                                                               int box_cap) {
+  const int s = blockIdx.y, lane = threadIdx.x & 31;
+  const int cb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cb >= box_cap) return;
+  const int j = cb * 32 + lane;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int rmin = 0x7fffffff, rmax = -0x7fffffff;
+  if (j < n[s]) {
+    const float4 q = cloud[(size_t)s * cap + j];
+    mn[0] = mx[0] = q.x; mn[1] = mx[1] = q.y; mn[2] = mx[2] = q.z;
+    rmin = rmax = (int)q.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  }
+  if (lane == 0) {
+    ChunkBox b;
+    b.mnx = mn[0]; b.mny = mn[1]; b.mnz = mn[2]; b.ring_min = rmin; b.mxx = mx[0]; b.mxy = mx[1]; b.mxz = mx[2]; b.ring_max = rmax;
+    boxes[(size_t)s * box_cap + cb] = b;
+  }
 }
 
 // transformToEnd for a batch: cloud [S][cap], tf6 [S][6], inv12 [S][12]; streams with on[s] == 0 keep their cloud as it is

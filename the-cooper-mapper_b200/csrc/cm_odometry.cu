@@ -171,6 +171,7 @@ int cm_odometry_batch_create(cm_ctx* ctx, int nstreams, int cap_sharp, int cap_l
     b.rows.reserve(S * ((size_t)cap_sharp + cap_flat) * sizeof(RowOut));
     b.state.reserve(S * sizeof(MatchState)); b.sums.reserve(S * 32 * sizeof(double)); b.pose.reserve(S * 6 * sizeof(float));
     b.tfinv.reserve(S * 18 * sizeof(float));
+    b.box_c.reserve(S * (size_t)((cap_less_sharp + 31) / 32) * 32); b.box_s.reserve(S * (size_t)((cap_less_flat + 31) / 32) * 32);   // 32 bytes per chunk of 32 points
     b.grid_c.create(nstreams, cap_less_sharp, ctx->stream); b.grid_s.create(nstreams, cap_less_flat, ctx->stream);
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   } catch (const CudaError& e) {
@@ -243,6 +244,8 @@ int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, cons
       o.max_sharp = max_sharp; o.max_flat = max_flat;
       o.last_corner = (const float4*)b.last_c.p; o.last_surf = (const float4*)b.last_s.p; o.cap_last_corner = b.cap_less_sharp; o.cap_last_surf = b.cap_less_flat;
       o.bound_corner = d_i + 2 * S; o.bound_surf = d_i + 3 * S;
+      static const bool no_boxes = getenv("COOPERMAP_ODOM_NO_BOXES") != nullptr;   // development: the plain ring walks
+      if (!no_boxes) { o.box_corner = b.box_c.p; o.box_surf = b.box_s.p; o.box_cap_corner = (b.cap_less_sharp + 31) / 32; o.box_cap_surf = (b.cap_less_flat + 31) / 32; }
       o.grid_corner = m.grid_corner; o.grid_surf = m.grid_surf; o.state = m.state; o.ind = (int*)b.ind.p; o.rows = m.rows;
       // launch sizes in whole tiles: the loop's graph is keyed by them and then repeats from frame to frame
       o.max_sharp = (max_sharp + 1023) & ~1023; o.max_flat = (max_flat + 1023) & ~1023;
@@ -284,6 +287,8 @@ int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, cons
     launch_odom_to_end_batch((float4*)b.last_s.p, b.cap_less_flat, d_i + 6 * S, max_lf, S, d_tf6, d_inv, d_i + 7 * S, st);
     b.grid_c.build((const float4*)b.last_c.p, d_i + 5 * S, std::max(max_ls, 1), d_i + 8 * S, odom_cell(true), 25.f, st);
     b.grid_s.build((const float4*)b.last_s.p, d_i + 6 * S, std::max(max_lf, 1), d_i + 8 * S, odom_cell(false), 25.f, st);
+    launch_odom_boxes_batch((const float4*)b.last_c.p, b.cap_less_sharp, d_i + 5 * S, max_ls, S, b.box_c.p, (b.cap_less_sharp + 31) / 32, st);
+    launch_odom_boxes_batch((const float4*)b.last_s.p, b.cap_less_flat, d_i + 6 * S, max_lf, S, b.box_s.p, (b.cap_less_flat + 31) / 32, st);
     if (corner_last) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(corner_last, b.last_c.p, (size_t)S * b.cap_less_sharp * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     if (surf_last) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(surf_last, b.last_s.p, (size_t)S * b.cap_less_flat * sizeof(cm_point), cudaMemcpyDeviceToHost, st));
     CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
