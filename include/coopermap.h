@@ -235,7 +235,8 @@ int cm_pipeline_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, 
                          cm_match_stats* stats);
 /* The same for sweeps the way a nodelet holds them after pcl::fromROSMsg (util/ros_utils.h:27-35): ONE cloud per stream,
  * clouds[s] = &cloud_s->points[0], in ordinary (pageable) host memory, points `stride` bytes apart with x, y, z as three floats at
- * offset 0 -- stride 32 for pcl::PointXYZI, 48 for PointXYZINormal, 16 for cm_point, 12 for packed coordinates.  The library
+ * offset 0 -- stride 32 for pcl::PointXYZI, 48 for PointXYZINormal, 16 for cm_point, 12 for packed coordinates, the point_step of a
+ * sensor_msgs::PointCloud2 data buffer (any value >= 12, no alignment required).  The library
  * gathers the coordinates into its own pinned staging buffers with worker threads (COOPERMAP_STAGE_THREADS, default: the cores
  * of the calling thread's affinity mask, at most 16), uploads 12 bytes per point chunk by chunk while the next chunk is being
  * packed, and expands them on the device; the intensity is not transferred (scan registration replaces it with ring + relTime,

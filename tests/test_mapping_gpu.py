@@ -247,7 +247,7 @@ def test_surround_and_full_map_clouds(cmb, oracle, synth):
 
 def test_strided_pageable_sweeps_match_packed_entry(cmb, synth):
     """cm_pipeline_prefetch_strided_host / cm_pipeline_step_strided_host: one pageable cloud per stream with the 32-byte point
-    stride of pcl::PointXYZI (and 48 / 12 byte strides) must give the poses and the map of the packed 16-byte entry, bit for bit,
+    stride of pcl::PointXYZI (and 48 / 12 / 22 byte strides -- 22 = a Velodyne PointCloud2 point_step) must give the poses and the map of the packed 16-byte entry, bit for bit,
     prefetched or not."""
     import ctypes as C
     sc = synth.make_scene(seed=91, extent=40.0, n_boxes=12, n_poles=10)
@@ -257,6 +257,10 @@ def test_strided_pageable_sweeps_match_packed_entry(cmb, synth):
     def pcl_cloud(fr, stride):
         """(rows, cols, 4) float32 -> flat array of rows*cols points `stride` bytes apart (x, y, z at offset 0, junk elsewhere)"""
         n = fr.shape[0] * fr.shape[1]
+        if stride % 4:                                    # a PointCloud2 point_step of 22: the floats are not aligned
+            raw = np.full((n, stride), 0x5A, np.uint8)
+            raw[:, :12] = np.ascontiguousarray(fr.reshape(n, 4)[:, :3]).view(np.uint8).reshape(n, 12)
+            return raw
         buf = np.full((n, stride // 4), 7.25, np.float32)
         buf[:, :3] = fr.reshape(n, 4)[:, :3]
         if stride >= 32:
@@ -286,7 +290,7 @@ def test_strided_pageable_sweeps_match_packed_entry(cmb, synth):
         return out, maps
 
     ref, maps_ref = run(0)
-    for stride in (32, 48, 12):
+    for stride in (32, 48, 12, 22):
         got, maps = run(stride)
         for (ma, ia), (mb, ib) in zip(ref, got):
             assert np.array_equal(ma, mb) and ia == ib, stride

@@ -864,8 +864,8 @@ int cm_pipeline_chain_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int 
 int cm_pipeline_prefetch_host(cm_ctx* ctx, const cm_point* frames, int rows, int cols) { return pipeline_prefetch(ctx, frames, rows, cols, true); }
 int cm_pipeline_prefetch_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols) { return pipeline_prefetch(ctx, d_frames, rows, cols, false); }
 static bool strided_args_ok(cm_ctx* ctx, const void* const* clouds, size_t stride) {
-  if (!clouds || stride < 12 || (stride & 3)) return false;
-  for (int s = 0; s < ctx->map_streams; s++) if (!clouds[s] || ((uintptr_t)clouds[s] & 3)) return false;
+  if (!clouds || stride < 12) return false;   // any stride and alignment: a PointCloud2 point_step of 22 leaves the floats unaligned
+  for (int s = 0; s < ctx->map_streams; s++) if (!clouds[s]) return false;
   return true;
 }
 int cm_pipeline_prefetch_strided_host(cm_ctx* ctx, const void* const* clouds, size_t stride, int rows, int cols) {

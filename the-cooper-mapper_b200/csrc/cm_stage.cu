@@ -90,17 +90,14 @@ void stage_pool_destroy(cm_ctx* ctx) { delete ctx->stage_pool; ctx->stage_pool =
 
 // x, y, z of `count` points, `stride` bytes apart, packed to 12 bytes each
 static void pack_xyz(const unsigned char* src, size_t stride, size_t count, float* dst) {
-  if (stride == 32) {   // pcl::PointXYZI: two points per 64-byte line, read 12 of every 32 bytes
+  if (stride == 32 && ((uintptr_t)src & 3) == 0) {   // pcl::PointXYZI: two points per 64-byte line, read 12 of every 32 bytes
     for (size_t i = 0; i < count; i++) {
       const float* p = reinterpret_cast<const float*>(src + i * 32);
       dst[3 * i] = p[0]; dst[3 * i + 1] = p[1]; dst[3 * i + 2] = p[2];
     }
     return;
   }
-  for (size_t i = 0; i < count; i++) {
-    const float* p = reinterpret_cast<const float*>(src + i * stride);
-    dst[3 * i] = p[0]; dst[3 * i + 1] = p[1]; dst[3 * i + 2] = p[2];
-  }
+  for (size_t i = 0; i < count; i++) memcpy(dst + 3 * i, src + i * stride, 12);   // any stride (a PointCloud2 point_step of 22: unaligned floats)
 }
 
 // packed xyz (12 B) -> float4 (x, y, z, 0): four points per thread, three 16-byte loads and four 16-byte stores
