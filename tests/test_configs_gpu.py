@@ -205,6 +205,48 @@ def test_chain_step_equals_the_three_stages(cmb, oracle, synth):
     ctx.close()
 
 
+def test_chain_step_device_sweeps_and_prefetch_equal_host_sweeps(cmb, synth):
+    """cm_pipeline_chain_step_dev (sweeps already in device memory) and a chain step whose sweep was announced with
+    cm_pipeline_prefetch_host give the poses of the plain host call, bit for bit."""
+    import torch
+    sc = synth.make_scene(seed=77, extent=50.0, n_boxes=18, n_poles=14)
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    S, NF, rows, cols = 2, 6, 16, 900
+    trajs = [synth.trajectory(NF, speed=0.1, yaw_amp=0.02), synth.trajectory(NF, speed=0.08, yaw_amp=-0.02)]
+    frames = [np.stack([synth.simulate_scan(sc, trajs[s][k][0], trajs[s][k][1], "VLP-16", seed=0x3000 + 50 * s + k, cols=cols) for s in range(S)]).astype(np.float32)
+              for k in range(NF)]
+    results = {}
+    for mode in ("host", "dev", "prefetch"):
+        ctx = cmb.Context(**cfg)
+        ctx.mapping_create(S, 100000, 600000)
+        ctx.pipeline_chain_create(rows, cols)
+        od = np.empty((S, 12), np.float32); mp = np.empty((S, 12), np.float32); ost = (cmb.OdomStats * S)(); mst = (cmb.MatchStats * S)()
+        pinned = [torch.from_numpy(f).pin_memory().numpy() for f in frames]
+        out = []
+        for k in range(NF):
+            if mode == "host":
+                ctx.pipeline_chain_step_packed(frames[k], od, mp, ost, mst)
+            elif mode == "dev":
+                d = torch.from_numpy(frames[k]).cuda()
+                torch.cuda.synchronize()
+                ctx.pipeline_chain_step_dev(d.data_ptr(), rows, cols, od, mp, ost, mst)
+            else:
+                if k == 0:
+                    ctx.pipeline_prefetch(pinned[0])
+                if k + 1 < NF:
+                    ctx.pipeline_prefetch(pinned[k + 1])                     # the next sweep uploads while this one is registered
+                ctx.pipeline_chain_step_packed(pinned[k], od, mp, ost, mst)
+            out.append((od.copy(), mp.copy(), [ost[s].iterations for s in range(S)], [mst[s].iterations for s in range(S)]))
+        ctx.mapping_sync()
+        results[mode] = (out, [ctx.map_export_sorted(s, cls)[0] for s in range(S) for cls in (0, 1)])
+        ctx.close()
+    for mode in ("dev", "prefetch"):
+        for a, b in zip(results["host"][0], results[mode][0]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3], mode
+        for a, b in zip(results["host"][1], results[mode][1]):
+            assert _same(a, b), mode
+
+
 def test_knn5_full_size_vs_nanoflann(cmb, oracle, synth):
     """Exact 5-NN at the headline size: the ~1M-point surf map of the bench workload, 20,000 queries, against the reference's
     own KD-tree (nanoflann) -- neighbour sets and float distances identical, both map cell sizes (surf and corner default)."""

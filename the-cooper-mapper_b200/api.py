@@ -430,6 +430,11 @@ class Context:
                        converged=bool(ost[s].converged)) for s in range(S)]
         return odoms, isos, ostats, stats
 
+    def pipeline_chain_step_dev(self, frames_dev_ptr, rows, cols, odom_out, mapped_out, ostats_out, mstats_out):
+        """the same with the sweeps already in device memory ([S][rows][cols] float4, raw pointer)"""
+        return self._check(self.L.cm_pipeline_chain_step_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols), _ptr(odom_out),
+                                                             _ptr(mapped_out), ostats_out, mstats_out))
+
     def pipeline_chain_step_packed(self, frames, odom_out, mapped_out, ostats_out, mstats_out):
         fr = frames
         return self._check(self.L.cm_pipeline_chain_step_host(self.h, _ptr(fr), C.c_int(fr.shape[1]), C.c_int(fr.shape[2]), _ptr(odom_out),
