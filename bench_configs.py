@@ -304,13 +304,17 @@ def run_config1(args, synth, rank, world, local_rank):
     pinned = [torch.from_numpy(np.ascontiguousarray(fstack[[(k + s) % NF if (k + s) < NF else NF - 1 for s in range(SB)]])).pin_memory().numpy()
               for k in range(NB)]
     tcn = []
+    cc.pipeline_prefetch(pinned[0])
     for k in range(NB):
         t0 = time.perf_counter()
+        if k + 1 < NB:
+            cc.pipeline_prefetch(pinned[k + 1])     # the next sweep set uploads and is scan-registered beside this one's odometry + mapping
         cc.pipeline_chain_step_packed(pinned[k], od_o, mp_o, ost, mst)
         tcn.append(time.perf_counter() - t0)
     cc.mapping_sync()
     batched["device_chain"] = {"value": SB * 28800 / float(np.mean(tcn[warm:])), "unit": "points/s", "ms_per_step": 1e3 * float(np.mean(tcn[warm:])),
-                               "note": "cm_pipeline_chain_step_host: pinned sweeps in, two poses per stream out, feature clouds never leave the device"}
+                               "note": "cm_pipeline_prefetch_host (next sweeps) + cm_pipeline_chain_step_host: pinned sweeps in, two poses per stream out, "
+                                       "feature clouds never leave the device"}
     cc.close()
     line = _line(args, 1, rate, 1e3 * float(np.mean(tg[warm:])), "weak",
                  "config 1: VLP-16 16x1800 sequence, ONE stream, scan registration -> laserOdometry -> laserMapping in one call per sweep (cm_pipeline_chain_step_host: host sweep in, two poses out)",
