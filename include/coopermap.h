@@ -337,6 +337,14 @@ int cm_pipeline_chain_step_host(cm_ctx* ctx, const cm_point* frames, int rows, i
                                 cm_match_stats* mstats);
 int cm_pipeline_chain_step_dev(cm_ctx* ctx, const void* d_frames, int rows, int cols, cm_iso* odom, cm_iso* mapped, cm_odom_stats* ostats,
                                cm_match_stats* mstats);
+/* The same chain for ONE stream (cm_mapping_create(ctx, 1, ...)) fed with RAW sweeps, the unorganised azimuth-major cloud a Velodyne /
+ * Pandar driver publishes: MultiScanRegistration::process (MultiScanRegistration.cpp:95-200; lidar 0 VLP-16, 1 HDL-32, 2 HDL-64E,
+ * 3 Pandar40) runs on the device in front of the three stages.  max_points: the largest sweep.  scan_time >= 0 de-skews with the IMU
+ * states given to cm_imu_push_host (ScanRegistration.cpp:89-188), < 0: no IMU.  Results are those of cm_scanreg_sweep_host (or
+ * _imu_host) + cm_odometry_batch_process_host + cm_mapping_process_host. */
+int cm_pipeline_chain_sweep_create(cm_ctx* ctx, size_t max_points);
+int cm_pipeline_chain_step_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, double scan_time, cm_iso* odom, cm_iso* mapped,
+                                      cm_odom_stats* ostats, cm_match_stats* mstats);
 
 
 /* ---- sharded-map matching (BASELINE config 4: one map split over ranks) ---------------------------------------------------

@@ -212,12 +212,27 @@ class LoamPipeline : public LaserMapping {
     ctx_.check(cm_pipeline_chain_step_host(ctx_.get(), organised.data(), rows_, cols_, &odom_, &mapped, &ostats_, &stats_));
     return mapped;
   }
+  // raw-sweep mode: the unorganised cloud of a spinning LiDAR (MultiScanRegistration in front of the chain); scanTime >= 0 de-skews
+  // with the IMU messages given to handleIMUMessage
+  LoamPipeline(MultiScanRegistration::Lidar lidar, size_t maxPoints, const cm_config& cfg = Context::defaults(), size_t maxCornerPoints = 400000, size_t maxSurfPoints = 4000000)
+      : LaserMapping(cfg, maxCornerPoints, maxSurfPoints), rows_(-1), cols_(0), lidar_((int)lidar) {
+    ctx_.check(cm_pipeline_chain_sweep_create(ctx_.get(), maxPoints));
+  }
+  cm_iso processSweep(const PointCloud& sweep, double scanTime = -1.0) {
+    cm_iso mapped;
+    ctx_.check(cm_pipeline_chain_step_sweep_host(ctx_.get(), sweep.data(), sweep.size(), lidar_, scanTime, &odom_, &mapped, &ostats_, &stats_));
+    return mapped;
+  }
+  void handleIMUMessage(double stamp, double roll, double pitch, double yaw, double ax, double ay, double az) {
+    const cm_imu_sample m = {stamp, roll, pitch, yaw, ax, ay, az};
+    ctx_.check(cm_imu_push_host(ctx_.get(), &m));
+  }
   const cm_iso& odometry() const { return odom_; }
   const cm_odom_stats& odometryStats() const { return ostats_; }
   void sync() { ctx_.check(cm_mapping_sync(ctx_.get())); }
 
  private:
-  int rows_, cols_;
+  int rows_, cols_, lidar_ = 0;
   cm_iso odom_ = cm_iso();
   cm_odom_stats ostats_ = cm_odom_stats();
 };

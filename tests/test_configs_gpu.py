@@ -247,6 +247,35 @@ def test_chain_step_device_sweeps_and_prefetch_equal_host_sweeps(cmb, synth):
             assert _same(a, b), mode
 
 
+def test_raw_sweep_chain_equals_oracle_chain(cmb, oracle, synth):
+    """cm_pipeline_chain_step_sweep_host: the unorganised sweep a driver publishes -> MultiScanRegistration front end -> feature
+    extraction -> odometry -> mapping in one call; poses and the final map are those of the oracle's chain started from
+    oracle.scanreg_sweep (the raw-sweep restatement, MultiScanRegistration.cpp:95-200)."""
+    sc = synth.make_scene(seed=0x5EED0001 & 0xFFFF, extent=60.0, n_boxes=24, n_poles=20)
+    cfg = dict(filter_corner=0.4, filter_surf=0.8, map_filter_corner=0.4, map_filter_surf=0.4)
+    NF = 8
+    ctx = cmb.Context(**cfg)
+    ctx.mapping_create(1, 100000, 800000)
+    ctx.pipeline_chain_sweep_create(16 * 1800)
+    oo = oracle.Odometry()
+    om = oracle.Mapping(map_params=dict(filterCorner=0.4, filterSurf=0.8, mapFilterCorner=0.4, mapFilterSurf=0.4))
+    for k, (R, t) in enumerate(synth.trajectory(NF, speed=0.1, yaw_amp=0.02)):
+        fr = synth.simulate_scan(sc, R, t, "VLP-16", seed=0x4000 + k, cols=1200)
+        sweep = synth.organised_to_sweep(fr)
+        ok = np.where(np.isfinite(sweep[:, 0]))[0]
+        sweep = sweep[ok[0]:ok[-1] + 1]
+        (gR, gt), (mR, mt), ost, mst = ctx.pipeline_chain_step_sweep(sweep, 0)
+        o = oracle.scanreg_sweep(sweep, 0)
+        oo_ = oo.process(o["sharp"], o["lessSharp"], o["flat"], o["lessFlat"])
+        assert np.array_equal(gR, oo_["R"]) and np.array_equal(gt, oo_["t"]), k
+        oR, ot, ostm = om.process(oo_["R"], oo_["t"], oo_["corner_last"], oo_["surf_last"])
+        assert mst["iterations"] == ostm["iterations"], k
+        assert np.array_equal(mR, oR) and np.array_equal(mt, ot), k
+    for cls, which in ((0, 4), (1, 5)):
+        assert _same(ctx.map_export_sorted(0, cls)[0], om.cloud(which))
+    ctx.close()
+
+
 def test_knn5_full_size_vs_nanoflann(cmb, oracle, synth):
     """Exact 5-NN at the headline size: the ~1M-point surf map of the bench workload, 20,000 queries, against the reference's
     own KD-tree (nanoflann) -- neighbour sets and float distances identical, both map cell sizes (surf and corner default)."""

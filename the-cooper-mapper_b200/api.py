@@ -430,6 +430,22 @@ class Context:
                        converged=bool(ost[s].converged)) for s in range(S)]
         return odoms, isos, ostats, stats
 
+    def pipeline_chain_sweep_create(self, max_points):
+        """the chain for ONE stream fed with raw (unorganised) sweeps of at most max_points points"""
+        self._check(self.L.cm_pipeline_chain_sweep_create(self.h, C.c_size_t(max_points)))
+
+    def pipeline_chain_step_sweep(self, sweep, lidar, imu_scan_time=None):
+        """MultiScanRegistration front end -> feature extraction -> odometry -> mapping for one raw sweep (n, 4);
+        returns ((R, t) odometry, (R, t) mapped, odometry stats dict, mapping stats dict)"""
+        sw = _f32(sweep, 4)
+        od = np.empty((1, 12), np.float32); mapped = np.empty((1, 12), np.float32)
+        ost = (OdomStats * 1)(); mst = (MatchStats * 1)()
+        self._check(self.L.cm_pipeline_chain_step_sweep_host(self.h, _ptr(sw), C.c_size_t(len(sw)), C.c_int(lidar),
+                                                             C.c_double(-1.0 if imu_scan_time is None else imu_scan_time), _ptr(od), _ptr(mapped), ost, mst))
+        isos, stats = self._unpack_results(mapped, mst)
+        return ((od[0, :9].reshape(3, 3).copy(), od[0, 9:].copy()), isos[0],
+                dict(iterations=ost[0].iterations, rows=ost[0].rows, matched=bool(ost[0].matched), initialising=bool(ost[0].initialising)), stats[0])
+
     def pipeline_chain_step_dev(self, frames_dev_ptr, rows, cols, odom_out, mapped_out, ostats_out, mstats_out):
         """the same with the sweeps already in device memory ([S][rows][cols] float4, raw pointer)"""
         return self._check(self.L.cm_pipeline_chain_step_dev(self.h, C.c_void_p(frames_dev_ptr), C.c_int(rows), C.c_int(cols), _ptr(odom_out),

@@ -595,7 +595,7 @@ int cm_mapping_local_window_host(cm_ctx* ctx, int* n_frames, size_t* n_corner, s
 // which re-projects them to the sweep end; with instantaneous synthetic sweeps that projection is the identity.)
 // Stage 1 (scan registration into a slot's buffers) only depends on the sweep, so it can be issued ahead of time on the
 // side stream; stage 2 (mapping) consumes the slot on the context's main stream.
-static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* d_frames, int rows, int cols, cudaStream_t st) {
+static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* d_frames, int rows, int cols, cudaStream_t st, const float* d_tags = nullptr) {
   const cm_config& cfg = ctx->cfg;
   const int S = ctx->map_streams;
   const int cap = rows * cols;
@@ -604,8 +604,9 @@ static void pipeline_scanreg(cm_ctx* ctx, cm_ctx::PipeSlot& slot, const float4* 
   ScanRegLaunch L;
   memset(&L, 0, sizeof(L));
   L.nstreams = S; L.rows = rows; L.cols = cols; L.frames = d_frames;
+  L.tags = d_tags;   // ring + relTime of every point (raw sweeps: computed by the front end); NULL: from the column index
   fill_scanreg_params(cfg, L);
-  L.blind_sq_override = -1.f;
+  L.blind_sq_override = d_tags ? 0.f : -1.f;   // raw sweeps: MultiScanRegistration has no blind radius (its front end dropped r^2 < 1e-4 already)
   L.prof = &ctx->prof_sr;
   for (int k = 0; k < 4; k++) { L.out_pts[k] = (float4*)slot.pts[k].p; L.cap[k] = cap; }
   L.out_n = (int*)slot.n.p + 2 * S;   // [S][5], after the [2][S] count rows the mapping stage reads
@@ -835,6 +836,60 @@ static int pipeline_chain_step(cm_ctx* ctx, const void* frames, int rows, int co
     // the counts of the projected clouds sit in the odometry batch's integer block: rows 5 and 6 = [2][S], the layout the mapping stage reads
     return mapping_process_dev(ctx, (const float4*)b.last_c.p, b.cap_less_sharp, (const float4*)b.last_s.p, b.cap_less_flat,
                                (const int*)b.ints.p + 5 * S, max_ls, max_lf, od.data(), mapped, mstats, false);
+  } catch (const CudaError& e) {
+    return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+// The chain for ONE stream fed with RAW spinning-LiDAR sweeps (what the Velodyne driver publishes: an unorganised, azimuth-major
+// cloud): MultiScanRegistration::process (front end on the device, cm_frontend.cu) -> feature extraction -> LaserOdometry ->
+// LaserMapping, nothing but the sweep going up and the two poses coming down.  scan_time >= 0: de-skew with the IMU states pushed
+// with cm_imu_push_host (cm_scanreg_sweep_imu_host); < 0: no IMU.
+int cm_pipeline_chain_sweep_create(cm_ctx* ctx, size_t max_points) {
+  if (!ctx || ctx->map_streams != 1) return fail(ctx, CM_ERR_ARG, "cm_mapping_create(ctx, 1, ...) first: the raw-sweep chain drives one stream");
+  if (max_points == 0 || max_points > 0x7fffffffu) return fail(ctx, CM_ERR_ARG, "bad argument");
+  const int cap = (int)max_points;
+  const int rc = cm_odometry_batch_create(ctx, 1, cap, cap, cap, cap);
+  if (rc != CM_OK) return rc;
+  ctx->chain_rows = -1; ctx->chain_cols = cap;   // rows < 0: raw-sweep mode, chain_cols = point capacity
+  return CM_OK;
+}
+int cm_pipeline_chain_step_sweep_host(cm_ctx* ctx, const cm_point* sweep, size_t n, int lidar, double scan_time, cm_iso* odom, cm_iso* mapped,
+                                      cm_odom_stats* ostats, cm_match_stats* mstats) {
+  float lo, up; int nr;
+  if (!ctx || ctx->map_streams != 1 || ctx->chain_rows != -1 || ctx->obatch.S != 1)
+    return fail(ctx, CM_ERR_ARG, "cm_pipeline_chain_sweep_create has not been called");
+  if ((!sweep && n) || !frontend_mapper(lidar, &lo, &up, &nr) || n > (size_t)ctx->chain_cols) return fail(ctx, CM_ERR_ARG, "bad argument / sweep larger than max_points");
+  try {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    OdomBatch& b = ctx->obatch;
+    int rows = nr, cols = 1;
+    ctx->d_sweep.reserve((n ? n : 1) * sizeof(cm_point));
+    if (n) CM_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sweep.p, sweep, n * sizeof(cm_point), cudaMemcpyHostToDevice, st));
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 first = n ? make_float4(sweep[0].x, sweep[0].y, sweep[0].z, 0.f) : zero;
+    const float4 last = n ? make_float4(sweep[n - 1].x, sweep[n - 1].y, sweep[n - 1].z, 0.f) : zero;
+    ctx->frontend.run((const float4*)ctx->d_sweep.p, (int)n, first, last, lidar, ctx->cfg.scan_period, st, &rows, &cols,
+                      (scan_time >= 0.0 && !ctx->imu.stamp.empty()) ? &ctx->imu : nullptr, scan_time, nullptr);
+    if (scanreg_smem_bytes(cols) > 220 * 1024) return fail(ctx, CM_ERR_UNSUPPORTED, "a ring of this sweep is too long for one CTA");
+    cm_ctx::PipeSlot& slot = ctx->pipe[CM_PIPE_SLOTS];
+    pipeline_scanreg(ctx, slot, (const float4*)ctx->frontend.frame.p, rows, cols, st, (const float*)ctx->frontend.tags.p);
+    int n5[5];
+    CM_CUDA_CHECK(ctx, cudaMemcpyAsync(n5, (const int*)slot.n.p + 2, sizeof(n5), cudaMemcpyDeviceToHost, st));
+    CM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    ctx->last_features = 0;
+    for (int k = 0; k < 4; k++) ctx->last_features += (unsigned long long)n5[k];
+    if (n5[0] > b.cap_sharp || n5[1] > b.cap_less_sharp || n5[2] > b.cap_flat || n5[3] > b.cap_less_flat)
+      return fail(ctx, CM_ERR_CAPACITY, "a feature cloud exceeds the chain's capacity");
+    const size_t pitch = (size_t)rows * cols * sizeof(cm_point);
+    cm_iso od;
+    int rc = odometry_batch_core(ctx, slot.pts[0].p, pitch, &n5[0], slot.pts[1].p, pitch, &n5[1], slot.pts[2].p, pitch, &n5[2], slot.pts[3].p, pitch, &n5[3],
+                                 &od, nullptr, nullptr, nullptr, ostats);
+    if (rc != CM_OK) return rc;
+    if (odom) *odom = od;
+    return mapping_process_dev(ctx, (const float4*)b.last_c.p, b.cap_less_sharp, (const float4*)b.last_s.p, b.cap_less_flat, (const int*)b.ints.p + 5,
+                               std::max(n5[1], 1), std::max(n5[3], 1), &od, mapped, mstats, false);
   } catch (const CudaError& e) {
     return fail(ctx, CM_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
