@@ -6,6 +6,10 @@
 // chunk, each chunk's upload starts as soon as it is packed (the copy of chunk c overlaps the packing of chunk c + 1), and a small
 // kernel expands the packed coordinates to the float4 layout scan registration reads.  12 instead of 16 bytes per point cross PCIe.
 #include "cm_ctx.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <string.h>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -90,6 +94,32 @@ void stage_pool_destroy(cm_ctx* ctx) { delete ctx->stage_pool; ctx->stage_pool =
 
 // x, y, z of `count` points, `stride` bytes apart, packed to 12 bytes each
 static void pack_xyz(const unsigned char* src, size_t stride, size_t count, float* dst) {
+#if defined(__SSE2__)
+  // four points per round: four 16-byte loads (x, y, z and the float behind them -- inside the point for every stride >= 16), three
+  // shuffled 16-byte stores; non-temporal when the destination is aligned (the staging buffer is read next by the copy engine, not
+  // by this core: no read-for-ownership, no cache pollution)
+  static const bool simd = getenv("COOPERMAP_STAGE_SCALAR") == nullptr;
+  if (simd && stride >= 16 && count >= 4) {
+    const bool nt = ((uintptr_t)dst & 15) == 0;
+    size_t i = 0;
+    for (; i + 4 <= count; i += 4) {
+      const unsigned char* q = src + i * stride;
+      const __m128 p0 = _mm_loadu_ps(reinterpret_cast<const float*>(q)), p1 = _mm_loadu_ps(reinterpret_cast<const float*>(q + stride));
+      const __m128 p2 = _mm_loadu_ps(reinterpret_cast<const float*>(q + 2 * stride)), p3 = _mm_loadu_ps(reinterpret_cast<const float*>(q + 3 * stride));
+      const __m128 t01 = _mm_shuffle_ps(p0, p1, _MM_SHUFFLE(0, 0, 2, 2));   // z0 z0 x1 x1
+      const __m128 o0 = _mm_shuffle_ps(p0, t01, _MM_SHUFFLE(2, 0, 1, 0));   // x0 y0 z0 x1
+      const __m128 o1 = _mm_shuffle_ps(p1, p2, _MM_SHUFFLE(1, 0, 2, 1));    // y1 z1 x2 y2
+      const __m128 t23 = _mm_shuffle_ps(p2, p3, _MM_SHUFFLE(0, 0, 2, 2));   // z2 z2 x3 x3
+      const __m128 o2 = _mm_shuffle_ps(t23, p3, _MM_SHUFFLE(2, 1, 2, 0));   // z2 x3 y3 z3
+      float* d = dst + 3 * i;
+      if (nt) { _mm_stream_ps(d, o0); _mm_stream_ps(d + 4, o1); _mm_stream_ps(d + 8, o2); }
+      else { _mm_storeu_ps(d, o0); _mm_storeu_ps(d + 4, o1); _mm_storeu_ps(d + 8, o2); }
+    }
+    if (nt) _mm_sfence();
+    for (; i < count; i++) memcpy(dst + 3 * i, src + i * stride, 12);
+    return;
+  }
+#endif
   if (stride == 32 && ((uintptr_t)src & 3) == 0) {   // pcl::PointXYZI: two points per 64-byte line, read 12 of every 32 bytes
     for (size_t i = 0; i < count; i++) {
       const float* p = reinterpret_cast<const float*>(src + i * 32);
