@@ -220,6 +220,7 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
 void launch_match_solve_warp(const MatchLaunch& m, int it, cudaStream_t stream);
 void launch_match_solve(const MatchLaunch& m, int it, const double* sums, cudaStream_t stream);
 void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream);
+void launch_match_reduce_solve(const MatchLaunch& m, int it, cudaStream_t stream, const int* d_iter = nullptr);
 
 // K8: scan-to-scan odometry (cm_odom.inl)
 struct OdomLaunch {

@@ -523,6 +523,10 @@ struct SolveArgs {
 
 // K6a: deterministic reduction of one stream's rows.  One CTA per stream.  Float products are exact in double and
 // are accumulated in double, so any summation order rounds to the same float A^T A as the oracle's.
+__device__ __noinline__ void solve_stream(const SolveArgs& a_in, int s, const double* tot);
+// kSolve: the 6x6 step of the stream right behind its reduction, by warp 0 of the same CTA (the odometry loop: one launch less per
+// evaluation; the sharded-map path keeps them apart, its exchange sits in between)
+template <bool kSolve>
 __global__ void __launch_bounds__(512) reduce_rows_kernel(SolveArgs a, double* __restrict__ sums) {
   const int s = blockIdx.x;
   if (a.state[s].done) return;
@@ -563,6 +567,10 @@ __global__ void __launch_bounds__(512) reduce_rows_kernel(SolveArgs a, double* _
     double v = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += sm[w][threadIdx.x];
     sums[(size_t)s * 32 + threadIdx.x] = v;
+  }
+  if (kSolve) {
+    __syncthreads();   // the sums of this stream are in global memory, visible to the whole CTA
+    if (threadIdx.x < 32) solve_stream(a, s, sums + (size_t)s * 32);
   }
 }
 
@@ -1073,7 +1081,14 @@ void launch_match_partial(const MatchLaunch& m, int it, cudaStream_t stream, Ker
     return;
   }
   CM_LAUNCH(fit_kernel, grid, 256, 0, stream, ca);
-  CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+  CM_LAUNCH(reduce_rows_kernel<false>, m.nstreams, 512, 0, stream, sa, m.sums);
+}
+// reduction + 6x6 step in one launch (it: the evaluation index, or read from d_iter)
+void launch_match_reduce_solve(const MatchLaunch& m, int it, cudaStream_t stream, const int* d_iter) {
+  CorrArgs ca; SolveArgs sa;
+  fill_args(m, ca, sa);
+  sa.iter = it; sa.iter_dev = d_iter;
+  CM_LAUNCH(reduce_rows_kernel<true>, m.nstreams, 512, 0, stream, sa, m.sums);
 }
 
 // solve + pose update + convergence test from the (complete) sums
@@ -1082,7 +1097,7 @@ void launch_match_reduce(const MatchLaunch& m, int it, cudaStream_t stream) {
   CorrArgs ca; SolveArgs sa;
   fill_args(m, ca, sa);
   sa.iter = it;
-  CM_LAUNCH(reduce_rows_kernel, m.nstreams, 512, 0, stream, sa, m.sums);
+  CM_LAUNCH(reduce_rows_kernel<false>, m.nstreams, 512, 0, stream, sa, m.sums);
 }
 
 void launch_match_solve_warp(const MatchLaunch& m, int it, cudaStream_t stream) {
@@ -1297,11 +1312,7 @@ bool OdomGraphCache::launch(const MatchLaunch& m, const OdomBatchLaunch& o, cons
                                 [&]() { launch_match_init(m, stream); launch_odom_gate(m.state, d_active, m.nstreams, stream); },
                                 [&]() {
                                   launch_odom_corr_batch(o, 0, stream, di);
-                                  launch_match_reduce(m, 0, stream);
-                                  CorrArgs ca; SolveArgs sa;
-                                  fill_args(m, ca, sa);
-                                  sa.iter_dev = di;
-                                  CM_LAUNCH(solve_warp_kernel, m.nstreams, 32, 0, stream, sa, (const double*)m.sums);
+                                  launch_match_reduce_solve(m, 0, stream, di);
                                 }, &per_eval);
   if (!e.exec) { usable = false; return false; }
   e.launches = 2 + per_eval;

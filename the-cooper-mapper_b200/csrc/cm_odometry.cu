@@ -255,8 +255,7 @@ int odometry_batch_core(cm_ctx* ctx, const void* sharp, size_t pitch_sharp, cons
         launch_odom_gate(m.state, d_i + 4 * S, S, st);
         for (int it = 0; it < MAXIT; it++) {
           launch_odom_corr_batch(o, it, st);
-          launch_match_reduce(m, it, st);
-          launch_match_solve(m, it, (const double*)m.sums, st);
+          launch_match_reduce_solve(m, it, st);
         }
       }
       CM_CUDA_CHECK(ctx, cudaMemcpyAsync(hs.data(), b.state.p, sizeof(MatchState) * S, cudaMemcpyDeviceToHost, st));
