@@ -42,3 +42,26 @@ def test_math_device_equals_host(ctx, oracle, op):
     dev = ctx.debug_math(op, x)
     host = oracle.debug_math(op, x)
     assert np.array_equal(dev.view(np.uint32), host.view(np.uint32))
+
+
+def test_warp_qr_equals_sequential_qr(ctx, oracle):
+    """warp_qr_solve6 (the column-parallel 6x6 column-pivoted Householder QR of the Gauss-Newton step, one warp per system) against
+    cm_math.h::colpiv_qr_solve<6, 6> on the host: bit for bit, for well-conditioned normal equations and for rank-deficient ones
+    (zero columns, repeated columns, zero matrix, tiny pivots) where the pivot count stops short of 6."""
+    rng = np.random.default_rng(77)
+    x = _inputs(0, 6000, rng)
+    A = x[:, :36].reshape(-1, 6, 6).copy()
+    A[::11, :, 2] = 0.0; A[::11, 2, :] = 0.0                      # a zero column (and row)
+    A[::13, :, 4] = A[::13, :, 1]; A[::13, 4, :] = A[::13, 1, :]  # two equal columns
+    A[::17] = 0.0                                                 # nothing at all
+    A[::19, :, 5] *= 1e-9; A[::19, 5, :] *= 1e-9                  # a pivot below the rank threshold
+    A[5::23] = rng.normal(size=A[5::23].shape).astype(np.float32)  # general (unsymmetric) systems
+    x[:, :36] = A.reshape(-1, 36)
+    dev = ctx.debug_math(8, x)
+    host = oracle.debug_math(0, x)
+    # (a zero matrix divides 0 by 0 in the back substitution, as Eigen does: NaNs in the same places -- their sign bit is the platform's)
+    nan = np.isnan(host)
+    assert np.array_equal(np.isnan(dev), nan)
+    bad = np.where((dev.view(np.uint32) != host.view(np.uint32)) & ~nan)[0]
+    assert len(bad) == 0, (len(bad), sorted(set(bad.tolist()))[:20], dev[bad[:2]], host[bad[:2]])
+    assert np.isfinite(host).mean() > 0.9

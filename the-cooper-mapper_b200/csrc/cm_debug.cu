@@ -4,12 +4,15 @@
 // see the note in colpiv_qr_solve).
 #include "cm_host.h"
 #include "cm_math.h"
+#include "cm_device.cuh"
 
 namespace cm {
 
 // op 0: colpiv_qr_solve<6,6> (36 + 6 -> 6)   1: colpiv_qr_solve<5,3> (15 + 5 -> 3)   2: eig3_sym (6 -> 3 + 9)
 // op 3: eig_sym<6> (36 -> 6 + 36)   4: eig_sym<6> values only (36 -> 6)   5: inverse_lu<6> (36 -> 36)
 // op 6: pose_to_matrix + cm_sincosf (6 -> 9 + 3 + 3)   7: cm_atan2f(y, x), cm_atanf(y / x) (2 -> 2)
+// op 8: warp_qr_solve6 (cm_device.cuh), the column-parallel 6x6 solve of the Gauss-Newton step, one warp per problem (36 + 6 -> 6): must
+//       equal op 0 on the host bit for bit, rank-deficient systems included
 __device__ void debug_math_op(int op, const float* in, float* out) {
   if (op == 0) { float A[36], b[6], x[6]; for (int i = 0; i < 36; i++) A[i] = in[i]; for (int i = 0; i < 6; i++) b[i] = in[36 + i]; colpiv_qr_solve<6, 6>(A, b, x); for (int i = 0; i < 6; i++) out[i] = x[i]; }
   else if (op == 1) { float A[15], b[5], x[3]; for (int i = 0; i < 15; i++) A[i] = in[i]; for (int i = 0; i < 5; i++) b[i] = in[15 + i]; colpiv_qr_solve<5, 3>(A, b, x); for (int i = 0; i < 3; i++) out[i] = x[i]; }
@@ -24,13 +27,24 @@ __global__ void debug_math_kernel(int op, const float* in, int nin, float* out, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) debug_math_op(op, in + (size_t)i * nin, out + (size_t)i * nout);
 }
+__global__ void __launch_bounds__(128) debug_warp_qr_kernel(const float* in, float* out, int n) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float* p = in + (size_t)i * 42;
+  float col[6], X[6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) col[r] = lane < 6 ? p[r * 6 + lane] : (lane == 6 ? p[36 + r] : 0.f);
+  warp_qr_solve6(col, lane, X);
+  if (lane == 0) for (int k = 0; k < 6; k++) out[(size_t)i * 6 + k] = X[k];
+}
 int debug_math_dims(int op, int* nin, int* nout) {
-  static const int ni[8] = {42, 20, 6, 36, 36, 36, 6, 2}, no[8] = {6, 3, 12, 42, 6, 36, 15, 2};
-  if (op < 0 || op > 7) return -1;
+  static const int ni[9] = {42, 20, 6, 36, 36, 36, 6, 2, 42}, no[9] = {6, 3, 12, 42, 6, 36, 15, 2, 6};
+  if (op < 0 || op > 8) return -1;
   *nin = ni[op]; *nout = no[op];
   return 0;
 }
 void launch_debug_math(int op, const float* d_in, int nin, float* d_out, int nout, int n, cudaStream_t stream) {
+  if (op == 8) { CM_LAUNCH(debug_warp_qr_kernel, (n * 32 + 127) / 128, 128, 0, stream, d_in, d_out, n); return; }
   CM_LAUNCH(debug_math_kernel, (n + 63) / 64, 64, 0, stream, op, d_in, nin, d_out, nout, n);
 }
 

@@ -597,127 +597,6 @@ __device__ __noinline__ bool dev_inverse6(const float* A, float* inv) {
   return ok;
 }
 
-// Column-parallel form of cm_math.h::colpiv_qr_solve<6, 6> for one warp: the SAME float operations on the same operands in the same
-// order as the sequential routine the oracle runs (every dot product and norm is still summed row by row inside one lane; -fmad=false),
-// only spread over the lanes: lane c < 6 holds column c of A in a[0..5], lane 6 holds b (the reflectors are applied to it as to a
-// seventh trailing column, step by step, instead of in a second sweep), the other lanes carry zeros.  The pivot scan, the reflector
-// of column k and the back substitution are evaluated redundantly by every lane from shuffled values, so the control flow is
-// uniform.  One lane running the unrolled sequential routine took 35 us per Gauss-Newton iteration (~5,000 dependent instructions,
-// 80 KB of straight-line code fetched once); this form is ~7x shorter.  Every lane returns the whole solution X.
-__device__ __forceinline__ void warp_qr_solve6(float (&a)[6], const int lane, float (&X)[6]) {
-  const unsigned int FULL = 0xffffffffu;
-  float nu, nd;
-  int perm = lane;
-  {
-    float sq = 0.f;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) sq += a[r] * a[r];
-    nd = sqrtf(sq); nu = nd;
-  }
-  float maxnorm = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { const float v = __shfl_sync(FULL, nu, k); if (v > maxnorm) maxnorm = v; }
-  const float te = maxnorm * FLT_EPSILON;
-  const float threshold_helper = (te * te) / 6.0f;
-  const float norm_downdate_threshold = sqrtf(FLT_EPSILON);
-  int nzp = 6;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    int big = k;
-    float bigv = __shfl_sync(FULL, nu, k);
-#pragma unroll
-    for (int j = k + 1; j < 6; ++j) { const float v = __shfl_sync(FULL, nu, j); if (v > bigv) { bigv = v; big = j; } }
-    const float big_sq = bigv * bigv;
-    if (nzp == 6 && big_sq < threshold_helper * (float)(6 - k)) nzp = k;
-    {   // column swap k <-> big (whole columns, with their norms and permutation entry)
-      const int src = lane == k ? big : (lane == big ? k : lane);
-#pragma unroll
-      for (int r = 0; r < 6; ++r) a[r] = __shfl_sync(FULL, a[r], src);
-      nu = __shfl_sync(FULL, nu, src); nd = __shfl_sync(FULL, nd, src); perm = __shfl_sync(FULL, perm, src);
-    }
-    // Householder reflector of column k, rows k..5
-    float ck[6], v[6];
-#pragma unroll
-    for (int r = k; r < 6; ++r) ck[r] = __shfl_sync(FULL, a[r], k);
-    float tailSqNorm = 0.f;
-#pragma unroll
-    for (int r = k + 1; r < 6; ++r) tailSqNorm += ck[r] * ck[r];
-    const float c0 = ck[k];
-    float tau, beta;
-    if (k == 5 || tailSqNorm <= FLT_MIN) {
-      tau = 0.f; beta = c0;
-#pragma unroll
-      for (int r = k + 1; r < 6; ++r) v[r] = 0.f;
-    } else {
-      float bb = sqrtf(c0 * c0 + tailSqNorm);
-      if (c0 >= 0.f) bb = -bb;
-      const float d = c0 - bb;
-#pragma unroll
-      for (int r = k + 1; r < 6; ++r) v[r] = ck[r] / d;
-      tau = (bb - c0) / bb;
-      beta = bb;
-    }
-    if (lane == k) {
-      a[k] = beta;
-#pragma unroll
-      for (int r = k + 1; r < 6; ++r) a[r] = v[r];
-    }
-    // H_k on the trailing columns and on b (b only while k < nonzero_pivots: colpiv_qr_solve's second sweep stops there)
-    if ((lane > k && lane < 6) || (lane == 6 && k < nzp)) {
-      float tmp = a[k];
-#pragma unroll
-      for (int r = k + 1; r < 6; ++r) tmp += v[r] * a[r];
-      a[k] -= tau * tmp;
-#pragma unroll
-      for (int r = k + 1; r < 6; ++r) a[r] -= tau * v[r] * tmp;
-    }
-    if (lane > k && lane < 6 && nu != 0.f) {   // LAPACK-style norm downdate
-      float temp = fabsf(a[k]) / nu;
-      temp = (1.f + temp) * (1.f - temp);
-      temp = temp < 0.f ? 0.f : temp;
-      const float ratio = nu / nd;
-      const float temp2 = temp * (ratio * ratio);
-      if (temp2 <= norm_downdate_threshold) {
-        float sq = 0.f;
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) sq += a[r] * a[r];
-        nd = sqrtf(sq); nu = nd;
-      } else {
-        nu *= sqrtf(temp);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) X[i] = 0.f;
-  if (nzp == 0) return;
-  float bq[6], Rm[6][6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    bq[i] = __shfl_sync(FULL, a[i], 6);
-#pragma unroll
-    for (int j = i; j < 6; ++j) Rm[i][j] = __shfl_sync(FULL, a[i], j);
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    if (i < nzp) {
-      float sb = bq[i];
-#pragma unroll
-      for (int j = i + 1; j < 6; ++j)
-        if (j < nzp) sb -= Rm[i][j] * bq[j];
-      bq[i] = sb / Rm[i][i];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int pi = __shfl_sync(FULL, perm, i);
-    if (i < nzp) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c)
-        if (pi == c) X[c] = bq[i];
-    }
-  }
-}
-
 // true when the smallest eigenvalue of the symmetric 6x6 float matrix A is PROVABLY above `threshold` as the restated Eigen solver
 // would compute it: A - shift I is positive definite (LDL^T in double, every pivot clearly positive) for shift = threshold + 1e-4
 // trace(A).  The float eigen-solver's error is a small multiple of eps_float * ||A|| (<= 1e-5 trace with room to spare), so above the
