@@ -65,3 +65,30 @@ def test_warp_qr_equals_sequential_qr(ctx, oracle):
     bad = np.where((dev.view(np.uint32) != host.view(np.uint32)) & ~nan)[0]
     assert len(bad) == 0, (len(bad), sorted(set(bad.tolist()))[:20], dev[bad[:2]], host[bad[:2]])
     assert np.isfinite(host).mean() > 0.9
+
+
+def test_eigen_solve_skip_never_hides_a_degenerate_system(ctx, oracle):
+    """dev_min_eig_above6 (evaluation 0 skips SelfAdjointEigenSolver when A^T A is provably well-conditioned): whenever it says
+    "skip", the restated Eigen solver's smallest eigenvalue IS at or above the threshold -- over matrices whose smallest eigenvalue
+    sweeps through the threshold (100, and the odometry's 10), near-singular ones, and non-finite ones; and it does skip the
+    clearly well-conditioned ones."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    Q, _ = np.linalg.qr(rng.normal(size=(n, 6, 6)))
+    lam = np.sort(np.exp(rng.uniform(np.log(1e2), np.log(1e7), (n, 6))), axis=1)
+    thr = np.where(np.arange(n) % 2 == 0, 100.0, 10.0)
+    lam[:, 0] = thr * np.exp(rng.normal(0, 0.02, n))                 # smallest eigenvalue within a few per cent of the threshold
+    lam[::5, 0] = thr[::5] * rng.uniform(2.0, 50.0, len(thr[::5]))   # clearly above
+    lam[1::5, 0] = thr[1::5] * rng.uniform(0.0, 0.5, len(thr[1::5])) # clearly below
+    A = np.einsum("nij,nj,nkj->nik", Q, lam, Q).astype(np.float32)
+    A = 0.5 * (A + A.transpose(0, 2, 1))
+    A[7::101, 0, 0] = np.nan; A[9::103] = 0.0; A[11::107, 3, 3] = np.inf
+    x = np.concatenate([A.reshape(n, 36), thr[:, None].astype(np.float32)], 1)
+    skip = ctx.debug_math(9, x)[:, 0] > 0
+    E0 = oracle.debug_math(4, A.reshape(n, 36))[:, 0]
+    assert not np.any(skip & ~(E0 >= thr)), "skipped a system the eigen-solver calls degenerate (or non-finite)"
+    # its margin is 1e-4 trace(A): a system whose smallest eigenvalue clears the threshold by twice that is skipped
+    fin = np.isfinite(A.reshape(n, 36)).all(1) & (np.abs(A.reshape(n, 36)).sum(1) > 0)
+    clear = fin & (E0 > thr + 2e-4 * np.trace(A, axis1=1, axis2=2))
+    assert clear.sum() > 500 and skip[clear].all()
+    assert 0.02 < skip.mean() < 0.8

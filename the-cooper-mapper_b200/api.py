@@ -126,7 +126,7 @@ class Context:
         return int(self.L.cm_launch_count(self.h))
 
     # ---- device self-test of the shared math ------------------------------------------------------------------
-    MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15), 7: (2, 2), 8: (42, 6)}
+    MATH_DIMS = {0: (42, 6), 1: (20, 3), 2: (6, 12), 3: (36, 42), 4: (36, 6), 5: (36, 36), 6: (6, 15), 7: (2, 2), 8: (42, 6), 9: (37, 1)}
 
     def debug_math(self, op, inputs):
         nin, nout = self.MATH_DIMS[op]

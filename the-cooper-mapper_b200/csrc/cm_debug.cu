@@ -21,6 +21,7 @@ __device__ void debug_math_op(int op, const float* in, float* out) {
   else if (op == 4) { float w[6]; eig_sym<6>(in, w, (float*)nullptr); for (int i = 0; i < 6; i++) out[i] = w[i]; }
   else if (op == 5) { float inv[36]; bool ok = inverse_lu<6>(in, inv); for (int i = 0; i < 36; i++) out[i] = ok ? inv[i] : 0.f; }
   else if (op == 7) { out[0] = cm_atan2f(in[0], in[1]); out[1] = cm_atanf(in[0] / in[1]); }
+  else if (op == 9) { out[0] = dev_min_eig_above6(in, in[36]) ? 1.f : 0.f; }   // the eigen-solve skip of evaluation 0: 36 + threshold -> 0 / 1
   else if (op == 6) { float R[9]; pose_to_matrix(in, R); for (int i = 0; i < 9; i++) out[i] = R[i]; for (int i = 0; i < 3; i++) cm_sincosf(in[i], &out[9 + i], &out[12 + i]); }
 }
 __global__ void debug_math_kernel(int op, const float* in, int nin, float* out, int nout, int n) {
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(128) debug_warp_qr_kernel(const float* in, flo
   if (lane == 0) for (int k = 0; k < 6; k++) out[(size_t)i * 6 + k] = X[k];
 }
 int debug_math_dims(int op, int* nin, int* nout) {
-  static const int ni[9] = {42, 20, 6, 36, 36, 36, 6, 2, 42}, no[9] = {6, 3, 12, 42, 6, 36, 15, 2, 6};
-  if (op < 0 || op > 8) return -1;
+  static const int ni[10] = {42, 20, 6, 36, 36, 36, 6, 2, 42, 37}, no[10] = {6, 3, 12, 42, 6, 36, 15, 2, 6, 1};
+  if (op < 0 || op > 9) return -1;
   *nin = ni[op]; *nout = no[op];
   return 0;
 }

@@ -698,4 +698,36 @@ __device__ __forceinline__ void warp_qr_solve6(float (&a)[6], const int lane, fl
 }
 
 
+// true when the smallest eigenvalue of the symmetric 6x6 float matrix A is PROVABLY above `threshold` as the restated Eigen solver
+// would compute it: A - shift I is positive definite (LDL^T in double, every pivot clearly positive) for shift = threshold + 1e-4
+// trace(A).  The float eigen-solver's error is a small multiple of eps_float * ||A|| (<= 1e-5 trace with room to spare), so above the
+// shift its smallest eigenvalue cannot come out below the threshold and the 6x6 eigen-decomposition of evaluation 0 (one lane,
+// ~5,000 dependent instructions, 20 us) is skipped for the usual, well-conditioned frame.  Anything else -- degenerate, borderline,
+// non-finite -- takes the full solve as before.
+static __device__ __noinline__ bool dev_min_eig_above6(const float* A, float threshold) {
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) tr += (double)A[i * 6 + i];
+  if (!(tr > 0.0) || !(tr < 1e300)) return false;
+  const double shift = (double)threshold + 1e-4 * tr, tiny = 1e-9 * tr;
+  double L[36], D[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double d = (double)A[j * 6 + j] - shift;
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+    if (!(d > tiny)) return false;
+    D[j] = d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double v = (double)A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+      L[i * 6 + j] = v / d;
+    }
+  }
+  return true;
+}
+
+
 }  // namespace cm
