@@ -86,3 +86,44 @@ def test_odometry_batch_equals_per_stream_oracle(cmb, oracle, synth):
             moved = max(moved, float(np.linalg.norm(g["t"])))
     assert moved > 0.5
     ctx.close()
+
+
+def test_odometry_ring_walks_on_unsorted_last_clouds(cmb, oracle, synth):
+    """The ring walks of LaserOdometry::scanMatch (:363-398, 427-476) stop at the FIRST point whose ring index is off by more than 2.5 --
+    on a cloud that is not sorted by ring that is an arbitrary place.  The device walks skip whole 32-point chunks through their
+    bounding boxes; they must still stop where the reference stops.  Last clouds in shuffled block order (rings interleaved):
+    poses, iteration counts and projected clouds equal the oracle's literal walk."""
+    sc = synth.make_scene(seed=47, extent=40.0, n_boxes=12, n_poles=10)
+    S, NF = 2, 4
+    ctx = cmb.Context()
+    ctx.odometry_batch_create(S, 4000, 30000, 8000, 30000)
+    oos = [oracle.Odometry() for _ in range(S)]
+    trajs = [synth.trajectory(NF, seed=10 + s, speed=0.2 + 0.1 * s) for s in range(S)]
+    rng = np.random.default_rng(3)
+
+    def shuffle_blocks(c, block):
+        """keep runs of `block` consecutive points together, permute the runs: ring indices go up and down along the cloud"""
+        nb = (len(c) + block - 1) // block
+        order = rng.permutation(nb)
+        return np.concatenate([c[b * block:(b + 1) * block] for b in order]) if nb else c
+
+    for k in range(NF):
+        feats = []
+        for s in range(S):
+            R, t = trajs[s][k]
+            f = oracle.scanreg_organised(synth.simulate_scan(sc, R, t, "VLP-16", seed=700 + 10 * s + k, cols=1000))
+            f = dict(f)
+            f["lessSharp"] = shuffle_blocks(f["lessSharp"], 23 if s == 0 else 150)
+            f["lessFlat"] = shuffle_blocks(f["lessFlat"], 57 if s == 0 else 400)
+            feats.append(f)
+        got = ctx.odometry_batch_process([f["sharp"] for f in feats], [f["lessSharp"] for f in feats], [f["flat"] for f in feats],
+                                         [f["lessFlat"] for f in feats])
+        for s in range(S):
+            f = feats[s]
+            o = oos[s].process(f["sharp"], f["lessSharp"], f["flat"], f["lessFlat"])
+            g = got[s]
+            assert g["iterations"] == o["iterations"], (k, s)
+            assert np.array_equal(g["transform"], o["transform"]), (k, s)
+            assert np.array_equal(g["R"], o["R"]) and np.array_equal(g["t"], o["t"]), (k, s)
+            assert _same(g["corner_last"], o["corner_last"]) and _same(g["surf_last"], o["surf_last"]), (k, s)
+    ctx.close()
