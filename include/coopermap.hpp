@@ -161,6 +161,9 @@ class LaserMapping {
   }
   int lastStatus() const { return stats_.status; }
   const cm_match_stats& stats() const { return stats_; }
+  // process() returns with the pose; the map insertion of that frame finishes behind it.  sync() waits for it and throws what it hit
+  // (map capacity) -- otherwise the next process() reports it
+  void sync() { ctx_.check(cm_mapping_sync(ctx_.get())); }
   // saveMap service (LaserMatcher.cpp:357-394 -> FeatureMap::saveCloudToFiles)
   int saveMap(const std::string& dir) { int n = 0; ctx_.check(cm_map_save_host(ctx_.get(), 0, dir.c_str(), &n)); return n; }
   // /laser_cloud_surround_corner, _surf: FeatureMap::getSurroundFeature (FeatureMap.h:256-265), published at LaserMatcher.cpp:357-394
@@ -229,7 +232,6 @@ class LoamPipeline : public LaserMapping {
   }
   const cm_iso& odometry() const { return odom_; }
   const cm_odom_stats& odometryStats() const { return ostats_; }
-  void sync() { ctx_.check(cm_mapping_sync(ctx_.get())); }
 
  private:
   int rows_, cols_, lidar_ = 0;
