@@ -15,13 +15,14 @@ REF_SO = os.path.join(_HERE, "_ref", "libcm_ref_nanoflann.so")
 
 def build(force=False):
     """Compile liboracle.so / liboracle_fast.so (and oracle/_ref when /root/reference is present)."""
-    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
+    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so", "liboracle_libm.so"))
     if need or (os.path.isdir("/root/reference") and not os.path.exists(REF_SO)):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
 def lib(fast=False):
-    name = "liboracle_fast.so" if fast else "liboracle.so"
+    # fast="libm": the variant built with the reference's libm trigonometry (a measuring instrument, not a parity target)
+    name = "liboracle_libm.so" if fast == "libm" else ("liboracle_fast.so" if fast else "liboracle.so")
     if name in _libs:
         return _libs[name]
     path = os.path.join(_HERE, name)

@@ -64,9 +64,15 @@ CM_HD void cm_sincos_d(double x, double* s, double* c) {
   *s = ss; *c = cc;
 }
 CM_HD void cm_sincosf(float x, float* s, float* c) {
+#if defined(CM_LIBM_TRIG) && !defined(__CUDACC__)
+  // oracle variant liboracle_libm.so only (tests/test_parity_lapack_cpu.py): the reference's own calls, libm float sin / cos -- used to
+  // bound what the canonical definition below changes at the pose level
+  *s = sinf(x); *c = cosf(x);
+#else
   double sd, cd;
   cm_sincos_d((double)x, &sd, &cd);
   *s = (float)sd; *c = (float)cd;
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -110,10 +116,16 @@ CM_HD double cm_atan_pos_d(double x) {   // x >= 0 (or NaN) -> atan(x) in [0, pi
   return inv ? (pio2_hi - a) + pio2_lo : a;
 }
 CM_HD float cm_atanf(float x) {
+#if defined(CM_LIBM_TRIG) && !defined(__CUDACC__)
+  return atanf(x);   // (oracle variant liboracle_libm.so only, see cm_sincosf)
+#endif
   const double a = cm_atan_pos_d(fabs((double)x));
   return (float)copysign(a, (double)x);
 }
 CM_HD float cm_atan2f(float y, float x) {   // finite arguments or NaN (the front end drops non-finite points before it gets here)
+#if defined(CM_LIBM_TRIG) && !defined(__CUDACC__)
+  return atan2f(y, x);
+#endif
   const double pi_hi = 3.14159265358979312e+00, pi_lo = 1.22464679914735321e-16;
   const double pio2_hi = 1.57079632679489656e+00, pio2_lo = 6.12323399573676604e-17;
   const double ax = fabs((double)x), ay = fabs((double)y);
