@@ -36,9 +36,21 @@ def test_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--pool", "2"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
+    assert len(r.stdout.strip().splitlines()) == 1            # stdout carries the JSON line and nothing else
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "lidar_points_registered_per_s" and line["unit"] == "points/s"
     assert line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_stdout_is_reserved_for_the_result_line():
+    """claim_stdout(): whatever a library writes to file descriptor 1 during the run (NCCL prints its version banner there when
+    torch.distributed creates the communicator) ends up on stderr; emit() still reaches the real stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'banner from a library\\n'); "
+            "print('a stray print'); bench.emit({'metric': 'x', 'value': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines() == ['{"metric": "x", "value": 1}']
+    assert "banner from a library" in r.stderr and "a stray print" in r.stderr
